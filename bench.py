@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — 3D Poisson CSC assembly throughput (nonzeros/s) on 1..8 B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 128]
+
+One "step" = one numeric assembly (GT.update_matrix!/update_vector! analogue, problems.jl:276-285,
+352-361) of the 3D Q1 Poisson matrix AND right-hand side on BASELINE config 2 (128^3 hex cells,
+full Dirichlet boundary, Float64/Int32): geometry, quadrature, element matrices, deterministic
+scatter into CSC nzval and b.  The sparsity pattern (symbolic phase) is built once before the
+timed region and reported separately as `symbolic_ms`.
+
+  value     whole-job nnz/s with every input resident in HBM (CUDA events, max over ranks)
+  e2e       the same metric through the public C ABI with HOST buffers: per step the node
+            coordinates go host->device from pinned memory and nzval + b come back
+  roofline  algorithmic bytes of the step / device time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline   the C restatement of the reference's CPU path (oracle/, "port") on this box
+
+N > 1: one process per GPU (torchrun), the mesh is a stack of N z-slabs of 128^3 cells each
+(weak scaling); every rank assembles its slab, ghost-row contributions of the slab interfaces
+are summed into their owner over NCCL (send/recv between z-neighbours) inside the timed step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "3D Poisson Q1 CSC matrix+RHS assembly throughput (128^3 cells per GPU, numeric re-assembly)"
+UNIT = "nnz/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(n, rank=0, world=1):
+    """Config 2 inputs.  world>1: this rank's z-slab of the n x n x (n*world) mesh."""
+    import gtk_b200
+    H = gtk_b200.hostprep
+    if world == 1:
+        mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (n, n, n))
+        V = H.lagrange_space(mesh, 1, "boundary")
+        part = None
+    else:
+        from galerkintoolkit_jl_b200 import partition as P
+        part = P.slab_problem((0, 1, 0, 1, 0, float(world)), (n, n, n * world), rank, world)
+        mesh, V = part.mesh, part.space
+    tab = H.measure_tabulation(V, 2)
+    return mesh, V, tab, part
+
+
+def algorithmic_bytes(mesh, V, nnz, n_rows):
+    """BASELINE.md §3 / SURVEY.md §8d for a numeric-only step: coordinates + cell->nodes + cell->dofs read once,
+    nzval and b written once (rowval/colptr are written once by the symbolic phase, outside the timed step)."""
+    return 8 * mesh.D * mesh.n_nodes + 4 * mesh.n_lnodes * mesh.n_cells + 4 * V.n_ldofs * mesh.n_cells + 8 * nnz + 8 * n_rows
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (C port in oracle/; the Julia package cannot run here)
+    on the host cores, same metric.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import c_oracle
+    import gtk_b200
+    H = gtk_b200.hostprep
+    threads = os.cpu_count() or 1
+
+    def one(n, nthreads):
+        mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (n, n, n))
+        V = H.lagrange_space(mesh, 1, "boundary")
+        tab = H.measure_tabulation(V, 2)
+        tabd = dict(w=tab.w, N=tab.N, dN=tab.dN, M=tab.M, dM=tab.dM)
+        t = time.perf_counter()
+        out = c_oracle.assemble(1, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, tabd, nthreads=nthreads)
+        return time.perf_counter() - t, out[1].size, out[4]
+
+    t32, _, _ = one(32, threads)
+    est = lambda n: t32 * (n / 32.0) ** 3
+    budget = 150.0
+    n = next((m for m in (128, 96, 64, 48, 32) if (args.steps + args.warmup) * est(m) <= budget), 32)
+    for _ in range(args.warmup):
+        one(n, threads)
+    times, nnz, phases = [], 0, None
+    for _ in range(args.steps):
+        dt, nnz, phases = one(n, threads)
+        times.append(dt)
+    total = sum(times)
+    value = nnz * args.steps / total
+    sample = (f"{n}^3-cell Q1 Poisson matrix+RHS per step (count + cell loop + COO->CSC compress), "
+              f"cell loop on {threads} pthreads, compress serial; phases(s) count/loop/compress/vector="
+              f"{[round(float(x), 3) for x in phases]}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D Poisson Q1 hex {n}^3 cells (bounded sample of config 2: 128^3), Float64/Int32, CPU",
+                       "cells": n ** 3},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(n_full):
+    """Timed C-oracle run on this box's host cores, bounded to ~10-30 s (rank 0, N=1 only)."""
+    import c_oracle
+    import gtk_b200
+    H = gtk_b200.hostprep
+    threads = os.cpu_count() or 1
+
+    def one(n):
+        mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (n, n, n))
+        V = H.lagrange_space(mesh, 1, "boundary")
+        tab = H.measure_tabulation(V, 2)
+        tabd = dict(w=tab.w, N=tab.N, dN=tab.dN, M=tab.M, dM=tab.dM)
+        t = time.perf_counter()
+        out = c_oracle.assemble(1, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, tabd, nthreads=threads)
+        return time.perf_counter() - t, out[1].size
+
+    t32, _ = one(32)
+    n = next((m for m in (n_full, 96, 64, 48, 32) if m <= n_full and t32 * (m / 32.0) ** 3 <= 30.0), 32)
+    dt, nnz = one(n)
+    return {"value": nnz / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"one full assembly (count + cell loop + COO->CSC + RHS) of {n}^3 cells, {dt:.2f} s; cell loop on "
+                      f"{threads} pthreads, compress serial (the reference itself is single-threaded Julia)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="cells per direction per GPU (128 = BASELINE config 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import gtk_b200
+    E = gtk_b200.engine
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA GPU (the engine has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.n
+    mesh, V, tab, part = build_problem(n, rank, world)
+    eng = E.Engine(local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_mesh(mesh.node_coordinates, mesh.cell_nodes)
+    eng.set_space(V.cell_dofs, V.n_free, V.n_dirichlet)
+    eng.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nnz_local = eng.matrix_symbolic()
+    eng.vector_symbolic()
+    torch.cuda.synchronize()
+    symbolic_ms = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        uid = [E.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(rank, world, uid[0])
+        eng.comm_setup_ghost_rows(part.own_lo, part.own_hi)
+        nnz_owned = int(eng.lib.gtk_comm_ghost_info(eng.h, 3))
+    else:
+        nnz_owned = nnz_local
+    mp = dict(alpha=1.0)
+    vp = dict(f_const=[1.0])
+
+    def step():
+        eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
+        if world > 1:
+            eng.comm_sum_ghost_rows()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    launches_per_step = eng.info(0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        tn = torch.tensor([nnz_owned], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tn)
+        nnz_total = int(tn.item())
+    else:
+        nnz_total = nnz_owned
+    ms_per_step = ms_total / args.steps
+    value = nnz_total / (ms_per_step * 1e-3)
+
+    # per-kernel device times (events inside the lib around every launch), separate short loop
+    eng.set_profiling(True)
+    acc = {}
+    for _ in range(5):
+        step()
+        torch.cuda.synchronize()
+        for name, ms in eng.profile():
+            acc.setdefault(name, []).append(ms)
+    eng.set_profiling(False)
+    kernels = {k: float(np.mean(v)) for k, v in acc.items()}
+    dominant = max(kernels, key=kernels.get) if kernels else None
+
+    # end to end through the C ABI with pinned host buffers
+    xyz_pin = torch.from_numpy(mesh.node_coordinates).pin_memory()
+    nz_pin = torch.empty(nnz_local, dtype=torch.float64).pin_memory()
+    b_pin = torch.empty(V.n_free, dtype=torch.float64).pin_memory()
+    xyz_np, nz_np, b_np = xyz_pin.numpy(), nz_pin.numpy(), b_pin.numpy()
+
+    def e2e_step():
+        eng.update_coordinates(xyz_np)                                # H2D
+        eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
+        if world > 1:
+            eng.comm_sum_ghost_rows()
+        eng.copy_nzval(nz_np)                                         # D2H
+        eng.copy_vector(b_np)                                         # D2H
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    checksum = float(nz_np.sum() + b_np.sum())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        alg = algorithmic_bytes(mesh, V, nnz_local, V.n_free)
+        step_dev_ms = ms_per_step
+        achieved = alg / (step_dev_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 2: 3D Poisson Q1 hex {n}^3 cells per GPU, full Dirichlet boundary, "
+                                   f"Float64/Int32, matrix+RHS numeric assembly on a cached pattern",
+                       "cells_per_gpu": n ** 3, "nnz_per_gpu": nnz_local, "free_dofs_per_gpu": V.n_free,
+                       "partition": "none" if world == 1 else f"{world} z-slabs, NCCL ghost-row sum",
+                       "l2": "per-step traffic (>0.6 GB) exceeds the 126 MB L2; no explicit flush",
+                       "fast_path": eng.info(5)},
+            "symbolic_ms": symbolic_ms,
+            "dofs_per_s": (V.n_free * world) / (ms_per_step * 1e-3),
+            "e2e": {"value": nnz_total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(xyz_np.nbytes),
+                    "d2h_bytes_per_step": int(nz_np.nbytes + b_np.nbytes), "ms_per_step": 1e3 * e2e_s, "checksum": checksum},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                         "bytes_per_nnz": alg / max(nnz_local, 1), "kernel": dominant,
+                         "kernels_ms": kernels, "basis": "whole step device time (all kernels of the step)"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(n)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,296 @@
+// C ABI of libgtkasm (include/gtk_assembly.h): argument checks, HBM residency of the inputs,
+// dispatch to symbolic.cu / numeric.cu / fastq1.cu / comm.cu.  No CPU compute path exists here:
+// every numeric entry point launches CUDA kernels or returns an error.
+#include <cstring>
+#include "gtk_internal.h"
+
+int32_t gtk_dev_alloc(gtk_ctx* ctx, void** p, size_t bytes) {
+  *p = nullptr;
+  GTK_CK(cudaMalloc(p, bytes ? bytes : 1));
+  ctx->bytes_held += (int64_t)bytes;
+  return GTK_OK;
+}
+
+void gtk_dev_free(gtk_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  cudaFree(p);
+  ctx->bytes_held -= (int64_t)bytes;
+}
+
+void gtk_fastq1_release(gtk_ctx* ctx);
+void gtk_comm_release(gtk_ctx* ctx);
+
+namespace {
+template <class T>
+int32_t upload(gtk_ctx* ctx, T** dst, size_t* old_n, const T* src, size_t n) {
+  if (*dst && *old_n != n) { gtk_dev_free(ctx, *dst, *old_n * sizeof(T)); *dst = nullptr; }
+  if (!*dst) {
+    int32_t rc = gtk_dev_alloc(ctx, (void**)dst, n * sizeof(T));
+    if (rc) return rc;
+  }
+  *old_n = n;
+  if (n) GTK_CK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return GTK_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t gtk_version(void) { return 100; }
+
+int32_t gtk_create(int32_t device, gtk_ctx** out) {
+  if (!out) return GTK_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return GTK_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return GTK_ERR_CUDA;
+  gtk_ctx* ctx = new gtk_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return GTK_ERR_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = ctx;
+  return GTK_OK;
+}
+
+int32_t gtk_destroy(gtk_ctx* ctx) {
+  if (!ctx) return GTK_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  gtk_comm_release(ctx);
+  gtk_fastq1_release(ctx);
+  gtk_matsym_release(ctx);
+  gtk_vecsym_release(ctx);
+  cudaFree(ctx->xyz); cudaFree(ctx->cell_nodes); cudaFree(ctx->cell_dofs);
+  cudaFree(ctx->w); cudaFree(ctx->N); cudaFree(ctx->dN); cudaFree(ctx->M); cudaFree(ctx->dM);
+  cudaFree(ctx->KE); cudaFree(ctx->BE); cudaFree(ctx->nzval); cudaFree(ctx->bvec); cudaFree(ctx->f_dev);
+  delete ctx;
+  return GTK_OK;
+}
+
+const char* gtk_last_error(const gtk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t gtk_set_stream(gtk_ctx* ctx, void* s) {
+  if (!ctx) return GTK_ERR_INVALID;
+  ctx->stream = (cudaStream_t)s;
+  return GTK_OK;
+}
+
+int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz, int64_t n_cells,
+                     int32_t n_lnodes, const int32_t* cell_nodes) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (D < 1 || D > 3 || n_nodes < 0 || n_cells < 0 || n_lnodes < 1 || (!xyz && n_nodes) || (!cell_nodes && n_cells))
+    GTK_FAIL(GTK_ERR_INVALID, "gtk_set_mesh: bad arguments");
+  GTK_CK(cudaSetDevice(ctx->device));
+  auto& sz = ctx->sz;
+  ctx->D = D; ctx->n_nodes = n_nodes; ctx->n_cells = n_cells; ctx->nln = n_lnodes;
+  int32_t rc = upload(ctx, &ctx->xyz, &sz.xyz, xyz, (size_t)n_nodes * D);
+  if (rc) return rc;
+  rc = upload(ctx, &ctx->cell_nodes, &sz.cell_nodes, cell_nodes, (size_t)n_cells * n_lnodes);
+  if (rc) return rc;
+  gtk_matsym_release(ctx); gtk_vecsym_release(ctx); gtk_fastq1_release(ctx);
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_update_coordinates(gtk_ctx* ctx, const double* xyz) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (!ctx->xyz || !xyz) GTK_FAIL(GTK_ERR_STATE, "gtk_update_coordinates: set the mesh first");
+  GTK_CK(cudaSetDevice(ctx->device));
+  GTK_CK(cudaMemcpyAsync(ctx->xyz, xyz, sizeof(double) * (size_t)ctx->n_nodes * ctx->D, cudaMemcpyHostToDevice, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_set_space(gtk_ctx* ctx, int32_t n_ldofs, int32_t n_comp, const int32_t* cell_dofs,
+                      int64_t n_free, int64_t n_dirichlet) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (n_ldofs < 1 || n_comp < 1 || n_comp > 3 || n_ldofs % n_comp || n_free < 0 || n_dirichlet < 0 ||
+      (!cell_dofs && ctx->n_cells))
+    GTK_FAIL(GTK_ERR_INVALID, "gtk_set_space: bad arguments");
+  if (n_free >= 0x7FFFFFFFll || n_dirichlet >= 0x7FFFFFFFll)
+    GTK_FAIL(GTK_ERR_TOO_LARGE, "dof ids are Int32 on this ABI");
+  GTK_CK(cudaSetDevice(ctx->device));
+  auto& sz = ctx->sz;
+  ctx->nld = n_ldofs; ctx->ncomp = n_comp; ctx->nls = n_ldofs / n_comp;
+  ctx->n_free = n_free; ctx->n_diri = n_dirichlet;
+  int32_t rc = upload(ctx, &ctx->cell_dofs, &sz.cell_dofs, cell_dofs, (size_t)ctx->n_cells * n_ldofs);
+  if (rc) return rc;
+  gtk_matsym_release(ctx); gtk_vecsym_release(ctx); gtk_fastq1_release(ctx);
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_set_tabulation(gtk_ctx* ctx, int32_t n_q, const double* w, const double* N, const double* dN,
+                           const double* M, const double* dM) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (n_q < 1 || !w || !N || !dN || !M || !dM) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_tabulation: bad arguments");
+  if (!ctx->D || !ctx->nls) GTK_FAIL(GTK_ERR_STATE, "gtk_set_tabulation: set mesh and space first");
+  GTK_CK(cudaSetDevice(ctx->device));
+  auto& sz = ctx->sz;
+  ctx->nq = n_q;
+  const int D = ctx->D;
+  size_t nN = (size_t)n_q * ctx->nls, nM = (size_t)n_q * ctx->nln;
+  ctx->h_w.assign(w, w + n_q);
+  ctx->h_N.assign(N, N + nN);
+  ctx->h_dN.assign(dN, dN + nN * D);
+  ctx->h_M.assign(M, M + nM);
+  ctx->h_dM.assign(dM, dM + nM * D);
+  int32_t rc;
+  if ((rc = upload(ctx, &ctx->w, &sz.w, w, (size_t)n_q))) return rc;
+  if ((rc = upload(ctx, &ctx->N, &sz.N, N, nN))) return rc;
+  if ((rc = upload(ctx, &ctx->dN, &sz.dN, dN, nN * D))) return rc;
+  if ((rc = upload(ctx, &ctx->M, &sz.M, M, nM))) return rc;
+  if ((rc = upload(ctx, &ctx->dM, &sz.dM, dM, nM * D))) return rc;
+  gtk_fastq1_release(ctx);
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_matrix_symbolic(gtk_ctx* ctx, int32_t rfd, int32_t cfd, int64_t* nnz_out) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if ((rfd != GTK_FREE && rfd != GTK_DIRICHLET) || (cfd != GTK_FREE && cfd != GTK_DIRICHLET))
+    GTK_FAIL(GTK_ERR_INVALID, "free_or_dirichlet must be GTK_FREE or GTK_DIRICHLET");
+  if (!ctx->cell_dofs) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_symbolic: set mesh and space first");
+  GTK_CK(cudaSetDevice(ctx->device));
+  gtk_fastq1_release(ctx);
+  int32_t rc = gtk_symbolic_matrix_impl(ctx, rfd, cfd);
+  if (rc) return rc;
+  if (nnz_out) *nnz_out = ctx->ms.nnz;
+  return GTK_OK;
+}
+
+int32_t gtk_matrix_pattern(gtk_ctx* ctx, int32_t* colptr, int32_t* rowval) {
+  if (!ctx) return GTK_ERR_INVALID;
+  MatSym& m = ctx->ms;
+  if (!m.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_pattern: no symbolic result");
+  if (m.nnz >= 0x7FFFFFFFll) GTK_FAIL(GTK_ERR_TOO_LARGE, "nnz does not fit the Int32 colptr of SparseMatrixCSC{Float64,Int32}");
+  GTK_CK(cudaSetDevice(ctx->device));
+  if (colptr) {
+    std::vector<int64_t> cp((size_t)m.n_cols + 1);
+    GTK_CK(cudaMemcpyAsync(cp.data(), m.colptr, sizeof(int64_t) * cp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    GTK_CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < cp.size(); ++i) colptr[i] = (int32_t)(cp[i] + 1);
+  }
+  if (rowval && m.nnz) {
+    GTK_CK(cudaMemcpyAsync(rowval, m.rowval, sizeof(int32_t) * (size_t)m.nnz, cudaMemcpyDeviceToHost, ctx->stream));
+    GTK_CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return GTK_OK;
+}
+
+int32_t gtk_matrix_numeric_device(gtk_ctx* ctx, int32_t form, const gtk_form_params* p) {
+  if (!ctx) return GTK_ERR_INVALID;
+  GTK_CK(cudaSetDevice(ctx->device));
+  return gtk_numeric_matrix_impl(ctx, form, p);
+}
+
+int32_t gtk_copy_nzval(gtk_ctx* ctx, double* nzval) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (!ctx->ms.ready || !ctx->nzval) GTK_FAIL(GTK_ERR_STATE, "no assembled matrix");
+  if (ctx->ms.nnz && nzval)
+    GTK_CK(cudaMemcpyAsync(nzval, ctx->nzval, sizeof(double) * (size_t)ctx->ms.nnz, cudaMemcpyDeviceToHost, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_copy_vector(gtk_ctx* ctx, double* b) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (!ctx->vs.ready || !ctx->bvec) GTK_FAIL(GTK_ERR_STATE, "no assembled vector");
+  if (ctx->vs.n_rows && b)
+    GTK_CK(cudaMemcpyAsync(b, ctx->bvec, sizeof(double) * (size_t)ctx->vs.n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_matrix_numeric(gtk_ctx* ctx, int32_t form, const gtk_form_params* p, double* nzval) {
+  int32_t rc = gtk_matrix_numeric_device(ctx, form, p);
+  if (rc) return rc;
+  return gtk_copy_nzval(ctx, nzval);
+}
+
+int32_t gtk_vector_symbolic(gtk_ctx* ctx, int32_t fd) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (fd != GTK_FREE && fd != GTK_DIRICHLET) GTK_FAIL(GTK_ERR_INVALID, "free_or_dirichlet must be GTK_FREE or GTK_DIRICHLET");
+  if (!ctx->cell_dofs) GTK_FAIL(GTK_ERR_STATE, "gtk_vector_symbolic: set mesh and space first");
+  GTK_CK(cudaSetDevice(ctx->device));
+  return gtk_symbolic_vector_impl(ctx, fd);
+}
+
+int32_t gtk_vector_assemble_device(gtk_ctx* ctx, int32_t form, const gtk_form_params* p) {
+  if (!ctx) return GTK_ERR_INVALID;
+  GTK_CK(cudaSetDevice(ctx->device));
+  return gtk_numeric_vector_impl(ctx, form, p);
+}
+
+int32_t gtk_vector_assemble(gtk_ctx* ctx, int32_t form, const gtk_form_params* p, double* b) {
+  int32_t rc = gtk_vector_assemble_device(ctx, form, p);
+  if (rc) return rc;
+  return gtk_copy_vector(ctx, b);
+}
+
+int32_t gtk_assemble_matrix_and_vector_device(gtk_ctx* ctx, int32_t mform, const gtk_form_params* pm,
+                                              int32_t vform, const gtk_form_params* pv) {
+  if (!ctx) return GTK_ERR_INVALID;
+  GTK_CK(cudaSetDevice(ctx->device));
+  return gtk_numeric_both_impl(ctx, mform, pm, vform, pv);
+}
+
+int32_t gtk_assemble_matrix_and_vector(gtk_ctx* ctx, int32_t mform, const gtk_form_params* pm, int32_t vform,
+                                       const gtk_form_params* pv, double* nzval, double* b) {
+  int32_t rc = gtk_assemble_matrix_and_vector_device(ctx, mform, pm, vform, pv);
+  if (rc) return rc;
+  if (ctx->ms.nnz && nzval)
+    GTK_CK(cudaMemcpyAsync(nzval, ctx->nzval, sizeof(double) * (size_t)ctx->ms.nnz, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->vs.n_rows && b)
+    GTK_CK(cudaMemcpyAsync(b, ctx->bvec, sizeof(double) * (size_t)ctx->vs.n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_device_pointer(gtk_ctx* ctx, int32_t which, void** dptr, int64_t* count) {
+  if (!ctx || !dptr) return GTK_ERR_INVALID;
+  switch (which) {
+    case 0: *dptr = ctx->nzval; if (count) *count = ctx->ms.nnz; break;
+    case 1: *dptr = ctx->bvec; if (count) *count = ctx->vs.n_rows; break;
+    case 2: *dptr = ctx->ms.colptr; if (count) *count = ctx->ms.n_cols + 1; break;
+    case 3: *dptr = ctx->ms.rowval; if (count) *count = ctx->ms.nnz; break;
+    default: GTK_FAIL(GTK_ERR_INVALID, "gtk_device_pointer: unknown selector");
+  }
+  return GTK_OK;
+}
+
+int32_t gtk_set_profiling(gtk_ctx* ctx, int32_t on) {
+  if (!ctx) return GTK_ERR_INVALID;
+  ctx->profiling = on != 0;
+  return GTK_OK;
+}
+
+int32_t gtk_profile_count(const gtk_ctx* ctx) { return ctx ? (int32_t)ctx->prof.size() : 0; }
+
+int32_t gtk_profile_get(gtk_ctx* ctx, int32_t i, char* name64, double* ms) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (i < 0 || i >= (int32_t)ctx->prof.size()) GTK_FAIL(GTK_ERR_INVALID, "gtk_profile_get: index out of range");
+  GTK_CK(cudaEventSynchronize(ctx->prof[i].b));
+  float f = 0.f;
+  GTK_CK(cudaEventElapsedTime(&f, ctx->prof[i].a, ctx->prof[i].b));
+  if (ms) *ms = (double)f;
+  if (name64) { strncpy(name64, ctx->prof[i].name, 63); name64[63] = 0; }
+  return GTK_OK;
+}
+
+int64_t gtk_info(const gtk_ctx* ctx, int32_t key) {
+  if (!ctx) return -1;
+  switch (key) {
+    case 0: return ctx->launches_last;
+    case 1: return ctx->launches_total;
+    case 2: return ctx->bytes_held;
+    case 3: return ctx->ms.nnz;
+    case 4: return ctx->ms.n_valid;
+    case 5: return ctx->fast_path_last;
+    default: return -1;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// Internal engine state (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/gtk_assembly.h"
+
+#define GTK_CK(call)                                                                      \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ +   \
+                 ":" + std::to_string(__LINE__) + ")";                                    \
+      return GTK_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define GTK_FAIL(code, msg) \
+  do {                      \
+    ctx->err = (msg);       \
+    return (code);          \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;  // elements allocated
+};
+
+// Sparse-pattern + assembly plan of one (rows, cols) selection.
+struct MatSym {
+  bool ready = false;
+  int rows_fd = GTK_FREE, cols_fd = GTK_FREE;
+  int64_t n_rows = 0, n_cols = 0;
+  int64_t n_full = 0;    // n_cells * n_ldofs^2  (COO slots incl. skipped ones)
+  int64_t n_valid = 0;   // N_coo: triplets the reference would push (assembly.jl:545-556)
+  int64_t nnz = 0;
+  int64_t* colptr = nullptr;   // [n_cols+1], 0-based, device
+  int32_t* rowval = nullptr;   // [nnz], 1-based, device
+  uint32_t* perm = nullptr;    // [n_valid] sorted position -> COO slot e = cell*nld^2 + c*nld + r
+  uint32_t* nzptr = nullptr;   // [nnz+1]  first sorted position of every stored nonzero
+  // Q1-hex structured fast path ("tile plan"), see plan.cu
+  void* plan = nullptr;
+};
+
+struct VecSym {
+  bool ready = false;
+  int fd = GTK_FREE;
+  int64_t n_rows = 0;
+  int64_t n_full = 0;   // n_cells * n_ldofs
+  int64_t n_valid = 0;
+  int64_t n_urows = 0;  // rows that receive at least one contribution
+  uint32_t* perm = nullptr;    // [n_valid] sorted position -> e = cell*nld + i
+  uint32_t* rowptr = nullptr;  // [n_urows+1]
+  int32_t* urow = nullptr;     // [n_urows] 0-based row id
+};
+
+struct gtk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+
+  // mesh
+  int D = 0, nln = 0;
+  int64_t n_nodes = 0, n_cells = 0;
+  double* xyz = nullptr;
+  int32_t* cell_nodes = nullptr;
+  // space
+  int nld = 0, ncomp = 1, nls = 0;
+  int64_t n_free = 0, n_diri = 0;
+  int32_t* cell_dofs = nullptr;
+  // tabulation (device + host copies)
+  int nq = 0;
+  double *w = nullptr, *N = nullptr, *dN = nullptr, *M = nullptr, *dM = nullptr;
+  std::vector<double> h_w, h_N, h_dN, h_M, h_dM;
+
+  MatSym ms;
+  VecSym vs;
+  // staging / results
+  double* KE = nullptr;  size_t KE_cap = 0;   // [n_cells][nld][nld] element matrices, e-indexed
+  double* BE = nullptr;  size_t BE_cap = 0;   // [n_cells][nld]
+  double* nzval = nullptr; size_t nzval_cap = 0;
+  double* bvec = nullptr;  size_t bvec_cap = 0;
+  double* f_dev = nullptr; size_t f_cap = 0;  // uploaded f_nodal / f_qp
+
+  struct { size_t xyz = 0, cell_nodes = 0, cell_dofs = 0, w = 0, N = 0, dN = 0, M = 0, dM = 0; } sz;  // uploaded element counts
+
+  int64_t launches_last = 0, launches_total = 0;
+  int64_t bytes_held = 0;
+  int fast_path_last = 0;
+
+  // per-kernel profiling (events around each launch of the last numeric call)
+  bool profiling = false;
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;       // records of the last numeric call
+  std::vector<ProfRec> prof_pool;  // reusable events
+
+  // multi-GPU
+  void* comm = nullptr;   // ncclComm_t
+  int rank = 0, n_ranks = 1;
+  void* ghost = nullptr;  // GhostPlan*
+};
+
+// ---- helpers implemented in gtk_api.cu ----
+int32_t gtk_dev_alloc(gtk_ctx* ctx, void** p, size_t bytes);
+void gtk_dev_free(gtk_ctx* ctx, void* p, size_t bytes);
+template <class T>
+inline int32_t gtk_alloc(gtk_ctx* ctx, T** p, size_t n) {
+  return gtk_dev_alloc(ctx, reinterpret_cast<void**>(p), n * sizeof(T));
+}
+template <class T>
+inline void gtk_free(gtk_ctx* ctx, T*& p, size_t n) {
+  if (p) gtk_dev_free(ctx, p, n * sizeof(T));
+  p = nullptr;
+}
+inline void gtk_count_launch(gtk_ctx* ctx, int n = 1) {
+  ctx->launches_last += n;
+  ctx->launches_total += n;
+}
+// Brackets one kernel launch with events when profiling is on:  { GtkProf p(ctx, "name"); kernel<<<>>>(); }
+struct GtkProf {
+  gtk_ctx* ctx; int idx = -1;
+  GtkProf(gtk_ctx* c, const char* name) : ctx(c) {
+    if (!c->profiling) return;
+    gtk_ctx::ProfRec r;
+    if (!c->prof_pool.empty()) { r = c->prof_pool.back(); c->prof_pool.pop_back(); }
+    else { cudaEventCreate(&r.a); cudaEventCreate(&r.b); }
+    r.name = name;
+    cudaEventRecord(r.a, c->stream);
+    c->prof.push_back(r);
+    idx = (int)c->prof.size() - 1;
+  }
+  ~GtkProf() { if (idx >= 0) cudaEventRecord(ctx->prof[idx].b, ctx->stream); }
+};
+inline void gtk_prof_reset(gtk_ctx* ctx) {
+  for (auto& r : ctx->prof) ctx->prof_pool.push_back(r);
+  ctx->prof.clear();
+}
+
+// ---- symbolic.cu ----
+int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd);
+int32_t gtk_symbolic_vector_impl(gtk_ctx* ctx, int fd);
+void gtk_matsym_release(gtk_ctx* ctx);
+void gtk_vecsym_release(gtk_ctx* ctx);
+
+// ---- numeric.cu ----
+int32_t gtk_numeric_matrix_impl(gtk_ctx* ctx, int form, const gtk_form_params* p);
+int32_t gtk_numeric_vector_impl(gtk_ctx* ctx, int form, const gtk_form_params* p);
+int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
+                              const gtk_form_params* pv);

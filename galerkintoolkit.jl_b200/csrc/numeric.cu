@@ -1,0 +1,407 @@
+// Numeric phase, generic path: any Lagrange element the host tabulates.
+//
+//   k_elem_matrix / k_elem_vector : the generated cell loop (compiler.jl:1865-1917, 1958-1990)
+//       with the per-point arithmetic of accessors.jl (J :941-968, dV :1000-1007 +
+//       quadrature.jl:4-6, ∇N = Jᵀ\∇̂N :1365-1368), two phases per CTA through shared memory:
+//       A) one thread per (cell, point): geometry + physical gradients -> smem
+//       B) one thread per element-matrix entry: Σ_q integrand·dV in the reference's q order,
+//          written to the e-indexed staging array (coalesced, 8 B/thread consecutive).
+//   k_reduce_nz / k_reduce_rows   : compress (assembly.jl:571-588): fixed-order segmented sum of
+//       duplicates in reference push order (no atomics; bit-reproducible).
+//
+// The structured Q1 fast path lives in fastq1.cu and is tried first.
+#include "gtk_internal.h"
+
+int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
+                       const gtk_form_params* pv, bool* handled);
+
+namespace {
+
+struct ElemArgs {
+  const double* xyz;
+  const int32_t* cell_nodes;
+  int64_t n_cells;
+  int nln, nls, ncomp, nld, nq;
+  const double *w, *N, *dN, *M, *dM;
+  int form;
+  double alpha, lambda, mu;
+  double f_const[3];
+  const double* f_ptr;
+  double* out;
+  int cb;
+};
+
+template <int D>
+__device__ __forceinline__ double det_mat(const double (&a)[D][D]) {
+  if constexpr (D == 1) return a[0][0];
+  if constexpr (D == 2) return a[0][0] * a[1][1] - a[0][1] * a[1][0];
+  if constexpr (D == 3) {
+    // StaticArrays: x0 . (x1 × x2) over columns
+    double c0 = a[1][1] * a[2][2] - a[2][1] * a[1][2];
+    double c1 = a[2][1] * a[0][2] - a[0][1] * a[2][2];
+    double c2 = a[0][1] * a[1][2] - a[1][1] * a[0][2];
+    return a[0][0] * c0 + a[1][0] * c1 + a[2][0] * c2;
+  }
+}
+
+// sqrt(det(JᵀJ))  (quadrature.jl:4-6)
+template <int D>
+__device__ __forceinline__ double change_of_measure(const double (&J)[D][D]) {
+  double G[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      double s = J[0][i] * J[0][j];
+#pragma unroll
+      for (int k = 1; k < D; ++k) s += J[k][i] * J[k][j];
+      G[i][j] = s;
+    }
+  return sqrt(det_mat<D>(G));
+}
+
+// g = a \ b with a = Jᵀ  (StaticArrays closed forms; accessors.jl:1365-1368)
+template <int D>
+__device__ __forceinline__ void solve_JT(const double (&J)[D][D], double d, const double* b, double* g) {
+  if constexpr (D == 1) { g[0] = b[0] / J[0][0]; }
+  if constexpr (D == 2) {
+    // a[i][j] = J[j][i]
+    g[0] = (J[1][1] * b[0] - J[1][0] * b[1]) / d;
+    g[1] = (J[0][0] * b[1] - J[0][1] * b[0]) / d;
+  }
+  if constexpr (D == 3) {
+#define A_(i, j) J[(j)-1][(i)-1]
+    g[0] = ((A_(2, 2) * A_(3, 3) - A_(2, 3) * A_(3, 2)) * b[0] + (A_(1, 3) * A_(3, 2) - A_(1, 2) * A_(3, 3)) * b[1] +
+            (A_(1, 2) * A_(2, 3) - A_(1, 3) * A_(2, 2)) * b[2]) / d;
+    g[1] = ((A_(2, 3) * A_(3, 1) - A_(2, 1) * A_(3, 3)) * b[0] + (A_(1, 1) * A_(3, 3) - A_(1, 3) * A_(3, 1)) * b[1] +
+            (A_(1, 3) * A_(2, 1) - A_(1, 1) * A_(2, 3)) * b[2]) / d;
+    g[2] = ((A_(2, 1) * A_(3, 2) - A_(2, 2) * A_(3, 1)) * b[0] + (A_(1, 2) * A_(3, 1) - A_(1, 1) * A_(3, 2)) * b[1] +
+            (A_(1, 1) * A_(2, 2) - A_(1, 2) * A_(2, 1)) * b[2]) / d;
+#undef A_
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void jacobian_at(const ElemArgs& a, int64_t cell, int q, double (&J)[D][D]) {
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) J[i][j] = 0.0;
+  const int32_t* nodes = a.cell_nodes + cell * a.nln;
+  const double* dMq = a.dM + (size_t)q * a.nln * D;
+  for (int n = 0; n < a.nln; ++n) {   // sequential in local-node order (accessors.jl:941-948)
+    const double* x = a.xyz + (size_t)(nodes[n] - 1) * D;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) J[i][j] += x[i] * dMq[n * D + j];
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
+  extern __shared__ double smem[];
+  const int nq = a.nq, nls = a.nls, nld = a.nld, ncomp = a.ncomp;
+  double* G = smem;                                  // [cb][nq][nls][D]
+  double* dV = G + (size_t)a.cb * nq * nls * D;      // [cb][nq]
+  const int64_t cell0 = (int64_t)blockIdx.x * a.cb;
+  const int ncb = (int)min((int64_t)a.cb, a.n_cells - cell0);
+  const bool need_grad = a.form != GTK_FORM_MASS;
+  for (int t = threadIdx.x; t < ncb * nq; t += blockDim.x) {
+    int cl = t / nq, q = t - cl * nq;
+    double J[D][D];
+    jacobian_at<D>(a, cell0 + cl, q, J);
+    dV[t] = change_of_measure<D>(J) * a.w[q];
+    if (need_grad) {
+      double JT[D][D];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) JT[i][j] = J[j][i];
+      double d = det_mat<D>(JT);
+      double* g = G + (size_t)t * nls * D;
+      const double* dNq = a.dN + (size_t)q * nls * D;
+      for (int s = 0; s < nls; ++s) solve_JT<D>(J, d, dNq + s * D, g + s * D);
+    }
+  }
+  __syncthreads();
+  const int nld2 = nld * nld;
+  for (int t = threadIdx.x; t < ncb * nld2; t += blockDim.x) {
+    int cl = t / nld2, rem = t - cl * nld2;
+    int c = rem / nld, r = rem - c * nld;
+    int ra = r / ncomp, ri = r - ra * ncomp;
+    int ca = c / ncomp, cj = c - ca * ncomp;
+    double acc = 0.0;
+    for (int q = 0; q < nq; ++q) {
+      const double* gq = G + ((size_t)(cl * nq + q) * nls) * D;
+      double v;
+      if (a.form == GTK_FORM_LAPLACE) {
+        double dt = 0.0;
+        if (ri == cj) {
+          dt = gq[ra * D] * gq[ca * D];
+#pragma unroll
+          for (int k = 1; k < D; ++k) dt += gq[ra * D + k] * gq[ca * D + k];
+        }
+        v = a.alpha * dt;
+      } else if (a.form == GTK_FORM_MASS) {
+        v = ri == cj ? a.alpha * (a.N[q * nls + ra] * a.N[q * nls + ca]) : 0.0;
+      } else {  // ELASTICITY_ISO: λ ∂_i s_a ∂_j s_b + μ ∂_j s_a ∂_i s_b + μ δ_ij ∇s_a·∇s_b
+        double tt = a.lambda * (gq[ra * D + ri] * gq[ca * D + cj]) + a.mu * (gq[ra * D + cj] * gq[ca * D + ri]);
+        if (ri == cj) {
+          double dt = gq[ra * D] * gq[ca * D];
+#pragma unroll
+          for (int k = 1; k < D; ++k) dt += gq[ra * D + k] * gq[ca * D + k];
+          tt += a.mu * dt;
+        }
+        v = a.alpha * tt;
+      }
+      acc += v * dV[cl * nq + q];
+    }
+    a.out[(cell0 + cl) * (int64_t)nld2 + rem] = acc;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_elem_vector(ElemArgs a) {
+  extern __shared__ double smem[];
+  const int nq = a.nq, nls = a.nls, nld = a.nld, ncomp = a.ncomp;
+  double* dV = smem;                          // [cb][nq]
+  double* F = dV + (size_t)a.cb * nq;         // [cb][nq][ncomp]
+  const int64_t cell0 = (int64_t)blockIdx.x * a.cb;
+  const int ncb = (int)min((int64_t)a.cb, a.n_cells - cell0);
+  for (int t = threadIdx.x; t < ncb * nq; t += blockDim.x) {
+    int cl = t / nq, q = t - cl * nq;
+    int64_t cell = cell0 + cl;
+    double J[D][D];
+    jacobian_at<D>(a, cell, q, J);
+    dV[t] = change_of_measure<D>(J) * a.w[q];
+    for (int k = 0; k < ncomp; ++k) {
+      double f;
+      if (a.form == GTK_FORM_SOURCE_CONST) f = a.f_const[k];
+      else if (a.form == GTK_FORM_SOURCE_QP) f = a.f_ptr[((size_t)cell * nq + q) * ncomp + k];
+      else {  // nodal: Σ_node f_node M_node(ξ_q), sequential
+        f = 0.0;
+        const int32_t* nodes = a.cell_nodes + cell * a.nln;
+        for (int n = 0; n < a.nln; ++n) f += a.f_ptr[(size_t)(nodes[n] - 1) * ncomp + k] * a.M[q * a.nln + n];
+      }
+      F[(size_t)t * ncomp + k] = f;
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < ncb * nld; t += blockDim.x) {
+    int cl = t / nld, i = t - cl * nld;
+    int ia = i / ncomp, ic = i - ia * ncomp;
+    double acc = 0.0;
+    for (int q = 0; q < nq; ++q)
+      acc += (a.alpha * (F[(size_t)(cl * nq + q) * ncomp + ic] * a.N[q * nls + ia])) * dV[cl * nq + q];
+    a.out[(cell0 + cl) * (int64_t)nld + i] = acc;
+  }
+}
+
+// nzval[p] = Σ_{s in segment p} KE[perm[s]], left to right = reference push order.
+__global__ void k_reduce_nz(const double* __restrict__ KE, const uint32_t* __restrict__ perm,
+                            const uint32_t* __restrict__ nzptr, int64_t nnz, double* __restrict__ nzval) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < nnz;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t s0 = nzptr[p], s1 = nzptr[p + 1];
+    double acc = KE[perm[s0]];
+    for (uint32_t s = s0 + 1; s < s1; ++s) acc += KE[perm[s]];
+    nzval[p] = acc;
+  }
+}
+
+__global__ void k_reduce_rows(const double* __restrict__ BE, const uint32_t* __restrict__ perm,
+                              const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ urow,
+                              int64_t n_urows, double* __restrict__ b) {
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n_urows;
+       u += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t s0 = rowptr[u], s1 = rowptr[u + 1];
+    double acc = 0.0 + BE[perm[s0]];   // dense_vector starts from zeros (assembly.jl:562)
+    for (uint32_t s = s0 + 1; s < s1; ++s) acc += BE[perm[s]];
+    b[urow[u]] = acc;
+  }
+}
+
+inline int grid_for(int64_t n, int block, int sm) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)sm * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int32_t ensure(gtk_ctx* ctx, double** p, size_t* cap, size_t n) {
+  if (*cap >= n && *p) return GTK_OK;
+  if (*p) gtk_dev_free(ctx, *p, *cap * sizeof(double));
+  *p = nullptr; *cap = 0;
+  if (n == 0) n = 1;
+  int32_t rc = gtk_dev_alloc(ctx, (void**)p, n * sizeof(double));
+  if (rc == GTK_OK) *cap = n;
+  return rc;
+}
+
+int32_t fill_args(gtk_ctx* ctx, ElemArgs& a, int form, const gtk_form_params* p) {
+  if (!ctx->xyz || !ctx->cell_dofs || !ctx->w) GTK_FAIL(GTK_ERR_STATE, "mesh, space and tabulation must be set first");
+  a.xyz = ctx->xyz; a.cell_nodes = ctx->cell_nodes; a.n_cells = ctx->n_cells;
+  a.nln = ctx->nln; a.nls = ctx->nls; a.ncomp = ctx->ncomp; a.nld = ctx->nld; a.nq = ctx->nq;
+  a.w = ctx->w; a.N = ctx->N; a.dN = ctx->dN; a.M = ctx->M; a.dM = ctx->dM;
+  a.form = form;
+  a.alpha = p ? p->alpha : 1.0;
+  a.lambda = p ? p->lambda : 0.0;
+  a.mu = p ? p->mu : 0.0;
+  for (int k = 0; k < 3; ++k) a.f_const[k] = p ? p->f_const[k] : 0.0;
+  a.f_ptr = nullptr;
+  return GTK_OK;
+}
+
+int32_t pick_cb(gtk_ctx* ctx, size_t per_cell_bytes, int* cb, size_t* smem) {
+  size_t soft = 96 * 1024;
+  int c = (int)(soft / per_cell_bytes);
+  if (c > 32) c = 32;
+  if (c < 1) c = (int)((ctx->smem_optin - 2048) / per_cell_bytes);
+  if (c < 1) GTK_FAIL(GTK_ERR_TOO_LARGE, "element too large for the generic shared-memory kernel");
+  *cb = c;
+  *smem = c * per_cell_bytes;
+  return GTK_OK;
+}
+
+}  // namespace
+
+int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params* p) {
+  MatSym& m = ctx->ms;
+  if (form == GTK_FORM_ELASTICITY_ISO && ctx->ncomp != ctx->D)
+    GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "ELASTICITY_ISO needs a vector space with n_comp == D");
+  if (form != GTK_FORM_LAPLACE && form != GTK_FORM_MASS && form != GTK_FORM_ELASTICITY_ISO)
+    GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "unsupported bilinear form id " + std::to_string(form) +
+                                           " (supported: LAPLACE, MASS, ELASTICITY_ISO); no CPU fallback");
+  ElemArgs a;
+  int32_t rc = fill_args(ctx, a, form, p);
+  if (rc) return rc;
+  rc = ensure(ctx, &ctx->KE, &ctx->KE_cap, (size_t)m.n_full);
+  if (rc) return rc;
+  rc = ensure(ctx, &ctx->nzval, &ctx->nzval_cap, (size_t)m.nnz);
+  if (rc) return rc;
+  if (ctx->n_cells == 0 || m.nnz == 0) return GTK_OK;
+  a.out = ctx->KE;
+  const int D = ctx->D;
+  size_t per_cell = ((size_t)ctx->nq * ctx->nls * D + ctx->nq) * sizeof(double);
+  size_t smem;
+  rc = pick_cb(ctx, per_cell, &a.cb, &smem);
+  if (rc) return rc;
+  int grid = (int)((ctx->n_cells + a.cb - 1) / a.cb);
+  cudaStream_t st = ctx->stream;
+#define LAUNCH_M(DD)                                                                                        \
+  do {                                                                                                      \
+    GTK_CK(cudaFuncSetAttribute(k_elem_matrix<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    { GtkProf pr_(ctx, "k_elem_matrix"); k_elem_matrix<DD><<<grid, 128, smem, st>>>(a); }                                                          \
+  } while (0)
+  if (D == 1) LAUNCH_M(1); else if (D == 2) LAUNCH_M(2); else if (D == 3) LAUNCH_M(3);
+  else GTK_FAIL(GTK_ERR_INVALID, "D must be 1, 2 or 3");
+#undef LAUNCH_M
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  { GtkProf pr_(ctx, "k_reduce_nz"); k_reduce_nz<<<grid_for(m.nnz, 256, ctx->sm_count), 256, 0, st>>>(ctx->KE, m.perm, m.nzptr, m.nnz, ctx->nzval); }
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  return GTK_OK;
+}
+
+static int32_t upload_f(gtk_ctx* ctx, const double* host, size_t n) {
+  if (!host) GTK_FAIL(GTK_ERR_INVALID, "source data pointer is null");
+  int32_t rc = ensure(ctx, &ctx->f_dev, &ctx->f_cap, n);
+  if (rc) return rc;
+  GTK_CK(cudaMemcpyAsync(ctx->f_dev, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params* p) {
+  VecSym& v = ctx->vs;
+  if (form != GTK_FORM_SOURCE_CONST && form != GTK_FORM_SOURCE_NODAL && form != GTK_FORM_SOURCE_QP)
+    GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "unsupported linear form id " + std::to_string(form) +
+                                           " (supported: SOURCE_CONST, SOURCE_NODAL, SOURCE_QP); no CPU fallback");
+  ElemArgs a;
+  int32_t rc = fill_args(ctx, a, form, p);
+  if (rc) return rc;
+  if (form == GTK_FORM_SOURCE_NODAL) {
+    rc = upload_f(ctx, p ? p->f_nodal : nullptr, (size_t)ctx->n_nodes * ctx->ncomp);
+    if (rc) return rc;
+    a.f_ptr = ctx->f_dev;
+  } else if (form == GTK_FORM_SOURCE_QP) {
+    rc = upload_f(ctx, p ? p->f_qp : nullptr, (size_t)ctx->n_cells * ctx->nq * ctx->ncomp);
+    if (rc) return rc;
+    a.f_ptr = ctx->f_dev;
+  }
+  rc = ensure(ctx, &ctx->BE, &ctx->BE_cap, (size_t)v.n_full);
+  if (rc) return rc;
+  rc = ensure(ctx, &ctx->bvec, &ctx->bvec_cap, (size_t)v.n_rows);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  GTK_CK(cudaMemsetAsync(ctx->bvec, 0, sizeof(double) * (size_t)(v.n_rows > 0 ? v.n_rows : 1), st));
+  if (ctx->n_cells == 0 || v.n_urows == 0) return GTK_OK;
+  a.out = ctx->BE;
+  const int D = ctx->D;
+  size_t per_cell = ((size_t)ctx->nq * (1 + ctx->ncomp)) * sizeof(double);
+  size_t smem;
+  rc = pick_cb(ctx, per_cell, &a.cb, &smem);
+  if (rc) return rc;
+  int grid = (int)((ctx->n_cells + a.cb - 1) / a.cb);
+#define LAUNCH_V(DD)                                                                                        \
+  do {                                                                                                      \
+    GTK_CK(cudaFuncSetAttribute(k_elem_vector<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    { GtkProf pr_(ctx, "k_elem_vector"); k_elem_vector<DD><<<grid, 128, smem, st>>>(a); }                                                          \
+  } while (0)
+  if (D == 1) LAUNCH_V(1); else if (D == 2) LAUNCH_V(2); else if (D == 3) LAUNCH_V(3);
+  else GTK_FAIL(GTK_ERR_INVALID, "D must be 1, 2 or 3");
+#undef LAUNCH_V
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  { GtkProf pr_(ctx, "k_reduce_rows"); k_reduce_rows<<<grid_for(v.n_urows, 256, ctx->sm_count), 256, 0, st>>>(ctx->BE, v.perm, v.rowptr, v.urow,
+                                                                         v.n_urows, ctx->bvec); }
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  return GTK_OK;
+}
+
+int32_t gtk_numeric_matrix_impl(gtk_ctx* ctx, int form, const gtk_form_params* p) {
+  if (!ctx->ms.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_symbolic must be called before gtk_matrix_numeric");
+  ctx->launches_last = 0;
+  ctx->fast_path_last = 0;
+  gtk_prof_reset(ctx);
+  bool handled = false;
+  int32_t rc = gtk_fastq1_try(ctx, form, p, 0, nullptr, &handled);
+  if (rc) return rc;
+  if (handled) return GTK_OK;
+  return gtk_numeric_matrix_generic(ctx, form, p);
+}
+
+int32_t gtk_numeric_vector_impl(gtk_ctx* ctx, int form, const gtk_form_params* p) {
+  if (!ctx->vs.ready) {
+    int32_t rc = gtk_symbolic_vector_impl(ctx, GTK_FREE);
+    if (rc) return rc;
+  }
+  ctx->launches_last = 0;
+  ctx->fast_path_last = 0;
+  gtk_prof_reset(ctx);
+  bool handled = false;
+  int32_t rc = gtk_fastq1_try(ctx, 0, nullptr, form, p, &handled);
+  if (rc) return rc;
+  if (handled) return GTK_OK;
+  return gtk_numeric_vector_generic(ctx, form, p);
+}
+
+int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
+                              const gtk_form_params* pv) {
+  if (!ctx->ms.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_symbolic must be called first");
+  if (!ctx->vs.ready) {
+    int32_t rc = gtk_symbolic_vector_impl(ctx, ctx->ms.rows_fd);
+    if (rc) return rc;
+  }
+  ctx->launches_last = 0;
+  ctx->fast_path_last = 0;
+  gtk_prof_reset(ctx);
+  bool handled = false;
+  int32_t rc = gtk_fastq1_try(ctx, mform, pm, vform, pv, &handled);
+  if (rc) return rc;
+  if (handled) return GTK_OK;
+  rc = gtk_numeric_matrix_generic(ctx, mform, pm);
+  if (rc) return rc;
+  return gtk_numeric_vector_generic(ctx, vform, pv);
+}

@@ -1,0 +1,312 @@
+"""ctypes binding of libgtkasm's C ABI (include/gtk_assembly.h).
+
+This is the stand-in for the Julia `ccall` shim: the same symbols,
+the same argument order, plain pointers and sizes.  There is no CPU fallback: if the
+shared library is missing, or no GPU is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgtkasm.so")
+
+GTK_OK = 0
+GTK_ERR_INVALID, GTK_ERR_CUDA, GTK_ERR_UNSUPPORTED_FORM, GTK_ERR_STATE, GTK_ERR_TOO_LARGE, GTK_ERR_NCCL = -1, -2, -3, -4, -5, -6
+FREE, DIRICHLET = 1, 2
+FORM_LAPLACE, FORM_MASS, FORM_ELASTICITY_ISO = 1, 2, 3
+FORM_SOURCE_CONST, FORM_SOURCE_NODAL, FORM_SOURCE_QP = 101, 102, 103
+
+# every symbol include/gtk_assembly.h declares (tests check the .so exports all of them)
+ABI_SYMBOLS = [
+    "gtk_version", "gtk_create", "gtk_destroy", "gtk_last_error", "gtk_set_stream",
+    "gtk_set_mesh", "gtk_update_coordinates", "gtk_set_space", "gtk_set_tabulation",
+    "gtk_matrix_symbolic", "gtk_matrix_pattern", "gtk_matrix_numeric", "gtk_matrix_numeric_device",
+    "gtk_vector_symbolic", "gtk_vector_assemble", "gtk_vector_assemble_device",
+    "gtk_assemble_matrix_and_vector", "gtk_assemble_matrix_and_vector_device",
+    "gtk_device_pointer", "gtk_copy_nzval", "gtk_copy_vector", "gtk_info",
+    "gtk_comm_unique_id", "gtk_comm_init", "gtk_comm_setup_ghost_rows", "gtk_comm_sum_ghost_rows",
+    "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
+]
+
+
+class GtkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libgtkasm error {code}: {msg}")
+        self.code = code
+
+
+class UnsupportedFormError(GtkError):
+    """The engine does not recognise the form; it never falls back to the CPU."""
+
+
+class FormParams(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("lam", C.c_double), ("mu", C.c_double),
+                ("f_const", C.c_double * 3), ("f_nodal", C.c_void_p), ("f_qp", C.c_void_p)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libgtkasm.so (built in-tree by build.py).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the engine has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    sig = {
+        "gtk_version": (i32, []),
+        "gtk_create": (i32, [i32, C.POINTER(vp)]),
+        "gtk_destroy": (i32, [vp]),
+        "gtk_last_error": (C.c_char_p, [vp]),
+        "gtk_set_stream": (i32, [vp, vp]),
+        "gtk_set_mesh": (i32, [vp, i32, i64, vp, i64, i32, vp]),
+        "gtk_update_coordinates": (i32, [vp, vp]),
+        "gtk_set_space": (i32, [vp, i32, i32, vp, i64, i64]),
+        "gtk_set_tabulation": (i32, [vp, i32, vp, vp, vp, vp, vp]),
+        "gtk_matrix_symbolic": (i32, [vp, i32, i32, C.POINTER(i64)]),
+        "gtk_matrix_pattern": (i32, [vp, vp, vp]),
+        "gtk_matrix_numeric": (i32, [vp, i32, C.POINTER(FormParams), vp]),
+        "gtk_matrix_numeric_device": (i32, [vp, i32, C.POINTER(FormParams)]),
+        "gtk_vector_symbolic": (i32, [vp, i32]),
+        "gtk_vector_assemble": (i32, [vp, i32, C.POINTER(FormParams), vp]),
+        "gtk_vector_assemble_device": (i32, [vp, i32, C.POINTER(FormParams)]),
+        "gtk_assemble_matrix_and_vector": (i32, [vp, i32, C.POINTER(FormParams), i32, C.POINTER(FormParams), vp, vp]),
+        "gtk_assemble_matrix_and_vector_device": (i32, [vp, i32, C.POINTER(FormParams), i32, C.POINTER(FormParams)]),
+        "gtk_device_pointer": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
+        "gtk_copy_nzval": (i32, [vp, vp]),
+        "gtk_copy_vector": (i32, [vp, vp]),
+        "gtk_info": (i64, [vp, i32]),
+        "gtk_comm_unique_id": (i32, [vp]),
+        "gtk_comm_init": (i32, [vp, i32, i32, vp]),
+        "gtk_comm_setup_ghost_rows": (i32, [vp, i64, i64]),
+        "gtk_comm_sum_ghost_rows": (i32, [vp]),
+        "gtk_comm_ghost_info": (i64, [vp, i32]),
+        "gtk_set_profiling": (i32, [vp, i32]),
+        "gtk_profile_count": (i32, [vp]),
+        "gtk_profile_get": (i32, [vp, i32, C.c_char_p, C.POINTER(C.c_double)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def make_params(alpha=1.0, lam=0.0, mu=0.0, f_const=None, f_nodal=None, f_qp=None):
+    """Returns (FormParams, keepalive) — keepalive holds the numpy buffers the struct points to."""
+    p = FormParams()
+    p.alpha, p.lam, p.mu = float(alpha), float(lam), float(mu)
+    fc = np.zeros(3)
+    if f_const is not None:
+        v = np.atleast_1d(np.asarray(f_const, dtype=np.float64)).reshape(-1)
+        fc[: v.size] = v
+    for k in range(3):
+        p.f_const[k] = fc[k]
+    keep = []
+    if f_nodal is not None:
+        a = _f64(f_nodal); keep.append(a); p.f_nodal = a.ctypes.data
+    if f_qp is not None:
+        a = _f64(f_qp); keep.append(a); p.f_qp = a.ctypes.data
+    return p, keep
+
+
+class Engine:
+    """One gtk_ctx on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.gtk_create(int(device), C.byref(h))
+        if rc != GTK_OK or not h.value:
+            raise GtkError(rc, f"gtk_create(device={device}) failed — a CUDA GPU is required (no CPU fallback)")
+        self.h = h
+        self.device = device
+        self.nnz = 0
+        self.n_rows = 0
+        self.n_cols = 0
+        self.n_vec_rows = 0
+
+    # -- plumbing ---------------------------------------------------------------
+    def _ck(self, rc: int):
+        if rc != GTK_OK:
+            msg = self.lib.gtk_last_error(self.h)
+            msg = msg.decode() if msg else ""
+            if rc == GTK_ERR_UNSUPPORTED_FORM:
+                raise UnsupportedFormError(rc, msg)
+            raise GtkError(rc, msg)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.gtk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle: int):
+        self._ck(self.lib.gtk_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    # -- inputs -------------------------------------------------------------------
+    def set_mesh(self, node_coordinates, cell_nodes):
+        xyz = _f64(node_coordinates)
+        cn = _i32(cell_nodes)
+        self._D = xyz.shape[1]
+        self._n_cells = cn.shape[0]
+        self._ck(self.lib.gtk_set_mesh(self.h, xyz.shape[1], xyz.shape[0], _ptr(xyz), cn.shape[0], cn.shape[1], _ptr(cn)))
+
+    def update_coordinates(self, node_coordinates):
+        xyz = _f64(node_coordinates)
+        self._ck(self.lib.gtk_update_coordinates(self.h, _ptr(xyz)))
+
+    def set_space(self, cell_dofs, n_free: int, n_dirichlet: int, n_comp: int = 1):
+        cd = _i32(cell_dofs)
+        self._n_free, self._n_diri = int(n_free), int(n_dirichlet)
+        self._ck(self.lib.gtk_set_space(self.h, cd.shape[1], n_comp, _ptr(cd), n_free, n_dirichlet))
+
+    def set_tabulation(self, w, N, dN, M, dM):
+        w, N, dN, M, dM = map(_f64, (w, N, dN, M, dM))
+        self._ck(self.lib.gtk_set_tabulation(self.h, w.shape[0], _ptr(w), _ptr(N), _ptr(dN), _ptr(M), _ptr(dM)))
+
+    # -- matrix ---------------------------------------------------------------------
+    def matrix_symbolic(self, rows=FREE, cols=FREE) -> int:
+        nnz = C.c_int64(0)
+        self._ck(self.lib.gtk_matrix_symbolic(self.h, rows, cols, C.byref(nnz)))
+        self.nnz = nnz.value
+        self.n_rows = self._n_free if rows == FREE else self._n_diri
+        self.n_cols = self._n_free if cols == FREE else self._n_diri
+        return self.nnz
+
+    def matrix_pattern(self):
+        colptr = np.empty(self.n_cols + 1, dtype=np.int32)
+        rowval = np.empty(self.nnz, dtype=np.int32)
+        self._ck(self.lib.gtk_matrix_pattern(self.h, _ptr(colptr), _ptr(rowval)))
+        return colptr, rowval
+
+    def matrix_numeric(self, form: int, out: Optional[np.ndarray] = None, **params) -> np.ndarray:
+        p, keep = make_params(**params)
+        nz = np.empty(self.nnz, dtype=np.float64) if out is None else out
+        self._ck(self.lib.gtk_matrix_numeric(self.h, form, C.byref(p), _ptr(nz)))
+        del keep
+        return nz
+
+    def matrix_numeric_device(self, form: int, **params):
+        p, keep = make_params(**params)
+        self._ck(self.lib.gtk_matrix_numeric_device(self.h, form, C.byref(p)))
+        del keep
+
+    # -- vector ---------------------------------------------------------------------
+    def vector_symbolic(self, fd=FREE):
+        self._ck(self.lib.gtk_vector_symbolic(self.h, fd))
+        self.n_vec_rows = self._n_free if fd == FREE else self._n_diri
+
+    def vector_assemble(self, form: int, out: Optional[np.ndarray] = None, **params) -> np.ndarray:
+        if self.n_vec_rows == 0 and self.lib.gtk_info(self.h, 3) >= 0:
+            self.vector_symbolic(FREE)
+        p, keep = make_params(**params)
+        b = np.empty(self.n_vec_rows, dtype=np.float64) if out is None else out
+        self._ck(self.lib.gtk_vector_assemble(self.h, form, C.byref(p), _ptr(b)))
+        del keep
+        return b
+
+    def vector_assemble_device(self, form: int, **params):
+        p, keep = make_params(**params)
+        self._ck(self.lib.gtk_vector_assemble_device(self.h, form, C.byref(p)))
+        del keep
+
+    # -- both -----------------------------------------------------------------------
+    def assemble_matrix_and_vector(self, mform: int, mparams: dict, vform: int, vparams: dict,
+                                   nzval: Optional[np.ndarray] = None, b: Optional[np.ndarray] = None):
+        if self.n_vec_rows == 0:
+            self.vector_symbolic(FREE)
+        pm, k1 = make_params(**mparams)
+        pv, k2 = make_params(**vparams)
+        nz = np.empty(self.nnz, dtype=np.float64) if nzval is None else nzval
+        bb = np.empty(self.n_vec_rows, dtype=np.float64) if b is None else b
+        self._ck(self.lib.gtk_assemble_matrix_and_vector(self.h, mform, C.byref(pm), vform, C.byref(pv), _ptr(nz), _ptr(bb)))
+        del k1, k2
+        return nz, bb
+
+    def assemble_matrix_and_vector_device(self, mform: int, mparams: dict, vform: int, vparams: dict):
+        if self.n_vec_rows == 0:
+            self.vector_symbolic(FREE)
+        pm, k1 = make_params(**mparams)
+        pv, k2 = make_params(**vparams)
+        self._ck(self.lib.gtk_assemble_matrix_and_vector_device(self.h, mform, C.byref(pm), vform, C.byref(pv)))
+        del k1, k2
+
+    def copy_nzval(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        nz = np.empty(self.nnz, dtype=np.float64) if out is None else out
+        self._ck(self.lib.gtk_copy_nzval(self.h, _ptr(nz)))
+        return nz
+
+    def copy_vector(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        b = np.empty(self.n_vec_rows, dtype=np.float64) if out is None else out
+        self._ck(self.lib.gtk_copy_vector(self.h, _ptr(b)))
+        return b
+
+    def device_pointer(self, which: int):
+        p = C.c_void_p()
+        n = C.c_int64(0)
+        self._ck(self.lib.gtk_device_pointer(self.h, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def info(self, key: int) -> int:
+        return int(self.lib.gtk_info(self.h, key))
+
+    def set_profiling(self, on: bool):
+        self._ck(self.lib.gtk_set_profiling(self.h, 1 if on else 0))
+
+    def profile(self):
+        """[(kernel name, milliseconds)] of the last numeric call (needs set_profiling(True))."""
+        out = []
+        for i in range(self.lib.gtk_profile_count(self.h)):
+            name = C.create_string_buffer(64)
+            ms = C.c_double(0)
+            self._ck(self.lib.gtk_profile_get(self.h, i, name, C.byref(ms)))
+            out.append((name.value.decode(), ms.value))
+        return out
+
+    # -- multi-GPU ------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.gtk_comm_unique_id(buf)
+        if rc != GTK_OK:
+            raise GtkError(rc, "gtk_comm_unique_id failed (NCCL not loadable?)")
+        return buf.raw
+
+    def comm_init(self, rank: int, n_ranks: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.lib.gtk_comm_init(self.h, rank, n_ranks, buf))
+
+    def comm_setup_ghost_rows(self, own_lo: int, own_hi: int):
+        self._ck(self.lib.gtk_comm_setup_ghost_rows(self.h, own_lo, own_hi))
+
+    def comm_sum_ghost_rows(self):
+        self._ck(self.lib.gtk_comm_sum_ghost_rows(self.h))

@@ -1,0 +1,426 @@
+"""Host-side mirror of the reference's user API for the assembly path.
+
+Same names, argument meaning and error behaviour as GalerkinToolkit
+(problems.jl:4-34, 244-274, 319-404; assembly.jl:11-25) so tests read like the
+reference's own (test/problems_tests.jl, test/assembly_tests.jl):
+
+    mesh = GT.cartesian_mesh((0,1,0,1),(64,64))
+    Ω = GT.interior(mesh);  Γ = GT.boundary(mesh)
+    V = GT.lagrange_space(Ω, 1, dirichlet_boundary=Γ)
+    dΩ = GT.measure(Ω, 2)
+    a = lambda u, v: GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dΩ)     # ∫(x->∇(u,x)⋅∇(v,x),dΩ)
+    l = lambda v:    GT.integrate(lambda x: f(x) * v(x), dΩ)
+    A = GT.assemble_matrix(a, float, V, V)
+    b = GT.assemble_vector(l, float, V)
+
+The integrand lambdas run on *symbolic quantities* and build a small term tree
+(the role of compiler.jl:372-390, 487-531, 1544-1606).  `recognise_*` is the
+stand-in for compiler.jl/passes.jl's form recognition: the
+supported shapes (mass, Laplacian, isotropic elasticity, source terms) are
+dispatched to the fused CUDA kernels; anything else raises
+:class:`UnsupportedFormError` — there is no CPU fallback.
+
+The cell loop, scatter and compression all run in libgtkasm (CUDA); numpy is
+only used here to prepare the flat input arrays (hostprep.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+
+from . import engine as _eng
+from . import hostprep as _hp
+from .engine import DIRICHLET, FREE, UnsupportedFormError  # noqa: F401
+
+Float64 = float
+
+# ---------------------------------------------------------------------------
+# mesh / domains / spaces / measures
+# ---------------------------------------------------------------------------
+cartesian_mesh = _hp.cartesian_mesh
+
+
+@dataclass
+class Domain:
+    """interior(mesh) / boundary(mesh; group_names) (mesh.jl:223-271)."""
+    mesh: _hp.Mesh
+    kind: str                      # "interior" | "boundary"
+    sides: Optional[Sequence[int]] = None
+
+
+def interior(mesh) -> Domain:
+    return Domain(mesh, "interior")
+
+
+def boundary(mesh, group_names: Optional[Sequence[str]] = None) -> Domain:
+    """group names are the reference's "<D-1>-face-<i>" (cartesian_mesh.jl:169-178)."""
+    sides = None
+    if group_names is not None:
+        sides = []
+        for g in group_names:
+            d, _, i = g.split("-")
+            if int(d) != mesh.D - 1:
+                raise ValueError(f"only (D-1)-face groups can be boundaries, got {g}")
+            sides.append(int(i))
+    return Domain(mesh, "boundary", sides)
+
+
+@dataclass
+class Measure:
+    domain: Domain
+    degree: int
+
+
+def measure(domain: Domain, degree: int) -> Measure:
+    if domain.kind != "interior":
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "boundary/skeleton measures are not dispatched to the GPU engine yet")
+    return Measure(domain, degree)
+
+
+class Space:
+    """lagrange_space(Ω, order; dirichlet_boundary, tensor_size) (space.jl:1702-1735)."""
+
+    def __init__(self, domain: Domain, order: int, dirichlet_boundary: Optional[Domain] = None, tensor_size=None):
+        if domain.kind != "interior":
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "spaces on boundary domains are out of scope")
+        n_comp = 1 if tensor_size is None else int(np.prod(tensor_size))
+        bc = None
+        if dirichlet_boundary is not None:
+            bc = "boundary" if dirichlet_boundary.sides is None else list(dirichlet_boundary.sides)
+        self.domain = domain
+        self.data = _hp.lagrange_space(domain.mesh, order, bc, n_comp)
+        self._tab = {}
+
+    # -- reference accessors ---------------------------------------------------
+    def face_dofs(self):
+        return self.data.cell_dofs
+
+    def num_free_dofs(self):
+        return self.data.n_free
+
+    def num_dirichlet_dofs(self):
+        return self.data.n_dirichlet
+
+    def tabulation(self, degree: int):
+        if degree not in self._tab:
+            self._tab[degree] = _hp.measure_tabulation(self.data, degree)
+        return self._tab[degree]
+
+
+def lagrange_space(domain, order, dirichlet_boundary=None, tensor_size=None) -> Space:
+    return Space(domain, order, dirichlet_boundary, tensor_size)
+
+
+# ---------------------------------------------------------------------------
+# symbolic quantities (tiny stand-in for compiler.jl's term IR)
+# ---------------------------------------------------------------------------
+class Term:
+    def __mul__(self, o): return Call("*", self, _lift(o))
+    def __rmul__(self, o): return Call("*", _lift(o), self)
+    def __add__(self, o): return Call("+", self, _lift(o))
+    def __radd__(self, o): return Call("+", _lift(o), self)
+    def __matmul__(self, o): return Call("dot", self, _lift(o))
+
+
+@dataclass
+class Const(Term):
+    value: object
+
+
+@dataclass
+class Coordinate(Term):        # CoordinateTerm (compiler.jl:60-1028)
+    pass
+
+
+@dataclass
+class FormArg(Term):           # FormArgumentTerm: arg 1 = test, arg 2 = trial (problems.jl:324-327)
+    arg: int
+    op: str                    # "value" | "gradient"
+
+
+@dataclass
+class Call(Term):              # CallTerm
+    fn: object
+    a: Term
+    b: Optional[Term] = None
+
+
+@dataclass
+class Named(Term):             # named integrand whose identity is matched
+    name: str
+    params: dict
+    args: tuple
+
+
+def _lift(o):
+    return o if isinstance(o, Term) else Const(o)
+
+
+class FormArgument:
+    """form_argument_quantity(space, arg) (compiler.jl:487-531)."""
+
+    def __init__(self, space: Space, arg: int):
+        self.space, self.arg = space, arg
+
+    def __call__(self, x):
+        return FormArg(self.arg, "value")
+
+
+def grad(u, x):
+    """∇(u,x) = ForwardDiff.gradient(u,x) on a form argument → tabulated gradient (compiler.jl:573-589)."""
+    if isinstance(u, FormArgument):
+        return FormArg(u.arg, "gradient")
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "∇ of a non form-argument quantity is not supported on the GPU path")
+
+
+def dot(a, b):
+    return Call("dot", _lift(a), _lift(b))
+
+
+class AnalyticalField:
+    """GT.analytical_field(f, Ω) (field.jl:17-58): evaluated by the host at x_q, enters the engine as data."""
+
+    def __init__(self, f: Callable, domain: Optional[Domain] = None):
+        self.f = f
+
+    def __call__(self, x):
+        if isinstance(x, Coordinate):
+            return Call(self.f, x)
+        return self.f(x)
+
+
+analytical_field = AnalyticalField
+
+
+def isotropic_elasticity(lam: float, mu: float):
+    """Named integrand σ(ε(u)):ε(v) with σ = λ tr(ε) I + 2μ ε.  The docs example builds this from opaque
+    closures through GT.external (docs/src/src_jl/example_linear_elasticity.jl:76-105), which cannot be
+    pattern-matched; the shim ships it as a named integrand instead."""
+    def integrand(u, v, x):
+        return Named("isotropic_elasticity", dict(lam=lam, mu=mu), (u.arg, v.arg))
+    return integrand
+
+
+@dataclass
+class Integral:
+    """∫(f, dΩ) → DomainContribution (problems.jl:29-125): list of (term, measure, scale)."""
+    contributions: list
+
+    def __add__(self, o):
+        return Integral(self.contributions + o.contributions)
+
+    def __rmul__(self, s):
+        return Integral([(t, m, s * a) for (t, m, a) in self.contributions])
+
+
+def integrate(f: Callable, measure: Measure) -> Integral:
+    term = f(Coordinate())
+    return Integral([(_lift(term), measure, 1.0)])
+
+
+# ---------------------------------------------------------------------------
+# form recognition (compiler.jl/passes.jl stand-in)
+# ---------------------------------------------------------------------------
+def _flatten_product(t):
+    """a*b*c → ([factors], scalar)"""
+    if isinstance(t, Call) and t.fn == "*":
+        fa, sa = _flatten_product(t.a)
+        fb, sb = _flatten_product(t.b)
+        return fa + fb, sa * sb
+    if isinstance(t, Const) and np.isscalar(t.value):
+        return [], float(t.value)
+    return [t], 1.0
+
+
+def recognise_bilinear(term):
+    """→ (form_id, params).  Raises UnsupportedFormError for anything that is not mass / Laplacian / elasticity."""
+    factors, scale = _flatten_product(term)
+    if len(factors) == 1 and isinstance(factors[0], Named) and factors[0].name == "isotropic_elasticity":
+        return _eng.FORM_ELASTICITY_ISO, dict(alpha=scale, **factors[0].params)
+    if len(factors) == 1 and isinstance(factors[0], Call) and factors[0].fn == "dot":
+        a, b = factors[0].a, factors[0].b
+        if isinstance(a, FormArg) and isinstance(b, FormArg) and {a.arg, b.arg} == {1, 2}:
+            if a.op == b.op == "gradient":
+                return _eng.FORM_LAPLACE, dict(alpha=scale)
+            if a.op == b.op == "value":
+                return _eng.FORM_MASS, dict(alpha=scale)
+    if len(factors) == 2 and all(isinstance(f, FormArg) and f.op == "value" for f in factors) \
+            and {factors[0].arg, factors[1].arg} == {1, 2}:
+        return _eng.FORM_MASS, dict(alpha=scale)
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM,
+                               "bilinear form not recognised by the GPU engine (supported: ∫∇u·∇v, ∫u v, "
+                               "isotropic_elasticity); refusing to fall back to a CPU loop")
+
+
+def recognise_linear(term, space: Space, meas: Measure):
+    """→ (form_id, params) for ∫ f·v with f a constant or a host-evaluated analytical field."""
+    factors, scale = _flatten_product(term)
+    if isinstance(term, Call) and term.fn == "dot":
+        factors = [term.a, term.b]
+    tests = [f for f in factors if isinstance(f, FormArg)]
+    others = [f for f in factors if not isinstance(f, FormArg)]
+    if len(tests) != 1 or tests[0].arg != 1 or tests[0].op != "value" or len(others) > 1:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM,
+                                   "linear form not recognised by the GPU engine (supported: ∫ f v with f constant "
+                                   "or an analytical field); refusing to fall back to a CPU loop")
+    n_comp = space.data.n_comp
+    if not others:
+        return _eng.FORM_SOURCE_CONST, dict(alpha=scale, f_const=np.ones(n_comp))
+    f = others[0]
+    if isinstance(f, Const):
+        return _eng.FORM_SOURCE_CONST, dict(alpha=scale, f_const=np.broadcast_to(np.asarray(f.value, dtype=float), (n_comp,)))
+    if isinstance(f, Call) and callable(f.fn) and isinstance(f.a, Coordinate):
+        xq = quadrature_point_coordinates(space, meas)                 # [nc, nq, D]
+        vals = np.asarray(f.fn(np.moveaxis(xq, -1, 0)), dtype=np.float64)   # user f gets x[0], x[1], … arrays
+        if n_comp == 1:
+            vals = np.broadcast_to(vals, xq.shape[:2])[..., None]
+        else:
+            vals = np.moveaxis(np.broadcast_to(vals, (n_comp,) + xq.shape[:2]), 0, -1)
+        return _eng.FORM_SOURCE_QP, dict(alpha=scale, f_qp=np.ascontiguousarray(vals))
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "source term not recognised by the GPU engine")
+
+
+def quadrature_point_coordinates(space: Space, meas: Measure) -> np.ndarray:
+    """x_q = Σ_i x_i M_i(ξ_q) (accessors.jl:983-988), all cells at once (host input preparation for f(x_q))."""
+    tab = space.tabulation(meas.degree)
+    mesh = space.domain.mesh
+    X = mesh.node_coordinates[mesh.cell_nodes.astype(np.int64) - 1]       # [nc, nln, D]
+    return np.einsum("qn,cnd->cqd", tab.M, X)
+
+
+# ---------------------------------------------------------------------------
+# containers
+# ---------------------------------------------------------------------------
+@dataclass
+class SparseMatrixCSC:
+    """Julia's SparseMatrixCSC{Float64,Int32}: 1-based colptr/rowval."""
+    m: int
+    n: int
+    colptr: np.ndarray
+    rowval: np.ndarray
+    nzval: np.ndarray
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.nzval, self.rowval.astype(np.int64) - 1, self.colptr.astype(np.int64) - 1), shape=(self.m, self.n))
+
+    def sum(self):
+        return float(self.nzval.sum())
+
+
+@dataclass
+class AssemblyCache:
+    """What `reuse=Val(true)` returns next to the matrix/vector (problems.jl:267-273, 343-349):
+    here the engine context holding pattern + plan on the device."""
+    engine: _eng.Engine
+    form: int
+    params: dict
+    kind: str
+
+
+# ---------------------------------------------------------------------------
+# assemble_* (problems.jl:244-404)
+# ---------------------------------------------------------------------------
+_default_device = 0
+
+
+def set_device(device: int):
+    global _default_device
+    _default_device = device
+
+
+def _setup_engine(space: Space, meas: Measure, engine: Optional[_eng.Engine] = None) -> _eng.Engine:
+    eng = engine or _eng.Engine(_default_device)
+    mesh = space.domain.mesh
+    tab = space.tabulation(meas.degree)
+    eng.set_mesh(mesh.node_coordinates, mesh.cell_nodes)
+    eng.set_space(space.data.cell_dofs, space.data.n_free, space.data.n_dirichlet, space.data.n_comp)
+    eng.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+    return eng
+
+
+def _single_contribution(integral: Integral):
+    if len(integral.contributions) != 1:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "sums of integrals are assembled one call at a time on the GPU path")
+    return integral.contributions[0]
+
+
+def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False,
+                    free_or_dirichlet=(FREE, FREE), engine: Optional[_eng.Engine] = None):
+    """GT.assemble_matrix(a, T, U, V; reuse, free_or_dirichlet) (problems.jl:319-350).
+    Rows enumerate V (test), columns U (trial); only U is V is supported on the GPU path."""
+    if T not in (float, np.float64):
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "the engine assembles Float64 only")
+    if U is not V:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
+    u, v = FormArgument(U, 2), FormArgument(V, 1)
+    term, meas, scale = _single_contribution(a(u, v))
+    form, params = recognise_bilinear(term)
+    params["alpha"] = params.get("alpha", 1.0) * scale
+    eng = _setup_engine(V, meas, engine)
+    eng.matrix_symbolic(*free_or_dirichlet)
+    colptr, rowval = eng.matrix_pattern()
+    nzval = eng.matrix_numeric(form, **params)
+    A = SparseMatrixCSC(eng.n_rows, eng.n_cols, colptr, rowval, nzval)
+    if reuse:
+        return A, AssemblyCache(eng, form, params, "matrix")
+    eng.close()
+    return A
+
+
+def update_matrix(A: SparseMatrixCSC, cache: AssemblyCache, **new_params):
+    """GT.update_matrix!(A, cache) (problems.jl:352-361): numeric re-assembly on the cached pattern."""
+    cache.params.update(new_params)
+    cache.engine.matrix_numeric(cache.form, out=A.nzval, **cache.params)
+    return A
+
+
+def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, free_or_dirichlet=FREE,
+                    engine: Optional[_eng.Engine] = None):
+    """GT.assemble_vector(l, T, V; reuse) (problems.jl:244-274)."""
+    if T not in (float, np.float64):
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "the engine assembles Float64 only")
+    v = FormArgument(V, 1)
+    term, meas, scale = _single_contribution(l(v))
+    form, params = recognise_linear(term, V, meas)
+    params["alpha"] = params.get("alpha", 1.0) * scale
+    eng = _setup_engine(V, meas, engine)
+    eng.vector_symbolic(free_or_dirichlet)
+    b = eng.vector_assemble(form, **params)
+    if reuse:
+        return b, AssemblyCache(eng, form, params, "vector")
+    eng.close()
+    return b
+
+
+def update_vector(b: np.ndarray, cache: AssemblyCache, **new_params):
+    """GT.update_vector!(b, cache) (problems.jl:276-285)."""
+    cache.params.update(new_params)
+    cache.engine.vector_assemble(cache.form, out=b, **cache.params)
+    return b
+
+
+def assemble_matrix_and_vector(a: Callable, l: Callable, T, U: Space, V: Space, *, reuse: bool = False):
+    """GT.assemble_matrix_and_vector(a, l, T, U, V) (problems.jl:391-404): one fused pass over the cells."""
+    if U is not V:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
+    u, v = FormArgument(U, 2), FormArgument(V, 1)
+    term_a, meas_a, sa = _single_contribution(a(u, v))
+    term_l, meas_l, sl = _single_contribution(l(v))
+    if meas_a.degree != meas_l.degree:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "matrix and vector must share one measure in the fused call")
+    mform, mparams = recognise_bilinear(term_a)
+    vform, vparams = recognise_linear(term_l, V, meas_l)
+    mparams["alpha"] = mparams.get("alpha", 1.0) * sa
+    vparams["alpha"] = vparams.get("alpha", 1.0) * sl
+    eng = _setup_engine(V, meas_a)
+    eng.matrix_symbolic(FREE, FREE)
+    colptr, rowval = eng.matrix_pattern()
+    nzval, b = eng.assemble_matrix_and_vector(mform, mparams, vform, vparams)
+    A = SparseMatrixCSC(eng.n_rows, eng.n_cols, colptr, rowval, nzval)
+    if reuse:
+        return A, b, AssemblyCache(eng, mform, dict(m=mparams, v=vparams, vform=vform), "both")
+    eng.close()
+    return A, b

@@ -1,0 +1,160 @@
+/* gtk_assembly.h — C ABI of libgtkasm, the B200-native assembly engine for
+ * GalerkinToolkit.jl's hot path (the cell loop behind GT.assemble_matrix /
+ * GT.assemble_vector).
+ *
+ * The reference has no FFI for this path (pure Julia).  Each entry point below
+ * names the reference interface it replaces (file:line relative to
+ * /root/reference/src) — that is what a Julia `ccall` shim binds; see
+ * INTEGRATION.md for the shim.
+ *
+ * Conventions:
+ *  - plain pointers and sizes only; every function returns an int32 status
+ *    (GTK_OK = 0, < 0 = error) and never throws; gtk_last_error() gives text;
+ *  - all indices on the ABI are 1-based Int32 exactly as Julia stores them
+ *    (cell->node ids, cell->dof ids with NEGATIVE = Dirichlet id, colptr/rowval);
+ *  - input pointers are HOST pointers borrowed for the duration of the call
+ *    (the Julia side wraps the call in GC.@preserve); the engine copies to HBM;
+ *  - outputs go to CALLER-allocated host arrays (two-phase: query nnz, allocate,
+ *    fill) so Julia owns the SparseMatrixCSC storage; *_device variants leave
+ *    results in HBM and hand out device pointers valid until the next call
+ *    that re-assembles, or gtk_destroy;
+ *  - a ctx is bound to one GPU and is not re-entrant; calls are synchronous
+ *    unless noted; there is NO CPU fallback: without a usable GPU gtk_create fails.
+ */
+#ifndef GTK_ASSEMBLY_H
+#define GTK_ASSEMBLY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gtk_ctx gtk_ctx;
+
+/* status codes */
+enum {
+  GTK_OK = 0,
+  GTK_ERR_INVALID = -1,            /* bad argument */
+  GTK_ERR_CUDA = -2,               /* CUDA runtime error (text in gtk_last_error) */
+  GTK_ERR_UNSUPPORTED_FORM = -3,   /* form/element not recognised: explicit error, never a CPU fallback */
+  GTK_ERR_STATE = -4,              /* call order violated (e.g. numeric before symbolic) */
+  GTK_ERR_TOO_LARGE = -5,          /* index range exceeded (Int32 colptr, COO index) */
+  GTK_ERR_NCCL = -6
+};
+
+/* field.jl:136-142 FREE / DIRICHLET; selects rows/cols like `free_or_dirichlet`
+ * of allocate_matrix (assembly.jl:75-104) */
+enum { GTK_FREE = 1, GTK_DIRICHLET = 2 };
+
+/* Recognised forms (what compiler.jl/passes.jl would pattern-match).
+ * Bilinear:  be[r,c] = sum_q (alpha * integrand(u=phi_r, v=phi_c)) * dV_q
+ * Linear:    be[i]   = sum_q (alpha * (f(x_q) . phi_i)) * dV_q                 */
+enum {
+  GTK_FORM_LAPLACE = 1,          /* ∫ ∇u·∇v            (scalar space)                      */
+  GTK_FORM_MASS = 2,             /* ∫ u v  (component-wise u·v for vector spaces)           */
+  GTK_FORM_ELASTICITY_ISO = 3,   /* ∫ σ(ε(u)):ε(v), σ = λ tr(ε) I + 2 μ ε (n_comp == D)     */
+  GTK_FORM_SOURCE_CONST = 101,   /* ∫ f·v, f constant (f_const[0..n_comp))                  */
+  GTK_FORM_SOURCE_NODAL = 102,   /* ∫ f_h·v, f_h = Σ_node f_node M_node (mesh nodes)         */
+  GTK_FORM_SOURCE_QP = 103       /* ∫ f·v, f given per (cell, quadrature point)             */
+};
+
+typedef struct gtk_form_params {
+  double alpha;            /* scalar in front of the integral (problems.jl:29-33, 102-108) */
+  double lambda, mu;       /* Lamé parameters (ELASTICITY_ISO) */
+  double f_const[3];       /* SOURCE_CONST */
+  const double* f_nodal;   /* SOURCE_NODAL: host [n_nodes][n_comp] */
+  const double* f_qp;      /* SOURCE_QP:    host [n_cells][n_q][n_comp] */
+} gtk_form_params;
+
+/* ---- life cycle ------------------------------------------------------------ */
+int32_t gtk_version(void);
+/* One engine context on CUDA device `device`.  Fails (GTK_ERR_CUDA) if there is no GPU. */
+int32_t gtk_create(int32_t device, gtk_ctx** out);
+int32_t gtk_destroy(gtk_ctx* ctx);
+const char* gtk_last_error(const gtk_ctx* ctx);
+/* Launch everything on this cudaStream_t (default: the legacy default stream) so a
+ * host that owns streams/events (Julia CUDA.jl, torch) can order and time the work. */
+int32_t gtk_set_stream(gtk_ctx* ctx, void* cuda_stream);
+
+/* ---- inputs ---------------------------------------------------------------- */
+/* node_coordinates(mesh) :: Vector{SVector{D,Float64}} = AoS [n_nodes][D];
+ * face_nodes(mesh,D) JaggedArray .data with constant n_lnodes per cell
+ * (cartesian_mesh.jl:213-263; GalerkinToolkitExamples/src/poisson.jl:323-325). */
+int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz,
+                     int64_t n_cells, int32_t n_lnodes, const int32_t* cell_nodes);
+/* Replace coordinates only (geometry update before a numeric re-assembly). */
+int32_t gtk_update_coordinates(gtk_ctx* ctx, const double* xyz);
+/* face_dofs(V).data (space.jl:81-87, 372-417): [n_cells][n_ldofs], 1-based, < 0 = Dirichlet id
+ * (assembly.jl:155-157).  n_comp > 1: dof = (node-1)*n_comp + c (space.jl:1267-1271). */
+int32_t gtk_set_space(gtk_ctx* ctx, int32_t n_ldofs, int32_t n_comp, const int32_t* cell_dofs,
+                      int64_t n_free, int64_t n_dirichlet);
+/* weights(quadrature) and the tabulated reference shape functions
+ * (quadrature.jl:78-95; accessors.jl:486-496; poisson.jl:321-324).
+ * N  [n_q][n_ldofs/n_comp]      = Julia Matrix[dof,point] memory order
+ * dN [n_q][n_ldofs/n_comp][D]   M/dM: same for the n_lnodes geometry functions. */
+int32_t gtk_set_tabulation(gtk_ctx* ctx, int32_t n_q, const double* w,
+                           const double* N, const double* dN,
+                           const double* M, const double* dM);
+
+/* ---- matrix: allocate_matrix + compress pattern (assembly.jl:75-153, 571-575) -- */
+/* Builds colptr/rowval of SparseMatrixCSC{Float64,Int32} and the device-side
+ * assembly plan.  Replaces the counting loop (assembly.jl:119-153) and the
+ * symbolic half of PartitionedArrays.sparse_matrix (assembly.jl:574). */
+int32_t gtk_matrix_symbolic(gtk_ctx* ctx, int32_t rows_free_or_dirichlet,
+                            int32_t cols_free_or_dirichlet, int64_t* nnz_out);
+/* Copy the pattern out: colptr[n_cols+1], rowval[nnz], 1-based Int32. */
+int32_t gtk_matrix_pattern(gtk_ctx* ctx, int32_t* colptr, int32_t* rowval);
+/* Numeric assembly = generated loop (compiler.jl:1826-1923) + contribute!
+ * (assembly.jl:189-208) + compress/compress! (assembly.jl:571-588).  Re-callable:
+ * second and later calls are GT.update_matrix! (problems.jl:352-361). */
+int32_t gtk_matrix_numeric(gtk_ctx* ctx, int32_t form_id, const gtk_form_params* p, double* nzval);
+int32_t gtk_matrix_numeric_device(gtk_ctx* ctx, int32_t form_id, const gtk_form_params* p);
+
+/* ---- vector: assemble_vector (problems.jl:244-274; assembly.jl:175-187, 558-569) -- */
+int32_t gtk_vector_symbolic(gtk_ctx* ctx, int32_t free_or_dirichlet);
+int32_t gtk_vector_assemble(gtk_ctx* ctx, int32_t form_id, const gtk_form_params* p, double* b);
+int32_t gtk_vector_assemble_device(gtk_ctx* ctx, int32_t form_id, const gtk_form_params* p);
+
+/* ---- matrix + vector in one pass: assemble_matrix_and_vector (problems.jl:391-404) -- */
+int32_t gtk_assemble_matrix_and_vector(gtk_ctx* ctx, int32_t matrix_form, const gtk_form_params* pm,
+                                       int32_t vector_form, const gtk_form_params* pv,
+                                       double* nzval, double* b);
+int32_t gtk_assemble_matrix_and_vector_device(gtk_ctx* ctx, int32_t matrix_form, const gtk_form_params* pm,
+                                              int32_t vector_form, const gtk_form_params* pv);
+
+/* ---- device-resident results -------------------------------------------------- */
+/* which: 0 nzval (double[nnz]) 1 b (double[n_rows]) 2 colptr (int64[n_cols+1], 0-based)
+ *        3 rowval (int32[nnz], 1-based) */
+int32_t gtk_device_pointer(gtk_ctx* ctx, int32_t which, void** dptr, int64_t* count);
+int32_t gtk_copy_nzval(gtk_ctx* ctx, double* nzval);
+int32_t gtk_copy_vector(gtk_ctx* ctx, double* b);
+
+/* ---- introspection (bench / tests) --------------------------------------------- */
+/* key: 0 kernels launched by the last numeric call   1 total kernels launched
+ *      2 device bytes held   3 nnz   4 n_coo (valid triplets)   5 fast-path id of last numeric call */
+int64_t gtk_info(const gtk_ctx* ctx, int32_t key);
+
+/* Per-kernel device timing of the LAST numeric call (CUDA events recorded on the ctx stream around
+ * every kernel launch while profiling is on).  gtk_profile_get synchronises the stream. */
+int32_t gtk_set_profiling(gtk_ctx* ctx, int32_t on);
+int32_t gtk_profile_count(const gtk_ctx* ctx);
+int32_t gtk_profile_get(gtk_ctx* ctx, int32_t i, char* name64, double* milliseconds);
+
+/* ---- multi-GPU: ghost-row summation over NCCL ------------------- */
+/* 128-byte ncclUniqueId produced on rank 0; the host broadcasts it by its own means. */
+int32_t gtk_comm_unique_id(void* id128);
+int32_t gtk_comm_init(gtk_ctx* ctx, int32_t rank, int32_t n_ranks, const void* id128);
+/* Rows (1-based, of the rank-local free numbering) [own_lo, own_hi] are owned by this rank.
+ * Ghost rows below/above are summed into their owner (previous/next rank) in rank order —
+ * PartitionedArrays.assemble! semantics.  Must be called after gtk_matrix_symbolic. */
+int32_t gtk_comm_setup_ghost_rows(gtk_ctx* ctx, int64_t own_lo, int64_t own_hi);
+/* Exchange + add ghost-row nzval and b contributions after a numeric call. */
+int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx);
+/* key: 0 ghost nz entries sent per exchange  1 ghost nz entries received  2 bytes moved per exchange */
+int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTK_ASSEMBLY_H */

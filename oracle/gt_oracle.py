@@ -1,0 +1,485 @@
+"""ORACLE — test infrastructure only.  PARITY UNPINNED (see below).
+
+CPU restatement of GalerkinToolkit.jl v0.6.3's assembly hot path, following the
+reference line by line.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s cpu_baseline / ``--impl reference`` legs may import this file.
+The product (``galerkintoolkit.jl_b200``) never does.
+
+Pinning status: the reference is pure Julia and cannot run in this container
+(no ``julia``, no depot, no network), and its test-suite holds **no golden
+matrices** for assembly.  This oracle is therefore pinned
+only by (i) re-derivation from the source lines cited on every function and
+(ii) the reference's own known-answer invariants, checked in
+``tests/test_oracle_invariants.py``: sum(M)=|Ω|, sum(b)=∫f
+(test/problems_tests.jl:53-57), tabulator(nodes)=I (test/space_tests.jl:218-220),
+quadrature weights sum (test/integration_tests.jl:28-34), dof counts
+(test/assembly_tests.jl:72-73), manufactured Poisson solution
+(test/problems_tests.jl:96-105).  Entry-level parity with a running reference is
+"unpinned" until a Julia-equipped box dumps colptr/rowval/nzval fixtures.
+
+Third-party algorithms restated (not vendored in /root/reference; compat pins of
+Project.toml:39-63): StaticArrays 1.x closed-form ``det``/``\\`` for 2x2 and 3x3
+SMatrix, SparseArrays ``sparse(I,J,V,m,n)`` (column-major, rows sorted, duplicates
+summed in input order, explicit zeros kept), PartitionedArrays 0.5.4
+``sparse_matrix``/``dense_vector`` (skip indices < 1), FastGaussQuadrature
+``gausslegendre``.
+
+All citations are relative to /root/reference/src.  Arithmetic is vectorised
+over *cells only*; per cell the operation order is exactly the scalar order of
+the reference (numpy elementwise ops are IEEE-754 and are not FMA-contracted).
+"""
+from __future__ import annotations
+
+import itertools
+import numpy as np
+
+FREE, DIRICHLET = 1, 2
+
+# ---------------------------------------------------------------------------
+# Literal mesh + numbering restatements (small sizes; python loops)
+# ---------------------------------------------------------------------------
+SIMPLEX_NODES = {2: [[1, 2, 3], [4, 3, 2]],
+                 3: [[1, 2, 3, 7], [1, 2, 5, 7], [2, 3, 4, 7], [2, 4, 7, 8], [2, 5, 6, 7], [2, 6, 7, 8]]}  # domain.jl:322-336
+
+# local faces of the reference cube / simplex: domain.jl:224, 252-255, 452-457
+CUBE_FACES = {
+    2: [[[1], [2], [3], [4]], [[1, 2], [3, 4], [1, 3], [2, 4]]],
+    3: [[[i] for i in range(1, 9)],
+        [[1, 2], [3, 4], [1, 3], [2, 4], [5, 6], [7, 8], [5, 7], [6, 8], [1, 5], [3, 7], [2, 6], [4, 8]],
+        [[1, 2, 3, 4], [5, 6, 7, 8], [1, 2, 5, 6], [3, 4, 7, 8], [1, 3, 5, 7], [2, 4, 6, 8]]],
+}
+
+
+def cartesian_chain(domain, cells_per_dir, simplexify=False):
+    """cartesian_mesh.jl:213-263 (hex) / :265-328 (simplices), loop for loop.
+    Returns coords [n,D] and cell_nodes (list of lists, 1-based)."""
+    D = len(cells_per_dir)
+    pmin = [domain[2 * d] for d in range(D)]
+    pmax = [domain[2 * d + 1] for d in range(D)]
+    h = [(pmax[d] - pmin[d]) / cells_per_dir[d] for d in range(D)]
+    npd = [c + 1 for c in cells_per_dir]
+
+    def lin(ci, dims):  # LinearIndices, 1-based, first index fastest
+        li, s = 0, 1
+        for d in range(len(dims)):
+            li += (ci[d] - 1) * s
+            s *= dims[d]
+        return li + 1
+
+    def cis(dims):      # CartesianIndices iteration order (first fastest), 1-based tuples
+        for t in itertools.product(*[range(1, n + 1) for n in reversed(dims)]):
+            yield tuple(reversed(t))
+
+    lnode_cis = [tuple(reversed(t)) for t in itertools.product(*[range(0, 2)] * D)]
+    cell_nodes = []
+    for cell_ci in cis(cells_per_dir):
+        cl = [lin(tuple(cell_ci[d] + ln[d] for d in range(D)), npd) for ln in lnode_cis]
+        if simplexify:
+            for lnodes in SIMPLEX_NODES[D]:
+                cell_nodes.append([cl[i - 1] for i in lnodes])
+        else:
+            cell_nodes.append(cl)
+    coords = np.zeros((int(np.prod(npd)), D))
+    for node_li, node_ci in enumerate(cis(npd)):
+        for d in range(D):
+            coords[node_li, d] = pmin[d] + h[d] * (node_ci[d] - 1)
+    return coords, cell_nodes
+
+
+def boundary_0faces(cell_nodes, nnodes, D):
+    """cartesian_mesh.jl:107-166 for d=0: nodes touched by exactly one cell,
+    enumerated cell-major then local-vertex order."""
+    node_to_n = [0] * (nnodes + 1)
+    for nodes in cell_nodes:
+        for n in nodes:
+            node_to_n[n] += 1
+    out = []
+    for nodes in cell_nodes:
+        for n in nodes:              # local 0-faces are the local nodes in order
+            if node_to_n[n] <= 1:    # nmax = 2^0
+                out.append(n)
+    return out
+
+
+def vertex_ids(cell_nodes, nnodes, preexisting_0faces):
+    """topology.jl:1034-1097 (create_vertices!)."""
+    node_vertex = [0] * (nnodes + 1)
+    for nodes in cell_nodes:
+        for n in nodes:
+            node_vertex[n] = -1
+    v = 0
+    for n in preexisting_0faces:
+        if node_vertex[n] == -1:
+            v += 1
+            node_vertex[n] = v
+    for n in range(1, nnodes + 1):
+        if node_vertex[n] == -1:
+            v += 1
+            node_vertex[n] = v
+    return node_vertex[1:]
+
+
+def q1_space(domain, cells_per_dir, dirichlet_sides=None, simplexify=False, n_comp=1):
+    """lagrange_space(Ω,1;dirichlet_boundary) on cartesian_mesh: space.jl:299-535.
+    One own dof per vertex ⇒ dof = vertex id (:348-417); Dirichlet tagging of the
+    dofs of boundary (D-1)-faces (:477-511) and stable partition (:512-524, :910-920).
+    ``dirichlet_sides``: None (no BC) | "boundary" | list of 1-based box-side ids."""
+    D = len(cells_per_dir)
+    coords, cell_nodes = cartesian_chain(domain, cells_per_dir, simplexify)
+    nn = coords.shape[0]
+    if all(c == 1 for c in cells_per_dir) and not simplexify:
+        pre = list(cell_nodes[0])
+    else:
+        pre = boundary_0faces(cell_nodes, nn, D) if not simplexify else _simplex_boundary_0faces(cells_per_dir)
+    vert = vertex_ids(cell_nodes, nn, pre)
+    scal = [[vert[n - 1] for n in nodes] for nodes in cell_nodes]
+    tag = [0] * nn
+    if dirichlet_sides is not None:
+        npd = [c + 1 for c in cells_per_dir]
+        sides = range(1, 2 * D + 1) if dirichlet_sides == "boundary" else dirichlet_sides
+        for node in range(nn):
+            idx, r = [], node
+            for d in range(D):
+                idx.append(r % npd[d]); r //= npd[d]
+            for s in sides:
+                axis = D - 1 - (s - 1) // 2
+                if idx[axis] == ((npd[axis] - 1) if (s - 1) % 2 == 1 else 0):
+                    tag[vert[node] - 1] = 1
+    # vector-valued: dof = (node-1)*n_comp + c  (space.jl:1267-1271)
+    ndofs = nn * n_comp
+    dof_tag = [tag[(d // n_comp)] for d in range(ndofs)]
+    free = [d for d in range(ndofs) if dof_tag[d] == 0]
+    diri = [d for d in range(ndofs) if dof_tag[d] != 0]
+    perm = [0] * ndofs
+    for i, d in enumerate(free):
+        perm[d] = i + 1
+    for i, d in enumerate(diri):
+        perm[d] = -(i + 1)
+    cell_dofs = [[perm[(s - 1) * n_comp + c] for s in row for c in range(n_comp)] for row in scal]
+    return dict(coords=coords, cell_nodes=np.array(cell_nodes, dtype=np.int32),
+                cell_dofs=np.array(cell_dofs, dtype=np.int32), n_free=len(free), n_dirichlet=len(diri))
+
+
+def _simplex_boundary_0faces(cells_per_dir):
+    """structured_simplex_mesh_with_boundary keeps the same 2^D box corners as 0-faces
+    (cartesian_mesh.jl:330-461: boundary built from the hex chain), lexicographic."""
+    D = len(cells_per_dir)
+    npd = [c + 1 for c in cells_per_dir]
+    out = []
+    for ln in range(2 ** D):
+        li, s = 0, 1
+        for d in range(D):
+            li += ((ln >> d) & 1) * (npd[d] - 1) * s
+            s *= npd[d]
+        out.append(li + 1)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# Reference element / quadrature / tabulation
+# ---------------------------------------------------------------------------
+def monomial_exponents(D, order, kind):
+    """space.jl:1127-1145."""
+    out = []
+    for t in itertools.product(*[range(order + 1)] * D):
+        e = tuple(reversed(t))
+        if kind == "P" and sum(e) > order:
+            continue
+        out.append(e)
+    return out
+
+
+def tabulate(D, order, kind, points):
+    """space.jl:960-970 + accessors.jl:486-496: value and gradient tables [p][dof]."""
+    exps = monomial_exponents(D, order, kind)
+    nodes = [[e[d] / order for d in range(D)] for e in exps]
+
+    def mono(e, x):
+        v = 1.0
+        for d in range(D):
+            v *= x[d] ** e[d]
+        return v
+
+    def dmono(e, x, k):
+        v = 1.0
+        for d in range(D):
+            if d == k:
+                v *= (e[d] * x[d] ** (e[d] - 1)) if e[d] > 0 else 0.0
+            else:
+                v *= x[d] ** e[d]
+        return v
+    A = np.array([[mono(e, x) for e in exps] for x in nodes])
+    B = np.linalg.solve(A, np.eye(len(exps)))
+    C = np.array([[mono(e, x) for e in exps] for x in points])
+    N = C @ B
+    dN = np.zeros((len(points), len(exps), D))
+    for k in range(D):
+        Ck = np.array([[dmono(e, x, k) for e in exps] for x in points])
+        dN[:, :, k] = Ck @ B
+    return N, dN
+
+
+def tensor_gauss(D, degree):
+    """quadrature.jl:60-106."""
+    n = int(np.ceil((degree + 1) / 2))
+    x, w = np.polynomial.legendre.leggauss(n)
+    x = 0.5 * x + 0.5
+    w = 0.5 * w
+    pts, wts = [], []
+    for t in itertools.product(*[range(n)] * D):
+        ci = tuple(reversed(t))
+        pts.append([x[i] for i in ci])
+        ww = 1.0
+        for i in ci:
+            ww *= w[i]
+        wts.append(ww)
+    return np.array(pts), np.array(wts)
+
+
+# ---------------------------------------------------------------------------
+# StaticArrays closed forms
+# ---------------------------------------------------------------------------
+def _det(J):
+    """StaticArrays det: 2x2 a11*a22 - a12*a21 ; 3x3 x0 . (x1 × x2) by columns."""
+    D = J.shape[-1]
+    if D == 1:
+        return J[..., 0, 0]
+    if D == 2:
+        return J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+    x0, x1, x2 = J[..., :, 0], J[..., :, 1], J[..., :, 2]
+    c0 = x1[..., 1] * x2[..., 2] - x1[..., 2] * x2[..., 1]
+    c1 = x1[..., 2] * x2[..., 0] - x1[..., 0] * x2[..., 2]
+    c2 = x1[..., 0] * x2[..., 1] - x1[..., 1] * x2[..., 0]
+    return x0[..., 0] * c0 + x0[..., 1] * c1 + x0[..., 2] * c2
+
+
+def _matmul_small(A, B):
+    """SMatrix product, sequential k-sum."""
+    n, m, k = A.shape[-2], B.shape[-1], A.shape[-1]
+    out = np.zeros(A.shape[:-2] + (n, m))
+    for i in range(n):
+        for j in range(m):
+            acc = A[..., i, 0] * B[..., 0, j]
+            for kk in range(1, k):
+                acc = acc + A[..., i, kk] * B[..., kk, j]
+            out[..., i, j] = acc
+    return out
+
+
+def change_of_measure(J):
+    """quadrature.jl:4-6: sqrt(det(transpose(J)*J))."""
+    Jt = np.swapaxes(J, -1, -2)
+    return np.sqrt(_det(_matmul_small(Jt, J)))
+
+
+def _solve(a, b):
+    """StaticArrays ``a \\ b`` for 2x2 / 3x3 (Cramer / adjugate closed form, one det)."""
+    D = a.shape[-1]
+    d = _det(a)
+    if D == 1:
+        return b / a[..., 0, :]
+    if D == 2:
+        return np.stack([(a[..., 1, 1] * b[..., 0] - a[..., 0, 1] * b[..., 1]) / d,
+                         (a[..., 0, 0] * b[..., 1] - a[..., 1, 0] * b[..., 0]) / d], axis=-1)
+    A = lambda i, j: a[..., i - 1, j - 1]
+    B = lambda i: b[..., i - 1]
+    r1 = ((A(2, 2) * A(3, 3) - A(2, 3) * A(3, 2)) * B(1) + (A(1, 3) * A(3, 2) - A(1, 2) * A(3, 3)) * B(2)
+          + (A(1, 2) * A(2, 3) - A(1, 3) * A(2, 2)) * B(3)) / d
+    r2 = ((A(2, 3) * A(3, 1) - A(2, 1) * A(3, 3)) * B(1) + (A(1, 1) * A(3, 3) - A(1, 3) * A(3, 1)) * B(2)
+          + (A(1, 3) * A(2, 1) - A(1, 1) * A(2, 3)) * B(3)) / d
+    r3 = ((A(2, 1) * A(3, 2) - A(2, 2) * A(3, 1)) * B(1) + (A(1, 2) * A(3, 1) - A(1, 1) * A(3, 2)) * B(2)
+          + (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) * B(3)) / d
+    return np.stack([r1, r2, r3], axis=-1)
+
+
+def _dot(a, b):
+    acc = a[..., 0] * b[..., 0]
+    for k in range(1, a.shape[-1]):
+        acc = acc + a[..., k] * b[..., k]
+    return acc
+
+
+# ---------------------------------------------------------------------------
+# Per-point geometry (accessors.jl:941-968, 1000-1007, 1365-1368)
+# ---------------------------------------------------------------------------
+def point_geometry(coords, cell_nodes, dM_q):
+    """J = Σ_node x_node ⊗ ∇̂M_node (sequential in local-node order), for all cells."""
+    nc, nln = cell_nodes.shape
+    D = coords.shape[1]
+    J = np.zeros((nc, D, dM_q.shape[1]))
+    for n in range(nln):
+        x = coords[cell_nodes[:, n] - 1]                 # [nc, D]
+        J = J + x[:, :, None] * dM_q[n][None, None, :]   # outer(x, ref∇m)  (quadrature.jl:2)
+    return J
+
+
+# ---------------------------------------------------------------------------
+# Forms: integrand(r, c, q) following compiler.jl:1879-1894 / A.8b
+# ---------------------------------------------------------------------------
+LAPLACE, MASS, ELASTICITY = 1, 2, 3
+SOURCE_CONST, SOURCE_NODAL, SOURCE_QP = 101, 102, 103
+
+
+def element_matrices(form, coords, cell_nodes, tab, n_comp=1, alpha=1.0, lam=1.0, mu=1.0):
+    """be[cell, r, c] = Σ_q ((α·integrand(u=φ_r, v=φ_c))·dV_q), q outermost, then c, then r
+    (compiler.jl:1865-1900; problems.jl:55-63)."""
+    w, N, dN, dM = tab["w"], tab["N"], tab["dN"], tab["dM"]
+    nc = cell_nodes.shape[0]
+    nq, nls = N.shape
+    D = coords.shape[1]
+    nld = nls * n_comp
+    be = np.zeros((nc, nld, nld))
+    for q in range(nq):
+        J = point_geometry(coords, cell_nodes, dM[q])
+        dV = change_of_measure(J) * w[q]                                        # accessors.jl:1000-1007
+        Jt = np.swapaxes(J, -1, -2)
+        if form in (LAPLACE, ELASTICITY):
+            g = [_solve(Jt, np.broadcast_to(dN[q, a], (nc, D))) for a in range(nls)]   # accessors.jl:1365-1368
+        for c in range(nld):
+            for r in range(nld):
+                a, i = divmod(r, n_comp)      # dof = (node-1)*n_comp + comp  (space.jl:1267-1271)
+                b, j = divmod(c, n_comp)
+                if form == LAPLACE:           # ∇u:∇v = δ_ij ∇s_a·∇s_b for vector-valued spaces
+                    v = (alpha * (_dot(g[a], g[b]) if i == j else np.zeros(nc))) * dV
+                elif form == MASS:            # u·v = δ_ij s_a s_b
+                    v = (alpha * ((N[q, a] * N[q, b]) if i == j else 0.0)) * dV
+                elif form == ELASTICITY:
+                    # σ(ε(u)):ε(v), u = s_a e_i, v = s_b e_j, isotropic (λ, μ)
+                    t = lam * (g[a][:, i] * g[b][:, j]) + mu * (g[a][:, j] * g[b][:, i])
+                    if i == j:
+                        t = t + mu * _dot(g[a], g[b])
+                    v = (alpha * t) * dV
+                else:
+                    raise ValueError(form)
+                be[:, r, c] += v
+    return be
+
+
+def element_vectors(form, coords, cell_nodes, tab, n_comp=1, alpha=1.0, f_const=None, f_nodal=None, f_qp=None):
+    """be[cell, i] = Σ_q ((α·(f(x_q)·φ_i))·dV_q)  (compiler.jl:1958-1979)."""
+    w, N, M, dM = tab["w"], tab["N"], tab["M"], tab["dM"]
+    nc = cell_nodes.shape[0]
+    nq, nls = N.shape
+    nld = nls * n_comp
+    be = np.zeros((nc, nld))
+    for q in range(nq):
+        J = point_geometry(coords, cell_nodes, dM[q])
+        dV = change_of_measure(J) * w[q]
+        if form == SOURCE_CONST:
+            f = np.broadcast_to(np.asarray(f_const, dtype=np.float64).reshape(1, -1), (nc, n_comp))
+        elif form == SOURCE_NODAL:   # f_h(x_q) = Σ_node f_node M_node(ξ_q), sequential
+            f = np.zeros((nc, n_comp))
+            fn = np.asarray(f_nodal, dtype=np.float64).reshape(coords.shape[0], n_comp)
+            for n in range(cell_nodes.shape[1]):
+                f = f + fn[cell_nodes[:, n] - 1] * M[q, n]
+        elif form == SOURCE_QP:
+            f = np.asarray(f_qp, dtype=np.float64).reshape(nc, nq, n_comp)[:, q, :]
+        else:
+            raise ValueError(form)
+        for i in range(nld):
+            a, comp = divmod(i, n_comp)
+            be[:, i] += (alpha * (f[:, comp] * N[q, a])) * dV
+    return be
+
+
+# ---------------------------------------------------------------------------
+# Scatter + compression
+# ---------------------------------------------------------------------------
+def _skip(d, fd):
+    """assembly.jl:155-157."""
+    return ((d > 0) & (fd == DIRICHLET)) | ((d < 0) & (fd == FREE))
+
+
+def coo_matrix(be, cell_dofs_rows, cell_dofs_cols, fd_rows=FREE, fd_cols=FREE):
+    """contribute!(::MatrixAllocation) assembly.jl:189-208 → COO push :545-556.
+    Order: cell-major; within a cell column j outer, row i inner; skipped by sign."""
+    nc, ni, nj = be.shape
+    I = np.broadcast_to(cell_dofs_rows[:, :, None], (nc, ni, nj))
+    Jd = np.broadcast_to(cell_dofs_cols[:, None, :], (nc, ni, nj))
+    # memory order must be (cell, j, i): transpose to [cell, j, i]
+    I = np.transpose(I, (0, 2, 1)).reshape(-1)
+    Jd = np.transpose(Jd, (0, 2, 1)).reshape(-1)
+    V = np.transpose(be, (0, 2, 1)).reshape(-1)
+    keep = ~(_skip(I, fd_rows) | _skip(Jd, fd_cols))
+    mi = 1 if fd_rows == FREE else -1
+    mj = 1 if fd_cols == FREE else -1
+    return (mi * I[keep]).astype(np.int32), (mj * Jd[keep]).astype(np.int32), V[keep]
+
+
+def sparse_csc(I, J, V, m, n):
+    """Julia sparse(I,J,V,m,n) via PartitionedArrays.sparse_matrix (assembly.jl:571-575):
+    CSC, rows sorted inside each column, duplicates summed left-to-right in input order,
+    explicit zeros kept.  Returns 1-based Int32 colptr/rowval and Float64 nzval."""
+    I = np.asarray(I, dtype=np.int64)
+    J = np.asarray(J, dtype=np.int64)
+    key = (J - 1) * m + (I - 1)
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    vs = np.asarray(V, dtype=np.float64)[order]
+    head = np.ones(ks.size, dtype=bool)
+    head[1:] = ks[1:] != ks[:-1]
+    starts = np.flatnonzero(head)
+    nnz = starts.size
+    lens = np.diff(np.append(starts, ks.size))
+    nzval = np.zeros(nnz)
+    if nnz:
+        nzval[:] = vs[starts]
+        for k in range(1, int(lens.max())):
+            sel = lens > k
+            nzval[sel] = nzval[sel] + vs[starts[sel] + k]     # sequential, input order
+    ukeys = ks[starts]
+    rowval = (ukeys % m + 1).astype(np.int32)
+    cols = ukeys // m
+    colptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(colptr, cols + 1, 1)
+    colptr = (np.cumsum(colptr) + 1).astype(np.int32)
+    return colptr, rowval, nzval
+
+
+def coo_vector(be, cell_dofs, fd=FREE):
+    """contribute!(::VectorAllocation) assembly.jl:175-187 → :535-543."""
+    I = cell_dofs.reshape(-1)
+    V = be.reshape(-1)
+    keep = ~_skip(I, fd)
+    m = 1 if fd == FREE else -1
+    return (m * I[keep]).astype(np.int32), V[keep]
+
+
+def dense_vector(I, V, n):
+    """PartitionedArrays.dense_vector (assembly.jl:558-569): b[i] += v sequentially in COO order."""
+    I = np.asarray(I, dtype=np.int64) - 1
+    order = np.argsort(I, kind="stable")
+    Is, Vs = I[order], np.asarray(V, dtype=np.float64)[order]
+    b = np.zeros(n)
+    if Is.size == 0:
+        return b
+    head = np.ones(Is.size, dtype=bool)
+    head[1:] = Is[1:] != Is[:-1]
+    starts = np.flatnonzero(head)
+    lens = np.diff(np.append(starts, Is.size))
+    acc = np.zeros(starts.size) + Vs[starts]       # 0.0 + v is exact
+    for k in range(1, int(lens.max())):
+        sel = lens > k
+        acc[sel] = acc[sel] + Vs[starts[sel] + k]
+    b[Is[starts]] = acc
+    return b
+
+
+# ---------------------------------------------------------------------------
+# Whole path: assemble_matrix / assemble_vector (problems.jl:244-274, 319-350)
+# ---------------------------------------------------------------------------
+def assemble_matrix(form, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, tab, n_comp=1,
+                    free_or_dirichlet=(FREE, FREE), **params):
+    be = element_matrices(form, coords, cell_nodes, tab, n_comp=n_comp, **params)
+    fr, fcn = free_or_dirichlet
+    I, J, V = coo_matrix(be, cell_dofs, cell_dofs, fr, fcn)
+    m = n_free if fr == FREE else n_dirichlet
+    n = n_free if fcn == FREE else n_dirichlet
+    return sparse_csc(I, J, V, m, n)
+
+
+def assemble_vector(form, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, tab, n_comp=1,
+                    free_or_dirichlet=FREE, **params):
+    be = element_vectors(form, coords, cell_nodes, tab, n_comp=n_comp, **params)
+    I, V = coo_vector(be, cell_dofs, free_or_dirichlet)
+    return dense_vector(I, V, n_free if free_or_dirichlet == FREE else n_dirichlet)

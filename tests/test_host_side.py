@@ -1,0 +1,129 @@
+"""CPU tests of the host side: input preparation vs the oracle's literal restatement, form
+recognition, the C-ABI library (loads, exports every declared symbol, fails loudly without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gt_oracle as O
+import gtk_b200
+
+H, GT, E = gtk_b200.hostprep, gtk_b200.GT, gtk_b200.engine
+
+
+@pytest.mark.parametrize("cells,domain", [((4, 3), (0, 1, 0, 1)), ((3, 2, 4), (0, 1, 0, 2, 0, 1)), ((2, 2, 2), (0, 1, 0, 1, 0, 1)), ((1, 1), (0, 1, 0, 1))])
+@pytest.mark.parametrize("bc", [None, "boundary", [1]])
+@pytest.mark.parametrize("n_comp", [1, 2])
+def test_hostprep_matches_literal_numbering(cells, domain, bc, n_comp):
+    o = O.q1_space(domain, cells, bc, n_comp=n_comp)
+    mesh = H.cartesian_mesh(domain, cells)
+    V = H.lagrange_space(mesh, 1, bc, n_comp)
+    assert np.array_equal(mesh.cell_nodes, o["cell_nodes"])
+    assert np.array_equal(mesh.node_coordinates, o["coords"])
+    assert np.array_equal(V.cell_dofs, o["cell_dofs"])
+    assert (V.n_free, V.n_dirichlet) == (o["n_free"], o["n_dirichlet"])
+
+
+def test_simplexified_mesh_matches_literal():
+    for cells, dom in (((3, 2), (0, 1, 0, 1)), ((2, 3, 2), (0, 1, 0, 1, 0, 1))):
+        coords, cn = O.cartesian_chain(dom, cells, simplexify=True)
+        mesh = H.cartesian_mesh(dom, cells, simplexify=True)
+        assert np.array_equal(mesh.cell_nodes, np.array(cn, dtype=np.int32))
+        assert np.array_equal(mesh.node_coordinates, coords)
+
+
+def test_closed_form_q1_dofs_full_dirichlet():
+    # free id of interior node (i,j,k) = 1+(i-1)+(n1-1)(j-1)+(n1-1)(n2-1)(k-1)
+    mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (5, 4, 3))
+    V = H.lagrange_space(mesh, 1, "boundary")
+    cell = 1 + 1 * 5 + 1 * 20          # cell (1,1,1) 0-based: all 8 nodes... node (1..2,1..2,1..2)
+    d = V.cell_dofs[cell]
+    assert d[0] == 1 + 0 + 4 * 0 + 12 * 0
+    assert d[1] == 2 and d[2] == 1 + 4 and d[4] == 1 + 12
+    assert V.n_free == 4 * 3 * 2
+
+
+def test_tabulation_and_quadrature_match_oracle():
+    for D in (2, 3):
+        q = H.quadrature(D, False, 2)
+        x, w = O.tensor_gauss(D, 2)
+        assert np.array_equal(q.coordinates, x) and np.array_equal(q.weights, w)
+        N, dN = H.tabulate(D, 1, "Q", q.coordinates)
+        N2, dN2 = O.tabulate(D, 1, "Q", x)
+        assert np.allclose(N, N2, rtol=0, atol=1e-15) and np.allclose(dN, dN2, rtol=0, atol=1e-15)
+
+
+def test_partition_slab_inputs_cover_the_global_mesh():
+    full = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (4, 4, 6))
+    parts = [H.cartesian_mesh((0, 1, 0, 1, 0, 1), (4, 4, 6), z_cell_range=r) for r in ((0, 2), (2, 6))]
+    assert np.array_equal(np.vstack([p.cell_nodes for p in parts]), full.cell_nodes)
+
+
+# ---- form recognition -----------------------------------------------------------------------
+def _space():
+    mesh = GT.cartesian_mesh((0, 1, 0, 1), (4, 4))
+    om = GT.interior(mesh)
+    V = GT.lagrange_space(om, 1, dirichlet_boundary=GT.boundary(mesh))
+    return mesh, om, V, GT.measure(om, 2)
+
+
+def test_form_recognition():
+    mesh, om, V, dom = _space()
+    u, v = GT.FormArgument(V, 2), GT.FormArgument(V, 1)
+    t = GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dom).contributions[0][0]
+    assert GT.recognise_bilinear(t) == (E.FORM_LAPLACE, dict(alpha=1.0))
+    t = GT.integrate(lambda x: 3.0 * (u(x) * v(x)), dom).contributions[0][0]
+    assert GT.recognise_bilinear(t) == (E.FORM_MASS, dict(alpha=3.0))
+    t = GT.integrate(lambda x: GT.isotropic_elasticity(2.0, 1.0)(u, v, x), dom).contributions[0][0]
+    assert GT.recognise_bilinear(t)[0] == E.FORM_ELASTICITY_ISO
+    f = GT.analytical_field(lambda x: x[0] + x[1])
+    form, params = GT.recognise_linear(GT.integrate(lambda x: f(x) * v(x), dom).contributions[0][0], V, dom)
+    assert form == E.FORM_SOURCE_QP and params["f_qp"].shape == (16, 4, 1)
+    form, params = GT.recognise_linear(GT.integrate(lambda x: 2.0 * v(x), dom).contributions[0][0], V, dom)
+    assert form == E.FORM_SOURCE_CONST and params["alpha"] == 2.0
+
+
+def test_unsupported_forms_raise_instead_of_falling_back():
+    mesh, om, V, dom = _space()
+    u, v = GT.FormArgument(V, 2), GT.FormArgument(V, 1)
+    with pytest.raises(GT.UnsupportedFormError):       # convection-like, non-symmetric
+        GT.recognise_bilinear(GT.integrate(lambda x: u(x) * GT.dot(GT.grad(v, x), GT.grad(v, x)), dom).contributions[0][0])
+    with pytest.raises(GT.UnsupportedFormError):
+        GT.recognise_bilinear(GT.integrate(lambda x: u(x) + v(x), dom).contributions[0][0])
+    with pytest.raises(GT.UnsupportedFormError):
+        GT.recognise_linear(GT.integrate(lambda x: GT.dot(GT.grad(v, x), GT.grad(v, x)), dom).contributions[0][0], V, dom)
+    with pytest.raises(GT.UnsupportedFormError):
+        GT.measure(GT.boundary(mesh), 2)
+
+
+# ---- the C-ABI library ----------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(built_library):
+    header = open(os.path.join(os.path.dirname(gtk_b200.PACKAGE_DIR), "include", "gtk_assembly.h")).read()
+    declared = set(re.findall(r"\b(gtk_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(E.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(built_library, name), name
+    assert built_library.gtk_version() >= 100
+
+
+def test_engine_fails_loudly_without_gpu(built_library):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(E.GtkError):
+        E.Engine(0)
+    with pytest.raises(E.GtkError):
+        mesh, om, V, dom = _space()
+        GT.assemble_matrix(lambda u, v: GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dom), float, V, V)
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, smoke() and bench.py's cpu_baseline leg may touch oracle/."""
+    pat = re.compile(r"^\s*(import\s+(gt_oracle|oracle)|from\s+(gt_oracle|oracle)[\s.]|#include\s+\".*oracle|.*dlopen.*oracle|.*CDLL.*oracle)", re.M)
+    for root, _, files in os.walk(gtk_b200.PACKAGE_DIR):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh", ".jl")):
+                src = open(os.path.join(root, f)).read()
+                assert not pat.search(src), f

@@ -1,0 +1,97 @@
+"""Pin the oracle with the reference's own known-answer invariants.
+The reference holds no golden matrices; these are the checks its test-suite makes."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import gt_oracle as O
+from util import oracle_matrix, oracle_vector, problem, tab_dict
+
+
+def _csc(colptr, rowval, nzval, m, n):
+    return sp.csc_matrix((nzval, rowval.astype(np.int64) - 1, colptr.astype(np.int64) - 1), shape=(m, n))
+
+
+def test_mass_and_source_sums_2x2_square():
+    # test/problems_tests.jl:48-57: Q1 on a 2x2 unit square: sum(M) ≈ 1, sum(b) ≈ 1
+    mesh, V, tab = problem((2, 2), bc=None)
+    cp, rv, nz = oracle_matrix(O.MASS, mesh, V, tab)
+    assert abs(nz.sum() - 1.0) < 1e-14
+    b = oracle_vector(O.SOURCE_CONST, mesh, V, tab, f_const=[1.0])
+    assert abs(b.sum() - 1.0) < 1e-14
+
+
+@pytest.mark.parametrize("cells,domain", [((4, 3), (0, 2, 0, 1)), ((3, 4, 2), (0, 1, 0, 2, 0, 3))])
+def test_mass_sum_is_volume_and_laplace_rowsums_vanish(cells, domain):
+    mesh, V, tab = problem(cells, bc=None, warp=0.2, domain=domain)
+    vol = np.prod([domain[2 * d + 1] - domain[2 * d] for d in range(len(cells))])
+    cp, rv, nz = oracle_matrix(O.MASS, mesh, V, tab)
+    assert abs(nz.sum() - vol) < 1e-12 * vol
+    cp, rv, nz = oracle_matrix(O.LAPLACE, mesh, V, tab)
+    A = _csc(cp, rv, nz, V.n_free, V.n_free)
+    assert np.abs(A.sum(axis=1)).max() < 1e-12 * np.abs(nz).max()
+    assert abs(A - A.T).max() == 0.0          # dot() is bitwise commutative ⇒ Ke bitwise symmetric (A.6)
+
+
+def test_quadrature_weights_sum_and_tabulator_identity():
+    # test/integration_tests.jl:28-34 ; test/space_tests.jl:218-220, 250-252
+    for D in (1, 2, 3):
+        for deg in (1, 2, 4, 6):
+            x, w = O.tensor_gauss(D, deg)
+            assert abs(w.sum() - 1.0) < 1e-14
+    for D, kind in ((2, "Q"), (3, "Q"), (2, "P"), (3, "P")):
+        for order in (1, 2, 3):
+            nodes = [[e[d] / order for d in range(D)] for e in O.monomial_exponents(D, order, kind)]
+            N, dN = O.tabulate(D, order, kind, nodes)
+            assert np.abs(N - np.eye(len(nodes))).max() < 1e-10
+            assert np.abs(dN.sum(axis=1)).max() < 1e-9      # partition of unity
+
+
+def test_dof_counts():
+    # 2x2x2 Q1 cube with full Dirichlet boundary: 1 free, 26 Dirichlet
+    o = O.q1_space((0, 1, 0, 1, 0, 1), (2, 2, 2), "boundary")
+    assert (o["n_free"], o["n_dirichlet"]) == (1, 26)
+    # corners are numbered first (topology.jl:1072-1078): without BC node 1 is dof 1, the far corner dof 8
+    o = O.q1_space((0, 1, 0, 1, 0, 1), (2, 2, 2), None)
+    assert o["cell_dofs"][0, 0] == 1 and o["cell_dofs"][-1, -1] == 8
+    assert o["cell_dofs"].max() == 27
+
+
+def test_pattern_counts_match_closed_form():
+    # nnz = (3m-2)^D with m free nodes per direction (Q1, full Dirichlet boundary)
+    for cells in ((8, 8), (6, 6, 6)):
+        mesh, V, tab = problem(cells, bc="boundary")
+        cp, rv, nz = oracle_matrix(O.LAPLACE, mesh, V, tab)
+        m = cells[0] - 1
+        assert rv.size == (3 * m - 2) ** len(cells)
+        assert cp[-1] - 1 == rv.size
+        # rows sorted inside each column, explicit zeros kept
+        for j in range(V.n_free):
+            seg = rv[cp[j] - 1: cp[j + 1] - 1]
+            assert np.all(np.diff(seg) > 0)
+
+
+def test_manufactured_poisson_solution():
+    """test/problems_tests.jl:86-105: u = x+y is reproduced exactly by Q1 (el2 ≈ 0) with
+    b = -Ad*xd (problems.jl:439-453)."""
+    mesh, V, tab = problem((6, 5), bc="boundary", warp=0.15)
+    cp, rv, nz = oracle_matrix(O.LAPLACE, mesh, V, tab)
+    A = _csc(cp, rv, nz, V.n_free, V.n_free)
+    cpd, rvd, nzd = oracle_matrix(O.LAPLACE, mesh, V, tab, fd=(O.FREE, O.DIRICHLET))
+    Ad = _csc(cpd, rvd, nzd, V.n_free, V.n_dirichlet)
+    u = lambda x: x[:, 0] + x[:, 1]
+    xd = u(V.dirichlet_dof_nodes)
+    x = spla.spsolve(A.tocsc(), -Ad @ xd)
+    assert np.abs(x - u(V.free_dof_nodes)).max() < 1e-12
+
+
+def test_sparse_combines_duplicates_in_input_order_and_keeps_zeros():
+    I = np.array([2, 1, 2, 2, 1], dtype=np.int32)
+    J = np.array([1, 1, 1, 1, 2], dtype=np.int32)
+    V = np.array([1e16, 3.0, 1.0, -1e16, 0.0])
+    cp, rv, nz = O.sparse_csc(I, J, V, 2, 2)
+    assert cp.tolist() == [1, 3, 4] and rv.tolist() == [1, 2, 1]
+    assert nz.tolist() == [3.0, (1e16 + 1.0) - 1e16, 0.0]      # left-to-right; explicit zero stays
+    b = O.dense_vector(np.array([2, 2, 1], dtype=np.int32), np.array([1e16, 1.0, 5.0]), 3)
+    assert b.tolist() == [5.0, 1e16 + 1.0, 0.0]
