@@ -1,9 +1,430 @@
-// Structured Q1 fast path (placeholder until the tile-plan kernels land): never claims a call.
+// Fast path for the headline workload: 3D Q1 hexahedra on a *topologically structured* mesh
+// (what GT.cartesian_mesh produces, cartesian_mesh.jl:213-263) with ARBITRARY node coordinates,
+// Dirichlet pattern and dof numbering; forms LAPLACE (+ SOURCE_CONST), Float64.
+//
+// One kernel does the whole numeric assembly (cell loop + contribute! + compress of the reference,
+// compiler.jl:1865-1917, assembly.jl:189-208, 571-588) with exactly the compulsory HBM traffic:
+// coordinates and dof ids in, nzval and b out — no COO staging, no atomics.
+//
+// k_q1hex_sweep: a CTA owns a BX x BY footprint of *nodes* (= matrix columns) and sweeps a z-range.
+//   per cell layer L (the cells between node layers L and L+1, including a one-cell halo ring in x,y):
+//     A) one thread per cell: lerped Jacobian columns, adjugate Gram tensors, sum-factorised
+//        Ke (36 unique entries) + be (8)  -> shared memory             [q1hex_math.cuh; FP64 pipe]
+//     B) one thread per (column, neighbour offset): gather the <=8 cell contributions of that
+//        matrix entry in increasing cell id — the reference's push order, so the sum is the
+//        same left-to-right sum Julia's sparse() performs — and write nzval[colptr[col]+slot];
+//        entries that also need the next cell layer wait in an 18-value/column pending buffer.
+//   The halo ring is recomputed by the neighbouring CTA (factor (BX+1)(BY+1)/(BX BY)); in exchange
+//   every nonzero is produced by exactly one thread in a fixed order: bit-reproducible, no fix-up pass.
 #include "gtk_internal.h"
-int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
-                       const gtk_form_params* pv, bool* handled) {
-  (void)ctx; (void)mform; (void)pm; (void)vform; (void)pv;
-  *handled = false;
+#include "q1hex_math.cuh"
+
+namespace {
+
+struct FastPlan {
+  int n1 = 0, n2 = 0, n3 = 0;        // cells per direction
+  int64_t node_off = 0;              // mesh node id of node (0,0,0), minus 1
+  int64_t n_nodes = 0;
+  int32_t* node_dof = nullptr;       // [n_nodes] signed 1-based dof id of every node
+  int32_t* dof_node = nullptr;       // [n_free]  node index of every free dof
+  uint8_t* slot_tbl = nullptr;       // [n_free][32] slot of neighbour offset o in the column, 255 = absent
+  bool ok = false;
+  bool tried = false;
+};
+
+__global__ void k_verify_structure(const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ cell_dofs,
+                                   int n1, int n2, int n3, int64_t node_off, int32_t* __restrict__ node_dof, int* bad) {
+  const int64_t nc = (int64_t)n1 * n2 * n3;
+  const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(c % n1), j = (int)((c / n1) % n2), k = (int)(c / ((int64_t)n1 * n2));
+    int64_t base = i + s1 * j + s2 * k;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      int64_t node = base + (v & 1) + s1 * ((v >> 1) & 1) + s2 * (v >> 2);
+      if ((int64_t)cell_nodes[c * 8 + v] != node + node_off + 1) *bad = 1;
+      node_dof[node] = cell_dofs[c * 8 + v];    // every writer of one node must agree (checked below)
+    }
+  }
+}
+
+__global__ void k_verify_node_dof(const int32_t* __restrict__ cell_dofs, int n1, int n2, int n3,
+                                  const int32_t* __restrict__ node_dof, int* bad) {
+  const int64_t nc = (int64_t)n1 * n2 * n3;
+  const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(c % n1), j = (int)((c / n1) % n2), k = (int)(c / ((int64_t)n1 * n2));
+    int64_t base = i + s1 * j + s2 * k;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      int64_t node = base + (v & 1) + s1 * ((v >> 1) & 1) + s2 * (v >> 2);
+      int d = cell_dofs[c * 8 + v];
+      if (node_dof[node] != d || d == 0) *bad = 1;
+    }
+  }
+}
+
+__global__ void k_dof_node(const int32_t* __restrict__ node_dof, int64_t n_nodes, int64_t n_free,
+                           int32_t* __restrict__ dof_node, int* bad) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < n_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    int d = node_dof[n];
+    if (d > 0) {
+      if (d > n_free) *bad = 1; else dof_node[d - 1] = (int32_t)n;
+    }
+  }
+}
+
+// slot_tbl[col][o]: position of the row dof of neighbour offset o inside CSC column col
+__global__ void k_slot_table(const int32_t* __restrict__ node_dof, const int32_t* __restrict__ dof_node,
+                             const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, int64_t n_free,
+                             int n1, int n2, int n3, uint8_t* __restrict__ slot_tbl, int* bad) {
+  const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < n_free; col += (int64_t)gridDim.x * blockDim.x) {
+    int64_t node = dof_node[col];
+    if (node < 0 || node_dof[node] != col + 1) { *bad = 1; continue; }   // not a bijection (e.g. periodic dofs)
+    int i = (int)(node % s1), j = (int)((node / s1) % (n2 + 1)), k = (int)(node / s2);
+    const int64_t p0 = colptr[col], p1 = colptr[col + 1];
+    int found = 0;
+    for (int o = 0; o < 27; ++o) {
+      int dx = o % 3 - 1, dy = (o / 3) % 3 - 1, dz = o / 9 - 1;
+      int ii = i + dx, jj = j + dy, kk = k + dz;
+      uint8_t slot = 255;
+      if (ii >= 0 && ii <= n1 && jj >= 0 && jj <= n2 && kk >= 0 && kk <= n3) {
+        int r = node_dof[ii + s1 * jj + s2 * kk];
+        if (r > 0) {
+          for (int64_t p = p0; p < p1; ++p)
+            if (rowval[p] == r) { slot = (uint8_t)(p - p0); ++found; break; }
+          if (slot == 255) *bad = 1;
+        }
+      }
+      slot_tbl[col * 32 + o] = slot;
+    }
+    if (found != (int)(p1 - p0)) *bad = 1;    // the column has rows this stencil does not produce
+  }
+}
+
+struct SweepArgs {
+  const double* xyz;
+  const int32_t* node_dof;
+  const int64_t* colptr;
+  const uint8_t* slot_tbl;
+  double* nzval;
+  double* b;
+  int n1, n2, n3;
+  int seg_len;
+  double alpha, fscale;
+  int do_matrix, do_vector;
+};
+
+template <int BX, int BY>
+struct Cfg {
+  static constexpr int CX = BX + 1, CY = BY + 1, NC = CX * CY, NN = BX * BY;
+  static constexpr int NT = ((NC + 31) / 32) * 32;
+  static constexpr int KSTR = 45;   // doubles per cell slot: 36 Ke + 8 be + 1 pad (odd stride: conflict-free row reads)
+  // KeS[NC][KSTR] | Pend[18][NN] | PendB[NN] | OutS[NN][27] | ColBase[NN] (i64) | ColIdx[NN] (i32)
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)NC * KSTR + (size_t)NN * 18 + NN + (size_t)NN * 27) +
+                                 sizeof(long long) * NN + sizeof(int) * NN;
+};
+
+// one matrix entry (column = node of the footprint, row = its neighbour at offset O): sum of the <= 4 cells of
+// this layer that contain both nodes, in increasing cell id (decreasing e) = the reference's push order.
+//   acc: contributions where the column node is a BOTTOM node of the cell (finalises node layer L)
+//   hi : contributions where it is a TOP node (first part of node layer L+1, parked in Pend)
+template <int O, int CXK, int KSTR>
+__device__ __forceinline__ void gather_entry(const double* __restrict__ base, double& acc, double& hi) {
+  constexpr int dx = O % 3 - 1, dy = (O / 3) % 3 - 1, dz = O / 9 - 1;
+#pragma unroll
+  for (int e2 = 1; e2 >= 0; --e2)
+#pragma unroll
+    for (int e1 = 1; e1 >= 0; --e1) {
+      const int r1 = e1 + dx, r2 = e2 + dy;
+      if (r1 < 0 || r1 > 1 || r2 < 0 || r2 > 1) continue;
+      const double* ke = base - (e1 + CXK * e2) * KSTR;
+      if (dz <= 0) hi += ke[q1hex::sym(r1 + 2 * r2 + 4 * (1 + dz), e1 + 2 * e2 + 4)];
+      if (dz >= 0) acc += ke[q1hex::sym(r1 + 2 * r2 + 4 * dz, e1 + 2 * e2)];
+    }
+}
+
+template <int BX, int BY, int O>
+struct GatherAll {
+  using C = Cfg<BX, BY>;
+  static __device__ __forceinline__ void run(const double* __restrict__ base, double* __restrict__ pend,
+                                             double* __restrict__ out) {
+    constexpr int dz = O / 9 - 1;
+    double acc = 0.0, hi = 0.0;
+    if (dz <= 0) acc = pend[O * C::NN];
+    gather_entry<O, C::CX, C::KSTR>(base, acc, hi);
+    if (dz <= 0) pend[O * C::NN] = hi;
+    out[O] = acc;
+    if constexpr (O + 1 < 27) GatherAll<BX, BY, O + 1>::run(base, pend, out);
+  }
+};
+
+template <int BX, int BY, int MINB>
+__global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs a) {
+  using C = Cfg<BX, BY>;
+  extern __shared__ double sm[];
+  double* KeS = sm;                                   // [NC][KSTR] element matrices of the current cell layer
+  double* Pend = KeS + C::NC * C::KSTR;               // [18][NN]   entries waiting for the next cell layer
+  double* PendB = Pend + C::NN * 18;                  // [NN]
+  double* OutS = PendB + C::NN;                       // [NN][27]   finished columns of node layer L (transpose buffer)
+  long long* ColBase = (long long*)(OutS + C::NN * 27);   // [NN] colptr of each node's column, -1 = none
+  int* ColIdx = (int*)(ColBase + C::NN);              // [NN]
+
+  const int t = threadIdx.x;
+  const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY;
+  const int kz0 = blockIdx.z * a.seg_len;
+  const int kz1 = min(kz0 + a.seg_len, a.n3 + 1);
+  const int n1 = a.n1, n2 = a.n2, n3 = a.n3;
+  const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  const int cx = t % C::CX, cy = t / C::CX;
+  const int ci = i0 - 1 + cx, cj = j0 - 1 + cy;
+  const bool has_slot = t < C::NC;
+  const bool cell_ok = has_slot && ci >= 0 && ci < n1 && cj >= 0 && cj < n2;
+  double* myslot = KeS + (has_slot ? t : 0) * C::KSTR;
+  // gather role: thread t < NN owns node (li, lj) of the footprint
+  const int li = t % BX, lj = t / BX;
+  const bool node_thread = t < C::NN;
+  const bool node_in_mesh = node_thread && (i0 + li <= n1) && (j0 + lj <= n2);
+  const double* gbase = KeS + ((li + 1) + C::CX * (lj + 1)) * C::KSTR;
+
+  // cells outside the mesh never compute: their slots stay zero, so the gather needs no bounds checks
+  if (has_slot) {
+#pragma unroll
+    for (int e = 0; e < C::KSTR; ++e) myslot[e] = 0.0;
+  }
+  for (int idx = t; idx < C::NN * 18; idx += C::NT) Pend[idx] = 0.0;
+  for (int idx = t; idx < C::NN; idx += C::NT) PendB[idx] = 0.0;
+
+  for (int L = kz0 - 1; L < kz1; ++L) {
+    const bool layer_ok = L >= 0 && L < n3;
+    // ---- A) element matrices of cell layer L ----
+    if (cell_ok) {
+      if (layer_ok) {
+        double X[8][3];
+        const int64_t base = ci + s1 * cj + s2 * L;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const double* p = a.xyz + 3 * (base + (v & 1) + s1 * ((v >> 1) & 1) + s2 * (v >> 2));
+          X[v][0] = __ldg(p); X[v][1] = __ldg(p + 1); X[v][2] = __ldg(p + 2);
+        }
+        q1hex::Cell<double> g;
+        q1hex::geometry<double>(X, g);
+        if (a.do_matrix) {
+          double Ke[36];
+          q1hex::laplace_ke<double>(g, a.alpha, Ke);
+#pragma unroll
+          for (int e = 0; e < 36; ++e) myslot[e] = Ke[e];
+        }
+        if (a.do_vector) {
+          double be[8];
+          q1hex::source_be<double>(g, a.fscale, be);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) myslot[36 + e] = be[e];
+        }
+      } else {   // below / above the mesh: contributes nothing
+#pragma unroll
+        for (int e = 0; e < 44; ++e) myslot[e] = 0.0;
+      }
+    }
+    // column ids of node layer L (finalised in this step)
+    if (node_thread && L >= kz0) {
+      long long cb = -1; int col = -1;
+      if (node_in_mesh) {
+        int d = a.node_dof[(i0 + li) + s1 * (j0 + lj) + s2 * L];
+        if (d > 0) { col = d - 1; cb = a.colptr[col]; }
+      }
+      ColBase[t] = cb; ColIdx[t] = col;
+    }
+    __syncthreads();
+    // ---- B) gather: thread per node, all 27 entries, compile-time offsets ----
+    if (node_thread) {
+      if (a.do_matrix) GatherAll<BX, BY, 0>::run(gbase, Pend + t, OutS + t * 27);
+      if (a.do_vector) {
+        double acc = PendB[t], hi = 0.0;
+#pragma unroll
+        for (int e2 = 1; e2 >= 0; --e2)
+#pragma unroll
+          for (int e1 = 1; e1 >= 0; --e1) {
+            const double* ke = gbase - (e1 + C::CX * e2) * C::KSTR + 36;
+            hi += ke[e1 + 2 * e2 + 4];
+            acc += ke[e1 + 2 * e2];
+          }
+        PendB[t] = hi;
+        if (L >= kz0 && ColIdx[t] >= 0) a.b[ColIdx[t]] = acc;
+      }
+    }
+    __syncthreads();
+    // ---- C) copy-out: consecutive threads write consecutive nzval addresses ----
+    if (a.do_matrix && L >= kz0) {
+      for (int item = t; item < C::NN * 27; item += C::NT) {
+        const int nl = item / 27, o = item - nl * 27;
+        const long long cb = ColBase[nl];
+        if (cb >= 0) {
+          const unsigned slot = a.slot_tbl[(size_t)ColIdx[nl] * 32 + o];
+          if (slot != 255u) a.nzval[cb + slot] = OutS[item];
+        }
+      }
+    }
+  }
+}
+
+inline int grid_for(int64_t n, int block) {
+  int64_t g = (n + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g));
+}
+
+void plan_free(gtk_ctx* ctx, FastPlan* p) {
+  if (!p) return;
+  if (p->node_dof) gtk_dev_free(ctx, p->node_dof, sizeof(int32_t) * (size_t)p->n_nodes);
+  if (p->dof_node) gtk_dev_free(ctx, p->dof_node, sizeof(int32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
+  if (p->slot_tbl) gtk_dev_free(ctx, p->slot_tbl, (size_t)32 * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
+  delete p;
+}
+
+// tabulation must be the Q1 / 2x2x2 Gauss rule the kernel hard-codes
+bool tabulation_is_q1_gauss2(const gtk_ctx* ctx) {
+  if (ctx->nq != 8 || ctx->nls != 8 || ctx->nln != 8) return false;
+  for (int q = 0; q < 8; ++q) {
+    if (fabs(ctx->h_w[q] - 0.125) > 1e-14) return false;
+    for (int i = 0; i < 8; ++i) {
+      double n = 1.0;
+      for (int d = 0; d < 3; ++d) n *= q1hex::nval((i >> d) & 1, (q >> d) & 1);
+      if (fabs(ctx->h_N[q * 8 + i] - n) > 1e-13 || fabs(ctx->h_M[q * 8 + i] - n) > 1e-13) return false;
+      for (int d = 0; d < 3; ++d) {
+        double g = 1.0;
+        for (int e = 0; e < 3; ++e) g *= e == d ? (((i >> e) & 1) ? 1.0 : -1.0) : q1hex::nval((i >> e) & 1, (q >> e) & 1);
+        if (fabs(ctx->h_dN[(q * 8 + i) * 3 + d] - g) > 1e-13 || fabs(ctx->h_dM[(q * 8 + i) * 3 + d] - g) > 1e-13) return false;
+      }
+    }
+  }
+  return true;
+}
+
+// Detect the structured topology and build node<->dof maps + slot table.  Any mismatch leaves
+// plan->ok = false and the generic path is used.
+int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
+  p->tried = true;
+  if (ctx->D != 3 || ctx->nln != 8 || ctx->nld != 8 || ctx->ncomp != 1 || ctx->n_cells < 1) return GTK_OK;
+  if (!ctx->ms.ready || ctx->ms.rows_fd != GTK_FREE || ctx->ms.cols_fd != GTK_FREE || ctx->n_free < 1) return GTK_OK;
+  if (!tabulation_is_q1_gauss2(ctx)) return GTK_OK;
+  cudaStream_t st = ctx->stream;
+  int32_t first[8];
+  GTK_CK(cudaMemcpyAsync(first, ctx->cell_nodes, sizeof(first), cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
+  int64_t s1 = (int64_t)first[2] - first[0], s2 = (int64_t)first[4] - first[0];
+  if (first[1] - first[0] != 1 || s1 < 2 || s2 < s1 || s2 % s1 != 0) return GTK_OK;
+  int64_t n1 = s1 - 1, n2 = s2 / s1 - 1;
+  if (n1 < 1 || n2 < 1 || ctx->n_cells % (n1 * n2) != 0) return GTK_OK;
+  int64_t n3 = ctx->n_cells / (n1 * n2);
+  int64_t n_nodes = (n1 + 1) * (n2 + 1) * (n3 + 1);
+  int64_t node_off = (int64_t)first[0] - 1;
+  if (node_off < 0 || node_off + n_nodes > ctx->n_nodes || n_nodes >= 0x7FFFFFFFll) return GTK_OK;
+  p->n1 = (int)n1; p->n2 = (int)n2; p->n3 = (int)n3; p->node_off = node_off; p->n_nodes = n_nodes;
+  int32_t rc;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->node_dof, sizeof(int32_t) * (size_t)n_nodes))) return rc;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->dof_node, sizeof(int32_t) * (size_t)ctx->n_free))) return rc;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->slot_tbl, (size_t)32 * (size_t)ctx->n_free))) return rc;
+  int* d_bad = nullptr;
+  GTK_CK(cudaMalloc(&d_bad, sizeof(int)));
+  GTK_CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  GTK_CK(cudaMemsetAsync(p->node_dof, 0, sizeof(int32_t) * (size_t)n_nodes, st));
+  GTK_CK(cudaMemsetAsync(p->dof_node, 0xFF, sizeof(int32_t) * (size_t)ctx->n_free, st));
+  const int g = grid_for(ctx->n_cells, 256);
+  k_verify_structure<<<g, 256, 0, st>>>(ctx->cell_nodes, ctx->cell_dofs, p->n1, p->n2, p->n3, node_off, p->node_dof, d_bad);
+  k_verify_node_dof<<<g, 256, 0, st>>>(ctx->cell_dofs, p->n1, p->n2, p->n3, p->node_dof, d_bad);
+  k_dof_node<<<grid_for(n_nodes, 256), 256, 0, st>>>(p->node_dof, n_nodes, ctx->n_free, p->dof_node, d_bad);
+  k_slot_table<<<grid_for(ctx->n_free, 128), 128, 0, st>>>(p->node_dof, p->dof_node, ctx->ms.colptr, ctx->ms.rowval,
+                                                         ctx->n_free, p->n1, p->n2, p->n3, p->slot_tbl, d_bad);
+  GTK_CK(cudaGetLastError());
+  int bad = 1;
+  GTK_CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
+  cudaFree(d_bad);
+  p->ok = bad == 0;
   return GTK_OK;
 }
-void gtk_fastq1_release(gtk_ctx* ctx) { (void)ctx; }
+
+template <int BX, int BY, int MINB>
+int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
+  using C = Cfg<BX, BY>;
+  SweepArgs a = a0;
+  const int gx = (p->n1 + 1 + BX - 1) / BX, gy = (p->n2 + 1 + BY - 1) / BY;
+  // z-segments: enough CTAs for a few waves over sm_count*MINB resident CTAs, segments >= 8 layers
+  const int layers = p->n3 + 1;
+  int64_t slots = (int64_t)ctx->sm_count * MINB;
+  int nseg = (int)((4 * slots + (int64_t)gx * gy - 1) / ((int64_t)gx * gy));
+  if (nseg < 1) nseg = 1;
+  int max_seg = (layers + 7) / 8;
+  if (nseg > max_seg) nseg = max_seg;
+  a.seg_len = (layers + nseg - 1) / nseg;
+  nseg = (layers + a.seg_len - 1) / a.seg_len;
+  GTK_CK(cudaFuncSetAttribute(k_q1hex_sweep<BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  dim3 grid(gx, gy, nseg);
+  { GtkProf pr_(ctx, "k_q1hex_sweep"); k_q1hex_sweep<BX, BY, MINB><<<grid, C::NT, C::SMEM, ctx->stream>>>(a); }
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  return GTK_OK;
+}
+
+}  // namespace
+
+void gtk_fastq1_release(gtk_ctx* ctx) {
+  plan_free(ctx, (FastPlan*)ctx->ms.plan);
+  ctx->ms.plan = nullptr;
+}
+
+// Handles {LAPLACE}, {SOURCE_CONST} or both in one sweep when the mesh/space qualify.
+int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
+                       const gtk_form_params* pv, bool* handled) {
+  *handled = false;
+  if (getenv("GTK_DISABLE_FASTPATH")) return GTK_OK;
+  if (mform && mform != GTK_FORM_LAPLACE) return GTK_OK;
+  if (vform && vform != GTK_FORM_SOURCE_CONST) return GTK_OK;
+  if (vform && (!ctx->vs.ready || ctx->vs.fd != GTK_FREE)) return GTK_OK;
+  if (!ctx->ms.ready) return GTK_OK;   // the plan needs the pattern (also for vector-only calls)
+  FastPlan* p = (FastPlan*)ctx->ms.plan;
+  if (!p) {
+    p = new FastPlan();
+    ctx->ms.plan = p;
+    int32_t rc = plan_build(ctx, p);
+    if (rc) return rc;
+  }
+  if (!p->ok) return GTK_OK;
+  int32_t rc;
+  if (mform) {
+    if (ctx->nzval_cap < (size_t)ctx->ms.nnz || !ctx->nzval) {
+      if (ctx->nzval) gtk_dev_free(ctx, ctx->nzval, ctx->nzval_cap * sizeof(double));
+      ctx->nzval = nullptr; ctx->nzval_cap = 0;
+      if ((rc = gtk_dev_alloc(ctx, (void**)&ctx->nzval, sizeof(double) * (size_t)ctx->ms.nnz))) return rc;
+      ctx->nzval_cap = (size_t)ctx->ms.nnz;
+    }
+  }
+  if (vform) {
+    if (ctx->bvec_cap < (size_t)ctx->vs.n_rows || !ctx->bvec) {
+      if (ctx->bvec) gtk_dev_free(ctx, ctx->bvec, ctx->bvec_cap * sizeof(double));
+      ctx->bvec = nullptr; ctx->bvec_cap = 0;
+      if ((rc = gtk_dev_alloc(ctx, (void**)&ctx->bvec, sizeof(double) * (size_t)ctx->vs.n_rows))) return rc;
+      ctx->bvec_cap = (size_t)ctx->vs.n_rows;
+    }
+  }
+  SweepArgs a;
+  a.xyz = ctx->xyz + 3 * p->node_off;
+  a.node_dof = p->node_dof;
+  a.colptr = ctx->ms.colptr;
+  a.slot_tbl = p->slot_tbl;
+  a.nzval = ctx->nzval;
+  a.b = ctx->bvec;
+  a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3;
+  a.seg_len = 0;
+  a.alpha = pm ? pm->alpha : 1.0;
+  a.fscale = pv ? pv->alpha * pv->f_const[0] : 0.0;
+  a.do_matrix = mform != 0;
+  a.do_vector = vform != 0;
+  // every free dof belongs to a node of the structured block, so all of nzval / b is overwritten
+  rc = launch_sweep<16, 8, 2>(ctx, p, a);
+  if (rc) return rc;
+  ctx->fast_path_last = 1;
+  *handled = true;
+  return GTK_OK;
+}

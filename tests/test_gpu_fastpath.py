@@ -1,0 +1,113 @@
+"""The structured Q1-hex sweep kernel (csrc/fastq1.cu) against the oracle AND against the generic
+sort/segmented-reduce path of the same library, on meshes that stress its index logic."""
+import os
+
+import numpy as np
+import pytest
+
+import gt_oracle as O
+import gtk_b200
+from util import assert_values_close, make_engine, oracle_matrix, oracle_vector, problem
+
+E = gtk_b200.engine
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ((16, 8, 9), "boundary", 0.0),      # exactly one footprint
+    ((17, 9, 8), "boundary", 0.2),      # one node past the footprint in x and y
+    ((33, 20, 21), "boundary", 0.2),    # several footprints and z-segments, ragged
+    ((5, 4, 3), None, 0.2),             # no BC: corner dofs numbered first (non-monotone columns)
+    ((9, 7, 30), [1, 4, 5], 0.1),       # partial Dirichlet boundary, long z sweep
+    ((2, 2, 2), "boundary", 0.0),
+    ((1, 1, 1), None, 0.0),
+    ((40, 3, 2), [3], 0.15),
+    ((48, 48, 48), "boundary", 0.1),
+]
+
+
+@pytest.mark.parametrize("cells,bc,warp", CASES)
+def test_fast_path_matches_oracle_and_generic(cells, bc, warp):
+    mesh, V, tab = problem(cells, bc=bc, warp=warp)
+    colptr, rowval, nzval = oracle_matrix(O.LAPLACE, mesh, V, tab, alpha=1.5)
+    b_ref = oracle_vector(O.SOURCE_CONST, mesh, V, tab, f_const=[2.0], alpha=0.5)
+    eng = make_engine(mesh, V, tab)
+    eng.matrix_symbolic()
+    cp, rv = eng.matrix_pattern()
+    assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
+    nz, b = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.5), E.FORM_SOURCE_CONST, dict(f_const=[2.0], alpha=0.5))
+    assert eng.info(5) == 1, "the structured fast path was not taken"
+    assert eng.info(0) == 1, "the fast path must be a single kernel launch"
+    assert_values_close(nz, nzval)
+    assert_values_close(b, b_ref)
+    # matrix-only and vector-only entry points use the same kernel
+    assert_values_close(eng.matrix_numeric(E.FORM_LAPLACE, alpha=1.5), nzval)
+    assert eng.info(5) == 1
+    assert_values_close(eng.vector_assemble(E.FORM_SOURCE_CONST, f_const=[2.0], alpha=0.5), b_ref)
+    # bit-reproducible
+    nz2, b2 = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.5), E.FORM_SOURCE_CONST, dict(f_const=[2.0], alpha=0.5))
+    assert nz2.tobytes() == nz.tobytes() and b2.tobytes() == b.tobytes()
+    eng.close()
+    # generic path of the same library
+    os.environ["GTK_DISABLE_FASTPATH"] = "1"
+    try:
+        eng = make_engine(mesh, V, tab)
+        eng.matrix_symbolic()
+        nz_g, b_g = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.5), E.FORM_SOURCE_CONST, dict(f_const=[2.0], alpha=0.5))
+        assert eng.info(5) == 0
+        eng.close()
+    finally:
+        del os.environ["GTK_DISABLE_FASTPATH"]
+    assert_values_close(nz, nz_g)
+    assert_values_close(b, b_g)
+
+
+def test_fast_path_declines_what_it_does_not_cover():
+    # shuffled cell order: not a structured topology any more -> generic path, same answer
+    mesh, V, tab = problem((6, 5, 4), bc="boundary", warp=0.1)
+    colptr, rowval, nzval = oracle_matrix(O.LAPLACE, mesh, V, tab)
+    perm = np.random.default_rng(3).permutation(mesh.n_cells)
+    eng = gtk_b200.engine.Engine(0)
+    eng.set_mesh(mesh.node_coordinates, mesh.cell_nodes[perm])
+    eng.set_space(V.cell_dofs[perm], V.n_free, V.n_dirichlet)
+    eng.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+    eng.matrix_symbolic()
+    cp, rv = eng.matrix_pattern()
+    assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
+    nz = eng.matrix_numeric(E.FORM_LAPLACE)
+    assert eng.info(5) == 0
+    assert_values_close(nz, nzval)      # other summation order than the oracle's cell order: still within 1e-12
+    # mass on the structured mesh: fast path declines (LAPLACE only)
+    eng2 = make_engine(mesh, V, tab)
+    eng2.matrix_symbolic()
+    eng2.matrix_numeric(E.FORM_MASS)
+    assert eng2.info(5) == 0
+    eng.close(); eng2.close()
+
+
+def test_full_size_config2_invariants():
+    """BASELINE config 2 at full size (128^3): size-independent properties instead of an oracle run:
+    nnz = (3m-2)^3, row sums of the Dirichlet-reduced Laplacian are >= 0 and vanish for rows not touching the
+    boundary, A is bitwise symmetric, sum(b) = volume of the union of interior-node supports."""
+    n = 128
+    mesh, V, tab = problem((n, n, n), bc="boundary")
+    eng = make_engine(mesh, V, tab)
+    nnz = eng.matrix_symbolic()
+    assert nnz == (3 * (n - 1) - 2) ** 3 == 54439939
+    cp, rv = eng.matrix_pattern()
+    nz, b = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+    assert eng.info(5) == 1
+    import scipy.sparse as sp
+    A = sp.csc_matrix((nz, rv.astype(np.int64) - 1, cp.astype(np.int64) - 1), shape=(V.n_free, V.n_free))
+    assert abs(A - A.T).max() == 0.0
+    rs = np.asarray(A.sum(axis=1)).ravel()
+    interior = np.diff(cp) == 27
+    assert np.abs(rs[interior]).max() < 1e-12 * np.abs(nz).max()
+    assert rs.min() > -1e-12 * np.abs(nz).max()
+    # diagonal of the uniform-mesh Q1 Laplacian: 8 cells * h/3 each
+    h = 1.0 / n
+    assert np.allclose(A.diagonal(), 8 * h / 3, rtol=1e-12)
+    # Σ_i b_i = ∫ Σ_i N_i = volume minus the part carried by boundary shape functions
+    assert abs(b.sum() - (1 - h) ** 3) < 1e-12
+    nz2, b2 = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+    assert nz2.tobytes() == nz.tobytes() and b2.tobytes() == b.tobytes()
+    eng.close()
