@@ -28,6 +28,7 @@ struct FastPlan {
   int32_t* node_dof = nullptr;       // [n_nodes] signed 1-based dof id of every node
   int32_t* dof_node = nullptr;       // [n_free]  node index of every free dof
   uint8_t* slot_tbl = nullptr;       // [n_free][32] slot of neighbour offset o in the column, 255 = absent
+  uint32_t* col_mask = nullptr;      // [n_free] bit o: neighbour o present; bit 31: slots are not popcount-monotone
   bool ok = false;
   bool tried = false;
 };
@@ -77,7 +78,8 @@ __global__ void k_dof_node(const int32_t* __restrict__ node_dof, int64_t n_nodes
 // slot_tbl[col][o]: position of the row dof of neighbour offset o inside CSC column col
 __global__ void k_slot_table(const int32_t* __restrict__ node_dof, const int32_t* __restrict__ dof_node,
                              const int64_t* __restrict__ colptr, const int32_t* __restrict__ rowval, int64_t n_free,
-                             int n1, int n2, int n3, uint8_t* __restrict__ slot_tbl, int* bad) {
+                             int n1, int n2, int n3, uint8_t* __restrict__ slot_tbl, uint32_t* __restrict__ col_mask,
+                             int* bad) {
   const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
   for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < n_free; col += (int64_t)gridDim.x * blockDim.x) {
     int64_t node = dof_node[col];
@@ -85,6 +87,8 @@ __global__ void k_slot_table(const int32_t* __restrict__ node_dof, const int32_t
     int i = (int)(node % s1), j = (int)((node / s1) % (n2 + 1)), k = (int)(node / s2);
     const int64_t p0 = colptr[col], p1 = colptr[col + 1];
     int found = 0;
+    uint32_t mask = 0;
+    bool monotone = true;
     for (int o = 0; o < 27; ++o) {
       int dx = o % 3 - 1, dy = (o / 3) % 3 - 1, dz = o / 9 - 1;
       int ii = i + dx, jj = j + dy, kk = k + dz;
@@ -98,7 +102,12 @@ __global__ void k_slot_table(const int32_t* __restrict__ node_dof, const int32_t
         }
       }
       slot_tbl[col * 32 + o] = slot;
+      if (slot != 255) {
+        if (slot != (uint8_t)__popc(mask)) monotone = false;   // slot(o) = number of present neighbours before o ?
+        mask |= 1u << o;
+      }
     }
+    col_mask[col] = monotone ? mask : (mask | 0x80000000u);
     if (found != (int)(p1 - p0)) *bad = 1;    // the column has rows this stencil does not produce
   }
 }
@@ -108,6 +117,7 @@ struct SweepArgs {
   const int32_t* node_dof;
   const int64_t* colptr;
   const uint8_t* slot_tbl;
+  const uint32_t* col_mask;
   double* nzval;
   double* b;
   int n1, n2, n3;
@@ -119,12 +129,20 @@ struct SweepArgs {
 template <int BX, int BY>
 struct Cfg {
   static constexpr int CX = BX + 1, CY = BY + 1, NC = CX * CY, NN = BX * BY;
+  static constexpr int PX = BX + 2, PY = BY + 2, NP = PX * PY;   // nodes of one layer incl. halo
   static constexpr int NT = ((NC + 31) / 32) * 32;
   static constexpr int KSTR = 45;   // doubles per cell slot: 36 Ke + 8 be + 1 pad (odd stride: conflict-free row reads)
-  // KeS[NC][KSTR] | Pend[18][NN] | PendB[NN] | OutS[NN][27] | ColBase[NN] (i64) | ColIdx[NN] (i32)
-  static constexpr size_t SMEM = sizeof(double) * ((size_t)NC * KSTR + (size_t)NN * 18 + NN + (size_t)NN * 27) +
-                                 sizeof(long long) * NN + sizeof(int) * NN;
+  // KeS[NC][KSTR] | Pend[18][NN] | PendB[NN] | OutS[NN][27] | XS[3][NP][3] | ColBase[3][NN] (i64) | ColIdx[3][NN] | ColMask[3][NN]
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)NC * KSTR + (size_t)NN * 18 + NN + (size_t)NN * 27 + 3 * NP * 3) +
+                                 sizeof(long long) * 3 * NN + sizeof(int) * 6 * NN;
 };
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // one matrix entry (column = node of the footprint, row = its neighbour at offset O): sum of the <= 4 cells of
 // this layer that contain both nodes, in increasing cell id (decreasing e) = the reference's push order.
@@ -145,18 +163,24 @@ __device__ __forceinline__ void gather_entry(const double* __restrict__ base, do
     }
 }
 
+// All 27 entries of one column.  Finished values go to out[] already in CSC slot order:
+// slot(o) = number of present neighbours before o (popcount of the presence mask), or the
+// byte table for the rare columns whose dof numbering is not monotone in the neighbour order.
 template <int BX, int BY, int O>
 struct GatherAll {
   using C = Cfg<BX, BY>;
   static __device__ __forceinline__ void run(const double* __restrict__ base, double* __restrict__ pend,
-                                             double* __restrict__ out) {
+                                             double* __restrict__ out, unsigned mask, const uint8_t* __restrict__ tbl) {
     constexpr int dz = O / 9 - 1;
     double acc = 0.0, hi = 0.0;
     if (dz <= 0) acc = pend[O * C::NN];
     gather_entry<O, C::CX, C::KSTR>(base, acc, hi);
     if (dz <= 0) pend[O * C::NN] = hi;
-    out[O] = acc;
-    if constexpr (O + 1 < 27) GatherAll<BX, BY, O + 1>::run(base, pend, out);
+    if ((mask >> O) & 1u) {
+      const unsigned slot = tbl ? (unsigned)tbl[O] : (unsigned)__popc(mask & ((1u << O) - 1u));
+      out[slot] = acc;
+    }
+    if constexpr (O + 1 < 27) GatherAll<BX, BY, O + 1>::run(base, pend, out, mask, tbl);
   }
 };
 
@@ -168,8 +192,10 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
   double* Pend = KeS + C::NC * C::KSTR;               // [18][NN]   entries waiting for the next cell layer
   double* PendB = Pend + C::NN * 18;                  // [NN]
   double* OutS = PendB + C::NN;                       // [NN][27]   finished columns of node layer L (transpose buffer)
-  long long* ColBase = (long long*)(OutS + C::NN * 27);   // [NN] colptr of each node's column, -1 = none
-  int* ColIdx = (int*)(ColBase + C::NN);              // [NN]
+  double* XS = OutS + C::NN * 27;                     // [3][NP][3] ring of node-coordinate layers (cp.async, 2 ahead)
+  long long* ColBase = (long long*)(XS + 3 * C::NP * 3);   // [3][NN] colptr of each node's column, -1 = none (ring: layer m in slot m%3)
+  int* ColIdx = (int*)(ColBase + 3 * C::NN);          // [3][NN]
+  unsigned* ColMask = (unsigned*)(ColIdx + 3 * C::NN);     // [3][NN]
 
   const int t = threadIdx.x;
   const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY;
@@ -188,6 +214,21 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
   const bool node_in_mesh = node_thread && (i0 + li <= n1) && (j0 + lj <= n2);
   const double* gbase = KeS + ((li + 1) + C::CX * (lj + 1)) * C::KSTR;
 
+  // asynchronous copy of one node layer (footprint + halo ring) into the ring slot (m+3)%3
+  auto prefetch_nodes = [&](int m) {
+    if (m >= 0 && m <= n3) {
+      double* dst = XS + ((m + 3) % 3) * (C::NP * 3);
+      for (int idx = t; idx < C::NP * 3; idx += C::NT) {
+        const int nd = idx / 3, k = idx - nd * 3;
+        const int gi = i0 - 1 + nd % C::PX, gj = j0 - 1 + nd / C::PX;
+        if (gi >= 0 && gi <= n1 && gj >= 0 && gj <= n2) cp_async8(dst + idx, a.xyz + 3 * (gi + s1 * gj + s2 * m) + k);
+      }
+    }
+    cp_async_commit();
+  };
+
+  prefetch_nodes(kz0 - 1);
+  prefetch_nodes(kz0);
   // cells outside the mesh never compute: their slots stay zero, so the gather needs no bounds checks
   if (has_slot) {
 #pragma unroll
@@ -195,18 +236,29 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
   }
   for (int idx = t; idx < C::NN * 18; idx += C::NT) Pend[idx] = 0.0;
   for (int idx = t; idx < C::NN; idx += C::NT) PendB[idx] = 0.0;
+  cp_async_wait_all();
+  __syncthreads();
 
   for (int L = kz0 - 1; L < kz1; ++L) {
     const bool layer_ok = L >= 0 && L < n3;
+    prefetch_nodes(L + 2);                                  // lands during phases A/B, waited before the 2nd barrier
+    // column info of node layer L+1 (consumed one step later): loads issued now, stored after the FP64 work
+    long long cbn = -1; int coln = -1; unsigned maskn = 0;
+    if (node_in_mesh && L + 1 <= n3 && L + 1 < kz1) {
+      int d = __ldg(a.node_dof + (i0 + li) + s1 * (j0 + lj) + s2 * (L + 1));
+      if (d > 0) { coln = d - 1; cbn = __ldg(a.colptr + coln); maskn = __ldg(a.col_mask + coln); }
+    }
     // ---- A) element matrices of cell layer L ----
     if (cell_ok) {
       if (layer_ok) {
         double X[8][3];
-        const int64_t base = ci + s1 * cj + s2 * L;
+        const double* x0 = XS + ((L + 3) % 3) * (C::NP * 3) + 3 * (cx + C::PX * cy);
+        const double* x1 = XS + ((L + 4) % 3) * (C::NP * 3) + 3 * (cx + C::PX * cy);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const double* p = a.xyz + 3 * (base + (v & 1) + s1 * ((v >> 1) & 1) + s2 * (v >> 2));
-          X[v][0] = __ldg(p); X[v][1] = __ldg(p + 1); X[v][2] = __ldg(p + 2);
+        for (int v = 0; v < 4; ++v) {
+          const int off = 3 * ((v & 1) + C::PX * (v >> 1));
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { X[v][k] = x0[off + k]; X[v + 4][k] = x1[off + k]; }
         }
         q1hex::Cell<double> g;
         q1hex::geometry<double>(X, g);
@@ -227,19 +279,19 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
         for (int e = 0; e < 44; ++e) myslot[e] = 0.0;
       }
     }
-    // column ids of node layer L (finalised in this step)
-    if (node_thread && L >= kz0) {
-      long long cb = -1; int col = -1;
-      if (node_in_mesh) {
-        int d = a.node_dof[(i0 + li) + s1 * (j0 + lj) + s2 * L];
-        if (d > 0) { col = d - 1; cb = a.colptr[col]; }
-      }
-      ColBase[t] = cb; ColIdx[t] = col;
+    if (node_thread) {
+      const int nb = ((L + 4) % 3) * C::NN + t;   // written 2 barriers after its last reader (step L-2)
+      ColBase[nb] = cbn; ColIdx[nb] = coln; ColMask[nb] = maskn;
     }
     __syncthreads();
     // ---- B) gather: thread per node, all 27 entries, compile-time offsets ----
+    const int cur = ((L + 3) % 3) * C::NN;
     if (node_thread) {
-      if (a.do_matrix) GatherAll<BX, BY, 0>::run(gbase, Pend + t, OutS + t * 27);
+      if (a.do_matrix) {
+        const unsigned mask = L >= kz0 ? ColMask[cur + t] : 0u;     // 0: nothing to emit (halo layer / no column)
+        const uint8_t* tbl = (mask & 0x80000000u) ? a.slot_tbl + (size_t)ColIdx[cur + t] * 32 : nullptr;
+        GatherAll<BX, BY, 0>::run(gbase, Pend + t, OutS + t * 27, mask, tbl);
+      }
       if (a.do_vector) {
         double acc = PendB[t], hi = 0.0;
 #pragma unroll
@@ -251,19 +303,22 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
             acc += ke[e1 + 2 * e2];
           }
         PendB[t] = hi;
-        if (L >= kz0 && ColIdx[t] >= 0) a.b[ColIdx[t]] = acc;
+        if (L >= kz0 && ColIdx[cur + t] >= 0) a.b[ColIdx[cur + t]] = acc;
       }
     }
+    cp_async_wait_all();
     __syncthreads();
-    // ---- C) copy-out: consecutive threads write consecutive nzval addresses ----
+    // ---- C) copy-out: column nl owns OutS[nl*27 .. +count); consecutive threads -> consecutive addresses ----
     if (a.do_matrix && L >= kz0) {
+      int nl = t / 27, sl = t - nl * 27;
+      constexpr int DN = C::NT / 27, DS = C::NT % 27;
+#pragma unroll 4
       for (int item = t; item < C::NN * 27; item += C::NT) {
-        const int nl = item / 27, o = item - nl * 27;
-        const long long cb = ColBase[nl];
-        if (cb >= 0) {
-          const unsigned slot = a.slot_tbl[(size_t)ColIdx[nl] * 32 + o];
-          if (slot != 255u) a.nzval[cb + slot] = OutS[item];
-        }
+        const long long cb = ColBase[cur + nl];
+        const int cnt = __popc(ColMask[cur + nl] & 0x07FFFFFFu);
+        if (cb >= 0 && sl < cnt) a.nzval[cb + sl] = OutS[item];
+        nl += DN; sl += DS;
+        if (sl >= 27) { sl -= 27; nl += 1; }
       }
     }
   }
@@ -279,6 +334,7 @@ void plan_free(gtk_ctx* ctx, FastPlan* p) {
   if (p->node_dof) gtk_dev_free(ctx, p->node_dof, sizeof(int32_t) * (size_t)p->n_nodes);
   if (p->dof_node) gtk_dev_free(ctx, p->dof_node, sizeof(int32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   if (p->slot_tbl) gtk_dev_free(ctx, p->slot_tbl, (size_t)32 * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
+  if (p->col_mask) gtk_dev_free(ctx, p->col_mask, sizeof(uint32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   delete p;
 }
 
@@ -325,6 +381,7 @@ int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
   if ((rc = gtk_dev_alloc(ctx, (void**)&p->node_dof, sizeof(int32_t) * (size_t)n_nodes))) return rc;
   if ((rc = gtk_dev_alloc(ctx, (void**)&p->dof_node, sizeof(int32_t) * (size_t)ctx->n_free))) return rc;
   if ((rc = gtk_dev_alloc(ctx, (void**)&p->slot_tbl, (size_t)32 * (size_t)ctx->n_free))) return rc;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->col_mask, sizeof(uint32_t) * (size_t)ctx->n_free))) return rc;
   int* d_bad = nullptr;
   GTK_CK(cudaMalloc(&d_bad, sizeof(int)));
   GTK_CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
@@ -335,7 +392,7 @@ int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
   k_verify_node_dof<<<g, 256, 0, st>>>(ctx->cell_dofs, p->n1, p->n2, p->n3, p->node_dof, d_bad);
   k_dof_node<<<grid_for(n_nodes, 256), 256, 0, st>>>(p->node_dof, n_nodes, ctx->n_free, p->dof_node, d_bad);
   k_slot_table<<<grid_for(ctx->n_free, 128), 128, 0, st>>>(p->node_dof, p->dof_node, ctx->ms.colptr, ctx->ms.rowval,
-                                                         ctx->n_free, p->n1, p->n2, p->n3, p->slot_tbl, d_bad);
+                                                         ctx->n_free, p->n1, p->n2, p->n3, p->slot_tbl, p->col_mask, d_bad);
   GTK_CK(cudaGetLastError());
   int bad = 1;
   GTK_CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -413,6 +470,7 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   a.node_dof = p->node_dof;
   a.colptr = ctx->ms.colptr;
   a.slot_tbl = p->slot_tbl;
+  a.col_mask = p->col_mask;
   a.nzval = ctx->nzval;
   a.b = ctx->bvec;
   a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3;
@@ -422,7 +480,17 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   a.do_matrix = mform != 0;
   a.do_vector = vform != 0;
   // every free dof belongs to a node of the structured block, so all of nzval / b is overwritten
-  rc = launch_sweep<16, 8, 2>(ctx, p, a);
+  // footprint variants (tuning knob for experiments; default chosen from measurements)
+  const char* var = getenv("GTK_SWEEP_VARIANT");
+  const int v = var ? atoi(var) : 3;
+  switch (v) {
+    case 1: rc = launch_sweep<16, 6, 2>(ctx, p, a); break;
+    case 2: rc = launch_sweep<24, 8, 1>(ctx, p, a); break;
+    case 3: rc = launch_sweep<12, 8, 2>(ctx, p, a); break;
+    case 4: rc = launch_sweep<8, 8, 3>(ctx, p, a); break;
+    case 0: rc = launch_sweep<16, 8, 1>(ctx, p, a); break;
+    default: rc = launch_sweep<12, 8, 2>(ctx, p, a); break;
+  }
   if (rc) return rc;
   ctx->fast_path_last = 1;
   *handled = true;
