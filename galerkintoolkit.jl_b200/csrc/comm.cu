@@ -1,14 +1,237 @@
-// Multi-GPU ghost-row summation (placeholder).
+// Multi-GPU data path: ghost-row summation over NCCL.
+//
+// One process per GPU.  Every cell is assembled exactly once, by the rank that owns it; rows whose
+// owner is another rank ("ghost rows", PartitionedArrays vocabulary) hold partial sums that are sent
+// to their owner and added there — PartitionedArrays.assemble! semantics.  The reference has no
+// distributed assembly (docs/src/manual/introduction.md:22-28; space.jl:2776-2827 is commented out),
+// so this mirrors the data model of docs/src/src_jl/manual_mesh_partitioning.jl:14-35 instead.
+//
+// The HOST computes the exchange plan (which nzval / b entries go to which peer, and where the
+// received values are added) — galerkintoolkit.jl_b200/partition.py, testable on CPU over gloo.
+// This file only moves bytes:  pack kernel -> ncclSend / ncclRecv in one group -> add kernels in
+// increasing peer rank (deterministic; no float atomics).  NCCL is dlopen'ed so that single-GPU
+// users need no NCCL at all.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <algorithm>
 #include "gtk_internal.h"
-void gtk_comm_release(gtk_ctx* ctx) { (void)ctx; }
+
+namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.handle) return api;
+  // a copy already loaded by the host process (e.g. torch's bundled one) wins; else the system library
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return api;
+#define LOAD(field, sym) api.field = (decltype(api.field))dlsym(api.handle, sym)
+  LOAD(GetUniqueId, "ncclGetUniqueId");
+  LOAD(CommInitRank, "ncclCommInitRank");
+  LOAD(CommDestroy, "ncclCommDestroy");
+  LOAD(Send, "ncclSend");
+  LOAD(Recv, "ncclRecv");
+  LOAD(GroupStart, "ncclGroupStart");
+  LOAD(GroupEnd, "ncclGroupEnd");
+  LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart &&
+           api.GroupEnd && api.GetErrorString;
+  return api;
+}
+
+struct Peer {
+  int rank = -1;
+  int64_t n_send_nz = 0, n_send_b = 0, n_recv_nz = 0, n_recv_b = 0;
+  int64_t* send_nz = nullptr;   // device: nz positions (0-based) whose values go to the peer
+  int32_t* send_rows = nullptr; // device: rows of b (0-based) that go to the peer
+  int64_t* recv_nz = nullptr;   // device: nz positions the received values are added to
+  int32_t* recv_rows = nullptr;
+  double* send_buf = nullptr;   // [n_send_nz + n_send_b]
+  double* recv_buf = nullptr;   // [n_recv_nz + n_recv_b]
+};
+
+struct GhostPlan {
+  std::vector<Peer> peers;   // sorted by rank
+};
+
+__global__ void k_pack(const double* __restrict__ nzval, const int64_t* __restrict__ idx, int64_t n,
+                       const double* __restrict__ b, const int32_t* __restrict__ rows, int64_t nb,
+                       double* __restrict__ buf) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x)
+    buf[i] = i < n ? nzval[idx[i]] : b[rows[i - n]];
+}
+
+// each target position appears at most once per peer (checked on the host), so no atomics are needed
+__global__ void k_unpack_add(double* __restrict__ nzval, const int64_t* __restrict__ idx, int64_t n,
+                             double* __restrict__ b, const int32_t* __restrict__ rows, int64_t nb,
+                             const double* __restrict__ buf) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n) nzval[idx[i]] += buf[i]; else b[rows[i - n]] += buf[i];
+  }
+}
+
+inline int grid_for(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+
+void free_peer(gtk_ctx* ctx, Peer& p) {
+  gtk_dev_free(ctx, p.send_nz, sizeof(int64_t) * p.n_send_nz);
+  gtk_dev_free(ctx, p.send_rows, sizeof(int32_t) * p.n_send_b);
+  gtk_dev_free(ctx, p.recv_nz, sizeof(int64_t) * p.n_recv_nz);
+  gtk_dev_free(ctx, p.recv_rows, sizeof(int32_t) * p.n_recv_b);
+  gtk_dev_free(ctx, p.send_buf, sizeof(double) * (p.n_send_nz + p.n_send_b));
+  gtk_dev_free(ctx, p.recv_buf, sizeof(double) * (p.n_recv_nz + p.n_recv_b));
+}
+
+template <class T>
+int32_t upload_idx(gtk_ctx* ctx, T** dst, const T* src, int64_t n) {
+  *dst = nullptr;
+  if (n == 0) return GTK_OK;
+  int32_t rc = gtk_dev_alloc(ctx, (void**)dst, sizeof(T) * n);
+  if (rc) return rc;
+  GTK_CK(cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+  return GTK_OK;
+}
+
+}  // namespace
+
+#define NCCL_CK(call)                                                                          \
+  do {                                                                                         \
+    ncclResult_t r_ = (call);                                                                  \
+    if (r_ != ncclSuccess) {                                                                   \
+      ctx->err = std::string(#call) + ": " + nccl().GetErrorString(r_);                        \
+      return GTK_ERR_NCCL;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+void gtk_comm_release(gtk_ctx* ctx) {
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  if (g) {
+    for (auto& p : g->peers) free_peer(ctx, p);
+    delete g;
+    ctx->ghost = nullptr;
+  }
+  if (ctx->comm && nccl().ok) nccl().CommDestroy((ncclComm_t)ctx->comm);
+  ctx->comm = nullptr;
+}
+
 extern "C" {
-int32_t gtk_comm_unique_id(void* id128) { (void)id128; return GTK_ERR_NCCL; }
+
+int32_t gtk_comm_unique_id(void* id128) {
+  if (!id128 || !nccl().ok) return GTK_ERR_NCCL;
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return GTK_ERR_NCCL;
+  memcpy(id128, &id, sizeof(id));
+  return GTK_OK;
+}
+
 int32_t gtk_comm_init(gtk_ctx* ctx, int32_t rank, int32_t n_ranks, const void* id128) {
-  (void)rank; (void)n_ranks; (void)id128; if (!ctx) return GTK_ERR_INVALID; GTK_FAIL(GTK_ERR_NCCL, "not built yet");
+  if (!ctx) return GTK_ERR_INVALID;
+  if (!id128 || rank < 0 || rank >= n_ranks) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_init: bad arguments");
+  if (!nccl().ok) GTK_FAIL(GTK_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  GTK_CK(cudaSetDevice(ctx->device));
+  if (ctx->comm) { nccl().CommDestroy((ncclComm_t)ctx->comm); ctx->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm;
+  NCCL_CK(nccl().CommInitRank(&comm, n_ranks, id, rank));
+  ctx->comm = comm;
+  ctx->rank = rank;
+  ctx->n_ranks = n_ranks;
+  return GTK_OK;
 }
-int32_t gtk_comm_setup_ghost_rows(gtk_ctx* ctx, int64_t lo, int64_t hi) {
-  (void)lo; (void)hi; if (!ctx) return GTK_ERR_INVALID; GTK_FAIL(GTK_ERR_NCCL, "not built yet");
+
+int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, const int64_t* send_nz, int64_t n_send_b,
+                              const int32_t* send_rows, int64_t n_recv_nz, const int64_t* recv_nz, int64_t n_recv_b,
+                              const int32_t* recv_rows) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (peer < 0 || peer == ctx->rank || (ctx->comm && peer >= ctx->n_ranks) || n_send_nz < 0 || n_send_b < 0 ||
+      n_recv_nz < 0 || n_recv_b < 0 || (n_send_nz && !send_nz) || (n_send_b && !send_rows) || (n_recv_nz && !recv_nz) ||
+      (n_recv_b && !recv_rows))
+    GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_set_exchange: bad arguments");
+  GTK_CK(cudaSetDevice(ctx->device));
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  if (!g) { g = new GhostPlan(); ctx->ghost = g; }
+  for (size_t i = 0; i < g->peers.size(); ++i)
+    if (g->peers[i].rank == peer) { free_peer(ctx, g->peers[i]); g->peers.erase(g->peers.begin() + i); break; }
+  Peer p;
+  p.rank = peer;
+  p.n_send_nz = n_send_nz; p.n_send_b = n_send_b; p.n_recv_nz = n_recv_nz; p.n_recv_b = n_recv_b;
+  int32_t rc;
+  if ((rc = upload_idx(ctx, &p.send_nz, send_nz, n_send_nz))) return rc;
+  if ((rc = upload_idx(ctx, &p.send_rows, send_rows, n_send_b))) return rc;
+  if ((rc = upload_idx(ctx, &p.recv_nz, recv_nz, n_recv_nz))) return rc;
+  if ((rc = upload_idx(ctx, &p.recv_rows, recv_rows, n_recv_b))) return rc;
+  if (n_send_nz + n_send_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.send_buf, sizeof(double) * (n_send_nz + n_send_b)))) return rc;
+  if (n_recv_nz + n_recv_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.recv_buf, sizeof(double) * (n_recv_nz + n_recv_b)))) return rc;
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  g->peers.push_back(p);
+  std::sort(g->peers.begin(), g->peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
+  return GTK_OK;
 }
-int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key) { (void)ctx; (void)key; return 0; }
-int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx) { if (!ctx) return GTK_ERR_INVALID; GTK_FAIL(GTK_ERR_NCCL, "not built yet"); }
+
+int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx) {
+  if (!ctx) return GTK_ERR_INVALID;
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  if (!g || g->peers.empty()) return GTK_OK;
+  if (!ctx->comm) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: call gtk_comm_init first");
+  if (!ctx->nzval) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: nothing assembled yet");
+  GTK_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  for (auto& p : g->peers) {
+    const int64_t n = p.n_send_nz + p.n_send_b;
+    if (n == 0) continue;
+    if (p.n_send_b && !ctx->bvec) GTK_FAIL(GTK_ERR_STATE, "ghost rows of b requested but no vector assembled");
+    { GtkProf pr_(ctx, "k_pack"); k_pack<<<grid_for(n), 256, 0, st>>>(ctx->nzval, p.send_nz, p.n_send_nz, ctx->bvec, p.send_rows, p.n_send_b, p.send_buf); }
+    GTK_CK(cudaGetLastError());
+    gtk_count_launch(ctx);
+  }
+  NCCL_CK(nccl().GroupStart());
+  for (auto& p : g->peers) {
+    if (p.n_send_nz + p.n_send_b) NCCL_CK(nccl().Send(p.send_buf, (size_t)(p.n_send_nz + p.n_send_b), ncclFloat64, p.rank, comm, st));
+    if (p.n_recv_nz + p.n_recv_b) NCCL_CK(nccl().Recv(p.recv_buf, (size_t)(p.n_recv_nz + p.n_recv_b), ncclFloat64, p.rank, comm, st));
+  }
+  NCCL_CK(nccl().GroupEnd());
+  for (auto& p : g->peers) {   // increasing peer rank: fixed summation order
+    const int64_t n = p.n_recv_nz + p.n_recv_b;
+    if (n == 0) continue;
+    { GtkProf pr_(ctx, "k_unpack_add"); k_unpack_add<<<grid_for(n), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b, p.recv_buf); }
+    GTK_CK(cudaGetLastError());
+    gtk_count_launch(ctx);
+  }
+  return GTK_OK;
 }
+
+int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key) {
+  if (!ctx) return -1;
+  const GhostPlan* g = (const GhostPlan*)ctx->ghost;
+  int64_t s = 0, r = 0;
+  if (g) for (auto& p : g->peers) { s += p.n_send_nz + p.n_send_b; r += p.n_recv_nz + p.n_recv_b; }
+  switch (key) {
+    case 0: return s;
+    case 1: return r;
+    case 2: return 8 * (s + r);
+    default: return -1;
+  }
+}
+
+}  // extern "C"

@@ -122,6 +122,7 @@ struct SweepArgs {
   double* b;
   int n1, n2, n3;
   int seg_len;
+  int kact0, kact1;   // numeric-active cell layers [kact0, kact1)
   double alpha, fscale;
   int do_matrix, do_vector;
 };
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
   __syncthreads();
 
   for (int L = kz0 - 1; L < kz1; ++L) {
-    const bool layer_ok = L >= 0 && L < n3;
+    const bool layer_ok = L >= a.kact0 && L < a.kact1;
     prefetch_nodes(L + 2);                                  // lands during phases A/B, waited before the 2nd barrier
     // column info of node layer L+1 (consumed one step later): loads issued now, stored after the FP64 work
     long long cbn = -1; int coln = -1; unsigned maskn = 0;
@@ -475,6 +476,13 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   a.b = ctx->bvec;
   a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3;
   a.seg_len = 0;
+  a.kact0 = 0; a.kact1 = p->n3;
+  if (ctx->act_count >= 0) {   // active cells must be whole cell layers for the sweep
+    const int64_t per_layer = (int64_t)p->n1 * p->n2;
+    if (ctx->act_first % per_layer || ctx->act_count % per_layer) return GTK_OK;
+    a.kact0 = (int)(ctx->act_first / per_layer);
+    a.kact1 = a.kact0 + (int)(ctx->act_count / per_layer);
+  }
   a.alpha = pm ? pm->alpha : 1.0;
   a.fscale = pv ? pv->alpha * pv->f_const[0] : 0.0;
   a.do_matrix = mform != 0;

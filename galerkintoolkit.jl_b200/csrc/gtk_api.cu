@@ -85,12 +85,21 @@ int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz
   GTK_CK(cudaSetDevice(ctx->device));
   auto& sz = ctx->sz;
   ctx->D = D; ctx->n_nodes = n_nodes; ctx->n_cells = n_cells; ctx->nln = n_lnodes;
+  ctx->act_first = 0; ctx->act_count = -1;
   int32_t rc = upload(ctx, &ctx->xyz, &sz.xyz, xyz, (size_t)n_nodes * D);
   if (rc) return rc;
   rc = upload(ctx, &ctx->cell_nodes, &sz.cell_nodes, cell_nodes, (size_t)n_cells * n_lnodes);
   if (rc) return rc;
   gtk_matsym_release(ctx); gtk_vecsym_release(ctx); gtk_fastq1_release(ctx);
   GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_set_active_cells(gtk_ctx* ctx, int64_t first, int64_t count) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (first < 0 || count < 0 || first + count > ctx->n_cells) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_active_cells: range outside the mesh");
+  ctx->act_first = first;
+  ctx->act_count = count;
   return GTK_OK;
 }
 

@@ -69,6 +69,7 @@ struct gtk_ctx {
   int64_t n_nodes = 0, n_cells = 0;
   double* xyz = nullptr;
   int32_t* cell_nodes = nullptr;
+  int64_t act_first = 0, act_count = -1;   // numeric-active cell range (-1 = all)
   // space
   int nld = 0, ncomp = 1, nls = 0;
   int64_t n_free = 0, n_diri = 0;

@@ -29,6 +29,7 @@ struct ElemArgs {
   const double* f_ptr;
   double* out;
   int cb;
+  int64_t act0, act1;   // numeric-active cells [act0, act1); others contribute zeros
 };
 
 template <int D>
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
       }
       acc += v * dV[cl * nq + q];
     }
-    a.out[(cell0 + cl) * (int64_t)nld2 + rem] = acc;
+    const int64_t cell = cell0 + cl;
+    a.out[cell * (int64_t)nld2 + rem] = (cell >= a.act0 && cell < a.act1) ? acc : 0.0;
   }
 }
 
@@ -194,7 +196,8 @@ __global__ void __launch_bounds__(128) k_elem_vector(ElemArgs a) {
     double acc = 0.0;
     for (int q = 0; q < nq; ++q)
       acc += (a.alpha * (F[(size_t)(cl * nq + q) * ncomp + ic] * a.N[q * nls + ia])) * dV[cl * nq + q];
-    a.out[(cell0 + cl) * (int64_t)nld + i] = acc;
+    const int64_t cell = cell0 + cl;
+    a.out[cell * (int64_t)nld + i] = (cell >= a.act0 && cell < a.act1) ? acc : 0.0;
   }
 }
 
@@ -249,6 +252,8 @@ int32_t fill_args(gtk_ctx* ctx, ElemArgs& a, int form, const gtk_form_params* p)
   a.mu = p ? p->mu : 0.0;
   for (int k = 0; k < 3; ++k) a.f_const[k] = p ? p->f_const[k] : 0.0;
   a.f_ptr = nullptr;
+  a.act0 = ctx->act_count < 0 ? 0 : ctx->act_first;
+  a.act1 = ctx->act_count < 0 ? ctx->n_cells : ctx->act_first + ctx->act_count;
   return GTK_OK;
 }
 

@@ -24,12 +24,12 @@ FORM_SOURCE_CONST, FORM_SOURCE_NODAL, FORM_SOURCE_QP = 101, 102, 103
 # every symbol include/gtk_assembly.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "gtk_version", "gtk_create", "gtk_destroy", "gtk_last_error", "gtk_set_stream",
-    "gtk_set_mesh", "gtk_update_coordinates", "gtk_set_space", "gtk_set_tabulation",
+    "gtk_set_mesh", "gtk_set_active_cells", "gtk_update_coordinates", "gtk_set_space", "gtk_set_tabulation",
     "gtk_matrix_symbolic", "gtk_matrix_pattern", "gtk_matrix_numeric", "gtk_matrix_numeric_device",
     "gtk_vector_symbolic", "gtk_vector_assemble", "gtk_vector_assemble_device",
     "gtk_assemble_matrix_and_vector", "gtk_assemble_matrix_and_vector_device",
     "gtk_device_pointer", "gtk_copy_nzval", "gtk_copy_vector", "gtk_info",
-    "gtk_comm_unique_id", "gtk_comm_init", "gtk_comm_setup_ghost_rows", "gtk_comm_sum_ghost_rows",
+    "gtk_comm_unique_id", "gtk_comm_init", "gtk_comm_set_exchange", "gtk_comm_sum_ghost_rows",
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
 ]
 
@@ -87,7 +87,7 @@ def load_library() -> C.CDLL:
         "gtk_info": (i64, [vp, i32]),
         "gtk_comm_unique_id": (i32, [vp]),
         "gtk_comm_init": (i32, [vp, i32, i32, vp]),
-        "gtk_comm_setup_ghost_rows": (i32, [vp, i64, i64]),
+        "gtk_comm_set_exchange": (i32, [vp, i64, i64]),
         "gtk_comm_sum_ghost_rows": (i32, [vp]),
         "gtk_comm_ghost_info": (i64, [vp, i32]),
         "gtk_set_profiling": (i32, [vp, i32]),
@@ -178,6 +178,9 @@ class Engine:
         self._D = xyz.shape[1]
         self._n_cells = cn.shape[0]
         self._ck(self.lib.gtk_set_mesh(self.h, xyz.shape[1], xyz.shape[0], _ptr(xyz), cn.shape[0], cn.shape[1], _ptr(cn)))
+
+    def set_active_cells(self, first: int, count: int):
+        self._ck(self.lib.gtk_set_active_cells(self.h, int(first), int(count)))
 
     def update_coordinates(self, node_coordinates):
         xyz = _f64(node_coordinates)
@@ -305,8 +308,14 @@ class Engine:
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.lib.gtk_comm_init(self.h, rank, n_ranks, buf))
 
-    def comm_setup_ghost_rows(self, own_lo: int, own_hi: int):
-        self._ck(self.lib.gtk_comm_setup_ghost_rows(self.h, own_lo, own_hi))
+    def comm_set_exchange(self, peer: int, send_nz, send_rows, recv_nz, recv_rows):
+        sn = np.ascontiguousarray(send_nz, dtype=np.int64); sr = _i32(send_rows)
+        rn = np.ascontiguousarray(recv_nz, dtype=np.int64); rr = _i32(recv_rows)
+        self._ck(self.lib.gtk_comm_set_exchange(self.h, int(peer), sn.size, _ptr(sn), sr.size, _ptr(sr),
+                                                rn.size, _ptr(rn), rr.size, _ptr(rr)))
+
+    def comm_ghost_info(self, key: int) -> int:
+        return int(self.lib.gtk_comm_ghost_info(self.h, key))
 
     def comm_sum_ghost_rows(self):
         self._ck(self.lib.gtk_comm_sum_ghost_rows(self.h))

@@ -1,0 +1,239 @@
+"""z-slab partition of a Cartesian Q1 problem over the GPUs of one box, and the ghost-row exchange
+plan (host side; numpy only).  SURVEY.md §8e.
+
+Data model = PartitionedArrays' (docs/src/src_jl/manual_mesh_partitioning.jl:14-35): every rank holds
+local ids, a ``local_to_global`` map and a ``local_to_owner`` map; a cell is owned by exactly one rank;
+a node (dof) is owned by the MAX rank among the cells around it (mesh.jl:1107-1112), i.e. the node
+layer on the interface of two slabs belongs to the upper slab.
+
+Rank r's local problem:
+  cells      cell layers [k0-1, k1) of the global mesh (k0-1 = the lower neighbour's top layer, present
+             only so that the sparsity pattern of r's own rows is complete: it is *symbolic-only*,
+             ``active_cells`` excludes it from the numeric assembly — each cell is assembled once);
+  nodes/dofs node layers [k0-1, k1]; local free dofs numbered in increasing global dof id;
+  own rows   dofs of node layers [k0, k1) (+ layer k1 on the last rank);
+  ghost rows dofs of node layer k1 (owner r+1): their partial sums are sent up and added there.
+After the exchange every rank holds its own rows fully summed = the row-partitioned matrix
+PartitionedArrays.assemble! would produce.  Same GPU count ⇒ bitwise-identical results.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import hostprep as H
+
+
+@dataclass
+class SlabPart:
+    rank: int
+    world: int
+    mesh: H.Mesh                 # local mesh (local node ids)
+    space: H.LagrangeSpace       # local dof numbering
+    active_cells: tuple          # (first, count) cells assembled numerically by this rank
+    row_gid: np.ndarray          # [n_free_local] global (1-based) dof id of every local free dof (increasing)
+    row_owner: np.ndarray        # [n_free_local] owning rank
+    n_global_free: int
+    k0: int
+    k1: int
+
+
+def _free_1d(n_nodes: int, lo_tag: bool, hi_tag: bool) -> np.ndarray:
+    f = np.ones(n_nodes, dtype=bool)
+    if lo_tag:
+        f[0] = False
+    if hi_tag:
+        f[-1] = False
+    return f
+
+
+def slab_ranges(n3: int, world: int):
+    """Cell layers [k0, k1) of every rank (contiguous, as even as possible)."""
+    base, rem = divmod(n3, world)
+    out, k = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((k, k + n))
+        k += n
+    return out
+
+
+def slab_problem(domain: Sequence[float], cells: Sequence[int], rank: int, world: int,
+                 dirichlet_boundary="boundary") -> SlabPart:
+    """Local Q1 problem of `rank` for GT.cartesian_mesh(domain, cells) + lagrange_space(Ω,1;dirichlet_boundary).
+    Global dof ids follow the reference numbering (hostprep.lagrange_space) restricted to Dirichlet patterns that
+    tag all 8 box corners (any side list containing at least one side per corner, or "boundary"), for which the
+    free dofs are numbered lexicographically by node."""
+    n1, n2, n3 = (int(c) for c in cells)
+    assert world >= 1 and 0 <= rank < world and n3 >= world
+    sides = list(range(1, 7)) if dirichlet_boundary == "boundary" else sorted(dirichlet_boundary or [])
+    fx = _free_1d(n1 + 1, 5 in sides, 6 in sides)
+    fy = _free_1d(n2 + 1, 3 in sides, 4 in sides)
+    fz = _free_1d(n3 + 1, 1 in sides, 2 in sides)
+    corners_free = [fx[i] and fy[j] and fz[k] for k in (0, n3) for j in (0, n2) for i in (0, n1)]
+    if any(corners_free):
+        raise ValueError("slab_problem needs every box corner on the Dirichlet boundary (lexicographic free numbering)")
+    k0, k1 = slab_ranges(n3, world)[rank]
+    kc0 = k0 - 1 if rank > 0 else k0                       # first local cell layer (symbolic halo below)
+    mesh_full_nodes_per_layer = (n1 + 1) * (n2 + 1)
+    # local mesh: cell layers [kc0, k1), node layers [kc0, k1]
+    pmin = np.array([domain[0], domain[2], domain[4]], dtype=np.float64)
+    pmax = np.array([domain[1], domain[3], domain[5]], dtype=np.float64)
+    h = (pmax - pmin) / np.array([n1, n2, n3], dtype=np.float64)
+    nzl = k1 - kc0
+    local = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (n1, n2, nzl))          # topology only
+    gi, gj, gk = np.meshgrid(np.arange(n1 + 1), np.arange(n2 + 1), np.arange(kc0, k1 + 1), indexing="ij")
+    coords = np.empty((local.n_nodes, 3))
+    coords[:, 0] = (pmin[0] + h[0] * gi.astype(np.float64)).reshape(-1, order="F")   # cartesian_mesh.jl:243-247
+    coords[:, 1] = (pmin[1] + h[1] * gj.astype(np.float64)).reshape(-1, order="F")
+    coords[:, 2] = (pmin[2] + h[2] * gk.astype(np.float64)).reshape(-1, order="F")
+    mesh = H.Mesh(3, coords, local.cell_nodes, (n1, n2, nzl), False, tuple(domain))
+    # free mask of the local nodes (global position decides), lexicographic local numbering
+    free = (fx[:, None, None] & fy[None, :, None] & fz[None, None, kc0:k1 + 1]).reshape(-1, order="F")
+    n_free_loc = int(free.sum())
+    node_dof = np.empty(local.n_nodes, dtype=np.int64)
+    node_dof[free] = np.arange(1, n_free_loc + 1)
+    node_dof[~free] = -np.arange(1, local.n_nodes - n_free_loc + 1)
+    cell_dofs = node_dof[mesh.cell_nodes.astype(np.int64) - 1].astype(np.int32)
+    per_layer = int(fx.sum()) * int(fy.sum())
+    below = int(fz[:kc0].sum()) * per_layer                    # global free dofs in node layers < kc0
+    row_gid = below + np.arange(1, n_free_loc + 1, dtype=np.int64)
+    # owner of every local free dof: node layer m belongs to the rank whose [k0,k1) contains m (top layer: last rank)
+    layer_of_dof = np.repeat(np.arange(kc0, k1 + 1), [per_layer if fz[m] else 0 for m in range(kc0, k1 + 1)])
+    starts = np.array([r[0] for r in slab_ranges(n3, world)])
+    row_owner = (np.searchsorted(starts, layer_of_dof, side="right") - 1).astype(np.int32)
+    space = H.LagrangeSpace(mesh, 1, 1, "Q", np.ascontiguousarray(cell_dofs), n_free_loc, local.n_nodes - n_free_loc,
+                            free_dof_nodes=coords[free], dirichlet_dof_nodes=coords[~free])
+    first_active = (k0 - kc0) * n1 * n2
+    return SlabPart(rank, world, mesh, space, (first_active, (k1 - k0) * n1 * n2), row_gid, row_owner,
+                    int(fz.sum()) * per_layer, k0, k1)
+
+
+# ---------------------------------------------------------------------------------------------
+# exchange plan
+# ---------------------------------------------------------------------------------------------
+def ghost_send_lists(part: SlabPart, colptr: np.ndarray, rowval: np.ndarray, touched_rows: Optional[np.ndarray] = None):
+    """Entries this rank sends: all stored nonzeros (and b rows) in rows owned by another rank that the rank's ACTIVE
+    cells contribute to.  → {peer: (nz_pos int64[], grow int64[], gcol int64[], b_rows int32[], b_grow int64[])},
+    in CSC storage order (the receive side relies on that order)."""
+    n = part.space.n_free
+    if touched_rows is None:
+        f, c = part.active_cells
+        d = part.space.cell_dofs[f:f + c].reshape(-1)
+        touched_rows = np.zeros(n, dtype=bool)
+        touched_rows[d[d > 0] - 1] = True
+    ghost = (part.row_owner != part.rank) & touched_rows
+    out = {}
+    if not ghost.any():
+        return out
+    rows0 = rowval.astype(np.int64) - 1
+    col_of_nz = np.repeat(np.arange(n, dtype=np.int64), np.diff(colptr.astype(np.int64)))
+    for peer in np.unique(part.row_owner[ghost]):
+        sel_rows = ghost & (part.row_owner == peer)
+        nz_pos = np.flatnonzero(sel_rows[rows0])
+        b_rows = np.flatnonzero(sel_rows).astype(np.int32)
+        out[int(peer)] = (nz_pos.astype(np.int64), part.row_gid[rows0[nz_pos]], part.row_gid[col_of_nz[nz_pos]],
+                          b_rows, part.row_gid[b_rows])
+    return out
+
+
+def match_received(part: SlabPart, colptr: np.ndarray, rowval: np.ndarray, grow: np.ndarray, gcol: np.ndarray,
+                   b_grow: np.ndarray):
+    """Owner side: positions in the local nzval / b where the values announced by a peer are added."""
+    gid = part.row_gid
+    lrow = np.searchsorted(gid, grow)
+    lcol = np.searchsorted(gid, gcol)
+    if (lrow >= gid.size).any() or (lcol >= gid.size).any() or (gid[lrow] != grow).any() or (gid[lcol] != gcol).any():
+        raise ValueError("a peer sent a ghost-row entry whose row/column is not a local dof of the owner")
+    cp = colptr.astype(np.int64) - 1
+    rv = rowval.astype(np.int64)
+    pos = np.empty(grow.size, dtype=np.int64)
+    # binary search of (lrow+1) inside each column segment (rows are sorted within a column)
+    lo, hi = cp[lcol].copy(), cp[lcol + 1].copy()
+    target = lrow + 1
+    while True:
+        act = lo < hi
+        if not act.any():
+            break
+        mid = (lo + hi) // 2
+        less = np.zeros_like(act)
+        less[act] = rv[mid[act]] < target[act]
+        lo = np.where(act & less, mid + 1, lo)
+        hi = np.where(act & ~less, mid, hi)
+    pos[:] = lo
+    if (pos >= cp[lcol + 1]).any() or (rv[np.minimum(pos, rv.size - 1)] != target).any():
+        raise ValueError("a received ghost-row entry is missing from the owner's sparsity pattern")
+    if np.unique(pos).size != pos.size:
+        raise ValueError("duplicate target in one peer's ghost-row message")
+    b_rows = np.searchsorted(gid, b_grow).astype(np.int32)
+    if b_grow.size and ((b_rows >= gid.size).any() or (gid[b_rows] != b_grow).any()):
+        raise ValueError("a received b row is not a local dof of the owner")
+    if (part.row_owner[lrow] != part.rank).any():
+        raise ValueError("received rows that this rank does not own")
+    return pos, b_rows
+
+
+def build_exchange_plan(part: SlabPart, colptr, rowval, alltoall_objects):
+    """alltoall_objects(list_of_per_rank_python_objects) -> list received from every rank (any transport:
+    torch.distributed over gloo/nccl, MPI, or an in-process fake).  Returns {peer: dict(send_nz, send_rows, recv_nz,
+    recv_rows)} ready for gtk_comm_set_exchange."""
+    sends = ghost_send_lists(part, colptr, rowval)
+    outbox = [None] * part.world
+    for peer, (nz_pos, grow, gcol, b_rows, b_grow) in sends.items():
+        outbox[peer] = (grow, gcol, b_grow)
+    inbox = alltoall_objects(outbox)
+    plan = {}
+    for peer, (nz_pos, grow, gcol, b_rows, b_grow) in sends.items():
+        plan.setdefault(peer, dict(send_nz=np.zeros(0, np.int64), send_rows=np.zeros(0, np.int32),
+                                   recv_nz=np.zeros(0, np.int64), recv_rows=np.zeros(0, np.int32)))
+        plan[peer]["send_nz"], plan[peer]["send_rows"] = nz_pos, b_rows
+    for peer, msg in enumerate(inbox):
+        if msg is None or peer == part.rank:
+            continue
+        grow, gcol, b_grow = msg
+        pos, b_rows = match_received(part, colptr, rowval, np.asarray(grow), np.asarray(gcol), np.asarray(b_grow))
+        plan.setdefault(peer, dict(send_nz=np.zeros(0, np.int64), send_rows=np.zeros(0, np.int32),
+                                   recv_nz=np.zeros(0, np.int64), recv_rows=np.zeros(0, np.int32)))
+        plan[peer]["recv_nz"], plan[peer]["recv_rows"] = pos, b_rows
+    return plan
+
+
+def torch_alltoall_objects(dist):
+    """Object all-to-all over an initialised torch.distributed process group (gloo on CPU, nccl on GPU)."""
+    def fn(outbox):
+        world = dist.get_world_size()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, outbox)
+        me = dist.get_rank()
+        return [gathered[src][me] for src in range(world)]
+    return fn
+
+
+def owned_rows_mask(part: SlabPart) -> np.ndarray:
+    return part.row_owner == part.rank
+
+
+def attach(engine, part: SlabPart, tab, dist):
+    """Load `part` into an Engine, build pattern + exchange plan, and connect the ranks over NCCL.
+    `dist` is an initialised torch.distributed module (any backend; only object collectives are used here —
+    the numeric data path is NCCL inside libgtkasm).  Returns (colptr, rowval, n_owned_nnz)."""
+    m, V = part.mesh, part.space
+    engine.set_mesh(m.node_coordinates, m.cell_nodes)
+    engine.set_space(V.cell_dofs, V.n_free, V.n_dirichlet)
+    engine.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+    engine.set_active_cells(*part.active_cells)
+    engine.matrix_symbolic()
+    engine.vector_symbolic()
+    colptr, rowval = engine.matrix_pattern()
+    plan = build_exchange_plan(part, colptr, rowval, torch_alltoall_objects(dist))
+    uid = [type(engine).comm_unique_id() if part.rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    engine.comm_init(part.rank, part.world, uid[0])
+    for peer in sorted(plan):
+        pl = plan[peer]
+        engine.comm_set_exchange(peer, pl["send_nz"], pl["send_rows"], pl["recv_nz"], pl["recv_rows"])
+    owned = owned_rows_mask(part)
+    n_owned_nnz = int(owned[rowval.astype(np.int64) - 1].sum())
+    return colptr, rowval, n_owned_nnz

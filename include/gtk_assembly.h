@@ -83,6 +83,10 @@ int32_t gtk_set_stream(gtk_ctx* ctx, void* cuda_stream);
  * (cartesian_mesh.jl:213-263; GalerkinToolkitExamples/src/poisson.jl:323-325). */
 int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz,
                      int64_t n_cells, int32_t n_lnodes, const int32_t* cell_nodes);
+/* Cells [first, first+count) (0-based) take part in the NUMERIC assembly; all cells take part in the symbolic
+ * phase.  Used by the multi-GPU partition: a rank adds the neighbour's boundary cell layer to its mesh so that the
+ * pattern of its own rows is complete, but assembles only the cells it owns.  Default: all cells. */
+int32_t gtk_set_active_cells(gtk_ctx* ctx, int64_t first, int64_t count);
 /* Replace coordinates only (geometry update before a numeric re-assembly). */
 int32_t gtk_update_coordinates(gtk_ctx* ctx, const double* xyz);
 /* face_dofs(V).data (space.jl:81-87, 372-417): [n_cells][n_ldofs], 1-based, < 0 = Dirichlet id
@@ -145,10 +149,16 @@ int32_t gtk_profile_get(gtk_ctx* ctx, int32_t i, char* name64, double* milliseco
 /* 128-byte ncclUniqueId produced on rank 0; the host broadcasts it by its own means. */
 int32_t gtk_comm_unique_id(void* id128);
 int32_t gtk_comm_init(gtk_ctx* ctx, int32_t rank, int32_t n_ranks, const void* id128);
-/* Rows (1-based, of the rank-local free numbering) [own_lo, own_hi] are owned by this rank.
- * Ghost rows below/above are summed into their owner (previous/next rank) in rank order —
- * PartitionedArrays.assemble! semantics.  Must be called after gtk_matrix_symbolic. */
-int32_t gtk_comm_setup_ghost_rows(gtk_ctx* ctx, int64_t own_lo, int64_t own_hi);
+/* Exchange plan with one peer rank, computed by the host (PartitionedArrays-style local_to_owner /
+ * local_to_global bookkeeping; see galerkintoolkit.jl_b200/partition.py):
+ *   send_nz[n_send_nz]  0-based positions in nzval of the ghost-row entries this rank sends to `peer`
+ *   send_rows[n_send_b] 0-based rows of b sent to `peer`
+ *   recv_nz / recv_rows where the values received from `peer` are ADDED (each position at most once per peer;
+ *                       the peer's send order must match this receive order).
+ * Must be called after gtk_matrix_symbolic; replaces any previous plan for that peer. */
+int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, const int64_t* send_nz,
+                              int64_t n_send_b, const int32_t* send_rows, int64_t n_recv_nz, const int64_t* recv_nz,
+                              int64_t n_recv_b, const int32_t* recv_rows);
 /* Exchange + add ghost-row nzval and b contributions after a numeric call. */
 int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx);
 /* key: 0 ghost nz entries sent per exchange  1 ghost nz entries received  2 bytes moved per exchange */

@@ -1,0 +1,73 @@
+"""Two-GPU test of the NCCL ghost-row path (needs >= 2 GPUs: run with `gpurun --gpus 2`)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, cells, dom, q):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        sys.path[:0] = [os.path.dirname(os.path.abspath(__file__))]
+        import gt_oracle as O
+        import gtk_b200
+        import importlib
+        P = importlib.import_module("galerkintoolkit_jl_b200.partition")
+        from util import problem, tab_dict
+        from test_partition import check_owned_rows
+        E = gtk_b200.engine
+        torch.cuda.set_device(rank)
+        mesh, V, tab = problem(cells, bc="boundary", domain=dom)
+        tabd = tab_dict(tab)
+        cp, rv, nz = O.assemble_matrix(O.LAPLACE, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, V.n_dirichlet, tabd)
+        bg = O.assemble_vector(O.SOURCE_CONST, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, V.n_dirichlet, tabd, f_const=[1.0])
+        A_glob = sp.csc_matrix((nz, rv.astype(np.int64) - 1, cp.astype(np.int64) - 1), shape=(V.n_free, V.n_free))
+        part = P.slab_problem(dom, cells, rank, world)
+        eng = E.Engine(rank)
+        colptr, rowval, n_owned = P.attach(eng, part, tab, dist)
+        results = []
+        for rep in range(3):
+            eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+            fast = eng.info(5)
+            eng.comm_sum_ghost_rows()
+            results.append((eng.copy_nzval(), eng.copy_vector()))
+        nzval, b = results[0]
+        check_owned_rows(part, colptr, rowval, nzval, b, A_glob, bg)
+        own = part.row_owner == part.rank
+        for nz_i, b_i in results[1:]:   # same GPU count => bitwise identical
+            assert nz_i[own[rowval - 1]].tobytes() == nzval[own[rowval - 1]].tobytes() and b_i[own].tobytes() == b[own].tobytes()
+        tot = torch.tensor([n_owned]); dist.all_reduce(tot)
+        assert int(tot.item()) == rv.size
+        eng.close()
+        dist.barrier(); dist.destroy_process_group()
+        q.put((rank, "ok", fast))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc(), -1))
+
+
+@pytest.mark.parametrize("cells", [(6, 5, 8), (20, 12, 17)])
+def test_two_gpu_ghost_rows_match_single_domain(cells):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cells, (0, 1, 0, 1, 0, 2), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg, fast in results:
+        assert msg == "ok", f"rank {rank}: {msg}"
+        assert fast == 1, "slab meshes must take the structured fast path"
