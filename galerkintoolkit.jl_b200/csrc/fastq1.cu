@@ -164,24 +164,20 @@ __device__ __forceinline__ void gather_entry(const double* __restrict__ base, do
     }
 }
 
-// All 27 entries of one column.  Finished values go to out[] already in CSC slot order:
-// slot(o) = number of present neighbours before o (popcount of the presence mask), or the
-// byte table for the rare columns whose dof numbering is not monotone in the neighbour order.
+// All 27 entries of one column.  Finished values go to out[O] (fixed position, no branches); the copy-out
+// compacts them into CSC slot order.
 template <int BX, int BY, int O>
 struct GatherAll {
   using C = Cfg<BX, BY>;
   static __device__ __forceinline__ void run(const double* __restrict__ base, double* __restrict__ pend,
-                                             double* __restrict__ out, unsigned mask, const uint8_t* __restrict__ tbl) {
+                                             double* __restrict__ out) {
     constexpr int dz = O / 9 - 1;
     double acc = 0.0, hi = 0.0;
     if (dz <= 0) acc = pend[O * C::NN];
     gather_entry<O, C::CX, C::KSTR>(base, acc, hi);
     if (dz <= 0) pend[O * C::NN] = hi;
-    if ((mask >> O) & 1u) {
-      const unsigned slot = tbl ? (unsigned)tbl[O] : (unsigned)__popc(mask & ((1u << O) - 1u));
-      out[slot] = acc;
-    }
-    if constexpr (O + 1 < 27) GatherAll<BX, BY, O + 1>::run(base, pend, out, mask, tbl);
+    out[O] = acc;
+    if constexpr (O + 1 < 27) GatherAll<BX, BY, O + 1>::run(base, pend, out);
   }
 };
 
@@ -215,15 +211,24 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
   const bool node_in_mesh = node_thread && (i0 + li <= n1) && (j0 + lj <= n2);
   const double* gbase = KeS + ((li + 1) + C::CX * (lj + 1)) * C::KSTR;
 
-  // asynchronous copy of one node layer (footprint + halo ring) into the ring slot (m+3)%3
+  // asynchronous copy of one node layer (footprint + halo ring) into the ring slot (m+3)%3; the per-thread
+  // source offsets inside a layer do not depend on the layer and are computed once
+  constexpr int NPF = (C::NP * 3 + C::NT - 1) / C::NT;
+  int pf_off[NPF];
+#pragma unroll
+  for (int r = 0; r < NPF; ++r) {
+    const int idx = t + r * C::NT;
+    const int nd = idx / 3, k = idx - nd * 3;
+    const int gi = i0 - 1 + nd % C::PX, gj = j0 - 1 + nd / C::PX;
+    pf_off[r] = (idx < C::NP * 3 && gi >= 0 && gi <= n1 && gj >= 0 && gj <= n2) ? (int)(3 * (gi + s1 * gj) + k) : -1;
+  }
   auto prefetch_nodes = [&](int m) {
     if (m >= 0 && m <= n3) {
-      double* dst = XS + ((m + 3) % 3) * (C::NP * 3);
-      for (int idx = t; idx < C::NP * 3; idx += C::NT) {
-        const int nd = idx / 3, k = idx - nd * 3;
-        const int gi = i0 - 1 + nd % C::PX, gj = j0 - 1 + nd / C::PX;
-        if (gi >= 0 && gi <= n1 && gj >= 0 && gj <= n2) cp_async8(dst + idx, a.xyz + 3 * (gi + s1 * gj + s2 * m) + k);
-      }
+      double* dst = XS + ((m + 3) % 3) * (C::NP * 3) + t;
+      const double* src = a.xyz + 3 * s2 * m;
+#pragma unroll
+      for (int r = 0; r < NPF; ++r)
+        if (pf_off[r] >= 0) cp_async8(dst + r * C::NT, src + pf_off[r]);
     }
     cp_async_commit();
   };
@@ -288,11 +293,7 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
     // ---- B) gather: thread per node, all 27 entries, compile-time offsets ----
     const int cur = ((L + 3) % 3) * C::NN;
     if (node_thread) {
-      if (a.do_matrix) {
-        const unsigned mask = L >= kz0 ? ColMask[cur + t] : 0u;     // 0: nothing to emit (halo layer / no column)
-        const uint8_t* tbl = (mask & 0x80000000u) ? a.slot_tbl + (size_t)ColIdx[cur + t] * 32 : nullptr;
-        GatherAll<BX, BY, 0>::run(gbase, Pend + t, OutS + t * 27, mask, tbl);
-      }
+      if (a.do_matrix) GatherAll<BX, BY, 0>::run(gbase, Pend + t, OutS + t * 27);
       if (a.do_vector) {
         double acc = PendB[t], hi = 0.0;
 #pragma unroll
@@ -309,17 +310,21 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
     }
     cp_async_wait_all();
     __syncthreads();
-    // ---- C) copy-out: column nl owns OutS[nl*27 .. +count); consecutive threads -> consecutive addresses ----
+    // ---- C) copy-out: one warp per column; lane o owns neighbour offset o and writes it to its CSC slot
+    //      slot(o) = number of present neighbours before o (popcount of the presence mask), or the byte table for
+    //      the rare columns whose dof numbering is not monotone in the neighbour order.  The lanes of a warp write
+    //      one contiguous run of nzval.
     if (a.do_matrix && L >= kz0) {
-      int nl = t / 27, sl = t - nl * 27;
-      constexpr int DN = C::NT / 27, DS = C::NT % 27;
+      const int lane = t & 31;
+      const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 4
-      for (int item = t; item < C::NN * 27; item += C::NT) {
-        const long long cb = ColBase[cur + nl];
-        const int cnt = __popc(ColMask[cur + nl] & 0x07FFFFFFu);
-        if (cb >= 0 && sl < cnt) a.nzval[cb + sl] = OutS[item];
-        nl += DN; sl += DS;
-        if (sl >= 27) { sl -= 27; nl += 1; }
+      for (int nl = t >> 5; nl < C::NN; nl += C::NT / 32) {
+        const unsigned mask = ColMask[cur + nl];
+        if ((mask >> lane) & 1u & (lane < 27)) {
+          unsigned slot = (unsigned)__popc(mask & lt);
+          if (mask & 0x80000000u) slot = a.slot_tbl[(size_t)ColIdx[cur + nl] * 32 + lane];
+          a.nzval[ColBase[cur + nl] + slot] = OutS[nl * 27 + lane];
+        }
       }
     }
   }
