@@ -18,6 +18,7 @@ void gtk_dev_free(gtk_ctx* ctx, void* p, size_t bytes) {
 }
 
 void gtk_fastq1_release(gtk_ctx* ctx);
+void gtk_fastq1_coords_changed(gtk_ctx* ctx);
 void gtk_comm_release(gtk_ctx* ctx);
 
 namespace {
@@ -109,6 +110,7 @@ int32_t gtk_update_coordinates(gtk_ctx* ctx, const double* xyz) {
   GTK_CK(cudaSetDevice(ctx->device));
   GTK_CK(cudaMemcpyAsync(ctx->xyz, xyz, sizeof(double) * (size_t)ctx->n_nodes * ctx->D, cudaMemcpyHostToDevice, ctx->stream));
   GTK_CK(cudaStreamSynchronize(ctx->stream));
+  gtk_fastq1_coords_changed(ctx);
   return GTK_OK;
 }
 

@@ -35,18 +35,31 @@ def test_fast_path_matches_oracle_and_generic(cells, bc, warp):
     cp, rv = eng.matrix_pattern()
     assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
     nz, b = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.5), E.FORM_SOURCE_CONST, dict(f_const=[2.0], alpha=0.5))
-    assert eng.info(5) == 1, "the structured fast path was not taken"
-    assert eng.info(0) == 1, "the fast path must be a single kernel launch"
+    fast = 2 if warp == 0.0 else 1       # 2: exactly-affine kernel (Cartesian coordinates), 1: general sweep kernel
+    assert eng.info(5) == fast, "the structured fast path was not taken"
+    assert eng.info(0) <= 2, "the fast path is a single kernel launch (+ one classification kernel per coordinate upload)"
     assert_values_close(nz, nzval)
     assert_values_close(b, b_ref)
     # matrix-only and vector-only entry points use the same kernel
     assert_values_close(eng.matrix_numeric(E.FORM_LAPLACE, alpha=1.5), nzval)
-    assert eng.info(5) == 1
+    assert eng.info(5) == fast and eng.info(0) == 1
     assert_values_close(eng.vector_assemble(E.FORM_SOURCE_CONST, f_const=[2.0], alpha=0.5), b_ref)
     # bit-reproducible
     nz2, b2 = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.5), E.FORM_SOURCE_CONST, dict(f_const=[2.0], alpha=0.5))
     assert nz2.tobytes() == nz.tobytes() and b2.tobytes() == b.tobytes()
     eng.close()
+    if fast == 2:   # the general sweep kernel on the same (affine) mesh
+        os.environ["GTK_DISABLE_AFFINE"] = "1"
+        try:
+            eng = make_engine(mesh, V, tab)
+            eng.matrix_symbolic()
+            nz_s, b_s = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.5), E.FORM_SOURCE_CONST, dict(f_const=[2.0], alpha=0.5))
+            assert eng.info(5) == 1
+            eng.close()
+        finally:
+            del os.environ["GTK_DISABLE_AFFINE"]
+        assert_values_close(nz, nz_s)
+        assert_values_close(b, b_s)
     # generic path of the same library
     os.environ["GTK_DISABLE_FASTPATH"] = "1"
     try:
@@ -59,6 +72,44 @@ def test_fast_path_matches_oracle_and_generic(cells, bc, warp):
         del os.environ["GTK_DISABLE_FASTPATH"]
     assert_values_close(nz, nz_g)
     assert_values_close(b, b_g)
+
+
+def _graded(mesh, cells):
+    """non-uniform tensor-product spacing: still exactly affine cells"""
+    X = mesh.node_coordinates
+    for d in range(3):
+        X[:, d] = X[:, d] ** (1.0 + 0.35 * d) * (1.0 + d) - 0.3 * d
+    return mesh
+
+
+@pytest.mark.parametrize("cells,bc", [((18, 9, 11), "boundary"), ((7, 5, 6), None), ((33, 17, 20), [2, 3])])
+def test_affine_kernel_on_graded_and_mixed_meshes(cells, bc):
+    mesh, V, tab = problem(cells, bc=bc)
+    _graded(mesh, cells)
+    colptr, rowval, nzval = oracle_matrix(O.LAPLACE, mesh, V, tab, alpha=0.75)
+    b_ref = oracle_vector(O.SOURCE_CONST, mesh, V, tab, f_const=[3.0])
+    eng = make_engine(mesh, V, tab)
+    eng.matrix_symbolic()
+    nz, b = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=0.75), E.FORM_SOURCE_CONST, dict(f_const=[3.0]))
+    assert eng.info(5) == 2, "graded Cartesian meshes are exactly affine"
+    assert_values_close(nz, nzval)
+    assert_values_close(b, b_ref)
+    import scipy.sparse as sp
+    A = sp.csc_matrix((nz, rowval.astype(np.int64) - 1, colptr.astype(np.int64) - 1), shape=(V.n_free, V.n_free))
+    assert abs(A - A.T).max() == 0.0, "the affine kernel keeps A bitwise symmetric"
+    # move ONE interior node: the classification must notice and the general kernel must take over
+    X = mesh.node_coordinates.copy()
+    inner = np.flatnonzero(~gtk_b200.hostprep.boundary_node_mask(mesh))
+    k = inner[len(inner) // 2]
+    X[k] += 1e-9
+    mesh.node_coordinates[:] = X
+    _, _, nzval2 = oracle_matrix(O.LAPLACE, mesh, V, tab, alpha=0.75)
+    eng.update_coordinates(X)
+    nz2 = eng.matrix_numeric(E.FORM_LAPLACE, alpha=0.75)
+    assert eng.info(5) == 1, "one non-affine cell must route the mesh to the general kernel"
+    assert_values_close(nz2, nzval2)
+    assert np.abs(nz2 - nz).max() > 0
+    eng.close()
 
 
 def test_fast_path_declines_what_it_does_not_cover():
@@ -95,7 +146,7 @@ def test_full_size_config2_invariants():
     assert nnz == (3 * (n - 1) - 2) ** 3 == 54439939
     cp, rv = eng.matrix_pattern()
     nz, b = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
-    assert eng.info(5) == 1
+    assert eng.info(5) == 2
     import scipy.sparse as sp
     A = sp.csc_matrix((nz, rv.astype(np.int64) - 1, cp.astype(np.int64) - 1), shape=(V.n_free, V.n_free))
     assert abs(A - A.T).max() == 0.0

@@ -70,4 +70,4 @@ def test_two_gpu_ghost_rows_match_single_domain(cells):
         p.join(timeout=60)
     for rank, msg, fast in results:
         assert msg == "ok", f"rank {rank}: {msg}"
-        assert fast == 1, "slab meshes must take the structured fast path"
+        assert fast in (1, 2), "slab meshes must take a structured fast path"
