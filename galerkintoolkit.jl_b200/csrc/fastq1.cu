@@ -31,6 +31,16 @@
 
 namespace {
 
+// Column record of one mesh node (one 16-byte load per node and layer, no dependent loads):
+//   cb   colptr of the node's matrix column (0-based), -1 when the node has no free dof
+//   mask bit o: neighbour offset o is a row of the column; bit 31: slots are not popcount-monotone (use slot_tbl)
+//   col  0-based column id (-1 when none)
+struct __align__(16) NodeCol {
+  long long cb;
+  unsigned mask;
+  int col;
+};
+
 struct FastPlan {
   int n1 = 0, n2 = 0, n3 = 0;        // cells per direction
   int64_t node_off = 0;              // mesh node id of node (0,0,0), minus 1
@@ -39,10 +49,15 @@ struct FastPlan {
   int32_t* dof_node = nullptr;       // [n_free]  node index of every free dof
   uint8_t* slot_tbl = nullptr;       // [n_free][32] slot of neighbour offset o in the column, 255 = absent
   uint32_t* col_mask = nullptr;      // [n_free] bit o: neighbour o present; bit 31: slots are not popcount-monotone
+  NodeCol* node_col = nullptr;       // [n_nodes]
   bool ok = false;
   bool tried = false;
   int affine_state = -1;             // -1 unknown (coordinates changed), 0 some cell is not affine, 1 every cell is exactly affine
   int* d_flag = nullptr;
+  // affine kernel launch plan (per footprint variant): z-segment length and per-CTA skip flags
+  uint8_t* tile_active = nullptr;
+  size_t ta_n = 0;
+  int ta_bx = 0, ta_by = 0, ta_seg = 0, ta_nseg = 0;
 };
 
 __global__ void k_verify_structure(const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ cell_dofs,
@@ -124,12 +139,25 @@ __global__ void k_slot_table(const int32_t* __restrict__ node_dof, const int32_t
   }
 }
 
+__global__ void k_node_col(const int32_t* __restrict__ node_dof, const int64_t* __restrict__ colptr,
+                           const uint32_t* __restrict__ col_mask, int64_t n_nodes, NodeCol* __restrict__ out) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < n_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    const int d = node_dof[n];
+    NodeCol r;
+    r.cb = -1; r.mask = 0; r.col = -1;
+    if (d > 0) { r.col = d - 1; r.cb = colptr[d - 1]; r.mask = col_mask[d - 1]; }
+    out[n] = r;
+  }
+}
+
 struct SweepArgs {
   const double* xyz;
+  const NodeCol* node_col;
   const int32_t* node_dof;
   const int64_t* colptr;
   const uint8_t* slot_tbl;
   const uint32_t* col_mask;
+  const uint8_t* tile_active;   // affine kernel: per-CTA skip flags (nullptr = all active)
   double* nzval;
   double* b;
   int n1, n2, n3;
@@ -263,8 +291,8 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
     // column info of node layer L+1 (consumed one step later): loads issued now, stored after the FP64 work
     long long cbn = -1; int coln = -1; unsigned maskn = 0;
     if (node_in_mesh && L + 1 <= n3 && L + 1 < kz1) {
-      int d = __ldg(a.node_dof + (i0 + li) + s1 * (j0 + lj) + s2 * (L + 1));
-      if (d > 0) { coln = d - 1; cbn = __ldg(a.colptr + coln); maskn = __ldg(a.col_mask + coln); }
+      const int4 nc = __ldg(reinterpret_cast<const int4*>(a.node_col + (i0 + li) + s1 * (j0 + lj) + s2 * (L + 1)));
+      cbn = ((long long)(unsigned)nc.y << 32) | (unsigned)nc.x; maskn = (unsigned)nc.z; coln = nc.w;
     }
     // ---- A) element matrices of cell layer L ----
     if (cell_ok) {
@@ -371,12 +399,12 @@ template <int BX, int BY>
 struct ACfg {
   static constexpr int CX = BX + 1, CY = BY + 1, NC = CX * CY, NN = BX * BY;
   static constexpr int PX = BX + 2, PY = BY + 2, NP = PX * PY;
-  static constexpr int NT = NN;
+  static constexpr int NT = ((NC + 31) / 32) * 32;   // one thread per cell of a layer; threads t < NN also own a node
   static constexpr int CSTR = 7;    // doubles per cell: A0 A1 A2 B01 B02 B12 bv (odd stride: conflict-free)
-  static_assert(NN % 32 == 0, "footprint must be a whole number of warps");
-  // CellS[NC][7] | OutS[NN][27] | XS[3][NP][3] | ColBase[NN] (i64) | ColIdx[NN] | ColMask[NN]
-  static constexpr size_t SMEM = sizeof(double) * ((size_t)NC * CSTR + (size_t)NN * 27 + 3 * NP * 3) +
-                                 sizeof(long long) * NN + sizeof(int) * 2 * NN;
+  static constexpr int OSTR = 28;   // doubles per column in OutS: 27 entries + 1 so that the 16-byte phase can follow nzval
+  static_assert(NN % 32 == 0, "node threads must be whole warps");
+  // OutS[NN][28] | CellS[2][NC][7] | XS[4][NP][3]
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)NN * OSTR + 2 * (size_t)NC * CSTR + 4 * NP * 3);
 };
 
 // Contribution of one affine cell to the entry (row = local node I, column = local node J), added to acc.
@@ -406,22 +434,38 @@ __host__ __device__ constexpr int off_index() {
   return ((I & 1) - (J & 1) + 1) + 3 * (((I >> 1) & 1) - ((J >> 1) & 1) + 1) + 9 * (((I >> 2) & 1) - ((J >> 2) & 1) + 1);
 }
 
-// all 8 rows of column node J of one cell; dst is indexed by the neighbour offset (minus SHIFT)
-template <int J, int SHIFT, int... I>
+// all 8 rows of column node J of one cell; dst is indexed by the neighbour offset
+template <int J, int... I>
 __device__ __forceinline__ void affine_column(const double (&c)[6], double* dst, std::integer_sequence<int, I...>) {
-  (affine_entry<J, I>(c, dst[off_index<J, I>() - SHIFT]), ...);
+  (affine_entry<J, I>(c, dst[off_index<J, I>()]), ...);
 }
+
+template <int O>
+__device__ __forceinline__ void store_permuted(const double (&acc)[27], unsigned mask, const uint8_t* __restrict__ tbl,
+                                               double* __restrict__ dst) {
+  if ((mask >> O) & 1u) dst[tbl[O]] = acc[O];
+  if constexpr (O + 1 < 27) store_permuted<O + 1>(acc, mask, tbl, dst);
+}
+
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+// TMA bulk store shared -> global (UBLKCP): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 template <int BX, int BY, int MINB>
 __global__ void __launch_bounds__(ACfg<BX, BY>::NT, MINB) k_q1hex_affine(SweepArgs a) {
   using C = ACfg<BX, BY>;
-  extern __shared__ double sm[];
-  double* CellS = sm;                                   // [NC][7]  cell data of the current cell layer
-  double* OutS = CellS + C::NC * C::CSTR;               // [NN][27] finished columns of one node layer
-  double* XS = OutS + C::NN * 27;                       // [3][NP][3] ring of node-coordinate layers
-  long long* ColBase = (long long*)(XS + 3 * C::NP * 3);   // [NN] colptr of the columns in OutS
-  int* ColIdx = (int*)(ColBase + C::NN);                // [NN]
-  unsigned* ColMask = (unsigned*)(ColIdx + C::NN);      // [NN]
+  if (a.tile_active && !a.tile_active[blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)]) return;
+  extern __shared__ __align__(16) double sm[];
+  double* OutS = sm;                                    // [NN][28] one finished column per node thread
+  double* CellS = OutS + C::NN * C::OSTR;               // [2][NC][7] cell data, double-buffered over cell layers
+  double* XS = CellS + 2 * C::NC * C::CSTR;             // [4][NP][3] ring of node-coordinate layers (3 ahead)
 
   const int t = threadIdx.x;
   const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY;
@@ -429,10 +473,19 @@ __global__ void __launch_bounds__(ACfg<BX, BY>::NT, MINB) k_q1hex_affine(SweepAr
   const int kz1 = min(kz0 + a.seg_len, a.n3 + 1);
   const int n1 = a.n1, n2 = a.n2, n3 = a.n3;
   const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  const bool node_thread = t < C::NN;
   const int li = t % BX, lj = t / BX;
-  const bool node_in_mesh = (i0 + li <= n1) && (j0 + lj <= n2);
-  const int64_t node_xy = (i0 + li) + s1 * (j0 + lj);
-  const double* cbase = CellS + (li + C::CX * lj) * C::CSTR;   // cell (u,v) of this node: cbase + (u + CX v) * CSTR
+  const bool node_in_mesh = node_thread && (i0 + li <= n1) && (j0 + lj <= n2);
+  const NodeCol* ncp = a.node_col + (i0 + li) + s1 * (j0 + lj);
+  const int nbase = (li + C::CX * lj) * C::CSTR;       // cell (u,v) of this node: nbase + (u + CX v) * CSTR
+  double* orow = OutS + (node_thread ? t : 0) * C::OSTR;
+  // cell role: thread t owns cell (cx, cy) of every layer
+  const int cx = t % C::CX, cy = t / C::CX;
+  const bool cell_ok = t < C::NC && (i0 - 1 + cx) >= 0 && (i0 - 1 + cx) < n1 && (j0 - 1 + cy) >= 0 && (j0 - 1 + cy) < n2;
+  const int coff = (t < C::NC ? t : 0) * C::CSTR;
+  const int xoff = 3 * (cx + C::PX * cy);
+  const int lane = t & 31;
+  const unsigned lt = (1u << lane) - 1u;
 
   constexpr int NPF = (C::NP * 3 + C::NT - 1) / C::NT;
   int pf_off[NPF];
@@ -445,7 +498,7 @@ __global__ void __launch_bounds__(ACfg<BX, BY>::NT, MINB) k_q1hex_affine(SweepAr
   }
   auto prefetch_nodes = [&](int m) {
     if (m >= 0 && m <= n3) {
-      double* dst = XS + ((m + 3) % 3) * (C::NP * 3) + t;
+      double* dst = XS + (m & 3) * (C::NP * 3) + t;
       const double* src = a.xyz + 3 * s2 * m;
 #pragma unroll
       for (int r = 0; r < NPF; ++r)
@@ -453,48 +506,36 @@ __global__ void __launch_bounds__(ACfg<BX, BY>::NT, MINB) k_q1hex_affine(SweepAr
     }
     cp_async_commit();
   };
-  // copy-out of the node layer held in OutS: one warp per column, lane o owns neighbour offset o
-  auto copy_out = [&]() {
-    const int lane = t & 31;
-    const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 4
-    for (int nl = t >> 5; nl < C::NN; nl += C::NT / 32) {
-      const unsigned mask = ColMask[nl];
-      if ((mask >> lane) & 1u & (lane < 27)) {
-        unsigned slot = (unsigned)__popc(mask & lt);
-        if (mask & 0x80000000u) slot = a.slot_tbl[(size_t)ColIdx[nl] * 32 + lane];
-        a.nzval[ColBase[nl] + slot] = OutS[nl * 27 + lane];
-      }
-    }
-  };
 
-  prefetch_nodes(kz0 - 1);
-  prefetch_nodes(kz0);
   double pend[18], pendb = 0.0;   // contributions of the cell layer below to the next node layer (this thread's node)
 #pragma unroll
   for (int o = 0; o < 18; ++o) pend[o] = 0.0;
-  bool have_out = false;
-  cp_async_wait_all();
+  if (t < C::NC) {
+#pragma unroll
+    for (int e = 0; e < 2 * C::CSTR; ++e) CellS[(e / C::CSTR) * C::NC * C::CSTR + coff + e % C::CSTR] = 0.0;   // cells outside the mesh stay zero
+  }
+  int4 ncn = make_int4(-1, -1, 0, -1);   // NodeCol of the next node layer (none for the halo step)
+  prefetch_nodes(kz0 - 1);               // kz0 - 1 may be -1: an empty group keeps the group count uniform
+  prefetch_nodes(kz0);
+  prefetch_nodes(kz0 + 1);
+  cp_async_wait_1();
   __syncthreads();
 
   for (int L = kz0 - 1; L < kz1; ++L) {
     const bool layer_ok = L >= a.kact0 && L < a.kact1;
-    prefetch_nodes(L + 2);
-    // column of this thread's node in node layer L (consumed after the cell phase)
-    long long cb = -1; int col = -1; unsigned mask = 0;
-    if (node_in_mesh && L >= kz0) {
-      const int d = __ldg(a.node_dof + node_xy + s2 * L);
-      if (d > 0) { col = d - 1; cb = __ldg(a.colptr + col); mask = __ldg(a.col_mask + col); }
-    }
-    if (have_out) copy_out();                            // node layer L-1 (stores drain during the cell phase)
-    // ---- A) six numbers + source weight per cell of layer L ----
-    for (int c = t; c < C::NC; c += C::NT) {
-      const int cx = c % C::CX, cy = c / C::CX;
-      const int ci = i0 - 1 + cx, cj = j0 - 1 + cy;
-      double* cs = CellS + c * C::CSTR;
-      if (layer_ok && ci >= 0 && ci < n1 && cj >= 0 && cj < n2) {
-        const double* x0 = XS + ((L + 3) % 3) * (C::NP * 3) + 3 * (cx + C::PX * cy);
-        const double* x4 = XS + ((L + 4) % 3) * (C::NP * 3) + 3 * (cx + C::PX * cy);
+    const bool emit = L >= kz0;
+    // column record of this thread's node: layer L was loaded one step ago, layer L+1 is requested now
+    const long long cb = ((long long)(unsigned)ncn.y << 32) | (unsigned)ncn.x;
+    unsigned mask = (unsigned)ncn.z;
+    const int col = ncn.w;
+    ncn = make_int4(-1, -1, 0, -1);
+    if (node_in_mesh && L + 1 < kz1) ncn = __ldg(reinterpret_cast<const int4*>(ncp + s2 * (L + 1)));
+    // ---- A) six numbers + source weight per cell of layer L (needs node layers L and L+1) ----
+    double* cs = CellS + (L & 1) * (C::NC * C::CSTR) + coff;
+    if (cell_ok) {
+      if (layer_ok) {
+        const double* x0 = XS + (L & 3) * (C::NP * 3) + xoff;
+        const double* x4 = XS + ((L + 1) & 3) * (C::NP * 3) + xoff;
         double c0[3], c1[3], c2[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -520,9 +561,11 @@ __global__ void __launch_bounds__(ACfg<BX, BY>::NT, MINB) k_q1hex_affine(SweepAr
         for (int e = 0; e < C::CSTR; ++e) cs[e] = 0.0;
       }
     }
-    __syncthreads();
+    prefetch_nodes(L + 3);      // slot (L-1)&3: last read in the cell phase of step L-1, before the previous barrier
+    cp_async_wait_1();          // node layer L+2 (this thread's part) has landed; only group L+3 may be pending
+    __syncthreads();            // the ONLY block barrier of a step: cell layer L and node layer L+2 are visible
     // ---- B) this thread's node: finish node layer L (cells below are in pend), start node layer L+1 ----
-    {
+    if (node_thread) {
       double acc[27], accb = pendb;
 #pragma unroll
       for (int o = 0; o < 18; ++o) acc[o] = pend[o];
@@ -532,33 +575,258 @@ __global__ void __launch_bounds__(ACfg<BX, BY>::NT, MINB) k_q1hex_affine(SweepAr
       for (int o = 0; o < 18; ++o) pend[o] = 0.0;
       pendb = 0.0;
       using Rows = std::make_integer_sequence<int, 8>;
+      const double* cl = CellS + (L & 1) * (C::NC * C::CSTR) + nbase;
       // cells in increasing cell id (the reference's push order): v outer, u inner
-#define GTK_AFF_CELL(U, V)                                                              \
-      {                                                                                   \
-        const double* cs = cbase + ((U) + C::CX * (V)) * C::CSTR;                         \
-        const double c6[6] = {cs[0], cs[1], cs[2], cs[3], cs[4], cs[5]};                  \
-        const double bv = cs[6];                                                          \
-        constexpr int JB = (1 - (U)) + 2 * (1 - (V));       /* node is a bottom node */   \
-        affine_column<JB, 0>(c6, acc, Rows{});                                            \
-        affine_column<JB + 4, 0>(c6, pend, Rows{});         /* ... and a top node   */    \
-        accb += bv; pendb += bv;                                                          \
+#define GTK_AFF_CELL(U, V)                                                                 \
+      {                                                                                      \
+        const double* cc = cl + ((U) + C::CX * (V)) * C::CSTR;                               \
+        const double c6[6] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5]};                     \
+        const double bv = cc[6];                                                             \
+        constexpr int JB = (1 - (U)) + 2 * (1 - (V));                                        \
+        if (emit) { affine_column<JB>(c6, acc, Rows{}); accb += bv; }   /* bottom node */   \
+        affine_column<JB + 4>(c6, pend, Rows{}); pendb += bv;           /* top node    */   \
       }
       GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
 #undef GTK_AFF_CELL
-      if (L >= kz0) {
-        if (a.do_matrix) {
-#pragma unroll
-          for (int o = 0; o < 27; ++o) OutS[t * 27 + o] = acc[o];
-          ColBase[t] = cb; ColIdx[t] = col; ColMask[t] = mask;
-        }
+      if (emit) {
         if (a.do_vector && col >= 0) a.b[col] = accb;
+        if (a.do_matrix) {
+          // ---- C) copy-out, warp-local (no block barrier): the column goes to shared memory with the same
+          // 16-byte phase as its run of nzval, then one TMA bulk store moves the 26 aligned entries and a scalar
+          // store the odd one.  Columns with fewer than 27 entries are compacted by the warp, lane o -> slot.
+          if (mask & 0x80000000u) {   // rare: slots not monotone in the neighbour order -> permuted stores from registers
+            store_permuted<0>(acc, mask, a.slot_tbl + (size_t)col * 32, a.nzval + cb);
+            mask = 0;
+          }
+          const bool full = mask == 0x07FFFFFFu;
+          const int ph = (int)(cb & 1);
+          bulk_wait_read();                        // the previous layer's bulk store has finished reading this row
+          __syncwarp();                            // ... and the warp has finished compacting it
+#pragma unroll
+          for (int o = 0; o < 27; ++o) orow[ph + o] = acc[o];
+          fence_async_smem();
+          if (full) {
+            double* dst = a.nzval + cb;
+            bulk_store(dst + ph, orow + 2 * ph, 26 * sizeof(double));
+            bulk_commit();
+            dst[ph ? 0 : 26] = ph ? acc[0] : acc[26];
+          }
+          unsigned irr = __ballot_sync(0xFFFFFFFFu, mask != 0 && !full);
+          __syncwarp();
+          while (irr) {
+            const int n = __ffs(irr) - 1;
+            irr &= irr - 1;
+            const unsigned m = __shfl_sync(0xFFFFFFFFu, mask, n);
+            const long long cbn = __shfl_sync(0xFFFFFFFFu, cb, n);
+            if ((m >> lane) & 1u) a.nzval[cbn + __popc(m & lt)] = OutS[((t & ~31) + n) * C::OSTR + (int)(cbn & 1) + lane];
+          }
+        }
       }
     }
-    cp_async_wait_all();
-    __syncthreads();
-    have_out = a.do_matrix && L >= kz0;
   }
-  if (have_out) copy_out();
+  bulk_wait_read();   // shared memory must outlive the bulk stores reading it
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-private variant of the affine sweep: every warp owns a 16 x 2 patch of nodes and sweeps its
+// z-segment on its own.  No block barrier exists in the kernel — lanes exchange cell data and finished
+// columns through the warp's private slice of shared memory under __syncwarp — so the 16 resident warps
+// of an SM run fully decoupled and hide each other's FP64 and memory latencies.
+//   per step (cell layer L):
+//     A) the 17 x 3 cells around the patch, two passes over the lanes: six numbers + source weight per cell
+//     B) lane = node: 27 entries of node layer L (bottom role) + the 18 pending ones of layer L+1 (top role)
+//     C) a row of 16 full, contiguous columns leaves as ONE TMA bulk store (UBLKCP) of 3456 B; anything else is
+//        compacted by the warp (lane o -> slot popcount(mask below o)).
+// ------------------------------------------------------------------------------------------------
+struct WCfg {
+  static constexpr int BX = 16, BY = 2, CX = 17, CY = 3, NC = 51;
+  static constexpr int CSTR = 7;
+  static constexpr int ROWS = 434;                     // 16 * 27 + 1 (phase) + 1 (keeps rows 16-byte aligned)
+  static constexpr int CELL_D = ((NC * CSTR + 1) / 2) * 2;
+  static constexpr int WARP_D = CELL_D + 2 * ROWS;     // doubles of shared memory per warp
+};
+
+template <int WPB, int MINB>
+__global__ void __launch_bounds__(WPB * 32, MINB) k_q1hex_affine_w(SweepArgs a) {
+  using C = WCfg;
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int py = blockIdx.y * WPB + w;                 // patch row
+  const int gyp = (a.n2 + 1 + C::BY - 1) / C::BY;      // patch rows in the mesh
+  if (py >= gyp) return;
+  if (a.tile_active && !a.tile_active[blockIdx.x + gridDim.x * (py + (int64_t)gyp * blockIdx.z)]) return;
+  double* OutW = sm + w * C::WARP_D;                   // [2][ROWS]
+  double* CellW = OutW + 2 * C::ROWS;                  // [NC][7]
+
+  const int i0 = blockIdx.x * C::BX, j0 = py * C::BY;
+  const int kz0 = blockIdx.z * a.seg_len;
+  const int kz1 = min(kz0 + a.seg_len, a.n3 + 1);
+  const int n1 = a.n1, n2 = a.n2;
+  const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  const int li = lane & 15, lj = lane >> 4;
+  const bool node_in_mesh = (i0 + li <= n1) && (j0 + lj <= n2);
+  const NodeCol* ncp = a.node_col + (i0 + li) + s1 * (j0 + lj);
+  const double* cl = CellW + (li + C::CX * lj) * C::CSTR;     // cell (u,v) of this node: cl + (u + CX v) * CSTR
+  double* orow = OutW + lj * C::ROWS;
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned rowbits = 0xFFFFu << (lane & 16);
+  // the two cells this lane computes in every layer
+  int64_t cnode[2]; bool cok[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int c = lane + 32 * p;
+    const int cx = c % C::CX, cy = c / C::CX;
+    const int gi = i0 - 1 + cx, gj = j0 - 1 + cy;
+    cok[p] = c < C::NC && gi >= 0 && gi < n1 && gj >= 0 && gj < n2;
+    cnode[p] = cok[p] ? gi + s1 * gj : 0;
+    if (c < C::NC && !cok[p]) {
+#pragma unroll
+      for (int e = 0; e < C::CSTR; ++e) CellW[c * C::CSTR + e] = 0.0;   // cells outside the mesh stay zero
+    }
+  }
+  double pend[18], pendb = 0.0;
+#pragma unroll
+  for (int o = 0; o < 18; ++o) pend[o] = 0.0;
+  int4 ncn = make_int4(-1, -1, 0, -1);
+  bool bulk_pending = false;
+
+  for (int L = kz0 - 1; L < kz1; ++L) {
+    const bool layer_ok = L >= a.kact0 && L < a.kact1;
+    const bool emit = L >= kz0;
+    const long long cb = ((long long)(unsigned)ncn.y << 32) | (unsigned)ncn.x;
+    unsigned mask = (unsigned)ncn.z;
+    const int col = ncn.w;
+    ncn = make_int4(-1, -1, 0, -1);
+    if (node_in_mesh && L + 1 < kz1) ncn = __ldg(reinterpret_cast<const int4*>(ncp + s2 * (L + 1)));
+    // ---- A) cells of layer L ----
+    __syncwarp();                                      // node phase of the previous step has read CellW
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (cok[p]) {
+        double* cs = CellW + (lane + 32 * p) * C::CSTR;
+        if (layer_ok) {
+          const double* x = a.xyz + 3 * (cnode[p] + s2 * L);
+          if (L + 2 <= a.n3) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + 3 * s2 * 2));   // next step's top nodes
+          if (L + 5 <= a.n3) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + 3 * s2 * 5));
+          double c0[3], c1[3], c2[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const double X0 = __ldg(x + k);
+            c0[k] = __ldg(x + 3 + k) - X0; c1[k] = __ldg(x + 3 * s1 + k) - X0; c2[k] = __ldg(x + 3 * s2 + k) - X0;
+          }
+          const double r0[3] = {c1[1] * c2[2] - c1[2] * c2[1], c1[2] * c2[0] - c1[0] * c2[2], c1[0] * c2[1] - c1[1] * c2[0]};
+          const double r1[3] = {c2[1] * c0[2] - c2[2] * c0[1], c2[2] * c0[0] - c2[0] * c0[2], c2[0] * c0[1] - c2[1] * c0[0]};
+          const double r2[3] = {c0[1] * c1[2] - c0[2] * c1[1], c0[2] * c1[0] - c0[0] * c1[2], c0[0] * c1[1] - c0[1] * c1[0]};
+          const double det = c0[0] * r0[0] + c0[1] * r0[1] + c0[2] * r0[2];
+          const double ad = fabs(det);
+          const double s = q1hex::W8 * q1hex::fast_rcp<double>(ad);
+          const double sd = a.alpha * (2.0 / 9.0) * s, so = a.alpha * (2.0 / 3.0) * s;
+          cs[0] = sd * (r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]);
+          cs[1] = sd * (r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+          cs[2] = sd * (r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
+          cs[3] = so * (r0[0] * r1[0] + r0[1] * r1[1] + r0[2] * r1[2]);
+          cs[4] = so * (r0[0] * r2[0] + r0[1] * r2[1] + r0[2] * r2[2]);
+          cs[5] = so * (r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2]);
+          cs[6] = a.fscale * (q1hex::W8 * ad);
+        } else {
+#pragma unroll
+          for (int e = 0; e < C::CSTR; ++e) cs[e] = 0.0;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- B) this lane's node ----
+    double acc[27], accb = pendb;
+#pragma unroll
+    for (int o = 0; o < 18; ++o) acc[o] = pend[o];
+#pragma unroll
+    for (int o = 18; o < 27; ++o) acc[o] = 0.0;
+#pragma unroll
+    for (int o = 0; o < 18; ++o) pend[o] = 0.0;
+    pendb = 0.0;
+    using Rows = std::make_integer_sequence<int, 8>;
+#define GTK_AFF_CELL(U, V)                                                               \
+    {                                                                                      \
+      const double* cc = cl + ((U) + C::CX * (V)) * C::CSTR;                               \
+      const double c6[6] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5]};                     \
+      const double bv = cc[6];                                                             \
+      constexpr int JB = (1 - (U)) + 2 * (1 - (V));                                        \
+      if (emit) { affine_column<JB>(c6, acc, Rows{}); accb += bv; }                        \
+      affine_column<JB + 4>(c6, pend, Rows{}); pendb += bv;                                \
+    }
+    GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
+#undef GTK_AFF_CELL
+    if (emit) {
+      if (a.do_vector && col >= 0) a.b[col] = accb;
+      if (a.do_matrix) {
+        // ---- C) copy-out ----
+        if (mask & 0x80000000u) {   // rare: slots not monotone in the neighbour order -> permuted stores from registers
+          store_permuted<0>(acc, mask, a.slot_tbl + (size_t)col * 32, a.nzval + cb);
+          mask = 0;
+        }
+        // runs of full 27-entry columns that are contiguous in nzval leave as one TMA bulk store each; the row is laid
+        // out in shared memory with the 16-byte phase of its first run, runs of the other phase fall back to the
+        // warp-cooperative path together with the columns that have fewer than 27 entries
+        const long long cbp = __shfl_up_sync(0xFFFFFFFFu, cb, 1);
+        const bool full = mask == 0x07FFFFFFu;
+        const unsigned fullb = __ballot_sync(0xFFFFFFFFu, full);
+        const bool link = full && li > 0 && ((fullb >> (lane - 1)) & 1u) && cb == cbp + 27;    // continues the run of lane-1
+        const unsigned linkb = __ballot_sync(0xFFFFFFFFu, link) & rowbits;
+        const unsigned startb = fullb & ~linkb & rowbits;                                     // run starts of this row
+        const int first = startb ? __ffs(startb) - 1 : (lane & 16);
+        const int ph = __shfl_sync(0xFFFFFFFFu, (int)((cb + li) & 1), first);                  // phase of the row
+        const bool is_start = full && !link;
+        const unsigned up = (linkb >> lane) >> 1;                                              // link bits of the lanes above
+        const int len = __ffs(~up);                                                            // columns in the run starting here
+        const bool my_ok = is_start && (int)((cb + li) & 1) == ph;
+        // every lane learns whether the run it belongs to goes out as a bulk store: start lane = highest start bit <= lane
+        const unsigned okb = __ballot_sync(0xFFFFFFFFu, my_ok);
+        const unsigned below = (fullb & ~linkb) & ((lt << 1) | 1u);                            // run starts at or below this lane
+        const bool in_bulk = full && below && ((okb >> (31 - __clz(below))) & 1u);
+        if (bulk_pending) bulk_wait_read();        // the bulk store of the previous layer has read this row
+        __syncwarp();                              // ... and the warp has finished compacting the others
+        double* mine = orow + ph + li * 27;
+#pragma unroll
+        for (int o = 0; o < 27; ++o) mine[o] = acc[o];
+        fence_async_smem();
+        __syncwarp();
+        bulk_pending = false;
+        if (in_bulk) {
+          if (my_ok) {
+            const int head = (int)(cb & 1);
+            bulk_store(a.nzval + cb + head, mine + head, (unsigned)(((27 * len - head) & ~1) * sizeof(double)));
+            bulk_commit();
+            bulk_pending = true;
+            if (head) a.nzval[cb] = acc[0];                          // lone first element (odd index)
+          }
+          const bool is_end = !(up & 1u);
+          if (is_end && !(cb & 1)) a.nzval[cb + 26] = acc[26];       // lone last element (even index)
+        }
+        unsigned irr = __ballot_sync(0xFFFFFFFFu, mask != 0 && !in_bulk);
+        while (irr) {
+          const int n = __ffs(irr) - 1;
+          irr &= irr - 1;
+          const unsigned m = __shfl_sync(0xFFFFFFFFu, mask, n);
+          const long long cbn = __shfl_sync(0xFFFFFFFFu, cb, n);
+          const int phn = __shfl_sync(0xFFFFFFFFu, ph, n);
+          if ((m >> lane) & 1u) a.nzval[cbn + __popc(m & lt)] = OutW[(n >> 4) * C::ROWS + phn + (n & 15) * 27 + lane];
+        }
+      }
+    }
+  }
+  if (bulk_pending) bulk_wait_read();   // shared memory must outlive the bulk store reading it
+}
+
+// tile_active[x + gx (y + gy z)] = 1 when the tile's footprint x z-segment holds at least one matrix column
+__global__ void k_tile_active(const int32_t* __restrict__ node_dof, int n1, int n2, int n3, int bx, int by, int seg_len,
+                              int gx, int gy, uint8_t* __restrict__ active) {
+  const int64_t nn = (int64_t)(n1 + 1) * (n2 + 1) * (n3 + 1);
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    if (node_dof[n] > 0) {
+      const int i = (int)(n % (n1 + 1)), j = (int)((n / (n1 + 1)) % (n2 + 1)), k = (int)(n / ((int64_t)(n1 + 1) * (n2 + 1)));
+      active[i / bx + gx * (j / by + gy * (k / seg_len))] = 1;
+    }
+  }
 }
 
 inline int grid_for(int64_t n, int block) {
@@ -572,7 +840,9 @@ void plan_free(gtk_ctx* ctx, FastPlan* p) {
   if (p->dof_node) gtk_dev_free(ctx, p->dof_node, sizeof(int32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   if (p->slot_tbl) gtk_dev_free(ctx, p->slot_tbl, (size_t)32 * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   if (p->col_mask) gtk_dev_free(ctx, p->col_mask, sizeof(uint32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
+  if (p->node_col) gtk_dev_free(ctx, p->node_col, sizeof(NodeCol) * (size_t)p->n_nodes);
   if (p->d_flag) cudaFree(p->d_flag);
+  if (p->tile_active) gtk_dev_free(ctx, p->tile_active, p->ta_n);
   delete p;
 }
 
@@ -632,6 +902,9 @@ int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
   k_slot_table<<<grid_for(ctx->n_free, 128), 128, 0, st>>>(p->node_dof, p->dof_node, ctx->ms.colptr, ctx->ms.rowval,
                                                          ctx->n_free, p->n1, p->n2, p->n3, p->slot_tbl, p->col_mask, d_bad);
   GTK_CK(cudaGetLastError());
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->node_col, sizeof(NodeCol) * (size_t)n_nodes))) return rc;
+  k_node_col<<<grid_for(n_nodes, 256), 256, 0, st>>>(p->node_dof, ctx->ms.colptr, p->col_mask, n_nodes, p->node_col);
+  GTK_CK(cudaGetLastError());
   int bad = 1;
   GTK_CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
   GTK_CK(cudaStreamSynchronize(st));
@@ -668,18 +941,111 @@ int32_t launch_affine(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   SweepArgs a = a0;
   const int gx = (p->n1 + 1 + BX - 1) / BX, gy = (p->n2 + 1 + BY - 1) / BY;
   const int layers = p->n3 + 1;
-  const char* ws = getenv("GTK_AFFINE_WAVES");
-  const int waves = ws ? atoi(ws) : 4;
-  int64_t slots = (int64_t)ctx->sm_count * MINB;
-  int nseg = (int)((waves * slots + (int64_t)gx * gy - 1) / ((int64_t)gx * gy));
-  if (nseg < 1) nseg = 1;
-  int max_seg = (layers + 7) / 8;
-  if (nseg > max_seg) nseg = max_seg;
-  a.seg_len = (layers + nseg - 1) / nseg;
-  nseg = (layers + a.seg_len - 1) / a.seg_len;
+  cudaStream_t st = ctx->stream;
   GTK_CK(cudaFuncSetAttribute(k_q1hex_affine<BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-  dim3 grid(gx, gy, nseg);
-  { GtkProf pr_(ctx, "k_q1hex_affine"); k_q1hex_affine<BX, BY, MINB><<<grid, C::NT, C::SMEM, ctx->stream>>>(a); }
+  if (p->ta_bx != BX || p->ta_by != BY || !p->tile_active) {
+    // footprints without any matrix column (e.g. the Dirichlet plane past the last full footprint) are skipped;
+    // z-segments are sized so that the ACTIVE tiles fill whole waves of resident CTAs
+    if (p->tile_active) gtk_dev_free(ctx, p->tile_active, p->ta_n);
+    p->tile_active = nullptr;
+    int occ = MINB;
+    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_q1hex_affine<BX, BY, MINB>, C::NT, C::SMEM));
+    if (occ < 1) occ = 1;
+    const int64_t slots = (int64_t)ctx->sm_count * occ;
+    uint8_t* xy = nullptr;
+    int32_t rc;
+    if ((rc = gtk_dev_alloc(ctx, (void**)&xy, (size_t)gx * gy))) return rc;
+    GTK_CK(cudaMemsetAsync(xy, 0, (size_t)gx * gy, st));
+    k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, p->n1, p->n2, p->n3, BX, BY, layers, gx, gy, xy);
+    std::vector<uint8_t> h((size_t)gx * gy);
+    GTK_CK(cudaMemcpyAsync(h.data(), xy, h.size(), cudaMemcpyDeviceToHost, st));
+    GTK_CK(cudaStreamSynchronize(st));
+    gtk_dev_free(ctx, xy, (size_t)gx * gy);
+    int64_t nxy = 0;
+    for (uint8_t v : h) nxy += v;
+    if (nxy < 1) nxy = 1;
+    int best = 1; double best_cost = 1e300;
+    const char* ns = getenv("GTK_AFFINE_NSEG");
+    for (int nseg = 1; nseg <= (layers + 3) / 4; ++nseg) {
+      const int len = (layers + nseg - 1) / nseg;
+      const int64_t tiles = nxy * ((layers + len - 1) / len);
+      const double cost = (double)((tiles + slots - 1) / slots) * (len + 0.6);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = nseg; }
+    }
+    if (ns && atoi(ns) > 0) best = atoi(ns);
+    p->ta_seg = (layers + best - 1) / best;
+    p->ta_nseg = (layers + p->ta_seg - 1) / p->ta_seg;
+    p->ta_n = (size_t)gx * gy * p->ta_nseg;
+    if ((rc = gtk_dev_alloc(ctx, (void**)&p->tile_active, p->ta_n))) return rc;
+    GTK_CK(cudaMemsetAsync(p->tile_active, 0, p->ta_n, st));
+    k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, p->n1, p->n2, p->n3, BX, BY, p->ta_seg, gx, gy, p->tile_active);
+    GTK_CK(cudaGetLastError());
+    p->ta_bx = BX; p->ta_by = BY;
+  }
+  a.seg_len = p->ta_seg;
+  a.tile_active = p->tile_active;
+  dim3 grid(gx, gy, p->ta_nseg);
+  { GtkProf pr_(ctx, "k_q1hex_affine"); k_q1hex_affine<BX, BY, MINB><<<grid, C::NT, C::SMEM, st>>>(a); }
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  return GTK_OK;
+}
+
+template <int WPB, int MINB>
+int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
+  using C = WCfg;
+  SweepArgs a = a0;
+  const int gx = (p->n1 + 1 + C::BX - 1) / C::BX, gyp = (p->n2 + 1 + C::BY - 1) / C::BY;
+  const int gy = (gyp + WPB - 1) / WPB;
+  const int layers = p->n3 + 1;
+  const size_t smem = sizeof(double) * (size_t)WPB * C::WARP_D;
+  cudaStream_t st = ctx->stream;
+  GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p->ta_bx != -WPB || !p->tile_active) {
+    if (p->tile_active) gtk_dev_free(ctx, p->tile_active, p->ta_n);
+    p->tile_active = nullptr;
+    int occ = MINB;
+    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_q1hex_affine_w<WPB, MINB>, WPB * 32, smem));
+    if (occ < 1) occ = 1;
+    const int64_t slots = (int64_t)ctx->sm_count * occ * WPB;       // resident warps
+    uint8_t* xy = nullptr;
+    int32_t rc;
+    if ((rc = gtk_dev_alloc(ctx, (void**)&xy, (size_t)gx * gyp))) return rc;
+    GTK_CK(cudaMemsetAsync(xy, 0, (size_t)gx * gyp, st));
+    k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, p->n1, p->n2, p->n3, C::BX, C::BY, layers, gx, gyp, xy);
+    std::vector<uint8_t> h((size_t)gx * gyp);
+    GTK_CK(cudaMemcpyAsync(h.data(), xy, h.size(), cudaMemcpyDeviceToHost, st));
+    GTK_CK(cudaStreamSynchronize(st));
+    gtk_dev_free(ctx, xy, (size_t)gx * gyp);
+    int64_t nxy = 0;
+    for (uint8_t v : h) nxy += v;
+    if (nxy < 1) nxy = 1;
+    int best = 1; double best_cost = 1e300;
+    for (int nseg = 1; nseg <= (layers + 3) / 4; ++nseg) {
+      const int len = (layers + nseg - 1) / nseg;
+      const int64_t tiles = nxy * ((layers + len - 1) / len);
+      const double cost = (double)((tiles + slots - 1) / slots) * (len + 0.6);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = nseg; }
+    }
+    // measured (profiles/): decoupled warps prefer many short z-segments over whole waves of long ones — the tail
+    // shrinks and concurrently written parts of nzval stay close; the halo step of a segment costs about half a step
+    (void)best;
+    best = (layers + 3) / 4;
+    const char* ns = getenv("GTK_AFFINE_NSEG");
+    if (ns && atoi(ns) > 0) best = atoi(ns);
+    p->ta_seg = (layers + best - 1) / best;
+    p->ta_nseg = (layers + p->ta_seg - 1) / p->ta_seg;
+    p->ta_n = (size_t)gx * gyp * p->ta_nseg;
+    if ((rc = gtk_dev_alloc(ctx, (void**)&p->tile_active, p->ta_n))) return rc;
+    GTK_CK(cudaMemsetAsync(p->tile_active, 0, p->ta_n, st));
+    k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, p->n1, p->n2, p->n3, C::BX, C::BY, p->ta_seg, gx, gyp, p->tile_active);
+    GTK_CK(cudaGetLastError());
+    p->ta_bx = -WPB; p->ta_by = C::BY;
+  }
+  a.seg_len = p->ta_seg;
+  a.tile_active = p->tile_active;
+  dim3 grid(gx, gy, p->ta_nseg);
+  { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MINB><<<grid, WPB * 32, smem, st>>>(a); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   return GTK_OK;
@@ -751,9 +1117,11 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   SweepArgs a;
   a.xyz = ctx->xyz + 3 * p->node_off;
   a.node_dof = p->node_dof;
+  a.node_col = p->node_col;
   a.colptr = ctx->ms.colptr;
   a.slot_tbl = p->slot_tbl;
   a.col_mask = p->col_mask;
+  a.tile_active = nullptr;
   a.nzval = ctx->nzval;
   a.b = ctx->bvec;
   a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3;
@@ -776,11 +1144,15 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   if (p->affine_state == 1 && !getenv("GTK_DISABLE_AFFINE")) {
     const char* var = getenv("GTK_AFFINE_VARIANT");
     switch (var ? atoi(var) : 0) {
-      case 1: rc = launch_affine<32, 8, 2>(ctx, p, a); break;
-      case 2: rc = launch_affine<16, 16, 2>(ctx, p, a); break;
-      case 3: rc = launch_affine<16, 8, 3>(ctx, p, a); break;
-      case 4: rc = launch_affine<32, 4, 4>(ctx, p, a); break;
-      default: rc = launch_affine<16, 8, 4>(ctx, p, a); break;
+      case 1: rc = launch_affine<32, 8, 1>(ctx, p, a); break;
+      case 2: rc = launch_affine<16, 16, 1>(ctx, p, a); break;
+      case 3: rc = launch_affine<16, 8, 2>(ctx, p, a); break;
+      case 4: rc = launch_affine<32, 4, 2>(ctx, p, a); break;
+      case 5: rc = launch_affine<16, 8, 3>(ctx, p, a); break;
+      case 6: rc = launch_affine_w<2, 8>(ctx, p, a); break;
+      case 7: rc = launch_affine_w<8, 2>(ctx, p, a); break;
+      case 8: rc = launch_affine_w<4, 3>(ctx, p, a); break;
+      default: rc = launch_affine_w<4, 4>(ctx, p, a); break;
     }
     if (rc) return rc;
     ctx->fast_path_last = 2;
