@@ -643,11 +643,12 @@ struct WCfg {
   static constexpr int CSTR = 7;
   static constexpr int ROWS = 434;                     // 16 * 27 + 1 (phase) + 1 (keeps rows 16-byte aligned)
   static constexpr int CELL_D = ((NC * CSTR + 1) / 2) * 2;
-  static constexpr int WARP_D = CELL_D + 2 * ROWS;     // doubles of shared memory per warp
+  static constexpr int PX = 18, PY = 4, XL = PX * PY * 3;   // node coordinates of one layer of the patch + halo ring
+  static constexpr int WARP_D = CELL_D + 2 * ROWS + 3 * XL;   // doubles of shared memory per warp
 };
 
-template <int WPB, int MINB>
-__global__ void __launch_bounds__(WPB * 32, MINB) k_q1hex_affine_w(SweepArgs a) {
+template <int WPB, int MAXREG, bool TWOPASS>
+__global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
   using C = WCfg;
   extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -657,6 +658,7 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_q1hex_affine_w(SweepArgs a) 
   if (a.tile_active && !a.tile_active[blockIdx.x + gridDim.x * (py + (int64_t)gyp * blockIdx.z)]) return;
   double* OutW = sm + w * C::WARP_D;                   // [2][ROWS]
   double* CellW = OutW + 2 * C::ROWS;                  // [NC][7]
+  double* XW = CellW + C::CELL_D;                      // [3][PY][PX][3] ring of node-coordinate layers (cp.async, 2 ahead)
 
   const int i0 = blockIdx.x * C::BX, j0 = py * C::BY;
   const int kz0 = blockIdx.z * a.seg_len;
@@ -671,14 +673,14 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_q1hex_affine_w(SweepArgs a) 
   const unsigned lt = (1u << lane) - 1u;
   const unsigned rowbits = 0xFFFFu << (lane & 16);
   // the two cells this lane computes in every layer
-  int64_t cnode[2]; bool cok[2];
+  int xoff[2]; bool cok[2];
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     const int c = lane + 32 * p;
     const int cx = c % C::CX, cy = c / C::CX;
     const int gi = i0 - 1 + cx, gj = j0 - 1 + cy;
     cok[p] = c < C::NC && gi >= 0 && gi < n1 && gj >= 0 && gj < n2;
-    cnode[p] = cok[p] ? gi + s1 * gj : 0;
+    xoff[p] = cx + C::PX * cy;
     if (c < C::NC && !cok[p]) {
 #pragma unroll
       for (int e = 0; e < C::CSTR; ++e) CellW[c * C::CSTR + e] = 0.0;   // cells outside the mesh stay zero
@@ -689,6 +691,33 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_q1hex_affine_w(SweepArgs a) 
   for (int o = 0; o < 18; ++o) pend[o] = 0.0;
   int4 ncn = make_int4(-1, -1, 0, -1);
   bool bulk_pending = false;
+  // node coordinates: every lane copies up to 3 of the 72 nodes of a layer, component by component into a
+  // structure-of-arrays slot XW[slot][k][node] (lanes then read consecutive doubles: no bank conflicts)
+  constexpr int NPN = (C::PX * C::PY + 31) / 32;
+  int pf_node[NPN];
+#pragma unroll
+  for (int r = 0; r < NPN; ++r) {
+    const int nd = lane + 32 * r;
+    const int gi = i0 - 1 + nd % C::PX, gj = j0 - 1 + nd / C::PX;
+    pf_node[r] = (nd < C::PX * C::PY && gi >= 0 && gi <= n1 && gj >= 0 && gj <= n2) ? (int)(3 * (gi + s1 * gj)) : -1;
+  }
+  auto prefetch_nodes = [&](int m, int slot) {
+    if (m >= 0 && m <= a.n3) {
+      double* dst = XW + slot * C::XL + lane;
+      const double* src = a.xyz + 3 * s2 * m;
+#pragma unroll
+      for (int r = 0; r < NPN; ++r)
+        if (pf_node[r] >= 0) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) cp_async8(dst + 32 * r + k * (C::PX * C::PY), src + pf_node[r] + k);
+        }
+    }
+    cp_async_commit();
+  };
+  prefetch_nodes(kz0 - 1, 0);
+  prefetch_nodes(kz0, 1);
+  int s0 = 0;                                          // ring slot of node layer L
+  cp_async_wait_all();
 
   for (int L = kz0 - 1; L < kz1; ++L) {
     const bool layer_ok = L >= a.kact0 && L < a.kact1;
@@ -698,21 +727,23 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_q1hex_affine_w(SweepArgs a) 
     const int col = ncn.w;
     ncn = make_int4(-1, -1, 0, -1);
     if (node_in_mesh && L + 1 < kz1) ncn = __ldg(reinterpret_cast<const int4*>(ncp + s2 * (L + 1)));
+    const int s1r = s0 == 2 ? 0 : s0 + 1, s2r = s1r == 2 ? 0 : s1r + 1;
     // ---- A) cells of layer L ----
-    __syncwarp();                                      // node phase of the previous step has read CellW
+    __syncwarp();                                      // node phase of the previous step has read CellW; node layers L, L+1 visible
+    prefetch_nodes(L + 2, s2r);                        // lands during this step; its slot held layer L-1
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       if (cok[p]) {
         double* cs = CellW + (lane + 32 * p) * C::CSTR;
         if (layer_ok) {
-          const double* x = a.xyz + 3 * (cnode[p] + s2 * L);
-          if (L + 2 <= a.n3) asm volatile("prefetch.global.L1 [%0];" ::"l"(x + 3 * s2 * 2));   // next step's top nodes
-          if (L + 5 <= a.n3) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + 3 * s2 * 5));
+          const double* x0 = XW + s0 * C::XL + xoff[p];
+          const double* x4 = XW + s1r * C::XL + xoff[p];
           double c0[3], c1[3], c2[3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const double X0 = __ldg(x + k);
-            c0[k] = __ldg(x + 3 + k) - X0; c1[k] = __ldg(x + 3 * s1 + k) - X0; c2[k] = __ldg(x + 3 * s2 + k) - X0;
+            constexpr int NS = C::PX * C::PY;
+            const double X0 = x0[k * NS];
+            c0[k] = x0[k * NS + 1] - X0; c1[k] = x0[k * NS + C::PX] - X0; c2[k] = x4[k * NS] - X0;
           }
           const double r0[3] = {c1[1] * c2[2] - c1[2] * c2[1], c1[2] * c2[0] - c1[0] * c2[2], c1[0] * c2[1] - c1[1] * c2[0]};
           const double r1[3] = {c2[1] * c0[2] - c2[2] * c0[1], c2[2] * c0[0] - c2[0] * c0[2], c2[0] * c0[1] - c2[1] * c0[0]};
@@ -735,27 +766,30 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_q1hex_affine_w(SweepArgs a) 
       }
     }
     __syncwarp();
-    // ---- B) this lane's node ----
+    // ---- B) this lane's node: two passes over its 4 cells keep the live registers low (27 accumulators at a time) ----
+    using Rows = std::make_integer_sequence<int, 8>;
     double acc[27], accb = pendb;
 #pragma unroll
     for (int o = 0; o < 18; ++o) acc[o] = pend[o];
 #pragma unroll
     for (int o = 18; o < 27; ++o) acc[o] = 0.0;
+    if constexpr (!TWOPASS) {
 #pragma unroll
-    for (int o = 0; o < 18; ++o) pend[o] = 0.0;
-    pendb = 0.0;
-    using Rows = std::make_integer_sequence<int, 8>;
-#define GTK_AFF_CELL(U, V)                                                               \
-    {                                                                                      \
-      const double* cc = cl + ((U) + C::CX * (V)) * C::CSTR;                               \
-      const double c6[6] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5]};                     \
-      const double bv = cc[6];                                                             \
-      constexpr int JB = (1 - (U)) + 2 * (1 - (V));                                        \
-      if (emit) { affine_column<JB>(c6, acc, Rows{}); accb += bv; }                        \
-      affine_column<JB + 4>(c6, pend, Rows{}); pendb += bv;                                \
+      for (int o = 0; o < 18; ++o) pend[o] = 0.0;
+      pendb = 0.0;
     }
-    GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
+    if (emit || !TWOPASS) {   // bottom role: finishes node layer L (cells in increasing cell id: v outer, u inner)
+#define GTK_AFF_CELL(U, V)                                                               \
+      {                                                                                    \
+        const double* cc = cl + ((U) + C::CX * (V)) * C::CSTR;                             \
+        const double c6[6] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5]};                   \
+        constexpr int JB = (1 - (U)) + 2 * (1 - (V));                                      \
+        if (emit) { affine_column<JB>(c6, acc, Rows{}); accb += cc[6]; }                   \
+        if constexpr (!TWOPASS) { affine_column<JB + 4>(c6, pend, Rows{}); pendb += cc[6]; }   /* top role in the same pass */ \
+      }
+      GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
 #undef GTK_AFF_CELL
+    }
     if (emit) {
       if (a.do_vector && col >= 0) a.b[col] = accb;
       if (a.do_matrix) {
@@ -813,6 +847,22 @@ __global__ void __launch_bounds__(WPB * 32, MINB) k_q1hex_affine_w(SweepArgs a) 
         }
       }
     }
+    if constexpr (TWOPASS) {   // top role: starts node layer L+1 with the same 4 cells (second pass: fewer live registers)
+#pragma unroll
+      for (int o = 0; o < 18; ++o) pend[o] = 0.0;
+      pendb = 0.0;
+#define GTK_AFF_CELL(U, V)                                                               \
+      {                                                                                    \
+        const double* cc = cl + ((U) + C::CX * (V)) * C::CSTR;                             \
+        const double c6[6] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5]};                   \
+        affine_column<(1 - (U)) + 2 * (1 - (V)) + 4>(c6, pend, Rows{});                    \
+        pendb += cc[6];                                                                    \
+      }
+      GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
+#undef GTK_AFF_CELL
+    }
+    cp_async_wait_all();       // node layer L+2 has landed (this lane's part; the __syncwarp of the next step publishes it)
+    s0 = s1r;
   }
   if (bulk_pending) bulk_wait_read();   // shared memory must outlive the bulk store reading it
 }
@@ -991,7 +1041,7 @@ int32_t launch_affine(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   return GTK_OK;
 }
 
-template <int WPB, int MINB>
+template <int WPB, int MAXREG, bool TWOPASS>
 int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   using C = WCfg;
   SweepArgs a = a0;
@@ -1000,12 +1050,12 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   const int layers = p->n3 + 1;
   const size_t smem = sizeof(double) * (size_t)WPB * C::WARP_D;
   cudaStream_t st = ctx->stream;
-  GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (p->ta_bx != -WPB || !p->tile_active) {
     if (p->tile_active) gtk_dev_free(ctx, p->tile_active, p->ta_n);
     p->tile_active = nullptr;
-    int occ = MINB;
-    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_q1hex_affine_w<WPB, MINB>, WPB * 32, smem));
+    int occ = 1;
+    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, WPB * 32, smem));
     if (occ < 1) occ = 1;
     const int64_t slots = (int64_t)ctx->sm_count * occ * WPB;       // resident warps
     uint8_t* xy = nullptr;
@@ -1030,7 +1080,7 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
     // measured (profiles/): decoupled warps prefer many short z-segments over whole waves of long ones — the tail
     // shrinks and concurrently written parts of nzval stay close; the halo step of a segment costs about half a step
     (void)best;
-    best = (layers + 3) / 4;
+    best = (layers + 5) / 6;
     const char* ns = getenv("GTK_AFFINE_NSEG");
     if (ns && atoi(ns) > 0) best = atoi(ns);
     p->ta_seg = (layers + best - 1) / best;
@@ -1045,7 +1095,7 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   a.seg_len = p->ta_seg;
   a.tile_active = p->tile_active;
   dim3 grid(gx, gy, p->ta_nseg);
-  { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MINB><<<grid, WPB * 32, smem, st>>>(a); }
+  { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MAXREG, TWOPASS><<<grid, WPB * 32, smem, st>>>(a); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   return GTK_OK;
@@ -1149,10 +1199,13 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
       case 3: rc = launch_affine<16, 8, 2>(ctx, p, a); break;
       case 4: rc = launch_affine<32, 4, 2>(ctx, p, a); break;
       case 5: rc = launch_affine<16, 8, 3>(ctx, p, a); break;
-      case 6: rc = launch_affine_w<2, 8>(ctx, p, a); break;
-      case 7: rc = launch_affine_w<8, 2>(ctx, p, a); break;
-      case 8: rc = launch_affine_w<4, 3>(ctx, p, a); break;
-      default: rc = launch_affine_w<4, 4>(ctx, p, a); break;
+      case 6: rc = launch_affine_w<3, 168, false>(ctx, p, a); break;
+      case 7: rc = launch_affine_w<6, 168, false>(ctx, p, a); break;
+      case 8: rc = launch_affine_w<2, 168, false>(ctx, p, a); break;
+      case 9: rc = launch_affine_w<4, 168, true>(ctx, p, a); break;
+      case 10: rc = launch_affine_w<5, 128, true>(ctx, p, a); break;
+      case 11: rc = launch_affine_w<4, 168, false>(ctx, p, a); break;
+      default: rc = launch_affine_w<3, 136, true>(ctx, p, a); break;
     }
     if (rc) return rc;
     ctx->fast_path_last = 2;
