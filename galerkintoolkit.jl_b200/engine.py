@@ -87,7 +87,8 @@ def load_library() -> C.CDLL:
         "gtk_info": (i64, [vp, i32]),
         "gtk_comm_unique_id": (i32, [vp]),
         "gtk_comm_init": (i32, [vp, i32, i32, vp]),
-        "gtk_comm_set_exchange": (i32, [vp, i64, i64]),
+        "gtk_set_active_cells": (i32, [vp, i64, i64]),
+        "gtk_comm_set_exchange": (i32, [vp, i32, i64, vp, i64, vp, i64, vp, i64, vp]),
         "gtk_comm_sum_ghost_rows": (i32, [vp]),
         "gtk_comm_ghost_info": (i64, [vp, i32]),
         "gtk_set_profiling": (i32, [vp, i32]),

@@ -108,6 +108,20 @@ def test_library_exports_every_declared_symbol(built_library):
     assert built_library.gtk_version() >= 100
 
 
+def test_ctypes_prototypes_match_the_header(built_library):
+    """Every entry point has a ctypes prototype whose arity equals the C declaration's (a wrong arity silently
+    passes garbage in the upper halves of 64-bit arguments)."""
+    header = open(os.path.join(os.path.dirname(gtk_b200.PACKAGE_DIR), "include", "gtk_assembly.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(gtk_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header)
+    assert len(protos) == len(E.ABI_SYMBOLS)
+    for name, args in protos:
+        n = 0 if args.strip() in ("", "void") else len(args.split(","))
+        fn = getattr(built_library, name)
+        assert fn.argtypes is not None, f"{name} has no ctypes prototype"
+        assert len(fn.argtypes) == n, f"{name}: header has {n} parameters, ctypes prototype {len(fn.argtypes)}"
+
+
 def test_engine_fails_loudly_without_gpu(built_library):
     import torch
     if torch.cuda.is_available():

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+nvidia-smi -L
+timeout 600 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -5
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?"; tail -c 2500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
