@@ -63,6 +63,38 @@ def test_elasticity_and_vector_mass(cells, n_comp):
     eng.close()
 
 
+HIGH_ORDER_CASES = [
+    # cells, order, simplexify, n_comp, bc, warp, form, params
+    ((7, 5), 2, False, 1, "boundary", 0.2, "laplace", {}),
+    ((4, 3, 3), 2, False, 1, [1, 4], 0.15, "laplace", {}),
+    ((3, 3, 2), 3, False, 1, "boundary", 0.1, "laplace", {}),          # config 3 element (Q3 hex, 64 dofs, 64 points)
+    ((3, 2, 2), 3, False, 1, None, 0.0, "mass", {}),
+    ((5, 4), 2, True, 1, "boundary", 0.2, "laplace", {}),              # P2 triangles, Duffy rule
+    ((4, 3, 3), 1, True, 1, [2], 0.2, "laplace", {}),                  # P1 tets
+    ((3, 2, 2), 2, True, 3, [1], 0.15, "elasticity", dict(lam=1.0, mu=1.0)),   # config 4 element (P2 x 3 on tets)
+]
+
+
+@pytest.mark.parametrize("cells,order,simplexify,n_comp,bc,warp,form,params", HIGH_ORDER_CASES)
+def test_high_order_and_simplex_parity(cells, order, simplexify, n_comp, bc, warp, form, params):
+    """Generic sort/segmented-reduce path on the elements of BASELINE configs 3 and 4 (small meshes).  The dof map is a
+    valid conforming numbering built by hostprep/highorder.py, not the reference's face-complex numbering (an input of
+    the ABI), so this pins the cell loop + scatter + compression for these elements, not the numbering."""
+    mesh, V, tab = problem(cells, order=order, bc=bc, n_comp=n_comp, simplexify=simplexify, warp=warp)
+    oform, gform = FORMS[form]
+    colptr, rowval, nzval = oracle_matrix(oform, mesh, V, tab, alpha=1.25, **params)
+    eng = make_engine(mesh, V, tab)
+    assert eng.matrix_symbolic() == rowval.size
+    cp, rv = eng.matrix_pattern()
+    assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
+    nz = eng.matrix_numeric(gform, alpha=1.25, **params)
+    assert_values_close(nz, nzval)
+    assert eng.matrix_numeric(gform, alpha=1.25, **params).tobytes() == nz.tobytes()
+    f = [1.0, -2.0, 0.5][:n_comp]
+    assert_values_close(eng.vector_assemble(E.FORM_SOURCE_CONST, f_const=f), oracle_vector(O.SOURCE_CONST, mesh, V, tab, f_const=f))
+    eng.close()
+
+
 def test_free_dirichlet_blocks():
     """Ad = free rows x Dirichlet columns (problems.jl:363-387) and the other selections."""
     mesh, V, tab = problem((6, 5, 4), bc=[1, 3, 6], warp=0.1)

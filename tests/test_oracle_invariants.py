@@ -95,3 +95,22 @@ def test_sparse_combines_duplicates_in_input_order_and_keeps_zeros():
     assert nz.tolist() == [3.0, (1e16 + 1.0) - 1e16, 0.0]      # left-to-right; explicit zero stays
     b = O.dense_vector(np.array([2, 2, 1], dtype=np.int32), np.array([1e16, 1.0, 5.0]), 3)
     assert b.tolist() == [5.0, 1e16 + 1.0, 0.0]
+
+
+@pytest.mark.parametrize("cells,order,simplexify,n_comp", [((3, 2), 2, False, 1), ((2, 2, 2), 2, False, 1), ((2, 2, 2), 3, False, 1),
+                                                           ((3, 3), 2, True, 1), ((2, 2, 2), 2, True, 3)])
+def test_high_order_invariants(cells, order, simplexify, n_comp):
+    """sum(M) = n_comp |Omega| (problems_tests.jl:56-57) and Laplacian row sums vanish without BCs, for the elements of
+    BASELINE configs 3/4 on the lattice dof numbering of hostprep/highorder.py."""
+    import scipy.sparse as sp
+    from util import oracle_matrix, problem
+    mesh, V, tab = problem(cells, order=order, bc=None, n_comp=n_comp, simplexify=simplexify)
+    cp, rv, nz = oracle_matrix(O.MASS, mesh, V, tab)
+    assert abs(nz.sum() - n_comp) < 1e-10
+    cp, rv, nz = oracle_matrix(O.LAPLACE, mesh, V, tab)
+    A = sp.csc_matrix((nz, rv.astype(np.int64) - 1, cp.astype(np.int64) - 1), shape=(V.n_free, V.n_free))
+    assert abs(A - A.T).max() == 0.0
+    assert np.abs(np.asarray(A.sum(axis=1))).max() < 1e-10 * np.abs(nz).max()
+    # every dof is shared consistently: number of dofs of the conforming space
+    if not simplexify:
+        assert V.n_free == n_comp * int(np.prod([order * c + 1 for c in cells]))
