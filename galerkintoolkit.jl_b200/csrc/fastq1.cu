@@ -54,10 +54,13 @@ struct FastPlan {
   bool tried = false;
   int affine_state = -1;             // -1 unknown (coordinates changed), 0 some cell is not affine, 1 every cell is exactly affine
   int* d_flag = nullptr;
-  // affine kernel launch plan (per footprint variant): z-segment length and per-CTA skip flags
-  uint8_t* tile_active = nullptr;
-  size_t ta_n = 0;
-  int ta_bx = 0, ta_by = 0, ta_seg = 0, ta_nseg = 0;
+  // launch plans (per kernel variant): z-segment length and per-tile skip flags
+  struct TilePlan {
+    uint8_t* active = nullptr;   // [gx * gy * nseg] 1 = the tile holds at least one matrix column
+    size_t n = 0;
+    int key = 0, seg = 0, nseg = 0;
+  };
+  TilePlan tp_affine, tp_sweep;
 };
 
 __global__ void k_verify_structure(const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ cell_dofs,
@@ -173,9 +176,10 @@ struct Cfg {
   static constexpr int PX = BX + 2, PY = BY + 2, NP = PX * PY;   // nodes of one layer incl. halo
   static constexpr int NT = ((NC + 31) / 32) * 32;
   static constexpr int KSTR = 45;   // doubles per cell slot: 36 Ke + 8 be + 1 pad (odd stride: conflict-free row reads)
-  // KeS[NC][KSTR] | Pend[18][NN] | PendB[NN] | OutS[NN][27] | XS[3][NP][3] | ColBase[3][NN] (i64) | ColIdx[3][NN] | ColMask[3][NN]
-  static constexpr size_t SMEM = sizeof(double) * ((size_t)NC * KSTR + (size_t)NN * 18 + NN + (size_t)NN * 27 + 3 * NP * 3) +
-                                 sizeof(long long) * 3 * NN + sizeof(int) * 6 * NN;
+  static constexpr int OW = 32 * 27 + 2 * 32 + 2;   // per node warp: 32 columns + 2 slack doubles per segment (16-byte phase of each run)
+  static_assert(NN % 32 == 0, "node threads must be whole warps");
+  // OutW[NN/32][OW] | KeS[NC][KSTR] | Pend[18][NN] | PendB[NN] | XS[3][NP][3]
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)NC * KSTR + (size_t)NN * 18 + NN + (size_t)(NN / 32) * OW + 3 * NP * 3);
 };
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
@@ -184,6 +188,17 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+// TMA bulk store shared -> global (UBLKCP): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // one matrix entry (column = node of the footprint, row = its neighbour at offset O): sum of the <= 4 cells of
 // this layer that contain both nodes, in increasing cell id (decreasing e) = the reference's push order.
@@ -224,15 +239,13 @@ struct GatherAll {
 template <int BX, int BY, int MINB>
 __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs a) {
   using C = Cfg<BX, BY>;
-  extern __shared__ double sm[];
-  double* KeS = sm;                                   // [NC][KSTR] element matrices of the current cell layer
+  if (a.tile_active && !a.tile_active[blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)]) return;
+  extern __shared__ __align__(16) double sm[];
+  double* OutW = sm;                                  // [NN/32][OW] finished columns, one region per node warp (16 B aligned)
+  double* KeS = OutW + (C::NN / 32) * C::OW;          // [NC][KSTR] element matrices of the current cell layer
   double* Pend = KeS + C::NC * C::KSTR;               // [18][NN]   entries waiting for the next cell layer
   double* PendB = Pend + C::NN * 18;                  // [NN]
-  double* OutS = PendB + C::NN;                       // [NN][27]   finished columns of node layer L (transpose buffer)
-  double* XS = OutS + C::NN * 27;                     // [3][NP][3] ring of node-coordinate layers (cp.async, 2 ahead)
-  long long* ColBase = (long long*)(XS + 3 * C::NP * 3);   // [3][NN] colptr of each node's column, -1 = none (ring: layer m in slot m%3)
-  int* ColIdx = (int*)(ColBase + 3 * C::NN);          // [3][NN]
-  unsigned* ColMask = (unsigned*)(ColIdx + 3 * C::NN);     // [3][NN]
+  double* XS = PendB + C::NN;                         // [3][NP][3] ring of node-coordinate layers (cp.async, 2 ahead)
 
   const int t = threadIdx.x;
   const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY;
@@ -282,18 +295,23 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
   }
   for (int idx = t; idx < C::NN * 18; idx += C::NT) Pend[idx] = 0.0;
   for (int idx = t; idx < C::NN; idx += C::NT) PendB[idx] = 0.0;
+  const int lane = t & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int4 ncn = make_int4(-1, -1, 0, -1);   // NodeCol of the next node layer
+  bool bulk_pending = false;
   cp_async_wait_all();
   __syncthreads();
 
   for (int L = kz0 - 1; L < kz1; ++L) {
     const bool layer_ok = L >= a.kact0 && L < a.kact1;
     prefetch_nodes(L + 2);                                  // lands during phases A/B, waited before the 2nd barrier
-    // column info of node layer L+1 (consumed one step later): loads issued now, stored after the FP64 work
-    long long cbn = -1; int coln = -1; unsigned maskn = 0;
-    if (node_in_mesh && L + 1 <= n3 && L + 1 < kz1) {
-      const int4 nc = __ldg(reinterpret_cast<const int4*>(a.node_col + (i0 + li) + s1 * (j0 + lj) + s2 * (L + 1)));
-      cbn = ((long long)(unsigned)nc.y << 32) | (unsigned)nc.x; maskn = (unsigned)nc.z; coln = nc.w;
-    }
+    // column record of this thread's node: layer L was loaded one step ago, layer L+1 is requested now
+    const long long cb = ((long long)(unsigned)ncn.y << 32) | (unsigned)ncn.x;
+    const unsigned mask_l = (unsigned)ncn.z;
+    const int col = ncn.w;
+    ncn = make_int4(-1, -1, 0, -1);
+    if (node_in_mesh && L + 1 <= n3 && L + 1 < kz1)
+      ncn = __ldg(reinterpret_cast<const int4*>(a.node_col + (i0 + li) + s1 * (j0 + lj) + s2 * (L + 1)));
     // ---- A) element matrices of cell layer L ----
     if (cell_ok) {
       if (layer_ok) {
@@ -325,15 +343,56 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
         for (int e = 0; e < 44; ++e) myslot[e] = 0.0;
       }
     }
-    if (node_thread) {
-      const int nb = ((L + 4) % 3) * C::NN + t;   // written 2 barriers after its last reader (step L-2)
-      ColBase[nb] = cbn; ColIdx[nb] = coln; ColMask[nb] = maskn;
-    }
     __syncthreads();
-    // ---- B) gather: thread per node, all 27 entries, compile-time offsets ----
-    const int cur = ((L + 3) % 3) * C::NN;
+    // ---- B) gather: thread per node, all 27 entries, compile-time offsets; C) warp-local copy-out ----
     if (node_thread) {
-      if (a.do_matrix) GatherAll<BX, BY, 0>::run(gbase, Pend + t, OutS + t * 27);
+      const bool emit = a.do_matrix && L >= kz0;
+      if (a.do_matrix) {
+        // segments of the warp's 32 columns: a run = consecutive lanes with full 27-entry columns that are contiguous
+        // in nzval; every other column is a segment of its own.  Each segment gets 2 slack doubles so that a run can be
+        // laid out with the 16-byte phase of its destination and leave as one TMA bulk store.
+        const unsigned mask = emit ? mask_l : 0u;
+        const bool full = mask == 0x07FFFFFFu;
+        const long long cbp = __shfl_up_sync(0xFFFFFFFFu, cb, 1);
+        const unsigned fullb = __ballot_sync(0xFFFFFFFFu, full);
+        const bool link = full && lane > 0 && ((fullb >> (lane - 1)) & 1u) && cb == cbp + 27;
+        const unsigned linkb = __ballot_sync(0xFFFFFFFFu, link);
+        const int seg = __popc(~linkb & ((lt << 1) | 1u));                 // segments starting at or below this lane (>= 1)
+        const int myoff = 27 * lane + 2 * (seg - 1) + (int)((cb + lane) & 1);
+        double* mine = OutW + (t >> 5) * C::OW + myoff;
+        if (bulk_pending) bulk_wait_read();        // the bulk store of the previous layer has read this region
+        bulk_pending = false;
+        __syncwarp();                              // ... and the warp has finished compacting the rest of it
+        GatherAll<BX, BY, 0>::run(gbase, Pend + t, mine);
+        fence_async_smem();
+        __syncwarp();
+        const unsigned up = (linkb >> lane) >> 1;  // link bits of the lanes above
+        if (full) {
+          if (!link) {                             // run start: one bulk store for the whole run
+            const int head = (int)(cb & 1);
+            const int len = __ffs(~up);
+            bulk_store(a.nzval + cb + head, mine + head, (unsigned)(((27 * len - head) & ~1) * sizeof(double)));
+            bulk_commit();
+            bulk_pending = true;
+            if (head) a.nzval[cb] = mine[0];                         // lone first element (odd index)
+          }
+          if (!(up & 1u) && !(cb & 1)) a.nzval[cb + 26] = mine[26];  // run end: lone last element (even index)
+        }
+        unsigned irr = __ballot_sync(0xFFFFFFFFu, (mask & 0x07FFFFFFu) != 0 && !full);
+        while (irr) {                              // columns with < 27 entries or non-monotone slots: lane o -> its CSC slot
+          const int n = __ffs(irr) - 1;
+          irr &= irr - 1;
+          const unsigned m = __shfl_sync(0xFFFFFFFFu, mask, n);
+          const long long cbn = __shfl_sync(0xFFFFFFFFu, cb, n);
+          const int offn = __shfl_sync(0xFFFFFFFFu, myoff, n);
+          const int coln = __shfl_sync(0xFFFFFFFFu, col, n);
+          if ((m >> lane) & 1u & (lane < 27)) {
+            unsigned slot = (unsigned)__popc(m & lt);
+            if (m & 0x80000000u) slot = a.slot_tbl[(size_t)coln * 32 + lane];
+            a.nzval[cbn + slot] = OutW[(t >> 5) * C::OW + offn + lane];
+          }
+        }
+      }
       if (a.do_vector) {
         double acc = PendB[t], hi = 0.0;
 #pragma unroll
@@ -345,29 +404,13 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
             acc += ke[e1 + 2 * e2];
           }
         PendB[t] = hi;
-        if (L >= kz0 && ColIdx[cur + t] >= 0) a.b[ColIdx[cur + t]] = acc;
+        if (L >= kz0 && col >= 0) a.b[col] = acc;
       }
     }
     cp_async_wait_all();
-    __syncthreads();
-    // ---- C) copy-out: one warp per column; lane o owns neighbour offset o and writes it to its CSC slot
-    //      slot(o) = number of present neighbours before o (popcount of the presence mask), or the byte table for
-    //      the rare columns whose dof numbering is not monotone in the neighbour order.  The lanes of a warp write
-    //      one contiguous run of nzval.
-    if (a.do_matrix && L >= kz0) {
-      const int lane = t & 31;
-      const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 4
-      for (int nl = t >> 5; nl < C::NN; nl += C::NT / 32) {
-        const unsigned mask = ColMask[cur + nl];
-        if ((mask >> lane) & 1u & (lane < 27)) {
-          unsigned slot = (unsigned)__popc(mask & lt);
-          if (mask & 0x80000000u) slot = a.slot_tbl[(size_t)ColIdx[cur + nl] * 32 + lane];
-          a.nzval[ColBase[cur + nl] + slot] = OutS[nl * 27 + lane];
-        }
-      }
-    }
+    __syncthreads();      // KeS is rewritten by the next cell phase; node layer L+2 is visible
   }
+  if (bulk_pending) bulk_wait_read();   // shared memory must outlive the bulk stores reading it
 }
 
 
@@ -394,18 +437,6 @@ __global__ void k_classify_affine(const double* __restrict__ xyz, int n1, int n2
   }
   if (bad) *nonaffine = 1;
 }
-
-template <int BX, int BY>
-struct ACfg {
-  static constexpr int CX = BX + 1, CY = BY + 1, NC = CX * CY, NN = BX * BY;
-  static constexpr int PX = BX + 2, PY = BY + 2, NP = PX * PY;
-  static constexpr int NT = ((NC + 31) / 32) * 32;   // one thread per cell of a layer; threads t < NN also own a node
-  static constexpr int CSTR = 7;    // doubles per cell: A0 A1 A2 B01 B02 B12 bv (odd stride: conflict-free)
-  static constexpr int OSTR = 28;   // doubles per column in OutS: 27 entries + 1 so that the 16-byte phase can follow nzval
-  static_assert(NN % 32 == 0, "node threads must be whole warps");
-  // OutS[NN][28] | CellS[2][NC][7] | XS[4][NP][3]
-  static constexpr size_t SMEM = sizeof(double) * ((size_t)NN * OSTR + 2 * (size_t)NC * CSTR + 4 * NP * 3);
-};
 
 // Contribution of one affine cell to the entry (row = local node I, column = local node J), added to acc.
 //   c = {A0,A1,A2,B01,B02,B12},  A_a = alpha (2/9) D_aa,  B_ab = alpha (2/3) D_ab,  D = w adj(J) adj(J)^T / |det J|
@@ -447,185 +478,6 @@ __device__ __forceinline__ void store_permuted(const double (&acc)[27], unsigned
   if constexpr (O + 1 < 27) store_permuted<O + 1>(acc, mask, tbl, dst);
 }
 
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
-// TMA bulk store shared -> global (UBLKCP): 16-byte aligned addresses, size a multiple of 16
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
-               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-template <int BX, int BY, int MINB>
-__global__ void __launch_bounds__(ACfg<BX, BY>::NT, MINB) k_q1hex_affine(SweepArgs a) {
-  using C = ACfg<BX, BY>;
-  if (a.tile_active && !a.tile_active[blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)]) return;
-  extern __shared__ __align__(16) double sm[];
-  double* OutS = sm;                                    // [NN][28] one finished column per node thread
-  double* CellS = OutS + C::NN * C::OSTR;               // [2][NC][7] cell data, double-buffered over cell layers
-  double* XS = CellS + 2 * C::NC * C::CSTR;             // [4][NP][3] ring of node-coordinate layers (3 ahead)
-
-  const int t = threadIdx.x;
-  const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY;
-  const int kz0 = blockIdx.z * a.seg_len;
-  const int kz1 = min(kz0 + a.seg_len, a.n3 + 1);
-  const int n1 = a.n1, n2 = a.n2, n3 = a.n3;
-  const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
-  const bool node_thread = t < C::NN;
-  const int li = t % BX, lj = t / BX;
-  const bool node_in_mesh = node_thread && (i0 + li <= n1) && (j0 + lj <= n2);
-  const NodeCol* ncp = a.node_col + (i0 + li) + s1 * (j0 + lj);
-  const int nbase = (li + C::CX * lj) * C::CSTR;       // cell (u,v) of this node: nbase + (u + CX v) * CSTR
-  double* orow = OutS + (node_thread ? t : 0) * C::OSTR;
-  // cell role: thread t owns cell (cx, cy) of every layer
-  const int cx = t % C::CX, cy = t / C::CX;
-  const bool cell_ok = t < C::NC && (i0 - 1 + cx) >= 0 && (i0 - 1 + cx) < n1 && (j0 - 1 + cy) >= 0 && (j0 - 1 + cy) < n2;
-  const int coff = (t < C::NC ? t : 0) * C::CSTR;
-  const int xoff = 3 * (cx + C::PX * cy);
-  const int lane = t & 31;
-  const unsigned lt = (1u << lane) - 1u;
-
-  constexpr int NPF = (C::NP * 3 + C::NT - 1) / C::NT;
-  int pf_off[NPF];
-#pragma unroll
-  for (int r = 0; r < NPF; ++r) {
-    const int idx = t + r * C::NT;
-    const int nd = idx / 3, k = idx - nd * 3;
-    const int gi = i0 - 1 + nd % C::PX, gj = j0 - 1 + nd / C::PX;
-    pf_off[r] = (idx < C::NP * 3 && gi >= 0 && gi <= n1 && gj >= 0 && gj <= n2) ? (int)(3 * (gi + s1 * gj) + k) : -1;
-  }
-  auto prefetch_nodes = [&](int m) {
-    if (m >= 0 && m <= n3) {
-      double* dst = XS + (m & 3) * (C::NP * 3) + t;
-      const double* src = a.xyz + 3 * s2 * m;
-#pragma unroll
-      for (int r = 0; r < NPF; ++r)
-        if (pf_off[r] >= 0) cp_async8(dst + r * C::NT, src + pf_off[r]);
-    }
-    cp_async_commit();
-  };
-
-  double pend[18], pendb = 0.0;   // contributions of the cell layer below to the next node layer (this thread's node)
-#pragma unroll
-  for (int o = 0; o < 18; ++o) pend[o] = 0.0;
-  if (t < C::NC) {
-#pragma unroll
-    for (int e = 0; e < 2 * C::CSTR; ++e) CellS[(e / C::CSTR) * C::NC * C::CSTR + coff + e % C::CSTR] = 0.0;   // cells outside the mesh stay zero
-  }
-  int4 ncn = make_int4(-1, -1, 0, -1);   // NodeCol of the next node layer (none for the halo step)
-  prefetch_nodes(kz0 - 1);               // kz0 - 1 may be -1: an empty group keeps the group count uniform
-  prefetch_nodes(kz0);
-  prefetch_nodes(kz0 + 1);
-  cp_async_wait_1();
-  __syncthreads();
-
-  for (int L = kz0 - 1; L < kz1; ++L) {
-    const bool layer_ok = L >= a.kact0 && L < a.kact1;
-    const bool emit = L >= kz0;
-    // column record of this thread's node: layer L was loaded one step ago, layer L+1 is requested now
-    const long long cb = ((long long)(unsigned)ncn.y << 32) | (unsigned)ncn.x;
-    unsigned mask = (unsigned)ncn.z;
-    const int col = ncn.w;
-    ncn = make_int4(-1, -1, 0, -1);
-    if (node_in_mesh && L + 1 < kz1) ncn = __ldg(reinterpret_cast<const int4*>(ncp + s2 * (L + 1)));
-    // ---- A) six numbers + source weight per cell of layer L (needs node layers L and L+1) ----
-    double* cs = CellS + (L & 1) * (C::NC * C::CSTR) + coff;
-    if (cell_ok) {
-      if (layer_ok) {
-        const double* x0 = XS + (L & 3) * (C::NP * 3) + xoff;
-        const double* x4 = XS + ((L + 1) & 3) * (C::NP * 3) + xoff;
-        double c0[3], c1[3], c2[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double X0 = x0[k];
-          c0[k] = x0[3 + k] - X0; c1[k] = x0[3 * C::PX + k] - X0; c2[k] = x4[k] - X0;
-        }
-        const double r0[3] = {c1[1] * c2[2] - c1[2] * c2[1], c1[2] * c2[0] - c1[0] * c2[2], c1[0] * c2[1] - c1[1] * c2[0]};
-        const double r1[3] = {c2[1] * c0[2] - c2[2] * c0[1], c2[2] * c0[0] - c2[0] * c0[2], c2[0] * c0[1] - c2[1] * c0[0]};
-        const double r2[3] = {c0[1] * c1[2] - c0[2] * c1[1], c0[2] * c1[0] - c0[0] * c1[2], c0[0] * c1[1] - c0[1] * c1[0]};
-        const double det = c0[0] * r0[0] + c0[1] * r0[1] + c0[2] * r0[2];
-        const double ad = fabs(det);
-        const double s = q1hex::W8 * q1hex::fast_rcp<double>(ad);
-        const double sd = a.alpha * (2.0 / 9.0) * s, so = a.alpha * (2.0 / 3.0) * s;
-        cs[0] = sd * (r0[0] * r0[0] + r0[1] * r0[1] + r0[2] * r0[2]);
-        cs[1] = sd * (r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
-        cs[2] = sd * (r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
-        cs[3] = so * (r0[0] * r1[0] + r0[1] * r1[1] + r0[2] * r1[2]);
-        cs[4] = so * (r0[0] * r2[0] + r0[1] * r2[1] + r0[2] * r2[2]);
-        cs[5] = so * (r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2]);
-        cs[6] = a.fscale * (q1hex::W8 * ad);              // be[i] = alpha f sum_q N_i dV = alpha f w |det J| (sum_q N_i = 1)
-      } else {
-#pragma unroll
-        for (int e = 0; e < C::CSTR; ++e) cs[e] = 0.0;
-      }
-    }
-    prefetch_nodes(L + 3);      // slot (L-1)&3: last read in the cell phase of step L-1, before the previous barrier
-    cp_async_wait_1();          // node layer L+2 (this thread's part) has landed; only group L+3 may be pending
-    __syncthreads();            // the ONLY block barrier of a step: cell layer L and node layer L+2 are visible
-    // ---- B) this thread's node: finish node layer L (cells below are in pend), start node layer L+1 ----
-    if (node_thread) {
-      double acc[27], accb = pendb;
-#pragma unroll
-      for (int o = 0; o < 18; ++o) acc[o] = pend[o];
-#pragma unroll
-      for (int o = 18; o < 27; ++o) acc[o] = 0.0;
-#pragma unroll
-      for (int o = 0; o < 18; ++o) pend[o] = 0.0;
-      pendb = 0.0;
-      using Rows = std::make_integer_sequence<int, 8>;
-      const double* cl = CellS + (L & 1) * (C::NC * C::CSTR) + nbase;
-      // cells in increasing cell id (the reference's push order): v outer, u inner
-#define GTK_AFF_CELL(U, V)                                                                 \
-      {                                                                                      \
-        const double* cc = cl + ((U) + C::CX * (V)) * C::CSTR;                               \
-        const double c6[6] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5]};                     \
-        const double bv = cc[6];                                                             \
-        constexpr int JB = (1 - (U)) + 2 * (1 - (V));                                        \
-        if (emit) { affine_column<JB>(c6, acc, Rows{}); accb += bv; }   /* bottom node */   \
-        affine_column<JB + 4>(c6, pend, Rows{}); pendb += bv;           /* top node    */   \
-      }
-      GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
-#undef GTK_AFF_CELL
-      if (emit) {
-        if (a.do_vector && col >= 0) a.b[col] = accb;
-        if (a.do_matrix) {
-          // ---- C) copy-out, warp-local (no block barrier): the column goes to shared memory with the same
-          // 16-byte phase as its run of nzval, then one TMA bulk store moves the 26 aligned entries and a scalar
-          // store the odd one.  Columns with fewer than 27 entries are compacted by the warp, lane o -> slot.
-          if (mask & 0x80000000u) {   // rare: slots not monotone in the neighbour order -> permuted stores from registers
-            store_permuted<0>(acc, mask, a.slot_tbl + (size_t)col * 32, a.nzval + cb);
-            mask = 0;
-          }
-          const bool full = mask == 0x07FFFFFFu;
-          const int ph = (int)(cb & 1);
-          bulk_wait_read();                        // the previous layer's bulk store has finished reading this row
-          __syncwarp();                            // ... and the warp has finished compacting it
-#pragma unroll
-          for (int o = 0; o < 27; ++o) orow[ph + o] = acc[o];
-          fence_async_smem();
-          if (full) {
-            double* dst = a.nzval + cb;
-            bulk_store(dst + ph, orow + 2 * ph, 26 * sizeof(double));
-            bulk_commit();
-            dst[ph ? 0 : 26] = ph ? acc[0] : acc[26];
-          }
-          unsigned irr = __ballot_sync(0xFFFFFFFFu, mask != 0 && !full);
-          __syncwarp();
-          while (irr) {
-            const int n = __ffs(irr) - 1;
-            irr &= irr - 1;
-            const unsigned m = __shfl_sync(0xFFFFFFFFu, mask, n);
-            const long long cbn = __shfl_sync(0xFFFFFFFFu, cb, n);
-            if ((m >> lane) & 1u) a.nzval[cbn + __popc(m & lt)] = OutS[((t & ~31) + n) * C::OSTR + (int)(cbn & 1) + lane];
-          }
-        }
-      }
-    }
-  }
-  bulk_wait_read();   // shared memory must outlive the bulk stores reading it
-}
 
 // ------------------------------------------------------------------------------------------------
 // Warp-private variant of the affine sweep: every warp owns a 16 x 2 patch of nodes and sweeps its
@@ -892,7 +744,8 @@ void plan_free(gtk_ctx* ctx, FastPlan* p) {
   if (p->col_mask) gtk_dev_free(ctx, p->col_mask, sizeof(uint32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   if (p->node_col) gtk_dev_free(ctx, p->node_col, sizeof(NodeCol) * (size_t)p->n_nodes);
   if (p->d_flag) cudaFree(p->d_flag);
-  if (p->tile_active) gtk_dev_free(ctx, p->tile_active, p->ta_n);
+  if (p->tp_affine.active) gtk_dev_free(ctx, p->tp_affine.active, p->tp_affine.n);
+  if (p->tp_sweep.active) gtk_dev_free(ctx, p->tp_sweep.active, p->tp_sweep.n);
   delete p;
 }
 
@@ -963,79 +816,41 @@ int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
   return GTK_OK;
 }
 
+// Per-tile skip flags for a (bx x by) footprint and z-segments of seg_len node layers: tiles without any matrix
+// column (e.g. the Dirichlet plane past the last full footprint) exit at once.  Cached per kernel variant (key).
+int32_t build_tile_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::TilePlan& tp, int key, int bx, int by, int gx, int gy, int seg_len) {
+  if (tp.key == key && tp.active && tp.seg == seg_len) return GTK_OK;
+  if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
+  tp.active = nullptr;
+  const int layers = p->n3 + 1;
+  tp.seg = seg_len < 1 ? 1 : seg_len;
+  tp.nseg = (layers + tp.seg - 1) / tp.seg;
+  tp.n = (size_t)gx * gy * tp.nseg;
+  int32_t rc;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&tp.active, tp.n))) return rc;
+  GTK_CK(cudaMemsetAsync(tp.active, 0, tp.n, ctx->stream));
+  k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, ctx->stream>>>(p->node_dof, p->n1, p->n2, p->n3, bx, by, tp.seg, gx, gy, tp.active);
+  GTK_CK(cudaGetLastError());
+  tp.key = key;
+  return GTK_OK;
+}
+
 template <int BX, int BY, int MINB>
 int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   using C = Cfg<BX, BY>;
   SweepArgs a = a0;
   const int gx = (p->n1 + 1 + BX - 1) / BX, gy = (p->n2 + 1 + BY - 1) / BY;
-  // z-segments: enough CTAs for a few waves over sm_count*MINB resident CTAs, segments >= 8 layers
-  const int layers = p->n3 + 1;
-  int64_t slots = (int64_t)ctx->sm_count * MINB;
-  int nseg = (int)((4 * slots + (int64_t)gx * gy - 1) / ((int64_t)gx * gy));
-  if (nseg < 1) nseg = 1;
-  int max_seg = (layers + 7) / 8;
-  if (nseg > max_seg) nseg = max_seg;
-  a.seg_len = (layers + nseg - 1) / nseg;
-  nseg = (layers + a.seg_len - 1) / a.seg_len;
+  // z-segments: the halo layer of a segment costs a full cell phase here (FP64-heavy), so segments are longer than in
+  // the affine kernel
+  const char* ns = getenv("GTK_SWEEP_SEG");
+  const int seg = ns && atoi(ns) > 0 ? atoi(ns) : 12;
+  int32_t rc = build_tile_plan(ctx, p, p->tp_sweep, BX * 100 + BY, BX, BY, gx, gy, seg);
+  if (rc) return rc;
+  a.seg_len = p->tp_sweep.seg;
+  a.tile_active = p->tp_sweep.active;
   GTK_CK(cudaFuncSetAttribute(k_q1hex_sweep<BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-  dim3 grid(gx, gy, nseg);
+  dim3 grid(gx, gy, p->tp_sweep.nseg);
   { GtkProf pr_(ctx, "k_q1hex_sweep"); k_q1hex_sweep<BX, BY, MINB><<<grid, C::NT, C::SMEM, ctx->stream>>>(a); }
-  GTK_CK(cudaGetLastError());
-  gtk_count_launch(ctx);
-  return GTK_OK;
-}
-
-template <int BX, int BY, int MINB>
-int32_t launch_affine(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
-  using C = ACfg<BX, BY>;
-  SweepArgs a = a0;
-  const int gx = (p->n1 + 1 + BX - 1) / BX, gy = (p->n2 + 1 + BY - 1) / BY;
-  const int layers = p->n3 + 1;
-  cudaStream_t st = ctx->stream;
-  GTK_CK(cudaFuncSetAttribute(k_q1hex_affine<BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-  if (p->ta_bx != BX || p->ta_by != BY || !p->tile_active) {
-    // footprints without any matrix column (e.g. the Dirichlet plane past the last full footprint) are skipped;
-    // z-segments are sized so that the ACTIVE tiles fill whole waves of resident CTAs
-    if (p->tile_active) gtk_dev_free(ctx, p->tile_active, p->ta_n);
-    p->tile_active = nullptr;
-    int occ = MINB;
-    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_q1hex_affine<BX, BY, MINB>, C::NT, C::SMEM));
-    if (occ < 1) occ = 1;
-    const int64_t slots = (int64_t)ctx->sm_count * occ;
-    uint8_t* xy = nullptr;
-    int32_t rc;
-    if ((rc = gtk_dev_alloc(ctx, (void**)&xy, (size_t)gx * gy))) return rc;
-    GTK_CK(cudaMemsetAsync(xy, 0, (size_t)gx * gy, st));
-    k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, p->n1, p->n2, p->n3, BX, BY, layers, gx, gy, xy);
-    std::vector<uint8_t> h((size_t)gx * gy);
-    GTK_CK(cudaMemcpyAsync(h.data(), xy, h.size(), cudaMemcpyDeviceToHost, st));
-    GTK_CK(cudaStreamSynchronize(st));
-    gtk_dev_free(ctx, xy, (size_t)gx * gy);
-    int64_t nxy = 0;
-    for (uint8_t v : h) nxy += v;
-    if (nxy < 1) nxy = 1;
-    int best = 1; double best_cost = 1e300;
-    const char* ns = getenv("GTK_AFFINE_NSEG");
-    for (int nseg = 1; nseg <= (layers + 3) / 4; ++nseg) {
-      const int len = (layers + nseg - 1) / nseg;
-      const int64_t tiles = nxy * ((layers + len - 1) / len);
-      const double cost = (double)((tiles + slots - 1) / slots) * (len + 0.6);
-      if (cost < best_cost - 1e-9) { best_cost = cost; best = nseg; }
-    }
-    if (ns && atoi(ns) > 0) best = atoi(ns);
-    p->ta_seg = (layers + best - 1) / best;
-    p->ta_nseg = (layers + p->ta_seg - 1) / p->ta_seg;
-    p->ta_n = (size_t)gx * gy * p->ta_nseg;
-    if ((rc = gtk_dev_alloc(ctx, (void**)&p->tile_active, p->ta_n))) return rc;
-    GTK_CK(cudaMemsetAsync(p->tile_active, 0, p->ta_n, st));
-    k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, p->n1, p->n2, p->n3, BX, BY, p->ta_seg, gx, gy, p->tile_active);
-    GTK_CK(cudaGetLastError());
-    p->ta_bx = BX; p->ta_by = BY;
-  }
-  a.seg_len = p->ta_seg;
-  a.tile_active = p->tile_active;
-  dim3 grid(gx, gy, p->ta_nseg);
-  { GtkProf pr_(ctx, "k_q1hex_affine"); k_q1hex_affine<BX, BY, MINB><<<grid, C::NT, C::SMEM, st>>>(a); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   return GTK_OK;
@@ -1047,55 +862,18 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   SweepArgs a = a0;
   const int gx = (p->n1 + 1 + C::BX - 1) / C::BX, gyp = (p->n2 + 1 + C::BY - 1) / C::BY;
   const int gy = (gyp + WPB - 1) / WPB;
-  const int layers = p->n3 + 1;
   const size_t smem = sizeof(double) * (size_t)WPB * C::WARP_D;
-  cudaStream_t st = ctx->stream;
   GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (p->ta_bx != -WPB || !p->tile_active) {
-    if (p->tile_active) gtk_dev_free(ctx, p->tile_active, p->ta_n);
-    p->tile_active = nullptr;
-    int occ = 1;
-    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, WPB * 32, smem));
-    if (occ < 1) occ = 1;
-    const int64_t slots = (int64_t)ctx->sm_count * occ * WPB;       // resident warps
-    uint8_t* xy = nullptr;
-    int32_t rc;
-    if ((rc = gtk_dev_alloc(ctx, (void**)&xy, (size_t)gx * gyp))) return rc;
-    GTK_CK(cudaMemsetAsync(xy, 0, (size_t)gx * gyp, st));
-    k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, p->n1, p->n2, p->n3, C::BX, C::BY, layers, gx, gyp, xy);
-    std::vector<uint8_t> h((size_t)gx * gyp);
-    GTK_CK(cudaMemcpyAsync(h.data(), xy, h.size(), cudaMemcpyDeviceToHost, st));
-    GTK_CK(cudaStreamSynchronize(st));
-    gtk_dev_free(ctx, xy, (size_t)gx * gyp);
-    int64_t nxy = 0;
-    for (uint8_t v : h) nxy += v;
-    if (nxy < 1) nxy = 1;
-    int best = 1; double best_cost = 1e300;
-    for (int nseg = 1; nseg <= (layers + 3) / 4; ++nseg) {
-      const int len = (layers + nseg - 1) / nseg;
-      const int64_t tiles = nxy * ((layers + len - 1) / len);
-      const double cost = (double)((tiles + slots - 1) / slots) * (len + 0.6);
-      if (cost < best_cost - 1e-9) { best_cost = cost; best = nseg; }
-    }
-    // measured (profiles/): decoupled warps prefer many short z-segments over whole waves of long ones — the tail
-    // shrinks and concurrently written parts of nzval stay close; the halo step of a segment costs about half a step
-    (void)best;
-    best = (layers + 5) / 6;
-    const char* ns = getenv("GTK_AFFINE_NSEG");
-    if (ns && atoi(ns) > 0) best = atoi(ns);
-    p->ta_seg = (layers + best - 1) / best;
-    p->ta_nseg = (layers + p->ta_seg - 1) / p->ta_seg;
-    p->ta_n = (size_t)gx * gyp * p->ta_nseg;
-    if ((rc = gtk_dev_alloc(ctx, (void**)&p->tile_active, p->ta_n))) return rc;
-    GTK_CK(cudaMemsetAsync(p->tile_active, 0, p->ta_n, st));
-    k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, p->n1, p->n2, p->n3, C::BX, C::BY, p->ta_seg, gx, gyp, p->tile_active);
-    GTK_CK(cudaGetLastError());
-    p->ta_bx = -WPB; p->ta_by = C::BY;
-  }
-  a.seg_len = p->ta_seg;
-  a.tile_active = p->tile_active;
-  dim3 grid(gx, gy, p->ta_nseg);
-  { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MAXREG, TWOPASS><<<grid, WPB * 32, smem, st>>>(a); }
+  // measured (profiles/): decoupled warps prefer many short z-segments over whole waves of long ones — the tail
+  // shrinks and concurrently written parts of nzval stay close; the halo step of a segment costs about half a step
+  const char* ns = getenv("GTK_AFFINE_SEG");
+  const int seg = ns && atoi(ns) > 0 ? atoi(ns) : 6;
+  int32_t rc = build_tile_plan(ctx, p, p->tp_affine, 1000 + WPB, C::BX, C::BY, gx, gyp, seg);
+  if (rc) return rc;
+  a.seg_len = p->tp_affine.seg;
+  a.tile_active = p->tp_affine.active;
+  dim3 grid(gx, gy, p->tp_affine.nseg);
+  { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MAXREG, TWOPASS><<<grid, WPB * 32, smem, ctx->stream>>>(a); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   return GTK_OK;
@@ -1194,11 +972,6 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   if (p->affine_state == 1 && !getenv("GTK_DISABLE_AFFINE")) {
     const char* var = getenv("GTK_AFFINE_VARIANT");
     switch (var ? atoi(var) : 0) {
-      case 1: rc = launch_affine<32, 8, 1>(ctx, p, a); break;
-      case 2: rc = launch_affine<16, 16, 1>(ctx, p, a); break;
-      case 3: rc = launch_affine<16, 8, 2>(ctx, p, a); break;
-      case 4: rc = launch_affine<32, 4, 2>(ctx, p, a); break;
-      case 5: rc = launch_affine<16, 8, 3>(ctx, p, a); break;
       case 6: rc = launch_affine_w<3, 168, false>(ctx, p, a); break;
       case 7: rc = launch_affine_w<6, 168, false>(ctx, p, a); break;
       case 8: rc = launch_affine_w<2, 168, false>(ctx, p, a); break;
@@ -1214,7 +987,7 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   }
   // footprint variants (tuning knob for experiments; default chosen from measurements)
   const char* var = getenv("GTK_SWEEP_VARIANT");
-  const int v = var ? atoi(var) : 3;
+  const int v = var ? atoi(var) : 1;
   switch (v) {
     case 1: rc = launch_sweep<16, 6, 2>(ctx, p, a); break;
     case 2: rc = launch_sweep<24, 8, 1>(ctx, p, a); break;
