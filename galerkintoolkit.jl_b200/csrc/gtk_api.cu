@@ -65,7 +65,7 @@ int32_t gtk_destroy(gtk_ctx* ctx) {
   gtk_vecsym_release(ctx);
   cudaFree(ctx->xyz); cudaFree(ctx->cell_nodes); cudaFree(ctx->cell_dofs);
   cudaFree(ctx->w); cudaFree(ctx->N); cudaFree(ctx->dN); cudaFree(ctx->M); cudaFree(ctx->dM);
-  cudaFree(ctx->KE); cudaFree(ctx->BE); cudaFree(ctx->nzval); cudaFree(ctx->bvec); cudaFree(ctx->f_dev);
+  cudaFree(ctx->KE); cudaFree(ctx->BE); cudaFree(ctx->nzval); cudaFree(ctx->bvec); cudaFree(ctx->f_dev); cudaFree(ctx->Cm);
   delete ctx;
   return GTK_OK;
 }

@@ -87,6 +87,7 @@ struct gtk_ctx {
   double* nzval = nullptr; size_t nzval_cap = 0;
   double* bvec = nullptr;  size_t bvec_cap = 0;
   double* f_dev = nullptr; size_t f_cap = 0;  // uploaded f_nodal / f_qp
+  double* Cm = nullptr;  size_t Cm_cap = 0;   // [n_cells][n_q padded][6] per-point metric (elemgemm.cu)
 
   struct { size_t xyz = 0, cell_nodes = 0, cell_dofs = 0, w = 0, N = 0, dN = 0, M = 0, dM = 0; } sz;  // uploaded element counts
 

@@ -14,6 +14,7 @@
 
 int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
                        const gtk_form_params* pv, bool* handled);
+int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool* handled);   // elemgemm.cu
 
 namespace {
 
@@ -270,8 +271,22 @@ int32_t pick_cb(gtk_ctx* ctx, size_t per_cell_bytes, int* cb, size_t* smem) {
 
 }  // namespace
 
+// compress (assembly.jl:571-588) of the staged element matrices: shared by the generic and the DMMA path
+int32_t gtk_reduce_nz_launch(gtk_ctx* ctx) {
+  MatSym& m = ctx->ms;
+  { GtkProf pr_(ctx, "k_reduce_nz"); k_reduce_nz<<<grid_for(m.nnz, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->KE, m.perm, m.nzptr, m.nnz, ctx->nzval); }
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  return GTK_OK;
+}
+
 int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params* p) {
   MatSym& m = ctx->ms;
+  {
+    bool handled = false;
+    int32_t rc = gtk_elemgemm_try(ctx, form, p, &handled);
+    if (rc || handled) return rc;
+  }
   if (form == GTK_FORM_ELASTICITY_ISO && ctx->ncomp != ctx->D)
     GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "ELASTICITY_ISO needs a vector space with n_comp == D");
   if (form != GTK_FORM_LAPLACE && form != GTK_FORM_MASS && form != GTK_FORM_ELASTICITY_ISO)
@@ -303,10 +318,7 @@ int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params
 #undef LAUNCH_M
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
-  { GtkProf pr_(ctx, "k_reduce_nz"); k_reduce_nz<<<grid_for(m.nnz, 256, ctx->sm_count), 256, 0, st>>>(ctx->KE, m.perm, m.nzptr, m.nnz, ctx->nzval); }
-  GTK_CK(cudaGetLastError());
-  gtk_count_launch(ctx);
-  return GTK_OK;
+  return gtk_reduce_nz_launch(ctx);
 }
 
 static int32_t upload_f(gtk_ctx* ctx, const double* host, size_t n) {
