@@ -12,15 +12,11 @@
 //
 //   k_cell_metric         : one thread per (cell, point): J = Σ_n x_n ⊗ ∇̂M_n (accessors.jl:941-968), C_q -> HBM
 //                           (48 B per point; 0.8 GB at config 3, 5 % of the step's traffic)
-//   k_elem_laplace_dmma   : persistent CTAs, one cell at a time, MT = n_ldofs/8 warps.  C_q of the NEXT cell arrives by
-//                           a TMA bulk copy (cp.async.bulk + mbarrier) while this cell's GEMM runs.  Thread (warp w,
-//                           lane = 4r+c) owns Ĝ[(q,·), i = 8w+r] for q ≡ c (mod 4): exactly its DMMA A fragments
-//                           AND the operands it needs to produce column j = 8w+r of Y.  K is ordered
-//                           k = 4·(3·(q/4) + a) + q%4 so that one k-step of 4 is one direction a of 4 consecutive points.
-//                           Y lives in shared memory with row stride n_ldofs+4 doubles: the B-fragment loads (lane reads
-//                           row c, column 8t+r) and the production stores are bank-conflict-free.
-//                           Result tile D[i][j] goes straight from the accumulator fragments to the e-indexed staging
-//                           array KE (slot c = i, r = j; 16-byte stores, full 32-byte sectors).
+//   k_elem_laplace_dmma   : persistent CTAs of MT = n_ldofs/8 warps, see the comment at the kernel: K is ordered
+//                           k = 4·(3·(q/4) + a) + q%4 so that one k-step of 4 is one direction a of 4 consecutive points;
+//                           lane (r, c) of warp w owns Ĝ[(q,·), 8w+r] for q ≡ c (mod 4), which are at the same time its
+//                           DMMA fragments of Ĝ and the operands it needs for column 8w+r of Y.  Result tiles go
+//                           straight from the accumulator fragments to the e-indexed staging array KE.
 // The scatter (compress) is the generic fixed-order segmented sum k_reduce_nz of numeric.cu: no float atomics.
 //
 // Roofline: FP64 tensor pipe.  F_alg = n_cells · 2 · n_ldofs² · 3 n_q; measured DMMA peak on this
@@ -45,21 +41,30 @@ struct MetricArgs {
 };
 
 __global__ void __launch_bounds__(256) k_cell_metric(MetricArgs a) {
+  __shared__ double2 sC[256 * 3];   // staged so that the 48-byte records leave as fully coalesced 16-byte stores
+  extern __shared__ double sdM[];   // [nln*3][nq]: consecutive lanes (points) read consecutive addresses
+  for (int i = threadIdx.x; i < a.nq * a.nln * 3; i += 256) {
+    const int q = i / (a.nln * 3), nj = i - q * (a.nln * 3);
+    sdM[nj * a.nq + q] = a.dM[i];
+  }
+  __syncthreads();
   const int64_t total = a.n_cells * a.nqp;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t base = blockIdx.x * (int64_t)256; base < total; base += (int64_t)gridDim.x * 256) {
+    const int64_t t = base + threadIdx.x;
     const int64_t cell = t / a.nqp;
     const int q = (int)(t - cell * a.nqp);
     double c[6] = {0, 0, 0, 0, 0, 0};
-    if (q < a.nq && cell >= a.act0 && cell < a.act1) {
+    if (t < total && q < a.nq && cell >= a.act0 && cell < a.act1) {
       double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
       const int32_t* nodes = a.cell_nodes + cell * a.nln;
-      const double* dMq = a.dM + (size_t)q * a.nln * 3;
       for (int n = 0; n < a.nln; ++n) {   // local-node order, as accessors.jl:941-948
         const double* x = a.xyz + (size_t)(nodes[n] - 1) * 3;
+        const double x0 = x[0], x1 = x[1], x2 = x[2];
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) J[i][j] += x[i] * dMq[n * 3 + j];
+        for (int j = 0; j < 3; ++j) {
+          const double dm = sdM[(n * 3 + j) * a.nq + q];
+          J[0][j] += x0 * dm; J[1][j] += x1 * dm; J[2][j] += x2 * dm;
+        }
       }
       // adj(J): J^{-1} = adj / det
       double A[3][3];
@@ -82,10 +87,15 @@ __global__ void __launch_bounds__(256) k_cell_metric(MetricArgs a) {
       c[4] = s * (A[1][0] * A[2][0] + A[1][1] * A[2][1] + A[1][2] * A[2][2]);
       c[5] = s * (A[2][0] * A[2][0] + A[2][1] * A[2][1] + A[2][2] * A[2][2]);
     }
-    double2* out = reinterpret_cast<double2*>(a.C + (size_t)t * 6);
-    out[0] = make_double2(c[0], c[1]);
-    out[1] = make_double2(c[2], c[3]);
-    out[2] = make_double2(c[4], c[5]);
+    sC[threadIdx.x * 3 + 0] = make_double2(c[0], c[1]);
+    sC[threadIdx.x * 3 + 1] = make_double2(c[2], c[3]);
+    sC[threadIdx.x * 3 + 2] = make_double2(c[4], c[5]);
+    __syncthreads();
+    const int64_t left = total - base;
+    const int n2 = (int)(left < 256 ? left : 256) * 3;
+    double2* out = reinterpret_cast<double2*>(a.C + (size_t)base * 6);
+    for (int i = threadIdx.x; i < n2; i += 256) out[i] = sC[i];
+    __syncthreads();
   }
 }
 
@@ -124,107 +134,125 @@ struct GemmArgs {
   double* KE;         // [n_cells][nld][nld]
 };
 
-// MT: 8-row tiles of the element matrix (padded n_ldofs = 8 MT) = warps per CTA;  NG: groups of 4 quadrature points.
+// MT: 8x8 tiles per side of the element matrix (padded n_ldofs = 8 MT);  NG: groups of 4 quadrature points.
+// WPB warps share one column block (they take alternate cells), so a CTA has WPB·MT warps.
 template <int MT, int NG>
 struct GemmCfg {
+  static constexpr int WPB = 2;
+  static constexpr int NW = WPB * MT;
   static constexpr int NLDP = 8 * MT;
   static constexpr int NQP = 4 * NG;
   static constexpr int KS = 3 * NG;          // k-steps of 4
-  static constexpr int SJ = NLDP + 4;        // row stride of Y in doubles (≡ 4 mod 16 when NLDP ≡ 0 mod 16; see below)
-  static constexpr int THREADS = 32 * MT;
-  static constexpr size_t Y_BYTES = (size_t)4 * KS * SJ * sizeof(double);
-  static constexpr size_t C_BYTES = (size_t)NQP * 6 * sizeof(double);
-  static constexpr size_t SMEM = Y_BYTES + 2 * C_BYTES + 16;
+  static constexpr int THREADS = 32 * NW;
+  static constexpr int NTW = MT / 2 + 1;     // tiles per warp (circulant split of the upper triangle)
+  static constexpr int CD = NQP * 6;         // doubles of one cell's metric
+  static constexpr size_t G_BYTES = (size_t)MT * KS * 32 * sizeof(double);   // fragment table of Ĝ
+  static constexpr size_t C_BYTES = (size_t)CD * sizeof(double);
+  static constexpr size_t SMEM = G_BYTES + (size_t)NW * 2 * C_BYTES + (size_t)NW * 2 * sizeof(uint64_t);
 };
 
+// A warp owns COLUMN block cb of Ke for every WPB-th cell of its CTA.  Its B fragments are the columns j = 8cb+r of Y,
+// which lane (r, c) computes in registers from C_q (q ≡ c mod 4) and the 3 values Ĝ[(q,·), j] — Y never touches shared
+// memory.  All fragments of Ĝ (A operands, and the production's inputs, which are the diagonal tile's A fragments) come
+// from a constant table in shared memory, Gs[row block][k-step][lane], built once per CTA: conflict-free 8-byte loads.
+// Ke is symmetric (C_q is), so only the upper triangle of tiles is computed: column block cb takes the row blocks
+// (cb + d) mod MT, d = 0 .. MT/2, the last one only for cb < MT/2 — every unordered pair of blocks exactly once, 4 or 5
+// tiles per warp for MT = 8.  Each off-diagonal tile is stored twice (as computed and transposed), which also makes the
+// assembled matrix bitwise symmetric.
+// Warps never synchronise with each other after the table is built: each streams through its cells on its own, fetching
+// C_q two cells ahead with its own TMA bulk copies (cp.async.bulk + a private pair of mbarriers); 4 warps per SM
+// sub-partition keep the DMMA pipe fed while others wait for operands or store.
 template <int MT, int NG>
-__global__ void __launch_bounds__(32 * MT, 1) k_elem_laplace_dmma(GemmArgs a) {
+__global__ void __launch_bounds__(GemmCfg<MT, NG>::THREADS, 1) k_elem_laplace_dmma(GemmArgs a) {
   using Cfg = GemmCfg<MT, NG>;
-  constexpr int SJ = Cfg::SJ, KS = Cfg::KS;
+  constexpr int NTW = Cfg::NTW, KS = Cfg::KS, CD = Cfg::CD;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* Ys = reinterpret_cast<double*>(smem_raw);
-  double* Cs = reinterpret_cast<double*>(smem_raw + Cfg::Y_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + Cfg::Y_BYTES + 2 * Cfg::C_BYTES);
-
+  double* Gs = reinterpret_cast<double*>(smem_raw);
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
+  const int cb = w % MT, sub = w / MT;   // column block, position among the warps sharing it
+  double* Cw = reinterpret_cast<double*>(smem_raw + Cfg::G_BYTES) + (size_t)w * 2 * CD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + Cfg::G_BYTES + (size_t)Cfg::NW * 2 * Cfg::C_BYTES) + 2 * w;
   const int nld = a.nld;
-  const int iown = 8 * w + r;   // row of Ĝᵀ (A fragment) = column of Y this thread produces
 
-  // A fragments: Ĝ[(q = 4g+c, a), i = iown], zero outside the element's real size
-  double A[NG][3];
-#pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    const int q = 4 * g + c;
-    const bool in = q < a.nq && iown < nld;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) A[g][d] = in ? a.dN[((size_t)q * nld + iown) * 3 + d] : 0.0;
+  // fragment table: Gs[(m*KS + 3g + d)*32 + 4r + c] = Ĝ[(q = 4g+c, d), i = 8m + r], zero outside the element's real size
+  for (int idx = threadIdx.x; idx < MT * KS * 32; idx += Cfg::THREADS) {
+    const int l = idx & 31, s = (idx >> 5) % KS, m = idx / (32 * KS);
+    const int q = 4 * (s / 3) + (l & 3), i = 8 * m + (l >> 2);
+    Gs[idx] = (q < a.nq && i < nld) ? a.dN[((size_t)q * nld + i) * 3 + (s % 3)] : 0.0;
   }
-
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  int64_t cell = blockIdx.x;
-  if (threadIdx.x == 0 && cell < a.n_cells) {
-    mbar_expect_tx(&bars[0], (uint32_t)Cfg::C_BYTES);
-    tma_load_1d(Cs, a.C + (size_t)cell * Cfg::NQP * 6, (uint32_t)Cfg::C_BYTES, &bars[0]);
-  }
-  uint32_t it = 0;
-  for (; cell < a.n_cells; cell += gridDim.x, ++it) {
-    const int par = it & 1;
-    const int64_t next = cell + gridDim.x;
-    if (threadIdx.x == 0 && next < a.n_cells) {   // buffer par^1 was last read before the previous iteration's barriers
-      mbar_expect_tx(&bars[par ^ 1], (uint32_t)Cfg::C_BYTES);
-      tma_load_1d(Cs + (par ^ 1) * Cfg::NQP * 6, a.C + (size_t)next * Cfg::NQP * 6, (uint32_t)Cfg::C_BYTES, &bars[par ^ 1]);
-    }
-    mbar_wait(&bars[par], (it >> 1) & 1);
 
-    // ---- produce Y[(q,a), j = iown] = Σ_b C_q[a][b] Ĝ[(q,b), j] for q ≡ c (mod 4) ----
-    const double* Cq = Cs + par * Cfg::NQP * 6;
+  const double* gt[NTW];   // fragment base of this warp's d-th tile (row block (cb+d) % MT); d = 0 is its own block
+#pragma unroll
+  for (int d = 0; d < NTW; ++d) gt[d] = Gs + (size_t)(((cb + d) % MT) * KS) * 32 + lane;
+  const bool last_tile = cb < MT / 2;   // warp-uniform
+
+  // cells of this warp: first + k*stride, k = 0 .. K-1
+  const int64_t stride = (int64_t)gridDim.x * Cfg::WPB, first = blockIdx.x + (int64_t)sub * gridDim.x;
+  if (first >= a.n_cells) return;
+  const int64_t K = (a.n_cells - first + stride - 1) / stride;
+  auto issue = [&](int64_t k) {   // lane 0: C of the warp's k-th cell -> its buffer k&1
+    const int b = (int)(k & 1);
+    mbar_expect_tx(&bars[b], (uint32_t)Cfg::C_BYTES);
+    tma_load_1d(Cw + b * CD, a.C + (size_t)(first + k * stride) * CD, (uint32_t)Cfg::C_BYTES, &bars[b]);
+  };
+  if (lane == 0) {
+    issue(0);
+    if (K > 1) issue(1);
+  }
+  const int jown = 8 * cb + 2 * c;   // first of the two Ke columns in this lane's accumulator fragments
+
+  for (int64_t k = 0; k < K; ++k) {
+    const double* Cq = Cw + (k & 1) * CD;
+    mbar_wait(&bars[k & 1], (uint32_t)((k >> 1) & 1));
+
+    double acc[NTW][2];
+#pragma unroll
+    for (int d = 0; d < NTW; ++d) acc[d][0] = acc[d][1] = 0.0;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
+      // Y[(q,·), j] = C_q Ĝ[(q,·), j] for q = 4g + c: the B fragments of k-steps 3g .. 3g+2
       const double2* cp = reinterpret_cast<const double2*>(Cq + (4 * g + c) * 6);
       const double2 c01 = cp[0], c23 = cp[1], c45 = cp[2];   // xx xy | xz yy | yz zz
-      const double g0 = A[g][0], g1 = A[g][1], g2 = A[g][2];
-      const double y0 = c01.x * g0 + c01.y * g1 + c23.x * g2;
-      const double y1 = c01.y * g0 + c23.y * g1 + c45.x * g2;
-      const double y2 = c23.x * g0 + c45.x * g1 + c45.y * g2;
-      double* yp = Ys + (size_t)(4 * (3 * g) + c) * SJ + iown;
-      yp[0] = y0;
-      yp[4 * SJ] = y1;
-      yp[8 * SJ] = y2;
-    }
-    __syncthreads();
-
-    // ---- Ke rows [8w, 8w+8) = Ĝᵀ Y : KS k-steps × MT column tiles of DMMA.8x8x4 ----
-    double acc[MT][2];
+      const double g0 = gt[0][(3 * g) * 32], g1 = gt[0][(3 * g + 1) * 32], g2 = gt[0][(3 * g + 2) * 32];
+      double y[3];
+      y[0] = c01.x * g0 + c01.y * g1 + c23.x * g2;
+      y[1] = c01.y * g0 + c23.y * g1 + c45.x * g2;
+      y[2] = c23.x * g0 + c45.x * g1 + c45.y * g2;
 #pragma unroll
-    for (int t = 0; t < MT; ++t) acc[t][0] = acc[t][1] = 0.0;
-    const double* yb = Ys + (size_t)c * SJ + r;
+      for (int d3 = 0; d3 < 3; ++d3) {
+        const int s = 3 * g + d3;
+        dmma884(acc[0][0], acc[0][1], d3 == 0 ? g0 : (d3 == 1 ? g1 : g2), y[d3]);
 #pragma unroll
-    for (int s = 0; s < KS; ++s) {
-      const double af = A[s / 3][s % 3];
-#pragma unroll
-      for (int t = 0; t < MT; ++t) dmma884(acc[t][0], acc[t][1], af, yb[(size_t)(4 * s) * SJ + 8 * t]);
-    }
-
-    // ---- store: D[i = 8w+r][j = 8t+2c+{0,1}] -> KE[cell][c_slot = i][r_slot = j] ----
-    double* out = a.KE + (size_t)cell * nld * nld + (size_t)iown * nld;
-    if (nld == Cfg::NLDP) {
-#pragma unroll
-      for (int t = 0; t < MT; ++t)
-        *reinterpret_cast<double2*>(out + 8 * t + 2 * c) = make_double2(acc[t][0], acc[t][1]);
-    } else if (iown < nld) {
-#pragma unroll
-      for (int t = 0; t < MT; ++t) {
-        const int j = 8 * t + 2 * c;
-        if (j < nld) out[j] = acc[t][0];
-        if (j + 1 < nld) out[j + 1] = acc[t][1];
+        for (int d = 1; d < NTW - 1; ++d) dmma884(acc[d][0], acc[d][1], gt[d][s * 32], y[d3]);
+        if (NTW > 1 && last_tile) dmma884(acc[NTW - 1][0], acc[NTW - 1][1], gt[NTW - 1][s * 32], y[d3]);
       }
     }
-    __syncthreads();   // Y is rewritten by the next iteration
+    __syncwarp();
+    if (lane == 0 && k + 2 < K) issue(k + 2);   // every lane is done reading buffer k&1
+
+    // ---- store: D[i = 8m+r][j = jown+{0,1}] -> KE[cell][c_slot = i][r_slot = j] and its transpose ----
+    double* ke = a.KE + (size_t)(first + k * stride) * nld * nld;
+#pragma unroll
+    for (int d = 0; d < NTW; ++d) {
+      if (d == NTW - 1 && d > 0 && !last_tile) break;
+      const int i = 8 * ((cb + d) % MT) + r;
+      if (nld == Cfg::NLDP) {
+        *reinterpret_cast<double2*>(ke + (size_t)i * nld + jown) = make_double2(acc[d][0], acc[d][1]);
+        if (d > 0) {
+          ke[(size_t)jown * nld + i] = acc[d][0];
+          ke[(size_t)(jown + 1) * nld + i] = acc[d][1];
+        }
+      } else if (i < nld) {
+        if (jown < nld) { ke[(size_t)i * nld + jown] = acc[d][0]; if (d > 0) ke[(size_t)jown * nld + i] = acc[d][0]; }
+        if (jown + 1 < nld) { ke[(size_t)i * nld + jown + 1] = acc[d][1]; if (d > 0) ke[(size_t)(jown + 1) * nld + i] = acc[d][1]; }
+      }
+    }
   }
 }
 
@@ -286,8 +314,11 @@ int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool*
   {
     int64_t total = ctx->n_cells * nqp;
     int64_t g = (total + 255) / 256, cap = (int64_t)ctx->sm_count * 16;
+    const size_t dm_bytes = (size_t)nq * ctx->nln * 3 * sizeof(double);
+    if (dm_bytes + 12288 > ctx->smem_optin) GTK_FAIL(GTK_ERR_TOO_LARGE, "geometry tabulation too large for k_cell_metric");
+    GTK_CK(cudaFuncSetAttribute(k_cell_metric, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dm_bytes));
     GtkProf pr_(ctx, "k_cell_metric");
-    k_cell_metric<<<(int)(g > cap ? cap : g), 256, 0, ctx->stream>>>(ma);
+    k_cell_metric<<<(int)(g > cap ? cap : g), 256, dm_bytes, ctx->stream>>>(ma);
   }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);

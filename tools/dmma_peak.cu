@@ -64,6 +64,7 @@ void run(int blocks, int threads, int iters) {
   cudaFree(out);
 }
 
+int main2();
 int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   printf("%s SMs=%d\n", p.name, p.multiProcessorCount);
@@ -79,5 +80,54 @@ int main() {
   run<2, 1>(148, 128, 4096);
   run<3, 8>(148, 256, 1024);
   run<3, 1>(148, 128, 2048);
+  main2();
+  return 0;
+}
+
+// ---- operand-pattern variants (what a real register-blocked kernel issues) --------------------------------
+// PAT 0: consecutive DMMAs share B, distinct A and C (column-block ownership)   PAT 1: share A, distinct B and C
+template <int PAT, int NT, int NK>
+__global__ void k_dmma_pat(double* out, int iters) {
+  double a[NK * NT], b[NK * NT];
+  for (int i = 0; i < NK * NT; ++i) { a[i] = 1e-3 * (threadIdx.x % 7) + i * 1e-4; b[i] = 1e-3 * (threadIdx.x % 5) - i * 1e-4; }
+  double c[NT][2];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        if constexpr (PAT == 0) dmma884(*reinterpret_cast<double (*)[2]>(&c[t][0]), a[k * NT + t], b[k]);
+        else dmma884(*reinterpret_cast<double (*)[2]>(&c[t][0]), a[k], b[k * NT + t]);
+      }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+template <int PAT, int NT, int NK>
+void run_pat(int threads, int iters) {
+  double* out; cudaMalloc(&out, 8);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_dmma_pat<PAT, NT, NK><<<148, threads>>>(out, iters);
+  cudaEventRecord(e0);
+  k_dmma_pat<PAT, NT, NK><<<148, threads>>>(out, iters);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  double n = (double)(threads / 32) / 4 * iters * NT * NK;   // DMMAs per SM sub-partition
+  printf("DMMA pattern %d (%s) NT=%d NK=%d threads=%d: %.3f ms  %.2f cycles/instr/SMSP  %.2f TFLOP/s\n", PAT,
+         PAT == 0 ? "shared B, distinct A,C" : "shared A, distinct B,C", NT, NK, threads, ms, ms * 1e-3 * 1.965e9 / n,
+         148.0 * 4 * n * 512 / ms / 1e9);
+  cudaFree(out);
+}
+int main2() {
+  run_pat<0, 5, 8>(256, 2048);
+  run_pat<1, 5, 8>(256, 2048);
+  run_pat<0, 4, 8>(256, 2048);
+  run_pat<0, 8, 4>(256, 2048);
+  run_pat<1, 8, 4>(256, 2048);
+  run_pat<0, 5, 8>(128, 2048);
   return 0;
 }
