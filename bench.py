@@ -273,11 +273,14 @@ def main():
     symbolic_first_ms = 1e3 * (time.perf_counter() - t0)   # includes lazy CUDA module load + first allocations
     symbolic_ms = symbolic_first_ms
     if world == 1:                                           # steady-state cost of the symbolic phase (pattern + plan)
-        t0 = time.perf_counter()
-        eng.matrix_symbolic()
-        eng.vector_symbolic()
-        torch.cuda.synchronize()
-        symbolic_ms = 1e3 * (time.perf_counter() - t0)
+        reps = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            eng.matrix_symbolic()
+            eng.vector_symbolic()
+            torch.cuda.synchronize()
+            reps.append(1e3 * (time.perf_counter() - t0))
+        symbolic_ms = sorted(reps)[1]
     mp = dict(alpha=1.0)
     vp = dict(f_const=[1.0])
 

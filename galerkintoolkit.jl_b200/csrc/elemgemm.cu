@@ -282,7 +282,8 @@ int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool*
   if (form != GTK_FORM_LAPLACE || ctx->D != 3 || ctx->ncomp != 1) return GTK_OK;
   const int nld = ctx->nld, nq = ctx->nq;
   int mt, ng;
-  if (nld <= 16 && nq <= 12) { mt = 2; ng = 3; }
+  if (nld <= 8 && nq <= 8) { mt = 1; ng = 2; }
+  else if (nld <= 16 && nq <= 12) { mt = 2; ng = 3; }
   else if (nld <= 32 && nq <= 28) { mt = 4; ng = 7; }
   else if (nld <= 64 && nq <= 64) { mt = 8; ng = 16; }
   else return GTK_OK;
@@ -325,7 +326,8 @@ int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool*
 
   GemmArgs ga;
   ga.dN = ctx->dN; ga.C = ctx->Cm; ga.n_cells = ctx->n_cells; ga.nld = nld; ga.nq = nq; ga.KE = ctx->KE;
-  if (mt == 2) rc = launch_gemm<2, 3>(ctx, ga);
+  if (mt == 1) rc = launch_gemm<1, 2>(ctx, ga);
+  else if (mt == 2) rc = launch_gemm<2, 3>(ctx, ga);
   else if (mt == 4) rc = launch_gemm<4, 7>(ctx, ga);
   else rc = launch_gemm<8, 16>(ctx, ga);
   if (rc) return rc;

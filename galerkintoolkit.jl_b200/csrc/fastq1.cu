@@ -26,6 +26,7 @@
 //   the general kernel's lerped Jacobian is the same constant at all 8 points, so both kernels evaluate
 //   the same mathematical expression on identical geometry data (results agree to rounding, ~1e-16).
 #include <utility>
+#include <cub/cub.cuh>
 #include "gtk_internal.h"
 #include "q1hex_math.cuh"
 
@@ -50,7 +51,8 @@ struct FastPlan {
   uint8_t* slot_tbl = nullptr;       // [n_free][32] slot of neighbour offset o in the column, 255 = absent
   uint32_t* col_mask = nullptr;      // [n_free] bit o: neighbour o present; bit 31: slots are not popcount-monotone
   NodeCol* node_col = nullptr;       // [n_nodes]
-  bool ok = false;
+  bool structured = false;           // topology verified (plan_detect)
+  bool ok = false;                   // tables built: the sweep kernels may run
   bool tried = false;
   int affine_state = -1;             // -1 unknown (coordinates changed), 0 some cell is not affine, 1 every cell is exactly affine
   int* d_flag = nullptr;
@@ -152,6 +154,80 @@ __global__ void k_node_col(const int32_t* __restrict__ node_dof, const int64_t* 
     out[n] = r;
   }
 }
+
+// ---- structured symbolic phase: the CSC pattern straight from the node lattice (no COO, no sort) -----------------
+// Column of free dof `col` = node (i,j,k): its rows are the free dofs of the <= 27 lattice neighbours (every neighbour
+// shares a cell with the node, so this is exactly the union of the element blocks the reference's counting loop +
+// sparse() produce, assembly.jl:119-153, 571-575), sorted by row id as CSC wants them.
+__global__ void k_struct_count(const int32_t* __restrict__ node_dof, const int32_t* __restrict__ dof_node, int64_t n_free,
+                               int n1, int n2, int n3, int32_t* __restrict__ cnt, int* bad) {
+  const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col <= n_free; col += (int64_t)gridDim.x * blockDim.x) {
+    if (col == n_free) { cnt[col] = 0; continue; }
+    int64_t node = dof_node[col];
+    if (node < 0 || node_dof[node] != col + 1) { *bad = 1; cnt[col] = 0; continue; }   // not a bijection (e.g. periodic dofs)
+    int i = (int)(node % s1), j = (int)((node / s1) % (n2 + 1)), k = (int)(node / s2);
+    int c = 0;
+    for (int o = 0; o < 27; ++o) {
+      int ii = i + o % 3 - 1, jj = j + (o / 3) % 3 - 1, kk = k + o / 9 - 1;
+      if (ii >= 0 && ii <= n1 && jj >= 0 && jj <= n2 && kk >= 0 && kk <= n3) c += node_dof[ii + s1 * jj + s2 * kk] > 0;
+    }
+    cnt[col] = c;
+  }
+}
+
+__global__ void k_struct_fill(const int32_t* __restrict__ node_dof, const int32_t* __restrict__ dof_node,
+                              const int64_t* __restrict__ colptr, int64_t n_free, int n1, int n2, int n3,
+                              int32_t* __restrict__ rowval, uint8_t* __restrict__ slot_tbl, uint32_t* __restrict__ col_mask) {
+  const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  for (int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; col < n_free; col += (int64_t)gridDim.x * blockDim.x) {
+    int64_t node = dof_node[col];
+    if (node < 0) continue;
+    int i = (int)(node % s1), j = (int)((node / s1) % (n2 + 1)), k = (int)(node / s2);
+    int rows[27];
+    uint32_t mask = 0;
+    for (int o = 0; o < 27; ++o) {
+      int ii = i + o % 3 - 1, jj = j + (o / 3) % 3 - 1, kk = k + o / 9 - 1;
+      int r = 0;
+      if (ii >= 0 && ii <= n1 && jj >= 0 && jj <= n2 && kk >= 0 && kk <= n3) r = node_dof[ii + s1 * jj + s2 * kk];
+      rows[o] = r;
+      if (r > 0) mask |= 1u << o;
+    }
+    const int64_t p0 = colptr[col];
+    bool monotone = true;
+    uint32_t seen = 0;
+    for (int o = 0; o < 27; ++o) {
+      uint8_t slot = 255;
+      if (rows[o] > 0) {
+        int rank = 0;   // row ids within one column are distinct (bijection checked by k_struct_count)
+        for (int u = 0; u < 27; ++u) rank += rows[u] > 0 && rows[u] < rows[o];
+        slot = (uint8_t)rank;
+        rowval[p0 + rank] = rows[o];
+        if (rank != __popc(seen)) monotone = false;
+        seen |= 1u << o;
+      }
+      slot_tbl[col * 32 + o] = slot;
+    }
+    col_mask[col] = monotone ? mask : (mask | 0x80000000u);
+  }
+}
+
+// N_coo = number of triplets the reference would push (assembly.jl:545-556): Σ_cells (#free dofs of the cell)^2
+__global__ void k_struct_ncoo(const int32_t* __restrict__ cell_dofs, int64_t n_cells, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    int f = 0;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) f += cell_dofs[c * 8 + v] > 0;
+    acc += (unsigned long long)(f * f);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+struct ToI64 {
+  __host__ __device__ __forceinline__ int64_t operator()(const int32_t& v) const { return (int64_t)v; }
+};
 
 struct SweepArgs {
   const double* xyz;
@@ -743,7 +819,7 @@ void plan_free(gtk_ctx* ctx, FastPlan* p) {
   if (p->slot_tbl) gtk_dev_free(ctx, p->slot_tbl, (size_t)32 * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   if (p->col_mask) gtk_dev_free(ctx, p->col_mask, sizeof(uint32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   if (p->node_col) gtk_dev_free(ctx, p->node_col, sizeof(NodeCol) * (size_t)p->n_nodes);
-  if (p->d_flag) cudaFree(p->d_flag);
+  if (p->d_flag) gtk_cuda_free(ctx, p->d_flag);
   if (p->tp_affine.active) gtk_dev_free(ctx, p->tp_affine.active, p->tp_affine.n);
   if (p->tp_sweep.active) gtk_dev_free(ctx, p->tp_sweep.active, p->tp_sweep.n);
   delete p;
@@ -768,13 +844,11 @@ bool tabulation_is_q1_gauss2(const gtk_ctx* ctx) {
   return true;
 }
 
-// Detect the structured topology and build node<->dof maps + slot table.  Any mismatch leaves
-// plan->ok = false and the generic path is used.
-int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
+// Detect the structured topology and build the node<->dof maps.  Any mismatch leaves p->structured = false and the
+// generic path is used.
+int32_t plan_detect(gtk_ctx* ctx, FastPlan* p) {
   p->tried = true;
-  if (ctx->D != 3 || ctx->nln != 8 || ctx->nld != 8 || ctx->ncomp != 1 || ctx->n_cells < 1) return GTK_OK;
-  if (!ctx->ms.ready || ctx->ms.rows_fd != GTK_FREE || ctx->ms.cols_fd != GTK_FREE || ctx->n_free < 1) return GTK_OK;
-  if (!tabulation_is_q1_gauss2(ctx)) return GTK_OK;
+  if (ctx->D != 3 || ctx->nln != 8 || ctx->nld != 8 || ctx->ncomp != 1 || ctx->n_cells < 1 || ctx->n_free < 1) return GTK_OK;
   cudaStream_t st = ctx->stream;
   int32_t first[8];
   GTK_CK(cudaMemcpyAsync(first, ctx->cell_nodes, sizeof(first), cudaMemcpyDeviceToHost, st));
@@ -791,27 +865,40 @@ int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
   int32_t rc;
   if ((rc = gtk_dev_alloc(ctx, (void**)&p->node_dof, sizeof(int32_t) * (size_t)n_nodes))) return rc;
   if ((rc = gtk_dev_alloc(ctx, (void**)&p->dof_node, sizeof(int32_t) * (size_t)ctx->n_free))) return rc;
-  if ((rc = gtk_dev_alloc(ctx, (void**)&p->slot_tbl, (size_t)32 * (size_t)ctx->n_free))) return rc;
-  if ((rc = gtk_dev_alloc(ctx, (void**)&p->col_mask, sizeof(uint32_t) * (size_t)ctx->n_free))) return rc;
-  int* d_bad = nullptr;
-  GTK_CK(cudaMalloc(&d_bad, sizeof(int)));
-  GTK_CK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+  if (!p->d_flag) GTK_CK(gtk_cuda_malloc(ctx, &p->d_flag, sizeof(int)));
+  GTK_CK(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
   GTK_CK(cudaMemsetAsync(p->node_dof, 0, sizeof(int32_t) * (size_t)n_nodes, st));
   GTK_CK(cudaMemsetAsync(p->dof_node, 0xFF, sizeof(int32_t) * (size_t)ctx->n_free, st));
   const int g = grid_for(ctx->n_cells, 256);
-  k_verify_structure<<<g, 256, 0, st>>>(ctx->cell_nodes, ctx->cell_dofs, p->n1, p->n2, p->n3, node_off, p->node_dof, d_bad);
-  k_verify_node_dof<<<g, 256, 0, st>>>(ctx->cell_dofs, p->n1, p->n2, p->n3, p->node_dof, d_bad);
-  k_dof_node<<<grid_for(n_nodes, 256), 256, 0, st>>>(p->node_dof, n_nodes, ctx->n_free, p->dof_node, d_bad);
-  k_slot_table<<<grid_for(ctx->n_free, 128), 128, 0, st>>>(p->node_dof, p->dof_node, ctx->ms.colptr, ctx->ms.rowval,
-                                                         ctx->n_free, p->n1, p->n2, p->n3, p->slot_tbl, p->col_mask, d_bad);
-  GTK_CK(cudaGetLastError());
-  if ((rc = gtk_dev_alloc(ctx, (void**)&p->node_col, sizeof(NodeCol) * (size_t)n_nodes))) return rc;
-  k_node_col<<<grid_for(n_nodes, 256), 256, 0, st>>>(p->node_dof, ctx->ms.colptr, p->col_mask, n_nodes, p->node_col);
+  k_verify_structure<<<g, 256, 0, st>>>(ctx->cell_nodes, ctx->cell_dofs, p->n1, p->n2, p->n3, node_off, p->node_dof, p->d_flag);
+  k_verify_node_dof<<<g, 256, 0, st>>>(ctx->cell_dofs, p->n1, p->n2, p->n3, p->node_dof, p->d_flag);
+  k_dof_node<<<grid_for(n_nodes, 256), 256, 0, st>>>(p->node_dof, n_nodes, ctx->n_free, p->dof_node, p->d_flag);
   GTK_CK(cudaGetLastError());
   int bad = 1;
-  GTK_CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaMemcpyAsync(&bad, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   GTK_CK(cudaStreamSynchronize(st));
-  cudaFree(d_bad);
+  p->structured = bad == 0;
+  return GTK_OK;
+}
+
+// Slot table + column records from an EXISTING pattern (the generic sort-based symbolic phase ran first).
+int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
+  if (!ctx->ms.ready || ctx->ms.rows_fd != GTK_FREE || ctx->ms.cols_fd != GTK_FREE) { p->tried = true; return GTK_OK; }
+  int32_t rc = plan_detect(ctx, p);
+  if (rc || !p->structured) return rc;
+  cudaStream_t st = ctx->stream;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->slot_tbl, (size_t)32 * (size_t)ctx->n_free))) return rc;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->col_mask, sizeof(uint32_t) * (size_t)ctx->n_free))) return rc;
+  GTK_CK(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
+  k_slot_table<<<grid_for(ctx->n_free, 128), 128, 0, st>>>(p->node_dof, p->dof_node, ctx->ms.colptr, ctx->ms.rowval,
+                                                         ctx->n_free, p->n1, p->n2, p->n3, p->slot_tbl, p->col_mask, p->d_flag);
+  GTK_CK(cudaGetLastError());
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->node_col, sizeof(NodeCol) * (size_t)p->n_nodes))) return rc;
+  k_node_col<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, ctx->ms.colptr, p->col_mask, p->n_nodes, p->node_col);
+  GTK_CK(cudaGetLastError());
+  int bad = 1;
+  GTK_CK(cudaMemcpyAsync(&bad, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
   p->ok = bad == 0;
   return GTK_OK;
 }
@@ -882,7 +969,7 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
 // exact per-cell affinity of the numeric-active cell layers; one small kernel + a 4-byte read-back per
 // coordinate upload (cached in the plan until gtk_update_coordinates / gtk_set_mesh)
 int32_t classify_affine(gtk_ctx* ctx, FastPlan* p, const double* xyz, int k0, int k1) {
-  if (!p->d_flag) GTK_CK(cudaMalloc(&p->d_flag, sizeof(int)));
+  if (!p->d_flag) GTK_CK(gtk_cuda_malloc(ctx, &p->d_flag, sizeof(int)));
   GTK_CK(cudaMemsetAsync(p->d_flag, 0, sizeof(int), ctx->stream));
   const int64_t nc = (int64_t)p->n1 * p->n2 * (k1 - k0);
   if (nc > 0) {
@@ -904,8 +991,78 @@ void gtk_fastq1_release(gtk_ctx* ctx) {
   ctx->ms.plan = nullptr;
 }
 
+bool gtk_fastq1_plan_ok(const gtk_ctx* ctx) {
+  return ctx->ms.plan && ((const FastPlan*)ctx->ms.plan)->ok && !getenv("GTK_DISABLE_FASTPATH");
+}
+
 void gtk_fastq1_coords_changed(gtk_ctx* ctx) {
   if (ctx->ms.plan) ((FastPlan*)ctx->ms.plan)->affine_state = -1;
+}
+
+// Structured symbolic phase (free x free): verifies the lattice topology on device and, if it holds, produces colptr /
+// rowval / N_coo and the sweep plan directly from the node lattice — O(nnz) work, no COO keys, no radix sort.  The
+// generic plan (perm / nzptr) is then built lazily, only if a form outside the sweep kernels is assembled.
+int32_t gtk_fastq1_symbolic(gtk_ctx* ctx, bool* handled) {
+  *handled = false;
+  if (getenv("GTK_DISABLE_FASTPATH") || getenv("GTK_DISABLE_STRUCT_SYMBOLIC")) return GTK_OK;
+  FastPlan* p = new FastPlan();
+  int32_t rc = plan_detect(ctx, p);
+  if (rc || !p->structured) { plan_free(ctx, p); return rc; }
+  MatSym& m = ctx->ms;
+  cudaStream_t st = ctx->stream;
+  const int64_t nf = ctx->n_free;
+  int32_t* cnt = nullptr;
+  void* tmp = nullptr;
+  unsigned long long* d_ncoo = nullptr;
+  auto fail = [&](int32_t code) { gtk_cuda_free(ctx, cnt); gtk_cuda_free(ctx, tmp); gtk_cuda_free(ctx, d_ncoo); plan_free(ctx, p); return code; };
+#define CKS(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return fail(GTK_ERR_CUDA); } } while (0)
+  CKS(gtk_cuda_malloc(ctx, &cnt, sizeof(int32_t) * (size_t)(nf + 1)));
+  CKS(gtk_cuda_malloc(ctx, &d_ncoo, sizeof(unsigned long long)));
+  CKS(cudaMemsetAsync(d_ncoo, 0, sizeof(unsigned long long), st));
+  CKS(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
+  k_struct_count<<<grid_for(nf + 1, 256), 256, 0, st>>>(p->node_dof, p->dof_node, nf, p->n1, p->n2, p->n3, cnt, p->d_flag);
+  k_struct_ncoo<<<grid_for(ctx->n_cells, 256), 256, 0, st>>>(ctx->cell_dofs, ctx->n_cells, d_ncoo);
+  CKS(cudaGetLastError());
+  // m.colptr [n_free+1] was allocated (zeroed) by the caller
+  cub::TransformInputIterator<int64_t, ToI64, const int32_t*> it(cnt, ToI64());
+  size_t tb = 0;
+  CKS(cub::DeviceScan::ExclusiveSum(nullptr, tb, it, m.colptr, (int)(nf + 1), st));
+  CKS(gtk_cuda_malloc(ctx, &tmp, tb));
+  CKS(cub::DeviceScan::ExclusiveSum(tmp, tb, it, m.colptr, (int)(nf + 1), st));
+  int64_t nnz = 0;
+  unsigned long long ncoo = 0;
+  int bad = 1;
+  CKS(cudaMemcpyAsync(&nnz, m.colptr + nf, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CKS(cudaMemcpyAsync(&ncoo, d_ncoo, sizeof(ncoo), cudaMemcpyDeviceToHost, st));
+  CKS(cudaMemcpyAsync(&bad, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CKS(cudaStreamSynchronize(st));
+  if (bad) {   // dof <-> node is not a bijection: leave it to the generic path
+    GTK_CK(cudaMemsetAsync(m.colptr, 0, sizeof(int64_t) * (size_t)(nf + 1), st));
+    fail(GTK_OK);
+    return GTK_OK;
+  }
+  gtk_cuda_free(ctx, cnt); cnt = nullptr;
+  gtk_cuda_free(ctx, tmp); tmp = nullptr;
+  gtk_cuda_free(ctx, d_ncoo); d_ncoo = nullptr;
+  m.nnz = nnz;
+  m.n_valid = (int64_t)ncoo;
+  if (nnz > 0) {
+    CKS(gtk_cuda_malloc(ctx, &m.rowval, sizeof(int32_t) * (size_t)nnz));
+    ctx->bytes_held += sizeof(int32_t) * nnz;
+  }
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->slot_tbl, (size_t)32 * (size_t)nf))) return fail(rc);
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->col_mask, sizeof(uint32_t) * (size_t)nf))) return fail(rc);
+  if ((rc = gtk_dev_alloc(ctx, (void**)&p->node_col, sizeof(NodeCol) * (size_t)p->n_nodes))) return fail(rc);
+  k_struct_fill<<<grid_for(nf, 128), 128, 0, st>>>(p->node_dof, p->dof_node, m.colptr, nf, p->n1, p->n2, p->n3, m.rowval,
+                                                  p->slot_tbl, p->col_mask);
+  k_node_col<<<grid_for(p->n_nodes, 256), 256, 0, st>>>(p->node_dof, m.colptr, p->col_mask, p->n_nodes, p->node_col);
+  CKS(cudaGetLastError());
+  CKS(cudaStreamSynchronize(st));
+#undef CKS
+  p->ok = true;
+  ctx->ms.plan = p;
+  *handled = true;
+  return GTK_OK;
 }
 
 // Handles {LAPLACE}, {SOURCE_CONST} or both in one sweep when the mesh/space qualify.
@@ -924,7 +1081,7 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
     int32_t rc = plan_build(ctx, p);
     if (rc) return rc;
   }
-  if (!p->ok) return GTK_OK;
+  if (!p->ok || !tabulation_is_q1_gauss2(ctx)) return GTK_OK;
   int32_t rc;
   if (mform) {
     if (ctx->nzval_cap < (size_t)ctx->ms.nnz || !ctx->nzval) {

@@ -4,16 +4,58 @@
 #include <cstring>
 #include "gtk_internal.h"
 
-int32_t gtk_dev_alloc(gtk_ctx* ctx, void** p, size_t bytes) {
+cudaError_t gtk_cuda_malloc(gtk_ctx* ctx, void** p, size_t bytes) {
   *p = nullptr;
-  GTK_CK(cudaMalloc(p, bytes ? bytes : 1));
+  const size_t sz = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+  auto& pool = ctx->pool;
+  auto it = pool.cached.find(sz);
+  if (it != pool.cached.end()) {
+    *p = it->second;
+    pool.cached.erase(it);
+    pool.cached_bytes -= sz;
+  } else {
+    cudaError_t e = cudaMalloc(p, sz);
+    if (e != cudaSuccess) {   // out of memory: give the cached blocks back to the driver and retry once
+      cudaGetLastError();
+      gtk_pool_flush(ctx);
+      e = cudaMalloc(p, sz);
+      if (e != cudaSuccess) { *p = nullptr; return e; }
+    }
+  }
+  pool.live[*p] = sz;
+  return cudaSuccess;
+}
+
+void gtk_cuda_free(gtk_ctx* ctx, void* p) {
+  if (!p) return;
+  auto& pool = ctx->pool;
+  auto it = pool.live.find(p);
+  if (it == pool.live.end()) { cudaFree(p); return; }   // not ours (should not happen)
+  const size_t sz = it->second;
+  pool.live.erase(it);
+  if (pool.cached_bytes + sz <= pool.cap_bytes) {
+    pool.cached.emplace(sz, p);
+    pool.cached_bytes += sz;
+  } else {
+    cudaFree(p);
+  }
+}
+
+void gtk_pool_flush(gtk_ctx* ctx) {
+  for (auto& kv : ctx->pool.cached) cudaFree(kv.second);
+  ctx->pool.cached.clear();
+  ctx->pool.cached_bytes = 0;
+}
+
+int32_t gtk_dev_alloc(gtk_ctx* ctx, void** p, size_t bytes) {
+  GTK_CK(gtk_cuda_malloc(ctx, p, bytes));
   ctx->bytes_held += (int64_t)bytes;
   return GTK_OK;
 }
 
 void gtk_dev_free(gtk_ctx* ctx, void* p, size_t bytes) {
   if (!p) return;
-  cudaFree(p);
+  gtk_cuda_free(ctx, p);
   ctx->bytes_held -= (int64_t)bytes;
 }
 
@@ -63,9 +105,12 @@ int32_t gtk_destroy(gtk_ctx* ctx) {
   gtk_fastq1_release(ctx);
   gtk_matsym_release(ctx);
   gtk_vecsym_release(ctx);
-  cudaFree(ctx->xyz); cudaFree(ctx->cell_nodes); cudaFree(ctx->cell_dofs);
-  cudaFree(ctx->w); cudaFree(ctx->N); cudaFree(ctx->dN); cudaFree(ctx->M); cudaFree(ctx->dM);
-  cudaFree(ctx->KE); cudaFree(ctx->BE); cudaFree(ctx->nzval); cudaFree(ctx->bvec); cudaFree(ctx->f_dev); cudaFree(ctx->Cm);
+  for (void* q : {(void*)ctx->xyz, (void*)ctx->cell_nodes, (void*)ctx->cell_dofs, (void*)ctx->w, (void*)ctx->N, (void*)ctx->dN,
+                  (void*)ctx->M, (void*)ctx->dM, (void*)ctx->KE, (void*)ctx->BE, (void*)ctx->nzval, (void*)ctx->bvec,
+                  (void*)ctx->f_dev, (void*)ctx->Cm})
+    gtk_cuda_free(ctx, q);
+  gtk_pool_flush(ctx);
+  for (auto& kv : ctx->pool.live) cudaFree(kv.first);   // anything still registered
   delete ctx;
   return GTK_OK;
 }
@@ -154,7 +199,7 @@ int32_t gtk_set_tabulation(gtk_ctx* ctx, int32_t n_q, const double* w, const dou
   if ((rc = upload(ctx, &ctx->dN, &sz.dN, dN, nN * D))) return rc;
   if ((rc = upload(ctx, &ctx->M, &sz.M, M, nM))) return rc;
   if ((rc = upload(ctx, &ctx->dM, &sz.dM, dM, nM * D))) return rc;
-  gtk_fastq1_release(ctx);
+  // the sweep plan depends on mesh + space only; whether the tabulation is the Q1/Gauss-2 one is checked per numeric call
   GTK_CK(cudaStreamSynchronize(ctx->stream));
   return GTK_OK;
 }

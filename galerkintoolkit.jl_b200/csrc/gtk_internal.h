@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "../../include/gtk_assembly.h"
 
@@ -32,6 +34,7 @@ struct DevBuf {
 // Sparse-pattern + assembly plan of one (rows, cols) selection.
 struct MatSym {
   bool ready = false;
+  bool generic_plan = false;   // perm / nzptr built (sort-based plan); false after the structured symbolic phase
   int rows_fd = GTK_FREE, cols_fd = GTK_FREE;
   int64_t n_rows = 0, n_cols = 0;
   int64_t n_full = 0;    // n_cells * n_ldofs^2  (COO slots incl. skipped ones)
@@ -47,6 +50,7 @@ struct MatSym {
 
 struct VecSym {
   bool ready = false;
+  bool generic_plan = false;   // perm / rowptr / urow built
   int fd = GTK_FREE;
   int64_t n_rows = 0;
   int64_t n_full = 0;   // n_cells * n_ldofs
@@ -101,6 +105,16 @@ struct gtk_ctx {
   std::vector<ProfRec> prof;       // records of the last numeric call
   std::vector<ProfRec> prof_pool;  // reusable events
 
+  // device-memory pool: freed blocks are kept and handed out again for requests of the same size, so that a repeated
+  // symbolic phase (same mesh, new space / new selection) does not pay cudaMalloc/cudaFree (ms each, driver-dependent).
+  // Everything the engine does is ordered on ctx->stream, so immediate reuse is safe.
+  struct Pool {
+    std::unordered_map<void*, size_t> live;
+    std::multimap<size_t, void*> cached;
+    size_t cached_bytes = 0;
+    size_t cap_bytes = (size_t)8 << 30;
+  } pool;
+
   // multi-GPU
   void* comm = nullptr;   // ncclComm_t
   int rank = 0, n_ranks = 1;
@@ -108,6 +122,11 @@ struct gtk_ctx {
 };
 
 // ---- helpers implemented in gtk_api.cu ----
+cudaError_t gtk_cuda_malloc(gtk_ctx* ctx, void** p, size_t bytes);   // pooled cudaMalloc (does not touch bytes_held)
+template <class T>
+inline cudaError_t gtk_cuda_malloc(gtk_ctx* ctx, T** p, size_t bytes) { return gtk_cuda_malloc(ctx, reinterpret_cast<void**>(p), bytes); }
+void gtk_cuda_free(gtk_ctx* ctx, void* p);                            // back to the pool
+void gtk_pool_flush(gtk_ctx* ctx);                                    // cudaFree every cached block
 int32_t gtk_dev_alloc(gtk_ctx* ctx, void** p, size_t bytes);
 void gtk_dev_free(gtk_ctx* ctx, void* p, size_t bytes);
 template <class T>
@@ -146,6 +165,8 @@ inline void gtk_prof_reset(gtk_ctx* ctx) {
 // ---- symbolic.cu ----
 int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd);
 int32_t gtk_symbolic_vector_impl(gtk_ctx* ctx, int fd);
+int32_t gtk_symbolic_generic_plan(gtk_ctx* ctx);          // matrix: sort-based pattern + reduction plan
+int32_t gtk_symbolic_vector_generic_plan(gtk_ctx* ctx);   // vector: same
 void gtk_matsym_release(gtk_ctx* ctx);
 void gtk_vecsym_release(gtk_ctx* ctx);
 

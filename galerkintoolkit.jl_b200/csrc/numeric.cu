@@ -282,6 +282,10 @@ int32_t gtk_reduce_nz_launch(gtk_ctx* ctx) {
 
 int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params* p) {
   MatSym& m = ctx->ms;
+  if (!m.generic_plan) {   // the structured symbolic phase deferred the sort-based plan
+    int32_t rc = gtk_symbolic_generic_plan(ctx);
+    if (rc) return rc;
+  }
   {
     bool handled = false;
     int32_t rc = gtk_elemgemm_try(ctx, form, p, &handled);
@@ -334,6 +338,10 @@ int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params
   if (form != GTK_FORM_SOURCE_CONST && form != GTK_FORM_SOURCE_NODAL && form != GTK_FORM_SOURCE_QP)
     GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "unsupported linear form id " + std::to_string(form) +
                                            " (supported: SOURCE_CONST, SOURCE_NODAL, SOURCE_QP); no CPU fallback");
+  if (!v.generic_plan) {
+    int32_t rc = gtk_symbolic_vector_generic_plan(ctx);
+    if (rc) return rc;
+  }
   ElemArgs a;
   int32_t rc = fill_args(ctx, a, form, p);
   if (rc) return rc;

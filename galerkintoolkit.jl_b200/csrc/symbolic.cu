@@ -121,6 +121,8 @@ void gtk_vecsym_release(gtk_ctx* ctx) {
   v = VecSym();
 }
 
+int32_t gtk_fastq1_symbolic(gtk_ctx* ctx, bool* handled);   // fastq1.cu
+
 int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd) {
   gtk_matsym_release(ctx);
   MatSym& m = ctx->ms;
@@ -130,15 +132,34 @@ int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd) {
   m.n_cols = cols_fd == GTK_FREE ? ctx->n_free : ctx->n_diri;
   const int nld = ctx->nld;
   m.n_full = ctx->n_cells * (int64_t)nld * nld;
+  cudaStream_t st = ctx->stream;
+  GTK_CK(gtk_cuda_malloc(ctx, &m.colptr, sizeof(int64_t) * (size_t)(m.n_cols + 1)));
+  ctx->bytes_held += sizeof(int64_t) * (m.n_cols + 1);
+  GTK_CK(cudaMemsetAsync(m.colptr, 0, sizeof(int64_t) * (size_t)(m.n_cols + 1), st));
+  if (rows_fd == GTK_FREE && cols_fd == GTK_FREE) {
+    // structured Q1-hex meshes: pattern + sweep plan straight from the node lattice, generic plan deferred
+    bool handled = false;
+    int32_t rc = gtk_fastq1_symbolic(ctx, &handled);
+    if (rc) return rc;
+    if (handled) { m.ready = true; m.generic_plan = false; return GTK_OK; }
+  }
+  return gtk_symbolic_generic_plan(ctx);
+}
+
+// The sort-based symbolic phase: pattern + reduction plan (perm, nzptr) for the staged generic numeric kernels.  Also
+// called lazily when the structured phase above produced the pattern and a form outside the sweep kernels is assembled
+// (the pattern it rebuilds is the same one, by construction and by test).
+int32_t gtk_symbolic_generic_plan(gtk_ctx* ctx) {
+  MatSym& m = ctx->ms;
+  const int rows_fd = m.rows_fd, cols_fd = m.cols_fd;
+  const int nld = ctx->nld;
   if (m.n_full >= (int64_t)0xFFFFFFFFll)
     GTK_FAIL(GTK_ERR_TOO_LARGE, "n_cells*n_ldofs^2 exceeds the 32-bit COO slot index of this build");
   cudaStream_t st = ctx->stream;
   const int64_t n = m.n_full;
   const uint64_t invalid = (uint64_t)m.n_rows * (uint64_t)m.n_cols;
-
-  GTK_CK(cudaMalloc(&m.colptr, sizeof(int64_t) * (size_t)(m.n_cols + 1)));
-  ctx->bytes_held += sizeof(int64_t) * (m.n_cols + 1);
-  GTK_CK(cudaMemsetAsync(m.colptr, 0, sizeof(int64_t) * (size_t)(m.n_cols + 1), st));
+  if (m.rowval) { ctx->bytes_held -= sizeof(int32_t) * m.nnz; gtk_cuda_free(ctx, m.rowval); m.rowval = nullptr; }
+  m.generic_plan = true;
   if (n == 0 || invalid == 0) {
     m.ready = true;
     GTK_CK(cudaStreamSynchronize(st));
@@ -150,14 +171,14 @@ int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd) {
   void* tmp = nullptr;
   int64_t* d_scalar = nullptr;
   auto cleanup = [&]() {
-    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(tmp); cudaFree(d_scalar);
+    gtk_cuda_free(ctx, k0); gtk_cuda_free(ctx, k1); gtk_cuda_free(ctx, v0); gtk_cuda_free(ctx, v1); gtk_cuda_free(ctx, tmp); gtk_cuda_free(ctx, d_scalar);
   };
 #define CKL(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return GTK_ERR_CUDA; } } while (0)
-  CKL(cudaMalloc(&k0, sizeof(uint64_t) * n));
-  CKL(cudaMalloc(&k1, sizeof(uint64_t) * n));
-  CKL(cudaMalloc(&v0, sizeof(uint32_t) * n));
-  CKL(cudaMalloc(&v1, sizeof(uint32_t) * n));
-  CKL(cudaMalloc(&d_scalar, sizeof(int64_t) * 2));
+  CKL(gtk_cuda_malloc(ctx, &k0, sizeof(uint64_t) * n));
+  CKL(gtk_cuda_malloc(ctx, &k1, sizeof(uint64_t) * n));
+  CKL(gtk_cuda_malloc(ctx, &v0, sizeof(uint32_t) * n));
+  CKL(gtk_cuda_malloc(ctx, &v1, sizeof(uint32_t) * n));
+  CKL(gtk_cuda_malloc(ctx, &d_scalar, sizeof(int64_t) * 2));
 
   k_matrix_keys<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(
       ctx->cell_dofs, n, nld, rows_fd, cols_fd, (uint64_t)m.n_rows, invalid, k0, v0);
@@ -168,7 +189,7 @@ int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd) {
   size_t tmp_bytes = 0;
   const int end_bit = bits_for(invalid);
   CKL(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n, 0, end_bit, st));
-  CKL(cudaMalloc(&tmp, tmp_bytes));
+  CKL(gtk_cuda_malloc(ctx, &tmp, tmp_bytes));
   CKL(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, n, 0, end_bit, st));
   const uint64_t* ks = dk.Current();
   const uint32_t* es = dv.Current();
@@ -183,27 +204,27 @@ int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd) {
   if (n_valid > 0) {
     // segment heads -> nzptr, nnz
     uint32_t* heads = nullptr;   // worst case n_valid entries; shrunk afterwards
-    CKL(cudaMalloc(&heads, sizeof(uint32_t) * (size_t)(n_valid + 1)));
+    CKL(gtk_cuda_malloc(ctx, &heads, sizeof(uint32_t) * (size_t)(n_valid + 1)));
     cub::CountingInputIterator<uint32_t> cnt(0);
     size_t tb2 = 0;
     HeadPred<uint64_t> pred{ks};
     int64_t* d_nsel = d_scalar + 1;
-    cudaFree(tmp); tmp = nullptr;
+    gtk_cuda_free(ctx, tmp); tmp = nullptr;
     CKL(cub::DeviceSelect::If(nullptr, tb2, cnt, heads, d_nsel, n_valid, pred, st));
-    CKL(cudaMalloc(&tmp, tb2));
+    CKL(gtk_cuda_malloc(ctx, &tmp, tb2));
     CKL(cub::DeviceSelect::If(tmp, tb2, cnt, heads, d_nsel, n_valid, pred, st));
     int64_t nnz = 0;
     CKL(cudaMemcpyAsync(&nnz, d_nsel, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CKL(cudaStreamSynchronize(st));
     m.nnz = nnz;
-    CKL(cudaMalloc(&m.nzptr, sizeof(uint32_t) * (size_t)(nnz + 1)));
+    CKL(gtk_cuda_malloc(ctx, &m.nzptr, sizeof(uint32_t) * (size_t)(nnz + 1)));
     CKL(cudaMemcpyAsync(m.nzptr, heads, sizeof(uint32_t) * (size_t)nnz, cudaMemcpyDeviceToDevice, st));
     uint32_t nv32 = (uint32_t)n_valid;
     CKL(cudaMemcpyAsync(m.nzptr + nnz, &nv32, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CKL(cudaStreamSynchronize(st));
-    cudaFree(heads);
-    CKL(cudaMalloc(&m.rowval, sizeof(int32_t) * (size_t)nnz));
-    CKL(cudaMalloc(&m.perm, sizeof(uint32_t) * (size_t)n_valid));
+    gtk_cuda_free(ctx, heads);
+    CKL(gtk_cuda_malloc(ctx, &m.rowval, sizeof(int32_t) * (size_t)nnz));
+    CKL(gtk_cuda_malloc(ctx, &m.perm, sizeof(uint32_t) * (size_t)n_valid));
     ctx->bytes_held += sizeof(uint32_t) * (nnz + 1) + sizeof(int32_t) * nnz + sizeof(uint32_t) * n_valid;
     k_pattern<<<grid_for(nnz, 256, ctx->sm_count), 256, 0, st>>>(ks, m.nzptr, nnz, (uint64_t)m.n_rows,
                                                                  m.n_cols, m.colptr, m.rowval);
@@ -217,37 +238,52 @@ int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd) {
   return GTK_OK;
 }
 
+bool gtk_fastq1_plan_ok(const gtk_ctx* ctx);   // fastq1.cu
+
 int32_t gtk_symbolic_vector_impl(gtk_ctx* ctx, int fd) {
   gtk_vecsym_release(ctx);
   VecSym& v = ctx->vs;
   v.fd = fd;
   v.n_rows = fd == GTK_FREE ? ctx->n_free : ctx->n_diri;
   v.n_full = ctx->n_cells * (int64_t)ctx->nld;
-  if (v.n_full >= (int64_t)0xFFFFFFFFll || v.n_rows >= (int64_t)0x7FFFFFFFll)
+  if (v.n_rows >= (int64_t)0x7FFFFFFFll) GTK_FAIL(GTK_ERR_TOO_LARGE, "row count exceeds Int32");
+  if (fd == GTK_FREE && gtk_fastq1_plan_ok(ctx)) {   // the sweep kernels write b themselves: generic plan deferred
+    v.ready = true;
+    v.generic_plan = false;
+    return GTK_OK;
+  }
+  return gtk_symbolic_vector_generic_plan(ctx);
+}
+
+int32_t gtk_symbolic_vector_generic_plan(gtk_ctx* ctx) {
+  VecSym& v = ctx->vs;
+  const int fd = v.fd;
+  if (v.n_full >= (int64_t)0xFFFFFFFFll)
     GTK_FAIL(GTK_ERR_TOO_LARGE, "n_cells*n_ldofs exceeds the 32-bit slot index of this build");
   cudaStream_t st = ctx->stream;
   const int64_t n = v.n_full;
+  v.generic_plan = true;
   if (n == 0 || v.n_rows == 0) { v.ready = true; return GTK_OK; }
   const uint32_t invalid = (uint32_t)v.n_rows;
   uint32_t *k0 = nullptr, *k1 = nullptr, *v0 = nullptr, *v1 = nullptr, *heads = nullptr;
   void* tmp = nullptr;
   int64_t* d_scalar = nullptr;
   auto cleanup = [&]() {
-    cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(tmp); cudaFree(d_scalar); cudaFree(heads);
+    gtk_cuda_free(ctx, k0); gtk_cuda_free(ctx, k1); gtk_cuda_free(ctx, v0); gtk_cuda_free(ctx, v1); gtk_cuda_free(ctx, tmp); gtk_cuda_free(ctx, d_scalar); gtk_cuda_free(ctx, heads);
   };
 #define CKL(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return GTK_ERR_CUDA; } } while (0)
-  CKL(cudaMalloc(&k0, sizeof(uint32_t) * n));
-  CKL(cudaMalloc(&k1, sizeof(uint32_t) * n));
-  CKL(cudaMalloc(&v0, sizeof(uint32_t) * n));
-  CKL(cudaMalloc(&v1, sizeof(uint32_t) * n));
-  CKL(cudaMalloc(&d_scalar, sizeof(int64_t) * 2));
+  CKL(gtk_cuda_malloc(ctx, &k0, sizeof(uint32_t) * n));
+  CKL(gtk_cuda_malloc(ctx, &k1, sizeof(uint32_t) * n));
+  CKL(gtk_cuda_malloc(ctx, &v0, sizeof(uint32_t) * n));
+  CKL(gtk_cuda_malloc(ctx, &v1, sizeof(uint32_t) * n));
+  CKL(gtk_cuda_malloc(ctx, &d_scalar, sizeof(int64_t) * 2));
   k_vector_keys<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(ctx->cell_dofs, n, fd, invalid, k0, v0);
   CKL(cudaGetLastError());
   cub::DoubleBuffer<uint32_t> dk(k0, k1), dv(v0, v1);
   size_t tb = 0;
   const int end_bit = bits_for(invalid);
   CKL(cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, n, 0, end_bit, st));
-  CKL(cudaMalloc(&tmp, tb));
+  CKL(gtk_cuda_malloc(ctx, &tmp, tb));
   CKL(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, n, 0, end_bit, st));
   const uint32_t* ks = dk.Current();
   const uint32_t* es = dv.Current();
@@ -258,22 +294,22 @@ int32_t gtk_symbolic_vector_impl(gtk_ctx* ctx, int fd) {
   CKL(cudaStreamSynchronize(st));
   v.n_valid = n_valid;
   if (n_valid > 0) {
-    CKL(cudaMalloc(&heads, sizeof(uint32_t) * (size_t)(n_valid + 1)));
+    CKL(gtk_cuda_malloc(ctx, &heads, sizeof(uint32_t) * (size_t)(n_valid + 1)));
     cub::CountingInputIterator<uint32_t> cnt(0);
     HeadPred<uint32_t> pred{ks};
     size_t tb2 = 0;
     int64_t* d_nsel = d_scalar + 1;
-    cudaFree(tmp); tmp = nullptr;
+    gtk_cuda_free(ctx, tmp); tmp = nullptr;
     CKL(cub::DeviceSelect::If(nullptr, tb2, cnt, heads, d_nsel, n_valid, pred, st));
-    CKL(cudaMalloc(&tmp, tb2));
+    CKL(gtk_cuda_malloc(ctx, &tmp, tb2));
     CKL(cub::DeviceSelect::If(tmp, tb2, cnt, heads, d_nsel, n_valid, pred, st));
     int64_t nu = 0;
     CKL(cudaMemcpyAsync(&nu, d_nsel, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CKL(cudaStreamSynchronize(st));
     v.n_urows = nu;
-    CKL(cudaMalloc(&v.rowptr, sizeof(uint32_t) * (size_t)(nu + 1)));
-    CKL(cudaMalloc(&v.urow, sizeof(int32_t) * (size_t)nu));
-    CKL(cudaMalloc(&v.perm, sizeof(uint32_t) * (size_t)n_valid));
+    CKL(gtk_cuda_malloc(ctx, &v.rowptr, sizeof(uint32_t) * (size_t)(nu + 1)));
+    CKL(gtk_cuda_malloc(ctx, &v.urow, sizeof(int32_t) * (size_t)nu));
+    CKL(gtk_cuda_malloc(ctx, &v.perm, sizeof(uint32_t) * (size_t)n_valid));
     ctx->bytes_held += sizeof(uint32_t) * (nu + 1) + sizeof(int32_t) * nu + sizeof(uint32_t) * n_valid;
     CKL(cudaMemcpyAsync(v.rowptr, heads, sizeof(uint32_t) * (size_t)nu, cudaMemcpyDeviceToDevice, st));
     uint32_t nv32 = (uint32_t)n_valid;

@@ -60,16 +60,20 @@ def test_fast_path_matches_oracle_and_generic(cells, bc, warp):
             del os.environ["GTK_DISABLE_AFFINE"]
         assert_values_close(nz, nz_s)
         assert_values_close(b, b_s)
-    # generic path of the same library
+    # generic path of the same library (sort-based symbolic phase, staged element matrices, segmented reduction)
     os.environ["GTK_DISABLE_FASTPATH"] = "1"
+    os.environ["GTK_DISABLE_DMMA"] = "1"
     try:
         eng = make_engine(mesh, V, tab)
         eng.matrix_symbolic()
+        cp_g, rv_g = eng.matrix_pattern()
         nz_g, b_g = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.5), E.FORM_SOURCE_CONST, dict(f_const=[2.0], alpha=0.5))
         assert eng.info(5) == 0
         eng.close()
     finally:
         del os.environ["GTK_DISABLE_FASTPATH"]
+        del os.environ["GTK_DISABLE_DMMA"]
+    assert np.array_equal(cp_g, cp) and np.array_equal(rv_g, rv)
     assert_values_close(nz, nz_g)
     assert_values_close(b, b_g)
 
@@ -125,7 +129,7 @@ def test_fast_path_declines_what_it_does_not_cover():
     cp, rv = eng.matrix_pattern()
     assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
     nz = eng.matrix_numeric(E.FORM_LAPLACE)
-    assert eng.info(5) == 0
+    assert eng.info(5) == 3             # not the sweep kernels (1, 2): the element-GEMM path for unstructured meshes
     assert_values_close(nz, nzval)      # other summation order than the oracle's cell order: still within 1e-12
     # mass on the structured mesh: fast path declines (LAPLACE only)
     eng2 = make_engine(mesh, V, tab)
@@ -161,4 +165,67 @@ def test_full_size_config2_invariants():
     assert abs(b.sum() - (1 - h) ** 3) < 1e-12
     nz2, b2 = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
     assert nz2.tobytes() == nz.tobytes() and b2.tobytes() == b.tobytes()
+    eng.close()
+
+
+STRUCT_CASES = [((12, 9, 7), "boundary"), ((5, 4, 3), None), ((9, 7, 11), [1, 4, 5]), ((1, 1, 1), None), ((2, 2, 2), "boundary"),
+                ((3, 1, 1), [2]), ((24, 24, 24), "boundary")]
+
+
+@pytest.mark.parametrize("cells,bc", STRUCT_CASES)
+def test_structured_symbolic_equals_sort_based(cells, bc):
+    """The lattice-derived pattern (no COO, no sort) is bit-identical to the sort-based one and to the oracle's; the
+    sweep tables built from it give bit-identical values; N_coo agrees; forms outside the sweep kernels build the
+    generic plan lazily on the same pattern."""
+    mesh, V, tab = problem(cells, bc=bc, warp=0.15)
+    colptr, rowval, nzval = oracle_matrix(O.LAPLACE, mesh, V, tab)
+    eng = make_engine(mesh, V, tab)
+    nnz = eng.matrix_symbolic()
+    cp, rv = eng.matrix_pattern()
+    assert nnz == rowval.size and np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
+    ncoo = eng.info(4)
+    nz = eng.matrix_numeric(E.FORM_LAPLACE)
+    fast = eng.info(5)
+    assert fast in (1, 2)      # 2 when the mesh has no interior node to displace
+    assert_values_close(nz, nzval)
+    # lazily built generic plan: MASS is not a sweep-kernel form
+    _, _, mass = oracle_matrix(O.MASS, mesh, V, tab)
+    assert_values_close(eng.matrix_numeric(E.FORM_MASS), mass)
+    assert eng.info(5) == 0
+    cp2, rv2 = eng.matrix_pattern()
+    assert np.array_equal(cp2, cp) and np.array_equal(rv2, rv)
+    assert eng.matrix_numeric(E.FORM_LAPLACE).tobytes() == nz.tobytes() and eng.info(5) == fast
+    fn = np.random.default_rng(3).standard_normal(mesh.n_nodes)
+    assert_values_close(eng.vector_assemble(E.FORM_SOURCE_NODAL, f_nodal=fn), oracle_vector(O.SOURCE_NODAL, mesh, V, tab, f_nodal=fn))
+    assert_values_close(eng.vector_assemble(E.FORM_SOURCE_CONST, f_const=[1.0]), oracle_vector(O.SOURCE_CONST, mesh, V, tab, f_const=[1.0]))
+    eng.close()
+    os.environ["GTK_DISABLE_STRUCT_SYMBOLIC"] = "1"
+    try:
+        eng = make_engine(mesh, V, tab)
+        assert eng.matrix_symbolic() == nnz
+        cp3, rv3 = eng.matrix_pattern()
+        assert eng.info(4) == ncoo
+        nz3 = eng.matrix_numeric(E.FORM_LAPLACE)
+        assert eng.info(5) == fast
+        eng.close()
+    finally:
+        del os.environ["GTK_DISABLE_STRUCT_SYMBOLIC"]
+    assert np.array_equal(cp3, cp) and np.array_equal(rv3, rv)
+    assert nz3.tobytes() == nz.tobytes()
+
+
+def test_structured_symbolic_rejects_scrambled_topology():
+    """A mesh whose cells are permuted is not a lattice in the reference's numbering: the structured phase must step
+    aside and the sort-based phase must still give the oracle's pattern."""
+    mesh, V, tab = problem((6, 5, 4), bc="boundary", warp=0.1)
+    perm = np.random.default_rng(5).permutation(mesh.n_cells)
+    mesh.cell_nodes[:] = mesh.cell_nodes[perm]
+    V.cell_dofs[:] = V.cell_dofs[perm]
+    colptr, rowval, nzval = oracle_matrix(O.LAPLACE, mesh, V, tab)
+    eng = make_engine(mesh, V, tab)
+    assert eng.matrix_symbolic() == rowval.size
+    cp, rv = eng.matrix_pattern()
+    assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
+    assert_values_close(eng.matrix_numeric(E.FORM_LAPLACE), nzval)
+    assert eng.info(5) != 1 and eng.info(5) != 2
     eng.close()
