@@ -128,17 +128,20 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
-def build_problem(n, rank=0, world=1):
-    """Config 2 inputs.  world>1: this rank's z-slab of the n x n x (n*world) mesh."""
+def build_problem(n, rank=0, world=1, cells=None):
+    """Config 2 inputs.  world>1: this rank's z-slab of the n x n x (n*world) mesh.
+    cells = (nx, ny, nz): that many cells PER GPU instead of n^3 (e.g. 512,512,64 = one GPU's share of config 5)."""
     import gtk_b200
     H = gtk_b200.hostprep
+    nx, ny, nz = cells if cells else (n, n, n)
+    zmax = float(nz * world) / nx
     if world == 1:
-        mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (n, n, n))
+        mesh = H.cartesian_mesh((0, 1, 0, float(ny) / nx, 0, zmax), (nx, ny, nz))
         V = H.lagrange_space(mesh, 1, "boundary")
         part = None
     else:
         from galerkintoolkit_jl_b200 import partition as P
-        part = P.slab_problem((0, 1, 0, 1, 0, float(world)), (n, n, n * world), rank, world)
+        part = P.slab_problem((0, 1, 0, float(ny) / nx, 0, zmax), (nx, ny, nz * world), rank, world)
         mesh, V = part.mesh, part.space
     tab = H.measure_tabulation(V, 2)
     return mesh, V, tab, part
@@ -226,6 +229,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="cells per direction per GPU (128 = BASELINE config 2)")
+    ap.add_argument("--cells", default=None, help="nx,ny,nz cells per GPU instead of n^3 (not a BASELINE bench line; e.g. 512,512,64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-high-order", action="store_true", help="skip the BASELINE config 3 (Q3 hex 64^3, DMMA path) entry")
     args = ap.parse_args()
@@ -249,7 +253,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n = args.n
-    mesh, V, tab, part = build_problem(n, rank, world)
+    cells = tuple(int(c) for c in args.cells.split(",")) if args.cells else None
+    if cells:
+        args.no_cpu_baseline = args.no_high_order = True
+    mesh, V, tab, part = build_problem(n, rank, world, cells)
     eng = E.Engine(local_rank)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
@@ -285,9 +292,10 @@ def main():
     vp = dict(f_const=[1.0])
 
     def step():
-        eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
-        if world > 1:
-            eng.comm_sum_ghost_rows()
+        if world > 1:   # one call: sweep + NCCL ghost-row summation, the exchange overlapped with the sweep
+            eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
+        else:
+            eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
 
     def barrier():
         if world > 1:
@@ -357,7 +365,7 @@ def main():
     # the same step on a NON-affine mesh (interior nodes displaced by 0.2 h U(-1,1)): exercises the general sweep
     # kernel instead of the exactly-affine one (reported next to the headline, never as the headline)
     general = None
-    if world == 1:
+    if world == 1 and not cells:
         rng = np.random.default_rng(0)
         warped = mesh.node_coordinates.copy()
         inner = ~gtk_b200.hostprep.boundary_node_mask(mesh)
@@ -390,9 +398,7 @@ def main():
 
     def e2e_step():
         eng.update_coordinates(xyz_np)                                # H2D
-        eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
-        if world > 1:
-            eng.comm_sum_ghost_rows()
+        step()
         eng.copy_nzval(nz_np)                                         # D2H
         eng.copy_vector(b_np)                                         # D2H
 
@@ -418,16 +424,18 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(dominant, {}).get("dram_bytes_per_launch") if n == 128 else None
+                traffic = json.load(f).get(dominant, {}).get("dram_bytes_per_launch") if (n == 128 and not cells) else None
         except Exception:
             traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 2: 3D Poisson Q1 hex {n}^3 cells per GPU, full Dirichlet boundary, "
-                                   f"Float64/Int32, matrix+RHS numeric assembly on a cached pattern",
-                       "cells_per_gpu": n ** 3, "nnz_per_gpu": nnz_local, "free_dofs_per_gpu": V.n_free,
+            "config": {"workload": (f"BASELINE config 2: 3D Poisson Q1 hex {n}^3 cells per GPU, full Dirichlet boundary, "
+                                    f"Float64/Int32, matrix+RHS numeric assembly on a cached pattern") if not cells else
+                                   (f"3D Poisson Q1 hex {cells[0]}x{cells[1]}x{cells[2]} cells per GPU (z-slab; 512x512x64 is one GPU's "
+                                    f"share of BASELINE config 5), full Dirichlet boundary, matrix+RHS numeric assembly on a cached pattern"),
+                       "cells_per_gpu": int(mesh.n_cells) if cells else n ** 3, "nnz_per_gpu": nnz_local, "free_dofs_per_gpu": V.n_free,
                        "partition": "none" if world == 1 else f"{world} z-slabs of {n}^3 cells, NCCL ghost-row sum ({eng.comm_ghost_info(2)} B/step on rank 0)",
                        "l2": "per-step traffic (>0.6 GB) exceeds the 126 MB L2; no explicit flush",
                        "fast_path": eng.info(5)},

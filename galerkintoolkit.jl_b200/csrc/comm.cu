@@ -16,6 +16,9 @@
 #include <algorithm>
 #include "gtk_internal.h"
 
+int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, const int32_t* d_rows, int64_t nb, int* layer);   // fastq1.cu
+bool gtk_fastq1_plan_ok(const gtk_ctx* ctx);
+
 namespace {
 
 struct NcclApi {
@@ -65,10 +68,13 @@ struct Peer {
   int32_t* recv_rows = nullptr;
   double* send_buf = nullptr;   // [n_send_nz + n_send_b]
   double* recv_buf = nullptr;   // [n_recv_nz + n_recv_b]
+  int min_send_layer = -1;      // lowest lattice node layer whose sweep segment writes a value sent to this peer (-1: unknown)
 };
 
 struct GhostPlan {
   std::vector<Peer> peers;   // sorted by rank
+  cudaStream_t side = nullptr;          // pack + NCCL run here while the rest of the sweep runs on ctx->stream
+  cudaEvent_t ev_first = nullptr, ev_xchg = nullptr;
 };
 
 __global__ void k_pack(const double* __restrict__ nzval, const int64_t* __restrict__ idx, int64_t n,
@@ -126,6 +132,9 @@ void gtk_comm_release(gtk_ctx* ctx) {
   GhostPlan* g = (GhostPlan*)ctx->ghost;
   if (g) {
     for (auto& p : g->peers) free_peer(ctx, p);
+    if (g->side) cudaStreamDestroy(g->side);
+    if (g->ev_first) cudaEventDestroy(g->ev_first);
+    if (g->ev_xchg) cudaEventDestroy(g->ev_xchg);
     delete g;
     ctx->ghost = nullptr;
   }
@@ -183,19 +192,16 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
   if (n_send_nz + n_send_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.send_buf, sizeof(double) * (n_send_nz + n_send_b)))) return rc;
   if (n_recv_nz + n_recv_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.recv_buf, sizeof(double) * (n_recv_nz + n_recv_b)))) return rc;
   GTK_CK(cudaStreamSynchronize(ctx->stream));
+  if ((rc = gtk_fastq1_min_layer(ctx, p.send_nz, n_send_nz, p.send_rows, n_send_b, &p.min_send_layer))) return rc;
   g->peers.push_back(p);
   std::sort(g->peers.begin(), g->peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
   return GTK_OK;
 }
 
-int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx) {
-  if (!ctx) return GTK_ERR_INVALID;
-  GhostPlan* g = (GhostPlan*)ctx->ghost;
-  if (!g || g->peers.empty()) return GTK_OK;
-  if (!ctx->comm) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: call gtk_comm_init first");
-  if (!ctx->nzval) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: nothing assembled yet");
-  GTK_CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
+}  // extern "C"
+
+// pack + send/recv on stream `st`
+static int32_t exchange_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
   ncclComm_t comm = (ncclComm_t)ctx->comm;
   for (auto& p : g->peers) {
     const int64_t n = p.n_send_nz + p.n_send_b;
@@ -211,7 +217,12 @@ int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx) {
     if (p.n_recv_nz + p.n_recv_b) NCCL_CK(nccl().Recv(p.recv_buf, (size_t)(p.n_recv_nz + p.n_recv_b), ncclFloat64, p.rank, comm, st));
   }
   NCCL_CK(nccl().GroupEnd());
-  for (auto& p : g->peers) {   // increasing peer rank: fixed summation order
+  return GTK_OK;
+}
+
+// add what the peers sent, in increasing peer rank: fixed summation order
+static int32_t unpack_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
+  for (auto& p : g->peers) {
     const int64_t n = p.n_recv_nz + p.n_recv_b;
     if (n == 0) continue;
     { GtkProf pr_(ctx, "k_unpack_add"); k_unpack_add<<<grid_for(n), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b, p.recv_buf); }
@@ -219,6 +230,87 @@ int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx) {
     gtk_count_launch(ctx);
   }
   return GTK_OK;
+}
+
+extern "C" {
+
+int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx) {
+  if (!ctx) return GTK_ERR_INVALID;
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  if (!g || g->peers.empty()) return GTK_OK;
+  if (!ctx->comm) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: call gtk_comm_init first");
+  if (!ctx->nzval) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: nothing assembled yet");
+  GTK_CK(cudaSetDevice(ctx->device));
+  int32_t rc = exchange_on(ctx, g, ctx->stream);
+  if (rc) return rc;
+  return unpack_on(ctx, g, ctx->stream);
+}
+
+// Numeric assembly + ghost-row summation with the exchange hidden behind the sweep: the z-segments that produce the
+// values a peer waits for run first; their pack + ncclSend/ncclRecv go to a side stream while the remaining segments
+// run on the main stream; the received partial sums are added once both are done.  Same values, same order of additions
+// as gtk_assemble_matrix_and_vector_device + gtk_comm_sum_ghost_rows (bitwise), which is also what runs when the sweep
+// kernels do not apply.
+int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t mform, const gtk_form_params* pm, int32_t vform,
+                                               const gtk_form_params* pv) {
+  if (!ctx) return GTK_ERR_INVALID;
+  GTK_CK(cudaSetDevice(ctx->device));
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  int32_t rc;
+  int layer = 0x7FFFFFFF;
+  if (g) for (auto& p : g->peers) if (p.n_send_nz + p.n_send_b) layer = p.min_send_layer < 0 ? -1 : (layer < 0 ? -1 : (p.min_send_layer < layer ? p.min_send_layer : layer));
+  const bool overlap = g && !g->peers.empty() && ctx->comm && layer >= 0 && layer != 0x7FFFFFFF && gtk_fastq1_plan_ok(ctx) &&
+                       !getenv("GTK_DISABLE_OVERLAP");
+  if (!overlap) {
+    if ((rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv))) return rc;
+    return gtk_comm_sum_ghost_rows(ctx);
+  }
+  if (!g->side) {
+    // highest priority: the block scheduler otherwise keeps feeding the (much larger) sweep grid launched right after
+    // and the pack / NCCL kernels would only start once that grid has been dispatched completely
+    int least = 0, greatest = 0;
+    GTK_CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    GTK_CK(cudaStreamCreateWithPriority(&g->side, cudaStreamNonBlocking, greatest));
+    GTK_CK(cudaEventCreateWithFlags(&g->ev_first, cudaEventDisableTiming));
+    GTK_CK(cudaEventCreateWithFlags(&g->ev_xchg, cudaEventDisableTiming));
+  }
+  static const bool timing = getenv("GTK_COMM_TIMING") != nullptr;   // debug: device timeline of one overlapped step
+  cudaEvent_t te[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (timing) { for (auto& e : te) cudaEventCreate(&e); cudaEventRecord(te[0], ctx->stream); }
+  ctx->seg_mode = 1; ctx->seg_layer = layer;
+  rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv);
+  ctx->seg_mode = 0;
+  if (rc) return rc;
+  if (timing) cudaEventRecord(te[1], ctx->stream);
+  const int64_t launches_first = ctx->launches_last;
+  if (ctx->fast_path_last != 1 && ctx->fast_path_last != 2)   // the sweep declined (form, tabulation): everything is assembled already
+    return gtk_comm_sum_ghost_rows(ctx);
+  GTK_CK(cudaEventRecord(g->ev_first, ctx->stream));
+  GTK_CK(cudaStreamWaitEvent(g->side, g->ev_first, 0));
+  if ((rc = exchange_on(ctx, g, g->side))) return rc;
+  GTK_CK(cudaEventRecord(g->ev_xchg, g->side));
+  if (timing) cudaEventRecord(te[2], g->side);
+  const int64_t launches_x = ctx->launches_last;
+  ctx->seg_mode = 2; ctx->seg_layer = layer;
+  rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv);
+  ctx->seg_mode = 0;
+  if (rc) return rc;
+  ctx->launches_last += launches_x;   // numeric_both_impl restarts the per-call counter
+  (void)launches_first;
+  if (timing) cudaEventRecord(te[3], ctx->stream);
+  GTK_CK(cudaStreamWaitEvent(ctx->stream, g->ev_xchg, 0));
+  rc = unpack_on(ctx, g, ctx->stream);
+  if (timing) {
+    cudaEventRecord(te[4], ctx->stream);
+    cudaEventSynchronize(te[4]);
+    cudaEventSynchronize(te[2]);
+    float t[5] = {0, 0, 0, 0, 0};
+    for (int i = 1; i < 5; ++i) cudaEventElapsedTime(&t[i], te[0], te[i]);
+    fprintf(stderr, "[gtk rank %d] overlap timeline (ms after start): first segments %.4f | exchange done %.4f | rest of sweep %.4f | unpack done %.4f\n",
+            ctx->rank, t[1], t[2], t[3], t[4]);
+    for (auto& e : te) cudaEventDestroy(e);
+  }
+  return rc;
 }
 
 int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key) {

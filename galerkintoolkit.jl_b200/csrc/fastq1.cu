@@ -60,9 +60,9 @@ struct FastPlan {
   struct TilePlan {
     uint8_t* active = nullptr;   // [gx * gy * nseg] 1 = the tile holds at least one matrix column
     size_t n = 0;
-    int key = 0, seg = 0, nseg = 0;
+    int key = 0, seg = 0, nseg = 0, z_begin = 0, z_end = 0;
   };
-  TilePlan tp_affine, tp_sweep;
+  TilePlan tp_affine[3], tp_sweep[3];   // [launch mode]: all layers / first part of an overlapped step / the rest
 };
 
 __global__ void k_verify_structure(const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ cell_dofs,
@@ -241,6 +241,7 @@ struct SweepArgs {
   double* b;
   int n1, n2, n3;
   int seg_len;
+  int z_begin, z_end; // node layers [z_begin, z_end) of this launch; segment blockIdx.z starts at z_begin + blockIdx.z*seg_len
   int kact0, kact1;   // numeric-active cell layers [kact0, kact1)
   double alpha, fscale;
   int do_matrix, do_vector;
@@ -325,8 +326,8 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
 
   const int t = threadIdx.x;
   const int i0 = blockIdx.x * BX, j0 = blockIdx.y * BY;
-  const int kz0 = blockIdx.z * a.seg_len;
-  const int kz1 = min(kz0 + a.seg_len, a.n3 + 1);
+  const int kz0 = a.z_begin + blockIdx.z * a.seg_len;
+  const int kz1 = min(kz0 + a.seg_len, a.z_end);
   const int n1 = a.n1, n2 = a.n2, n3 = a.n3;
   const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
   const int cx = t % C::CX, cy = t / C::CX;
@@ -589,8 +590,8 @@ __global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
   double* XW = CellW + C::CELL_D;                      // [3][PY][PX][3] ring of node-coordinate layers (cp.async, 2 ahead)
 
   const int i0 = blockIdx.x * C::BX, j0 = py * C::BY;
-  const int kz0 = blockIdx.z * a.seg_len;
-  const int kz1 = min(kz0 + a.seg_len, a.n3 + 1);
+  const int kz0 = a.z_begin + blockIdx.z * a.seg_len;
+  const int kz1 = min(kz0 + a.seg_len, a.z_end);
   const int n1 = a.n1, n2 = a.n2;
   const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
   const int li = lane & 15, lj = lane >> 4;
@@ -796,13 +797,15 @@ __global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
 }
 
 // tile_active[x + gx (y + gy z)] = 1 when the tile's footprint x z-segment holds at least one matrix column
-__global__ void k_tile_active(const int32_t* __restrict__ node_dof, int n1, int n2, int n3, int bx, int by, int seg_len,
-                              int gx, int gy, uint8_t* __restrict__ active) {
-  const int64_t nn = (int64_t)(n1 + 1) * (n2 + 1) * (n3 + 1);
-  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+__global__ void k_tile_active(const int32_t* __restrict__ node_dof, int n1, int n2, int z_begin, int z_end, int bx, int by,
+                              int seg_len, int gx, int gy, uint8_t* __restrict__ active) {
+  const int64_t s2 = (int64_t)(n1 + 1) * (n2 + 1);
+  const int64_t nn = s2 * (z_end - z_begin);
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < nn; m += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = m + s2 * z_begin;
     if (node_dof[n] > 0) {
-      const int i = (int)(n % (n1 + 1)), j = (int)((n / (n1 + 1)) % (n2 + 1)), k = (int)(n / ((int64_t)(n1 + 1) * (n2 + 1)));
-      active[i / bx + gx * (j / by + gy * (k / seg_len))] = 1;
+      const int i = (int)(n % (n1 + 1)), j = (int)((n / (n1 + 1)) % (n2 + 1)), k = (int)(n / s2);
+      active[i / bx + gx * (j / by + gy * ((k - z_begin) / seg_len))] = 1;
     }
   }
 }
@@ -820,8 +823,8 @@ void plan_free(gtk_ctx* ctx, FastPlan* p) {
   if (p->col_mask) gtk_dev_free(ctx, p->col_mask, sizeof(uint32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   if (p->node_col) gtk_dev_free(ctx, p->node_col, sizeof(NodeCol) * (size_t)p->n_nodes);
   if (p->d_flag) gtk_cuda_free(ctx, p->d_flag);
-  if (p->tp_affine.active) gtk_dev_free(ctx, p->tp_affine.active, p->tp_affine.n);
-  if (p->tp_sweep.active) gtk_dev_free(ctx, p->tp_sweep.active, p->tp_sweep.n);
+  for (auto& tp : p->tp_affine) if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
+  for (auto& tp : p->tp_sweep) if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
   delete p;
 }
 
@@ -903,23 +906,38 @@ int32_t plan_build(gtk_ctx* ctx, FastPlan* p) {
   return GTK_OK;
 }
 
-// Per-tile skip flags for a (bx x by) footprint and z-segments of seg_len node layers: tiles without any matrix
-// column (e.g. the Dirichlet plane past the last full footprint) exit at once.  Cached per kernel variant (key).
-int32_t build_tile_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::TilePlan& tp, int key, int bx, int by, int gx, int gy, int seg_len) {
-  if (tp.key == key && tp.active && tp.seg == seg_len) return GTK_OK;
+// Per-tile skip flags for a (bx x by) footprint and z-segments of seg_len node layers inside [z_begin, z_end): tiles
+// without any matrix column (e.g. the Dirichlet plane past the last full footprint) exit at once.  Cached per kernel
+// variant (key) and layer range.
+int32_t build_tile_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::TilePlan& tp, int key, int bx, int by, int gx, int gy, int seg_len,
+                        int z_begin, int z_end) {
+  if (tp.key == key && tp.active && tp.seg == seg_len && tp.z_begin == z_begin && tp.z_end == z_end) return GTK_OK;
   if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
   tp.active = nullptr;
-  const int layers = p->n3 + 1;
+  const int layers = z_end - z_begin;
   tp.seg = seg_len < 1 ? 1 : seg_len;
   tp.nseg = (layers + tp.seg - 1) / tp.seg;
-  tp.n = (size_t)gx * gy * tp.nseg;
+  tp.n = (size_t)gx * gy * (tp.nseg > 0 ? tp.nseg : 1);
+  tp.z_begin = z_begin; tp.z_end = z_end;
   int32_t rc;
   if ((rc = gtk_dev_alloc(ctx, (void**)&tp.active, tp.n))) return rc;
   GTK_CK(cudaMemsetAsync(tp.active, 0, tp.n, ctx->stream));
-  k_tile_active<<<grid_for(p->n_nodes, 256), 256, 0, ctx->stream>>>(p->node_dof, p->n1, p->n2, p->n3, bx, by, tp.seg, gx, gy, tp.active);
-  GTK_CK(cudaGetLastError());
+  if (layers > 0) {
+    k_tile_active<<<grid_for((int64_t)(p->n1 + 1) * (p->n2 + 1) * layers, 256), 256, 0, ctx->stream>>>(
+        p->node_dof, p->n1, p->n2, z_begin, z_end, bx, by, tp.seg, gx, gy, tp.active);
+    GTK_CK(cudaGetLastError());
+  }
   tp.key = key;
   return GTK_OK;
+}
+
+// node layers of this launch: all of them, or (multi-GPU overlap, comm.cu) only the layers >= seg_layer (mode 1: they hold
+// what goes to a peer and are launched first) / only the layers below (mode 2)
+void layer_range(const gtk_ctx* ctx, int layers, int* z_begin, int* z_end) {
+  int split = ctx->seg_layer < 0 ? 0 : (ctx->seg_layer > layers ? layers : ctx->seg_layer);
+  if (ctx->seg_mode == 1) { *z_begin = split; *z_end = layers; }
+  else if (ctx->seg_mode == 2) { *z_begin = 0; *z_end = split; }
+  else { *z_begin = 0; *z_end = layers; }
 }
 
 template <int BX, int BY, int MINB>
@@ -931,12 +949,15 @@ int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   // the affine kernel
   const char* ns = getenv("GTK_SWEEP_SEG");
   const int seg = ns && atoi(ns) > 0 ? atoi(ns) : 12;
-  int32_t rc = build_tile_plan(ctx, p, p->tp_sweep, BX * 100 + BY, BX, BY, gx, gy, seg);
+  layer_range(ctx, p->n3 + 1, &a.z_begin, &a.z_end);
+  if (a.z_end <= a.z_begin) return GTK_OK;
+  FastPlan::TilePlan& tp = p->tp_sweep[ctx->seg_mode];
+  int32_t rc = build_tile_plan(ctx, p, tp, BX * 100 + BY, BX, BY, gx, gy, seg, a.z_begin, a.z_end);
   if (rc) return rc;
-  a.seg_len = p->tp_sweep.seg;
-  a.tile_active = p->tp_sweep.active;
+  a.seg_len = tp.seg;
+  a.tile_active = tp.active;
   GTK_CK(cudaFuncSetAttribute(k_q1hex_sweep<BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-  dim3 grid(gx, gy, p->tp_sweep.nseg);
+  dim3 grid(gx, gy, tp.nseg);
   { GtkProf pr_(ctx, "k_q1hex_sweep"); k_q1hex_sweep<BX, BY, MINB><<<grid, C::NT, C::SMEM, ctx->stream>>>(a); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
@@ -955,11 +976,14 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   // shrinks and concurrently written parts of nzval stay close; the halo step of a segment costs about half a step
   const char* ns = getenv("GTK_AFFINE_SEG");
   const int seg = ns && atoi(ns) > 0 ? atoi(ns) : 6;
-  int32_t rc = build_tile_plan(ctx, p, p->tp_affine, 1000 + WPB, C::BX, C::BY, gx, gyp, seg);
+  layer_range(ctx, p->n3 + 1, &a.z_begin, &a.z_end);
+  if (a.z_end <= a.z_begin) return GTK_OK;
+  FastPlan::TilePlan& tp = p->tp_affine[ctx->seg_mode];
+  int32_t rc = build_tile_plan(ctx, p, tp, 1000 + WPB, C::BX, C::BY, gx, gyp, seg, a.z_begin, a.z_end);
   if (rc) return rc;
-  a.seg_len = p->tp_affine.seg;
-  a.tile_active = p->tp_affine.active;
-  dim3 grid(gx, gy, p->tp_affine.nseg);
+  a.seg_len = tp.seg;
+  a.tile_active = tp.active;
+  dim3 grid(gx, gy, tp.nseg);
   { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MAXREG, TWOPASS><<<grid, WPB * 32, smem, ctx->stream>>>(a); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
@@ -989,6 +1013,51 @@ int32_t classify_affine(gtk_ctx* ctx, FastPlan* p, const double* xyz, int k0, in
 void gtk_fastq1_release(gtk_ctx* ctx) {
   plan_free(ctx, (FastPlan*)ctx->ms.plan);
   ctx->ms.plan = nullptr;
+}
+
+bool gtk_fastq1_plan_ok(const gtk_ctx* ctx);
+namespace {
+// The sweep kernels produce whole COLUMNS per lattice node, so the z-segment that writes nzval[p] is the one of the node
+// of p's column (binary search in colptr); b[row] is written by the node of that row.
+__global__ void k_min_layer(const int64_t* __restrict__ nz_pos, int64_t n, const int32_t* __restrict__ rows, int64_t nb,
+                            const int64_t* __restrict__ colptr, int64_t n_cols, const int32_t* __restrict__ dof_node,
+                            int64_t s2, int* out) {
+  int m = 0x7FFFFFFF;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t dof;
+    if (i < n) {
+      const int64_t p = nz_pos[i];
+      int64_t lo = 0, hi = n_cols;   // largest col with colptr[col] <= p
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (colptr[mid] <= p) lo = mid; else hi = mid;
+      }
+      dof = lo;
+    } else {
+      dof = rows[i - n];
+    }
+    m = min(m, (int)(dof_node[dof] / s2));
+  }
+  if (m != 0x7FFFFFFF) atomicMin(out, m);
+}
+}  // namespace
+
+// Lowest node layer (z index of the lattice) whose sweep segment writes one of the given nzval positions / b rows; -1
+// without a sweep plan.
+// The multi-GPU exchange uses it to launch the z-segments that produce the rows a peer waits for first.
+int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, const int32_t* d_rows, int64_t nb, int* layer) {
+  *layer = -1;
+  if (!gtk_fastq1_plan_ok(ctx) || n + nb == 0) return GTK_OK;
+  FastPlan* p = (FastPlan*)ctx->ms.plan;
+  int h = 0x7FFFFFFF;
+  GTK_CK(cudaMemcpyAsync(p->d_flag, &h, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  k_min_layer<<<grid_for(n + nb, 256), 256, 0, ctx->stream>>>(d_nz_pos, n, d_rows, nb, ctx->ms.colptr, ctx->ms.n_cols,
+                                                            p->dof_node, (int64_t)(p->n1 + 1) * (p->n2 + 1), p->d_flag);
+  GTK_CK(cudaGetLastError());
+  GTK_CK(cudaMemcpyAsync(&h, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  if (h != 0x7FFFFFFF) *layer = h;
+  return GTK_OK;
 }
 
 bool gtk_fastq1_plan_ok(const gtk_ctx* ctx) {
@@ -1111,6 +1180,7 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   a.b = ctx->bvec;
   a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3;
   a.seg_len = 0;
+  a.z_begin = 0; a.z_end = p->n3 + 1;
   a.kact0 = 0; a.kact1 = p->n3;
   if (ctx->act_count >= 0) {   // active cells must be whole cell layers for the sweep
     const int64_t per_layer = (int64_t)p->n1 * p->n2;

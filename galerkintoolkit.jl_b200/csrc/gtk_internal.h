@@ -98,6 +98,7 @@ struct gtk_ctx {
   int64_t launches_last = 0, launches_total = 0;
   int64_t bytes_held = 0;
   int fast_path_last = 0;
+  int seg_mode = 0, seg_layer = 0;   // sweep kernels: z-segment subset of the next launch (comm.cu overlap), 0 = all
 
   // per-kernel profiling (events around each launch of the last numeric call)
   bool profiling = false;

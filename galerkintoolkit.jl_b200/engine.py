@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "gtk_assemble_matrix_and_vector", "gtk_assemble_matrix_and_vector_device",
     "gtk_device_pointer", "gtk_copy_nzval", "gtk_copy_vector", "gtk_info",
     "gtk_comm_unique_id", "gtk_comm_init", "gtk_comm_set_exchange", "gtk_comm_sum_ghost_rows",
+    "gtk_assemble_and_sum_ghost_rows_device",
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
 ]
 
@@ -90,6 +91,7 @@ def load_library() -> C.CDLL:
         "gtk_set_active_cells": (i32, [vp, i64, i64]),
         "gtk_comm_set_exchange": (i32, [vp, i32, i64, vp, i64, vp, i64, vp, i64, vp]),
         "gtk_comm_sum_ghost_rows": (i32, [vp]),
+        "gtk_assemble_and_sum_ghost_rows_device": (i32, [vp, i32, C.POINTER(FormParams), i32, C.POINTER(FormParams)]),
         "gtk_comm_ghost_info": (i64, [vp, i32]),
         "gtk_set_profiling": (i32, [vp, i32]),
         "gtk_profile_count": (i32, [vp]),
@@ -320,3 +322,12 @@ class Engine:
 
     def comm_sum_ghost_rows(self):
         self._ck(self.lib.gtk_comm_sum_ghost_rows(self.h))
+
+    def assemble_and_sum_ghost_rows_device(self, mform: int, mparams: dict, vform: int, vparams: dict):
+        """assemble_matrix_and_vector_device + comm_sum_ghost_rows with the exchange overlapped with the sweep."""
+        if self.n_vec_rows == 0:
+            self.vector_symbolic(FREE)
+        pm, k1 = make_params(**mparams)
+        pv, k2 = make_params(**vparams)
+        self._ck(self.lib.gtk_assemble_and_sum_ghost_rows_device(self.h, mform, C.byref(pm), vform, C.byref(pv)))
+        del k1, k2

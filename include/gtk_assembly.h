@@ -161,6 +161,12 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
                               int64_t n_recv_b, const int32_t* recv_rows);
 /* Exchange + add ghost-row nzval and b contributions after a numeric call. */
 int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx);
+/* gtk_assemble_matrix_and_vector_device + gtk_comm_sum_ghost_rows in one call, with the exchange overlapped with the
+ * assembly: the part of the sweep that produces the values a peer waits for runs first, pack + ncclSend/ncclRecv proceed
+ * on a private side stream while the rest of the sweep runs, the received partial sums are added at the end.  Bitwise the
+ * same result as the two separate calls (which is also what it does when the structured sweep kernels do not apply). */
+int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t matrix_form, const gtk_form_params* pm,
+                                               int32_t vector_form, const gtk_form_params* pv);
 /* key: 0 ghost nz entries sent per exchange  1 ghost nz entries received  2 bytes moved per exchange */
 int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key);
 
