@@ -102,9 +102,10 @@ int32_t gtk_destroy(gtk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   gtk_comm_release(ctx);
-  gtk_fastq1_release(ctx);
-  gtk_matsym_release(ctx);
+  gtk_release_all_matrices(ctx);
   gtk_vecsym_release(ctx);
+  for (auto& sl : ctx->slots) { gtk_cuda_free(ctx, sl.nzval); sl.nzval = nullptr; }
+  gtk_cuda_free(ctx, ctx->xvec);
   for (void* q : {(void*)ctx->xyz, (void*)ctx->cell_nodes, (void*)ctx->cell_dofs, (void*)ctx->w, (void*)ctx->N, (void*)ctx->dN,
                   (void*)ctx->M, (void*)ctx->dM, (void*)ctx->KE, (void*)ctx->BE, (void*)ctx->nzval, (void*)ctx->bvec,
                   (void*)ctx->f_dev, (void*)ctx->Cm})
@@ -136,7 +137,7 @@ int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz
   if (rc) return rc;
   rc = upload(ctx, &ctx->cell_nodes, &sz.cell_nodes, cell_nodes, (size_t)n_cells * n_lnodes);
   if (rc) return rc;
-  gtk_matsym_release(ctx); gtk_vecsym_release(ctx); gtk_fastq1_release(ctx);
+  gtk_release_all_matrices(ctx); gtk_vecsym_release(ctx);
   GTK_CK(cudaStreamSynchronize(ctx->stream));
   return GTK_OK;
 }
@@ -173,7 +174,7 @@ int32_t gtk_set_space(gtk_ctx* ctx, int32_t n_ldofs, int32_t n_comp, const int32
   ctx->n_free = n_free; ctx->n_diri = n_dirichlet;
   int32_t rc = upload(ctx, &ctx->cell_dofs, &sz.cell_dofs, cell_dofs, (size_t)ctx->n_cells * n_ldofs);
   if (rc) return rc;
-  gtk_matsym_release(ctx); gtk_vecsym_release(ctx); gtk_fastq1_release(ctx);
+  gtk_release_all_matrices(ctx); gtk_vecsym_release(ctx);
   GTK_CK(cudaStreamSynchronize(ctx->stream));
   return GTK_OK;
 }

@@ -46,6 +46,18 @@ struct MatSym {
   uint32_t* nzptr = nullptr;   // [nnz+1]  first sorted position of every stored nonzero
   // Q1-hex structured fast path ("tile plan"), see plan.cu
   void* plan = nullptr;
+  // row-major view for b = beta b + alpha A x (matvec.cu), built on first use
+  bool csr_ready = false;
+  int64_t* csr_ptr = nullptr;    // [n_rows+1]
+  uint32_t* csr_pos = nullptr;   // [nnz] position in nzval, rows ascending, columns ascending inside a row
+  int32_t* csr_col = nullptr;    // [nnz] 0-based column of that entry
+};
+
+// one assembled matrix kept next to the current one (gtk_select_matrix): pattern, plans and values
+struct MatSlot {
+  MatSym ms;
+  double* nzval = nullptr;
+  size_t nzval_cap = 0;
 };
 
 struct VecSym {
@@ -83,8 +95,12 @@ struct gtk_ctx {
   double *w = nullptr, *N = nullptr, *dN = nullptr, *M = nullptr, *dM = nullptr;
   std::vector<double> h_w, h_N, h_dN, h_M, h_dM;
 
-  MatSym ms;
+  MatSym ms;            // the SELECTED matrix (gtk_select_matrix); the others wait in `slots`
   VecSym vs;
+  static constexpr int N_SLOTS = 4;
+  MatSlot slots[N_SLOTS];
+  int cur_slot = 0;
+  double* xvec = nullptr; size_t xvec_cap = 0;   // uploaded x of gtk_matvec_add
   // staging / results
   double* KE = nullptr;  size_t KE_cap = 0;   // [n_cells][nld][nld] element matrices, e-indexed
   double* BE = nullptr;  size_t BE_cap = 0;   // [n_cells][nld]
@@ -168,7 +184,9 @@ int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd);
 int32_t gtk_symbolic_vector_impl(gtk_ctx* ctx, int fd);
 int32_t gtk_symbolic_generic_plan(gtk_ctx* ctx);          // matrix: sort-based pattern + reduction plan
 int32_t gtk_symbolic_vector_generic_plan(gtk_ctx* ctx);   // vector: same
-void gtk_matsym_release(gtk_ctx* ctx);
+void gtk_matsym_release(gtk_ctx* ctx);                   // the selected matrix: pattern, plans (values stay allocated)
+void gtk_release_all_matrices(gtk_ctx* ctx);             // every slot (mesh / space changed)
+int32_t gtk_select_matrix_impl(gtk_ctx* ctx, int slot);
 void gtk_vecsym_release(gtk_ctx* ctx);
 
 // ---- numeric.cu ----

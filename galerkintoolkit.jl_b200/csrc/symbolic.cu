@@ -104,8 +104,14 @@ int bits_for(uint64_t maxval) {
 
 }  // namespace
 
+void gtk_fastq1_release(gtk_ctx* ctx);   // fastq1.cu
+
 void gtk_matsym_release(gtk_ctx* ctx) {
   MatSym& m = ctx->ms;
+  gtk_fastq1_release(ctx);
+  gtk_free(ctx, m.csr_ptr, (size_t)m.n_rows + 1);
+  gtk_free(ctx, m.csr_pos, (size_t)m.nnz);
+  gtk_free(ctx, m.csr_col, (size_t)m.nnz);
   gtk_free(ctx, m.colptr, (size_t)m.n_cols + 1);
   gtk_free(ctx, m.rowval, (size_t)m.nnz);
   gtk_free(ctx, m.perm, (size_t)m.n_valid);

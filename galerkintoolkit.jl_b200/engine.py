@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "gtk_assemble_matrix_and_vector", "gtk_assemble_matrix_and_vector_device",
     "gtk_device_pointer", "gtk_copy_nzval", "gtk_copy_vector", "gtk_info",
     "gtk_comm_unique_id", "gtk_comm_init", "gtk_comm_set_exchange", "gtk_comm_sum_ghost_rows",
-    "gtk_assemble_and_sum_ghost_rows_device",
+    "gtk_assemble_and_sum_ghost_rows_device", "gtk_select_matrix", "gtk_matvec_add_device", "gtk_matvec_add",
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
 ]
 
@@ -91,6 +91,9 @@ def load_library() -> C.CDLL:
         "gtk_set_active_cells": (i32, [vp, i64, i64]),
         "gtk_comm_set_exchange": (i32, [vp, i32, i64, vp, i64, vp, i64, vp, i64, vp]),
         "gtk_comm_sum_ghost_rows": (i32, [vp]),
+        "gtk_select_matrix": (i32, [vp, i32]),
+        "gtk_matvec_add_device": (i32, [vp, C.c_double, C.c_void_p, C.c_double]),
+        "gtk_matvec_add": (i32, [vp, C.c_double, C.c_void_p, C.c_double, C.c_void_p]),
         "gtk_assemble_and_sum_ghost_rows_device": (i32, [vp, i32, C.POINTER(FormParams), i32, C.POINTER(FormParams)]),
         "gtk_comm_ghost_info": (i64, [vp, i32]),
         "gtk_set_profiling": (i32, [vp, i32]),
@@ -199,6 +202,30 @@ class Engine:
         self._ck(self.lib.gtk_set_tabulation(self.h, w.shape[0], _ptr(w), _ptr(N), _ptr(dN), _ptr(M), _ptr(dM)))
 
     # -- matrix ---------------------------------------------------------------------
+    def select_matrix(self, slot: int):
+        """Make matrix `slot` (0..3) the target of the matrix_* calls; every slot keeps pattern, plans and values."""
+        self._ck(self.lib.gtk_select_matrix(self.h, int(slot)))
+        if not hasattr(self, "_slot_dims"):
+            self._slot_dims, self._slot = {}, 0
+        self._slot_dims[self._slot] = (self.nnz, self.n_rows, self.n_cols)
+        self._slot = int(slot)
+        self.nnz, self.n_rows, self.n_cols = self._slot_dims.get(self._slot, (0, 0, 0))
+
+    def matvec_add(self, alpha: float, x: np.ndarray, beta: float, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """b = beta*b + alpha*M*x on device (Julia's 5-argument mul! for SparseMatrixCSC, bitwise); returns b."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.size != self.n_cols:
+            raise ValueError(f"x has {x.size} entries, the selected matrix has {self.n_cols} columns")
+        b = np.empty(self.n_vec_rows, dtype=np.float64) if out is None else out
+        self._ck(self.lib.gtk_matvec_add(self.h, float(alpha), _ptr(x), float(beta), _ptr(b)))
+        return b
+
+    def matvec_add_device(self, alpha: float, x: np.ndarray, beta: float):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.size != self.n_cols:
+            raise ValueError(f"x has {x.size} entries, the selected matrix has {self.n_cols} columns")
+        self._ck(self.lib.gtk_matvec_add_device(self.h, float(alpha), _ptr(x), float(beta)))
+
     def matrix_symbolic(self, rows=FREE, cols=FREE) -> int:
         nnz = C.c_int64(0)
         self._ck(self.lib.gtk_matrix_symbolic(self.h, rows, cols, C.byref(nnz)))

@@ -424,3 +424,53 @@ def assemble_matrix_and_vector(a: Callable, l: Callable, T, U: Space, V: Space, 
         return A, b, AssemblyCache(eng, mform, dict(m=mparams, v=vparams, vform=vform), "both")
     eng.close()
     return A, b
+
+
+# ---------------------------------------------------------------------------
+# free + Dirichlet columns and the linear-problem right-hand side (problems.jl:363-387, 413-453)
+# ---------------------------------------------------------------------------
+def assemble_matrix_and_vector_with_free_and_dirichlet_columns(a: Callable, l: Callable, T, U: Space, V: Space, *,
+                                                               reuse: bool = False, engine: Optional[_eng.Engine] = None):
+    """GT.assemble_matrix_and_vector_with_free_and_dirichlet_columns(a, l, T, U, V) (problems.jl:413-430):
+    A = free x free, Ad = free x Dirichlet, b.  The reference runs the cell loop twice for the matrices ("this can be
+    optimized", problems.jl:369); here both live in one engine context (matrix slots 0 and 1) next to b."""
+    if U is not V:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
+    u, v = FormArgument(U, 2), FormArgument(V, 1)
+    term_a, meas_a, sa = _single_contribution(a(u, v))
+    term_l, meas_l, sl = _single_contribution(l(v))
+    if meas_a.degree != meas_l.degree:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "matrix and vector must share one measure in the fused call")
+    mform, mparams = recognise_bilinear(term_a)
+    vform, vparams = recognise_linear(term_l, V, meas_l)
+    mparams["alpha"] = mparams.get("alpha", 1.0) * sa
+    vparams["alpha"] = vparams.get("alpha", 1.0) * sl
+    eng = _setup_engine(V, meas_a, engine)
+    eng.select_matrix(0)
+    eng.matrix_symbolic(FREE, FREE)
+    colptr, rowval = eng.matrix_pattern()
+    nzval, b = eng.assemble_matrix_and_vector(mform, mparams, vform, vparams)
+    A = SparseMatrixCSC(eng.n_rows, eng.n_cols, colptr, rowval, nzval)
+    eng.select_matrix(1)
+    eng.matrix_symbolic(FREE, DIRICHLET)
+    cpd, rvd = eng.matrix_pattern()
+    Ad = SparseMatrixCSC(eng.n_rows, eng.n_cols, cpd, rvd, eng.matrix_numeric(mform, **mparams))
+    eng.select_matrix(0)
+    if reuse:
+        return A, Ad, b, AssemblyCache(eng, mform, dict(m=mparams, v=vparams, vform=vform), "both+dirichlet")
+    eng.close()
+    return A, Ad, b
+
+
+def linear_problem(dirichlet_values: np.ndarray, a: Callable, l: Callable, U: Space, V: Optional[Space] = None):
+    """PartitionedSolvers_linear_problem(uhd, a, l) (problems.jl:439-453): returns (x0, A, b) with
+    b = l - Ad*xd computed on the device exactly like `mul!(b, Ad, xd, -1, 1)`, x0 = zeros."""
+    V = U if V is None else V
+    xd = np.ascontiguousarray(dirichlet_values, dtype=np.float64)
+    A, Ad, b, cache = assemble_matrix_and_vector_with_free_and_dirichlet_columns(a, l, np.float64, U, V, reuse=True)
+    eng = cache.engine
+    eng.select_matrix(1)
+    b = eng.matvec_add(-1.0, xd, 1.0)
+    eng.select_matrix(0)
+    eng.close()
+    return np.zeros(A.n, dtype=np.float64), A, b

@@ -127,6 +127,19 @@ int32_t gtk_assemble_matrix_and_vector(gtk_ctx* ctx, int32_t matrix_form, const 
 int32_t gtk_assemble_matrix_and_vector_device(gtk_ctx* ctx, int32_t matrix_form, const gtk_form_params* pm,
                                               int32_t vector_form, const gtk_form_params* pv);
 
+/* ---- several matrices side by side + linear-problem right-hand side (problems.jl:363-387, 439-453) ------------ */
+/* The reference keeps A (free x free) and Ad (free x Dirichlet) as two matrices with their own caches
+ * (assemble_matrix_with_free_and_dirichlet_columns, problems.jl:363-380).  A ctx holds up to 4 matrices; `slot`
+ * (0..3, default 0) selects the one gtk_matrix_symbolic / _pattern / _numeric / gtk_copy_nzval / gtk_device_pointer
+ * work on.  Each keeps its pattern, plans and values, so update_matrix! on either stays a numeric-only call. */
+int32_t gtk_select_matrix(gtk_ctx* ctx, int32_t slot);
+/* b = beta*b + alpha*M*x with M the selected matrix, b the ctx's assembled vector (same row selection), x a host
+ * vector of length n_cols: Julia's mul!(b, M, x, alpha, beta) for SparseMatrixCSC, same summation order per row
+ * (increasing column) and same roundings (separate multiply and add), so `mul!(b, Ad, xd, -1, 1)` of
+ * PartitionedSolvers_linear_problem (problems.jl:447) is reproduced bitwise given the same Ad, xd, b. */
+int32_t gtk_matvec_add_device(gtk_ctx* ctx, double alpha, const double* x, double beta);
+int32_t gtk_matvec_add(gtk_ctx* ctx, double alpha, const double* x, double beta, double* b);
+
 /* ---- device-resident results -------------------------------------------------- */
 /* which: 0 nzval (double[nnz]) 1 b (double[n_rows]) 2 colptr (int64[n_cols+1], 0-based)
  *        3 rowval (int32[nnz], 1-based) */

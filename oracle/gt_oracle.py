@@ -483,3 +483,40 @@ def assemble_vector(form, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, ta
     be = element_vectors(form, coords, cell_nodes, tab, n_comp=n_comp, **params)
     I, V = coo_vector(be, cell_dofs, free_or_dirichlet)
     return dense_vector(I, V, n_free if free_or_dirichlet == FREE else n_dirichlet)
+
+
+# ---------------------------------------------------------------------------
+# linear-problem right-hand side: mul!(b, Ad, xd, -1, 1)  (problems.jl:447)
+# ---------------------------------------------------------------------------
+def spmatmul_add(colptr, rowval, nzval, x, alpha, beta, b):
+    """Julia's 5-argument mul!(C, A::SparseMatrixCSC, B, alpha, beta) for a vector B, as SparseArrays implements it
+    (stdlib `_spmatmul!`, not vendored in /root/reference; semantics restated): C is scaled by beta first (left
+    alone for beta == 1, zero-filled for beta == 0), then for each column k in increasing order axk = B[k]*alpha and
+    every stored entry j of the column does C[rowval[j]] += nzval[j]*axk — multiply and add rounded separately.
+    1-based colptr/rowval as in the reference.  Returns the updated copy of b."""
+    c = np.array(b, dtype=np.float64, copy=True)
+    if beta != 1:
+        c = c * beta if beta != 0 else np.zeros_like(c)
+    cp = np.asarray(colptr, dtype=np.int64) - 1
+    rv = np.asarray(rowval, dtype=np.int64) - 1
+    nz = np.asarray(nzval, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    for k in range(cp.size - 1):
+        lo, hi = cp[k], cp[k + 1]
+        if hi > lo:
+            axk = x[k] * alpha
+            c[rv[lo:hi]] = c[rv[lo:hi]] + nz[lo:hi] * axk     # rows inside one column are distinct
+    return c
+
+
+def linear_problem_rhs(form_a, form_l, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, tab, xd, n_comp=1,
+                       params_a=None, params_l=None):
+    """A, Ad, b of assemble_matrix_and_vector_with_free_and_dirichlet_columns (problems.jl:413-430) followed by
+    b <- b - Ad*xd (problems.jl:447)."""
+    params_a, params_l = params_a or {}, params_l or {}
+    A = assemble_matrix(form_a, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, tab, n_comp=n_comp,
+                        free_or_dirichlet=(FREE, FREE), **params_a)
+    Ad = assemble_matrix(form_a, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, tab, n_comp=n_comp,
+                         free_or_dirichlet=(FREE, DIRICHLET), **params_a)
+    b = assemble_vector(form_l, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, tab, n_comp=n_comp, **params_l)
+    return A, Ad, spmatmul_add(Ad[0], Ad[1], Ad[2], xd, -1.0, 1.0, b)
