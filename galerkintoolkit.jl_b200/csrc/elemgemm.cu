@@ -279,7 +279,7 @@ int32_t launch_gemm(gtk_ctx* ctx, const GemmArgs& a) {
 int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool* handled) {
   *handled = false;
   if (getenv("GTK_DISABLE_DMMA")) return GTK_OK;
-  if (form != GTK_FORM_LAPLACE || ctx->D != 3 || ctx->ncomp != 1) return GTK_OK;
+  if (form != GTK_FORM_LAPLACE || ctx->D != 3 || ctx->dman != 3 || ctx->ncomp != 1) return GTK_OK;
   const int nld = ctx->nld, nq = ctx->nq;
   int mt, ng;
   if (nld <= 8 && nq <= 8) { mt = 1; ng = 2; }

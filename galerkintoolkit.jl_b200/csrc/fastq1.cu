@@ -851,7 +851,7 @@ bool tabulation_is_q1_gauss2(const gtk_ctx* ctx) {
 // generic path is used.
 int32_t plan_detect(gtk_ctx* ctx, FastPlan* p) {
   p->tried = true;
-  if (ctx->D != 3 || ctx->nln != 8 || ctx->nld != 8 || ctx->ncomp != 1 || ctx->n_cells < 1 || ctx->n_free < 1) return GTK_OK;
+  if (ctx->D != 3 || ctx->dman != 3 || ctx->nln != 8 || ctx->nld != 8 || ctx->ncomp != 1 || ctx->n_cells < 1 || ctx->n_free < 1) return GTK_OK;
   cudaStream_t st = ctx->stream;
   int32_t first[8];
   GTK_CK(cudaMemcpyAsync(first, ctx->cell_nodes, sizeof(first), cudaMemcpyDeviceToHost, st));
@@ -1140,7 +1140,7 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   *handled = false;
   if (getenv("GTK_DISABLE_FASTPATH")) return GTK_OK;
   if (mform && mform != GTK_FORM_LAPLACE) return GTK_OK;
-  if (vform && vform != GTK_FORM_SOURCE_CONST) return GTK_OK;
+  if (vform && (vform != GTK_FORM_SOURCE_CONST || (pv && pv->accumulate))) return GTK_OK;
   if (vform && (!ctx->vs.ready || ctx->vs.fd != GTK_FREE)) return GTK_OK;
   if (!ctx->ms.ready) return GTK_OK;   // the plan needs the pattern (also for vector-only calls)
   FastPlan* p = (FastPlan*)ctx->ms.plan;

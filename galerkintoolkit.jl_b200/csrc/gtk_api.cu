@@ -79,7 +79,7 @@ int32_t upload(gtk_ctx* ctx, T** dst, size_t* old_n, const T* src, size_t n) {
 
 extern "C" {
 
-int32_t gtk_version(void) { return 100; }
+int32_t gtk_version(void) { return 101; }
 
 int32_t gtk_create(int32_t device, gtk_ctx** out) {
   if (!out) return GTK_ERR_INVALID;
@@ -131,13 +131,39 @@ int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz
     GTK_FAIL(GTK_ERR_INVALID, "gtk_set_mesh: bad arguments");
   GTK_CK(cudaSetDevice(ctx->device));
   auto& sz = ctx->sz;
-  ctx->D = D; ctx->n_nodes = n_nodes; ctx->n_cells = n_cells; ctx->nln = n_lnodes;
+  ctx->D = D; ctx->dman = D; ctx->n_nodes = n_nodes; ctx->n_cells = n_cells; ctx->nln = n_lnodes;
   ctx->act_first = 0; ctx->act_count = -1;
   int32_t rc = upload(ctx, &ctx->xyz, &sz.xyz, xyz, (size_t)n_nodes * D);
   if (rc) return rc;
   rc = upload(ctx, &ctx->cell_nodes, &sz.cell_nodes, cell_nodes, (size_t)n_cells * n_lnodes);
   if (rc) return rc;
   gtk_release_all_matrices(ctx); gtk_vecsym_release(ctx);
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
+int32_t gtk_set_manifold_dim(gtk_ctx* ctx, int32_t d) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (!ctx->D) GTK_FAIL(GTK_ERR_STATE, "gtk_set_manifold_dim: set the mesh first");
+  if (d < 1 || d > ctx->D) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_manifold_dim: 1 <= d <= D");
+  ctx->dman = d;
+  return GTK_OK;
+}
+
+int32_t gtk_set_vector(gtk_ctx* ctx, const double* b) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (!ctx->vs.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_set_vector: call gtk_vector_symbolic first");
+  if (!b && ctx->vs.n_rows) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_vector: b is null");
+  GTK_CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)(ctx->vs.n_rows > 0 ? ctx->vs.n_rows : 1);
+  if (ctx->bvec_cap < n || !ctx->bvec) {
+    if (ctx->bvec) gtk_dev_free(ctx, ctx->bvec, ctx->bvec_cap * sizeof(double));
+    ctx->bvec = nullptr; ctx->bvec_cap = 0;
+    int32_t rc = gtk_dev_alloc(ctx, (void**)&ctx->bvec, n * sizeof(double));
+    if (rc) return rc;
+    ctx->bvec_cap = n;
+  }
+  if (ctx->vs.n_rows) GTK_CK(cudaMemcpyAsync(ctx->bvec, b, sizeof(double) * (size_t)ctx->vs.n_rows, cudaMemcpyHostToDevice, ctx->stream));
   GTK_CK(cudaStreamSynchronize(ctx->stream));
   return GTK_OK;
 }
@@ -187,7 +213,7 @@ int32_t gtk_set_tabulation(gtk_ctx* ctx, int32_t n_q, const double* w, const dou
   GTK_CK(cudaSetDevice(ctx->device));
   auto& sz = ctx->sz;
   ctx->nq = n_q;
-  const int D = ctx->D;
+  const int D = ctx->dman;   // reference-space dimension of the tabulated gradients
   size_t nN = (size_t)n_q * ctx->nls, nM = (size_t)n_q * ctx->nln;
   ctx->h_w.assign(w, w + n_q);
   ctx->h_N.assign(N, N + nN);

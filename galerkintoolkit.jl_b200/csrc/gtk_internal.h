@@ -82,6 +82,7 @@ struct gtk_ctx {
 
   // mesh
   int D = 0, nln = 0;
+  int dman = 0;          // dimension of the cells' reference space (= D for volume cells, D-1 for boundary faces)
   int64_t n_nodes = 0, n_cells = 0;
   double* xyz = nullptr;
   int32_t* cell_nodes = nullptr;

@@ -46,20 +46,20 @@ __device__ __forceinline__ double det_mat(const double (&a)[D][D]) {
   }
 }
 
-// sqrt(det(JᵀJ))  (quadrature.jl:4-6)
-template <int D>
-__device__ __forceinline__ double change_of_measure(const double (&J)[D][D]) {
-  double G[D][D];
+// sqrt(det(JᵀJ))  (quadrature.jl:4-6); J is D x d (d < D: boundary faces embedded in D dimensions)
+template <int D, int d>
+__device__ __forceinline__ double change_of_measure(const double (&J)[D][d]) {
+  double G[d][d];
 #pragma unroll
-  for (int i = 0; i < D; ++i)
+  for (int i = 0; i < d; ++i)
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
+    for (int j = 0; j < d; ++j) {
       double s = J[0][i] * J[0][j];
 #pragma unroll
       for (int k = 1; k < D; ++k) s += J[k][i] * J[k][j];
       G[i][j] = s;
     }
-  return sqrt(det_mat<D>(G));
+  return sqrt(det_mat<d>(G));
 }
 
 // g = a \ b with a = Jᵀ  (StaticArrays closed forms; accessors.jl:1365-1368)
@@ -83,24 +83,24 @@ __device__ __forceinline__ void solve_JT(const double (&J)[D][D], double d, cons
   }
 }
 
-template <int D>
-__device__ __forceinline__ void jacobian_at(const ElemArgs& a, int64_t cell, int q, double (&J)[D][D]) {
+template <int D, int d>
+__device__ __forceinline__ void jacobian_at(const ElemArgs& a, int64_t cell, int q, double (&J)[D][d]) {
 #pragma unroll
   for (int i = 0; i < D; ++i)
 #pragma unroll
-    for (int j = 0; j < D; ++j) J[i][j] = 0.0;
+    for (int j = 0; j < d; ++j) J[i][j] = 0.0;
   const int32_t* nodes = a.cell_nodes + cell * a.nln;
-  const double* dMq = a.dM + (size_t)q * a.nln * D;
+  const double* dMq = a.dM + (size_t)q * a.nln * d;
   for (int n = 0; n < a.nln; ++n) {   // sequential in local-node order (accessors.jl:941-948)
     const double* x = a.xyz + (size_t)(nodes[n] - 1) * D;
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
-      for (int j = 0; j < D; ++j) J[i][j] += x[i] * dMq[n * D + j];
+      for (int j = 0; j < d; ++j) J[i][j] += x[i] * dMq[n * d + j];
   }
 }
 
-template <int D>
+template <int D, int d>
 __global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
   extern __shared__ double smem[];
   const int nq = a.nq, nls = a.nls, nld = a.nld, ncomp = a.ncomp;
@@ -111,10 +111,10 @@ __global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
   const bool need_grad = a.form != GTK_FORM_MASS;
   for (int t = threadIdx.x; t < ncb * nq; t += blockDim.x) {
     int cl = t / nq, q = t - cl * nq;
-    double J[D][D];
-    jacobian_at<D>(a, cell0 + cl, q, J);
-    dV[t] = change_of_measure<D>(J) * a.w[q];
-    if (need_grad) {
+    double J[D][d];
+    jacobian_at<D, d>(a, cell0 + cl, q, J);
+    dV[t] = change_of_measure<D, d>(J) * a.w[q];
+    if constexpr (D == d) if (need_grad) {
       double JT[D][D];
 #pragma unroll
       for (int i = 0; i < D; ++i)
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
   }
 }
 
-template <int D>
+template <int D, int d>
 __global__ void __launch_bounds__(128) k_elem_vector(ElemArgs a) {
   extern __shared__ double smem[];
   const int nq = a.nq, nls = a.nls, nld = a.nld, ncomp = a.ncomp;
@@ -175,9 +175,9 @@ __global__ void __launch_bounds__(128) k_elem_vector(ElemArgs a) {
   for (int t = threadIdx.x; t < ncb * nq; t += blockDim.x) {
     int cl = t / nq, q = t - cl * nq;
     int64_t cell = cell0 + cl;
-    double J[D][D];
-    jacobian_at<D>(a, cell, q, J);
-    dV[t] = change_of_measure<D>(J) * a.w[q];
+    double J[D][d];
+    jacobian_at<D, d>(a, cell, q, J);
+    dV[t] = change_of_measure<D, d>(J) * a.w[q];
     for (int k = 0; k < ncomp; ++k) {
       double f;
       if (a.form == GTK_FORM_SOURCE_CONST) f = a.f_const[k];
@@ -216,11 +216,13 @@ __global__ void k_reduce_nz(const double* __restrict__ KE, const uint32_t* __res
 
 __global__ void k_reduce_rows(const double* __restrict__ BE, const uint32_t* __restrict__ perm,
                               const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ urow,
-                              int64_t n_urows, double* __restrict__ b) {
+                              int64_t n_urows, double* __restrict__ b, int accumulate) {
   for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < n_urows;
        u += (int64_t)gridDim.x * blockDim.x) {
     uint32_t s0 = rowptr[u], s1 = rowptr[u + 1];
-    double acc = 0.0 + BE[perm[s0]];   // dense_vector starts from zeros (assembly.jl:562)
+    // dense_vector starts from zeros (assembly.jl:562); with `accumulate` the COO entries of this integral follow the
+    // ones already summed into b (one COO vector for all contributions of a sum of integrals, problems.jl:258-266)
+    double acc = (accumulate ? b[urow[u]] : 0.0) + BE[perm[s0]];
     for (uint32_t s = s0 + 1; s < s1; ++s) acc += BE[perm[s]];
     b[urow[u]] = acc;
   }
@@ -312,13 +314,17 @@ int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params
   if (rc) return rc;
   int grid = (int)((ctx->n_cells + a.cb - 1) / a.cb);
   cudaStream_t st = ctx->stream;
-#define LAUNCH_M(DD)                                                                                        \
-  do {                                                                                                      \
-    GTK_CK(cudaFuncSetAttribute(k_elem_matrix<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    { GtkProf pr_(ctx, "k_elem_matrix"); k_elem_matrix<DD><<<grid, 128, smem, st>>>(a); }                                                          \
+#define LAUNCH_M(DD, dd)                                                                                        \
+  do {                                                                                                          \
+    GTK_CK(cudaFuncSetAttribute(k_elem_matrix<DD, dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    { GtkProf pr_(ctx, "k_elem_matrix"); k_elem_matrix<DD, dd><<<grid, 128, smem, st>>>(a); }                    \
   } while (0)
-  if (D == 1) LAUNCH_M(1); else if (D == 2) LAUNCH_M(2); else if (D == 3) LAUNCH_M(3);
-  else GTK_FAIL(GTK_ERR_INVALID, "D must be 1, 2 or 3");
+  const int dm = ctx->dman;
+  if (dm != D && form != GTK_FORM_MASS)
+    GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "only MASS is supported on cells of lower dimension than the space (boundary faces); no CPU fallback");
+  if (D == 1 && dm == 1) LAUNCH_M(1, 1); else if (D == 2 && dm == 2) LAUNCH_M(2, 2); else if (D == 3 && dm == 3) LAUNCH_M(3, 3);
+  else if (D == 2 && dm == 1) LAUNCH_M(2, 1); else if (D == 3 && dm == 2) LAUNCH_M(3, 2); else if (D == 3 && dm == 1) LAUNCH_M(3, 1);
+  else GTK_FAIL(GTK_ERR_INVALID, "D must be 1, 2 or 3 and 1 <= manifold dimension <= D");
 #undef LAUNCH_M
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
@@ -359,7 +365,8 @@ int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params
   rc = ensure(ctx, &ctx->bvec, &ctx->bvec_cap, (size_t)v.n_rows);
   if (rc) return rc;
   cudaStream_t st = ctx->stream;
-  GTK_CK(cudaMemsetAsync(ctx->bvec, 0, sizeof(double) * (size_t)(v.n_rows > 0 ? v.n_rows : 1), st));
+  const int accumulate = p && p->accumulate ? 1 : 0;
+  if (!accumulate) GTK_CK(cudaMemsetAsync(ctx->bvec, 0, sizeof(double) * (size_t)(v.n_rows > 0 ? v.n_rows : 1), st));
   if (ctx->n_cells == 0 || v.n_urows == 0) return GTK_OK;
   a.out = ctx->BE;
   const int D = ctx->D;
@@ -368,18 +375,20 @@ int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params
   rc = pick_cb(ctx, per_cell, &a.cb, &smem);
   if (rc) return rc;
   int grid = (int)((ctx->n_cells + a.cb - 1) / a.cb);
-#define LAUNCH_V(DD)                                                                                        \
-  do {                                                                                                      \
-    GTK_CK(cudaFuncSetAttribute(k_elem_vector<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    { GtkProf pr_(ctx, "k_elem_vector"); k_elem_vector<DD><<<grid, 128, smem, st>>>(a); }                                                          \
+#define LAUNCH_V(DD, dd)                                                                                        \
+  do {                                                                                                          \
+    GTK_CK(cudaFuncSetAttribute(k_elem_vector<DD, dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    { GtkProf pr_(ctx, "k_elem_vector"); k_elem_vector<DD, dd><<<grid, 128, smem, st>>>(a); }                    \
   } while (0)
-  if (D == 1) LAUNCH_V(1); else if (D == 2) LAUNCH_V(2); else if (D == 3) LAUNCH_V(3);
-  else GTK_FAIL(GTK_ERR_INVALID, "D must be 1, 2 or 3");
+  const int dm = ctx->dman;
+  if (D == 1 && dm == 1) LAUNCH_V(1, 1); else if (D == 2 && dm == 2) LAUNCH_V(2, 2); else if (D == 3 && dm == 3) LAUNCH_V(3, 3);
+  else if (D == 2 && dm == 1) LAUNCH_V(2, 1); else if (D == 3 && dm == 2) LAUNCH_V(3, 2); else if (D == 3 && dm == 1) LAUNCH_V(3, 1);
+  else GTK_FAIL(GTK_ERR_INVALID, "D must be 1, 2 or 3 and 1 <= manifold dimension <= D");
 #undef LAUNCH_V
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   { GtkProf pr_(ctx, "k_reduce_rows"); k_reduce_rows<<<grid_for(v.n_urows, 256, ctx->sm_count), 256, 0, st>>>(ctx->BE, v.perm, v.rowptr, v.urow,
-                                                                         v.n_urows, ctx->bvec); }
+                                                                         v.n_urows, ctx->bvec, accumulate); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   return GTK_OK;

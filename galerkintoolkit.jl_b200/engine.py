@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "gtk_assemble_matrix_and_vector", "gtk_assemble_matrix_and_vector_device",
     "gtk_device_pointer", "gtk_copy_nzval", "gtk_copy_vector", "gtk_info",
     "gtk_comm_unique_id", "gtk_comm_init", "gtk_comm_set_exchange", "gtk_comm_sum_ghost_rows",
-    "gtk_assemble_and_sum_ghost_rows_device", "gtk_select_matrix", "gtk_matvec_add_device", "gtk_matvec_add",
+    "gtk_assemble_and_sum_ghost_rows_device", "gtk_select_matrix", "gtk_matvec_add_device", "gtk_matvec_add", "gtk_set_manifold_dim", "gtk_set_vector",
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
 ]
 
@@ -47,7 +47,7 @@ class UnsupportedFormError(GtkError):
 
 class FormParams(C.Structure):
     _fields_ = [("alpha", C.c_double), ("lam", C.c_double), ("mu", C.c_double),
-                ("f_const", C.c_double * 3), ("f_nodal", C.c_void_p), ("f_qp", C.c_void_p)]
+                ("f_const", C.c_double * 3), ("f_nodal", C.c_void_p), ("f_qp", C.c_void_p), ("accumulate", C.c_int32)]
 
 
 _lib = None
@@ -92,6 +92,8 @@ def load_library() -> C.CDLL:
         "gtk_comm_set_exchange": (i32, [vp, i32, i64, vp, i64, vp, i64, vp, i64, vp]),
         "gtk_comm_sum_ghost_rows": (i32, [vp]),
         "gtk_select_matrix": (i32, [vp, i32]),
+        "gtk_set_manifold_dim": (i32, [vp, i32]),
+        "gtk_set_vector": (i32, [vp, C.c_void_p]),
         "gtk_matvec_add_device": (i32, [vp, C.c_double, C.c_void_p, C.c_double]),
         "gtk_matvec_add": (i32, [vp, C.c_double, C.c_void_p, C.c_double, C.c_void_p]),
         "gtk_assemble_and_sum_ghost_rows_device": (i32, [vp, i32, C.POINTER(FormParams), i32, C.POINTER(FormParams)]),
@@ -120,10 +122,11 @@ def _i32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
-def make_params(alpha=1.0, lam=0.0, mu=0.0, f_const=None, f_nodal=None, f_qp=None):
+def make_params(alpha=1.0, lam=0.0, mu=0.0, f_const=None, f_nodal=None, f_qp=None, accumulate=False):
     """Returns (FormParams, keepalive) — keepalive holds the numpy buffers the struct points to."""
     p = FormParams()
     p.alpha, p.lam, p.mu = float(alpha), float(lam), float(mu)
+    p.accumulate = 1 if accumulate else 0
     fc = np.zeros(3)
     if f_const is not None:
         v = np.atleast_1d(np.asarray(f_const, dtype=np.float64)).reshape(-1)
@@ -184,6 +187,17 @@ class Engine:
         self._D = xyz.shape[1]
         self._n_cells = cn.shape[0]
         self._ck(self.lib.gtk_set_mesh(self.h, xyz.shape[1], xyz.shape[0], _ptr(xyz), cn.shape[0], cn.shape[1], _ptr(cn)))
+
+    def set_manifold_dim(self, d: int):
+        """Cells of reference dimension d < D (boundary faces as a mesh of their own); call between set_mesh and set_tabulation."""
+        self._ck(self.lib.gtk_set_manifold_dim(self.h, int(d)))
+
+    def set_vector(self, b: np.ndarray):
+        """Upload the vector an `accumulate=True` linear-form assembly adds to."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        if b.size != self.n_vec_rows:
+            raise ValueError(f"b has {b.size} entries, the vector selection has {self.n_vec_rows} rows")
+        self._ck(self.lib.gtk_set_vector(self.h, _ptr(b)))
 
     def set_active_cells(self, first: int, count: int):
         self._ck(self.lib.gtk_set_active_cells(self.h, int(first), int(count)))

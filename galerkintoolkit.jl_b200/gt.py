@@ -74,8 +74,7 @@ class Measure:
 
 
 def measure(domain: Domain, degree: int) -> Measure:
-    if domain.kind != "interior":
-        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "boundary/skeleton measures are not dispatched to the GPU engine yet")
+    """GT.measure(Ω | Γ, degree) (problems.jl:12-25).  Boundary measures serve linear forms ∫_Γ g v dΓ (Neumann terms)."""
     return Measure(domain, degree)
 
 
@@ -107,6 +106,13 @@ class Space:
         if degree not in self._tab:
             self._tab[degree] = _hp.measure_tabulation(self.data, degree)
         return self._tab[degree]
+
+    def face_problem(self, meas: "Measure"):
+        """faces of the boundary domain of `meas` + this space's dofs on them + tabulation on the reference face"""
+        key = ("Γ", None if meas.domain.sides is None else tuple(meas.domain.sides), meas.degree)
+        if key not in self._tab:
+            self._tab[key] = _hp.face_problem(self.data, meas.domain.sides, meas.degree)
+        return self._tab[key]
 
 
 def lagrange_space(domain, order, dirichlet_boundary=None, tensor_size=None) -> Space:
@@ -283,9 +289,14 @@ def recognise_linear(term, space: Space, meas: Measure):
 
 
 def quadrature_point_coordinates(space: Space, meas: Measure) -> np.ndarray:
-    """x_q = Σ_i x_i M_i(ξ_q) (accessors.jl:983-988), all cells at once (host input preparation for f(x_q))."""
-    tab = space.tabulation(meas.degree)
+    """x_q = Σ_i x_i M_i(ξ_q) (accessors.jl:983-988), all cells (or boundary faces) at once (host input preparation
+    for f(x_q))."""
     mesh = space.domain.mesh
+    if meas.domain.kind == "boundary":
+        fp = space.face_problem(meas)
+        X = mesh.node_coordinates[fp.face_nodes.astype(np.int64) - 1]     # [nf, nfn, D]
+        return np.einsum("qn,cnd->cqd", fp.tab.M, X)
+    tab = space.tabulation(meas.degree)
     X = mesh.node_coordinates[mesh.cell_nodes.astype(np.int64) - 1]       # [nc, nln, D]
     return np.einsum("qn,cnd->cqd", tab.M, X)
 
@@ -334,6 +345,14 @@ def set_device(device: int):
 def _setup_engine(space: Space, meas: Measure, engine: Optional[_eng.Engine] = None) -> _eng.Engine:
     eng = engine or _eng.Engine(_default_device)
     mesh = space.domain.mesh
+    if meas.domain.kind == "boundary":
+        # the faces of Γ as a mesh of (D-1)-cells embedded in D dimensions (gtk_set_manifold_dim)
+        fp = space.face_problem(meas)
+        eng.set_mesh(mesh.node_coordinates, fp.face_nodes)
+        eng.set_manifold_dim(mesh.D - 1)
+        eng.set_space(fp.face_dofs, space.data.n_free, space.data.n_dirichlet, space.data.n_comp)
+        eng.set_tabulation(fp.tab.w, fp.tab.N, fp.tab.dN, fp.tab.M, fp.tab.dM)
+        return eng
     tab = space.tabulation(meas.degree)
     eng.set_mesh(mesh.node_coordinates, mesh.cell_nodes)
     eng.set_space(space.data.cell_dofs, space.data.n_free, space.data.n_dirichlet, space.data.n_comp)
@@ -358,6 +377,8 @@ def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False,
     u, v = FormArgument(U, 2), FormArgument(V, 1)
     term, meas, scale = _single_contribution(a(u, v))
     form, params = recognise_bilinear(term)
+    if meas.domain.kind == "boundary" and form != _eng.FORM_MASS:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "on a boundary measure only ∫_Γ u v dΓ (Robin term) is assembled by the GPU engine")
     params["alpha"] = params.get("alpha", 1.0) * scale
     eng = _setup_engine(V, meas, engine)
     eng.matrix_symbolic(*free_or_dirichlet)
@@ -383,7 +404,25 @@ def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, free_or_di
     if T not in (float, np.float64):
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "the engine assembles Float64 only")
     v = FormArgument(V, 1)
-    term, meas, scale = _single_contribution(l(v))
+    contributions = l(v).contributions
+    if len(contributions) > 1:
+        # ∫_Ω f v dΩ + ∫_Γ g v dΓ + …: the reference pushes every integral into ONE COO vector, contribution after
+        # contribution (problems.jl:258-266); each integral is one engine pass that continues the sums of the previous
+        if reuse or engine is not None:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "reuse is available for single-integral linear forms")
+        b = None
+        for term, meas, scale in contributions:
+            form, params = recognise_linear(term, V, meas)
+            params["alpha"] = params.get("alpha", 1.0) * scale
+            eng = _setup_engine(V, meas)
+            eng.vector_symbolic(free_or_dirichlet)
+            if b is not None:
+                eng.set_vector(b)
+                params["accumulate"] = True
+            b = eng.vector_assemble(form, **params)
+            eng.close()
+        return b
+    term, meas, scale = contributions[0]
     form, params = recognise_linear(term, V, meas)
     params["alpha"] = params.get("alpha", 1.0) * scale
     eng = _setup_engine(V, meas, engine)

@@ -147,6 +147,74 @@ def boundary_node_mask(mesh: Mesh, sides: Optional[Sequence[int]] = None) -> np.
     return mask
 
 
+# local nodes of the (D-1)-faces of the reference square / cube (domain.jl:206-224, 238-255)
+CUBE_FACE_LNODES = {2: [[1, 2], [3, 4], [1, 3], [2, 4]],
+                    3: [[1, 2, 3, 4], [5, 6, 7, 8], [1, 2, 5, 6], [3, 4, 7, 8], [1, 3, 5, 7], [2, 4, 6, 8]]}
+
+
+def boundary_faces(mesh: Mesh, sides: Optional[Sequence[int]] = None):
+    """The (D-1)-faces `cartesian_mesh` creates on the boundary (cartesian_mesh.jl:117-168): cell-major, local faces in
+    increasing order, a local face is a boundary face iff each of its nodes belongs to at most 2^(D-1) cells; face
+    `ldface` of a cell goes to group "<D-1>-face-<ldface>".  `sides` selects groups (None = group "boundary" = all);
+    faces of a domain come in increasing face id (domain.jl:705-753).
+    -> face_nodes [nf, 2^(D-1)] int32 1-based (reference local order), face_cell [nf] 0-based, face_ldface [nf] 1-based."""
+    if mesh.simplex:
+        raise NotImplementedError("boundary faces of simplexified meshes are not restated")
+    D = mesh.D
+    if any(c != 1 for c in mesh.cells_per_dir) and any(c < 2 for c in mesh.cells_per_dir):
+        raise ValueError("At least 2 cells in any direction (or 1 cell in all directions)")   # cartesian_mesh.jl:98-100
+    cn = mesh.cell_nodes.astype(np.int64) - 1
+    node_to_n = np.bincount(cn.reshape(-1), minlength=mesh.n_nodes)
+    nmax = 2 ** (D - 1)
+    tabl = np.array(CUBE_FACE_LNODES[D], dtype=np.int64) - 1                    # [nfl, nfn]
+    isb = (node_to_n[cn[:, tabl]] <= nmax).all(axis=2)                           # [nc, nfl]
+    cell, lf = np.nonzero(isb)                                                   # C order: cell-major, ldface ascending
+    if sides is not None:
+        keep = np.isin(lf + 1, np.asarray(list(sides), dtype=np.int64))
+        cell, lf = cell[keep], lf[keep]
+    face_nodes = cn[cell[:, None], tabl[lf]] + 1
+    return np.ascontiguousarray(face_nodes, dtype=np.int32), cell.astype(np.int64), (lf + 1).astype(np.int32)
+
+
+def face_local_dofs(space: "LagrangeSpace", ldface: int) -> np.ndarray:
+    """0-based local dofs of the cell that lie on local face `ldface` (1-based), in the face's own lattice order
+    (remaining axes, first fastest) — the Lagrange functions of the cell restricted to the face are exactly the face's
+    Lagrange functions in this order, all others vanish there."""
+    D, k = space.mesh.D, space.order
+    e = monomial_exponents(D, k, "Q")
+    axis = D - 1 - (ldface - 1) // 2
+    upper = (ldface - 1) % 2 == 1
+    ls = np.flatnonzero(e[:, axis] == (k if upper else 0))
+    c = np.arange(space.n_comp)
+    return (ls[:, None] * space.n_comp + c[None, :]).reshape(-1)
+
+
+@dataclass
+class FaceProblem:
+    """A boundary domain handed to the engine as a mesh of (D-1)-cells embedded in D dimensions."""
+    face_nodes: np.ndarray     # [nf, 2^(D-1)] int32 1-based mesh nodes
+    face_dofs: np.ndarray      # [nf, n_lfdofs] int32 signed dofs of the space on each face
+    face_cell: np.ndarray
+    face_ldface: np.ndarray
+    tab: "Tabulation"          # tabulation on the reference face (gradients with D-1 components)
+
+
+def face_problem(space: "LagrangeSpace", sides: Optional[Sequence[int]], degree: int) -> FaceProblem:
+    """Inputs of a boundary integral ∫_Γ g v dΓ (Neumann term): measure(Γ, degree) + the space's dofs on Γ's faces."""
+    mesh = space.mesh
+    fn, fc, lf = boundary_faces(mesh, sides)
+    nlf = face_local_dofs(space, 1).size
+    fd = np.empty((fn.shape[0], nlf), dtype=np.int32)
+    for f in range(1, 2 * mesh.D + 1):
+        sel = lf == f
+        if sel.any():
+            fd[sel] = space.cell_dofs[fc[sel]][:, face_local_dofs(space, f)]
+    q = quadrature(mesh.D - 1, False, degree)
+    N, dN = tabulate(mesh.D - 1, space.order, "Q", q.coordinates)
+    M, dM = tabulate(mesh.D - 1, 1, "Q", q.coordinates)
+    return FaceProblem(fn, np.ascontiguousarray(fd), fc, lf, Tabulation(np.ascontiguousarray(q.weights), N, dN, M, dM, q.coordinates))
+
+
 # ----------------------------------------------------------------------------
 # Reference elements, quadrature, tabulation
 # ----------------------------------------------------------------------------

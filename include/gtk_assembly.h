@@ -65,6 +65,9 @@ typedef struct gtk_form_params {
   double f_const[3];       /* SOURCE_CONST */
   const double* f_nodal;   /* SOURCE_NODAL: host [n_nodes][n_comp] */
   const double* f_qp;      /* SOURCE_QP:    host [n_cells][n_q][n_comp] */
+  int32_t accumulate;      /* linear forms: != 0 adds this integral to the vector already on the device (gtk_set_vector or a
+                              previous assembly) instead of starting from zeros — a sum of integrals such as
+                              ∫_Ω f v + ∫_Γ g v is one COO vector in the reference (problems.jl:258-266) */
 } gtk_form_params;
 
 /* ---- life cycle ------------------------------------------------------------ */
@@ -83,6 +86,13 @@ int32_t gtk_set_stream(gtk_ctx* ctx, void* cuda_stream);
  * (cartesian_mesh.jl:213-263; GalerkinToolkitExamples/src/poisson.jl:323-325). */
 int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz,
                      int64_t n_cells, int32_t n_lnodes, const int32_t* cell_nodes);
+/* Cells whose reference space has dimension d < D: boundary faces of a D-dimensional mesh handed over as a mesh of their
+ * own (face nodes = face_nodes(mesh, D-1) of the faces of a boundary domain, domain.jl:705-753; `cell_dofs` = the space's
+ * dofs on each face; tabulations on the (D-1)-dimensional reference face, gradients with d components).  dV is then
+ * sqrt(det(JᵀJ)) w with the D x d Jacobian (quadrature.jl:4-6, accessors.jl:1000-1007) — how the reference integrates
+ * Neumann / Robin terms ∫_Γ g v dΓ.  Call after gtk_set_mesh (which resets d = D) and before gtk_set_tabulation.
+ * Forms that need physical gradients are not available for d < D (GTK_ERR_UNSUPPORTED_FORM). */
+int32_t gtk_set_manifold_dim(gtk_ctx* ctx, int32_t d);
 /* Cells [first, first+count) (0-based) take part in the NUMERIC assembly; all cells take part in the symbolic
  * phase.  Used by the multi-GPU partition: a rank adds the neighbour's boundary cell layer to its mesh so that the
  * pattern of its own rows is complete, but assembles only the cells it owns.  Default: all cells. */
@@ -117,6 +127,8 @@ int32_t gtk_matrix_numeric_device(gtk_ctx* ctx, int32_t form_id, const gtk_form_
 
 /* ---- vector: assemble_vector (problems.jl:244-274; assembly.jl:175-187, 558-569) -- */
 int32_t gtk_vector_symbolic(gtk_ctx* ctx, int32_t free_or_dirichlet);
+/* Upload b (host, length n_rows of the vector selection) as the device vector that an `accumulate` assembly adds to. */
+int32_t gtk_set_vector(gtk_ctx* ctx, const double* b);
 int32_t gtk_vector_assemble(gtk_ctx* ctx, int32_t form_id, const gtk_form_params* p, double* b);
 int32_t gtk_vector_assemble_device(gtk_ctx* ctx, int32_t form_id, const gtk_form_params* p);
 

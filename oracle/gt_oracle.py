@@ -445,19 +445,22 @@ def coo_vector(be, cell_dofs, fd=FREE):
     return (m * I[keep]).astype(np.int32), V[keep]
 
 
-def dense_vector(I, V, n):
-    """PartitionedArrays.dense_vector (assembly.jl:558-569): b[i] += v sequentially in COO order."""
+def dense_vector(I, V, n, b0=None):
+    """PartitionedArrays.dense_vector (assembly.jl:558-569): b[i] += v sequentially in COO order.
+    b0: sums already accumulated from the COO entries of EARLIER integrals of the same linear form (a sum of integrals
+    pushes into one COO vector, contribution after contribution, problems.jl:258-266), so continuing from b0 is the
+    same left-to-right sum."""
     I = np.asarray(I, dtype=np.int64) - 1
     order = np.argsort(I, kind="stable")
     Is, Vs = I[order], np.asarray(V, dtype=np.float64)[order]
-    b = np.zeros(n)
+    b = np.zeros(n) if b0 is None else np.array(b0, dtype=np.float64, copy=True)
     if Is.size == 0:
         return b
     head = np.ones(Is.size, dtype=bool)
     head[1:] = Is[1:] != Is[:-1]
     starts = np.flatnonzero(head)
     lens = np.diff(np.append(starts, Is.size))
-    acc = np.zeros(starts.size) + Vs[starts]       # 0.0 + v is exact
+    acc = b[Is[starts]] + Vs[starts]               # 0.0 + v is exact
     for k in range(1, int(lens.max())):
         sel = lens > k
         acc[sel] = acc[sel] + Vs[starts[sel] + k]
@@ -479,10 +482,13 @@ def assemble_matrix(form, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, ta
 
 
 def assemble_vector(form, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, tab, n_comp=1,
-                    free_or_dirichlet=FREE, **params):
+                    free_or_dirichlet=FREE, b0=None, **params):
+    """`cell_nodes`/`cell_dofs`/`tab` may describe the faces of a boundary domain (cells of dimension D-1 embedded in D
+    dimensions, tabulated on the reference face): the same loop then integrates ∫_Γ g v dΓ, dV = sqrt(det(JᵀJ)) w with
+    the D x (D-1) Jacobian (quadrature.jl:4-6)."""
     be = element_vectors(form, coords, cell_nodes, tab, n_comp=n_comp, **params)
     I, V = coo_vector(be, cell_dofs, free_or_dirichlet)
-    return dense_vector(I, V, n_free if free_or_dirichlet == FREE else n_dirichlet)
+    return dense_vector(I, V, n_free if free_or_dirichlet == FREE else n_dirichlet, b0)
 
 
 # ---------------------------------------------------------------------------

@@ -94,8 +94,10 @@ def test_unsupported_forms_raise_instead_of_falling_back():
         GT.recognise_bilinear(GT.integrate(lambda x: u(x) + v(x), dom).contributions[0][0])
     with pytest.raises(GT.UnsupportedFormError):
         GT.recognise_linear(GT.integrate(lambda x: GT.dot(GT.grad(v, x), GT.grad(v, x)), dom).contributions[0][0], V, dom)
+    # boundary measures exist (Neumann / Robin terms), but forms with physical gradients on Γ are refused
+    dG = GT.measure(GT.boundary(mesh), 2)
     with pytest.raises(GT.UnsupportedFormError):
-        GT.measure(GT.boundary(mesh), 2)
+        GT.assemble_matrix(lambda u, v: GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dG), np.float64, V, V)
 
 
 # ---- the C-ABI library ----------------------------------------------------------------------
@@ -141,3 +143,30 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh", ".jl")):
                 src = open(os.path.join(root, f)).read()
                 assert not pat.search(src), f
+
+
+def test_boundary_faces_follow_cartesian_mesh_order_and_neumann_total():
+    """cartesian_mesh.jl:117-168: boundary faces cell-major / local face ascending, group = local face id; a constant
+    flux over Γ integrates to |Γ| (oracle, partition of unity on the faces)."""
+    import gt_oracle as O
+    H = gtk_b200.hostprep
+    mesh = H.cartesian_mesh((0, 2, 0, 1, 0, 3), (4, 3, 2))
+    fn, fc, lf = H.boundary_faces(mesh)
+    assert fn.shape == (2 * (4 * 3 + 4 * 2 + 3 * 2), 4)
+    assert (np.diff(fc) >= 0).all()                                   # cell-major
+    same = np.diff(fc) == 0
+    assert (np.diff(lf)[same] > 0).all()                              # local faces ascending inside a cell
+    # the first cell (corner) owns local faces 1 (z=0), 3 (y=0), 5 (x=0) with the reference's local node order
+    assert lf[:3].tolist() == [1, 3, 5]
+    assert fn[0].tolist() == mesh.cell_nodes[0][[0, 1, 2, 3]].tolist()
+    assert fn[1].tolist() == mesh.cell_nodes[0][[0, 1, 4, 5]].tolist()
+    assert fn[2].tolist() == mesh.cell_nodes[0][[0, 2, 4, 6]].tolist()
+    for sides, area in (([1], 2.0), ([6], 3.0), ([3, 4], 12.0), (None, 2 * (2 + 3 + 6))):
+        for order in (1, 2):
+            V = H.lagrange_space(mesh, order, None)
+            fp = H.face_problem(V, sides, 2 * order)
+            tab = dict(w=fp.tab.w, N=fp.tab.N, dN=fp.tab.dN, M=fp.tab.M, dM=fp.tab.dM)
+            b = O.assemble_vector(O.SOURCE_CONST, mesh.node_coordinates, fp.face_nodes, fp.face_dofs, V.n_free, V.n_dirichlet, tab, f_const=[1.0])
+            assert abs(b.sum() - area) < 1e-12 * area
+    with pytest.raises(ValueError):
+        H.boundary_faces(H.cartesian_mesh((0, 1, 0, 1), (3, 1)))     # cartesian_mesh.jl:98-100
