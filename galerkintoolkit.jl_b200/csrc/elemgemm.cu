@@ -24,7 +24,8 @@
 // as the DFMA pipe, so tensor cores here buy instruction-issue and register bandwidth, not a higher flop peak.
 #include "gtk_internal.h"
 
-int32_t gtk_reduce_nz_launch(gtk_ctx* ctx);   // numeric.cu
+int32_t gtk_reduce_nz_launch(gtk_ctx* ctx);      // numeric.cu
+int32_t gtk_reduce_multi_launch(gtk_ctx* ctx);   // numeric.cu
 
 namespace {
 
@@ -131,8 +132,18 @@ struct GemmArgs {
   const double* C;    // [n_cells][4*NG][6]
   int64_t n_cells;
   int nld, nq;
-  double* KE;         // [n_cells][nld][nld]
+  double* KE;         // [n_cells][nld][nld] staging of the slots whose nonzero has several contributions
+  const uint32_t* dest;   // [n_cells][nld][nld] MatSym::dest, or nullptr: stage everything
+  double* nzval;
 };
+
+// one element-matrix entry -> its place: straight into nzval when it is the nonzero's only contribution
+__device__ __forceinline__ void put_entry(const GemmArgs& a, size_t e, double v) {
+  if (!a.dest) { a.KE[e] = v; return; }
+  const uint32_t d = a.dest[e];
+  if (d & 0x80000000u) { if (d != 0xFFFFFFFFu) a.nzval[d & 0x7FFFFFFFu] = v; }
+  else a.KE[e] = v;
+}
 
 // MT: 8x8 tiles per side of the element matrix (padded n_ldofs = 8 MT);  NG: groups of 4 quadrature points.
 // WPB warps share one column block (they take alternate cells), so a CTA has WPB·MT warps.
@@ -237,20 +248,31 @@ __global__ void __launch_bounds__(GemmCfg<MT, NG>::THREADS, 1) k_elem_laplace_dm
     if (lane == 0 && k + 2 < K) issue(k + 2);   // every lane is done reading buffer k&1
 
     // ---- store: D[i = 8m+r][j = jown+{0,1}] -> KE[cell][c_slot = i][r_slot = j] and its transpose ----
-    double* ke = a.KE + (size_t)(first + k * stride) * nld * nld;
+    const size_t e0 = (size_t)(first + k * stride) * nld * nld;
 #pragma unroll
     for (int d = 0; d < NTW; ++d) {
       if (d == NTW - 1 && d > 0 && !last_tile) break;
       const int i = 8 * ((cb + d) % MT) + r;
       if (nld == Cfg::NLDP) {
-        *reinterpret_cast<double2*>(ke + (size_t)i * nld + jown) = make_double2(acc[d][0], acc[d][1]);
+        const size_t e = e0 + (size_t)i * nld + jown;
+        if (!a.dest) {
+          *reinterpret_cast<double2*>(a.KE + e) = make_double2(acc[d][0], acc[d][1]);
+        } else {
+          const uint2 dd = *reinterpret_cast<const uint2*>(a.dest + e);   // e is even: 8-byte aligned
+          if (dd.x == 0u && dd.y == 0u) {
+            *reinterpret_cast<double2*>(a.KE + e) = make_double2(acc[d][0], acc[d][1]);
+          } else {
+            if (dd.x & 0x80000000u) { if (dd.x != 0xFFFFFFFFu) a.nzval[dd.x & 0x7FFFFFFFu] = acc[d][0]; } else a.KE[e] = acc[d][0];
+            if (dd.y & 0x80000000u) { if (dd.y != 0xFFFFFFFFu) a.nzval[dd.y & 0x7FFFFFFFu] = acc[d][1]; } else a.KE[e + 1] = acc[d][1];
+          }
+        }
         if (d > 0) {
-          ke[(size_t)jown * nld + i] = acc[d][0];
-          ke[(size_t)(jown + 1) * nld + i] = acc[d][1];
+          put_entry(a, e0 + (size_t)jown * nld + i, acc[d][0]);
+          put_entry(a, e0 + (size_t)(jown + 1) * nld + i, acc[d][1]);
         }
       } else if (i < nld) {
-        if (jown < nld) { ke[(size_t)i * nld + jown] = acc[d][0]; if (d > 0) ke[(size_t)jown * nld + i] = acc[d][0]; }
-        if (jown + 1 < nld) { ke[(size_t)i * nld + jown + 1] = acc[d][1]; if (d > 0) ke[(size_t)(jown + 1) * nld + i] = acc[d][1]; }
+        if (jown < nld) { put_entry(a, e0 + (size_t)i * nld + jown, acc[d][0]); if (d > 0) put_entry(a, e0 + (size_t)jown * nld + i, acc[d][0]); }
+        if (jown + 1 < nld) { put_entry(a, e0 + (size_t)i * nld + jown + 1, acc[d][1]); if (d > 0) put_entry(a, e0 + (size_t)(jown + 1) * nld + i, acc[d][1]); }
       }
     }
   }
@@ -298,6 +320,12 @@ int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool*
     if (r2 == GTK_OK) *cap = n ? n : 1;
     return r2;
   };
+  // Opt-in experiment, measured SLOWER at config 3 (profiles/r01_q3_direct_write.txt): writing the 82 % single-contribution
+  // entries straight into nzval saves their staging round trip (reduction 5.3 -> 3.3 ms) but turns the epilogue's 64-byte
+  // row stores into 32-byte runs at unaligned places plus a dependent 4-byte index load per entry, and the GEMM kernel goes
+  // from 8.2 to 12.6 ms.  Kept for the bitwise A/B test; default is staging everything.
+  const bool direct = getenv("GTK_ENABLE_DIRECT_WRITE") != nullptr;
+  if (direct && (rc = gtk_symbolic_direct_plan(ctx))) return rc;
   if ((rc = ensure(&ctx->KE, &ctx->KE_cap, (size_t)m.n_full))) return rc;
   if ((rc = ensure(&ctx->nzval, &ctx->nzval_cap, (size_t)m.nnz))) return rc;
   if ((rc = ensure(&ctx->Cm, &ctx->Cm_cap, (size_t)ctx->n_cells * nqp * 6))) return rc;
@@ -326,10 +354,11 @@ int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool*
 
   GemmArgs ga;
   ga.dN = ctx->dN; ga.C = ctx->Cm; ga.n_cells = ctx->n_cells; ga.nld = nld; ga.nq = nq; ga.KE = ctx->KE;
+  ga.dest = direct ? m.dest : nullptr; ga.nzval = ctx->nzval;
   if (mt == 1) rc = launch_gemm<1, 2>(ctx, ga);
   else if (mt == 2) rc = launch_gemm<2, 3>(ctx, ga);
   else if (mt == 4) rc = launch_gemm<4, 7>(ctx, ga);
   else rc = launch_gemm<8, 16>(ctx, ga);
   if (rc) return rc;
-  return gtk_reduce_nz_launch(ctx);
+  return direct ? gtk_reduce_multi_launch(ctx) : gtk_reduce_nz_launch(ctx);
 }

@@ -46,6 +46,12 @@ struct MatSym {
   uint32_t* nzptr = nullptr;   // [nnz+1]  first sorted position of every stored nonzero
   // Q1-hex structured fast path ("tile plan"), see plan.cu
   void* plan = nullptr;
+  // direct-write plan of the element-GEMM path (elemgemm.cu), built on first use: where each COO slot's value goes
+  bool direct_ready = false;
+  uint32_t* dest = nullptr;      // [n_full] 0x80000000|p: the slot is the ONLY contribution of nonzero p -> nzval[p];
+                                 //          0xFFFFFFFF: skipped slot; anything else: staged in KE[e] and reduced
+  uint32_t* multi = nullptr;     // [n_multi] nonzeros with >= 2 contributions
+  int64_t n_multi = 0;
   // row-major view for b = beta b + alpha A x (matvec.cu), built on first use
   bool csr_ready = false;
   int64_t* csr_ptr = nullptr;    // [n_rows+1]
@@ -184,6 +190,7 @@ inline void gtk_prof_reset(gtk_ctx* ctx) {
 int32_t gtk_symbolic_matrix_impl(gtk_ctx* ctx, int rows_fd, int cols_fd);
 int32_t gtk_symbolic_vector_impl(gtk_ctx* ctx, int fd);
 int32_t gtk_symbolic_generic_plan(gtk_ctx* ctx);          // matrix: sort-based pattern + reduction plan
+int32_t gtk_symbolic_direct_plan(gtk_ctx* ctx);           // matrix: dest / multi on top of the generic plan
 int32_t gtk_symbolic_vector_generic_plan(gtk_ctx* ctx);   // vector: same
 void gtk_matsym_release(gtk_ctx* ctx);                   // the selected matrix: pattern, plans (values stay allocated)
 void gtk_release_all_matrices(gtk_ctx* ctx);             // every slot (mesh / space changed)

@@ -273,6 +273,28 @@ int32_t pick_cb(gtk_ctx* ctx, size_t per_cell_bytes, int* cb, size_t* smem) {
 
 }  // namespace
 
+// nzval[p] for the nonzeros with several contributions only (the single-contribution ones were written by the producer)
+__global__ void k_reduce_multi(const double* __restrict__ KE, const uint32_t* __restrict__ perm,
+                               const uint32_t* __restrict__ nzptr, const uint32_t* __restrict__ multi, int64_t n_multi,
+                               double* __restrict__ nzval) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_multi; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t p = multi[i];
+    uint32_t s0 = nzptr[p], s1 = nzptr[p + 1];
+    double acc = KE[perm[s0]];
+    for (uint32_t s = s0 + 1; s < s1; ++s) acc += KE[perm[s]];   // reference push order, as k_reduce_nz
+    nzval[p] = acc;
+  }
+}
+
+int32_t gtk_reduce_multi_launch(gtk_ctx* ctx) {
+  MatSym& m = ctx->ms;
+  if (m.n_multi == 0) return GTK_OK;
+  { GtkProf pr_(ctx, "k_reduce_multi"); k_reduce_multi<<<grid_for(m.n_multi, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->KE, m.perm, m.nzptr, m.multi, m.n_multi, ctx->nzval); }
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  return GTK_OK;
+}
+
 // compress (assembly.jl:571-588) of the staged element matrices: shared by the generic and the DMMA path
 int32_t gtk_reduce_nz_launch(gtk_ctx* ctx) {
   MatSym& m = ctx->ms;

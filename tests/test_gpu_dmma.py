@@ -41,8 +41,14 @@ def test_dmma_matches_oracle_and_generic(cells, order, simplexify, bc, warp):
         nz_generic = eng.matrix_numeric(E.FORM_LAPLACE, alpha=0.75)
         assert eng.info(5) == 0
         assert_values_close(nz, nz_generic)
+        os.environ.pop("GTK_DISABLE_DMMA", None)
+        os.environ["GTK_ENABLE_DIRECT_WRITE"] = "1"      # same kernel, single-contribution entries written straight to nzval
+        nz_direct = eng.matrix_numeric(E.FORM_LAPLACE, alpha=0.75)
+        assert eng.info(5) == 3
+        assert nz_direct.tobytes() == nz.tobytes()
     finally:
         os.environ.pop("GTK_DISABLE_DMMA", None)
+        os.environ.pop("GTK_ENABLE_DIRECT_WRITE", None)
         os.environ.pop("GTK_DISABLE_FASTPATH", None)
         eng.close()
 
