@@ -8,12 +8,20 @@
 //
 // The HOST computes the exchange plan (which nzval / b entries go to which peer, and where the
 // received values are added) — galerkintoolkit.jl_b200/partition.py, testable on CPU over gloo.
-// This file only moves bytes:  pack kernel -> ncclSend / ncclRecv in one group -> add kernels in
-// increasing peer rank (deterministic; no float atomics).  NCCL is dlopen'ed so that single-GPU
-// users need no NCCL at all.
+// This file only moves bytes, two ways:
+//  * peer-memory path (default once the host has exchanged the IPC handles, gtk_comm_p2p_export / _import):
+//    ONE kernel per peer gathers the ghost entries and stores them straight into the owner's receive buffer over
+//    NVLink (k_pack_push), then raises a sequence flag in the owner's memory; the owner's k_wait_unpack_add spins on
+//    that flag (system-scope acquire), adds the values in increasing peer rank (deterministic; no float atomics) and
+//    acknowledges, which is what the sender's next push waits for before it overwrites the buffer.  No NCCL kernel,
+//    no staging copy: at 8 ranks ncclSend/ncclRecv of the 2 x 20 MB per rank of BASELINE config 5 took 0.49 ms per
+//    step, the push takes the NVLink time of the payload.
+//  * NCCL path (fallback; GTK_DISABLE_P2P=1): pack kernel -> ncclSend / ncclRecv in one group -> add kernels.
+// NCCL is dlopen'ed so that single-GPU users need no NCCL at all.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <algorithm>
+#include <cstring>
 #include "gtk_internal.h"
 
 int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, const int32_t* d_rows, int64_t nb, int* layer);   // fastq1.cu
@@ -66,15 +74,29 @@ struct Peer {
   int32_t* send_rows = nullptr; // device: rows of b (0-based) that go to the peer
   int64_t* recv_nz = nullptr;   // device: nz positions the received values are added to
   int32_t* recv_rows = nullptr;
-  double* send_buf = nullptr;   // [n_send_nz + n_send_b]
-  double* recv_buf = nullptr;   // [n_recv_nz + n_recv_b]
+  double* send_buf = nullptr;   // [n_send_nz + n_send_b]  (NCCL path)
+  double* recv_buf = nullptr;   // = ipc_block + P2P_HDR doubles: [n_recv_nz + n_recv_b]
   int min_send_layer = -1;      // lowest lattice node layer whose sweep segment writes a value sent to this peer (-1: unknown)
+  // peer-memory path.  ipc_block (raw cudaMalloc, exported over CUDA IPC) = header of P2P_HDR doubles + receive buffer:
+  //   header word 0: `ready` sequence number, written by the PEER's k_pack_push after its data landed here
+  //   header word 1: `ack` sequence number, written by the PEER's k_wait_unpack_add after it consumed what WE pushed
+  double* ipc_block = nullptr;
+  size_t ipc_bytes = 0;
+  double* remote_block = nullptr;   // the peer's block for us, mapped with cudaIpcOpenMemHandle
+  unsigned int* done_ctr = nullptr; // [2] block counters of the push / unpack kernels of this peer
 };
+constexpr int P2P_HDR = 32;   // doubles (256 B) in front of the receive buffer
 
 struct GhostPlan {
   std::vector<Peer> peers;   // sorted by rank
   cudaStream_t side = nullptr;          // pack + NCCL run here while the rest of the sweep runs on ctx->stream
   cudaEvent_t ev_first = nullptr, ev_xchg = nullptr;
+  unsigned long long seq = 0;           // exchange counter of the peer-memory path (same on every rank)
+  bool p2p_ready() const {
+    if (peers.empty() || getenv("GTK_DISABLE_P2P")) return false;
+    for (auto& p : peers) if (!p.remote_block || !p.ipc_block) return false;
+    return true;
+  }
 };
 
 __global__ void k_pack(const double* __restrict__ nzval, const int64_t* __restrict__ idx, int64_t n,
@@ -82,6 +104,59 @@ __global__ void k_pack(const double* __restrict__ nzval, const int64_t* __restri
                        double* __restrict__ buf) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x)
     buf[i] = i < n ? nzval[idx[i]] : b[rows[i - n]];
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Sender: gather the ghost entries and store them into the OWNER's receive buffer (peer memory over NVLink); the last
+// block to finish raises the owner's `ready` flag.  Before overwriting the buffer every block waits until the owner has
+// acknowledged the previous exchange (`ack` flag in OUR block, written by the owner's k_wait_unpack_add).
+__global__ void __launch_bounds__(256) k_pack_push(const double* __restrict__ nzval, const int64_t* __restrict__ idx, int64_t n,
+                                                   const double* __restrict__ b, const int32_t* __restrict__ rows, int64_t nb,
+                                                   double* remote_buf, unsigned long long* remote_ready,
+                                                   const unsigned long long* local_ack, unsigned long long seq, unsigned int* ctr) {
+  if (threadIdx.x == 0) while (ld_acquire_sys(local_ack) + 1 < seq) __nanosleep(64);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x)
+    remote_buf[i] = i < n ? nzval[idx[i]] : b[rows[i - n]];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(ctr, 1u) == gridDim.x - 1) {   // every block's stores are fenced: publish
+      *ctr = 0;
+      __threadfence_system();
+      st_release_sys(remote_ready, seq);
+    }
+  }
+}
+
+// Owner: wait for the peer's data of exchange `seq`, add it (each target position at most once per peer, so no
+// atomics), then acknowledge in the PEER's block so that its next push may overwrite the buffer.
+__global__ void __launch_bounds__(256) k_wait_unpack_add(double* __restrict__ nzval, const int64_t* __restrict__ idx, int64_t n,
+                                                         double* __restrict__ b, const int32_t* __restrict__ rows, int64_t nb,
+                                                         const double* buf, const unsigned long long* local_ready,
+                                                         unsigned long long* remote_ack, unsigned long long seq, unsigned int* ctr) {
+  if (threadIdx.x == 0) while (ld_acquire_sys(local_ready) < seq) __nanosleep(64);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = __ldcg(buf + i);   // written by another GPU while this kernel runs: not through L1
+    if (i < n) nzval[idx[i]] += v; else b[rows[i - n]] += v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(ctr, 1u) == gridDim.x - 1) {
+      *ctr = 0;
+      __threadfence_system();
+      st_release_sys(remote_ack, seq);
+    }
+  }
 }
 
 // each target position appears at most once per peer (checked on the host), so no atomics are needed
@@ -104,7 +179,10 @@ void free_peer(gtk_ctx* ctx, Peer& p) {
   gtk_dev_free(ctx, p.recv_nz, sizeof(int64_t) * p.n_recv_nz);
   gtk_dev_free(ctx, p.recv_rows, sizeof(int32_t) * p.n_recv_b);
   gtk_dev_free(ctx, p.send_buf, sizeof(double) * (p.n_send_nz + p.n_send_b));
-  gtk_dev_free(ctx, p.recv_buf, sizeof(double) * (p.n_recv_nz + p.n_recv_b));
+  if (p.remote_block) cudaIpcCloseMemHandle(p.remote_block);
+  if (p.ipc_block) { cudaFree(p.ipc_block); ctx->bytes_held -= (int64_t)p.ipc_bytes; }
+  if (p.done_ctr) cudaFree(p.done_ctr);
+  p.remote_block = p.ipc_block = p.recv_buf = nullptr; p.done_ctr = nullptr;
 }
 
 template <class T>
@@ -190,7 +268,14 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
   if ((rc = upload_idx(ctx, &p.recv_nz, recv_nz, n_recv_nz))) return rc;
   if ((rc = upload_idx(ctx, &p.recv_rows, recv_rows, n_recv_b))) return rc;
   if (n_send_nz + n_send_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.send_buf, sizeof(double) * (n_send_nz + n_send_b)))) return rc;
-  if (n_recv_nz + n_recv_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.recv_buf, sizeof(double) * (n_recv_nz + n_recv_b)))) return rc;
+  // receive buffer + flag header in ONE raw allocation (not pooled): it is exported to the peer over CUDA IPC
+  p.ipc_bytes = sizeof(double) * (size_t)(P2P_HDR + n_recv_nz + n_recv_b);
+  GTK_CK(cudaMalloc(&p.ipc_block, p.ipc_bytes));
+  ctx->bytes_held += (int64_t)p.ipc_bytes;
+  GTK_CK(cudaMemsetAsync(p.ipc_block, 0, p.ipc_bytes, ctx->stream));
+  p.recv_buf = p.ipc_block + P2P_HDR;
+  GTK_CK(cudaMalloc(&p.done_ctr, 2 * sizeof(unsigned int)));
+  GTK_CK(cudaMemsetAsync(p.done_ctr, 0, 2 * sizeof(unsigned int), ctx->stream));
   GTK_CK(cudaStreamSynchronize(ctx->stream));
   if ((rc = gtk_fastq1_min_layer(ctx, p.send_nz, n_send_nz, p.send_rows, n_send_b, &p.min_send_layer))) return rc;
   g->peers.push_back(p);
@@ -202,6 +287,23 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
 
 // pack + send/recv on stream `st`
 static int32_t exchange_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
+  if (g->p2p_ready()) {   // gather + store into the owner's buffer over NVLink + flag, one kernel per peer
+    ++g->seq;
+    for (auto& p : g->peers) {
+      const int64_t n = p.n_send_nz + p.n_send_b;
+      if (n == 0) continue;
+      if (p.n_send_b && !ctx->bvec) GTK_FAIL(GTK_ERR_STATE, "ghost rows of b requested but no vector assembled");
+      unsigned long long* rhdr = reinterpret_cast<unsigned long long*>(p.remote_block);
+      const unsigned long long* lhdr = reinterpret_cast<const unsigned long long*>(p.ipc_block);
+      { GtkProf pr_(ctx, "k_pack_push");
+        k_pack_push<<<grid_for(n), 256, 0, st>>>(ctx->nzval, p.send_nz, p.n_send_nz, ctx->bvec, p.send_rows, p.n_send_b,
+                                                 p.remote_block + P2P_HDR, rhdr + 0, lhdr + 1, g->seq, p.done_ctr + 0); }
+      GTK_CK(cudaGetLastError());
+      gtk_count_launch(ctx);
+    }
+    return GTK_OK;
+  }
+  if (!ctx->comm) GTK_FAIL(GTK_ERR_STATE, "ghost-row exchange: neither peer memory (gtk_comm_p2p_import) nor NCCL (gtk_comm_init) is set up");
   ncclComm_t comm = (ncclComm_t)ctx->comm;
   for (auto& p : g->peers) {
     const int64_t n = p.n_send_nz + p.n_send_b;
@@ -222,6 +324,20 @@ static int32_t exchange_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
 
 // add what the peers sent, in increasing peer rank: fixed summation order
 static int32_t unpack_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
+  if (g->p2p_ready()) {
+    for (auto& p : g->peers) {
+      const int64_t n = p.n_recv_nz + p.n_recv_b;
+      if (n == 0) continue;
+      const unsigned long long* lhdr = reinterpret_cast<const unsigned long long*>(p.ipc_block);
+      unsigned long long* rhdr = reinterpret_cast<unsigned long long*>(p.remote_block);
+      { GtkProf pr_(ctx, "k_wait_unpack_add");
+        k_wait_unpack_add<<<grid_for(n), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b,
+                                                       p.recv_buf, lhdr + 0, rhdr + 1, g->seq, p.done_ctr + 1); }
+      GTK_CK(cudaGetLastError());
+      gtk_count_launch(ctx);
+    }
+    return GTK_OK;
+  }
   for (auto& p : g->peers) {
     const int64_t n = p.n_recv_nz + p.n_recv_b;
     if (n == 0) continue;
@@ -238,7 +354,7 @@ int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx) {
   if (!ctx) return GTK_ERR_INVALID;
   GhostPlan* g = (GhostPlan*)ctx->ghost;
   if (!g || g->peers.empty()) return GTK_OK;
-  if (!ctx->comm) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: call gtk_comm_init first");
+  if (!ctx->comm && !g->p2p_ready()) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: call gtk_comm_init (NCCL) or gtk_comm_p2p_import (peer memory) first");
   if (!ctx->nzval) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_sum_ghost_rows: nothing assembled yet");
   GTK_CK(cudaSetDevice(ctx->device));
   int32_t rc = exchange_on(ctx, g, ctx->stream);
@@ -259,7 +375,7 @@ int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t mform, cons
   int32_t rc;
   int layer = 0x7FFFFFFF;
   if (g) for (auto& p : g->peers) if (p.n_send_nz + p.n_send_b) layer = p.min_send_layer < 0 ? -1 : (layer < 0 ? -1 : (p.min_send_layer < layer ? p.min_send_layer : layer));
-  const bool overlap = g && !g->peers.empty() && ctx->comm && layer >= 0 && layer != 0x7FFFFFFF && gtk_fastq1_plan_ok(ctx) &&
+  const bool overlap = g && !g->peers.empty() && (ctx->comm || g->p2p_ready()) && layer >= 0 && layer != 0x7FFFFFFF && gtk_fastq1_plan_ok(ctx) &&
                        !getenv("GTK_DISABLE_OVERLAP");
   if (!overlap) {
     if ((rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv))) return rc;
@@ -313,6 +429,41 @@ int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t mform, cons
   return rc;
 }
 
+// Peer-memory transport: every rank exports, per peer, the block it receives that peer's values in (64-byte CUDA IPC
+// handle); the host carries the handles to the peers by its own means (as it does for the NCCL unique id) and each rank
+// imports the handle of the block its peer keeps for it.  Once every peer of a rank is imported the exchange uses direct
+// NVLink stores + flags instead of NCCL.  Needs peer access between the GPUs (NVLink / NVSwitch box).
+int32_t gtk_comm_p2p_export(gtk_ctx* ctx, int32_t peer, void* handle64) {
+  if (!ctx || !handle64) return GTK_ERR_INVALID;
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  if (g) for (auto& p : g->peers) if (p.rank == peer) {
+    GTK_CK(cudaSetDevice(ctx->device));
+    GTK_CK(cudaStreamSynchronize(ctx->stream));   // the block's zero-fill must be done before a peer can write to it
+    cudaIpcMemHandle_t h;
+    GTK_CK(cudaIpcGetMemHandle(&h, p.ipc_block));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(handle64, &h, sizeof(h));
+    return GTK_OK;
+  }
+  GTK_FAIL(GTK_ERR_STATE, "gtk_comm_p2p_export: no exchange plan for this peer (gtk_comm_set_exchange first)");
+}
+
+int32_t gtk_comm_p2p_import(gtk_ctx* ctx, int32_t peer, const void* handle64) {
+  if (!ctx || !handle64) return GTK_ERR_INVALID;
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  if (g) for (auto& p : g->peers) if (p.rank == peer) {
+    GTK_CK(cudaSetDevice(ctx->device));
+    if (p.remote_block) { cudaIpcCloseMemHandle(p.remote_block); p.remote_block = nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* ptr = nullptr;
+    GTK_CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p.remote_block = (double*)ptr;
+    return GTK_OK;
+  }
+  GTK_FAIL(GTK_ERR_STATE, "gtk_comm_p2p_import: no exchange plan for this peer (gtk_comm_set_exchange first)");
+}
+
 int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key) {
   if (!ctx) return -1;
   const GhostPlan* g = (const GhostPlan*)ctx->ghost;
@@ -322,6 +473,7 @@ int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key) {
     case 0: return s;
     case 1: return r;
     case 2: return 8 * (s + r);
+    case 3: return g && g->p2p_ready() ? 1 : 0;   // transport of the next exchange: 1 peer memory, 0 NCCL
     default: return -1;
   }
 }

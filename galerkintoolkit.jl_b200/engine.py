@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "gtk_assemble_matrix_and_vector", "gtk_assemble_matrix_and_vector_device",
     "gtk_device_pointer", "gtk_copy_nzval", "gtk_copy_vector", "gtk_info",
     "gtk_comm_unique_id", "gtk_comm_init", "gtk_comm_set_exchange", "gtk_comm_sum_ghost_rows",
-    "gtk_assemble_and_sum_ghost_rows_device", "gtk_select_matrix", "gtk_matvec_add_device", "gtk_matvec_add", "gtk_set_manifold_dim", "gtk_set_vector",
+    "gtk_assemble_and_sum_ghost_rows_device", "gtk_select_matrix", "gtk_matvec_add_device", "gtk_matvec_add", "gtk_set_manifold_dim", "gtk_set_vector", "gtk_comm_p2p_export", "gtk_comm_p2p_import",
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
 ]
 
@@ -92,6 +92,8 @@ def load_library() -> C.CDLL:
         "gtk_comm_set_exchange": (i32, [vp, i32, i64, vp, i64, vp, i64, vp, i64, vp]),
         "gtk_comm_sum_ghost_rows": (i32, [vp]),
         "gtk_select_matrix": (i32, [vp, i32]),
+        "gtk_comm_p2p_export": (i32, [vp, i32, C.c_void_p]),
+        "gtk_comm_p2p_import": (i32, [vp, i32, C.c_void_p]),
         "gtk_set_manifold_dim": (i32, [vp, i32]),
         "gtk_set_vector": (i32, [vp, C.c_void_p]),
         "gtk_matvec_add_device": (i32, [vp, C.c_double, C.c_void_p, C.c_double]),
@@ -360,6 +362,16 @@ class Engine:
 
     def comm_ghost_info(self, key: int) -> int:
         return int(self.lib.gtk_comm_ghost_info(self.h, key))
+
+    def comm_p2p_export(self, peer: int) -> bytes:
+        """64-byte CUDA IPC handle of the block this rank receives `peer`'s ghost values in."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.gtk_comm_p2p_export(self.h, int(peer), buf))
+        return buf.raw
+
+    def comm_p2p_import(self, peer: int, handle: bytes):
+        buf = C.create_string_buffer(bytes(handle), 64)
+        self._ck(self.lib.gtk_comm_p2p_import(self.h, int(peer), buf))
 
     def comm_sum_ghost_rows(self):
         self._ck(self.lib.gtk_comm_sum_ghost_rows(self.h))

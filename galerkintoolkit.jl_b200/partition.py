@@ -21,6 +21,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
+import os
+
 import numpy as np
 
 from . import hostprep as H
@@ -234,6 +236,16 @@ def attach(engine, part: SlabPart, tab, dist):
     for peer in sorted(plan):
         pl = plan[peer]
         engine.comm_set_exchange(peer, pl["send_nz"], pl["send_rows"], pl["recv_nz"], pl["recv_rows"])
+    # peer-memory transport: swap the CUDA IPC handles of the receive blocks (NCCL stays as the fallback)
+    if os.environ.get("GTK_DISABLE_P2P") is None:
+        outbox = [None] * part.world
+        for peer in plan:
+            outbox[peer] = engine.comm_p2p_export(peer)
+        inbox = torch_alltoall_objects(dist)(outbox)
+        for peer in plan:
+            if inbox[peer] is None:
+                raise RuntimeError(f"rank {part.rank}: peer {peer} did not export a receive block")
+            engine.comm_p2p_import(peer, inbox[peer])
     owned = owned_rows_mask(part)
     n_owned_nnz = int(owned[rowval.astype(np.int64) - 1].sum())
     return colptr, rowval, n_owned_nnz

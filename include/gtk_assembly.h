@@ -192,7 +192,15 @@ int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx);
  * same result as the two separate calls (which is also what it does when the structured sweep kernels do not apply). */
 int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t matrix_form, const gtk_form_params* pm,
                                                int32_t vector_form, const gtk_form_params* pv);
-/* key: 0 ghost nz entries sent per exchange  1 ghost nz entries received  2 bytes moved per exchange */
+/* Peer-memory transport (NVLink / NVSwitch boxes): after gtk_comm_set_exchange, every rank exports for each peer the
+ * 64-byte CUDA IPC handle of the block it receives that peer's values in; the host carries it to the peer (like the NCCL
+ * unique id), which imports it.  Once all peers of a rank are imported, the exchange is one kernel per peer that gathers
+ * the ghost entries and stores them straight into the owner's buffer over NVLink, plus system-scope sequence flags; NCCL
+ * (gtk_comm_init) is then only the fallback (GTK_DISABLE_P2P=1).  Results are bitwise the same on both transports. */
+int32_t gtk_comm_p2p_export(gtk_ctx* ctx, int32_t peer, void* handle64);
+int32_t gtk_comm_p2p_import(gtk_ctx* ctx, int32_t peer, const void* handle64);
+/* key: 0 ghost nz entries sent per exchange  1 ghost nz entries received  2 bytes moved per exchange
+ *      3 transport of the next exchange (1 peer memory, 0 NCCL) */
 int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key);
 
 #ifdef __cplusplus

@@ -42,6 +42,18 @@ def _worker(rank, world, port, cells, dom, q):
         for rep in range(2):
             eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
             results.append((eng.copy_nzval(), eng.copy_vector()))
+        # the same two ways over NCCL instead of peer memory (both transports are set up by attach): bitwise equal
+        assert eng.comm_ghost_info(3) == 1, "peer-memory transport not active"
+        os.environ["GTK_DISABLE_P2P"] = "1"
+        assert eng.comm_ghost_info(3) == 0
+        eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+        eng.comm_sum_ghost_rows()
+        results.append((eng.copy_nzval(), eng.copy_vector()))
+        eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+        results.append((eng.copy_nzval(), eng.copy_vector()))
+        del os.environ["GTK_DISABLE_P2P"]
+        eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+        results.append((eng.copy_nzval(), eng.copy_vector()))
         nzval, b = results[0]
         check_owned_rows(part, colptr, rowval, nzval, b, A_glob, bg)
         own = part.row_owner == part.rank
