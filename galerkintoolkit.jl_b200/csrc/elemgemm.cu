@@ -38,6 +38,9 @@ struct MetricArgs {
   int nln, nq, nqp;   // nqp = padded points per cell in the output
   double alpha;
   int64_t act0, act1;
+  const double* coef; // coefficient κ: nullptr, nodal [n_nodes] (coef_mode 1) or per point [n_cells][nq] (2)
+  const double* M;    // [nq][nln] geometry shape values (nodal coefficient)
+  int coef_mode;
   double* C;          // [n_cells][nqp][6]
 };
 
@@ -79,7 +82,13 @@ __global__ void __launch_bounds__(256) k_cell_metric(MetricArgs a) {
       A[2][1] = J[0][1] * J[2][0] - J[0][0] * J[2][1];
       A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
       const double det = J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0];
-      const double s = a.alpha * a.w[q] / fabs(det);
+      double s = a.alpha * a.w[q] / fabs(det);
+      if (a.coef_mode == 2) s *= a.coef[cell * a.nq + q];
+      else if (a.coef_mode == 1) {
+        double kq = 0.0;
+        for (int n = 0; n < a.nln; ++n) kq += a.coef[nodes[n] - 1] * a.M[q * a.nln + n];
+        s *= kq;
+      }
       // (J^{-1} J^{-T})[a][b] dV = s · Σ_k adj[a][k] adj[b][k]
       c[0] = s * (A[0][0] * A[0][0] + A[0][1] * A[0][1] + A[0][2] * A[0][2]);
       c[1] = s * (A[0][0] * A[1][0] + A[0][1] * A[1][1] + A[0][2] * A[1][2]);
@@ -339,6 +348,8 @@ int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool*
   ma.alpha = p ? p->alpha : 1.0;
   ma.act0 = ctx->act_count < 0 ? 0 : ctx->act_first;
   ma.act1 = ctx->act_count < 0 ? ctx->n_cells : ctx->act_first + ctx->act_count;
+  if ((rc = gtk_upload_coefficient(ctx, form, p, &ma.coef_mode))) return rc;
+  ma.coef = ctx->coef_dev; ma.M = ctx->M;
   ma.C = ctx->Cm;
   {
     int64_t total = ctx->n_cells * nqp;

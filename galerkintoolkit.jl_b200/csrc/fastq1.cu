@@ -1139,7 +1139,7 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
                        const gtk_form_params* pv, bool* handled) {
   *handled = false;
   if (getenv("GTK_DISABLE_FASTPATH")) return GTK_OK;
-  if (mform && mform != GTK_FORM_LAPLACE) return GTK_OK;
+  if (mform && (mform != GTK_FORM_LAPLACE || (pm && (pm->coef_nodal || pm->coef_qp)))) return GTK_OK;   // no coefficient fields in the sweep kernels
   if (vform && (vform != GTK_FORM_SOURCE_CONST || (pv && pv->accumulate))) return GTK_OK;
   if (vform && (!ctx->vs.ready || ctx->vs.fd != GTK_FREE)) return GTK_OK;
   if (!ctx->ms.ready) return GTK_OK;   // the plan needs the pattern (also for vector-only calls)

@@ -79,7 +79,7 @@ int32_t upload(gtk_ctx* ctx, T** dst, size_t* old_n, const T* src, size_t n) {
 
 extern "C" {
 
-int32_t gtk_version(void) { return 101; }
+int32_t gtk_version(void) { return 102; }
 
 int32_t gtk_create(int32_t device, gtk_ctx** out) {
   if (!out) return GTK_ERR_INVALID;
@@ -108,7 +108,7 @@ int32_t gtk_destroy(gtk_ctx* ctx) {
   gtk_cuda_free(ctx, ctx->xvec);
   for (void* q : {(void*)ctx->xyz, (void*)ctx->cell_nodes, (void*)ctx->cell_dofs, (void*)ctx->w, (void*)ctx->N, (void*)ctx->dN,
                   (void*)ctx->M, (void*)ctx->dM, (void*)ctx->KE, (void*)ctx->BE, (void*)ctx->nzval, (void*)ctx->bvec,
-                  (void*)ctx->f_dev, (void*)ctx->Cm})
+                  (void*)ctx->f_dev, (void*)ctx->coef_dev, (void*)ctx->Cm})
     gtk_cuda_free(ctx, q);
   gtk_pool_flush(ctx);
   for (auto& kv : ctx->pool.live) cudaFree(kv.first);   // anything still registered

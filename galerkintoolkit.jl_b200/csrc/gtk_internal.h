@@ -114,6 +114,7 @@ struct gtk_ctx {
   double* nzval = nullptr; size_t nzval_cap = 0;
   double* bvec = nullptr;  size_t bvec_cap = 0;
   double* f_dev = nullptr; size_t f_cap = 0;  // uploaded f_nodal / f_qp
+  double* coef_dev = nullptr; size_t coef_cap = 0;   // uploaded coef_nodal / coef_qp
   double* Cm = nullptr;  size_t Cm_cap = 0;   // [n_cells][n_q padded][6] per-point metric (elemgemm.cu)
 
   struct { size_t xyz = 0, cell_nodes = 0, cell_dofs = 0, w = 0, N = 0, dN = 0, M = 0, dM = 0; } sz;  // uploaded element counts
@@ -200,5 +201,7 @@ void gtk_vecsym_release(gtk_ctx* ctx);
 // ---- numeric.cu ----
 int32_t gtk_numeric_matrix_impl(gtk_ctx* ctx, int form, const gtk_form_params* p);
 int32_t gtk_numeric_vector_impl(gtk_ctx* ctx, int form, const gtk_form_params* p);
+// coefficient of a bilinear form: uploads p->coef_nodal / p->coef_qp; *mode = 0 none, 1 nodal, 2 per quadrature point
+int32_t gtk_upload_coefficient(gtk_ctx* ctx, int form, const gtk_form_params* p, int* mode);
 int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
                               const gtk_form_params* pv);

@@ -28,6 +28,8 @@ struct ElemArgs {
   double alpha, lambda, mu;
   double f_const[3];
   const double* f_ptr;
+  const double* coef_ptr;   // coefficient κ of a bilinear form
+  int coef_mode;            // 0 none, 1 nodal [n_nodes], 2 per quadrature point [n_cells][nq]
   double* out;
   int cb;
   int64_t act0, act1;   // numeric-active cells [act0, act1); others contribute zeros
@@ -113,7 +115,15 @@ __global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
     int cl = t / nq, q = t - cl * nq;
     double J[D][d];
     jacobian_at<D, d>(a, cell0 + cl, q, J);
-    dV[t] = change_of_measure<D, d>(J) * a.w[q];
+    double dv = change_of_measure<D, d>(J) * a.w[q];
+    if (a.coef_mode == 2) dv *= a.coef_ptr[(cell0 + cl) * nq + q];
+    else if (a.coef_mode == 1) {   // κ_q = Σ_node κ_node M_node(ξ_q), sequential in local-node order
+      const int32_t* nodes = a.cell_nodes + (cell0 + cl) * a.nln;
+      double kq = 0.0;
+      for (int n = 0; n < a.nln; ++n) kq += a.coef_ptr[nodes[n] - 1] * a.M[q * a.nln + n];
+      dv *= kq;
+    }
+    dV[t] = dv;
     if constexpr (D == d) if (need_grad) {
       double JT[D][D];
 #pragma unroll
@@ -255,6 +265,7 @@ int32_t fill_args(gtk_ctx* ctx, ElemArgs& a, int form, const gtk_form_params* p)
   a.mu = p ? p->mu : 0.0;
   for (int k = 0; k < 3; ++k) a.f_const[k] = p ? p->f_const[k] : 0.0;
   a.f_ptr = nullptr;
+  a.coef_ptr = nullptr; a.coef_mode = 0;
   a.act0 = ctx->act_count < 0 ? 0 : ctx->act_first;
   a.act1 = ctx->act_count < 0 ? ctx->n_cells : ctx->act_first + ctx->act_count;
   return GTK_OK;
@@ -295,6 +306,20 @@ int32_t gtk_reduce_multi_launch(gtk_ctx* ctx) {
   return GTK_OK;
 }
 
+int32_t gtk_upload_coefficient(gtk_ctx* ctx, int form, const gtk_form_params* p, int* mode) {
+  *mode = 0;
+  if (!p || (!p->coef_nodal && !p->coef_qp)) return GTK_OK;
+  if (p->coef_nodal && p->coef_qp) GTK_FAIL(GTK_ERR_INVALID, "give coef_nodal or coef_qp, not both");
+  if (form != GTK_FORM_LAPLACE && form != GTK_FORM_MASS)
+    GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "a scalar coefficient is supported for LAPLACE and MASS only; no CPU fallback");
+  const size_t n = p->coef_nodal ? (size_t)ctx->n_nodes : (size_t)ctx->n_cells * ctx->nq;
+  int32_t rc = ensure(ctx, &ctx->coef_dev, &ctx->coef_cap, n);
+  if (rc) return rc;
+  GTK_CK(cudaMemcpyAsync(ctx->coef_dev, p->coef_nodal ? p->coef_nodal : p->coef_qp, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  *mode = p->coef_nodal ? 1 : 2;
+  return GTK_OK;
+}
+
 // compress (assembly.jl:571-588) of the staged element matrices: shared by the generic and the DMMA path
 int32_t gtk_reduce_nz_launch(gtk_ctx* ctx) {
   MatSym& m = ctx->ms;
@@ -323,6 +348,8 @@ int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params
   ElemArgs a;
   int32_t rc = fill_args(ctx, a, form, p);
   if (rc) return rc;
+  if ((rc = gtk_upload_coefficient(ctx, form, p, &a.coef_mode))) return rc;
+  a.coef_ptr = ctx->coef_dev;
   rc = ensure(ctx, &ctx->KE, &ctx->KE_cap, (size_t)m.n_full);
   if (rc) return rc;
   rc = ensure(ctx, &ctx->nzval, &ctx->nzval_cap, (size_t)m.nnz);

@@ -47,7 +47,8 @@ class UnsupportedFormError(GtkError):
 
 class FormParams(C.Structure):
     _fields_ = [("alpha", C.c_double), ("lam", C.c_double), ("mu", C.c_double),
-                ("f_const", C.c_double * 3), ("f_nodal", C.c_void_p), ("f_qp", C.c_void_p), ("accumulate", C.c_int32)]
+                ("f_const", C.c_double * 3), ("f_nodal", C.c_void_p), ("f_qp", C.c_void_p),
+                ("coef_nodal", C.c_void_p), ("coef_qp", C.c_void_p), ("accumulate", C.c_int32)]
 
 
 _lib = None
@@ -124,7 +125,8 @@ def _i32(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
-def make_params(alpha=1.0, lam=0.0, mu=0.0, f_const=None, f_nodal=None, f_qp=None, accumulate=False):
+def make_params(alpha=1.0, lam=0.0, mu=0.0, f_const=None, f_nodal=None, f_qp=None, accumulate=False,
+                coef_nodal=None, coef_qp=None):
     """Returns (FormParams, keepalive) — keepalive holds the numpy buffers the struct points to."""
     p = FormParams()
     p.alpha, p.lam, p.mu = float(alpha), float(lam), float(mu)
@@ -140,6 +142,10 @@ def make_params(alpha=1.0, lam=0.0, mu=0.0, f_const=None, f_nodal=None, f_qp=Non
         a = _f64(f_nodal); keep.append(a); p.f_nodal = a.ctypes.data
     if f_qp is not None:
         a = _f64(f_qp); keep.append(a); p.f_qp = a.ctypes.data
+    if coef_nodal is not None:
+        a = _f64(coef_nodal); keep.append(a); p.coef_nodal = a.ctypes.data
+    if coef_qp is not None:
+        a = _f64(coef_qp); keep.append(a); p.coef_qp = a.ctypes.data
     return p, keep
 
 

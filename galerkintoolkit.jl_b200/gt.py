@@ -240,9 +240,24 @@ def _flatten_product(t):
     return [t], 1.0
 
 
-def recognise_bilinear(term):
-    """→ (form_id, params).  Raises UnsupportedFormError for anything that is not mass / Laplacian / elasticity."""
+def recognise_bilinear(term, space: Optional["Space"] = None, meas: Optional["Measure"] = None):
+    """→ (form_id, params).  Raises UnsupportedFormError for anything that is not mass / Laplacian / elasticity.
+    A scalar AnalyticalField factor κ(x) in front of ∇u·∇v or u v becomes a host-sampled coefficient (coef_qp)."""
     factors, scale = _flatten_product(term)
+    coefs = [f for f in factors if isinstance(f, Call) and callable(f.fn) and isinstance(f.a, Coordinate)]
+    if len(coefs) == 1 and space is not None and meas is not None:
+        rest = [f for f in factors if f is not coefs[0]]
+        inner = rest[0] if len(rest) == 1 else None
+        if len(rest) == 2:
+            inner = Call("*", rest[0], rest[1])
+        if inner is not None:
+            form, params = recognise_bilinear(inner)
+            if form in (_eng.FORM_LAPLACE, _eng.FORM_MASS):
+                xq = quadrature_point_coordinates(space, meas)
+                vals = np.asarray(coefs[0].fn(np.moveaxis(xq, -1, 0)), dtype=np.float64)
+                params["alpha"] = params.get("alpha", 1.0) * scale
+                params["coef_qp"] = np.ascontiguousarray(np.broadcast_to(vals, xq.shape[:2]))
+                return form, params
     if len(factors) == 1 and isinstance(factors[0], Named) and factors[0].name == "isotropic_elasticity":
         return _eng.FORM_ELASTICITY_ISO, dict(alpha=scale, **factors[0].params)
     if len(factors) == 1 and isinstance(factors[0], Call) and factors[0].fn == "dot":
@@ -376,7 +391,7 @@ def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False,
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
     u, v = FormArgument(U, 2), FormArgument(V, 1)
     term, meas, scale = _single_contribution(a(u, v))
-    form, params = recognise_bilinear(term)
+    form, params = recognise_bilinear(term, V, meas)
     if meas.domain.kind == "boundary" and form != _eng.FORM_MASS:
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "on a boundary measure only ∫_Γ u v dΓ (Robin term) is assembled by the GPU engine")
     params["alpha"] = params.get("alpha", 1.0) * scale

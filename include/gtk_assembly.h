@@ -65,6 +65,11 @@ typedef struct gtk_form_params {
   double f_const[3];       /* SOURCE_CONST */
   const double* f_nodal;   /* SOURCE_NODAL: host [n_nodes][n_comp] */
   const double* f_qp;      /* SOURCE_QP:    host [n_cells][n_q][n_comp] */
+  const double* coef_nodal;/* bilinear forms LAPLACE / MASS: scalar coefficient κ in front of the integrand, ∫ κ ∇u·∇v or ∫ κ u v,
+                              as a nodal field on the mesh nodes, host [n_nodes] (κ_q = Σ_node κ_node M_node(ξ_q): a Q1/P1
+                              DiscreteField passed as `parameters`, problems.jl:352-361, accessors.jl:1489-1563) … */
+  const double* coef_qp;   /* … or sampled by the host at the quadrature points, host [n_cells][n_q] (AnalyticalField
+                              coefficients, field.jl:17-58).  At most one of the two; NULL = no coefficient. */
   int32_t accumulate;      /* linear forms: != 0 adds this integral to the vector already on the device (gtk_set_vector or a
                               previous assembly) instead of starting from zeros — a sum of integrals such as
                               ∫_Ω f v + ∫_Γ g v is one COO vector in the reference (problems.jl:258-266) */

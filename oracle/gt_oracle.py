@@ -320,9 +320,12 @@ LAPLACE, MASS, ELASTICITY = 1, 2, 3
 SOURCE_CONST, SOURCE_NODAL, SOURCE_QP = 101, 102, 103
 
 
-def element_matrices(form, coords, cell_nodes, tab, n_comp=1, alpha=1.0, lam=1.0, mu=1.0):
+def element_matrices(form, coords, cell_nodes, tab, n_comp=1, alpha=1.0, lam=1.0, mu=1.0, coef_nodal=None, coef_qp=None):
     """be[cell, r, c] = Σ_q ((α·integrand(u=φ_r, v=φ_c))·dV_q), q outermost, then c, then r
-    (compiler.jl:1865-1900; problems.jl:55-63)."""
+    (compiler.jl:1865-1900; problems.jl:55-63).
+    coef_nodal / coef_qp: scalar coefficient κ(x_q) multiplying the integrand (∫ κ ∇u·∇v, ∫ κ u v): a nodal field
+    interpolated with the geometry functions (DiscreteField parameter, accessors.jl:1489-1563: Σ_node κ_node M_node(ξ_q),
+    sequential) or host-sampled values per (cell, point) (AnalyticalField, field.jl:17-58)."""
     w, N, dN, dM = tab["w"], tab["N"], tab["dN"], tab["dM"]
     nc = cell_nodes.shape[0]
     nq, nls = N.shape
@@ -332,6 +335,14 @@ def element_matrices(form, coords, cell_nodes, tab, n_comp=1, alpha=1.0, lam=1.0
     for q in range(nq):
         J = point_geometry(coords, cell_nodes, dM[q])
         dV = change_of_measure(J) * w[q]                                        # accessors.jl:1000-1007
+        kq = None
+        if coef_qp is not None:
+            kq = np.asarray(coef_qp, dtype=np.float64).reshape(nc, nq)[:, q]
+        elif coef_nodal is not None:
+            kq = np.zeros(nc)
+            kn = np.asarray(coef_nodal, dtype=np.float64).reshape(-1)
+            for n in range(cell_nodes.shape[1]):
+                kq = kq + kn[cell_nodes[:, n] - 1] * tab["M"][q, n]
         Jt = np.swapaxes(J, -1, -2)
         if form in (LAPLACE, ELASTICITY):
             g = [_solve(Jt, np.broadcast_to(dN[q, a], (nc, D))) for a in range(nls)]   # accessors.jl:1365-1368
@@ -340,9 +351,11 @@ def element_matrices(form, coords, cell_nodes, tab, n_comp=1, alpha=1.0, lam=1.0
                 a, i = divmod(r, n_comp)      # dof = (node-1)*n_comp + comp  (space.jl:1267-1271)
                 b, j = divmod(c, n_comp)
                 if form == LAPLACE:           # ∇u:∇v = δ_ij ∇s_a·∇s_b for vector-valued spaces
-                    v = (alpha * (_dot(g[a], g[b]) if i == j else np.zeros(nc))) * dV
+                    t = _dot(g[a], g[b]) if i == j else np.zeros(nc)
+                    v = (alpha * (t if kq is None else kq * t)) * dV
                 elif form == MASS:            # u·v = δ_ij s_a s_b
-                    v = (alpha * ((N[q, a] * N[q, b]) if i == j else 0.0)) * dV
+                    t = (N[q, a] * N[q, b]) if i == j else 0.0
+                    v = (alpha * (t if kq is None else kq * t)) * dV
                 elif form == ELASTICITY:
                     # σ(ε(u)):ε(v), u = s_a e_i, v = s_b e_j, isotropic (λ, μ)
                     t = lam * (g[a][:, i] * g[b][:, j]) + mu * (g[a][:, j] * g[b][:, i])

@@ -182,3 +182,31 @@ def test_empty_and_all_dirichlet():
     assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
     assert_values_close(eng.matrix_numeric(E.FORM_LAPLACE), nzval)
     eng.close()
+
+
+COEF_CASES = [((7, 6), 1, False), ((5, 4, 3), 1, False), ((3, 3, 2), 2, False), ((3, 2, 2), 3, False), ((4, 3, 3), 1, True), ((12, 10, 8), 1, False)]
+
+
+@pytest.mark.parametrize("cells,order,simplexify", COEF_CASES)
+def test_coefficient_fields(cells, order, simplexify):
+    """∫ κ ∇u·∇v and ∫ κ u v with κ a nodal field (DiscreteField parameter of update_matrix!) or sampled
+    at the quadrature points (AnalyticalField): generic kernel, element-GEMM path, and the sweep kernels stepping aside."""
+    mesh, V, tab = problem(cells, order=order, bc=[1], simplexify=simplexify, warp=0.15)
+    rng = np.random.default_rng(7)
+    kn = 1.0 + rng.random(mesh.n_nodes)
+    kq = 1.0 + rng.random((mesh.n_cells, tab.w.size))
+    eng = make_engine(mesh, V, tab)
+    eng.matrix_symbolic()
+    for form, oform in ((E.FORM_LAPLACE, O.LAPLACE), (E.FORM_MASS, O.MASS)):
+        for kw in (dict(coef_nodal=kn), dict(coef_qp=kq)):
+            _, _, ref = oracle_matrix(oform, mesh, V, tab, alpha=0.5, **kw)
+            nz = eng.matrix_numeric(form, alpha=0.5, **kw)
+            assert eng.info(5) in (0, 3)                 # never the constant-coefficient sweep kernels
+            assert_values_close(nz, ref)
+            assert eng.matrix_numeric(form, alpha=0.5, **kw).tobytes() == nz.tobytes()
+    # update_matrix! with a new coefficient on the cached pattern; κ ≡ 1 reproduces the plain form
+    _, _, plain = oracle_matrix(O.LAPLACE, mesh, V, tab, alpha=0.5)
+    assert_values_close(eng.matrix_numeric(E.FORM_LAPLACE, alpha=0.5, coef_nodal=np.ones(mesh.n_nodes)), plain)
+    with pytest.raises(E.GtkError):
+        eng.matrix_numeric(E.FORM_LAPLACE, coef_nodal=kn, coef_qp=kq)
+    eng.close()

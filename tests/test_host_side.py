@@ -83,6 +83,15 @@ def test_form_recognition():
     assert form == E.FORM_SOURCE_QP and params["f_qp"].shape == (16, 4, 1)
     form, params = GT.recognise_linear(GT.integrate(lambda x: 2.0 * v(x), dom).contributions[0][0], V, dom)
     assert form == E.FORM_SOURCE_CONST and params["alpha"] == 2.0
+    # variable coefficient κ(x) ∇u·∇v / κ(x) u v: κ sampled by the host at the quadrature points
+    kappa = GT.analytical_field(lambda x: 1.0 + x[0] * x[1])
+    t = GT.integrate(lambda x: 2.0 * (kappa(x) * GT.dot(GT.grad(u, x), GT.grad(v, x))), dom).contributions[0][0]
+    form, params = GT.recognise_bilinear(t, V, dom)
+    assert form == E.FORM_LAPLACE and params["alpha"] == 2.0 and params["coef_qp"].shape == (16, 4)
+    xq = GT.quadrature_point_coordinates(V, dom)
+    assert np.allclose(params["coef_qp"], 1.0 + xq[..., 0] * xq[..., 1])
+    t = GT.integrate(lambda x: kappa(x) * (u(x) * v(x)), dom).contributions[0][0]
+    assert GT.recognise_bilinear(t, V, dom)[0] == E.FORM_MASS
 
 
 def test_unsupported_forms_raise_instead_of_falling_back():
