@@ -24,7 +24,8 @@
 #include <cstring>
 #include "gtk_internal.h"
 
-int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, const int32_t* d_rows, int64_t nb, int* layer);   // fastq1.cu
+int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, const int32_t* d_rows, int64_t nb, int* layer,
+                             int* max_layer);   // fastq1.cu
 bool gtk_fastq1_plan_ok(const gtk_ctx* ctx);
 
 namespace {
@@ -77,6 +78,7 @@ struct Peer {
   double* send_buf = nullptr;   // [n_send_nz + n_send_b]  (NCCL path)
   double* recv_buf = nullptr;   // = ipc_block + P2P_HDR doubles: [n_recv_nz + n_recv_b]
   int min_send_layer = -1;      // lowest lattice node layer whose sweep segment writes a value sent to this peer (-1: unknown)
+  int max_recv_layer = -1;      // highest node layer whose columns hold a position this peer's values are added to (-1: unknown / none)
   // peer-memory path.  ipc_block (raw cudaMalloc, exported over CUDA IPC) = header of P2P_HDR doubles + receive buffer:
   //   header word 0: `ready` sequence number, written by the PEER's k_pack_push after its data landed here
   //   header word 1: `ack` sequence number, written by the PEER's k_wait_unpack_add after it consumed what WE pushed
@@ -277,7 +279,9 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
   GTK_CK(cudaMalloc(&p.done_ctr, 2 * sizeof(unsigned int)));
   GTK_CK(cudaMemsetAsync(p.done_ctr, 0, 2 * sizeof(unsigned int), ctx->stream));
   GTK_CK(cudaStreamSynchronize(ctx->stream));
-  if ((rc = gtk_fastq1_min_layer(ctx, p.send_nz, n_send_nz, p.send_rows, n_send_b, &p.min_send_layer))) return rc;
+  if ((rc = gtk_fastq1_min_layer(ctx, p.send_nz, n_send_nz, p.send_rows, n_send_b, &p.min_send_layer, nullptr))) return rc;
+  { int lo_unused = -1;
+    if ((rc = gtk_fastq1_min_layer(ctx, p.recv_nz, n_recv_nz, p.recv_rows, n_recv_b, &lo_unused, &p.max_recv_layer))) return rc; }
   g->peers.push_back(p);
   std::sort(g->peers.begin(), g->peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
   return GTK_OK;
@@ -296,7 +300,7 @@ static int32_t exchange_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
       unsigned long long* rhdr = reinterpret_cast<unsigned long long*>(p.remote_block);
       const unsigned long long* lhdr = reinterpret_cast<const unsigned long long*>(p.ipc_block);
       { GtkProf pr_(ctx, "k_pack_push");
-        k_pack_push<<<grid_for(n), 256, 0, st>>>(ctx->nzval, p.send_nz, p.n_send_nz, ctx->bvec, p.send_rows, p.n_send_b,
+        k_pack_push<<<std::min(grid_for(n), 4 * ctx->sm_count), 256, 0, st>>>(ctx->nzval, p.send_nz, p.n_send_nz, ctx->bvec, p.send_rows, p.n_send_b,
                                                  p.remote_block + P2P_HDR, rhdr + 0, lhdr + 1, g->seq, p.done_ctr + 0); }
       GTK_CK(cudaGetLastError());
       gtk_count_launch(ctx);
@@ -331,7 +335,8 @@ static int32_t unpack_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
       const unsigned long long* lhdr = reinterpret_cast<const unsigned long long*>(p.ipc_block);
       unsigned long long* rhdr = reinterpret_cast<unsigned long long*>(p.remote_block);
       { GtkProf pr_(ctx, "k_wait_unpack_add");
-        k_wait_unpack_add<<<grid_for(n), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b,
+        // at most 2 blocks per SM: a block may spin for the peer's flag while the sweep shares the GPU with it
+        k_wait_unpack_add<<<std::min(grid_for(n), 2 * ctx->sm_count), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b,
                                                        p.recv_buf, lhdr + 0, rhdr + 1, g->seq, p.done_ctr + 1); }
       GTK_CK(cudaGetLastError());
       gtk_count_launch(ctx);
@@ -373,9 +378,10 @@ int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t mform, cons
   GTK_CK(cudaSetDevice(ctx->device));
   GhostPlan* g = (GhostPlan*)ctx->ghost;
   int32_t rc;
-  int layer = 0x7FFFFFFF;
+  // top part: node layers >= `layer` hold what goes to a peer (none on a rank that only receives: empty top part)
+  int layer = 0x3FFFFFFF;
   if (g) for (auto& p : g->peers) if (p.n_send_nz + p.n_send_b) layer = p.min_send_layer < 0 ? -1 : (layer < 0 ? -1 : (p.min_send_layer < layer ? p.min_send_layer : layer));
-  const bool overlap = g && !g->peers.empty() && (ctx->comm || g->p2p_ready()) && layer >= 0 && layer != 0x7FFFFFFF && gtk_fastq1_plan_ok(ctx) &&
+  const bool overlap = g && !g->peers.empty() && (ctx->comm || g->p2p_ready()) && layer >= 0 && gtk_fastq1_plan_ok(ctx) &&
                        !getenv("GTK_DISABLE_OVERLAP");
   if (!overlap) {
     if ((rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv))) return rc;
@@ -393,29 +399,57 @@ int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t mform, cons
   static const bool timing = getenv("GTK_COMM_TIMING") != nullptr;   // debug: device timeline of one overlapped step
   cudaEvent_t te[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (timing) { for (auto& e : te) cudaEventCreate(&e); cudaEventRecord(te[0], ctx->stream); }
-  ctx->seg_mode = 1; ctx->seg_layer = layer;
+  // bottom part: the node layers whose columns hold the positions the peers' values are added to.  Sweeping them early
+  // lets the unpack run on the side stream too, concurrently with the middle of the sweep.
+  int lo = 0;
+  bool lo_known = true;
+  for (auto& p : g->peers) if (p.n_recv_nz + p.n_recv_b) {
+    if (p.max_recv_layer < 0) lo_known = false;
+    else if (p.max_recv_layer + 1 > lo) lo = p.max_recv_layer + 1;
+  }
+  // Measured on 2 GPUs: with 1.2 MB received per step (128^3 slabs) the early unpack gains 2 % (0.1531 -> 0.1498 ms); with
+  // 19.8 MB (512x512x64 slabs) it LOSES 3 % (0.998 -> 1.026 ms): the sweep runs at 5 CTAs/SM with the register file full,
+  // so every block of the spinning / adding unpack kernel that is resident displaces one sweep CTA of its SM for as long as
+  // it lives.  Hence: early only for small messages (GTK_EARLY_UNPACK=0/1 overrides).
+  int64_t recv_total = 0;
+  for (auto& p : g->peers) recv_total += p.n_recv_nz + p.n_recv_b;
+  const char* eu = getenv("GTK_EARLY_UNPACK");
+  const bool want_early = eu ? atoi(eu) != 0 : recv_total * 8 <= (4 << 20);
+  const bool early_unpack = lo_known && lo <= layer && want_early && !getenv("GTK_DISABLE_EARLY_UNPACK");
+  if (!early_unpack) lo = 0;
+  ctx->seg_mode = 1; ctx->seg_layer = layer; ctx->seg_lo = lo;
   rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv);
   ctx->seg_mode = 0;
   if (rc) return rc;
   if (timing) cudaEventRecord(te[1], ctx->stream);
-  const int64_t launches_first = ctx->launches_last;
+  int64_t launches_acc = ctx->launches_last;
   if (ctx->fast_path_last != 1 && ctx->fast_path_last != 2)   // the sweep declined (form, tabulation): everything is assembled already
     return gtk_comm_sum_ghost_rows(ctx);
+  if (lo > 0) {
+    ctx->seg_mode = 3; ctx->seg_layer = layer; ctx->seg_lo = lo;
+    rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv);
+    ctx->seg_mode = 0;
+    if (rc) return rc;
+    launches_acc += ctx->launches_last;
+  }
   GTK_CK(cudaEventRecord(g->ev_first, ctx->stream));
   GTK_CK(cudaStreamWaitEvent(g->side, g->ev_first, 0));
+  ctx->launches_last = 0;
   if ((rc = exchange_on(ctx, g, g->side))) return rc;
+  if (early_unpack && (rc = unpack_on(ctx, g, g->side))) return rc;
   GTK_CK(cudaEventRecord(g->ev_xchg, g->side));
   if (timing) cudaEventRecord(te[2], g->side);
-  const int64_t launches_x = ctx->launches_last;
-  ctx->seg_mode = 2; ctx->seg_layer = layer;
+  launches_acc += ctx->launches_last;
+  ctx->seg_mode = 2; ctx->seg_layer = layer; ctx->seg_lo = lo;
   rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv);
   ctx->seg_mode = 0;
   if (rc) return rc;
-  ctx->launches_last += launches_x;   // numeric_both_impl restarts the per-call counter
-  (void)launches_first;
+  launches_acc += ctx->launches_last;
+  ctx->launches_last = 0;
   if (timing) cudaEventRecord(te[3], ctx->stream);
   GTK_CK(cudaStreamWaitEvent(ctx->stream, g->ev_xchg, 0));
-  rc = unpack_on(ctx, g, ctx->stream);
+  if (!early_unpack) rc = unpack_on(ctx, g, ctx->stream);
+  ctx->launches_last += launches_acc;   // numeric_both_impl restarts the per-call counter
   if (timing) {
     cudaEventRecord(te[4], ctx->stream);
     cudaEventSynchronize(te[4]);

@@ -62,7 +62,7 @@ struct FastPlan {
     size_t n = 0;
     int key = 0, seg = 0, nseg = 0, z_begin = 0, z_end = 0;
   };
-  TilePlan tp_affine[3], tp_sweep[3];   // [launch mode]: all layers / first part of an overlapped step / the rest
+  TilePlan tp_affine[4], tp_sweep[4];   // [launch mode]: all layers / top part of an overlapped step / middle / bottom
 };
 
 __global__ void k_verify_structure(const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ cell_dofs,
@@ -868,7 +868,7 @@ int32_t plan_detect(gtk_ctx* ctx, FastPlan* p) {
   int32_t rc;
   if ((rc = gtk_dev_alloc(ctx, (void**)&p->node_dof, sizeof(int32_t) * (size_t)n_nodes))) return rc;
   if ((rc = gtk_dev_alloc(ctx, (void**)&p->dof_node, sizeof(int32_t) * (size_t)ctx->n_free))) return rc;
-  if (!p->d_flag) GTK_CK(gtk_cuda_malloc(ctx, &p->d_flag, sizeof(int)));
+  if (!p->d_flag) GTK_CK(gtk_cuda_malloc(ctx, &p->d_flag, 2 * sizeof(int)));
   GTK_CK(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
   GTK_CK(cudaMemsetAsync(p->node_dof, 0, sizeof(int32_t) * (size_t)n_nodes, st));
   GTK_CK(cudaMemsetAsync(p->dof_node, 0xFF, sizeof(int32_t) * (size_t)ctx->n_free, st));
@@ -935,8 +935,10 @@ int32_t build_tile_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::TilePlan& tp, int k
 // what goes to a peer and are launched first) / only the layers below (mode 2)
 void layer_range(const gtk_ctx* ctx, int layers, int* z_begin, int* z_end) {
   int split = ctx->seg_layer < 0 ? 0 : (ctx->seg_layer > layers ? layers : ctx->seg_layer);
+  int lo = ctx->seg_lo < 0 ? 0 : (ctx->seg_lo > split ? split : ctx->seg_lo);
   if (ctx->seg_mode == 1) { *z_begin = split; *z_end = layers; }
-  else if (ctx->seg_mode == 2) { *z_begin = 0; *z_end = split; }
+  else if (ctx->seg_mode == 2) { *z_begin = lo; *z_end = split; }
+  else if (ctx->seg_mode == 3) { *z_begin = 0; *z_end = lo; }
   else { *z_begin = 0; *z_end = layers; }
 }
 
@@ -993,7 +995,7 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
 // exact per-cell affinity of the numeric-active cell layers; one small kernel + a 4-byte read-back per
 // coordinate upload (cached in the plan until gtk_update_coordinates / gtk_set_mesh)
 int32_t classify_affine(gtk_ctx* ctx, FastPlan* p, const double* xyz, int k0, int k1) {
-  if (!p->d_flag) GTK_CK(gtk_cuda_malloc(ctx, &p->d_flag, sizeof(int)));
+  if (!p->d_flag) GTK_CK(gtk_cuda_malloc(ctx, &p->d_flag, 2 * sizeof(int)));
   GTK_CK(cudaMemsetAsync(p->d_flag, 0, sizeof(int), ctx->stream));
   const int64_t nc = (int64_t)p->n1 * p->n2 * (k1 - k0);
   if (nc > 0) {
@@ -1022,7 +1024,7 @@ namespace {
 __global__ void k_min_layer(const int64_t* __restrict__ nz_pos, int64_t n, const int32_t* __restrict__ rows, int64_t nb,
                             const int64_t* __restrict__ colptr, int64_t n_cols, const int32_t* __restrict__ dof_node,
                             int64_t s2, int* out) {
-  int m = 0x7FFFFFFF;
+  int m = 0x7FFFFFFF, mx = -1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t dof;
     if (i < n) {
@@ -1036,27 +1038,32 @@ __global__ void k_min_layer(const int64_t* __restrict__ nz_pos, int64_t n, const
     } else {
       dof = rows[i - n];
     }
-    m = min(m, (int)(dof_node[dof] / s2));
+    const int layer = (int)(dof_node[dof] / s2);
+    m = min(m, layer);
+    mx = max(mx, layer);
   }
-  if (m != 0x7FFFFFFF) atomicMin(out, m);
+  if (m != 0x7FFFFFFF) { atomicMin(out, m); atomicMax(out + 1, mx); }
 }
 }  // namespace
 
 // Lowest node layer (z index of the lattice) whose sweep segment writes one of the given nzval positions / b rows; -1
 // without a sweep plan.
 // The multi-GPU exchange uses it to launch the z-segments that produce the rows a peer waits for first.
-int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, const int32_t* d_rows, int64_t nb, int* layer) {
+int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, const int32_t* d_rows, int64_t nb, int* layer,
+                             int* max_layer) {
   *layer = -1;
+  if (max_layer) *max_layer = -1;
   if (!gtk_fastq1_plan_ok(ctx) || n + nb == 0) return GTK_OK;
   FastPlan* p = (FastPlan*)ctx->ms.plan;
-  int h = 0x7FFFFFFF;
-  GTK_CK(cudaMemcpyAsync(p->d_flag, &h, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  int h2[2] = {0x7FFFFFFF, -1};
+  int& h = h2[0];
+  GTK_CK(cudaMemcpyAsync(p->d_flag, h2, 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   k_min_layer<<<grid_for(n + nb, 256), 256, 0, ctx->stream>>>(d_nz_pos, n, d_rows, nb, ctx->ms.colptr, ctx->ms.n_cols,
                                                             p->dof_node, (int64_t)(p->n1 + 1) * (p->n2 + 1), p->d_flag);
   GTK_CK(cudaGetLastError());
-  GTK_CK(cudaMemcpyAsync(&h, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GTK_CK(cudaMemcpyAsync(h2, p->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GTK_CK(cudaStreamSynchronize(ctx->stream));
-  if (h != 0x7FFFFFFF) *layer = h;
+  if (h != 0x7FFFFFFF) { *layer = h; if (max_layer) *max_layer = h2[1]; }
   return GTK_OK;
 }
 

@@ -122,7 +122,9 @@ struct gtk_ctx {
   int64_t launches_last = 0, launches_total = 0;
   int64_t bytes_held = 0;
   int fast_path_last = 0;
-  int seg_mode = 0, seg_layer = 0;   // sweep kernels: z-segment subset of the next launch (comm.cu overlap), 0 = all
+  // sweep kernels: node-layer subset of the next launch (comm.cu overlap): 0 all, 1 layers >= seg_layer (hold what goes to
+  // a peer), 3 layers < seg_lo (hold what a peer adds to), 2 the layers in between
+  int seg_mode = 0, seg_layer = 0, seg_lo = 0;
 
   // per-kernel profiling (events around each launch of the last numeric call)
   bool profiling = false;

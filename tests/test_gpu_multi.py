@@ -42,6 +42,11 @@ def _worker(rank, world, port, cells, dom, q):
         for rep in range(2):
             eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
             results.append((eng.copy_nzval(), eng.copy_vector()))
+        for early in ("0", "1"):     # unpack after the whole sweep / concurrently with its middle (forced both ways)
+            os.environ["GTK_EARLY_UNPACK"] = early
+            eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+            results.append((eng.copy_nzval(), eng.copy_vector()))
+        del os.environ["GTK_EARLY_UNPACK"]
         # the same two ways over NCCL instead of peer memory (both transports are set up by attach): bitwise equal
         assert eng.comm_ghost_info(3) == 1, "peer-memory transport not active"
         os.environ["GTK_DISABLE_P2P"] = "1"
