@@ -74,16 +74,17 @@ def _worker(rank, world, port, cells, dom, q):
         q.put((rank, traceback.format_exc(), -1))
 
 
-@pytest.mark.parametrize("cells", [(6, 5, 8), (20, 12, 17), (33, 18, 60)])
-def test_two_gpu_ghost_rows_match_single_domain(cells):
+@pytest.mark.parametrize("cells,world", [((6, 5, 8), 2), ((20, 12, 17), 2), ((33, 18, 60), 2), ((18, 11, 41), 4)])
+def test_multi_gpu_ghost_rows_match_single_domain(cells, world):
+    """world = 4 has interior ranks that both send and receive (top, bottom and middle parts of the overlapped sweep)."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, cells, (0, 1, 0, 1, 0, 2), q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cells, (0, 1, 0, 1, 0, 2), q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
