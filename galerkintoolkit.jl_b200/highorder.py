@@ -1,4 +1,5 @@
-"""Order >= 2 Lagrange dof maps on Cartesian / simplexified Cartesian meshes (host-side input preparation).
+"""Order >= 2 Lagrange dof maps by lattice rank (host-side input preparation) — used for SIMPLEXIFIED meshes only; quad /
+hex meshes get the reference's own numbering from refnumbering.py.
 
 ``cell_dofs`` is an INPUT of the C ABI: in production the Julia host passes ``face_dofs(V)`` as the reference
 numbers it (face-complex construction, space.jl:299-535, topology.jl:1594-1704).  That

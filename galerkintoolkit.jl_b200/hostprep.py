@@ -345,13 +345,19 @@ def lagrange_space(mesh: Mesh, order: int = 1, dirichlet_boundary=None,
     """GT.lagrange_space(Ω, order; dirichlet_boundary, tensor_size=Val((n_comp,))).
 
     order 1: dof = vertex id (space.jl:327-417 with one own dof per 0-face),
-    vertex ids from :func:`node_to_vertex`.  Higher orders need the face-complex
-    numbering; see :mod:`highorder` (Cartesian closed forms checked against the
-    oracle's literal restatement).
+    vertex ids from :func:`node_to_vertex`.  Order >= 2 on quad / hex meshes: the
+    reference's face-complex numbering, :mod:`refnumbering` (checked against the
+    oracle's loop-for-loop restatement).  Order >= 2 on simplexified meshes: a valid
+    lattice numbering, :mod:`highorder` (the reference's is not restated there).
     ``dirichlet_boundary``: None | "boundary" | list of box-side ids.
     Vector-valued: dof = (node-1)*n_comp + c (space.jl:1267-1271, 1506-1510).
     """
     kind = "P" if mesh.simplex else "Q"
+    if order >= 2 and not mesh.simplex and node_dof_override is None:
+        # the reference's own numbering (face complex + dimension-major offsets + face permutations), see refnumbering.py
+        from . import refnumbering
+        cell_dofs, nfree, ndiri, xf, xd = refnumbering.scalar_or_vector_dofs(mesh, order, n_comp, dirichlet_boundary)
+        return LagrangeSpace(mesh, order, n_comp, kind, cell_dofs, nfree, ndiri, free_dof_nodes=xf, dirichlet_dof_nodes=xd)
     if order == 1:
         vert = node_to_vertex(mesh).astype(np.int64)
         scal = vert[mesh.cell_nodes.astype(np.int64) - 1]          # [nc, nln] scalar dof ids

@@ -1,0 +1,197 @@
+"""The reference's dof numbering of order-k Lagrange spaces on quad / hex `cartesian_mesh`es, vectorised (host-side
+input preparation; `cell_dofs` is an input of the C ABI).
+
+What the reference does:
+  * `complexify` builds the face complex: vertex ids (topology.jl:1034-1097); then, highest dimension first, the d-faces
+    from the (d+1)-faces (generate_face_boundary, topology.jl:1594-1704): the boundary d-faces `cartesian_mesh` created
+    (cartesian_mesh.jl:117-168) keep ids 1.., every other face gets the next id when it is FIRST met looping over the
+    (d+1)-faces in id order and their local faces in reference order; its vertex list is the one seen from that first
+    parent (generate_face_vertices, topology.jl:1468-1540);
+  * `generate_dof_ids` (space.jl:299-535) numbers dofs dimension-major, then by face id; the own dofs of a face are placed
+    in a cell through the permutation that maps the face's vertex order to the cell's (topology.jl:593-666,
+    space.jl:1439-1487); Dirichlet dofs = all dofs of the cell-local (D-1)-faces lying in Γ, stable partition (:477-535).
+
+Here "first met" is computed with `np.unique(..., return_index=True)` over all (parent, local face) candidates in loop
+order instead of a loop with a dictionary — a different implementation of the same rule; `tests/test_host_side.py` checks
+it against the loop-for-loop restatement in the oracle on small meshes, orders 1-4, 2D and 3D.
+"""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+from . import hostprep as _hp
+
+# local faces of the unit n-cube as 0-based local vertices (domain.jl:188-255)
+_LFACES = {
+    (1, 0): [[0], [1]],
+    (2, 0): [[0], [1], [2], [3]], (2, 1): [[0, 1], [2, 3], [0, 2], [1, 3]],
+    (3, 0): [[i] for i in range(8)],
+    (3, 1): [[0, 1], [2, 3], [0, 2], [1, 3], [4, 5], [6, 7], [4, 6], [5, 7], [0, 4], [2, 6], [1, 5], [3, 7]],
+    (3, 2): [[0, 1, 2, 3], [4, 5, 6, 7], [0, 1, 4, 5], [2, 3, 6, 7], [0, 2, 4, 6], [1, 3, 5, 7]],
+}
+# admissible vertex permutations (domain.jl:53-100): both orders of a segment; the 8 symmetries of the square in the
+# lexicographic order of Combinatorics.permutations; identity only for d = 0 and d > 2
+_VPERMS = {0: [[0]], 1: [[0, 1], [1, 0]],
+           2: [[0, 1, 2, 3], [0, 2, 1, 3], [1, 0, 3, 2], [1, 3, 0, 2], [2, 0, 3, 1], [2, 3, 0, 1], [3, 1, 2, 0], [3, 2, 1, 0]],
+           3: [list(range(8))]}
+
+
+def _lfaces(n, d):
+    return np.array([list(range(2 ** n))] if d == n else _LFACES[(n, d)], dtype=np.int64)
+
+
+def _first_occurrence_ids(rows_sorted: np.ndarray):
+    """ids 1.. in order of first occurrence of each distinct row; -> (id per row, first row index of every id)"""
+    _, first, inv = np.unique(rows_sorted, axis=0, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")                 # unique keys by first occurrence
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    return rank[inv.reshape(-1)] + 1, first[order]
+
+
+def face_complex(mesh: _hp.Mesh):
+    """vertex lists per face dimension, cell -> faces incidence, number / group of the pre-existing boundary faces"""
+    D = mesh.D
+    cn = mesh.cell_nodes.astype(np.int64) - 1
+    vert = _hp.node_to_vertex(mesh).astype(np.int64)
+    node_to_n = np.bincount(cn.reshape(-1), minlength=mesh.n_nodes)
+    verts = {D: vert[cn]}
+    inc, n_parent, group = {}, {}, {}
+    for d in range(D - 1, 0, -1):
+        n = d + 1
+        tabD = _lfaces(D, d)
+        isb = (node_to_n[cn[:, tabD]] <= 2 ** d).all(axis=2)                       # cartesian_mesh.jl:117-168
+        pc, pl = np.nonzero(isb)
+        pv = vert[cn[pc[:, None], tabD[pl]]]                                        # parents, own vertex order
+        tab = _lfaces(n, d)
+        cand = verts[n][:, tab].reshape(-1, 2 ** d)                                 # (parent, local face) in loop order
+        rows = np.vstack([pv, cand])
+        ids, first = _first_occurrence_ids(np.sort(rows, axis=1))
+        verts[d] = rows[first]                                                      # vertex order of the first incident parent
+        inc[(n, d)] = ids[pv.shape[0]:].reshape(-1, tab.shape[0])
+        n_parent[d], group[d] = pv.shape[0], pl + 1
+        if not np.array_equal(ids[: pv.shape[0]], np.arange(1, pv.shape[0] + 1)):
+            raise ValueError("boundary faces of the parent mesh are not pairwise distinct")
+    nv = int(vert.max())
+    verts[0] = np.arange(1, nv + 1, dtype=np.int64)[:, None]
+    cell_faces = {D: np.arange(1, cn.shape[0] + 1, dtype=np.int64)[:, None], 0: verts[D]}
+    for d in range(1, D):
+        if (D, d) in inc:
+            cell_faces[d] = inc[(D, d)]
+        else:                                                                       # non-adjacent dimensions: match vertex sets
+            tab = _lfaces(D, d)
+            cand = np.sort(verts[D][:, tab].reshape(-1, 2 ** d), axis=1)
+            rows = np.vstack([np.sort(verts[d], axis=1), cand])
+            _, inv = np.unique(rows, axis=0, return_inverse=True)
+            inv = inv.reshape(-1)
+            lut = np.zeros(inv.max() + 1, dtype=np.int64)
+            lut[inv[: verts[d].shape[0]]] = np.arange(1, verts[d].shape[0] + 1)
+            cell_faces[d] = lut[inv[verts[d].shape[0]:]].reshape(-1, tab.shape[0])
+            if (cell_faces[d] == 0).any():
+                raise ValueError("a cell-local face is missing from the face complex")
+    return dict(vert=vert, verts=verts, cell_faces=cell_faces, n_parent=n_parent, group=group)
+
+
+def _lattice(d, k, interior=False):
+    rng = range(1, k) if interior else range(0, k + 1)
+    return [tuple(reversed(t)) for t in itertools.product(*[rng] * d)]
+
+
+def _map_lattice(t, k, corners):
+    """k * Σ_v M_v(t/k) X_v as integers; corners: [2^d][dim] 0/1 coordinates"""
+    d = len(t)
+    acc = np.zeros(len(corners[0]))
+    for v, X in enumerate(corners):
+        w = 1.0
+        for m in range(d):
+            w *= (t[m] / k) if (v >> m) & 1 else (1.0 - t[m] / k)
+        acc += w * np.asarray(X, dtype=np.float64)
+    return tuple(int(round(k * x)) for x in acc)
+
+
+def element_tables(D, k, n_comp):
+    """per d: dofs[d] [nlf][n_face_dofs], own[d] [nlf][n_own], perms[d] [n_perms][n_own] (0-based local dofs / positions)"""
+    node_id = {t: i for i, t in enumerate(_lattice(D, k))}
+    corner = lambda v: [(v >> m) & 1 for m in range(D)]
+    dofs, own, perms = {}, {}, {}
+    for d in range(D + 1):
+        unit = [[(v >> m) & 1 for m in range(d)] for v in range(2 ** d)]
+        inter = _lattice(d, k, interior=True) if d > 0 else [()]
+        allp = _lattice(d, k) if d > 0 else [()]
+        expand = lambda nodes: [n * n_comp + c for n in nodes for c in range(n_comp)]
+        dofs[d] = np.array([expand([node_id[_map_lattice(t, k, [corner(v) for v in lv])] for t in allp]) for lv in _lfaces(D, d)], dtype=np.int64)
+        own[d] = np.array([expand([node_id[_map_lattice(t, k, [corner(v) for v in lv])] for t in inter]) for lv in _lfaces(D, d)], dtype=np.int64)
+        pp = []
+        for P in _VPERMS[d]:
+            npm = [inter.index(_map_lattice(t, k, [unit[p] for p in P])) for t in inter] if d > 0 else [0]
+            pp.append(expand(npm))
+        perms[d] = np.array(pp, dtype=np.int64).reshape(len(_VPERMS[d]), -1)
+    return dofs, own, perms
+
+
+def scalar_or_vector_dofs(mesh: _hp.Mesh, order: int, n_comp: int = 1, dirichlet_boundary=None):
+    """-> (cell_dofs [nc, nld] signed Int32 as the reference numbers them, n_free, n_dirichlet,
+           free_dof_xyz [n_free, D], dirichlet_dof_xyz [n_dirichlet, D])"""
+    if mesh.simplex:
+        raise NotImplementedError("reference numbering is restated for quad / hex meshes")
+    D, k = mesh.D, int(order)
+    fc = face_complex(mesh)
+    dofs, own, perms = element_tables(D, k, n_comp)
+    nc = mesh.n_cells
+    nld = (k + 1) ** D * n_comp
+    cell_dofs = np.zeros((nc, nld), dtype=np.int64)
+    base = 0
+    cv = fc["verts"][D]
+    for d in range(D + 1):
+        nown = own[d].shape[1]
+        nfaces = fc["verts"][d].shape[0]
+        if nown:
+            tab = _lfaces(D, d)
+            for lf in range(tab.shape[0]):
+                face = fc["cell_faces"][d][:, lf]                                   # [nc] 1-based
+                if 0 < d < D:                                                       # permutation id (topology.jl:593-634)
+                    fv = fc["verts"][d][face - 1]                                   # [nc, 2^d]
+                    want = cv[:, tab[lf]]
+                    P = np.array(_VPERMS[d], dtype=np.int64)                        # [nP, 2^d]
+                    ok = (fv[:, P] == want[:, None, :]).all(axis=2)                 # [nc, nP]
+                    if not ok.any(axis=1).all():
+                        raise ValueError("Valid pindex not found")
+                    pindex = np.argmax(ok, axis=1)
+                else:
+                    pindex = np.zeros(nc, dtype=np.int64)
+                cell_dofs[:, own[d][lf]] = base + (face[:, None] - 1) * nown + perms[d][pindex] + 1
+        base += nfaces * nown
+    ndofs = base
+    if (cell_dofs == 0).any():
+        raise AssertionError("some local dof was not numbered")
+    tag = np.zeros(ndofs, dtype=bool)
+    if dirichlet_boundary is not None:
+        N = D - 1
+        sides = range(1, 2 * D + 1) if dirichlet_boundary == "boundary" else dirichlet_boundary
+        face_tag = np.zeros(fc["verts"][N].shape[0], dtype=bool)
+        face_tag[: fc["n_parent"][N]] = np.isin(fc["group"][N], np.asarray(list(sides), dtype=np.int64))
+        for lf in range(_lfaces(D, N).shape[0]):
+            sel = face_tag[fc["cell_faces"][N][:, lf] - 1]
+            if sel.any():
+                tag[cell_dofs[sel][:, dofs[N][lf]].reshape(-1) - 1] = True
+    # physical position of every dof (lattice of the order-times refined mesh)
+    lat = np.array(_lattice(D, k), dtype=np.int64)                                  # [nls, D]
+    npd = np.array([c + 1 for c in mesh.cells_per_dir], dtype=np.int64)
+    strides = np.cumprod(np.concatenate(([1], npd[:-1])))
+    first = mesh.cell_nodes[:, 0].astype(np.int64) - 1
+    cidx = np.stack([(first // strides[d]) % npd[d] for d in range(D)], axis=1)     # lowest corner of every cell
+    glat = k * cidx[:, None, :] + lat[None, :, :]                                   # [nc, nls, D]
+    pmin = np.array([mesh.domain[2 * d] for d in range(D)])
+    pmax = np.array([mesh.domain[2 * d + 1] for d in range(D)])
+    ext = k * (npd - 1)
+    xyz_l = pmin + (pmax - pmin) * glat / ext                                        # [nc, nls, D]
+    dof_xyz = np.zeros((ndofs, D))
+    dof_xyz[cell_dofs.reshape(-1) - 1] = np.repeat(xyz_l.reshape(-1, D), n_comp, axis=0)
+    free = np.flatnonzero(~tag)
+    diri = np.flatnonzero(tag)
+    newid = np.empty(ndofs, dtype=np.int64)
+    newid[free] = np.arange(1, free.size + 1)
+    newid[diri] = -np.arange(1, diri.size + 1)
+    return (np.ascontiguousarray(newid[cell_dofs - 1], dtype=np.int32), int(free.size), int(diri.size), dof_xyz[free], dof_xyz[diri])

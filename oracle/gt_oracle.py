@@ -539,3 +539,218 @@ def linear_problem_rhs(form_a, form_l, coords, cell_nodes, cell_dofs, n_free, n_
                          free_or_dirichlet=(FREE, DIRICHLET), **params_a)
     b = assemble_vector(form_l, coords, cell_nodes, cell_dofs, n_free, n_dirichlet, tab, n_comp=n_comp, **params_l)
     return A, Ad, spmatmul_add(Ad[0], Ad[1], Ad[2], xd, -1.0, 1.0, b)
+
+
+# ---------------------------------------------------------------------------
+# Literal face complex + order-k Lagrange dof numbering on quad / hex meshes
+# (python loops, small meshes; what `lagrange_space(Ω, k; dirichlet_boundary)` numbers for k >= 1)
+# ---------------------------------------------------------------------------
+def _cube_lfaces(n, d):
+    """local d-faces of the reference n-cube as lists of 1-based local vertices (domain.jl:188-255)"""
+    if d == n:
+        return [list(range(1, 2 ** n + 1))]
+    if n == 1:
+        return [[1], [2]]
+    return CUBE_FACES[n][d]
+
+
+def parent_boundary_faces(cell_nodes, nnodes, D, d):
+    """cartesian_mesh.jl:117-168 for one d: boundary d-faces cell-major / local-face order; -> (nodes, group = ldface)"""
+    node_to_n = [0] * (nnodes + 1)
+    for nodes in cell_nodes:
+        for n in nodes:
+            node_to_n[n] += 1
+    nmax = 2 ** d
+    faces, groups = [], []
+    for nodes in cell_nodes:
+        for ldface, lnodes in enumerate(_cube_lfaces(D, d), start=1):
+            if all(node_to_n[nodes[ln - 1]] <= nmax for ln in lnodes):
+                faces.append([nodes[ln - 1] for ln in lnodes])
+                groups.append(ldface)
+    return faces, groups
+
+
+def face_complex(cell_nodes, nnodes, D):
+    """complexify (topology.jl:1034-1125, 1468-1540, 1594-1704) of `cartesian_mesh` output (not simplexified).
+    -> dict with, per dimension d: vertices[d][face] (vertex lists), cell_faces[d][cell] (global ids in the reference
+    cell's local order), n_parent[d] / group[d] (pre-existing boundary faces keep ids 1..n_parent, group = local face id)."""
+    if all(len(c) == 2 ** D for c in cell_nodes) and len(cell_nodes) == 1:
+        pre0 = list(cell_nodes[0])
+    else:
+        pre0 = [f[0] for f in parent_boundary_faces(cell_nodes, nnodes, D, 0)[0]]
+    node_vertex = vertex_ids(cell_nodes, nnodes, pre0)
+    vertices = {D: [[node_vertex[n - 1] for n in nodes] for nodes in cell_nodes]}
+    cell_faces, n_parent, group = {}, {}, {}
+    nface_dfaces = {}
+    for d in range(D - 1, 0, -1):                 # generate_face_boundary: d-faces from (d+1)-faces
+        n = d + 1
+        pfaces, pgroups = parent_boundary_faces(cell_nodes, nnodes, D, d)
+        pverts = [[node_vertex[x - 1] for x in f] for f in pfaces]
+        ids = {frozenset(v): i + 1 for i, v in enumerate(pverts)}            # same_valid_ids: equal vertex sets
+        verts = [list(v) for v in pverts]                                    # parents keep their own vertex order
+        lfaces = _cube_lfaces(n, d)
+        inc = []
+        for nv in vertices[n]:                                               # (d+1)-faces in id order
+            row = []
+            for lv in lfaces:                                                # local d-faces in reference order
+                fv = [nv[i - 1] for i in lv]
+                key = frozenset(fv)
+                if key not in ids:                                           # first encounter: new id, appended
+                    ids[key] = len(verts) + 1
+                    verts.append(fv)                                         # vertex order of the first incident parent
+                row.append(ids[key])
+            inc.append(row)
+        vertices[d] = verts
+        nface_dfaces[(n, d)] = inc
+        n_parent[d], group[d] = len(pfaces), pgroups
+    nv = max(node_vertex)
+    vertices[0] = [[v] for v in range(1, nv + 1)]
+    for d in range(0, D + 1):                                                # face_incidence(topology, D, d)
+        if d == D:
+            cell_faces[d] = [[c + 1] for c in range(len(cell_nodes))]
+        elif d == 0:
+            cell_faces[d] = [list(v) for v in vertices[D]]
+        elif (D, d) in nface_dfaces:
+            cell_faces[d] = nface_dfaces[(D, d)]
+        else:                                                                # non-adjacent dimensions: match vertex sets
+            ids = {frozenset(v): i + 1 for i, v in enumerate(vertices[d])}
+            cell_faces[d] = [[ids[frozenset(cv[i - 1] for i in lv)] for lv in _cube_lfaces(D, d)] for cv in vertices[D]]
+    return dict(node_vertex=node_vertex, vertices=vertices, cell_faces=cell_faces, n_parent=n_parent, group=group)
+
+
+def _vertex_permutations(d):
+    """domain.jl:53-100: admissible vertex permutations of the unit d-cube, Combinatorics.permutations order;
+    only the identity for d > 2 and d == 0."""
+    if d == 0:
+        return [[1]]
+    if d > 2:
+        return [list(range(1, 2 ** d + 1))]
+    if d == 1:
+        return [[1, 2], [2, 1]]
+    # unit square, vertices (0,0),(1,0),(0,1),(1,1): |det J| at the centre must equal the reference area
+    X = [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0), (1.0, 1.0)]
+    out = []
+    for p in itertools.permutations(range(1, 5)):
+        Y = [X[i - 1] for i in p]
+        # J at (1/2,1/2) of the bilinear map: dx/da = ((Y2-Y1)+(Y4-Y3))/2, dx/db = ((Y3-Y1)+(Y4-Y2))/2
+        ja = [((Y[1][k] - Y[0][k]) + (Y[3][k] - Y[2][k])) / 2 for k in range(2)]
+        jb = [((Y[2][k] - Y[0][k]) + (Y[3][k] - Y[1][k])) / 2 for k in range(2)]
+        if abs(abs(ja[0] * jb[1] - ja[1] * jb[0]) - 1.0) < 1e-12:
+            out.append(list(p))
+    return out
+
+
+def _lattice(d, k, interior=False):
+    """multi-indices of the order-k d-cube element's nodes, first index fastest (space.jl:1127-1177)"""
+    rng = range(1, k) if interior else range(0, k + 1)
+    return [tuple(reversed(t)) for t in itertools.product(*[rng] * d)]
+
+
+def _q1_map(t, k, corners):
+    """Σ_v M_v(t/k) X_v for the d-cube with vertex coordinates `corners` (2^d tuples), returned scaled by k (integers)"""
+    d = len(t)
+    out = [0.0] * len(corners[0])
+    for v, X in enumerate(corners):
+        w = 1.0
+        for m in range(d):
+            w *= (t[m] / k) if (v >> m) & 1 else (1.0 - t[m] / k)
+        for c in range(len(X)):
+            out[c] += w * X[c]
+    return tuple(int(round(k * x)) for x in out)
+
+
+def reference_face_tables(D, k, n_comp=1):
+    """Per dimension d: for every local d-face of the order-k D-cube element
+    dofs[d][ldface]      all local dofs on the face (face_dofs, space.jl:1343-1360, 1488-1510)
+    own[d][ldface]       its own (interior) local dofs (face_own_dofs, :1374-1392)
+    perms[d][ldface]     own-dof permutation per vertex permutation id (face_own_dof_permutations, :1439-1487, 1512-1575)
+    local dof = (node-1)*n_comp + c, node-major / component-minor."""
+    cell_nodes = {t: i + 1 for i, t in enumerate(_lattice(D, k))}
+    corner = lambda v: tuple(float((v - 1) >> m & 1) for m in range(D))
+    dofs, own, perms = {}, {}, {}
+    for d in range(D + 1):
+        dofs[d], own[d], perms[d] = [], [], []
+        unit = [tuple(float((v >> m) & 1) for m in range(d)) for v in range(2 ** d)]
+        inter = _lattice(d, k, interior=True) if d > 0 else [()]
+        vperms = _vertex_permutations(d)
+        node_perms = []
+        for P in vperms:                                    # interior node iq -> interior node located at the permuted map
+            pc = [unit[p - 1] for p in P]
+            node_perms.append([inter.index(_q1_map(t, k, pc)) + 1 for t in inter] if d > 0 else [1])
+        for lv in _cube_lfaces(D, d):
+            X = [corner(v) for v in lv]
+            allnodes = [cell_nodes[_q1_map(t, k, X)] for t in (_lattice(d, k) if d > 0 else [()])]
+            inodes = [cell_nodes[_q1_map(t, k, X)] for t in inter]
+            expand = lambda nodes: [(n - 1) * n_comp + c + 1 for n in nodes for c in range(n_comp)]
+            dofs[d].append(expand(allnodes))
+            own[d].append(expand(inodes))
+            perms[d].append([[(j - 1) * n_comp + c + 1 for j in npm for c in range(n_comp)] for npm in node_perms])
+    return dofs, own, perms, vperms_by_dim(D)
+
+
+def vperms_by_dim(D):
+    return {d: _vertex_permutations(d) for d in range(D + 1)}
+
+
+def lagrange_space_literal(domain, cells_per_dir, order, dirichlet_sides=None, n_comp=1):
+    """generate_dof_ids (space.jl:299-535) on cartesian_mesh(domain, cells) with the order-k Lagrange cube element:
+    dof offsets dimension-major then by global face id (:348-370), own dofs placed through the face's permutation id
+    relative to the cell (:380-417, topology.jl:593-666), Dirichlet tagging of ALL dofs of the cell-local (D-1)-faces in Γ
+    (:477-511), stable free/Dirichlet partition (:512-524, 910-920)."""
+    D = len(cells_per_dir)
+    coords, cell_nodes = cartesian_chain(domain, cells_per_dir, False)
+    fc = face_complex(cell_nodes, coords.shape[0], D)
+    ldofs, own, perms, vperms = reference_face_tables(D, order, n_comp)
+    nld = (order + 1) ** D * n_comp
+    # offsets
+    offset, ndofs = {}, 0
+    for d in range(D + 1):
+        nown = len(own[d][0])
+        offset[d] = []
+        for _ in fc["vertices"][d]:
+            offset[d].append(ndofs)
+            ndofs += nown
+    cell_dofs = [[0] * nld for _ in cell_nodes]
+    for d in range(D + 1):
+        lfaces = _cube_lfaces(D, d)
+        for cell, cv in enumerate(fc["vertices"][D]):
+            for lface, cvertices in enumerate(lfaces):
+                face = fc["cell_faces"][d][cell][lface]
+                pindex = 0
+                if 0 < d < D:                                         # fill_face_permutation_ids! (topology.jl:593-634)
+                    fv = fc["vertices"][d][face - 1]
+                    for pi, P in enumerate(vperms[d]):
+                        if all(fv[P[c] - 1] == cv[cvertices[c] - 1] for c in range(len(cvertices))):
+                            pindex = pi
+                            break
+                    else:
+                        raise AssertionError("Valid pindex not found")
+                perm = perms[d][lface][pindex]
+                for i, own_dof in enumerate(own[d][lface]):
+                    cell_dofs[cell][own_dof - 1] = perm[i] + offset[d][face - 1]
+    # Dirichlet
+    tag = [0] * ndofs
+    if dirichlet_sides is not None:
+        N = D - 1
+        sides = set(range(1, 2 * D + 1)) if dirichlet_sides == "boundary" else set(dirichlet_sides)
+        if D == 1:
+            raise NotImplementedError
+        face_tag = [0] * len(fc["vertices"][N])
+        for f in range(fc["n_parent"][N]):                            # parent faces keep ids 1..n_parent; group = ldface
+            if fc["group"][N][f] in sides:
+                face_tag[f] = 1
+        for cell in range(len(cell_nodes)):
+            for lface in range(len(_cube_lfaces(D, N))):
+                if face_tag[fc["cell_faces"][N][cell][lface] - 1]:
+                    for ld in ldofs[N][lface]:
+                        tag[cell_dofs[cell][ld - 1] - 1] = 1
+    free = [i for i in range(ndofs) if tag[i] == 0]
+    diri = [i for i in range(ndofs) if tag[i] != 0]
+    newid = [0] * ndofs
+    for i, dof in enumerate(free):
+        newid[dof] = i + 1
+    for i, dof in enumerate(diri):
+        newid[dof] = -(i + 1)
+    out = [[newid[x - 1] for x in row] for row in cell_dofs]
+    return dict(coords=coords, cell_nodes=np.array(cell_nodes, dtype=np.int32), cell_dofs=np.array(out, dtype=np.int32),
+                n_free=len(free), n_dirichlet=len(diri), n_dofs=ndofs, face_complex=fc)

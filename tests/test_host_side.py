@@ -179,3 +179,36 @@ def test_boundary_faces_follow_cartesian_mesh_order_and_neumann_total():
             assert abs(b.sum() - area) < 1e-12 * area
     with pytest.raises(ValueError):
         H.boundary_faces(H.cartesian_mesh((0, 1, 0, 1), (3, 1)))     # cartesian_mesh.jl:98-100
+
+
+@pytest.mark.parametrize("cells,domain", [((3, 2), (0, 1, 0, 1)), ((4, 3), (0, 2, 0, 1)), ((2, 3, 2), (0, 1, 0, 1, 0, 1)), ((3, 3, 3), (0, 1, 0, 1, 0, 1)),
+                                          ((1, 1, 1), (0, 1, 0, 1, 0, 1)), ((4, 2, 3), (0, 1, 0, 2, 0, 1))])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_high_order_numbering_matches_literal_face_complex(cells, domain, order):
+    """hostprep (vectorised, first occurrence by np.unique) against the oracle's loop-for-loop restatement of complexify +
+    generate_dof_ids (topology.jl:1034-1125, 1468-1704; space.jl:299-535) — SURVEY.md A.3-A.5.  Also: the numbering is
+    conforming (a dof shared by two cells sits at one physical point) and Dirichlet dofs are exactly those on Γ."""
+    import importlib
+    R = importlib.import_module("galerkintoolkit_jl_b200.refnumbering")
+    mesh = H.cartesian_mesh(domain, cells)
+    D = len(cells)
+    for bc in (None, "boundary", [1, 4]):
+        for n_comp in (1, 2):
+            lit = O.lagrange_space_literal(domain, cells, order, bc, n_comp=n_comp)
+            cd, nf, nd, xf, xd = R.scalar_or_vector_dofs(mesh, order, n_comp, bc)
+            assert np.array_equal(cd, lit["cell_dofs"]) and (nf, nd) == (lit["n_free"], lit["n_dirichlet"])
+            if order == 1:      # consistent with the separate Q1 restatement
+                assert np.array_equal(cd, O.q1_space(domain, cells, bc, n_comp=n_comp)["cell_dofs"])
+    V = H.lagrange_space(mesh, order, [1, 4])
+    # conformity + geometry of the Dirichlet set through the dof coordinates hostprep reports
+    lat = np.array(O._lattice(D, order), dtype=np.float64) / order
+    X = mesh.node_coordinates[mesh.cell_nodes.astype(np.int64) - 1]                 # [nc, 2^D, D]
+    lo, hi = X[:, 0, :], X[:, -1, :]
+    xl = lo[:, None, :] + lat[None, :, :] * (hi - lo)[:, None, :]                    # dof positions per cell
+    d = V.cell_dofs
+    idx = np.abs(d) - 1
+    got = np.where((d > 0)[..., None], V.free_dof_nodes[np.minimum(idx, V.n_free - 1)],
+                   V.dirichlet_dof_nodes[np.minimum(idx, V.n_dirichlet - 1)])
+    assert np.allclose(got, xl, atol=1e-13)
+    on = (np.abs(xl[..., D - 1] - domain[2 * (D - 1)]) < 1e-13) | (np.abs(xl[..., D - 2] - domain[2 * (D - 2) + 1]) < 1e-13)   # sides 1 and 4
+    assert np.array_equal(d < 0, on)
