@@ -54,6 +54,8 @@ def _first_occurrence_ids(rows_sorted: np.ndarray):
 def face_complex(mesh: _hp.Mesh):
     """vertex lists per face dimension, cell -> faces incidence, number / group of the pre-existing boundary faces"""
     D = mesh.D
+    if any(c != 1 for c in mesh.cells_per_dir) and any(c < 2 for c in mesh.cells_per_dir):
+        raise ValueError("At least 2 cells in any direction (or 1 cell in all directions)")   # cartesian_mesh.jl:98-100
     cn = mesh.cell_nodes.astype(np.int64) - 1
     vert = _hp.node_to_vertex(mesh).astype(np.int64)
     node_to_n = np.bincount(cn.reshape(-1), minlength=mesh.n_nodes)

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 CASES = [
     # cells, order, simplexify, bc, warp      -> template instance
     ((4, 3, 3), 3, False, "boundary", 0.15),   # Q3: 8 warps, 48 k-steps
-    ((2, 2, 1), 3, False, None, 0.0),          # Q3, no Dirichlet, affine
+    ((2, 2, 2), 3, False, None, 0.0),          # Q3, no Dirichlet, affine
     ((5, 4, 3), 2, False, [1, 4], 0.2),        # Q2: 27 dofs padded to 32, 27 points padded to 28
     ((4, 4, 3), 2, True, "boundary", 0.2),     # P2 tets: 10 dofs padded to 16, 11 points padded to 12
     ((5, 3, 4), 1, True, [2], 0.2),            # P1 tets
