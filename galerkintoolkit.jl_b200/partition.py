@@ -236,16 +236,33 @@ def attach(engine, part: SlabPart, tab, dist):
     for peer in sorted(plan):
         pl = plan[peer]
         engine.comm_set_exchange(peer, pl["send_nz"], pl["send_rows"], pl["recv_nz"], pl["recv_rows"])
-    # peer-memory transport: swap the CUDA IPC handles of the receive blocks (NCCL stays as the fallback)
+    # peer-memory transport: swap the CUDA IPC handles of the receive blocks (NCCL stays as the fallback).  Every rank must
+    # end up on the same transport, so the outcome of the imports is agreed on collectively: if any rank could not map a
+    # peer's block (no peer access between two GPUs, IPC disabled in a container, ...) all ranks stay on NCCL.
     if os.environ.get("GTK_DISABLE_P2P") is None:
+        a2a = torch_alltoall_objects(dist)
+        ok, why = True, ""
         outbox = [None] * part.world
-        for peer in plan:
-            outbox[peer] = engine.comm_p2p_export(peer)
-        inbox = torch_alltoall_objects(dist)(outbox)
-        for peer in plan:
-            if inbox[peer] is None:
-                raise RuntimeError(f"rank {part.rank}: peer {peer} did not export a receive block")
-            engine.comm_p2p_import(peer, inbox[peer])
+        try:
+            for peer in plan:
+                outbox[peer] = engine.comm_p2p_export(peer)
+        except Exception as exc:        # noqa: BLE001 - reported below, decided collectively
+            ok, why = False, f"export: {exc}"
+        inbox = a2a(outbox)
+        if ok:
+            try:
+                for peer in plan:
+                    if inbox[peer] is None:
+                        raise RuntimeError(f"peer {peer} did not export a receive block")
+                    engine.comm_p2p_import(peer, inbox[peer])
+            except Exception as exc:    # noqa: BLE001
+                ok, why = False, f"import: {exc}"
+        verdicts = a2a([(ok, why)] * part.world)
+        if not all(v[0] for v in verdicts):
+            os.environ["GTK_DISABLE_P2P"] = "1"      # read by the library at every exchange
+            if part.rank == 0:
+                bad = [(r, v[1]) for r, v in enumerate(verdicts) if not v[0]]
+                print(f"[gtk] peer-memory transport unavailable ({bad}); ghost rows go over NCCL", flush=True)
     owned = owned_rows_mask(part)
     n_owned_nnz = int(owned[rowval.astype(np.int64) - 1].sum())
     return colptr, rowval, n_owned_nnz
