@@ -449,7 +449,9 @@ def main():
                                    (f"3D Poisson Q1 hex {cells[0]}x{cells[1]}x{cells[2]} cells per GPU (z-slab; 512x512x64 is one GPU's "
                                     f"share of BASELINE config 5), full Dirichlet boundary, matrix+RHS numeric assembly on a cached pattern"),
                        "cells_per_gpu": int(mesh.n_cells) if cells else n ** 3, "nnz_per_gpu": nnz_local, "free_dofs_per_gpu": V.n_free,
-                       "partition": "none" if world == 1 else f"{world} z-slabs of {n}^3 cells, NCCL ghost-row sum ({eng.comm_ghost_info(2)} B/step on rank 0)",
+                       "partition": "none" if world == 1 else (f"{world} z-slabs of " + (f"{cells[0]}x{cells[1]}x{cells[2]}" if cells else f"{n}^3") +
+                                                                  f" cells, ghost-row sum over " + ("peer memory (NVLink stores + flags)" if eng.comm_ghost_info(3) == 1 else "NCCL send/recv") +
+                                                                  f", overlapped with the sweep ({eng.comm_ghost_info(2)} B/step on rank 0)"),
                        "l2": "per-step traffic (>0.6 GB) exceeds the 126 MB L2; no explicit flush",
                        "fast_path": eng.info(5)},
             "symbolic_ms": symbolic_ms, "symbolic_first_ms": symbolic_first_ms,
