@@ -345,15 +345,14 @@ def lagrange_space(mesh: Mesh, order: int = 1, dirichlet_boundary=None,
     """GT.lagrange_space(Ω, order; dirichlet_boundary, tensor_size=Val((n_comp,))).
 
     order 1: dof = vertex id (space.jl:327-417 with one own dof per 0-face),
-    vertex ids from :func:`node_to_vertex`.  Order >= 2 on quad / hex meshes: the
-    reference's face-complex numbering, :mod:`refnumbering` (checked against the
-    oracle's loop-for-loop restatement).  Order >= 2 on simplexified meshes: a valid
-    lattice numbering, :mod:`highorder` (the reference's is not restated there).
+    vertex ids from :func:`node_to_vertex`.  Order >= 2 (quad / hex and simplexified
+    meshes): the reference's face-complex numbering, :mod:`refnumbering` (checked
+    against the oracle's loop-for-loop restatement).
     ``dirichlet_boundary``: None | "boundary" | list of box-side ids.
     Vector-valued: dof = (node-1)*n_comp + c (space.jl:1267-1271, 1506-1510).
     """
     kind = "P" if mesh.simplex else "Q"
-    if order >= 2 and not mesh.simplex and node_dof_override is None:
+    if order >= 2 and node_dof_override is None:
         # the reference's own numbering (face complex + dimension-major offsets + face permutations), see refnumbering.py
         from . import refnumbering
         cell_dofs, nfree, ndiri, xf, xd = refnumbering.scalar_or_vector_dofs(mesh, order, n_comp, dirichlet_boundary)
@@ -372,8 +371,7 @@ def lagrange_space(mesh: Mesh, order: int = 1, dirichlet_boundary=None,
             tag_scal = boundary_node_mask(mesh, sides)[dof_node]
         dof_xyz = mesh.node_coordinates[dof_node]
     else:
-        from . import highorder
-        scal, n_scal, tag_scal, dof_xyz = highorder.scalar_dofs(mesh, order, dirichlet_boundary)
+        raise ValueError("order must be >= 1 (order >= 2 is numbered by refnumbering.py above)")
     if n_comp == 1:
         all_dofs, ndofs, tag = scal, n_scal, tag_scal
         dof_scalar = np.arange(n_scal)

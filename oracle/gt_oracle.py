@@ -570,52 +570,125 @@ def parent_boundary_faces(cell_nodes, nnodes, D, d):
     return faces, groups
 
 
-def face_complex(cell_nodes, nnodes, D):
-    """complexify (topology.jl:1034-1125, 1468-1540, 1594-1704) of `cartesian_mesh` output (not simplexified).
-    -> dict with, per dimension d: vertices[d][face] (vertex lists), cell_faces[d][cell] (global ids in the reference
-    cell's local order), n_parent[d] / group[d] (pre-existing boundary faces keep ids 1..n_parent, group = local face id)."""
-    if all(len(c) == 2 ** D for c in cell_nodes) and len(cell_nodes) == 1:
-        pre0 = list(cell_nodes[0])
-    else:
-        pre0 = [f[0] for f in parent_boundary_faces(cell_nodes, nnodes, D, 0)[0]]
-    node_vertex = vertex_ids(cell_nodes, nnodes, pre0)
-    vertices = {D: [[node_vertex[n - 1] for n in nodes] for nodes in cell_nodes]}
-    cell_faces, n_parent, group = {}, {}, {}
+SIMPLEX_LFACES = {   # domain.jl:389-470 (face_nodes of mesh(::UnitSimplex{n}))
+    1: {0: [[1], [2]]},
+    2: {0: [[1], [2], [3]], 1: [[1, 2], [1, 3], [2, 3]]},
+    3: {0: [[1], [2], [3], [4]], 1: [[1, 2], [1, 3], [2, 3], [1, 4], [2, 4], [3, 4]], 2: [[1, 2, 3], [1, 2, 4], [1, 3, 4], [2, 3, 4]]},
+}
+
+
+def _simplex_lfaces(n, d):
+    return [list(range(1, n + 2))] if d == n else SIMPLEX_LFACES[n][d]
+
+
+def _complex(cell_vertices, D, lfaces, parents, n_vertices):
+    """complexify's face generation (generate_face_boundary topology.jl:1594-1704 + generate_face_vertices :1468-1540):
+    d-faces from (d+1)-faces, highest d first; pre-existing faces `parents[d]` (vertex lists) keep ids 1.., every other
+    face gets the next id at its first encounter looping over the (d+1)-faces in id order and their local faces in
+    reference order, with the vertex order seen from that first parent.  -> vertices[d], cell_faces[d]."""
+    vertices = {D: [list(v) for v in cell_vertices]}
     nface_dfaces = {}
-    for d in range(D - 1, 0, -1):                 # generate_face_boundary: d-faces from (d+1)-faces
+    for d in range(D - 1, 0, -1):
         n = d + 1
-        pfaces, pgroups = parent_boundary_faces(cell_nodes, nnodes, D, d)
-        pverts = [[node_vertex[x - 1] for x in f] for f in pfaces]
-        ids = {frozenset(v): i + 1 for i, v in enumerate(pverts)}            # same_valid_ids: equal vertex sets
-        verts = [list(v) for v in pverts]                                    # parents keep their own vertex order
-        lfaces = _cube_lfaces(n, d)
+        ids = {frozenset(v): i + 1 for i, v in enumerate(parents.get(d, []))}            # same_valid_ids: equal vertex sets
+        assert len(ids) == len(parents.get(d, [])), "pre-existing faces are not pairwise distinct"
+        verts = [list(v) for v in parents.get(d, [])]
         inc = []
-        for nv in vertices[n]:                                               # (d+1)-faces in id order
+        for nv in vertices[n]:
             row = []
-            for lv in lfaces:                                                # local d-faces in reference order
+            for lv in lfaces(n, d):
                 fv = [nv[i - 1] for i in lv]
                 key = frozenset(fv)
-                if key not in ids:                                           # first encounter: new id, appended
+                if key not in ids:
                     ids[key] = len(verts) + 1
-                    verts.append(fv)                                         # vertex order of the first incident parent
+                    verts.append(fv)
                 row.append(ids[key])
             inc.append(row)
         vertices[d] = verts
         nface_dfaces[(n, d)] = inc
-        n_parent[d], group[d] = len(pfaces), pgroups
-    nv = max(node_vertex)
-    vertices[0] = [[v] for v in range(1, nv + 1)]
+    vertices[0] = [[v] for v in range(1, n_vertices + 1)]
+    cell_faces = {}
     for d in range(0, D + 1):                                                # face_incidence(topology, D, d)
         if d == D:
-            cell_faces[d] = [[c + 1] for c in range(len(cell_nodes))]
+            cell_faces[d] = [[c + 1] for c in range(len(cell_vertices))]
         elif d == 0:
             cell_faces[d] = [list(v) for v in vertices[D]]
         elif (D, d) in nface_dfaces:
             cell_faces[d] = nface_dfaces[(D, d)]
         else:                                                                # non-adjacent dimensions: match vertex sets
             ids = {frozenset(v): i + 1 for i, v in enumerate(vertices[d])}
-            cell_faces[d] = [[ids[frozenset(cv[i - 1] for i in lv)] for lv in _cube_lfaces(D, d)] for cv in vertices[D]]
+            cell_faces[d] = [[ids[frozenset(cv[i - 1] for i in lv)] for lv in lfaces(D, d)] for cv in vertices[D]]
+    return vertices, cell_faces
+
+
+def face_complex(cell_nodes, nnodes, D):
+    """complexify (topology.jl:1034-1125, 1468-1540, 1594-1704) of `cartesian_mesh` output (not simplexified).
+    -> dict with, per dimension d: vertices[d][face] (vertex lists), cell_faces[d][cell] (global ids in the reference
+    cell's local order), n_parent[d] / group[d] (pre-existing boundary faces keep ids 1..n_parent, group = local face id)."""
+    if len(cell_nodes) == 1:
+        pre0 = list(cell_nodes[0])
+    else:
+        pre0 = [f[0] for f in parent_boundary_faces(cell_nodes, nnodes, D, 0)[0]]
+    node_vertex = vertex_ids(cell_nodes, nnodes, pre0)
+    parents, n_parent, group = {}, {}, {}
+    for d in range(1, D):
+        pfaces, pgroups = parent_boundary_faces(cell_nodes, nnodes, D, d)
+        parents[d] = [[node_vertex[x - 1] for x in f] for f in pfaces]
+        n_parent[d], group[d] = len(pfaces), pgroups
+    vertices, cell_faces = _complex([[node_vertex[n - 1] for n in nodes] for nodes in cell_nodes], D, _cube_lfaces, parents,
+                                    max(node_vertex))
     return dict(node_vertex=node_vertex, vertices=vertices, cell_faces=cell_faces, n_parent=n_parent, group=group)
+
+
+def simplexified_unit_cube(D):
+    """simplexify(::UnitNCube) (domain.jl:270-320): the 2 / 6 simplices of the cube (:322-336) complexified WITHOUT
+    pre-existing faces (vertex id = node id), and per cube-local d-face the simplex d-faces lying in it, ascending ids.
+    -> face_nodes[d] (1-based cube-local nodes), groups[d][cube ldface-1] = [simplex d-face ids]"""
+    cells = SIMPLEX_NODES[D]
+    vertices, _ = _complex(cells, D, _simplex_lfaces, {}, 2 ** D)
+    groups = {}
+    for d in range(0, D):
+        groups[d] = []
+        for cnodes in _cube_lfaces(D, d):
+            groups[d].append([i + 1 for i, sn in enumerate(vertices[d]) if all(n in cnodes for n in sn)])
+    return vertices, groups
+
+
+def simplex_parent_boundary_faces(hex_cell_nodes, nnodes, D, d):
+    """structured_simplex_mesh_with_boundary (cartesian_mesh.jl:330-461) for one d: for every boundary local d-face of
+    every HEX cell (same test as the hex mesh, on the hex chain), its simplex sub-faces in ascending id."""
+    ref_nodes, ref_groups = simplexified_unit_cube(D)
+    node_to_n = [0] * (nnodes + 1)
+    for nodes in hex_cell_nodes:
+        for n in nodes:
+            node_to_n[n] += 1
+    nmax = 2 ** d
+    faces, groups = [], []
+    for nodes in hex_cell_nodes:
+        for ldface, lnodes in enumerate(_cube_lfaces(D, d), start=1):
+            if all(node_to_n[nodes[ln - 1]] <= nmax for ln in lnodes):
+                for sface in ref_groups[d][ldface - 1]:
+                    faces.append([nodes[ln - 1] for ln in ref_nodes[d][sface - 1]])
+                    groups.append(ldface)
+    return faces, groups
+
+
+def simplex_face_complex(domain, cells_per_dir):
+    """complexify of cartesian_mesh(domain, cells; simplexify=true)"""
+    D = len(cells_per_dir)
+    coords, hex_cells = cartesian_chain(domain, cells_per_dir, False)
+    _, cell_nodes = cartesian_chain(domain, cells_per_dir, True)
+    nn = coords.shape[0]
+    pre0 = [f[0] for f in simplex_parent_boundary_faces(hex_cells, nn, D, 0)[0]]
+    node_vertex = vertex_ids(cell_nodes, nn, pre0)
+    parents, n_parent, group = {}, {}, {}
+    for d in range(1, D):
+        pfaces, pgroups = simplex_parent_boundary_faces(hex_cells, nn, D, d)
+        parents[d] = [[node_vertex[x - 1] for x in f] for f in pfaces]
+        n_parent[d], group[d] = len(pfaces), pgroups
+    vertices, cell_faces = _complex([[node_vertex[n - 1] for n in nodes] for nodes in cell_nodes], D, _simplex_lfaces, parents,
+                                    max(node_vertex))
+    return coords, cell_nodes, dict(node_vertex=node_vertex, vertices=vertices, cell_faces=cell_faces, n_parent=n_parent, group=group)
 
 
 def _vertex_permutations(d):
@@ -659,49 +732,94 @@ def _q1_map(t, k, corners):
     return tuple(int(round(k * x)) for x in out)
 
 
-def reference_face_tables(D, k, n_comp=1):
-    """Per dimension d: for every local d-face of the order-k D-cube element
+def _simplex_lattice(d, k, interior=False):
+    """exponents of the order-k d-simplex element's nodes (sum <= k, first index fastest; space.jl:1127-1177);
+    interior: every barycentric coordinate >= 1"""
+    out = []
+    for t in itertools.product(*[range(k + 1)] * d):
+        e = tuple(reversed(t))
+        if sum(e) > k:
+            continue
+        if interior and (any(x < 1 for x in e) or sum(e) > k - 1):
+            continue
+        out.append(e)
+    return out
+
+
+def _p1_map(t, k, corners):
+    """k * Σ_v M_v(t/k) X_v for the d-simplex with vertex coordinates `corners` (d+1 tuples): barycentric map, integers"""
+    X0 = corners[0]
+    out = [k * x for x in X0]
+    for m, tm in enumerate(t):
+        for c in range(len(X0)):
+            out[c] += tm * (corners[m + 1][c] - X0[c])
+    return tuple(int(round(x)) for x in out)
+
+
+def _simplex_vertex_permutations(d):
+    """domain.jl:53-77: every permutation is admissible for a simplex (Combinatorics.permutations order), identity for d > 2"""
+    if d == 0:
+        return [[1]]
+    if d > 2:
+        return [list(range(1, d + 2))]
+    return [list(p) for p in itertools.permutations(range(1, d + 2))]
+
+
+def reference_face_tables(D, k, n_comp=1, simplex=False):
+    """Per dimension d: for every local d-face of the order-k reference element (D-cube, or D-simplex)
     dofs[d][ldface]      all local dofs on the face (face_dofs, space.jl:1343-1360, 1488-1510)
     own[d][ldface]       its own (interior) local dofs (face_own_dofs, :1374-1392)
     perms[d][ldface]     own-dof permutation per vertex permutation id (face_own_dof_permutations, :1439-1487, 1512-1575)
     local dof = (node-1)*n_comp + c, node-major / component-minor."""
-    cell_nodes = {t: i + 1 for i, t in enumerate(_lattice(D, k))}
-    corner = lambda v: tuple(float((v - 1) >> m & 1) for m in range(D))
-    dofs, own, perms = {}, {}, {}
+    if simplex:
+        lattice, fmap, lfaces, vpf = _simplex_lattice, _p1_map, _simplex_lfaces, _simplex_vertex_permutations
+        corner = lambda v: tuple(1.0 if v - 2 == m else 0.0 for m in range(D))          # v1 = 0, v_{m+2} = e_m
+        unit_of = lambda d: [tuple(1.0 if v - 1 == m else 0.0 for m in range(d)) for v in range(d + 1)]
+    else:
+        lattice, fmap, lfaces, vpf = _lattice, _q1_map, _cube_lfaces, _vertex_permutations
+        corner = lambda v: tuple(float((v - 1) >> m & 1) for m in range(D))
+        unit_of = lambda d: [tuple(float((v >> m) & 1) for m in range(d)) for v in range(2 ** d)]
+    cell_nodes = {t: i + 1 for i, t in enumerate(lattice(D, k))}
+    dofs, own, perms, vperms = {}, {}, {}, {}
     for d in range(D + 1):
         dofs[d], own[d], perms[d] = [], [], []
-        unit = [tuple(float((v >> m) & 1) for m in range(d)) for v in range(2 ** d)]
-        inter = _lattice(d, k, interior=True) if d > 0 else [()]
-        vperms = _vertex_permutations(d)
+        unit = unit_of(d)
+        inter = lattice(d, k, interior=True) if d > 0 else [()]
+        vperms[d] = vpf(d)
         node_perms = []
-        for P in vperms:                                    # interior node iq -> interior node located at the permuted map
+        for P in vperms[d]:                                 # interior node iq -> interior node located at the permuted map
             pc = [unit[p - 1] for p in P]
-            node_perms.append([inter.index(_q1_map(t, k, pc)) + 1 for t in inter] if d > 0 else [1])
-        for lv in _cube_lfaces(D, d):
+            node_perms.append([inter.index(fmap(t, k, pc)) + 1 for t in inter] if d > 0 else [1])
+        for lv in lfaces(D, d):
             X = [corner(v) for v in lv]
-            allnodes = [cell_nodes[_q1_map(t, k, X)] for t in (_lattice(d, k) if d > 0 else [()])]
-            inodes = [cell_nodes[_q1_map(t, k, X)] for t in inter]
+            allnodes = [cell_nodes[fmap(t, k, X)] for t in (lattice(d, k) if d > 0 else [()])]
+            inodes = [cell_nodes[fmap(t, k, X)] for t in inter]
             expand = lambda nodes: [(n - 1) * n_comp + c + 1 for n in nodes for c in range(n_comp)]
             dofs[d].append(expand(allnodes))
             own[d].append(expand(inodes))
             perms[d].append([[(j - 1) * n_comp + c + 1 for j in npm for c in range(n_comp)] for npm in node_perms])
-    return dofs, own, perms, vperms_by_dim(D)
+    return dofs, own, perms, vperms
 
 
 def vperms_by_dim(D):
     return {d: _vertex_permutations(d) for d in range(D + 1)}
 
 
-def lagrange_space_literal(domain, cells_per_dir, order, dirichlet_sides=None, n_comp=1):
+def lagrange_space_literal(domain, cells_per_dir, order, dirichlet_sides=None, n_comp=1, simplexify=False):
     """generate_dof_ids (space.jl:299-535) on cartesian_mesh(domain, cells) with the order-k Lagrange cube element:
     dof offsets dimension-major then by global face id (:348-370), own dofs placed through the face's permutation id
     relative to the cell (:380-417, topology.jl:593-666), Dirichlet tagging of ALL dofs of the cell-local (D-1)-faces in Γ
     (:477-511), stable free/Dirichlet partition (:512-524, 910-920)."""
     D = len(cells_per_dir)
-    coords, cell_nodes = cartesian_chain(domain, cells_per_dir, False)
-    fc = face_complex(cell_nodes, coords.shape[0], D)
-    ldofs, own, perms, vperms = reference_face_tables(D, order, n_comp)
-    nld = (order + 1) ** D * n_comp
+    if simplexify:
+        coords, cell_nodes, fc = simplex_face_complex(domain, cells_per_dir)
+        lfaces_of = _simplex_lfaces
+    else:
+        coords, cell_nodes = cartesian_chain(domain, cells_per_dir, False)
+        fc = face_complex(cell_nodes, coords.shape[0], D)
+        lfaces_of = _cube_lfaces
+    ldofs, own, perms, vperms = reference_face_tables(D, order, n_comp, simplex=simplexify)
+    nld = len((_simplex_lattice if simplexify else _lattice)(D, order)) * n_comp
     # offsets
     offset, ndofs = {}, 0
     for d in range(D + 1):
@@ -712,7 +830,7 @@ def lagrange_space_literal(domain, cells_per_dir, order, dirichlet_sides=None, n
             ndofs += nown
     cell_dofs = [[0] * nld for _ in cell_nodes]
     for d in range(D + 1):
-        lfaces = _cube_lfaces(D, d)
+        lfaces = lfaces_of(D, d)
         for cell, cv in enumerate(fc["vertices"][D]):
             for lface, cvertices in enumerate(lfaces):
                 face = fc["cell_faces"][d][cell][lface]
@@ -740,7 +858,7 @@ def lagrange_space_literal(domain, cells_per_dir, order, dirichlet_sides=None, n
             if fc["group"][N][f] in sides:
                 face_tag[f] = 1
         for cell in range(len(cell_nodes)):
-            for lface in range(len(_cube_lfaces(D, N))):
+            for lface in range(len(lfaces_of(D, N))):
                 if face_tag[fc["cell_faces"][N][cell][lface] - 1]:
                     for ld in ldofs[N][lface]:
                         tag[cell_dofs[cell][ld - 1] - 1] = 1

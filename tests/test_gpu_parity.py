@@ -77,9 +77,8 @@ HIGH_ORDER_CASES = [
 
 @pytest.mark.parametrize("cells,order,simplexify,n_comp,bc,warp,form,params", HIGH_ORDER_CASES)
 def test_high_order_and_simplex_parity(cells, order, simplexify, n_comp, bc, warp, form, params):
-    """Generic sort/segmented-reduce path on the elements of BASELINE configs 3 and 4 (small meshes).  The dof map is a
-    valid conforming numbering built by hostprep/highorder.py, not the reference's face-complex numbering (an input of
-    the ABI), so this pins the cell loop + scatter + compression for these elements, not the numbering."""
+    """The elements of BASELINE configs 3 and 4 (small meshes) with the reference's own face-complex dof numbering
+    (refnumbering.py, checked against the oracle's literal restatement in tests/test_host_side.py)."""
     mesh, V, tab = problem(cells, order=order, bc=bc, n_comp=n_comp, simplexify=simplexify, warp=warp)
     oform, gform = FORMS[form]
     colptr, rowval, nzval = oracle_matrix(oform, mesh, V, tab, alpha=1.25, **params)

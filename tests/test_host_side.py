@@ -199,6 +199,26 @@ def test_high_order_numbering_matches_literal_face_complex(cells, domain, order)
             assert np.array_equal(cd, lit["cell_dofs"]) and (nf, nd) == (lit["n_free"], lit["n_dirichlet"])
             if order == 1:      # consistent with the separate Q1 restatement
                 assert np.array_equal(cd, O.q1_space(domain, cells, bc, n_comp=n_comp)["cell_dofs"])
+            if order <= 3:      # simplexified mesh (cartesian_mesh.jl:265-461; simplexify(::UnitNCube) domain.jl:270-336)
+                smesh = H.cartesian_mesh(domain, cells, simplexify=True)
+                lit = O.lagrange_space_literal(domain, cells, order, bc, n_comp=n_comp, simplexify=True)
+                cd, nf, nd, xf, xd = R.scalar_or_vector_dofs(smesh, order, n_comp, bc)
+                assert np.array_equal(cd, lit["cell_dofs"]) and (nf, nd) == (lit["n_free"], lit["n_dirichlet"])
+                if order == 1:
+                    assert np.array_equal(cd, O.q1_space(domain, cells, bc, simplexify=True, n_comp=n_comp)["cell_dofs"])
+    if order >= 2:      # simplexified: dof positions hostprep reports are the barycentric lattice points of the cells
+        smesh = H.cartesian_mesh(domain, cells, simplexify=True)
+        Vs = H.lagrange_space(smesh, order, [1, 4], 1)
+        lat_s = np.array(O._simplex_lattice(D, order), dtype=np.float64) / order
+        Xs = smesh.node_coordinates[smesh.cell_nodes.astype(np.int64) - 1]              # [nc, D+1, D]
+        xs = Xs[:, None, 0, :] + np.einsum("lm,cmd->cld", lat_s, Xs[:, 1:, :] - Xs[:, :1, :])
+        ds = Vs.cell_dofs
+        ii = np.abs(ds) - 1
+        got = np.where((ds > 0)[..., None], Vs.free_dof_nodes[np.minimum(ii, Vs.n_free - 1)],
+                       Vs.dirichlet_dof_nodes[np.minimum(ii, max(Vs.n_dirichlet, 1) - 1)])
+        assert np.allclose(got, xs, atol=1e-13)
+        on = (np.abs(xs[..., D - 1] - domain[2 * (D - 1)]) < 1e-13) | (np.abs(xs[..., D - 2] - domain[2 * (D - 2) + 1]) < 1e-13)
+        assert np.array_equal(ds < 0, on)
     V = H.lagrange_space(mesh, order, [1, 4])
     # conformity + geometry of the Dirichlet set through the dof coordinates hostprep reports
     lat = np.array(O._lattice(D, order), dtype=np.float64) / order

@@ -101,7 +101,7 @@ def test_sparse_combines_duplicates_in_input_order_and_keeps_zeros():
                                                            ((3, 3), 2, True, 1), ((2, 2, 2), 2, True, 3)])
 def test_high_order_invariants(cells, order, simplexify, n_comp):
     """sum(M) = n_comp |Omega| (problems_tests.jl:56-57) and Laplacian row sums vanish without BCs, for the elements of
-    BASELINE configs 3/4 on the lattice dof numbering of hostprep/highorder.py."""
+    BASELINE configs 3/4 with the reference's face-complex dof numbering (hostprep -> refnumbering.py)."""
     import scipy.sparse as sp
     from util import oracle_matrix, problem
     mesh, V, tab = problem(cells, order=order, bc=None, n_comp=n_comp, simplexify=simplexify)
