@@ -21,7 +21,7 @@ CASES = {
     "q1_3d_4x3x3_warped_laplace": ((4, 3, 3), 1, False, 1, "boundary", 0.2, O.LAPLACE, {}),  # config 2 element, non-affine
     "q1_3d_5x4x3_nobc_laplace": ((5, 4, 3), 1, False, 1, None, 0.0, O.LAPLACE, {}),          # corner-first numbering
     "q2_2d_3x2_mass": ((3, 2), 2, False, 1, [1, 4], 0.1, O.MASS, {}),
-    "p2x3_tets_2x2x1_elasticity": ((2, 2, 1), 2, True, 3, [1], 0.1, O.ELASTICITY, dict(lam=1.0, mu=1.0)),  # config 4 element
+    "p2x3_tets_2x2x2_elasticity": ((2, 2, 2), 2, True, 3, [1], 0.1, O.ELASTICITY, dict(lam=1.0, mu=1.0)),  # config 4 element
 }
 
 
