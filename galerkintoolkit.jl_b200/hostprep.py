@@ -153,46 +153,47 @@ CUBE_FACE_LNODES = {2: [[1, 2], [3, 4], [1, 3], [2, 4]],
 
 
 def boundary_faces(mesh: Mesh, sides: Optional[Sequence[int]] = None):
-    """The (D-1)-faces `cartesian_mesh` creates on the boundary (cartesian_mesh.jl:117-168): cell-major, local faces in
-    increasing order, a local face is a boundary face iff each of its nodes belongs to at most 2^(D-1) cells; face
-    `ldface` of a cell goes to group "<D-1>-face-<ldface>".  `sides` selects groups (None = group "boundary" = all);
+    """The (D-1)-faces `cartesian_mesh` creates on the boundary (cartesian_mesh.jl:117-168; simplexified meshes :344-409,
+    sub-faces from simplexify(::UnitNCube) domain.jl:270-320): hex-cell-major, cube-local faces in increasing order,
+    simplex sub-faces in increasing id; a cube-local face is a boundary face iff each of its nodes belongs to at most
+    2^(D-1) hex cells; it goes to group "<D-1>-face-<ldface>".  `sides` selects groups (None = all, group "boundary");
     faces of a domain come in increasing face id (domain.jl:705-753).
-    -> face_nodes [nf, 2^(D-1)] int32 1-based (reference local order), face_cell [nf] 0-based, face_ldface [nf] 1-based."""
-    if mesh.simplex:
-        raise NotImplementedError("boundary faces of simplexified meshes are not restated")
-    D = mesh.D
-    if any(c != 1 for c in mesh.cells_per_dir) and any(c < 2 for c in mesh.cells_per_dir):
-        raise ValueError("At least 2 cells in any direction (or 1 cell in all directions)")   # cartesian_mesh.jl:98-100
-    cn = mesh.cell_nodes.astype(np.int64) - 1
-    node_to_n = np.bincount(cn.reshape(-1), minlength=mesh.n_nodes)
-    nmax = 2 ** (D - 1)
-    tabl = np.array(CUBE_FACE_LNODES[D], dtype=np.int64) - 1                    # [nfl, nfn]
-    isb = (node_to_n[cn[:, tabl]] <= nmax).all(axis=2)                           # [nc, nfl]
-    cell, lf = np.nonzero(isb)                                                   # C order: cell-major, ldface ascending
+    -> face_nodes [nf, n_face_nodes] int32 1-based (the face's own local order), face_cell [nf] 0-based HEX cell,
+       face_ldface [nf] 1-based cube-local face."""
+    from . import refnumbering
+    nodes, group, cell = refnumbering.boundary_face_nodes(mesh, mesh.D - 1)
     if sides is not None:
-        keep = np.isin(lf + 1, np.asarray(list(sides), dtype=np.int64))
-        cell, lf = cell[keep], lf[keep]
-    face_nodes = cn[cell[:, None], tabl[lf]] + 1
-    return np.ascontiguousarray(face_nodes, dtype=np.int32), cell.astype(np.int64), (lf + 1).astype(np.int32)
+        keep = np.isin(group, np.asarray(list(sides), dtype=np.int64))
+        nodes, group, cell = nodes[keep], group[keep], cell[keep]
+    return np.ascontiguousarray(nodes + 1, dtype=np.int32), cell.astype(np.int64), group.astype(np.int32)
 
 
-def face_local_dofs(space: "LagrangeSpace", ldface: int) -> np.ndarray:
-    """0-based local dofs of the cell that lie on local face `ldface` (1-based), in the face's own lattice order
-    (remaining axes, first fastest) — the Lagrange functions of the cell restricted to the face are exactly the face's
-    Lagrange functions in this order, all others vanish there."""
-    D, k = space.mesh.D, space.order
-    e = monomial_exponents(D, k, "Q")
-    axis = D - 1 - (ldface - 1) // 2
-    upper = (ldface - 1) % 2 == 1
-    ls = np.flatnonzero(e[:, axis] == (k if upper else 0))
-    c = np.arange(space.n_comp)
-    return (ls[:, None] * space.n_comp + c[None, :]).reshape(-1)
+def lattice_dof_map(space: "LagrangeSpace"):
+    """signed dof id of every point of the order-times refined node lattice (x fastest) and component:
+    -> (lat2dof [n_lattice_points, n_comp] int32, strides [D], k)"""
+    mesh, k, nc = space.mesh, space.order, space.n_comp
+    D = mesh.D
+    npd = np.array([c + 1 for c in mesh.cells_per_dir], dtype=np.int64)
+    strides_n = np.cumprod(np.concatenate(([1], npd[:-1])))
+    cnodes = mesh.cell_nodes.astype(np.int64) - 1
+    vidx = np.stack([(cnodes // strides_n[d]) % npd[d] for d in range(D)], axis=2)      # [nc, n_lnodes, D]
+    lat = monomial_exponents(D, k, space.kind)                                           # [nls, D] local lattice
+    if mesh.simplex:
+        glat = k * vidx[:, None, 0, :] + np.einsum("lm,cmd->cld", lat, vidx[:, 1:, :] - vidx[:, :1, :])
+    else:
+        glat = k * vidx[:, None, 0, :] + lat[None, :, :]
+    ext = k * (npd - 1) + 1
+    strides = np.cumprod(np.concatenate(([1], ext[:-1])))
+    lin = (glat * strides[None, None, :]).sum(axis=2)                                    # [nc, nls]
+    lat2dof = np.zeros((int(np.prod(ext)), nc), dtype=np.int32)
+    lat2dof[lin.reshape(-1)] = space.cell_dofs.reshape(-1, nc)
+    return lat2dof, strides, k
 
 
 @dataclass
 class FaceProblem:
     """A boundary domain handed to the engine as a mesh of (D-1)-cells embedded in D dimensions."""
-    face_nodes: np.ndarray     # [nf, 2^(D-1)] int32 1-based mesh nodes
+    face_nodes: np.ndarray     # [nf, n_face_nodes] int32 1-based mesh nodes
     face_dofs: np.ndarray      # [nf, n_lfdofs] int32 signed dofs of the space on each face
     face_cell: np.ndarray
     face_ldface: np.ndarray
@@ -200,19 +201,33 @@ class FaceProblem:
 
 
 def face_problem(space: "LagrangeSpace", sides: Optional[Sequence[int]], degree: int) -> FaceProblem:
-    """Inputs of a boundary integral ∫_Γ g v dΓ (Neumann term): measure(Γ, degree) + the space's dofs on Γ's faces."""
+    """Inputs of a boundary integral ∫_Γ g v dΓ (Neumann term): measure(Γ, degree) + the space's dofs on Γ's faces.
+    The Lagrange functions of a cell restricted to one of its faces are the face's own Lagrange functions (all others
+    vanish there), so a face's dofs are the space's dofs at the lattice points of the face, in the face's own node order
+    (its vertices as `face_nodes` lists them; Q1 / barycentric map of the reference face)."""
     mesh = space.mesh
+    D, k = mesh.D, space.order
     fn, fc, lf = boundary_faces(mesh, sides)
-    nlf = face_local_dofs(space, 1).size
-    fd = np.empty((fn.shape[0], nlf), dtype=np.int32)
-    for f in range(1, 2 * mesh.D + 1):
-        sel = lf == f
-        if sel.any():
-            fd[sel] = space.cell_dofs[fc[sel]][:, face_local_dofs(space, f)]
-    q = quadrature(mesh.D - 1, False, degree)
-    N, dN = tabulate(mesh.D - 1, space.order, "Q", q.coordinates)
-    M, dM = tabulate(mesh.D - 1, 1, "Q", q.coordinates)
-    return FaceProblem(fn, np.ascontiguousarray(fd), fc, lf, Tabulation(np.ascontiguousarray(q.weights), N, dN, M, dM, q.coordinates))
+    lat2dof, strides, _ = lattice_dof_map(space)
+    npd = np.array([c + 1 for c in mesh.cells_per_dir], dtype=np.int64)
+    strides_n = np.cumprod(np.concatenate(([1], npd[:-1])))
+    f0 = fn.astype(np.int64) - 1
+    vidx = np.stack([(f0 // strides_n[d]) % npd[d] for d in range(D)], axis=2)           # [nf, n_face_nodes, D]
+    latf = monomial_exponents(D - 1, k, space.kind)                                       # [nlf, D-1]
+    if mesh.simplex:
+        g = k * vidx[:, None, 0, :] + np.einsum("lm,fmd->fld", latf, vidx[:, 1:, :] - vidx[:, :1, :])
+    else:       # face vertices in tensor order: v0, v0 + e_a, v0 + e_b, ... -> axes from vertices 2^m
+        axes = np.stack([vidx[:, 2 ** m, :] - vidx[:, 0, :] for m in range(D - 1)], axis=1)   # [nf, D-1, D]
+        g = k * vidx[:, None, 0, :] + np.einsum("lm,fmd->fld", latf, axes)
+    lin = (g * strides[None, None, :]).sum(axis=2)                                        # [nf, nlf]
+    fd = lat2dof[lin].reshape(fn.shape[0], -1)                                            # node-major, component-minor
+    if (fd == 0).any():
+        raise AssertionError("a boundary-face lattice point carries no dof")
+    q = quadrature(D - 1, mesh.simplex, degree)
+    N, dN = tabulate(D - 1, k, space.kind, q.coordinates)
+    M, dM = tabulate(D - 1, 1, space.kind, q.coordinates)
+    return FaceProblem(fn, np.ascontiguousarray(fd, dtype=np.int32), fc, lf,
+                       Tabulation(np.ascontiguousarray(q.weights), N, dN, M, dM, q.coordinates))
 
 
 # ----------------------------------------------------------------------------

@@ -85,6 +85,31 @@ def _first_occurrence_ids(rows_sorted: np.ndarray):
     return rank[inv.reshape(-1)] + 1, first[order]
 
 
+def boundary_face_nodes(mesh: _hp.Mesh, d: int):
+    """The d-faces `cartesian_mesh` puts on the boundary (cartesian_mesh.jl:117-168; simplexified: :344-409), in face-id
+    order: cell-major over the HEX cells, local cube face ascending, (simplices: sub-face id ascending).
+    -> (nodes [nf, n_face_nodes] 0-based mesh nodes in the face's own local order, group [nf] = 1-based cube-local face,
+        hex cell [nf] 0-based)"""
+    D = mesh.D
+    sx = bool(mesh.simplex)
+    if any(c != 1 for c in mesh.cells_per_dir) and any(c < 2 for c in mesh.cells_per_dir):
+        raise ValueError("At least 2 cells in any direction (or 1 cell in all directions)")   # cartesian_mesh.jl:98-100, 331-333
+    cn = mesh.cell_nodes.astype(np.int64) - 1
+    hexn = (_hp.cartesian_mesh(mesh.domain, mesh.cells_per_dir).cell_nodes.astype(np.int64) - 1) if sx else cn
+    node_to_n = np.bincount(hexn.reshape(-1), minlength=mesh.n_nodes)
+    tabD = _lfaces(D, d)
+    isb = (node_to_n[hexn[:, tabD]] <= 2 ** d).all(axis=2)
+    pc, pl = np.nonzero(isb)                                                        # cell-major, local face ascending
+    if sx:
+        sub = _simplexified_cube_subfaces(D, d)
+        nsub = sub[0].shape[0]
+        assert all(x.shape[0] == nsub for x in sub)
+        subtab = np.stack(sub)                                                       # [n_lfaces, nsub, d+1]
+        nodes = hexn[pc[:, None, None], subtab[pl]].reshape(-1, d + 1)
+        return nodes, np.repeat(pl, nsub) + 1, np.repeat(pc, nsub)
+    return hexn[pc[:, None], tabD[pl]], pl + 1, pc
+
+
 def face_complex(mesh: _hp.Mesh):
     """vertex lists per face dimension, cell -> faces incidence, number / group of the pre-existing boundary faces"""
     D = mesh.D
@@ -100,19 +125,8 @@ def face_complex(mesh: _hp.Mesh):
     inc, n_parent, group = {}, {}, {}
     for d in range(D - 1, 0, -1):
         n = d + 1
-        tabD = _lfaces(D, d)
-        isb = (node_to_n[hexn[:, tabD]] <= 2 ** d).all(axis=2)
-        pc, pl = np.nonzero(isb)                                                    # cell-major, local face ascending
-        if sx:
-            # every boundary cube face contributes its simplex sub-faces, ascending sub-face id (same count per face)
-            sub = _simplexified_cube_subfaces(D, d)
-            nsub = sub[0].shape[0]
-            assert all(x.shape[0] == nsub for x in sub)
-            subtab = np.stack(sub)                                                   # [n_lfaces, nsub, d+1]
-            pv = vert[hexn[pc[:, None, None], subtab[pl]]].reshape(-1, d + 1)
-            pl = np.repeat(pl, nsub)
-        else:
-            pv = vert[hexn[pc[:, None], tabD[pl]]]                                   # parents, own vertex order
+        pnodes, pgroup, _ = boundary_face_nodes(mesh, d)
+        pv, pl = vert[pnodes], pgroup - 1                                            # parents, own vertex order
         tab = _lfaces(n, d, sx)
         cand = verts[n][:, tab].reshape(-1, tab.shape[1])                           # (parent, local face) in loop order
         rows = np.vstack([pv, cand])

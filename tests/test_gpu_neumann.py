@@ -33,7 +33,11 @@ def _face_engine(mesh, V, fp):
 
 
 CASES = [
-    # cells, order, dirichlet sides, neumann sides, n_comp
+    # cells, order, dirichlet sides, neumann sides, n_comp   (negative order = simplexified mesh)
+    ((6, 5), -1, [3], [4, 2], 1),            # P1 triangles
+    ((4, 3), -2, None, None, 1),             # P2 triangles
+    ((4, 3, 3), -1, [1], [2, 6], 1),         # P1 tets
+    ((3, 2, 2), -2, [5], [2, 4], 3),         # config 4 element: P2 x 3 on tets, traction on two sides
     ((7, 5), 1, [3], [4, 2], 1),
     ((4, 3), 2, None, None, 1),
     ((5, 4, 3), 1, [1], [2, 6], 1),
@@ -46,7 +50,8 @@ CASES = [
 @pytest.mark.parametrize("cells,order,diri,neu,n_comp", CASES)
 def test_neumann_vector_parity(cells, order, diri, neu, n_comp):
     D = len(cells)
-    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells)
+    simplexify, order = order < 0, abs(order)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells, simplexify=simplexify)
     _bend(mesh)
     V = H.lagrange_space(mesh, order, diri, n_comp)
     fp = H.face_problem(V, neu, 2 * order)

@@ -179,6 +179,25 @@ def test_boundary_faces_follow_cartesian_mesh_order_and_neumann_total():
             assert abs(b.sum() - area) < 1e-12 * area
     with pytest.raises(ValueError):
         H.boundary_faces(H.cartesian_mesh((0, 1, 0, 1), (3, 1)))     # cartesian_mesh.jl:98-100
+    # the dofs of a face sit at the face's own lattice points (cubes: Q1 map of the face; simplices: barycentric), and a
+    # simplexified mesh has the simplex sub-faces of every boundary cube face, cube-face order preserved
+    for simp in (False, True):
+        for order in (1, 2, 3):
+            m = H.cartesian_mesh((0, 2, 0, 1, 0, 3), (4, 3, 2), simplexify=simp)
+            V = H.lagrange_space(m, order, [1])
+            fp = H.face_problem(V, [2, 3, 6], 2 * order)
+            assert fp.face_nodes.shape[0] == (2 if simp else 1) * (4 * 3 + 4 * 2 + 3 * 2)
+            X = m.node_coordinates[fp.face_nodes.astype(np.int64) - 1]
+            lat = H.monomial_exponents(2, order, "P" if simp else "Q").astype(np.float64) / order
+            if simp:
+                xl = X[:, None, 0, :] + np.einsum("lm,fmd->fld", lat, X[:, 1:, :] - X[:, :1, :])
+            else:
+                xl = X[:, None, 0, :] + np.einsum("lm,fmd->fld", lat, np.stack([X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]], axis=1))
+            d = fp.face_dofs
+            ii = np.abs(d) - 1
+            got = np.where((d > 0)[..., None], V.free_dof_nodes[np.minimum(ii, V.n_free - 1)],
+                           V.dirichlet_dof_nodes[np.minimum(ii, V.n_dirichlet - 1)])
+            assert np.allclose(got, xl, atol=1e-13)
 
 
 @pytest.mark.parametrize("cells,domain", [((3, 2), (0, 1, 0, 1)), ((4, 3), (0, 2, 0, 1)), ((2, 3, 2), (0, 1, 0, 1, 0, 1)), ((3, 3, 3), (0, 1, 0, 1, 0, 1)),
