@@ -147,11 +147,6 @@ def boundary_node_mask(mesh: Mesh, sides: Optional[Sequence[int]] = None) -> np.
     return mask
 
 
-# local nodes of the (D-1)-faces of the reference square / cube (domain.jl:206-224, 238-255)
-CUBE_FACE_LNODES = {2: [[1, 2], [3, 4], [1, 3], [2, 4]],
-                    3: [[1, 2, 3, 4], [5, 6, 7, 8], [1, 2, 5, 6], [3, 4, 7, 8], [1, 3, 5, 7], [2, 4, 6, 8]]}
-
-
 def boundary_faces(mesh: Mesh, sides: Optional[Sequence[int]] = None):
     """The (D-1)-faces `cartesian_mesh` creates on the boundary (cartesian_mesh.jl:117-168; simplexified meshes :344-409,
     sub-faces from simplexify(::UnitNCube) domain.jl:270-320): hex-cell-major, cube-local faces in increasing order,
