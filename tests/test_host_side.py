@@ -251,3 +251,30 @@ def test_high_order_numbering_matches_literal_face_complex(cells, domain, order)
     assert np.allclose(got, xl, atol=1e-13)
     on = (np.abs(xl[..., D - 1] - domain[2 * (D - 1)]) < 1e-13) | (np.abs(xl[..., D - 2] - domain[2 * (D - 2) + 1]) < 1e-13)   # sides 1 and 4
     assert np.array_equal(d < 0, on)
+
+
+def test_every_entry_point_rejects_a_null_context(built_library):
+    """No GPU needed: a NULL ctx is an argument error (or a defined sentinel), never a crash."""
+    lib = built_library
+    z = None      # NULL for every pointer parameter
+    calls = {
+        "gtk_destroy": (z,), "gtk_set_stream": (z, z), "gtk_set_mesh": (z, 3, 0, z, 0, 8, z), "gtk_set_manifold_dim": (z, 2),
+        "gtk_set_active_cells": (z, 0, 0), "gtk_update_coordinates": (z, z), "gtk_set_space": (z, 8, 1, z, 0, 0),
+        "gtk_set_tabulation": (z, 8, z, z, z, z, z), "gtk_matrix_symbolic": (z, 1, 1, z), "gtk_matrix_pattern": (z, z, z),
+        "gtk_matrix_numeric": (z, 1, z, z), "gtk_matrix_numeric_device": (z, 1, z), "gtk_vector_symbolic": (z, 1),
+        "gtk_set_vector": (z, z), "gtk_vector_assemble": (z, 101, z, z), "gtk_vector_assemble_device": (z, 101, z),
+        "gtk_assemble_matrix_and_vector": (z, 1, z, 101, z, z, z), "gtk_assemble_matrix_and_vector_device": (z, 1, z, 101, z),
+        "gtk_select_matrix": (z, 0), "gtk_matvec_add_device": (z, 1.0, z, 1.0), "gtk_matvec_add": (z, 1.0, z, 1.0, z),
+        "gtk_device_pointer": (z, 0, z, z), "gtk_copy_nzval": (z, z), "gtk_copy_vector": (z, z), "gtk_set_profiling": (z, 1),
+        "gtk_profile_get": (z, 0, z, z), "gtk_comm_init": (z, 0, 1, z), "gtk_comm_set_exchange": (z, 1, 0, z, 0, z, 0, z, 0, z),
+        "gtk_comm_sum_ghost_rows": (z,), "gtk_assemble_and_sum_ghost_rows_device": (z, 1, z, 101, z),
+        "gtk_comm_p2p_export": (z, 0, z), "gtk_comm_p2p_import": (z, 0, z),
+    }
+    for name, args in calls.items():
+        rc = getattr(lib, name)(*args)
+        assert rc in (E.GTK_OK, E.GTK_ERR_INVALID) if name == "gtk_destroy" else rc == E.GTK_ERR_INVALID, (name, rc)
+    assert lib.gtk_info(z, 0) < 0 and lib.gtk_comm_ghost_info(z, 0) < 0 and lib.gtk_profile_count(z) <= 0
+    lib.gtk_last_error.restype = ctypes.c_char_p
+    assert b"null" in lib.gtk_last_error(z).lower()
+    covered = set(calls) | {"gtk_info", "gtk_comm_ghost_info", "gtk_profile_count", "gtk_last_error", "gtk_version", "gtk_create", "gtk_comm_unique_id"}
+    assert covered == set(E.ABI_SYMBOLS), set(E.ABI_SYMBOLS) ^ covered
