@@ -186,28 +186,42 @@ __global__ void k_struct_fill(const int32_t* __restrict__ node_dof, const int32_
     int i = (int)(node % s1), j = (int)((node / s1) % (n2 + 1)), k = (int)(node / s2);
     int rows[27];
     uint32_t mask = 0;
+    bool monotone = true;      // present rows ascend with the neighbour offset: slot(o) = number of present offsets below o
+    int prev = 0;
+#pragma unroll
     for (int o = 0; o < 27; ++o) {
       int ii = i + o % 3 - 1, jj = j + (o / 3) % 3 - 1, kk = k + o / 9 - 1;
       int r = 0;
       if (ii >= 0 && ii <= n1 && jj >= 0 && jj <= n2 && kk >= 0 && kk <= n3) r = node_dof[ii + s1 * jj + s2 * kk];
       rows[o] = r;
-      if (r > 0) mask |= 1u << o;
+      if (r > 0) {
+        mask |= 1u << o;
+        if (r < prev) monotone = false;
+        prev = r;
+      }
     }
     const int64_t p0 = colptr[col];
-    bool monotone = true;
-    uint32_t seen = 0;
+    uint32_t packed[8];        // the 32 slot bytes of the column, stored as two 16-byte words
+#pragma unroll
+    for (int q = 0; q < 8; ++q) packed[q] = 0xFFFFFFFFu;
+#pragma unroll
     for (int o = 0; o < 27; ++o) {
-      uint8_t slot = 255;
       if (rows[o] > 0) {
-        int rank = 0;   // row ids within one column are distinct (bijection checked by k_struct_count)
-        for (int u = 0; u < 27; ++u) rank += rows[u] > 0 && rows[u] < rows[o];
-        slot = (uint8_t)rank;
+        int rank;
+        if (monotone) {
+          rank = __popc(mask & ((1u << o) - 1u));
+        } else {               // rank among the present rows (row ids within one column are distinct: bijection checked before)
+          rank = 0;
+#pragma unroll
+          for (int u = 0; u < 27; ++u) rank += rows[u] > 0 && rows[u] < rows[o];
+        }
         rowval[p0 + rank] = rows[o];
-        if (rank != __popc(seen)) monotone = false;
-        seen |= 1u << o;
+        packed[o >> 2] = (packed[o >> 2] & ~(0xFFu << (8 * (o & 3)))) | ((uint32_t)rank << (8 * (o & 3)));
       }
-      slot_tbl[col * 32 + o] = slot;
     }
+    uint4* dst = reinterpret_cast<uint4*>(slot_tbl + col * 32);
+    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
     col_mask[col] = monotone ? mask : (mask | 0x80000000u);
   }
 }

@@ -528,3 +528,43 @@ def linear_problem(dirichlet_values: np.ndarray, a: Callable, l: Callable, U: Sp
     eng.select_matrix(0)
     eng.close()
     return np.zeros(A.n, dtype=np.float64), A, b
+
+
+# ---------------------------------------------------------------------------
+# Dirichlet data and solution fields (host side; space.jl:2000-2100, problems.jl:501-526)
+# ---------------------------------------------------------------------------
+def interpolate_dirichlet(g: Callable, V: Space) -> np.ndarray:
+    """GT.interpolate_dirichlet!(g, uh) for nodal Lagrange spaces: the Dirichlet value of a dof is g at its node
+    (component c of g for vector spaces; dofs are node-major / component-minor).  -> xd [n_dirichlet]"""
+    X = V.data.dirichlet_dof_nodes
+    vals = np.asarray(g(np.moveaxis(X, -1, 0)), dtype=np.float64)
+    nc = V.data.n_comp
+    if nc == 1:
+        return np.ascontiguousarray(np.broadcast_to(vals, X.shape[:1]))
+    comp = _dirichlet_component(V)
+    vals = np.broadcast_to(vals, (nc,) + X.shape[:1])
+    return np.ascontiguousarray(vals[comp, np.arange(X.shape[0])])
+
+
+def _dirichlet_component(V: Space) -> np.ndarray:
+    """component of every Dirichlet dof: local dof = node * n_comp + c in every cell (space.jl:1267-1271)"""
+    d = V.data.cell_dofs
+    nc = V.data.n_comp
+    comp = np.empty(V.data.n_dirichlet, dtype=np.int64)
+    lc = np.tile(np.arange(d.shape[1]) % nc, (d.shape[0], 1))
+    neg = d < 0
+    comp[-d[neg] - 1] = lc[neg]
+    return comp
+
+
+def solution_field(V: Space, x: np.ndarray, xd: np.ndarray) -> np.ndarray:
+    """GT.solution_field(uhd, x) restricted to what a nodal space needs: the value of every local dof of every cell,
+    free dofs from x, Dirichlet dofs from xd.  -> [n_cells, n_ldofs]"""
+    d = V.data.cell_dofs.astype(np.int64)
+    x = np.asarray(x, dtype=np.float64)
+    xd = np.asarray(xd, dtype=np.float64)
+    out = np.empty(d.shape, dtype=np.float64)
+    pos = d > 0
+    out[pos] = x[d[pos] - 1]
+    out[~pos] = xd[-d[~pos] - 1]
+    return out
