@@ -7,16 +7,17 @@
 //   Ke = Ĝᵀ · Y ,   Y[(q,a), j] = Σ_b C_q[a][b] Ĝ[(q,b), j] ,   C_q = α w_q adj(J_q) adj(J_q)ᵀ / |det J_q|
 // with Ĝ[(q,a), i] = ∂_a φ̂_i(ξ_q) the tabulated reference gradients (accessors.jl:486-496) — THE SAME matrix for
 // every cell.  So the whole mesh is one GEMM with M = n_ldofs, K = 3 n_q, N = n_ldofs · n_cells whose A operand is
-// constant: each warp keeps its 8 rows of Ĝᵀ in REGISTERS for the life of the kernel (48 doubles for Q3) and only
-// the B operand (Y, produced per cell from the 6 numbers per point of C_q) goes through shared memory.
+// constant: its DMMA fragments sit in a table in shared memory for the life of the kernel, and the B operand (Y) is
+// produced in REGISTERS by the very lanes that need it as fragments, from the 6 numbers per point of C_q — nothing but
+// C_q (TMA) is read per cell, nothing but the finished tiles is written.  Ke is symmetric: 36 of the 64 tiles are computed.
 //
 //   k_cell_metric         : one thread per (cell, point): J = Σ_n x_n ⊗ ∇̂M_n (accessors.jl:941-968), C_q -> HBM
 //                           (48 B per point; 0.8 GB at config 3, 5 % of the step's traffic)
-//   k_elem_laplace_dmma   : persistent CTAs of MT = n_ldofs/8 warps, see the comment at the kernel: K is ordered
+//   k_elem_laplace_dmma   : persistent CTAs of 2·(n_ldofs/8) independent warps, see the comment at the kernel: K is ordered
 //                           k = 4·(3·(q/4) + a) + q%4 so that one k-step of 4 is one direction a of 4 consecutive points;
-//                           lane (r, c) of warp w owns Ĝ[(q,·), 8w+r] for q ≡ c (mod 4), which are at the same time its
-//                           DMMA fragments of Ĝ and the operands it needs for column 8w+r of Y.  Result tiles go
-//                           straight from the accumulator fragments to the e-indexed staging array KE.
+//                           lane (r, c) of the warp owning column block cb computes Y[(q,·), 8cb+r] for q ≡ c (mod 4),
+//                           which is exactly its B fragment of the three k-steps of that point group.  Result tiles go
+//                           straight from the accumulator fragments to the e-indexed staging array KE (and mirrored).
 // The scatter (compress) is the generic fixed-order segmented sum k_reduce_nz of numeric.cu: no float atomics.
 //
 // Roofline: FP64 tensor pipe.  F_alg = n_cells · 2 · n_ldofs² · 3 n_q; measured DMMA peak on this
