@@ -17,7 +17,7 @@
 //   The halo ring is recomputed by the neighbouring CTA (factor (BX+1)(BY+1)/(BX BY)); in exchange
 //   every nonzero is produced by exactly one thread in a fixed order: bit-reproducible, no fix-up pass.
 //
-// k_q1hex_affine: same sweep for meshes whose cells are all EXACTLY affine (every Cartesian mesh of
+// k_q1hex_affine_w (warp-private, see its own comment below): same sweep for meshes whose cells are all EXACTLY affine (every Cartesian mesh of
 //   GT.cartesian_mesh, also graded ones): J is constant per cell, so the quadrature sum collapses to six
 //   numbers per cell (alpha w adj(J)adj(J)^T/|det J| times exact reference integrals) and a column's 27
 //   entries are integer-coefficient FMA chains over the <= 8 adjacent cells.  FP64 work drops ~5x and the
@@ -25,6 +25,9 @@
 //   comparisons (no tolerance): when the four edge vectors of each reference direction coincide bitwise,
 //   the general kernel's lerped Jacobian is the same constant at all 8 points, so both kernels evaluate
 //   the same mathematical expression on identical geometry data (results agree to rounding, ~1e-16).
+//
+// gtk_fastq1_symbolic: the symbolic phase of such meshes straight from the node lattice (pattern, slot table, column
+//   records; no COO keys, no sort), and the layer-range launches the multi-GPU exchange overlaps with (comm.cu).
 #include <utility>
 #include <cub/cub.cuh>
 #include "gtk_internal.h"
