@@ -148,3 +148,88 @@ def test_ghost_row_exchange_over_gloo_world2():
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+class _FakeEngine:
+    """Stands in for engine.Engine in attach(): pattern from the oracle, records the exchange plan and transport calls."""
+    fail_import_on_rank = None
+
+    def __init__(self, part, tabd):
+        self.part, self.tabd = part, tabd
+        self.exchanges, self.imported = {}, {}
+
+    def set_mesh(self, *a): pass
+    def set_space(self, *a): pass
+    def set_tabulation(self, *a): pass
+    def set_active_cells(self, *a): pass
+    def vector_symbolic(self, *a): pass
+
+    def matrix_symbolic(self):
+        self.colptr, self.rowval, _, _ = local_oracle(self.part, self.tabd)
+        return self.rowval.size
+
+    def matrix_pattern(self):
+        return self.colptr, self.rowval
+
+    @staticmethod
+    def comm_unique_id():
+        return b"\x00" * 128
+
+    def comm_init(self, rank, world, uid):
+        assert len(uid) == 128
+
+    def comm_set_exchange(self, peer, send_nz, send_rows, recv_nz, recv_rows):
+        self.exchanges[peer] = (send_nz.size, send_rows.size, recv_nz.size, recv_rows.size)
+
+    def comm_p2p_export(self, peer):
+        return bytes([self.part.rank, peer]) + b"\x00" * 62
+
+    def comm_p2p_import(self, peer, handle):
+        if self.part.rank == _FakeEngine.fail_import_on_rank:
+            raise RuntimeError("cudaIpcOpenMemHandle: peer access is not supported (simulated)")
+        assert handle[:2] == bytes([peer, self.part.rank])       # the block the PEER keeps for this rank
+        self.imported[peer] = handle
+
+
+def _attach_worker(rank, world, port, fail_rank, q):
+    try:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+        os.environ.pop("GTK_DISABLE_P2P", None)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        dom, cells = (0, 1, 0, 1, 0, 1), (4, 3, 9)
+        _, _, tab = problem(cells, bc="boundary", domain=dom)
+        part = P.slab_problem(dom, cells, rank, world)
+        _FakeEngine.fail_import_on_rank = fail_rank
+        eng = _FakeEngine(part, tab_dict(tab))
+        P.attach(eng, part, tab, dist)
+        peers = sorted(eng.exchanges)
+        assert peers == [p for p in (rank - 1, rank + 1) if 0 <= p < world]
+        disabled = os.environ.get("GTK_DISABLE_P2P") == "1"
+        dist.barrier(); dist.destroy_process_group()
+        q.put((rank, "ok", disabled, sorted(eng.imported)))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc(), None, None))
+
+
+@pytest.mark.parametrize("fail_rank", [None, 1])
+def test_attach_agrees_on_the_ghost_row_transport_over_gloo_world3(fail_rank):
+    """attach(): every rank exports/imports the peer blocks; if ANY rank cannot map a peer's block, ALL ranks fall back
+    to NCCL (GTK_DISABLE_P2P) — otherwise one side would push into memory the other side never polls."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 3
+    port = 29100 + (os.getpid() % 2000) + (7 if fail_rank else 0)
+    procs = [ctx.Process(target=_attach_worker, args=(r, world, port, fail_rank, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg, disabled, imported in results:
+        assert msg == "ok", f"rank {rank}: {msg}"
+        assert disabled == (fail_rank is not None)
+        if fail_rank is None:
+            assert imported == [p for p in (rank - 1, rank + 1) if 0 <= p < world]
