@@ -222,6 +222,26 @@ def cpu_baseline(n_full):
                       f"{threads} pthreads, compress serial (the reference itself is single-threaded Julia)"}
 
 
+def cpu_baseline_high_order(order=3, n=16):
+    """The same C-oracle run for BASELINE config 3's element on a bounded sample (Q3 hexahedra, n^3 cells): the
+    reference's generated loop costs n_q * n_ldofs^2 integrand evaluations per cell, which is what this times."""
+    import c_oracle
+    import gtk_b200
+    H = gtk_b200.hostprep
+    threads = os.cpu_count() or 1
+    mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (n, n, n))
+    V = H.lagrange_space(mesh, order, "boundary")
+    tab = H.measure_tabulation(V, 2 * order)
+    tabd = dict(w=tab.w, N=tab.N, dN=tab.dN, M=tab.M, dM=tab.dM)
+    cap = int(mesh.n_cells) * V.cell_dofs.shape[1] ** 2
+    t = time.perf_counter()
+    out = c_oracle.assemble(1, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, tabd, nthreads=threads, nnz_cap=cap)
+    dt = time.perf_counter() - t
+    return {"value": out[1].size / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"one full assembly of Q{order} hexahedra on {n}^3 cells ({out[1].size} nnz), {dt:.2f} s; phases(s) "
+                      f"count/loop/compress/vector={[round(float(x), 3) for x in out[4]]}; cell loop on {threads} pthreads, compress serial"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -475,6 +495,8 @@ def main():
                 eng.close()
                 eng = None
                 line["high_order"] = bench_highorder.run(64, 3, steps=5, warmup=2, device=local_rank, check=False)
+                if not args.no_cpu_baseline:
+                    line["high_order"]["cpu_baseline"] = cpu_baseline_high_order()
             except Exception as exc:   # reported, never hidden
                 line["high_order"] = {"error": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:

@@ -114,3 +114,19 @@ def test_high_order_invariants(cells, order, simplexify, n_comp):
     # every dof is shared consistently: number of dofs of the conforming space
     if not simplexify:
         assert V.n_free == n_comp * int(np.prod([order * c + 1 for c in cells]))
+
+
+@pytest.mark.parametrize("cells,order", [((3, 2, 2), 2), ((2, 2, 2), 3), ((4, 3), 3)])
+def test_c_oracle_matches_numpy_oracle_on_high_order_elements(cells, order):
+    """The C restatement is the timed CPU baseline of bench.py's high_order entry (config 3 element): same pattern and
+    values as the numpy oracle on the reference's own high-order dof numbering."""
+    import c_oracle
+    from util import oracle_matrix, oracle_vector, problem, tab_dict, assert_values_close
+    mesh, V, tab = problem(cells, order=order, bc=[1, 4], warp=0.1)
+    cp, rv, nz = oracle_matrix(O.LAPLACE, mesh, V, tab)
+    b = oracle_vector(O.SOURCE_CONST, mesh, V, tab, f_const=[1.0])
+    out = c_oracle.assemble(1, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, tab_dict(tab), nthreads=2,
+                            nnz_cap=mesh.n_cells * V.cell_dofs.shape[1] ** 2)
+    assert np.array_equal(out[0], cp) and np.array_equal(out[1], rv)
+    assert_values_close(out[2], nz)
+    assert_values_close(out[3], b)
