@@ -86,6 +86,9 @@ struct Peer {
   size_t ipc_bytes = 0;
   double* remote_block = nullptr;   // the peer's block for us, mapped with cudaIpcOpenMemHandle
   unsigned int* done_ctr = nullptr; // [2] block counters of the push / unpack kernels of this peer
+  // exchange counter of the peer-memory path WITH THIS PEER: starts at 0 together with the zero-filled flag header of a
+  // freshly created ipc_block, so replacing the plan of a pair (both sides re-export / re-import) restarts the protocol
+  unsigned long long seq = 0;
 };
 constexpr int P2P_HDR = 32;   // doubles (256 B) in front of the receive buffer
 
@@ -93,7 +96,6 @@ struct GhostPlan {
   std::vector<Peer> peers;   // sorted by rank
   cudaStream_t side = nullptr;          // pack + NCCL run here while the rest of the sweep runs on ctx->stream
   cudaEvent_t ev_first = nullptr, ev_xchg = nullptr;
-  unsigned long long seq = 0;           // exchange counter of the peer-memory path (same on every rank)
   bool p2p_ready() const {
     if (peers.empty() || getenv("GTK_DISABLE_P2P")) return false;
     for (auto& p : peers) if (!p.remote_block || !p.ipc_block) return false;
@@ -208,16 +210,24 @@ int32_t upload_idx(gtk_ctx* ctx, T** dst, const T* src, int64_t n) {
     }                                                                                          \
   } while (0)
 
-void gtk_comm_release(gtk_ctx* ctx) {
+// The exchange plan indexes nzval / b of ONE pattern: it dies with that pattern (gtk_set_mesh, gtk_set_space,
+// gtk_matrix_symbolic) so that a later gtk_comm_sum_ghost_rows cannot scatter through stale positions.  The NCCL
+// communicator survives.
+void gtk_comm_release_plan(gtk_ctx* ctx) {
   GhostPlan* g = (GhostPlan*)ctx->ghost;
-  if (g) {
-    for (auto& p : g->peers) free_peer(ctx, p);
-    if (g->side) cudaStreamDestroy(g->side);
-    if (g->ev_first) cudaEventDestroy(g->ev_first);
-    if (g->ev_xchg) cudaEventDestroy(g->ev_xchg);
-    delete g;
-    ctx->ghost = nullptr;
-  }
+  if (!g) return;
+  cudaStreamSynchronize(ctx->stream);
+  if (g->side) cudaStreamSynchronize(g->side);
+  for (auto& p : g->peers) free_peer(ctx, p);
+  if (g->side) cudaStreamDestroy(g->side);
+  if (g->ev_first) cudaEventDestroy(g->ev_first);
+  if (g->ev_xchg) cudaEventDestroy(g->ev_xchg);
+  delete g;
+  ctx->ghost = nullptr;
+}
+
+void gtk_comm_release(gtk_ctx* ctx) {
+  gtk_comm_release_plan(ctx);
   if (ctx->comm && nccl().ok) nccl().CommDestroy((ncclComm_t)ctx->comm);
   ctx->comm = nullptr;
 }
@@ -256,6 +266,14 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
       n_recv_nz < 0 || n_recv_b < 0 || (n_send_nz && !send_nz) || (n_send_b && !send_rows) || (n_recv_nz && !recv_nz) ||
       (n_recv_b && !recv_rows))
     GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_set_exchange: bad arguments");
+  if (!ctx->ms.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_set_exchange: call gtk_matrix_symbolic first (the plan indexes its nzval)");
+  {   // the kernels scatter through these positions unchecked: validate them once, here
+    const int64_t nnz = ctx->ms.nnz, nr = ctx->ms.n_rows;
+    for (int64_t i = 0; i < n_send_nz; ++i) if (send_nz[i] < 0 || send_nz[i] >= nnz) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_set_exchange: send_nz position outside [0, nnz)");
+    for (int64_t i = 0; i < n_recv_nz; ++i) if (recv_nz[i] < 0 || recv_nz[i] >= nnz) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_set_exchange: recv_nz position outside [0, nnz)");
+    for (int64_t i = 0; i < n_send_b; ++i) if (send_rows[i] < 0 || send_rows[i] >= nr) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_set_exchange: send_rows entry outside [0, n_rows)");
+    for (int64_t i = 0; i < n_recv_b; ++i) if (recv_rows[i] < 0 || recv_rows[i] >= nr) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_set_exchange: recv_rows entry outside [0, n_rows)");
+  }
   GTK_CK(cudaSetDevice(ctx->device));
   GhostPlan* g = (GhostPlan*)ctx->ghost;
   if (!g) { g = new GhostPlan(); ctx->ghost = g; }
@@ -292,8 +310,8 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
 // pack + send/recv on stream `st`
 static int32_t exchange_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
   if (g->p2p_ready()) {   // gather + store into the owner's buffer over NVLink + flag, one kernel per peer
-    ++g->seq;
     for (auto& p : g->peers) {
+      ++p.seq;   // one exchange = one push and one unpack per peer; both kernels of this exchange use the same number
       const int64_t n = p.n_send_nz + p.n_send_b;
       if (n == 0) continue;
       if (p.n_send_b && !ctx->bvec) GTK_FAIL(GTK_ERR_STATE, "ghost rows of b requested but no vector assembled");
@@ -301,7 +319,7 @@ static int32_t exchange_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
       const unsigned long long* lhdr = reinterpret_cast<const unsigned long long*>(p.ipc_block);
       { GtkProf pr_(ctx, "k_pack_push");
         k_pack_push<<<std::min(grid_for(n), 4 * ctx->sm_count), 256, 0, st>>>(ctx->nzval, p.send_nz, p.n_send_nz, ctx->bvec, p.send_rows, p.n_send_b,
-                                                 p.remote_block + P2P_HDR, rhdr + 0, lhdr + 1, g->seq, p.done_ctr + 0); }
+                                                 p.remote_block + P2P_HDR, rhdr + 0, lhdr + 1, p.seq, p.done_ctr + 0); }
       GTK_CK(cudaGetLastError());
       gtk_count_launch(ctx);
     }
@@ -337,7 +355,7 @@ static int32_t unpack_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
       { GtkProf pr_(ctx, "k_wait_unpack_add");
         // at most 2 blocks per SM: a block may spin for the peer's flag while the sweep shares the GPU with it
         k_wait_unpack_add<<<std::min(grid_for(n), 2 * ctx->sm_count), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b,
-                                                       p.recv_buf, lhdr + 0, rhdr + 1, g->seq, p.done_ctr + 1); }
+                                                       p.recv_buf, lhdr + 0, rhdr + 1, p.seq, p.done_ctr + 1); }
       GTK_CK(cudaGetLastError());
       gtk_count_launch(ctx);
     }

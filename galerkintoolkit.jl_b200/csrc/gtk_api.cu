@@ -79,7 +79,7 @@ int32_t upload(gtk_ctx* ctx, T** dst, size_t* old_n, const T* src, size_t n) {
 
 extern "C" {
 
-int32_t gtk_version(void) { return 102; }
+int32_t gtk_version(void) { return 103; }
 
 int32_t gtk_create(int32_t device, gtk_ctx** out) {
   if (!out) return GTK_ERR_INVALID;
@@ -108,7 +108,8 @@ int32_t gtk_destroy(gtk_ctx* ctx) {
   gtk_cuda_free(ctx, ctx->xvec);
   for (void* q : {(void*)ctx->xyz, (void*)ctx->cell_nodes, (void*)ctx->cell_dofs, (void*)ctx->w, (void*)ctx->N, (void*)ctx->dN,
                   (void*)ctx->M, (void*)ctx->dM, (void*)ctx->KE, (void*)ctx->BE, (void*)ctx->nzval, (void*)ctx->bvec,
-                  (void*)ctx->f_dev, (void*)ctx->coef_dev, (void*)ctx->Cm})
+                  (void*)ctx->f_dev, (void*)ctx->coef_dev, (void*)ctx->Cm, (void*)ctx->u_free, (void*)ctx->u_diri,
+                  (void*)ctx->xdof_free, (void*)ctx->xdof_diri, (void*)ctx->scal_part})
     gtk_cuda_free(ctx, q);
   gtk_pool_flush(ctx);
   for (auto& kv : ctx->pool.live) cudaFree(kv.first);   // anything still registered
@@ -120,6 +121,8 @@ const char* gtk_last_error(const gtk_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int32_t gtk_set_stream(gtk_ctx* ctx, void* s) {
   if (!ctx) return GTK_ERR_INVALID;
+  // everything issued so far (and every pooled block's last use) is ordered on the old stream
+  if (ctx->stream != (cudaStream_t)s) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
   ctx->stream = (cudaStream_t)s;
   return GTK_OK;
 }
@@ -133,6 +136,10 @@ int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz
   auto& sz = ctx->sz;
   ctx->D = D; ctx->dman = D; ctx->n_nodes = n_nodes; ctx->n_cells = n_cells; ctx->nln = n_lnodes;
   ctx->act_first = 0; ctx->act_count = -1;
+  // the space and the tabulation described the previous mesh: they must be handed over again
+  if (ctx->cell_dofs) { gtk_dev_free(ctx, ctx->cell_dofs, sz.cell_dofs * sizeof(int32_t)); ctx->cell_dofs = nullptr; sz.cell_dofs = 0; }
+  ctx->nld = 0; ctx->nls = 0; ctx->ncomp = 1; ctx->nq = 0;
+  gtk_field_release(ctx);
   int32_t rc = upload(ctx, &ctx->xyz, &sz.xyz, xyz, (size_t)n_nodes * D);
   if (rc) return rc;
   rc = upload(ctx, &ctx->cell_nodes, &sz.cell_nodes, cell_nodes, (size_t)n_cells * n_lnodes);
@@ -146,6 +153,7 @@ int32_t gtk_set_manifold_dim(gtk_ctx* ctx, int32_t d) {
   if (!ctx) return GTK_ERR_INVALID;
   if (!ctx->D) GTK_FAIL(GTK_ERR_STATE, "gtk_set_manifold_dim: set the mesh first");
   if (d < 1 || d > ctx->D) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_manifold_dim: 1 <= d <= D");
+  if (d != ctx->dman) ctx->nq = 0;   // gradients were tabulated with another number of components
   ctx->dman = d;
   return GTK_OK;
 }
@@ -173,6 +181,10 @@ int32_t gtk_set_active_cells(gtk_ctx* ctx, int64_t first, int64_t count) {
   if (first < 0 || count < 0 || first + count > ctx->n_cells) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_active_cells: range outside the mesh");
   ctx->act_first = first;
   ctx->act_count = count;
+  // the affine classification only inspected the previously active layers: every slot's plan must classify again
+  const int keep = ctx->cur_slot;
+  for (int s = 0; s < gtk_ctx::N_SLOTS; ++s) { gtk_select_matrix_impl(ctx, s); gtk_fastq1_coords_changed(ctx); }
+  gtk_select_matrix_impl(ctx, keep);
   return GTK_OK;
 }
 
@@ -196,8 +208,10 @@ int32_t gtk_set_space(gtk_ctx* ctx, int32_t n_ldofs, int32_t n_comp, const int32
     GTK_FAIL(GTK_ERR_TOO_LARGE, "dof ids are Int32 on this ABI");
   GTK_CK(cudaSetDevice(ctx->device));
   auto& sz = ctx->sz;
+  if (ctx->nls != n_ldofs / n_comp) ctx->nq = 0;   // N / dN were sized for another element
   ctx->nld = n_ldofs; ctx->ncomp = n_comp; ctx->nls = n_ldofs / n_comp;
   ctx->n_free = n_free; ctx->n_diri = n_dirichlet;
+  gtk_field_release(ctx);   // the discrete field belongs to the previous space
   int32_t rc = upload(ctx, &ctx->cell_dofs, &sz.cell_dofs, cell_dofs, (size_t)ctx->n_cells * n_ldofs);
   if (rc) return rc;
   gtk_release_all_matrices(ctx); gtk_vecsym_release(ctx);
@@ -339,6 +353,10 @@ int32_t gtk_device_pointer(gtk_ctx* ctx, int32_t which, void** dptr, int64_t* co
     case 1: *dptr = ctx->bvec; if (count) *count = ctx->vs.n_rows; break;
     case 2: *dptr = ctx->ms.colptr; if (count) *count = ctx->ms.n_cols + 1; break;
     case 3: *dptr = ctx->ms.rowval; if (count) *count = ctx->ms.nnz; break;
+    case 4: { int32_t rc = gtk_field_ensure(ctx); if (rc) return rc; *dptr = ctx->u_free; if (count) *count = ctx->n_free; break; }
+    case 5: { int32_t rc = gtk_field_ensure(ctx); if (rc) return rc; *dptr = ctx->u_diri; if (count) *count = ctx->n_diri; break; }
+    case 6: *dptr = ctx->xdof_free; if (count) *count = ctx->xdof_free ? ctx->n_free * ctx->D : 0; break;
+    case 7: *dptr = ctx->xdof_diri; if (count) *count = ctx->xdof_diri ? ctx->n_diri * ctx->D : 0; break;
     default: GTK_FAIL(GTK_ERR_INVALID, "gtk_device_pointer: unknown selector");
   }
   return GTK_OK;

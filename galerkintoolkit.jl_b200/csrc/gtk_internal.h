@@ -116,6 +116,12 @@ struct gtk_ctx {
   double* f_dev = nullptr; size_t f_cap = 0;  // uploaded f_nodal / f_qp
   double* coef_dev = nullptr; size_t coef_cap = 0;   // uploaded coef_nodal / coef_qp
   double* Cm = nullptr;  size_t Cm_cap = 0;   // [n_cells][n_q padded][6] per-point metric (elemgemm.cu)
+  // DiscreteField parameter u_h of the current space (field.cu): free / Dirichlet values, zero until set
+  double* u_free = nullptr;  size_t u_free_cap = 0;
+  double* u_diri = nullptr;  size_t u_diri_cap = 0;
+  double* xdof_free = nullptr; size_t xdof_free_cap = 0;   // [n_free][D] dof-node coordinates (gtk_space_dof_coordinates)
+  double* xdof_diri = nullptr; size_t xdof_diri_cap = 0;   // [n_dirichlet][D]
+  double* scal_part = nullptr; size_t scal_part_cap = 0;   // block partial sums of gtk_scalar_assemble
 
   struct { size_t xyz = 0, cell_nodes = 0, cell_dofs = 0, w = 0, N = 0, dN = 0, M = 0, dM = 0; } sz;  // uploaded element counts
 
@@ -207,3 +213,8 @@ int32_t gtk_numeric_vector_impl(gtk_ctx* ctx, int form, const gtk_form_params* p
 int32_t gtk_upload_coefficient(gtk_ctx* ctx, int form, const gtk_form_params* p, int* mode);
 int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
                               const gtk_form_params* pv);
+int32_t gtk_scalar_impl(gtk_ctx* ctx, int kind, const gtk_form_params* p, double* out);
+
+// ---- field.cu ----
+int32_t gtk_field_ensure(gtk_ctx* ctx);     // allocates (zero-filled) u_free / u_diri for the current space if missing
+void gtk_field_release(gtk_ctx* ctx);       // the space changed: drop values and dof coordinates

@@ -33,7 +33,26 @@ struct ElemArgs {
   double* out;
   int cb;
   int64_t act0, act1;   // numeric-active cells [act0, act1); others contribute zeros
+  // DiscreteField parameter u_h (PLAPLACE_* forms, scalar integrals): gathered per cell by the sign of the dof id
+  const int32_t* cell_dofs;
+  const double *u_free, *u_diri;
+  double expo;          // q of flux(∇u) = |∇u|^(q-2) ∇u
 };
+
+// x^e as Julia evaluates Float64^Int for the small integer exponents of the p-Laplacian tests (x^1 = x, x^0 = 1,
+// x^-1 = inv(x)); pow() otherwise
+__device__ __forceinline__ double powq(double x, double e) {
+  if (e == 0.0) return 1.0;
+  if (e == 1.0) return x;
+  if (e == 2.0) return x * x;
+  if (e == -1.0) return 1.0 / x;
+  if (e == -2.0) { const double i = 1.0 / x; return i * i; }
+  return pow(x, e);
+}
+
+__device__ __forceinline__ double field_value(const ElemArgs& a, int dof) {   // accessors.jl:1496-1508
+  return dof > 0 ? a.u_free[dof - 1] : a.u_diri[-dof - 1];
+}
 
 template <int D>
 __device__ __forceinline__ double det_mat(const double (&a)[D][D]) {
@@ -108,6 +127,7 @@ __global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
   const int nq = a.nq, nls = a.nls, nld = a.nld, ncomp = a.ncomp;
   double* G = smem;                                  // [cb][nq][nls][D]
   double* dV = G + (size_t)a.cb * nq * nls * D;      // [cb][nq]
+  double* FU = dV + (size_t)a.cb * nq;               // [cb][nq][D+2]: ∇u_h, (q-2)|∇u_h|^(q-4), |∇u_h|^(q-2)  (PLAPLACE_JACOBIAN)
   const int64_t cell0 = (int64_t)blockIdx.x * a.cb;
   const int ncb = (int)min((int64_t)a.cb, a.n_cells - cell0);
   const bool need_grad = a.form != GTK_FORM_MASS;
@@ -134,6 +154,27 @@ __global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
       double* g = G + (size_t)t * nls * D;
       const double* dNq = a.dN + (size_t)q * nls * D;
       for (int s = 0; s < nls; ++s) solve_JT<D>(J, d, dNq + s * D, g + s * D);
+      if (a.form == GTK_FORM_PLAPLACE_JACOBIAN) {
+        // ∇u_h = sum(i -> x[i]*s[i]; init = zero), sequential in local-dof order (accessors.jl:1549-1556)
+        const int32_t* dofs = a.cell_dofs + (cell0 + cl) * nld;
+        double gu[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) gu[k] = 0.0;
+        for (int s = 0; s < nls; ++s) {
+          const double us = field_value(a, dofs[s]);
+#pragma unroll
+          for (int k = 0; k < D; ++k) gu[k] += us * g[s * D + k];
+        }
+        double n2 = gu[0] * gu[0];
+#pragma unroll
+        for (int k = 1; k < D; ++k) n2 += gu[k] * gu[k];
+        const double nrm = sqrt(n2);
+        double* fu = FU + (size_t)t * (D + 2);
+#pragma unroll
+        for (int k = 0; k < D; ++k) fu[k] = gu[k];
+        fu[D] = (a.expo - 2.0) * powq(nrm, a.expo - 4.0);
+        fu[D + 1] = powq(nrm, a.expo - 2.0);
+      }
     }
   }
   __syncthreads();
@@ -157,6 +198,17 @@ __global__ void __launch_bounds__(128) k_elem_matrix(ElemArgs a) {
         v = a.alpha * dt;
       } else if (a.form == GTK_FORM_MASS) {
         v = ri == cj ? a.alpha * (a.N[q * nls + ra] * a.N[q * nls + ca]) : 0.0;
+      } else if (a.form == GTK_FORM_PLAPLACE_JACOBIAN) {
+        // ∇v ⋅ ((q-2)*norm(∇u)^(q-4)*(∇u⋅∇du)*∇u + norm(∇u)^(q-2)*∇du), du = φ_r, v = φ_c, left to right
+        const double* fu = FU + (size_t)(cl * nq + q) * (D + 2);
+        double udu = fu[0] * gq[ra * D];
+#pragma unroll
+        for (int k = 1; k < D; ++k) udu += fu[k] * gq[ra * D + k];
+        const double c1 = fu[D] * udu, c2 = fu[D + 1];
+        double dt = gq[ca * D] * (c1 * fu[0] + c2 * gq[ra * D]);
+#pragma unroll
+        for (int k = 1; k < D; ++k) dt += gq[ca * D + k] * (c1 * fu[k] + c2 * gq[ra * D + k]);
+        v = a.alpha * dt;
       } else {  // ELASTICITY_ISO: λ ∂_i s_a ∂_j s_b + μ ∂_j s_a ∂_i s_b + μ δ_ij ∇s_a·∇s_b
         double tt = a.lambda * (gq[ra * D + ri] * gq[ca * D + cj]) + a.mu * (gq[ra * D + cj] * gq[ca * D + ri]);
         if (ri == cj) {
@@ -212,6 +264,138 @@ __global__ void __launch_bounds__(128) k_elem_vector(ElemArgs a) {
   }
 }
 
+// Residual of the p-Laplacian about u_h (GTK_FORM_PLAPLACE_RESIDUAL):
+// be[i] = Σ_q (α·(∇φ_i⋅flux(∇u_h) − f φ_i))·dV_q, flux(∇u) = |∇u|^(q-2) ∇u  (test/problems_ext_tests.jl:160-162)
+template <int D>
+__global__ void __launch_bounds__(128) k_elem_vector_field(ElemArgs a) {
+  extern __shared__ double smem[];
+  const int nq = a.nq, nls = a.nls, nld = a.nld;
+  double* G = smem;                                  // [cb][nq][nls][D]
+  double* dV = G + (size_t)a.cb * nq * nls * D;      // [cb][nq]
+  double* FL = dV + (size_t)a.cb * nq;               // [cb][nq][D+1]: flux(∇u_h), f
+  const int64_t cell0 = (int64_t)blockIdx.x * a.cb;
+  const int ncb = (int)min((int64_t)a.cb, a.n_cells - cell0);
+  for (int t = threadIdx.x; t < ncb * nq; t += blockDim.x) {
+    int cl = t / nq, q = t - cl * nq;
+    const int64_t cell = cell0 + cl;
+    double J[D][D];
+    jacobian_at<D, D>(a, cell, q, J);
+    dV[t] = change_of_measure<D, D>(J) * a.w[q];
+    double JT[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) JT[i][j] = J[j][i];
+    const double dt = det_mat<D>(JT);
+    double* g = G + (size_t)t * nls * D;
+    const double* dNq = a.dN + (size_t)q * nls * D;
+    const int32_t* dofs = a.cell_dofs + cell * nld;
+    double gu[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) gu[k] = 0.0;
+    for (int s = 0; s < nls; ++s) {
+      solve_JT<D>(J, dt, dNq + s * D, g + s * D);
+      const double us = field_value(a, dofs[s]);
+#pragma unroll
+      for (int k = 0; k < D; ++k) gu[k] += us * g[s * D + k];
+    }
+    double n2 = gu[0] * gu[0];
+#pragma unroll
+    for (int k = 1; k < D; ++k) n2 += gu[k] * gu[k];
+    const double c = powq(sqrt(n2), a.expo - 2.0);
+    double* fl = FL + (size_t)t * (D + 1);
+#pragma unroll
+    for (int k = 0; k < D; ++k) fl[k] = c * gu[k];
+    fl[D] = a.f_ptr ? a.f_ptr[(size_t)cell * nq + q] : a.f_const[0];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < ncb * nld; t += blockDim.x) {
+    int cl = t / nld, i = t - cl * nld;
+    double acc = 0.0;
+    for (int q = 0; q < nq; ++q) {
+      const double* gq = G + ((size_t)(cl * nq + q) * nls + i) * D;
+      const double* fl = FL + (size_t)(cl * nq + q) * (D + 1);
+      double dt = gq[0] * fl[0];
+#pragma unroll
+      for (int k = 1; k < D; ++k) dt += gq[k] * fl[k];
+      acc += (a.alpha * (dt - fl[D] * a.N[q * nls + i])) * dV[cl * nq + q];
+    }
+    const int64_t cell = cell0 + cl;
+    a.out[cell * (int64_t)nld + i] = (cell >= a.act0 && cell < a.act1) ? acc : 0.0;
+  }
+}
+
+// Scalar integrals of u_h (assemble_scalar, problems.jl:173-190): one thread per (cell, point) evaluates integrand·dV, the
+// block sums its values in a fixed tree and writes one partial; k_sum_partials adds the partials in a fixed tree.
+template <int D>
+__global__ void __launch_bounds__(256) k_elem_scalar(ElemArgs a, int kind, double* __restrict__ part) {
+  __shared__ double red[256];
+  const int nq = a.nq, nls = a.nls, nld = a.nld;
+  const int64_t n_pts = (a.act1 - a.act0) * nq;
+  double acc = 0.0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_pts; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t cell = a.act0 + t / nq;
+    const int q = (int)(t % nq);
+    double J[D][D];
+    jacobian_at<D, D>(a, cell, q, J);
+    const double dv = change_of_measure<D, D>(J) * a.w[q];
+    double val = 1.0;
+    const int32_t* dofs = a.cell_dofs + cell * nld;
+    if (kind == GTK_SCALAR_L2SQ) {
+      double u = 0.0;
+      for (int s = 0; s < nls; ++s) u += field_value(a, dofs[s]) * a.N[q * nls + s];
+      if (a.f_ptr) u -= a.f_ptr[(size_t)cell * nq + q];
+      val = u * u;
+    } else if (kind == GTK_SCALAR_H1SQ) {
+      double JT[D][D];
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) JT[i][j] = J[j][i];
+      const double dt = det_mat<D>(JT);
+      const double* dNq = a.dN + (size_t)q * nls * D;
+      double gu[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) gu[k] = 0.0;
+      for (int s = 0; s < nls; ++s) {
+        double g[D];
+        solve_JT<D>(J, dt, dNq + s * D, g);
+        const double us = field_value(a, dofs[s]);
+#pragma unroll
+        for (int k = 0; k < D; ++k) gu[k] += us * g[k];
+      }
+      if (a.f_ptr) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) gu[k] -= a.f_ptr[((size_t)cell * nq + q) * D + k];
+      }
+      val = gu[0] * gu[0];
+#pragma unroll
+      for (int k = 1; k < D; ++k) val += gu[k] * gu[k];
+    }
+    acc += val * dv;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ part, int n, double* __restrict__ out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += part[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
 // nzval[p] = Σ_{s in segment p} KE[perm[s]], left to right = reference push order.
 __global__ void k_reduce_nz(const double* __restrict__ KE, const uint32_t* __restrict__ perm,
                             const uint32_t* __restrict__ nzptr, int64_t nnz, double* __restrict__ nzval) {
@@ -255,7 +439,8 @@ int32_t ensure(gtk_ctx* ctx, double** p, size_t* cap, size_t n) {
 }
 
 int32_t fill_args(gtk_ctx* ctx, ElemArgs& a, int form, const gtk_form_params* p) {
-  if (!ctx->xyz || !ctx->cell_dofs || !ctx->w) GTK_FAIL(GTK_ERR_STATE, "mesh, space and tabulation must be set first");
+  if (!ctx->xyz || !ctx->cell_dofs || !ctx->w || ctx->nq <= 0)
+    GTK_FAIL(GTK_ERR_STATE, "mesh, space and tabulation must be set first (in this order; a new mesh or element invalidates the tabulation)");
   a.xyz = ctx->xyz; a.cell_nodes = ctx->cell_nodes; a.n_cells = ctx->n_cells;
   a.nln = ctx->nln; a.nls = ctx->nls; a.ncomp = ctx->ncomp; a.nld = ctx->nld; a.nq = ctx->nq;
   a.w = ctx->w; a.N = ctx->N; a.dN = ctx->dN; a.M = ctx->M; a.dM = ctx->dM;
@@ -268,6 +453,18 @@ int32_t fill_args(gtk_ctx* ctx, ElemArgs& a, int form, const gtk_form_params* p)
   a.coef_ptr = nullptr; a.coef_mode = 0;
   a.act0 = ctx->act_count < 0 ? 0 : ctx->act_first;
   a.act1 = ctx->act_count < 0 ? ctx->n_cells : ctx->act_first + ctx->act_count;
+  a.cell_dofs = ctx->cell_dofs; a.u_free = ctx->u_free; a.u_diri = ctx->u_diri;
+  a.expo = p ? p->exponent : 0.0;
+  return GTK_OK;
+}
+
+// forms that read the DiscreteField parameter: scalar space, volume cells, values resident (zero until set)
+int32_t field_form_check(gtk_ctx* ctx, ElemArgs& a, const char* what) {
+  if (ctx->ncomp != 1) GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, std::string(what) + " needs a scalar space; no CPU fallback");
+  if (ctx->dman != ctx->D) GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, std::string(what) + " is not available on cells of lower dimension than the space");
+  int32_t rc = gtk_field_ensure(ctx);
+  if (rc) return rc;
+  a.u_free = ctx->u_free; a.u_diri = ctx->u_diri;
   return GTK_OK;
 }
 
@@ -316,6 +513,8 @@ int32_t gtk_upload_coefficient(gtk_ctx* ctx, int form, const gtk_form_params* p,
   int32_t rc = ensure(ctx, &ctx->coef_dev, &ctx->coef_cap, n);
   if (rc) return rc;
   GTK_CK(cudaMemcpyAsync(ctx->coef_dev, p->coef_nodal ? p->coef_nodal : p->coef_qp, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // the host pointer is only borrowed for the duration of the call; with pinned memory the copy above is truly asynchronous
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
   *mode = p->coef_nodal ? 1 : 2;
   return GTK_OK;
 }
@@ -342,12 +541,13 @@ int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params
   }
   if (form == GTK_FORM_ELASTICITY_ISO && ctx->ncomp != ctx->D)
     GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "ELASTICITY_ISO needs a vector space with n_comp == D");
-  if (form != GTK_FORM_LAPLACE && form != GTK_FORM_MASS && form != GTK_FORM_ELASTICITY_ISO)
+  if (form != GTK_FORM_LAPLACE && form != GTK_FORM_MASS && form != GTK_FORM_ELASTICITY_ISO && form != GTK_FORM_PLAPLACE_JACOBIAN)
     GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "unsupported bilinear form id " + std::to_string(form) +
-                                           " (supported: LAPLACE, MASS, ELASTICITY_ISO); no CPU fallback");
+                                           " (supported: LAPLACE, MASS, ELASTICITY_ISO, PLAPLACE_JACOBIAN); no CPU fallback");
   ElemArgs a;
   int32_t rc = fill_args(ctx, a, form, p);
   if (rc) return rc;
+  if (form == GTK_FORM_PLAPLACE_JACOBIAN && (rc = field_form_check(ctx, a, "PLAPLACE_JACOBIAN"))) return rc;
   if ((rc = gtk_upload_coefficient(ctx, form, p, &a.coef_mode))) return rc;
   a.coef_ptr = ctx->coef_dev;
   rc = ensure(ctx, &ctx->KE, &ctx->KE_cap, (size_t)m.n_full);
@@ -357,7 +557,7 @@ int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params
   if (ctx->n_cells == 0 || m.nnz == 0) return GTK_OK;
   a.out = ctx->KE;
   const int D = ctx->D;
-  size_t per_cell = ((size_t)ctx->nq * ctx->nls * D + ctx->nq) * sizeof(double);
+  size_t per_cell = ((size_t)ctx->nq * ctx->nls * D + ctx->nq + (size_t)ctx->nq * (D + 2)) * sizeof(double);
   size_t smem;
   rc = pick_cb(ctx, per_cell, &a.cb, &smem);
   if (rc) return rc;
@@ -385,14 +585,15 @@ static int32_t upload_f(gtk_ctx* ctx, const double* host, size_t n) {
   int32_t rc = ensure(ctx, &ctx->f_dev, &ctx->f_cap, n);
   if (rc) return rc;
   GTK_CK(cudaMemcpyAsync(ctx->f_dev, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));   // borrowed (possibly pinned) host buffer: do not return before it is read
   return GTK_OK;
 }
 
 int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params* p) {
   VecSym& v = ctx->vs;
-  if (form != GTK_FORM_SOURCE_CONST && form != GTK_FORM_SOURCE_NODAL && form != GTK_FORM_SOURCE_QP)
+  if (form != GTK_FORM_SOURCE_CONST && form != GTK_FORM_SOURCE_NODAL && form != GTK_FORM_SOURCE_QP && form != GTK_FORM_PLAPLACE_RESIDUAL)
     GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "unsupported linear form id " + std::to_string(form) +
-                                           " (supported: SOURCE_CONST, SOURCE_NODAL, SOURCE_QP); no CPU fallback");
+                                           " (supported: SOURCE_CONST, SOURCE_NODAL, SOURCE_QP, PLAPLACE_RESIDUAL); no CPU fallback");
   if (!v.generic_plan) {
     int32_t rc = gtk_symbolic_vector_generic_plan(ctx);
     if (rc) return rc;
@@ -408,6 +609,12 @@ int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params
     rc = upload_f(ctx, p ? p->f_qp : nullptr, (size_t)ctx->n_cells * ctx->nq * ctx->ncomp);
     if (rc) return rc;
     a.f_ptr = ctx->f_dev;
+  } else if (form == GTK_FORM_PLAPLACE_RESIDUAL) {
+    if ((rc = field_form_check(ctx, a, "PLAPLACE_RESIDUAL"))) return rc;
+    if (p && p->f_qp) {
+      if ((rc = upload_f(ctx, p->f_qp, (size_t)ctx->n_cells * ctx->nq))) return rc;
+      a.f_ptr = ctx->f_dev;
+    }
   }
   rc = ensure(ctx, &ctx->BE, &ctx->BE_cap, (size_t)v.n_full);
   if (rc) return rc;
@@ -420,10 +627,19 @@ int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params
   a.out = ctx->BE;
   const int D = ctx->D;
   size_t per_cell = ((size_t)ctx->nq * (1 + ctx->ncomp)) * sizeof(double);
+  if (form == GTK_FORM_PLAPLACE_RESIDUAL) per_cell = ((size_t)ctx->nq * ctx->nls * D + ctx->nq + (size_t)ctx->nq * (D + 1)) * sizeof(double);
   size_t smem;
   rc = pick_cb(ctx, per_cell, &a.cb, &smem);
   if (rc) return rc;
   int grid = (int)((ctx->n_cells + a.cb - 1) / a.cb);
+#define LAUNCH_VF(DD)                                                                                             \
+  do {                                                                                                            \
+    GTK_CK(cudaFuncSetAttribute(k_elem_vector_field<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    { GtkProf pr_(ctx, "k_elem_vector_field"); k_elem_vector_field<DD><<<grid, 128, smem, st>>>(a); }              \
+  } while (0)
+  if (form == GTK_FORM_PLAPLACE_RESIDUAL) {
+    if (D == 1) LAUNCH_VF(1); else if (D == 2) LAUNCH_VF(2); else LAUNCH_VF(3);
+  } else {
 #define LAUNCH_V(DD, dd)                                                                                        \
   do {                                                                                                          \
     GTK_CK(cudaFuncSetAttribute(k_elem_vector<DD, dd>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -434,6 +650,8 @@ int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params
   else if (D == 2 && dm == 1) LAUNCH_V(2, 1); else if (D == 3 && dm == 2) LAUNCH_V(3, 2); else if (D == 3 && dm == 1) LAUNCH_V(3, 1);
   else GTK_FAIL(GTK_ERR_INVALID, "D must be 1, 2 or 3 and 1 <= manifold dimension <= D");
 #undef LAUNCH_V
+  }
+#undef LAUNCH_VF
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   { GtkProf pr_(ctx, "k_reduce_rows"); k_reduce_rows<<<grid_for(v.n_urows, 256, ctx->sm_count), 256, 0, st>>>(ctx->BE, v.perm, v.rowptr, v.urow,
@@ -487,4 +705,36 @@ int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm
   rc = gtk_numeric_matrix_generic(ctx, mform, pm);
   if (rc) return rc;
   return gtk_numeric_vector_generic(ctx, vform, pv);
+}
+
+int32_t gtk_scalar_impl(gtk_ctx* ctx, int kind, const gtk_form_params* p, double* out) {
+  if (kind != GTK_SCALAR_VOLUME && kind != GTK_SCALAR_L2SQ && kind != GTK_SCALAR_H1SQ)
+    GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "unsupported scalar integral id " + std::to_string(kind) +
+                                           " (supported: VOLUME, L2SQ, H1SQ); no CPU fallback");
+  ElemArgs a;
+  int32_t rc = fill_args(ctx, a, kind, p);
+  if (rc) return rc;
+  if ((rc = field_form_check(ctx, a, "a scalar integral of the discrete field"))) return rc;
+  ctx->launches_last = 0;
+  gtk_prof_reset(ctx);
+  if (p && p->f_qp && kind != GTK_SCALAR_VOLUME) {
+    if ((rc = upload_f(ctx, p->f_qp, (size_t)ctx->n_cells * ctx->nq * (kind == GTK_SCALAR_H1SQ ? ctx->D : 1)))) return rc;
+    a.f_ptr = ctx->f_dev;
+  }
+  const int64_t n_pts = (a.act1 - a.act0) * ctx->nq;
+  const int grid = grid_for(n_pts, 256, ctx->sm_count);
+  if ((rc = ensure(ctx, &ctx->scal_part, &ctx->scal_part_cap, (size_t)ctx->sm_count * 16 + 1))) return rc;
+  double* d_out = ctx->scal_part + (size_t)ctx->sm_count * 16;
+  cudaStream_t st = ctx->stream;
+  const int D = ctx->D;
+  { GtkProf pr_(ctx, "k_elem_scalar");
+    if (D == 1) k_elem_scalar<1><<<grid, 256, 0, st>>>(a, kind, ctx->scal_part);
+    else if (D == 2) k_elem_scalar<2><<<grid, 256, 0, st>>>(a, kind, ctx->scal_part);
+    else k_elem_scalar<3><<<grid, 256, 0, st>>>(a, kind, ctx->scal_part); }
+  { GtkProf pr_(ctx, "k_sum_partials"); k_sum_partials<<<1, 256, 0, st>>>(ctx->scal_part, grid, d_out); }
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx, 2);
+  GTK_CK(cudaMemcpyAsync(out, d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
+  return GTK_OK;
 }

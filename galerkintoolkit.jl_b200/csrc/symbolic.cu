@@ -106,8 +106,11 @@ int bits_for(uint64_t maxval) {
 
 void gtk_fastq1_release(gtk_ctx* ctx);   // fastq1.cu
 
+void gtk_comm_release_plan(gtk_ctx* ctx);   // comm.cu
+
 void gtk_matsym_release(gtk_ctx* ctx) {
   MatSym& m = ctx->ms;
+  if (m.ready && ctx->cur_slot == 0) gtk_comm_release_plan(ctx);   // the ghost plan indexes the nzval of slot 0's pattern
   gtk_fastq1_release(ctx);
   gtk_free(ctx, m.dest, (size_t)m.n_full);
   gtk_free(ctx, m.multi, (size_t)m.n_multi);

@@ -18,8 +18,9 @@ LIB_PATH = os.path.join(HERE, "libgtkasm.so")
 GTK_OK = 0
 GTK_ERR_INVALID, GTK_ERR_CUDA, GTK_ERR_UNSUPPORTED_FORM, GTK_ERR_STATE, GTK_ERR_TOO_LARGE, GTK_ERR_NCCL = -1, -2, -3, -4, -5, -6
 FREE, DIRICHLET = 1, 2
-FORM_LAPLACE, FORM_MASS, FORM_ELASTICITY_ISO = 1, 2, 3
-FORM_SOURCE_CONST, FORM_SOURCE_NODAL, FORM_SOURCE_QP = 101, 102, 103
+FORM_LAPLACE, FORM_MASS, FORM_ELASTICITY_ISO, FORM_PLAPLACE_JACOBIAN = 1, 2, 3, 4
+FORM_SOURCE_CONST, FORM_SOURCE_NODAL, FORM_SOURCE_QP, FORM_PLAPLACE_RESIDUAL = 101, 102, 103, 104
+SCALAR_VOLUME, SCALAR_L2SQ, SCALAR_H1SQ = 200, 201, 202
 
 # every symbol include/gtk_assembly.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
@@ -32,6 +33,8 @@ ABI_SYMBOLS = [
     "gtk_comm_unique_id", "gtk_comm_init", "gtk_comm_set_exchange", "gtk_comm_sum_ghost_rows",
     "gtk_assemble_and_sum_ghost_rows_device", "gtk_select_matrix", "gtk_matvec_add_device", "gtk_matvec_add", "gtk_set_manifold_dim", "gtk_set_vector", "gtk_comm_p2p_export", "gtk_comm_p2p_import",
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
+    "gtk_field_set_values", "gtk_field_set_values_device", "gtk_field_get_values", "gtk_field_axpy_free",
+    "gtk_space_dof_coordinates", "gtk_scalar_assemble",
 ]
 
 
@@ -48,7 +51,8 @@ class UnsupportedFormError(GtkError):
 class FormParams(C.Structure):
     _fields_ = [("alpha", C.c_double), ("lam", C.c_double), ("mu", C.c_double),
                 ("f_const", C.c_double * 3), ("f_nodal", C.c_void_p), ("f_qp", C.c_void_p),
-                ("coef_nodal", C.c_void_p), ("coef_qp", C.c_void_p), ("accumulate", C.c_int32)]
+                ("coef_nodal", C.c_void_p), ("coef_qp", C.c_void_p), ("accumulate", C.c_int32),
+                ("exponent", C.c_double)]
 
 
 _lib = None
@@ -104,6 +108,12 @@ def load_library() -> C.CDLL:
         "gtk_set_profiling": (i32, [vp, i32]),
         "gtk_profile_count": (i32, [vp]),
         "gtk_profile_get": (i32, [vp, i32, C.c_char_p, C.POINTER(C.c_double)]),
+        "gtk_field_set_values": (i32, [vp, vp, vp]),
+        "gtk_field_set_values_device": (i32, [vp, vp, vp]),
+        "gtk_field_get_values": (i32, [vp, vp, vp]),
+        "gtk_field_axpy_free": (i32, [vp, C.c_double, vp]),
+        "gtk_space_dof_coordinates": (i32, [vp, vp, vp, vp]),
+        "gtk_scalar_assemble": (i32, [vp, i32, C.POINTER(FormParams), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -126,10 +136,11 @@ def _i32(a) -> np.ndarray:
 
 
 def make_params(alpha=1.0, lam=0.0, mu=0.0, f_const=None, f_nodal=None, f_qp=None, accumulate=False,
-                coef_nodal=None, coef_qp=None):
+                coef_nodal=None, coef_qp=None, exponent=0.0):
     """Returns (FormParams, keepalive) — keepalive holds the numpy buffers the struct points to."""
     p = FormParams()
     p.alpha, p.lam, p.mu = float(alpha), float(lam), float(mu)
+    p.exponent = float(exponent)
     p.accumulate = 1 if accumulate else 0
     fc = np.zeros(3)
     if f_const is not None:
@@ -313,6 +324,48 @@ class Engine:
         pv, k2 = make_params(**vparams)
         self._ck(self.lib.gtk_assemble_matrix_and_vector_device(self.h, mform, C.byref(pm), vform, C.byref(pv)))
         del k1, k2
+
+    # -- DiscreteField parameter, interpolation inputs, scalar integrals ---------------
+    def field_set_values(self, free_values=None, dirichlet_values=None):
+        """u_h of the current space: free / Dirichlet values to HBM (None = leave as is)."""
+        fv = None if free_values is None else _f64(free_values)
+        dv = None if dirichlet_values is None else _f64(dirichlet_values)
+        if fv is not None and fv.size != self._n_free:
+            raise ValueError(f"free_values has {fv.size} entries, the space has {self._n_free} free dofs")
+        if dv is not None and dv.size != self._n_diri:
+            raise ValueError(f"dirichlet_values has {dv.size} entries, the space has {self._n_diri} Dirichlet dofs")
+        self._ck(self.lib.gtk_field_set_values(self.h, _ptr(fv), _ptr(dv)))
+
+    def field_set_values_device(self, d_free: Optional[int] = None, d_dirichlet: Optional[int] = None):
+        """same from device pointers (ints), device-to-device on the engine's stream"""
+        self._ck(self.lib.gtk_field_set_values_device(self.h, C.c_void_p(d_free or 0), C.c_void_p(d_dirichlet or 0)))
+
+    def field_get_values(self):
+        fv = np.empty(self._n_free, dtype=np.float64)
+        dv = np.empty(self._n_diri, dtype=np.float64)
+        self._ck(self.lib.gtk_field_get_values(self.h, _ptr(fv), _ptr(dv)))
+        return fv, dv
+
+    def field_axpy_free(self, a: float, dx):
+        dx = _f64(dx)
+        if dx.size != self._n_free:
+            raise ValueError(f"dx has {dx.size} entries, the space has {self._n_free} free dofs")
+        self._ck(self.lib.gtk_field_axpy_free(self.h, float(a), _ptr(dx)))
+
+    def space_dof_coordinates(self, M_at_nodes):
+        """(x_free [n_free, D], x_dirichlet [n_dirichlet, D]): node_coordinates(space) seen through the dofs"""
+        Mn = _f64(M_at_nodes)
+        xf = np.empty((self._n_free, self._D), dtype=np.float64)
+        xd = np.empty((self._n_diri, self._D), dtype=np.float64)
+        self._ck(self.lib.gtk_space_dof_coordinates(self.h, _ptr(Mn), _ptr(xf), _ptr(xd)))
+        return xf, xd
+
+    def scalar_assemble(self, kind: int, **params) -> float:
+        p, keep = make_params(**params)
+        out = C.c_double(0.0)
+        self._ck(self.lib.gtk_scalar_assemble(self.h, kind, C.byref(p), C.byref(out)))
+        del keep
+        return out.value
 
     def copy_nzval(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         nz = np.empty(self.nnz, dtype=np.float64) if out is None else out

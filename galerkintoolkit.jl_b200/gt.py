@@ -127,6 +127,8 @@ class Term:
     def __rmul__(self, o): return Call("*", _lift(o), self)
     def __add__(self, o): return Call("+", self, _lift(o))
     def __radd__(self, o): return Call("+", _lift(o), self)
+    def __sub__(self, o): return Call("-", self, _lift(o))
+    def __rsub__(self, o): return Call("-", _lift(o), self)
     def __matmul__(self, o): return Call("dot", self, _lift(o))
 
 
@@ -175,9 +177,15 @@ class FormArgument:
 
 
 def grad(u, x):
-    """∇(u,x) = ForwardDiff.gradient(u,x) on a form argument → tabulated gradient (compiler.jl:573-589)."""
+    """∇(u,x) = ForwardDiff.gradient(u,x) on a form argument → tabulated gradient (compiler.jl:573-589); on a
+    DiscreteField → Σ_i u_i ∇φ_i (DiscreteFieldTerm, accessors.jl:1549-1556); on an AnalyticalField with a known
+    gradient → that gradient sampled by the host."""
     if isinstance(u, FormArgument):
         return FormArg(u.arg, "gradient")
+    if isinstance(u, DiscreteField):
+        return FieldTerm(u, "gradient")
+    if isinstance(u, AnalyticalField) and u.gradient is not None:
+        return Call(u.gradient, x)
     raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "∇ of a non form-argument quantity is not supported on the GPU path")
 
 
@@ -185,11 +193,55 @@ def dot(a, b):
     return Call("dot", _lift(a), _lift(b))
 
 
-class AnalyticalField:
-    """GT.analytical_field(f, Ω) (field.jl:17-58): evaluated by the host at x_q, enters the engine as data."""
+@dataclass
+class FieldTerm(Term):         # DiscreteFieldTerm (compiler.jl:60-1028): value or gradient of a DiscreteField at x
+    field: "DiscreteField"
+    op: str                    # "value" | "gradient"
 
-    def __init__(self, f: Callable, domain: Optional[Domain] = None):
+
+class DiscreteField:
+    """GT.DiscreteField (field.jl:93-125): a space plus free and Dirichlet values.  Passed as `parameters=(uh,)` it is
+    uploaded to the engine's field slot before every re-assembly (gtk_field_set_values)."""
+
+    def __init__(self, space: "Space", free_values, dirichlet_values):
+        self.space = space
+        self.free_values = np.ascontiguousarray(free_values, dtype=np.float64)
+        self.dirichlet_values = np.ascontiguousarray(dirichlet_values, dtype=np.float64)
+
+    def __call__(self, x):
+        return FieldTerm(self, "value")
+
+
+def discrete_field(space, free_values, dirichlet_values) -> DiscreteField:
+    return DiscreteField(space, free_values, dirichlet_values)
+
+
+def free_values(uh: DiscreteField):
+    return uh.free_values
+
+
+def dirichlet_values(uh: DiscreteField):
+    return uh.dirichlet_values
+
+
+def zero_field(T, space: "Space") -> DiscreteField:
+    """GT.zero_field(T, V) (field.jl:202-204)"""
+    return DiscreteField(space, np.zeros(space.num_free_dofs()), np.zeros(space.num_dirichlet_dofs()))
+
+
+def rand_field(T, space: "Space", rng=None) -> DiscreteField:
+    """GT.rand_field(T, V) (field.jl:196-200): random free values in [0,1), ZERO Dirichlet values"""
+    rng = np.random.default_rng() if rng is None else rng
+    return DiscreteField(space, rng.random(space.num_free_dofs()), np.zeros(space.num_dirichlet_dofs()))
+
+
+class AnalyticalField:
+    """GT.analytical_field(f, Ω) (field.jl:17-58): evaluated by the host at x_q, enters the engine as data.
+    `gradient` (optional) plays ForwardDiff.gradient(f, x) for error norms ∇(u,q) − ∇(uh,q)."""
+
+    def __init__(self, f: Callable, domain: Optional[Domain] = None, gradient: Optional[Callable] = None):
         self.f = f
+        self.gradient = gradient
 
     def __call__(self, x):
         if isinstance(x, Coordinate):
@@ -198,6 +250,44 @@ class AnalyticalField:
 
 
 analytical_field = AnalyticalField
+
+
+def call(fn, *args):
+    """GT.call(f, args...) (compiler.jl:372-390): apply an external function to quantities.  Only the named functions
+    the engine has a fused kernel for can be recognised afterwards (plaplacian_flux / plaplacian_dflux)."""
+    if len(args) == 1:
+        return Call(fn, _lift(args[0]))
+    if len(args) == 2:
+        return Call(fn, _lift(args[0]), _lift(args[1]))
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "GT.call with more than two arguments is not recognised by the GPU engine")
+
+
+def abs2(t):
+    return Call("abs2", _lift(t))
+
+
+class plaplacian_flux:
+    """flux(∇u) = norm(∇u)^(q-2) * ∇u (test/problems_ext_tests.jl:160, test/assembly_tests.jl:678) as a NAMED callable:
+    the reference passes an opaque closure to GT.call, which no recogniser can look into."""
+
+    def __init__(self, q):
+        self.q = q
+
+    def __call__(self, gu):
+        gu = np.asarray(gu, dtype=np.float64)
+        return np.linalg.norm(gu, axis=0) ** (self.q - 2) * gu
+
+
+class plaplacian_dflux:
+    """dflux(∇du,∇u) = (q-2)*norm(∇u)^(q-4)*(∇u⋅∇du)*∇u + norm(∇u)^(q-2)*∇du (test/problems_ext_tests.jl:161)"""
+
+    def __init__(self, q):
+        self.q = q
+
+    def __call__(self, gdu, gu):
+        gu = np.asarray(gu, dtype=np.float64); gdu = np.asarray(gdu, dtype=np.float64)
+        n = np.linalg.norm(gu, axis=0)
+        return (self.q - 2) * n ** (self.q - 4) * (gu * gdu).sum(0) * gu + n ** (self.q - 2) * gdu
 
 
 def isotropic_elasticity(lam: float, mu: float):
@@ -219,6 +309,13 @@ class Integral:
 
     def __rmul__(self, s):
         return Integral([(t, m, s * a) for (t, m, a) in self.contributions])
+
+    def __sub__(self, o):
+        return self + (-1.0) * o
+
+    def sum(self):
+        """`∫(...) |> sum` = assemble_scalar (problems.jl:173-199)"""
+        return assemble_scalar(self)
 
 
 def integrate(f: Callable, measure: Measure) -> Integral:
@@ -258,6 +355,13 @@ def recognise_bilinear(term, space: Optional["Space"] = None, meas: Optional["Me
                 params["alpha"] = params.get("alpha", 1.0) * scale
                 params["coef_qp"] = np.ascontiguousarray(np.broadcast_to(vals, xq.shape[:2]))
                 return form, params
+    if len(factors) == 1 and isinstance(factors[0], Call) and factors[0].fn == "dot":
+        # ∇(v,x)⋅GT.call(dflux, ∇(du,x), ∇(u,x)): Jacobian of the p-Laplacian about the DiscreteField u
+        for a, b in ((factors[0].a, factors[0].b), (factors[0].b, factors[0].a)):
+            if isinstance(a, FormArg) and a.arg == 1 and a.op == "gradient" and isinstance(b, Call) \
+                    and isinstance(b.fn, plaplacian_dflux) and isinstance(b.a, FormArg) and b.a.arg == 2 \
+                    and b.a.op == "gradient" and isinstance(b.b, FieldTerm) and b.b.op == "gradient":
+                return _eng.FORM_PLAPLACE_JACOBIAN, dict(alpha=scale, exponent=float(b.fn.q), field=b.b.field)
     if len(factors) == 1 and isinstance(factors[0], Named) and factors[0].name == "isotropic_elasticity":
         return _eng.FORM_ELASTICITY_ISO, dict(alpha=scale, **factors[0].params)
     if len(factors) == 1 and isinstance(factors[0], Call) and factors[0].fn == "dot":
@@ -276,7 +380,21 @@ def recognise_bilinear(term, space: Optional["Space"] = None, meas: Optional["Me
 
 
 def recognise_linear(term, space: Space, meas: Measure):
-    """→ (form_id, params) for ∫ f·v with f a constant or a host-evaluated analytical field."""
+    """→ (form_id, params) for ∫ f·v with f a constant or a host-evaluated analytical field, and for the p-Laplacian
+    residual ∫ ∇v⋅flux(∇u_h) − f v about a DiscreteField u_h."""
+    if isinstance(term, Call) and term.fn == "-" and isinstance(term.a, Call) and term.a.fn == "dot":
+        for a, b in ((term.a.a, term.a.b), (term.a.b, term.a.a)):
+            if isinstance(a, FormArg) and a.arg == 1 and a.op == "gradient" and isinstance(b, Call) \
+                    and isinstance(b.fn, plaplacian_flux) and isinstance(b.a, FieldTerm) and b.a.op == "gradient" and b.b is None:
+                sform, sparams = recognise_linear(term.b, space, meas)      # the source part f v
+                if space.data.n_comp != 1 or sparams.get("alpha", 1.0) != 1.0:
+                    break
+                params = dict(alpha=1.0, exponent=float(b.fn.q), field=b.a.field)
+                if sform == _eng.FORM_SOURCE_CONST:
+                    params["f_const"] = sparams["f_const"]
+                else:
+                    params["f_qp"] = sparams["f_qp"]
+                return _eng.FORM_PLAPLACE_RESIDUAL, params
     factors, scale = _flatten_product(term)
     if isinstance(term, Call) and term.fn == "dot":
         factors = [term.a, term.b]
@@ -359,6 +477,10 @@ def set_device(device: int):
 
 def _setup_engine(space: Space, meas: Measure, engine: Optional[_eng.Engine] = None) -> _eng.Engine:
     eng = engine or _eng.Engine(_default_device)
+    key = (id(space), meas.domain.kind, None if meas.domain.sides is None else tuple(meas.domain.sides), meas.degree)
+    if getattr(eng, "_gt_setup", None) == key:
+        return eng          # same mesh / space / measure already resident: keep patterns, plans and the field
+    eng._gt_setup = key
     mesh = space.domain.mesh
     if meas.domain.kind == "boundary":
         # the faces of Γ as a mesh of (D-1)-cells embedded in D dimensions (gtk_set_manifold_dim)
@@ -375,13 +497,33 @@ def _setup_engine(space: Space, meas: Measure, engine: Optional[_eng.Engine] = N
     return eng
 
 
+def _require_same_measure(meas_a: Measure, meas_l: Measure):
+    """the fused calls set the engine up from the bilinear form's measure: the linear form must integrate over the same
+    cells with the same rule, otherwise it would silently be integrated over the wrong domain"""
+    da, dl = meas_a.domain, meas_l.domain
+    sides = lambda d: None if d.sides is None else tuple(d.sides)
+    if meas_a.degree != meas_l.degree or da.kind != dl.kind or da.mesh is not dl.mesh or sides(da) != sides(dl):
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM,
+                                   "matrix and vector must share one measure (same domain, same degree) in the fused call; "
+                                   "assemble them separately with assemble_matrix / assemble_vector")
+
+
 def _single_contribution(integral: Integral):
     if len(integral.contributions) != 1:
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "sums of integrals are assembled one call at a time on the GPU path")
     return integral.contributions[0]
 
 
-def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False,
+def _upload_field(eng: _eng.Engine, params: dict) -> dict:
+    """`parameters=(uh,)`: the DiscreteField a recognised form depends on goes to the engine's field slot
+    (problems.jl:276-285, 352-361); returns the params the engine call takes"""
+    fld = params.get("field")
+    if fld is not None:
+        eng.field_set_values(fld.free_values, fld.dirichlet_values)
+    return {k: v for k, v in params.items() if k != "field"}
+
+
+def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, parameters=(),
                     free_or_dirichlet=(FREE, FREE), engine: Optional[_eng.Engine] = None):
     """GT.assemble_matrix(a, T, U, V; reuse, free_or_dirichlet) (problems.jl:319-350).
     Rows enumerate V (test), columns U (trial); only U is V is supported on the GPU path."""
@@ -398,22 +540,25 @@ def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False,
     eng = _setup_engine(V, meas, engine)
     eng.matrix_symbolic(*free_or_dirichlet)
     colptr, rowval = eng.matrix_pattern()
-    nzval = eng.matrix_numeric(form, **params)
+    nzval = eng.matrix_numeric(form, **_upload_field(eng, params))
     A = SparseMatrixCSC(eng.n_rows, eng.n_cols, colptr, rowval, nzval)
-    if reuse:
+    if reuse or parameters:
         return A, AssemblyCache(eng, form, params, "matrix")
     eng.close()
     return A
 
 
-def update_matrix(A: SparseMatrixCSC, cache: AssemblyCache, **new_params):
-    """GT.update_matrix!(A, cache) (problems.jl:352-361): numeric re-assembly on the cached pattern."""
+def update_matrix(A: SparseMatrixCSC, cache: AssemblyCache, parameters=(), **new_params):
+    """GT.update_matrix!(A, cache; parameters) (problems.jl:352-361): numeric re-assembly on the cached pattern; a
+    DiscreteField in `parameters` replaces the one the form was recognised with."""
     cache.params.update(new_params)
-    cache.engine.matrix_numeric(cache.form, out=A.nzval, **cache.params)
+    if parameters:
+        cache.params["field"] = parameters[0]
+    cache.engine.matrix_numeric(cache.form, out=A.nzval, **_upload_field(cache.engine, cache.params))
     return A
 
 
-def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, free_or_dirichlet=FREE,
+def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, parameters=(), free_or_dirichlet=FREE,
                     engine: Optional[_eng.Engine] = None):
     """GT.assemble_vector(l, T, V; reuse) (problems.jl:244-274)."""
     if T not in (float, np.float64):
@@ -442,17 +587,19 @@ def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, free_or_di
     params["alpha"] = params.get("alpha", 1.0) * scale
     eng = _setup_engine(V, meas, engine)
     eng.vector_symbolic(free_or_dirichlet)
-    b = eng.vector_assemble(form, **params)
-    if reuse:
+    b = eng.vector_assemble(form, **_upload_field(eng, params))
+    if reuse or parameters:
         return b, AssemblyCache(eng, form, params, "vector")
     eng.close()
     return b
 
 
-def update_vector(b: np.ndarray, cache: AssemblyCache, **new_params):
-    """GT.update_vector!(b, cache) (problems.jl:276-285)."""
+def update_vector(b: np.ndarray, cache: AssemblyCache, parameters=(), **new_params):
+    """GT.update_vector!(b, cache; parameters) (problems.jl:276-285)."""
     cache.params.update(new_params)
-    cache.engine.vector_assemble(cache.form, out=b, **cache.params)
+    if parameters:
+        cache.params["field"] = parameters[0]
+    cache.engine.vector_assemble(cache.form, out=b, **_upload_field(cache.engine, cache.params))
     return b
 
 
@@ -463,8 +610,7 @@ def assemble_matrix_and_vector(a: Callable, l: Callable, T, U: Space, V: Space, 
     u, v = FormArgument(U, 2), FormArgument(V, 1)
     term_a, meas_a, sa = _single_contribution(a(u, v))
     term_l, meas_l, sl = _single_contribution(l(v))
-    if meas_a.degree != meas_l.degree:
-        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "matrix and vector must share one measure in the fused call")
+    _require_same_measure(meas_a, meas_l)
     mform, mparams = recognise_bilinear(term_a)
     vform, vparams = recognise_linear(term_l, V, meas_l)
     mparams["alpha"] = mparams.get("alpha", 1.0) * sa
@@ -493,8 +639,7 @@ def assemble_matrix_and_vector_with_free_and_dirichlet_columns(a: Callable, l: C
     u, v = FormArgument(U, 2), FormArgument(V, 1)
     term_a, meas_a, sa = _single_contribution(a(u, v))
     term_l, meas_l, sl = _single_contribution(l(v))
-    if meas_a.degree != meas_l.degree:
-        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "matrix and vector must share one measure in the fused call")
+    _require_same_measure(meas_a, meas_l)
     mform, mparams = recognise_bilinear(term_a)
     vform, vparams = recognise_linear(term_l, V, meas_l)
     mparams["alpha"] = mparams.get("alpha", 1.0) * sa
@@ -531,40 +676,207 @@ def linear_problem(dirichlet_values: np.ndarray, a: Callable, l: Callable, U: Sp
 
 
 # ---------------------------------------------------------------------------
-# Dirichlet data and solution fields (host side; space.jl:2000-2100, problems.jl:501-526)
+# 0-forms: assemble_scalar (problems.jl:173-199)
 # ---------------------------------------------------------------------------
-def interpolate_dirichlet(g: Callable, V: Space) -> np.ndarray:
-    """GT.interpolate_dirichlet!(g, uh) for nodal Lagrange spaces: the Dirichlet value of a dof is g at its node
-    (component c of g for vector spaces; dofs are node-major / component-minor).  -> xd [n_dirichlet]"""
-    X = V.data.dirichlet_dof_nodes
+def _recognise_scalar(term, space_hint=None):
+    """→ (kind, field, g_fn or None): abs2(uh(x)), abs2(u(x) − uh(x)), ∇e⋅∇e with e = u − uh (or uh alone), 1"""
+    def split_diff(t, op):
+        # → (field, analytic callable or None, sign of the field) for `uh`, `u − uh`, `uh − u`
+        if isinstance(t, FieldTerm) and t.op == op:
+            return t.field, None
+        if isinstance(t, Call) and t.fn == "-":
+            for f, g in ((t.a, t.b), (t.b, t.a)):
+                if isinstance(f, FieldTerm) and f.op == op and isinstance(g, Call) and callable(g.fn) and isinstance(g.a, Coordinate):
+                    return f.field, g.fn
+        return None
+    if isinstance(term, Const) and term.value == 1:
+        return _eng.SCALAR_VOLUME, None, None
+    if isinstance(term, Call) and term.fn == "abs2":
+        r = split_diff(term.a, "value")
+        if r:
+            return _eng.SCALAR_L2SQ, r[0], r[1]
+    if isinstance(term, Call) and term.fn == "dot":
+        ra, rb = split_diff(term.a, "gradient"), split_diff(term.b, "gradient")
+        if ra and rb and ra[0] is rb[0] and ra[1] is rb[1]:
+            return _eng.SCALAR_H1SQ, ra[0], ra[1]
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM,
+                               "scalar integrand not recognised by the GPU engine (supported: 1, abs2(uh), abs2(u - uh), "
+                               "∇e⋅∇e with e = uh or u - uh); refusing to fall back to a CPU loop")
+
+
+def assemble_scalar(integral: Integral, space: Optional[Space] = None) -> float:
+    """GT.assemble_scalar(∫(...)) = `∫(...) |> sum` (problems.jl:173-199): Σ over contributions of coefficient · Σ_cells Σ_q
+    integrand·dV, each on the device (gtk_scalar_assemble)."""
+    total = 0.0
+    for term, meas, scale in integral.contributions:
+        kind, fld, g = _recognise_scalar(term)
+        V = fld.space if fld is not None else space
+        if V is None:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "∫ 1 needs a space to pick the cells from (pass space=)")
+        eng = _setup_engine(V, meas)
+        params = {}
+        if fld is not None:
+            eng.field_set_values(fld.free_values, fld.dirichlet_values)
+        if g is not None:
+            xq = quadrature_point_coordinates(V, meas)
+            vals = np.asarray(g(np.moveaxis(xq, -1, 0)), dtype=np.float64)
+            if kind == _eng.SCALAR_H1SQ:
+                vals = np.moveaxis(np.broadcast_to(vals, (xq.shape[-1],) + xq.shape[:2]), 0, -1)
+            else:
+                vals = np.broadcast_to(vals, xq.shape[:2])
+            params["f_qp"] = np.ascontiguousarray(vals)
+        total += scale * eng.scalar_assemble(kind, **params)
+        eng.close()
+    return total
+
+
+# ---------------------------------------------------------------------------
+# Dirichlet data and solution fields (space.jl:1876-1897, 2000-2060; problems.jl:501-526)
+# ---------------------------------------------------------------------------
+def _reference_node_tabulation(V: Space) -> np.ndarray:
+    """tabulator(refface)(value, node_coordinates(reffe)) (space.jl:1918-1922): geometry shape functions at the reference
+    nodes of the space, [n_lnodes_space, n_lnodes_mesh]"""
+    d = V.data
+    return _hp.tabulate(d.mesh.D, 1, d.kind, _hp.reference_nodes(d.mesh.D, d.order, d.kind))[0]
+
+
+def dof_coordinates(V: Space):
+    """(x_free, x_dirichlet): node_coordinates(V) seen through free_dof_node / dirichlet_dof_node (space.jl:1876-1897,
+    1960-1998), computed on the device (gtk_space_dof_coordinates) and cached on the space"""
+    if "xdof" not in V._tab:
+        mesh = V.domain.mesh
+        eng = _eng.Engine(_default_device)
+        eng.set_mesh(mesh.node_coordinates, mesh.cell_nodes)
+        eng.set_space(V.data.cell_dofs, V.data.n_free, V.data.n_dirichlet, V.data.n_comp)
+        V._tab["xdof"] = eng.space_dof_coordinates(_reference_node_tabulation(V))
+        eng.close()
+    return V._tab["xdof"]
+
+
+def _dof_component(V: Space, free: bool) -> np.ndarray:
+    """component of every free / Dirichlet dof: local dof = node * n_comp + c in every cell (space.jl:1267-1271)"""
+    d = V.data.cell_dofs
+    nc = V.data.n_comp
+    lc = np.tile(np.arange(d.shape[1]) % nc, (d.shape[0], 1))
+    if free:
+        comp = np.zeros(V.data.n_free, dtype=np.int64)
+        sel = d > 0
+        comp[d[sel] - 1] = lc[sel]
+    else:
+        comp = np.zeros(V.data.n_dirichlet, dtype=np.int64)
+        sel = d < 0
+        comp[-d[sel] - 1] = lc[sel]
+    return comp
+
+
+def _evaluate_at(g, X: np.ndarray, V: Space, free: bool) -> np.ndarray:
+    g = g.f if isinstance(g, AnalyticalField) else g
     vals = np.asarray(g(np.moveaxis(X, -1, 0)), dtype=np.float64)
     nc = V.data.n_comp
     if nc == 1:
         return np.ascontiguousarray(np.broadcast_to(vals, X.shape[:1]))
-    comp = _dirichlet_component(V)
     vals = np.broadcast_to(vals, (nc,) + X.shape[:1])
-    return np.ascontiguousarray(vals[comp, np.arange(X.shape[0])])
+    return np.ascontiguousarray(vals[_dof_component(V, free), np.arange(X.shape[0])])
 
 
-def _dirichlet_component(V: Space) -> np.ndarray:
-    """component of every Dirichlet dof: local dof = node * n_comp + c in every cell (space.jl:1267-1271)"""
-    d = V.data.cell_dofs
-    nc = V.data.n_comp
-    comp = np.empty(V.data.n_dirichlet, dtype=np.int64)
-    lc = np.tile(np.arange(d.shape[1]) % nc, (d.shape[0], 1))
-    neg = d < 0
-    comp[-d[neg] - 1] = lc[neg]
-    return comp
+def interpolate_dirichlet(g: Callable, V):
+    """GT.interpolate_dirichlet(g, V) / interpolate_dirichlet!(g, uh) (field.jl:352-373; space.jl:2000-2060): the Dirichlet
+    value of a dof is g at its node (component c of g for vector spaces).  Given a space: → xd [n_dirichlet] (what
+    `dirichlet_values(interpolate_dirichlet(g, V))` holds); given a DiscreteField: updates it in place and returns it."""
+    if isinstance(V, DiscreteField):
+        V.dirichlet_values[:] = _evaluate_at(g, dof_coordinates(V.space)[1], V.space, False)
+        return V
+    return _evaluate_at(g, dof_coordinates(V)[1], V, False)
 
 
-def solution_field(V: Space, x: np.ndarray, xd: np.ndarray) -> np.ndarray:
-    """GT.solution_field(uhd, x) restricted to what a nodal space needs: the value of every local dof of every cell,
-    free dofs from x, Dirichlet dofs from xd.  -> [n_cells, n_ldofs]"""
-    d = V.data.cell_dofs.astype(np.int64)
-    x = np.asarray(x, dtype=np.float64)
-    xd = np.asarray(xd, dtype=np.float64)
-    out = np.empty(d.shape, dtype=np.float64)
-    pos = d > 0
-    out[pos] = x[d[pos] - 1]
-    out[~pos] = xd[-d[~pos] - 1]
-    return out
+def interpolate_free(g: Callable, V):
+    """GT.interpolate_free(g, V) / interpolate_free!(g, uh) (field.jl:352-360)"""
+    if isinstance(V, DiscreteField):
+        V.free_values[:] = _evaluate_at(g, dof_coordinates(V.space)[0], V.space, True)
+        return V
+    return _evaluate_at(g, dof_coordinates(V)[0], V, True)
+
+
+def interpolate(g: Callable, V: Space) -> DiscreteField:
+    """GT.interpolate(g, V) (field.jl:335-345)"""
+    xf, xd = dof_coordinates(V)
+    return DiscreteField(V, _evaluate_at(g, xf, V, True), _evaluate_at(g, xd, V, False))
+
+
+def solution_field(U, x, xd=None):
+    """GT.solution_field(uhd | U, x | problem) (problems.jl:501-563): the DiscreteField with free values x and the
+    Dirichlet values of uhd (zero for a space).  Legacy form solution_field(V, x, xd) -> the value of every local dof of
+    every cell [n_cells, n_ldofs] (kept for the linear-problem tests)."""
+    if isinstance(x, NonlinearProblem):
+        x = x.x
+    if xd is not None and isinstance(U, Space):
+        d = U.data.cell_dofs.astype(np.int64)
+        x = np.asarray(x, dtype=np.float64)
+        xd = np.asarray(xd, dtype=np.float64)
+        out = np.empty(d.shape, dtype=np.float64)
+        pos = d > 0
+        out[pos] = x[d[pos] - 1]
+        out[~pos] = xd[-d[~pos] - 1]
+        return out
+    if isinstance(U, DiscreteField):
+        return DiscreteField(U.space, np.array(x, dtype=np.float64), U.dirichlet_values)
+    return DiscreteField(U, np.array(x, dtype=np.float64), np.zeros(U.num_dirichlet_dofs()))
+
+
+# ---------------------------------------------------------------------------
+# Nonlinear problems (problems.jl:465-497)
+# ---------------------------------------------------------------------------
+class NonlinearProblem:
+    """PartitionedSolvers_nonlinear_problem(uh, r, j) (problems.jl:465-478): x = free values of uh, b = residual,
+    A = Jacobian, both assembled on ONE engine context (same mesh/space/measure) and re-assembled by `update`
+    (nonlinear_problem_update, problems.jl:480-497) with u_h resident in HBM."""
+
+    def __init__(self, uh: DiscreteField, r: Callable, j: Callable, V: Optional[Space] = None):
+        U = uh.space
+        V = U if V is None else V
+        self.uh = uh
+        self.x = uh.free_values.copy()
+        self.b, self.residual_cache = assemble_vector(r(uh), np.float64, V, parameters=(uh,))
+        self.A, self.jacobian_cache = assemble_matrix(j(uh), np.float64, U, V, parameters=(uh,),
+                                                      engine=self.residual_cache.engine)
+
+    def update(self, x, residual=True, jacobian=True):
+        """solution_field!(uh, x) then update_vector! / update_matrix! with parameters=(uh,)"""
+        self.x = np.array(x, dtype=np.float64)
+        self.uh.free_values[:] = self.x
+        if residual:
+            update_vector(self.b, self.residual_cache, parameters=(self.uh,))
+        if jacobian:
+            update_matrix(self.A, self.jacobian_cache, parameters=(self.uh,))
+        return self
+
+    def close(self):
+        self.residual_cache.engine.close()
+
+
+def nonlinear_problem(uh: DiscreteField, r: Callable, j: Callable, V: Optional[Space] = None) -> NonlinearProblem:
+    return NonlinearProblem(uh, r, j, V)
+
+
+def newton_solve(p: NonlinearProblem, *, rtol=1e-12, atol=1e-13, maxiter=60, verbose=False) -> NonlinearProblem:
+    """Stand-in for `NonlinearSolve.solve(prob)` / `PS.NLsolve_nlsolve(p; method=:newton)` of the reference's tests: Newton
+    with a backtracking line search on ‖r‖₂; the linear solves run on the host (SciPy sparse LU — solvers are out of
+    scope), every residual and Jacobian is a device re-assembly."""
+    import scipy.sparse.linalg as spl
+    r0 = None
+    for it in range(maxiter):
+        nr = float(np.linalg.norm(p.b))
+        r0 = nr if r0 is None else r0
+        if verbose:
+            print(f"newton {it}: |r| = {nr:.3e}")
+        if nr <= atol or nr <= rtol * r0:
+            return p
+        dx = spl.spsolve(p.A.to_scipy().tocsc(), -p.b)
+        x0, t = p.x.copy(), 1.0
+        while True:
+            p.update(x0 + t * dx, jacobian=False)
+            if float(np.linalg.norm(p.b)) < (1.0 - 1e-4 * t) * nr or t < 1e-8:
+                break
+            t *= 0.5
+        p.update(p.x, residual=False)
+    raise RuntimeError("newton_solve: no convergence")

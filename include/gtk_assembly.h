@@ -54,10 +54,23 @@ enum {
   GTK_FORM_LAPLACE = 1,          /* ∫ ∇u·∇v            (scalar space)                      */
   GTK_FORM_MASS = 2,             /* ∫ u v  (component-wise u·v for vector spaces)           */
   GTK_FORM_ELASTICITY_ISO = 3,   /* ∫ σ(ε(u)):ε(v), σ = λ tr(ε) I + 2 μ ε (n_comp == D)     */
+  GTK_FORM_PLAPLACE_JACOBIAN = 4,/* ∫ ∇v·dflux(∇du,∇u_h), dflux(∇du,∇u) = (q-2)|∇u|^(q-4)(∇u·∇du)∇u + |∇u|^(q-2)∇du: the Jacobian of
+                                    the p-Laplacian about the DiscreteField parameter u_h (gtk_field_set_values), q = `exponent`
+                                    (test/problems_ext_tests.jl:159-163, test/assembly_tests.jl:677-686; update_matrix! with
+                                    parameters=(uh,), problems.jl:352-361; field evaluation accessors.jl:1489-1563)            */
   GTK_FORM_SOURCE_CONST = 101,   /* ∫ f·v, f constant (f_const[0..n_comp))                  */
   GTK_FORM_SOURCE_NODAL = 102,   /* ∫ f_h·v, f_h = Σ_node f_node M_node (mesh nodes)         */
-  GTK_FORM_SOURCE_QP = 103       /* ∫ f·v, f given per (cell, quadrature point)             */
+  GTK_FORM_SOURCE_QP = 103,      /* ∫ f·v, f given per (cell, quadrature point)             */
+  GTK_FORM_PLAPLACE_RESIDUAL = 104 /* ∫ ∇v·flux(∇u_h) − f v, flux(∇u) = |∇u|^(q-2)∇u, f = f_qp if given else f_const[0]: the residual of
+                                    the p-Laplacian about u_h (update_vector! with parameters=(uh,), problems.jl:276-285)       */
 };
+
+/* Scalar integrals of the DiscreteField parameter (assemble_scalar, problems.jl:173-199: `∫(...) |> sum`):
+ *   VOLUME ∫ 1     L2SQ ∫ abs2(u_h − g)     H1SQ ∫ (∇u_h − ∇g)·(∇u_h − ∇g)
+ * with g (or ∇g) sampled by the host at the quadrature points through f_qp ([n_cells][n_q] values for L2SQ,
+ * [n_cells][n_q][D] gradients for H1SQ; NULL = 0): the norms and manufactured-solution errors of the reference's tests
+ * (test/problems_tests.jl:96-105, test/problems_ext_tests.jl:139-171). */
+enum { GTK_SCALAR_VOLUME = 200, GTK_SCALAR_L2SQ = 201, GTK_SCALAR_H1SQ = 202 };
 
 typedef struct gtk_form_params {
   double alpha;            /* scalar in front of the integral (problems.jl:29-33, 102-108) */
@@ -73,6 +86,7 @@ typedef struct gtk_form_params {
   int32_t accumulate;      /* linear forms: != 0 adds this integral to the vector already on the device (gtk_set_vector or a
                               previous assembly) instead of starting from zeros — a sum of integrals such as
                               ∫_Ω f v + ∫_Γ g v is one COO vector in the reference (problems.jl:258-266) */
+  double exponent;         /* PLAPLACE_*: the q of flux(∇u) = |∇u|^(q-2) ∇u */
 } gtk_form_params;
 
 /* ---- life cycle ------------------------------------------------------------ */
@@ -157,9 +171,35 @@ int32_t gtk_select_matrix(gtk_ctx* ctx, int32_t slot);
 int32_t gtk_matvec_add_device(gtk_ctx* ctx, double alpha, const double* x, double beta);
 int32_t gtk_matvec_add(gtk_ctx* ctx, double alpha, const double* x, double beta, double* b);
 
+/* ---- DiscreteField parameter u_h (field.jl:93-125) and nodal interpolation (space.jl:1876-1897, 2000-2060) -------- */
+/* The ctx holds ONE discrete field of the current space: free values [n_free] and Dirichlet values [n_dirichlet] in HBM.
+ * It is what `parameters=(uh,)` hands to the generated loops of the reference (problems.jl:465-497): the PLAPLACE_* forms
+ * and gtk_scalar_assemble read it per cell (dof > 0 -> free value, dof < 0 -> Dirichlet value; accessors.jl:1489-1510).
+ * gtk_field_set_values uploads host arrays (either may be NULL = leave as is; a field that was never set is zero):
+ * `solution_field!(uh, x)` (problems.jl:519-526) is gtk_field_set_values(ctx, x, NULL).  The _device variant takes device
+ * pointers (device-to-device copy on the ctx stream), so x and u_h need not leave HBM between Newton steps. */
+int32_t gtk_field_set_values(gtk_ctx* ctx, const double* free_values, const double* dirichlet_values);
+int32_t gtk_field_set_values_device(gtk_ctx* ctx, const double* d_free_values, const double* d_dirichlet_values);
+int32_t gtk_field_get_values(gtk_ctx* ctx, double* free_values, double* dirichlet_values);
+/* free values += a * dx  (Newton update x <- x + a dx; dx host [n_free]) */
+int32_t gtk_field_axpy_free(gtk_ctx* ctx, double a, const double* dx);
+/* Coordinates of the nodes the dofs sit on, as `interpolate!` sees them: node_coordinates(::LagrangeMeshSpace)
+ * (space.jl:1876-1897) loops over the cells, x = Σ_lmnode tab[lnode,lmnode]·x_mnode from zero in local-mesh-node order, and
+ * the LAST cell that holds a node wins.  `M_at_nodes` [n_ldofs/n_comp][n_lnodes] is that tabulator (geometry shape functions
+ * at the reference nodes of the space; identity for order 1).  Results: x_free [n_free][D], x_dirichlet [n_dirichlet][D]
+ * (every component dof of a node gets the node's coordinate), on the host and/or left in HBM
+ * (gtk_device_pointer 6, 7).  The host evaluates g there (a Julia closure cannot cross a C ABI; with CUDA.jl it can be
+ * broadcast over the device array) and hands the values to gtk_field_set_values[_device]: that IS
+ * interpolate_free! / interpolate_dirichlet! (field.jl:352-373, space.jl:2000-2060: v = fun(node_x[node]) per dof). */
+int32_t gtk_space_dof_coordinates(gtk_ctx* ctx, const double* M_at_nodes, double* x_free, double* x_dirichlet);
+/* assemble_scalar over the current measure (problems.jl:173-190): *out = Σ_cells Σ_q integrand·dV, summed in a fixed
+ * tree order (bit-reproducible).  kind: GTK_SCALAR_*. */
+int32_t gtk_scalar_assemble(gtk_ctx* ctx, int32_t kind, const gtk_form_params* p, double* out);
+
 /* ---- device-resident results -------------------------------------------------- */
 /* which: 0 nzval (double[nnz]) 1 b (double[n_rows]) 2 colptr (int64[n_cols+1], 0-based)
- *        3 rowval (int32[nnz], 1-based) */
+ *        3 rowval (int32[nnz], 1-based) 4 field free values (double[n_free]) 5 field Dirichlet values (double[n_dirichlet])
+ *        6 / 7 coordinates of the free / Dirichlet dofs (double[n][D], after gtk_space_dof_coordinates) */
 int32_t gtk_device_pointer(gtk_ctx* ctx, int32_t which, void** dptr, int64_t* count);
 int32_t gtk_copy_nzval(gtk_ctx* ctx, double* nzval);
 int32_t gtk_copy_vector(gtk_ctx* ctx, double* b);

@@ -396,6 +396,163 @@ def element_vectors(form, coords, cell_nodes, tab, n_comp=1, alpha=1.0, f_const=
 
 
 # ---------------------------------------------------------------------------
+# Forms with a DiscreteField parameter u_h (nonlinear problems: residual / Jacobian re-assembly,
+# problems.jl:276-285, 352-361, 465-497; field evaluation accessors.jl:1489-1563)
+# ---------------------------------------------------------------------------
+PLAPLACE_JACOBIAN = 4
+PLAPLACE_RESIDUAL = 104
+SCALAR_VOLUME, SCALAR_L2SQ, SCALAR_H1SQ = 200, 201, 202
+
+
+def field_cell_values(cell_dofs, free_values, dirichlet_values):
+    """values(::NewDiscreteFieldFace{AtInterior}) accessors.jl:1489-1510: per cell, dof > 0 reads free_values[dof],
+    dof < 0 reads dirichlet_values[-dof].  -> [n_cells, n_ldofs]"""
+    d = np.asarray(cell_dofs, dtype=np.int64)
+    fv = np.asarray(free_values, dtype=np.float64)
+    dv = np.asarray(dirichlet_values, dtype=np.float64)
+    out = np.empty(d.shape)
+    pos = d > 0
+    out[pos] = fv[d[pos] - 1]
+    out[~pos] = dv[-d[~pos] - 1]
+    return out
+
+
+def _physical_gradients(coords, cell_nodes, tab, q):
+    """(g[a] = Jᵀ \\ ∇̂N_a for every local shape function, dV) at point q (accessors.jl:941-1007, 1365-1368)"""
+    nc = cell_nodes.shape[0]
+    D = coords.shape[1]
+    J = point_geometry(coords, cell_nodes, tab["dM"][q])
+    dV = change_of_measure(J) * tab["w"][q]
+    Jt = np.swapaxes(J, -1, -2)
+    g = [_solve(Jt, np.broadcast_to(tab["dN"][q, a], (nc, D))) for a in range(tab["N"].shape[1])]
+    return g, dV
+
+
+def _field_gradient(uc, g):
+    """field(gradient, ::NewDiscreteFieldFace) accessors.jl:1549-1556: sum(i->x[i]*s[i], 1:n; init=zero) — sequential"""
+    gu = np.zeros_like(g[0])
+    for a in range(len(g)):
+        gu = gu + uc[:, a, None] * g[a]
+    return gu
+
+
+def _norm(v):
+    """LinearAlgebra.norm of an SVector: sqrt of the sequential sum of abs2"""
+    return np.sqrt(_dot(v, v))
+
+
+def plaplace_flux(gu, q):
+    """flux(∇u) = norm(∇u)^(q-2) * ∇u  (test/problems_ext_tests.jl:160, test/assembly_tests.jl:678)"""
+    return (_norm(gu) ** (q - 2))[:, None] * gu
+
+
+def plaplace_dflux(gdu, gu, q):
+    """dflux(∇du,∇u) = (q-2)*norm(∇u)^(q-4)*(∇u⋅∇du)*∇u + norm(∇u)^(q-2)*∇du  (test/problems_ext_tests.jl:161),
+    evaluated left to right as Julia parses it"""
+    n = _norm(gu)
+    t1 = (((q - 2) * n ** (q - 4)) * _dot(gu, gdu))[:, None] * gu
+    t2 = (n ** (q - 2))[:, None] * gdu
+    return t1 + t2
+
+
+def element_vectors_plaplace_residual(coords, cell_nodes, cell_dofs, tab, free_values, dirichlet_values, q,
+                                      alpha=1.0, f_const=1.0, f_qp=None):
+    """be[cell, i] = Σ_p ((α·(∇φ_i⋅flux(∇u_h) − f φ_i))·dV_p): the residual of test/problems_ext_tests.jl:162
+    (`∇(v,x)⋅GT.call(flux,∇(u,x)) - v(x)`, f ≡ 1) and of test/assembly_tests.jl:685 (`- f(x)*v(x)`, f sampled)."""
+    nc = cell_nodes.shape[0]
+    nq, nls = tab["N"].shape
+    uc = field_cell_values(cell_dofs, free_values, dirichlet_values)
+    be = np.zeros((nc, nls))
+    for p in range(nq):
+        g, dV = _physical_gradients(coords, cell_nodes, tab, p)
+        fl = plaplace_flux(_field_gradient(uc, g), q)
+        f = f_const if f_qp is None else np.asarray(f_qp, dtype=np.float64).reshape(nc, nq)[:, p]
+        for i in range(nls):
+            be[:, i] += (alpha * (_dot(g[i], fl) - f * tab["N"][p, i])) * dV
+    return be
+
+
+def element_matrices_plaplace_jacobian(coords, cell_nodes, cell_dofs, tab, free_values, dirichlet_values, q, alpha=1.0):
+    """be[cell, r, c] = Σ_p ((α·(∇φ_c⋅dflux(∇φ_r, ∇u_h)))·dV_p), du = φ_r, v = φ_c (the form is symmetric
+    in (du, v) up to rounding) — the Jacobian of test/problems_ext_tests.jl:163."""
+    nc = cell_nodes.shape[0]
+    nq, nls = tab["N"].shape
+    uc = field_cell_values(cell_dofs, free_values, dirichlet_values)
+    be = np.zeros((nc, nls, nls))
+    for p in range(nq):
+        g, dV = _physical_gradients(coords, cell_nodes, tab, p)
+        gu = _field_gradient(uc, g)
+        for c in range(nls):
+            for r in range(nls):
+                be[:, r, c] += (alpha * _dot(g[c], plaplace_dflux(g[r], gu, q))) * dV
+    return be
+
+
+def assemble_scalar_field(kind, coords, cell_nodes, cell_dofs, tab, free_values, dirichlet_values, g_qp=None):
+    """assemble_scalar (problems.jl:173-190; loop compiler.jl:1073-1083): s = init; for face, for point: s += integrand·dV.
+    kind: SCALAR_VOLUME ∫1, SCALAR_L2SQ ∫abs2(u_h − g), SCALAR_H1SQ ∫(∇u_h − ∇g)⋅(∇u_h − ∇g); g sampled at the points
+    (g_qp [n_cells][n_q] values or [n_cells][n_q][D] gradients), absent = 0.  The sum over (cell, point) is returned
+    with numpy's pairwise summation — the order of this reduction is not something 1e-12 can see."""
+    nc = cell_nodes.shape[0]
+    nq, nls = tab["N"].shape
+    uc = field_cell_values(cell_dofs, free_values, dirichlet_values)
+    vals = np.zeros((nc, nq))
+    for p in range(nq):
+        g, dV = _physical_gradients(coords, cell_nodes, tab, p)
+        if kind == SCALAR_VOLUME:
+            t = np.ones(nc)
+        elif kind == SCALAR_L2SQ:
+            u = np.zeros(nc)
+            for a in range(nls):
+                u = u + uc[:, a] * tab["N"][p, a]
+            if g_qp is not None:
+                u = u - np.asarray(g_qp, dtype=np.float64).reshape(nc, nq)[:, p]
+            t = u * u
+        elif kind == SCALAR_H1SQ:
+            gu = _field_gradient(uc, g)
+            if g_qp is not None:
+                gu = gu - np.asarray(g_qp, dtype=np.float64).reshape(nc, nq, -1)[:, p, :]
+            t = _dot(gu, gu)
+        else:
+            raise ValueError(kind)
+        vals[:, p] = t * dV
+    return float(vals.sum())
+
+
+def space_dof_coordinates(coords, cell_nodes, cell_dofs, n_free, n_dirichlet, M_at_nodes, n_comp=1):
+    """node_coordinates(::LagrangeMeshSpace) (space.jl:1876-1897) seen through free_dof_node / dirichlet_dof_node
+    (space.jl:1960-1998), loop for loop: for every cell in order, every local node: x = zero; for lmnode: x +=
+    tab[lnode,lmnode]*x_mnode; the LAST cell holding the node wins.  -> (x_free [n_free,D], x_dirichlet [n_dirichlet,D])"""
+    D = coords.shape[1]
+    xf, xd = np.zeros((n_free, D)), np.zeros((n_dirichlet, D))
+    for cell in range(cell_nodes.shape[0]):
+        mnodes = cell_nodes[cell]
+        for ldof in range(cell_dofs.shape[1]):
+            lnode = ldof // n_comp
+            x = np.zeros(D)
+            for m in range(len(mnodes)):
+                x = x + M_at_nodes[lnode, m] * coords[mnodes[m] - 1]
+            dof = cell_dofs[cell, ldof]
+            if dof > 0:
+                xf[dof - 1] = x
+            else:
+                xd[-dof - 1] = x
+    return xf, xd
+
+
+def assemble_vector_plaplace_residual(coords, cell_nodes, cell_dofs, n_free, tab, free_values, dirichlet_values, q, **kw):
+    be = element_vectors_plaplace_residual(coords, cell_nodes, cell_dofs, tab, free_values, dirichlet_values, q, **kw)
+    I, V = coo_vector(be, cell_dofs, FREE)
+    return dense_vector(I, V, n_free)
+
+
+def assemble_matrix_plaplace_jacobian(coords, cell_nodes, cell_dofs, n_free, tab, free_values, dirichlet_values, q, **kw):
+    be = element_matrices_plaplace_jacobian(coords, cell_nodes, cell_dofs, tab, free_values, dirichlet_values, q, **kw)
+    I, J, V = coo_matrix(be, cell_dofs, cell_dofs, FREE, FREE)
+    return sparse_csc(I, J, V, n_free, n_free)
+
+
+# ---------------------------------------------------------------------------
 # Scatter + compression
 # ---------------------------------------------------------------------------
 def _skip(d, fd):

@@ -1,0 +1,84 @@
+"""State handling of the C ABI: stale inputs, stale plans and out-of-range exchange plans are errors, never silent
+out-of-bounds work on the device."""
+import numpy as np
+import pytest
+
+import gtk_b200
+from gtk_b200 import gt as GT
+from util import make_engine, problem
+
+pytestmark = pytest.mark.gpu
+E = gtk_b200.engine
+
+
+def test_fused_call_requires_one_measure():
+    mesh = GT.cartesian_mesh((0, 1, 0, 1, 0, 1), (3, 3, 3))
+    Ω, Γ = GT.interior(mesh), GT.boundary(mesh, ["2-face-2"])
+    V = GT.lagrange_space(Ω, 1, dirichlet_boundary=GT.boundary(mesh, ["2-face-1"]))
+    dΩ, dΓ = GT.measure(Ω, 2), GT.measure(Γ, 2)
+    a = lambda u, v: GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dΩ)
+    l = lambda v: GT.integrate(lambda x: GT.analytical_field(lambda x: x[0])(x) * v(x), dΓ)
+    with pytest.raises(GT.UnsupportedFormError):
+        GT.assemble_matrix_and_vector(a, l, np.float64, V, V)
+    with pytest.raises(GT.UnsupportedFormError):
+        GT.assemble_matrix_and_vector_with_free_and_dirichlet_columns(a, l, np.float64, V, V)
+
+
+def test_new_mesh_invalidates_space_and_tabulation():
+    mesh, V, tab = problem((3, 3, 3))
+    eng = make_engine(mesh, V, tab)
+    eng.matrix_symbolic()
+    eng.matrix_numeric(E.FORM_LAPLACE)
+    big, Vb, _ = problem((5, 5, 5))
+    eng.set_mesh(big.node_coordinates, big.cell_nodes)
+    with pytest.raises(E.GtkError):           # the old (smaller) cell_dofs must not be read with the new cell count
+        eng.matrix_symbolic()
+    eng.set_space(Vb.cell_dofs, Vb.n_free, Vb.n_dirichlet)
+    eng.matrix_symbolic()
+    with pytest.raises(E.GtkError):           # tabulation belongs to the previous setup
+        eng.matrix_numeric(E.FORM_MASS)
+    eng.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+    eng.matrix_numeric(E.FORM_MASS)
+    eng.close()
+
+
+def test_exchange_plan_is_range_checked_and_dies_with_its_pattern():
+    mesh, V, tab = problem((3, 3, 3))
+    eng = make_engine(mesh, V, tab)
+    with pytest.raises(E.GtkError):
+        eng.comm_set_exchange(1, [0], [], [], [])            # before the symbolic phase
+    nnz = eng.matrix_symbolic()
+    with pytest.raises(E.GtkError):
+        eng.comm_set_exchange(1, [nnz], [], [], [])
+    with pytest.raises(E.GtkError):
+        eng.comm_set_exchange(1, [], [V.n_free], [], [])
+    with pytest.raises(E.GtkError):
+        eng.comm_set_exchange(1, [], [], [-1], [])
+    eng.comm_set_exchange(1, [0, 1], [0], [2], [1])
+    assert eng.comm_ghost_info(0) == 3 and eng.comm_ghost_info(1) == 2
+    eng.matrix_symbolic()                                    # new pattern: the plan of the old one is gone
+    assert eng.comm_ghost_info(0) == 0 and eng.comm_ghost_info(1) == 0
+    eng.close()
+
+
+def test_widening_the_active_cells_reclassifies_affine_layers():
+    """the affine kernel may only be used if EVERY active cell layer is affine"""
+    mesh, V, tab = problem((6, 6, 6))
+    X = mesh.node_coordinates.copy()
+    top = X[:, 2] > 0.7
+    inner = ~gtk_b200.hostprep.boundary_node_mask(mesh)
+    X[top & inner, 0] += 0.03 * np.sin(7 * X[top & inner, 1])            # non-affine cells in the upper layers only
+    eng = make_engine(mesh, V, tab)
+    eng.update_coordinates(X)
+    eng.matrix_symbolic()
+    eng.set_active_cells(0, 36 * 2)
+    eng.assemble_matrix_and_vector(E.FORM_LAPLACE, {}, E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+    assert eng.info(5) == 2                                              # affine kernel on the affine layers
+    eng.set_active_cells(0, 36 * 6)
+    nz, b = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, {}, E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+    assert eng.info(5) == 1                                              # general sweep now
+    import gt_oracle as O
+    from util import tab_dict
+    ref = O.assemble_matrix(O.LAPLACE, X, mesh.cell_nodes, V.cell_dofs, V.n_free, V.n_dirichlet, tab_dict(tab))
+    assert np.abs(nz - ref[2]).max() <= 1e-12 * np.abs(ref[2]).max()
+    eng.close()

@@ -269,6 +269,8 @@ def test_every_entry_point_rejects_a_null_context(built_library):
         "gtk_profile_get": (z, 0, z, z), "gtk_comm_init": (z, 0, 1, z), "gtk_comm_set_exchange": (z, 1, 0, z, 0, z, 0, z, 0, z),
         "gtk_comm_sum_ghost_rows": (z,), "gtk_assemble_and_sum_ghost_rows_device": (z, 1, z, 101, z),
         "gtk_comm_p2p_export": (z, 0, z), "gtk_comm_p2p_import": (z, 0, z),
+        "gtk_field_set_values": (z, z, z), "gtk_field_set_values_device": (z, z, z), "gtk_field_get_values": (z, z, z),
+        "gtk_field_axpy_free": (z, 1.0, z), "gtk_space_dof_coordinates": (z, z, z, z), "gtk_scalar_assemble": (z, 201, z, z),
     }
     for name, args in calls.items():
         rc = getattr(lib, name)(*args)
@@ -278,24 +280,3 @@ def test_every_entry_point_rejects_a_null_context(built_library):
     assert b"null" in lib.gtk_last_error(z).lower()
     covered = set(calls) | {"gtk_info", "gtk_comm_ghost_info", "gtk_profile_count", "gtk_last_error", "gtk_version", "gtk_create", "gtk_comm_unique_id"}
     assert covered == set(E.ABI_SYMBOLS), set(E.ABI_SYMBOLS) ^ covered
-
-
-def test_dirichlet_interpolation_and_solution_field():
-    mesh = GT.cartesian_mesh((0, 1, 0, 2, 0, 1), (3, 4, 2))
-    V = GT.lagrange_space(GT.interior(mesh), 2, dirichlet_boundary=GT.boundary(mesh, ["2-face-1", "2-face-4"]))
-    g = lambda x: 1.0 + x[0] - 2.0 * x[1] * x[2]
-    xd = GT.interpolate_dirichlet(g, V)
-    assert np.allclose(xd, g(V.data.dirichlet_dof_nodes.T))
-    x = g(V.data.free_dof_nodes.T)
-    uh = GT.solution_field(V, x, xd)
-    # the field reproduces g at every local node of every cell (order-2 lattice of each cell)
-    lat = np.array(O._lattice(3, 2), dtype=np.float64) / 2
-    X = mesh.node_coordinates[mesh.cell_nodes.astype(np.int64) - 1]
-    xl = X[:, None, 0, :] + lat[None] * (X[:, -1, :] - X[:, 0, :])[:, None, :]
-    assert np.allclose(uh, g(np.moveaxis(xl, -1, 0)))
-    Vv = GT.lagrange_space(GT.interior(mesh), 1, dirichlet_boundary=GT.boundary(mesh), tensor_size=(3,))
-    gv = lambda x: np.stack([x[0], 2 * x[1], -x[2]])
-    xdv = GT.interpolate_dirichlet(gv, Vv)
-    comp = GT._dirichlet_component(Vv)
-    ref = gv(Vv.data.dirichlet_dof_nodes.T)
-    assert np.allclose(xdv, ref[comp, np.arange(xdv.size)])

@@ -130,3 +130,36 @@ def test_c_oracle_matches_numpy_oracle_on_high_order_elements(cells, order):
     assert np.array_equal(out[0], cp) and np.array_equal(out[1], rv)
     assert_values_close(out[2], nz)
     assert_values_close(out[3], b)
+
+
+def test_oracle_reproduces_the_reference_plaplacian_golden():
+    """The ONE numeric known-answer the reference's tests hold on the assembly path: the L2 norm of the discrete
+    p-Laplacian solution, 0.09133166701839236 (test/problems_ext_tests.jl:148-172; same forms in
+    test/assembly_tests.jl:675-701).  It depends on the whole oracle chain — cartesian_mesh coordinates, Dirichlet
+    partition, Q1 tabulation, Gauss rule, J / dV / Jᵀ\\∇̂N, DiscreteField gradients, element vectors and matrices,
+    COO → CSC compression and the scalar integral — so reproducing it to 1e-10 (the reference's own tolerance; we get
+    ~1e-17) pins the oracle against a number the reference holds."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    mesh, V, tab = problem((10, 10), order=1, bc="boundary", domain=(0, 1, 0, 1))
+    td = tab_dict(tab)
+    X, CN, CD = mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs
+    x = np.random.default_rng(0).random(V.n_free)           # GT.rand_field: random free values, zero Dirichlet values
+    xd = np.zeros(V.n_dirichlet)
+    q = 3
+    R = lambda x: O.assemble_vector_plaplace_residual(X, CN, CD, V.n_free, td, x, xd, q)
+    for it in range(60):
+        r = R(x)
+        nr = np.linalg.norm(r)
+        if nr < 1e-13:
+            break
+        cp, rv, nz = O.assemble_matrix_plaplace_jacobian(X, CN, CD, V.n_free, td, x, xd, q)
+        dx = spl.spsolve(sp.csc_matrix((nz, rv - 1, cp - 1), shape=(V.n_free, V.n_free)), -r)
+        t = 1.0
+        while np.linalg.norm(R(x + t * dx)) >= (1 - 1e-4 * t) * nr and t > 1e-8:
+            t *= 0.5
+        x = x + t * dx
+    else:
+        raise AssertionError("Newton did not converge")
+    uhl2 = np.sqrt(O.assemble_scalar_field(O.SCALAR_L2SQ, X, CN, CD, td, x, xd))
+    assert abs(uhl2 - 0.09133166701839236) < 1.0e-10, uhl2
