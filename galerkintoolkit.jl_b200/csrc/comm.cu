@@ -20,6 +20,7 @@
 // NCCL is dlopen'ed so that single-GPU users need no NCCL at all.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <cub/cub.cuh>
 #include <algorithm>
 #include <cstring>
 #include "gtk_internal.h"
@@ -37,6 +38,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -59,11 +61,12 @@ NcclApi& nccl() {
   LOAD(CommDestroy, "ncclCommDestroy");
   LOAD(Send, "ncclSend");
   LOAD(Recv, "ncclRecv");
+  LOAD(AllGather, "ncclAllGather");
   LOAD(GroupStart, "ncclGroupStart");
   LOAD(GroupEnd, "ncclGroupEnd");
   LOAD(GetErrorString, "ncclGetErrorString");
 #undef LOAD
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart &&
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllGather && api.GroupStart &&
            api.GroupEnd && api.GetErrorString;
   return api;
 }
@@ -96,8 +99,9 @@ struct GhostPlan {
   std::vector<Peer> peers;   // sorted by rank
   cudaStream_t side = nullptr;          // pack + NCCL run here while the rest of the sweep runs on ctx->stream
   cudaEvent_t ev_first = nullptr, ev_xchg = nullptr;
+  bool p2p_off = false;                 // the ranks agreed to stay on NCCL (gtk_comm_build_exchange could not map every block)
   bool p2p_ready() const {
-    if (peers.empty() || getenv("GTK_DISABLE_P2P")) return false;
+    if (peers.empty() || p2p_off || getenv("GTK_DISABLE_P2P")) return false;
     for (auto& p : peers) if (!p.remote_block || !p.ipc_block) return false;
     return true;
   }
@@ -201,6 +205,34 @@ int32_t upload_idx(gtk_ctx* ctx, T** dst, const T* src, int64_t n) {
 
 }  // namespace
 
+// Takes ownership of the four device index arrays of `p` (allocated with gtk_dev_alloc), allocates its buffers and makes
+// it the plan for p.rank (replacing a previous one: the pair then restarts its peer-memory protocol, both sides must
+// re-export / re-import).
+static int32_t install_peer(gtk_ctx* ctx, Peer p) {
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  if (!g) { g = new GhostPlan(); ctx->ghost = g; }
+  for (size_t i = 0; i < g->peers.size(); ++i)
+    if (g->peers[i].rank == p.rank) { free_peer(ctx, g->peers[i]); g->peers.erase(g->peers.begin() + i); break; }
+  int32_t rc;
+  const int64_t n_send = p.n_send_nz + p.n_send_b, n_recv = p.n_recv_nz + p.n_recv_b;
+  if (n_send) if ((rc = gtk_dev_alloc(ctx, (void**)&p.send_buf, sizeof(double) * n_send))) return rc;
+  // receive buffer + flag header in ONE raw allocation (not pooled): it is exported to the peer over CUDA IPC
+  p.ipc_bytes = sizeof(double) * (size_t)(P2P_HDR + n_recv);
+  GTK_CK(cudaMalloc(&p.ipc_block, p.ipc_bytes));
+  ctx->bytes_held += (int64_t)p.ipc_bytes;
+  GTK_CK(cudaMemsetAsync(p.ipc_block, 0, p.ipc_bytes, ctx->stream));
+  p.recv_buf = p.ipc_block + P2P_HDR;
+  GTK_CK(cudaMalloc(&p.done_ctr, 2 * sizeof(unsigned int)));
+  GTK_CK(cudaMemsetAsync(p.done_ctr, 0, 2 * sizeof(unsigned int), ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  if ((rc = gtk_fastq1_min_layer(ctx, p.send_nz, p.n_send_nz, p.send_rows, p.n_send_b, &p.min_send_layer, nullptr))) return rc;
+  { int lo_unused = -1;
+    if ((rc = gtk_fastq1_min_layer(ctx, p.recv_nz, p.n_recv_nz, p.recv_rows, p.n_recv_b, &lo_unused, &p.max_recv_layer))) return rc; }
+  g->peers.push_back(p);
+  std::sort(g->peers.begin(), g->peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
+  return GTK_OK;
+}
+
 #define NCCL_CK(call)                                                                          \
   do {                                                                                         \
     ncclResult_t r_ = (call);                                                                  \
@@ -275,10 +307,6 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
     for (int64_t i = 0; i < n_recv_b; ++i) if (recv_rows[i] < 0 || recv_rows[i] >= nr) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_set_exchange: recv_rows entry outside [0, n_rows)");
   }
   GTK_CK(cudaSetDevice(ctx->device));
-  GhostPlan* g = (GhostPlan*)ctx->ghost;
-  if (!g) { g = new GhostPlan(); ctx->ghost = g; }
-  for (size_t i = 0; i < g->peers.size(); ++i)
-    if (g->peers[i].rank == peer) { free_peer(ctx, g->peers[i]); g->peers.erase(g->peers.begin() + i); break; }
   Peer p;
   p.rank = peer;
   p.n_send_nz = n_send_nz; p.n_send_b = n_send_b; p.n_recv_nz = n_recv_nz; p.n_recv_b = n_recv_b;
@@ -287,22 +315,7 @@ int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, con
   if ((rc = upload_idx(ctx, &p.send_rows, send_rows, n_send_b))) return rc;
   if ((rc = upload_idx(ctx, &p.recv_nz, recv_nz, n_recv_nz))) return rc;
   if ((rc = upload_idx(ctx, &p.recv_rows, recv_rows, n_recv_b))) return rc;
-  if (n_send_nz + n_send_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.send_buf, sizeof(double) * (n_send_nz + n_send_b)))) return rc;
-  // receive buffer + flag header in ONE raw allocation (not pooled): it is exported to the peer over CUDA IPC
-  p.ipc_bytes = sizeof(double) * (size_t)(P2P_HDR + n_recv_nz + n_recv_b);
-  GTK_CK(cudaMalloc(&p.ipc_block, p.ipc_bytes));
-  ctx->bytes_held += (int64_t)p.ipc_bytes;
-  GTK_CK(cudaMemsetAsync(p.ipc_block, 0, p.ipc_bytes, ctx->stream));
-  p.recv_buf = p.ipc_block + P2P_HDR;
-  GTK_CK(cudaMalloc(&p.done_ctr, 2 * sizeof(unsigned int)));
-  GTK_CK(cudaMemsetAsync(p.done_ctr, 0, 2 * sizeof(unsigned int), ctx->stream));
-  GTK_CK(cudaStreamSynchronize(ctx->stream));
-  if ((rc = gtk_fastq1_min_layer(ctx, p.send_nz, n_send_nz, p.send_rows, n_send_b, &p.min_send_layer, nullptr))) return rc;
-  { int lo_unused = -1;
-    if ((rc = gtk_fastq1_min_layer(ctx, p.recv_nz, n_recv_nz, p.recv_rows, n_recv_b, &lo_unused, &p.max_recv_layer))) return rc; }
-  g->peers.push_back(p);
-  std::sort(g->peers.begin(), g->peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
-  return GTK_OK;
+  return install_peer(ctx, p);
 }
 
 }  // extern "C"
@@ -531,3 +544,268 @@ int64_t gtk_comm_ghost_info(const gtk_ctx* ctx, int32_t key) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Exchange plan built ON THE DEVICE (gtk_comm_build_exchange).  Block row partition, PartitionedArrays'
+// variable_partition data model: local free row i has global id gid0 + i and rank p owns the global ids
+// [own_start[p], own_start[p+1]).  What the host numpy version (partition.py: ghost_send_lists / match_received /
+// build_exchange_plan) does with Python objects over torch.distributed happens here with three kernels, CUB stream
+// compaction and NCCL (counts: ncclAllGather; (row, column) keys: ncclSend/ncclRecv between the ranks that share rows).
+namespace {
+
+__global__ void k_touch_rows(const int32_t* __restrict__ cell_dofs, int64_t e0, int64_t e1, uint8_t* __restrict__ touched) {
+  for (int64_t e = e0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < e1; e += (int64_t)gridDim.x * blockDim.x) {
+    const int d = cell_dofs[e];
+    if (d > 0) touched[d - 1] = 1;     // same value from every writer
+  }
+}
+
+struct GhostNzPred {   // nz position -> stored in a row of [lo, hi) that the active cells touch
+  const int32_t* rowval; const uint8_t* touched; int64_t lo, hi;
+  __device__ __forceinline__ bool operator()(const int64_t& p) const {
+    const int64_t r = (int64_t)rowval[p] - 1;
+    return r >= lo && r < hi && touched[r];
+  }
+};
+struct GhostRowPred {
+  const uint8_t* touched;
+  __device__ __forceinline__ bool operator()(const int32_t& r) const { return touched[r] != 0; }
+};
+
+// keys of the selected entries: [0,n) global row, [n,2n) global column, [2n, 2n+nb) global row of the b entries
+__global__ void k_ghost_keys(const int64_t* __restrict__ nz_pos, int64_t n, const int32_t* __restrict__ b_rows, int64_t nb,
+                             const int32_t* __restrict__ rowval, const int64_t* __restrict__ colptr, int64_t n_cols, int64_t gid0,
+                             int64_t* __restrict__ keys) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= n) { keys[2 * n + (i - n)] = gid0 + b_rows[i - n]; continue; }
+    const int64_t p = nz_pos[i];
+    int64_t lo = 0, hi = n_cols;            // last column c with colptr[c] <= p
+    while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if (colptr[mid] <= p) lo = mid; else hi = mid - 1; }
+    keys[i] = gid0 + (int64_t)rowval[p] - 1;
+    keys[n + i] = gid0 + lo;
+  }
+}
+
+// owner side: where the announced entries are added.  err bits: 1 row/column not local, 2 entry missing from the pattern,
+// 4 row not owned by this rank
+__global__ void k_match_keys(const int64_t* __restrict__ keys, int64_t n, int64_t nb, const int32_t* __restrict__ rowval,
+                             const int64_t* __restrict__ colptr, int64_t n_rows, int64_t gid0, int64_t own_lo, int64_t own_hi,
+                             int64_t* __restrict__ recv_nz, int32_t* __restrict__ recv_rows, int* __restrict__ err) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i >= n) {
+      const int64_t g = keys[2 * n + (i - n)];
+      if (g < own_lo || g >= own_hi || g - gid0 < 0 || g - gid0 >= n_rows) { atomicOr(err, 4); recv_rows[i - n] = 0; }
+      else recv_rows[i - n] = (int32_t)(g - gid0);
+      continue;
+    }
+    const int64_t gr = keys[i], gc = keys[n + i];
+    const int64_t lr = gr - gid0, lc = gc - gid0;
+    if (lr < 0 || lr >= n_rows || lc < 0 || lc >= n_rows) { atomicOr(err, 1); recv_nz[i] = 0; continue; }
+    if (gr < own_lo || gr >= own_hi) atomicOr(err, 4);
+    int64_t lo = colptr[lc], hi = colptr[lc + 1];
+    const int32_t target = (int32_t)(lr + 1);
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < target) lo = mid + 1; else hi = mid; }
+    if (lo >= colptr[lc + 1] || rowval[lo] != target) { atomicOr(err, 2); recv_nz[i] = 0; }
+    else recv_nz[i] = lo;
+  }
+}
+
+struct Iota64 {   // counting iterator without thrust
+  using value_type = int64_t; using difference_type = int64_t; using pointer = const int64_t*; using reference = int64_t;
+  using iterator_category = std::random_access_iterator_tag;
+  int64_t v;
+  __host__ __device__ int64_t operator[](int64_t i) const { return v + i; }
+  __host__ __device__ int64_t operator*() const { return v; }
+  __host__ __device__ Iota64 operator+(int64_t i) const { return Iota64{v + i}; }
+};
+struct Iota32 {
+  using value_type = int32_t; using difference_type = int64_t; using pointer = const int32_t*; using reference = int32_t;
+  using iterator_category = std::random_access_iterator_tag;
+  int64_t v;
+  __host__ __device__ int32_t operator[](int64_t i) const { return (int32_t)(v + i); }
+  __host__ __device__ int32_t operator*() const { return (int32_t)v; }
+  __host__ __device__ Iota32 operator+(int64_t i) const { return Iota32{v + i}; }
+};
+
+}  // namespace
+
+extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int64_t* own_start) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (!own_start) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_build_exchange: own_start is null");
+  if (!ctx->comm) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_build_exchange: call gtk_comm_init first");
+  MatSym& m = ctx->ms;
+  if (!m.ready || ctx->cur_slot != 0 || m.rows_fd != GTK_FREE || m.cols_fd != GTK_FREE)
+    GTK_FAIL(GTK_ERR_STATE, "gtk_comm_build_exchange: needs the free x free pattern of slot 0 (gtk_matrix_symbolic)");
+  const int W = ctx->n_ranks, me = ctx->rank;
+  const int64_t n = m.n_rows;
+  for (int p = 0; p < W; ++p) if (own_start[p] > own_start[p + 1]) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_build_exchange: own_start must be non-decreasing");
+  GTK_CK(cudaSetDevice(ctx->device));
+  gtk_comm_release_plan(ctx);
+  cudaStream_t st = ctx->stream;
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  int32_t rc = GTK_OK;
+  // 1. rows the active cells contribute to
+  uint8_t* touched = nullptr;
+  GTK_CK(gtk_cuda_malloc(ctx, &touched, (size_t)(n ? n : 1)));
+  GTK_CK(cudaMemsetAsync(touched, 0, (size_t)(n ? n : 1), st));
+  {
+    const int64_t a0 = ctx->act_count < 0 ? 0 : ctx->act_first, a1 = ctx->act_count < 0 ? ctx->n_cells : ctx->act_first + ctx->act_count;
+    if (a1 > a0) k_touch_rows<<<grid_for((a1 - a0) * ctx->nld), 256, 0, st>>>(ctx->cell_dofs, a0 * ctx->nld, a1 * ctx->nld, touched);
+  }
+  // 2. per peer: nz positions (CSC order) and b rows stored in the rows that peer owns
+  struct Send { int peer; int64_t lo, hi, n_nz = 0, n_b = 0; int64_t* nz = nullptr; int32_t* rows = nullptr; int64_t* keys = nullptr; };
+  std::vector<Send> sends;
+  int64_t* d_cnt = nullptr;
+  GTK_CK(gtk_cuda_malloc(ctx, &d_cnt, 2 * sizeof(int64_t)));
+  void* tmp = nullptr; size_t tmp_bytes = 0;
+  for (int p = 0; p < W; ++p) {
+    if (p == me) continue;
+    Send sd; sd.peer = p;
+    sd.lo = std::max<int64_t>(own_start[p] - gid0, 0); sd.hi = std::min<int64_t>(own_start[p + 1] - gid0, n);
+    if (sd.hi <= sd.lo) continue;
+    int64_t* cand_nz = nullptr; int32_t* cand_rows = nullptr;
+    GTK_CK(gtk_cuda_malloc(ctx, &cand_nz, sizeof(int64_t) * (size_t)(m.nnz ? m.nnz : 1)));
+    GTK_CK(gtk_cuda_malloc(ctx, &cand_rows, sizeof(int32_t) * (size_t)(sd.hi - sd.lo)));
+    size_t need1 = 0, need2 = 0;
+    GhostNzPred pn{m.rowval, touched, sd.lo, sd.hi};
+    GhostRowPred pr{touched};
+    cub::DeviceSelect::If(nullptr, need1, Iota64{0}, cand_nz, d_cnt, m.nnz, pn, st);
+    cub::DeviceSelect::If(nullptr, need2, Iota32{sd.lo}, cand_rows, d_cnt + 1, sd.hi - sd.lo, pr, st);
+    const size_t need = std::max(need1, need2);
+    if (need > tmp_bytes) { gtk_cuda_free(ctx, tmp); GTK_CK(gtk_cuda_malloc(ctx, &tmp, need)); tmp_bytes = need; }
+    GTK_CK(cub::DeviceSelect::If(tmp, need1, Iota64{0}, cand_nz, d_cnt, m.nnz, pn, st));
+    GTK_CK(cub::DeviceSelect::If(tmp, need2, Iota32{sd.lo}, cand_rows, d_cnt + 1, sd.hi - sd.lo, pr, st));
+    int64_t h_cnt[2];
+    GTK_CK(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    GTK_CK(cudaStreamSynchronize(st));
+    sd.n_nz = h_cnt[0]; sd.n_b = h_cnt[1];
+    if (sd.n_nz + sd.n_b) {   // exact-size copies owned by the plan (allocated the way free_peer releases them)
+      if (sd.n_nz) { if ((rc = gtk_dev_alloc(ctx, (void**)&sd.nz, sizeof(int64_t) * sd.n_nz))) return rc;
+                     GTK_CK(cudaMemcpyAsync(sd.nz, cand_nz, sizeof(int64_t) * sd.n_nz, cudaMemcpyDeviceToDevice, st)); }
+      if (sd.n_b) { if ((rc = gtk_dev_alloc(ctx, (void**)&sd.rows, sizeof(int32_t) * sd.n_b))) return rc;
+                    GTK_CK(cudaMemcpyAsync(sd.rows, cand_rows, sizeof(int32_t) * sd.n_b, cudaMemcpyDeviceToDevice, st)); }
+      GTK_CK(gtk_cuda_malloc(ctx, &sd.keys, sizeof(int64_t) * (size_t)(2 * sd.n_nz + sd.n_b)));
+      k_ghost_keys<<<grid_for(sd.n_nz + sd.n_b), 256, 0, st>>>(sd.nz, sd.n_nz, sd.rows, sd.n_b, m.rowval, m.colptr, m.n_cols, gid0, sd.keys);
+      GTK_CK(cudaGetLastError());
+      sends.push_back(sd);
+    }
+    GTK_CK(cudaStreamSynchronize(st));
+    gtk_cuda_free(ctx, cand_nz); gtk_cuda_free(ctx, cand_rows);
+  }
+  gtk_cuda_free(ctx, tmp); gtk_cuda_free(ctx, touched); gtk_cuda_free(ctx, d_cnt);
+  // 3. everybody learns how much it receives from whom
+  std::vector<int64_t> row(2 * W, 0), mat((size_t)2 * W * W, 0);
+  for (auto& sd : sends) { row[2 * sd.peer] = sd.n_nz; row[2 * sd.peer + 1] = sd.n_b; }
+  int64_t *d_row = nullptr, *d_mat = nullptr;
+  GTK_CK(gtk_cuda_malloc(ctx, &d_row, sizeof(int64_t) * 2 * W));
+  GTK_CK(gtk_cuda_malloc(ctx, &d_mat, sizeof(int64_t) * 2 * W * W));
+  GTK_CK(cudaMemcpyAsync(d_row, row.data(), sizeof(int64_t) * 2 * W, cudaMemcpyHostToDevice, st));
+  NCCL_CK(nccl().AllGather(d_row, d_mat, (size_t)2 * W, ncclInt64, comm, st));
+  GTK_CK(cudaMemcpyAsync(mat.data(), d_mat, sizeof(int64_t) * 2 * W * W, cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
+  gtk_cuda_free(ctx, d_row); gtk_cuda_free(ctx, d_mat);
+  // 4. keys travel to the owners
+  struct Recv { int peer; int64_t n_nz, n_b; int64_t* keys = nullptr; };
+  std::vector<Recv> recvs;
+  for (int q = 0; q < W; ++q) {
+    if (q == me) continue;
+    const int64_t rn = mat[((size_t)q * W + me) * 2], rb = mat[((size_t)q * W + me) * 2 + 1];
+    if (rn + rb == 0) continue;
+    Recv rv{q, rn, rb};
+    GTK_CK(gtk_cuda_malloc(ctx, &rv.keys, sizeof(int64_t) * (size_t)(2 * rn + rb)));
+    recvs.push_back(rv);
+  }
+  NCCL_CK(nccl().GroupStart());
+  for (auto& sd : sends) NCCL_CK(nccl().Send(sd.keys, (size_t)(2 * sd.n_nz + sd.n_b), ncclInt64, sd.peer, comm, st));
+  for (auto& rv : recvs) NCCL_CK(nccl().Recv(rv.keys, (size_t)(2 * rv.n_nz + rv.n_b), ncclInt64, rv.peer, comm, st));
+  NCCL_CK(nccl().GroupEnd());
+  // 5. owners locate the announced entries in their own pattern
+  int* d_err = nullptr;
+  GTK_CK(gtk_cuda_malloc(ctx, &d_err, sizeof(int)));
+  GTK_CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+  std::vector<Peer> peers;
+  auto peer_of = [&](int r) -> Peer& {
+    for (auto& p : peers) if (p.rank == r) return p;
+    peers.emplace_back(); peers.back().rank = r; return peers.back();
+  };
+  for (auto& sd : sends) { Peer& p = peer_of(sd.peer); p.n_send_nz = sd.n_nz; p.n_send_b = sd.n_b; p.send_nz = sd.nz; p.send_rows = sd.rows; }
+  for (auto& rv : recvs) {
+    Peer& p = peer_of(rv.peer);
+    p.n_recv_nz = rv.n_nz; p.n_recv_b = rv.n_b;
+    if (rv.n_nz) if ((rc = gtk_dev_alloc(ctx, (void**)&p.recv_nz, sizeof(int64_t) * rv.n_nz))) return rc;
+    if (rv.n_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.recv_rows, sizeof(int32_t) * rv.n_b))) return rc;
+    k_match_keys<<<grid_for(rv.n_nz + rv.n_b), 256, 0, st>>>(rv.keys, rv.n_nz, rv.n_b, m.rowval, m.colptr, n, gid0, own_start[me], own_start[me + 1],
+                                                            p.recv_nz, p.recv_rows, d_err);
+    GTK_CK(cudaGetLastError());
+  }
+  int h_err = 0;
+  GTK_CK(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
+  gtk_cuda_free(ctx, d_err);
+  for (auto& sd : sends) gtk_cuda_free(ctx, sd.keys);
+  for (auto& rv : recvs) gtk_cuda_free(ctx, rv.keys);
+  if (h_err) {
+    for (auto& p : peers) free_peer(ctx, p);
+    GTK_FAIL(GTK_ERR_INVALID, std::string("gtk_comm_build_exchange: a peer announced a ghost-row entry that ") +
+                                  ((h_err & 1) ? "is not a local dof of the owner; " : "") + ((h_err & 2) ? "is missing from the owner's sparsity pattern; " : "") +
+                                  ((h_err & 4) ? "lies in a row the receiver does not own; " : ""));
+  }
+  std::sort(peers.begin(), peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
+  for (auto& p : peers) if ((rc = install_peer(ctx, p))) return rc;
+  return GTK_OK;   // transport: gtk_comm_connect_peer_memory (collective, also for a rank without peers)
+}
+
+// Second collective half of gtk_comm_build_exchange, separate so that EVERY rank (also one without peers) reaches the
+// agreement AllGather: swaps the CUDA IPC handles of the receive blocks over NCCL and imports them; if any rank failed
+// to map a block all ranks stay on NCCL.
+extern "C" int32_t gtk_comm_connect_peer_memory(gtk_ctx* ctx) {
+  if (!ctx) return GTK_ERR_INVALID;
+  if (!ctx->comm) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_connect_peer_memory: call gtk_comm_init first");
+  GTK_CK(cudaSetDevice(ctx->device));
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  cudaStream_t st = ctx->stream;
+  ncclComm_t comm = (ncclComm_t)ctx->comm;
+  const int W = ctx->n_ranks;
+  int ok = getenv("GTK_DISABLE_P2P") ? 0 : 1;
+  const size_t np = g ? g->peers.size() : 0;
+  unsigned char* d_h = nullptr;   // [np] mine, [np] theirs, 64 bytes each
+  GTK_CK(gtk_cuda_malloc(ctx, &d_h, 128 * (np ? np : 1)));
+  std::vector<unsigned char> mine(64 * (np ? np : 1), 0), theirs(64 * (np ? np : 1), 0);
+  for (size_t i = 0; i < np; ++i) {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, g->peers[i].ipc_block) != cudaSuccess) { cudaGetLastError(); ok = 0; memset(&h, 0, sizeof(h)); }
+    memcpy(mine.data() + 64 * i, &h, 64);
+  }
+  if (np) GTK_CK(cudaMemcpyAsync(d_h, mine.data(), 64 * np, cudaMemcpyHostToDevice, st));
+  NCCL_CK(nccl().GroupStart());
+  for (size_t i = 0; i < np; ++i) {
+    NCCL_CK(nccl().Send(d_h + 64 * i, 64, ncclUint8, g->peers[i].rank, comm, st));
+    NCCL_CK(nccl().Recv(d_h + 64 * (np + i), 64, ncclUint8, g->peers[i].rank, comm, st));
+  }
+  NCCL_CK(nccl().GroupEnd());
+  if (np) GTK_CK(cudaMemcpyAsync(theirs.data(), d_h + 64 * np, 64 * np, cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
+  if (ok) for (size_t i = 0; i < np; ++i) {
+    Peer& p = g->peers[i];
+    if (p.remote_block) { cudaIpcCloseMemHandle(p.remote_block); p.remote_block = nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, theirs.data() + 64 * i, 64);
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    p.remote_block = (double*)ptr;
+  }
+  // agreement: one int per rank
+  int *d_ok = nullptr, *d_all = nullptr;
+  GTK_CK(gtk_cuda_malloc(ctx, &d_ok, sizeof(int)));
+  GTK_CK(gtk_cuda_malloc(ctx, &d_all, sizeof(int) * W));
+  GTK_CK(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+  NCCL_CK(nccl().AllGather(d_ok, d_all, 1, ncclInt32, comm, st));
+  std::vector<int> all(W, 0);
+  GTK_CK(cudaMemcpyAsync(all.data(), d_all, sizeof(int) * W, cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
+  gtk_cuda_free(ctx, d_h); gtk_cuda_free(ctx, d_ok); gtk_cuda_free(ctx, d_all);
+  bool all_ok = true;
+  for (int v : all) all_ok = all_ok && v != 0;
+  if (g) g->p2p_off = !all_ok;
+  return GTK_OK;
+}

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "gtk_assemble_and_sum_ghost_rows_device", "gtk_select_matrix", "gtk_matvec_add_device", "gtk_matvec_add", "gtk_set_manifold_dim", "gtk_set_vector", "gtk_comm_p2p_export", "gtk_comm_p2p_import",
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
     "gtk_field_set_values", "gtk_field_set_values_device", "gtk_field_get_values", "gtk_field_axpy_free",
-    "gtk_space_dof_coordinates", "gtk_scalar_assemble",
+    "gtk_space_dof_coordinates", "gtk_scalar_assemble", "gtk_comm_build_exchange", "gtk_comm_connect_peer_memory",
 ]
 
 
@@ -114,6 +114,8 @@ def load_library() -> C.CDLL:
         "gtk_field_axpy_free": (i32, [vp, C.c_double, vp]),
         "gtk_space_dof_coordinates": (i32, [vp, vp, vp, vp]),
         "gtk_scalar_assemble": (i32, [vp, i32, C.POINTER(FormParams), C.POINTER(C.c_double)]),
+        "gtk_comm_build_exchange": (i32, [vp, i64, vp]),
+        "gtk_comm_connect_peer_memory": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -267,9 +269,9 @@ class Engine:
         self.n_cols = self._n_free if cols == FREE else self._n_diri
         return self.nnz
 
-    def matrix_pattern(self):
+    def matrix_pattern(self, want_rowval: bool = True):
         colptr = np.empty(self.n_cols + 1, dtype=np.int32)
-        rowval = np.empty(self.nnz, dtype=np.int32)
+        rowval = np.empty(self.nnz, dtype=np.int32) if want_rowval else None
         self._ck(self.lib.gtk_matrix_pattern(self.h, _ptr(colptr), _ptr(rowval)))
         return colptr, rowval
 
@@ -418,6 +420,14 @@ class Engine:
         rn = np.ascontiguousarray(recv_nz, dtype=np.int64); rr = _i32(recv_rows)
         self._ck(self.lib.gtk_comm_set_exchange(self.h, int(peer), sn.size, _ptr(sn), sr.size, _ptr(sr),
                                                 rn.size, _ptr(rn), rr.size, _ptr(rr)))
+
+    def comm_build_exchange(self, gid0: int, own_start):
+        """device-side exchange plan for a block row partition (collective over the NCCL communicator)"""
+        os_ = np.ascontiguousarray(own_start, dtype=np.int64)
+        self._ck(self.lib.gtk_comm_build_exchange(self.h, int(gid0), _ptr(os_)))
+
+    def comm_connect_peer_memory(self):
+        self._ck(self.lib.gtk_comm_connect_peer_memory(self.h))
 
     def comm_ghost_info(self, key: int) -> int:
         return int(self.lib.gtk_comm_ghost_info(self.h, key))

@@ -40,6 +40,8 @@ class SlabPart:
     n_global_free: int
     k0: int
     k1: int
+    gid0: int = 0                # 0-based global id of local free row 0 (local rows are numbered in increasing global id)
+    own_start: Optional[np.ndarray] = None   # [world+1] rank p owns the 0-based global ids [own_start[p], own_start[p+1])
 
 
 def _free_1d(n_nodes: int, lo_tag: bool, hi_tag: bool) -> np.ndarray:
@@ -109,8 +111,10 @@ def slab_problem(domain: Sequence[float], cells: Sequence[int], rank: int, world
     space = H.LagrangeSpace(mesh, 1, 1, "Q", np.ascontiguousarray(cell_dofs), n_free_loc, local.n_nodes - n_free_loc,
                             free_dof_nodes=coords[free], dirichlet_dof_nodes=coords[~free])
     first_active = (k0 - kc0) * n1 * n2
+    own_start = np.array([int(fz[:r[0]].sum()) * per_layer for r in slab_ranges(n3, world)] + [int(fz.sum()) * per_layer],
+                         dtype=np.int64)
     return SlabPart(rank, world, mesh, space, (first_active, (k1 - k0) * n1 * n2), row_gid, row_owner,
-                    int(fz.sum()) * per_layer, k0, k1)
+                    int(fz.sum()) * per_layer, k0, k1, below, own_start)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -265,4 +269,29 @@ def attach(engine, part: SlabPart, tab, dist):
                 print(f"[gtk] peer-memory transport unavailable ({bad}); ghost rows go over NCCL", flush=True)
     owned = owned_rows_mask(part)
     n_owned_nnz = int(owned[rowval.astype(np.int64) - 1].sum())
+    return colptr, rowval, n_owned_nnz
+
+
+def attach_device(engine, part: SlabPart, tab, dist, want_pattern: bool = True):
+    """attach() with the exchange plan built on the device (gtk_comm_build_exchange: CUB stream compaction of the ghost
+    entries, NCCL all-gather of the counts, NCCL send/recv of the (row, column) keys, binary-search matching kernel) and the
+    peer-memory handles swapped over NCCL (gtk_comm_connect_peer_memory).  `dist` only carries the 128-byte NCCL id.
+    Returns (colptr, rowval or None, n_owned_nnz); the number of owned nonzeros comes from colptr alone (the pattern of a
+    U = V form is structurally symmetric: nnz of the owned rows = nnz of the owned columns)."""
+    m, V = part.mesh, part.space
+    engine.set_mesh(m.node_coordinates, m.cell_nodes)
+    engine.set_space(V.cell_dofs, V.n_free, V.n_dirichlet)
+    engine.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+    engine.set_active_cells(*part.active_cells)
+    engine.matrix_symbolic()
+    engine.vector_symbolic()
+    uid = [type(engine).comm_unique_id() if part.rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    engine.comm_init(part.rank, part.world, uid[0])
+    engine.comm_build_exchange(part.gid0, part.own_start)
+    engine.comm_connect_peer_memory()
+    colptr, rowval = engine.matrix_pattern(want_rowval=want_pattern)
+    lo = int(np.clip(part.own_start[part.rank] - part.gid0, 0, V.n_free))
+    hi = int(np.clip(part.own_start[part.rank + 1] - part.gid0, 0, V.n_free))
+    n_owned_nnz = int(colptr[hi]) - int(colptr[lo])
     return colptr, rowval, n_owned_nnz

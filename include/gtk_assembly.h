@@ -229,6 +229,17 @@ int32_t gtk_comm_init(gtk_ctx* ctx, int32_t rank, int32_t n_ranks, const void* i
 int32_t gtk_comm_set_exchange(gtk_ctx* ctx, int32_t peer, int64_t n_send_nz, const int64_t* send_nz,
                               int64_t n_send_b, const int32_t* send_rows, int64_t n_recv_nz, const int64_t* recv_nz,
                               int64_t n_recv_b, const int32_t* recv_rows);
+/* The same plan built ON THE DEVICE for a block row partition (PartitionedArrays' variable_partition data model,
+ * docs/src/src_jl/manual_mesh_partitioning.jl:14-35): local free row i (0-based) has global id gid0 + i, rank p owns the
+ * global ids [own_start[p], own_start[p+1]) (own_start: host, n_ranks + 1 entries).  Rows of the local pattern that another
+ * rank owns and that the ACTIVE cells contribute to are ghost rows: their stored entries (CSC order) and b rows are sent to
+ * the owner, which locates them in its own pattern.  Collective over the communicator of gtk_comm_init (counts:
+ * ncclAllGather; (row, column) keys: ncclSend/ncclRecv); replaces every previous plan.  Needs the free x free pattern of
+ * slot 0.  Errors if an announced entry is missing from the owner's pattern or lies in a row the receiver does not own. */
+int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int64_t* own_start);
+/* Collective: swaps the CUDA IPC handles of all receive blocks over NCCL, imports them, and agrees on the transport (peer
+ * memory if EVERY rank mapped every block, else NCCL for everybody).  Call on every rank after the plan is set. */
+int32_t gtk_comm_connect_peer_memory(gtk_ctx* ctx);
 /* Exchange + add ghost-row nzval and b contributions after a numeric call. */
 int32_t gtk_comm_sum_ghost_rows(gtk_ctx* ctx);
 /* gtk_assemble_matrix_and_vector_device + gtk_comm_sum_ghost_rows in one call, with the exchange overlapped with the

@@ -1,4 +1,5 @@
-/* ORACLE (C) — test infrastructure only; PARITY UNPINNED (see oracle/gt_oracle.py header).
+/* ORACLE (C) — test infrastructure only; parity pinned through oracle/gt_oracle.py (see its header): this file is
+ * cross-checked against the numpy oracle entry by entry (tests/test_oracle_invariants.py).
  *
  * Plain-C restatement of the reference's CPU assembly path, used (a) to cross-check the numpy
  * oracle and (b) as the timed CPU baseline ("kind": "port") of bench.py.  Never linked into the
@@ -12,6 +13,9 @@
  *   3. compress -> sparse(I,J,V,m,n): CSC, rows sorted, duplicates summed in input order,
  *      explicit zeros kept                                  assembly.jl:571-575
  *   4. assemble_vector: COO (I,V) + dense_vector            assembly.jl:175-187, 535-543, 558-569
+ *   5. update_matrix! / update_vector! (gto_reassemble): reset!, rerun the loops into the SAME COO arrays, then
+ *      compress! = PartitionedArrays.sparse_matrix!(A,V,cache): nzval .= 0; nzval[K[k]] += V[k] with the nz index K
+ *      cached by the first compress (no sort)               problems.jl:276-285, 352-361; assembly.jl:577-588
  * Scalar Lagrange spaces, D = 2 or 3, forms LAPLACE(1) / MASS(2), source f = const.
  * The reference is single-threaded; `nthreads` > 1 parallelises only the cell loops (pthreads; this image has no libgomp),
  * writing each cell's triplets at the offset the serial loop would use, so results are identical.
@@ -151,7 +155,8 @@ int gto_assemble(int D, int64_t n_nodes, const double* xyz, int64_t n_cells, int
                  int nld, const int32_t* cell_dofs, int64_t n_free, int nq, const double* w, const double* N,
                  const double* dN, const double* dM, int form, double alpha, double fconst, int32_t* colptr,
                  int32_t* rowval, double* nzval, int64_t cap, int64_t* nnz_out, double* b, int nthreads,
-                 double* t_phase) {
+                 double* t_phase, int64_t* K_out /* NULL or [N_coo]: 0-based nz position of every COO entry (the cache of
+                 sparse_matrix(...; reuse=true)) */) {
   (void)n_nodes;
   double t0 = now_s(), t1, t2, t3;
   /* 1. counting loop */
@@ -233,6 +238,7 @@ int gto_assemble(int D, int64_t n_nodes, const double* xyz, int64_t n_cells, int
       nnz++;
       pi = I[k]; pj = Jc[k];
     }
+    if (K_out) K_out[k] = nnz - 1;
   }
   if (nnz > cap) rc = -1;
   colptr[0] = 1;
@@ -248,4 +254,65 @@ int gto_assemble(int D, int64_t n_nodes, const double* xyz, int64_t n_cells, int
   if (t_phase) { double t4 = now_s(); t_phase[0] = t1 - t0; t_phase[1] = t2 - t1; t_phase[2] = t3 - t2; t_phase[3] = t4 - t3; }
   free(off); free(I); free(Jc); free(V); free(voff); free(VI); free(VV); free(cnt); free(p1); free(p2);
   return rc;
+}
+
+/* N_coo of the matrix (what allocate_matrix counts, assembly.jl:119-153) and of the vector */
+void gto_count(int64_t n_cells, int nld, const int32_t* cell_dofs, int64_t* ncoo_matrix, int64_t* ncoo_vector) {
+  int64_t nm = 0, nv = 0;
+  for (int64_t cell = 0; cell < n_cells; ++cell) {
+    int64_t nf = 0;
+    for (int i = 0; i < nld; ++i) nf += cell_dofs[cell * nld + i] > 0;
+    nm += nf * nf; nv += nf;
+  }
+  *ncoo_matrix = nm; *ncoo_vector = nv;
+}
+
+/* 5. update_matrix! + update_vector! on a cached pattern: I, Jc, V, VI, VV are the allocation's COO arrays (kept between
+ * calls like the reference's `alloc`), K the cached nz index.  t_phase[0..2]: loop / compress! / dense_vector! seconds. */
+int gto_reassemble(int D, const double* xyz, int64_t n_cells, int nln, const int32_t* cell_nodes, int nld,
+                   const int32_t* cell_dofs, int64_t n_free, int nq, const double* w, const double* N, const double* dN,
+                   const double* dM, int form, double alpha, double fconst, int32_t* I, int32_t* Jc, double* V,
+                   int32_t* VI, double* VV, const int64_t* K, int64_t nnz, double* nzval, double* b, int nthreads,
+                   double* t_phase) {
+  double t0 = now_s(), t1, t2;
+  int64_t* off = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_cells + 1));
+  int64_t* voff = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_cells + 1));
+  off[0] = 0; voff[0] = 0;
+  for (int64_t cell = 0; cell < n_cells; ++cell) {   /* reset!: the push cursor restarts; offsets per cell as the serial loop */
+    int64_t nf = 0;
+    for (int i = 0; i < nld; ++i) nf += cell_dofs[cell * nld + i] > 0;
+    off[cell + 1] = off[cell] + nf * nf;
+    voff[cell + 1] = voff[cell] + nf;
+  }
+  loop_args la = {D, xyz, cell_nodes, nln, nld, cell_dofs, nq, w, N, dN, dM, form, alpha, fconst, off, voff, I, Jc, V,
+                  b ? VI : NULL, VV, 0, 0};
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads == 1 || n_cells < 1024) {
+    la.c0 = 0; la.c1 = n_cells;
+    loop_worker(&la);
+  } else {
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+    loop_args* as = (loop_args*)malloc(sizeof(loop_args) * nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+      as[t] = la;
+      as[t].c0 = n_cells * t / nthreads;
+      as[t].c1 = n_cells * (t + 1) / nthreads;
+      pthread_create(&th[t], NULL, loop_worker, &as[t]);
+    }
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    free(th); free(as);
+  }
+  t1 = now_s();
+  /* compress!(alloc, A, cache) -> sparse_matrix!(A, V, K) */
+  const int64_t ncoo = off[n_cells];
+  for (int64_t p = 0; p < nnz; ++p) nzval[p] = 0.0;
+  for (int64_t k = 0; k < ncoo; ++k) nzval[K[k]] += V[k];
+  t2 = now_s();
+  if (b) {   /* dense_vector!(b, I, V) */
+    for (int64_t i = 0; i < n_free; ++i) b[i] = 0.0;
+    for (int64_t k = 0; k < voff[n_cells]; ++k) b[VI[k] - 1] += VV[k];
+  }
+  if (t_phase) { t_phase[0] = t1 - t0; t_phase[1] = t2 - t1; t_phase[2] = now_s() - t2; }
+  free(off); free(voff);
+  return 0;
 }

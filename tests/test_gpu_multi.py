@@ -59,6 +59,18 @@ def _worker(rank, world, port, cells, dom, q):
         del os.environ["GTK_DISABLE_P2P"]
         eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
         results.append((eng.copy_nzval(), eng.copy_vector()))
+        # the same exchange plan built ON THE DEVICE (gtk_comm_build_exchange + gtk_comm_connect_peer_memory): same counts,
+        # same transport, bitwise the same owned rows
+        eng2 = E.Engine(rank)
+        cp2, rv2, n_owned2 = P.attach_device(eng2, part, tab, dist)
+        assert np.array_equal(cp2, colptr) and np.array_equal(rv2, rowval) and n_owned2 == n_owned
+        assert [eng2.comm_ghost_info(k) for k in range(4)] == [eng.comm_ghost_info(k) for k in range(4)]
+        eng2.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+        results.append((eng2.copy_nzval(), eng2.copy_vector()))
+        eng2.assemble_matrix_and_vector_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+        eng2.comm_sum_ghost_rows()
+        results.append((eng2.copy_nzval(), eng2.copy_vector()))
+        eng2.close()
         nzval, b = results[0]
         check_owned_rows(part, colptr, rowval, nzval, b, A_glob, bg)
         own = part.row_owner == part.rank
