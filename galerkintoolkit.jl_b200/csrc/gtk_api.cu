@@ -357,8 +357,24 @@ int32_t gtk_device_pointer(gtk_ctx* ctx, int32_t which, void** dptr, int64_t* co
     case 5: { int32_t rc = gtk_field_ensure(ctx); if (rc) return rc; *dptr = ctx->u_diri; if (count) *count = ctx->n_diri; break; }
     case 6: *dptr = ctx->xdof_free; if (count) *count = ctx->xdof_free ? ctx->n_free * ctx->D : 0; break;
     case 7: *dptr = ctx->xdof_diri; if (count) *count = ctx->xdof_diri ? ctx->n_diri * ctx->D : 0; break;
+    case 8: *dptr = ctx->xyz; if (count) *count = ctx->n_nodes * ctx->D; break;
+    case 9: *dptr = ctx->cell_nodes; if (count) *count = ctx->n_cells * ctx->nln; break;
+    case 10: *dptr = ctx->cell_dofs; if (count) *count = ctx->cell_dofs ? ctx->n_cells * ctx->nld : 0; break;
     default: GTK_FAIL(GTK_ERR_INVALID, "gtk_device_pointer: unknown selector");
   }
+  return GTK_OK;
+}
+
+int32_t gtk_copy_device_array(gtk_ctx* ctx, int32_t which, void* host, int64_t bytes) {
+  if (!ctx) return GTK_ERR_INVALID;
+  void* d = nullptr; int64_t count = 0;
+  int32_t rc = gtk_device_pointer(ctx, which, &d, &count);
+  if (rc) return rc;
+  const int64_t elem = (which == 2) ? 8 : ((which == 3 || which == 9 || which == 10) ? 4 : 8);
+  if (bytes < 0 || bytes > count * elem || (bytes && (!host || !d))) GTK_FAIL(GTK_ERR_INVALID, "gtk_copy_device_array: bad size or array not present");
+  GTK_CK(cudaSetDevice(ctx->device));
+  if (bytes) GTK_CK(cudaMemcpyAsync(host, d, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
   return GTK_OK;
 }
 

@@ -35,6 +35,7 @@ ABI_SYMBOLS = [
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
     "gtk_field_set_values", "gtk_field_set_values_device", "gtk_field_get_values", "gtk_field_axpy_free",
     "gtk_space_dof_coordinates", "gtk_scalar_assemble", "gtk_comm_build_exchange", "gtk_comm_connect_peer_memory",
+    "gtk_set_cartesian_q1_problem", "gtk_copy_device_array",
 ]
 
 
@@ -116,6 +117,8 @@ def load_library() -> C.CDLL:
         "gtk_scalar_assemble": (i32, [vp, i32, C.POINTER(FormParams), C.POINTER(C.c_double)]),
         "gtk_comm_build_exchange": (i32, [vp, i64, vp]),
         "gtk_comm_connect_peer_memory": (i32, [vp]),
+        "gtk_copy_device_array": (i32, [vp, i32, vp, i64]),
+        "gtk_set_cartesian_q1_problem": (i32, [vp, vp, vp, i64, i64, i32, C.POINTER(i64), C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -208,6 +211,27 @@ class Engine:
         self._D = xyz.shape[1]
         self._n_cells = cn.shape[0]
         self._ck(self.lib.gtk_set_mesh(self.h, xyz.shape[1], xyz.shape[0], _ptr(xyz), cn.shape[0], cn.shape[1], _ptr(cn)))
+
+    def set_cartesian_q1_problem(self, domain, cells, kz0: int = 0, kz1: Optional[int] = None, slab_local: bool = False):
+        """mesh + Q1 space (whole boundary Dirichlet) of GT.cartesian_mesh(domain, cells) generated in HBM; node layers
+        [kz0, kz1] only (multi-GPU slabs).  Replaces set_mesh + set_space.  -> (n_free, n_dirichlet)"""
+        dom = _f64(domain)
+        cl = np.ascontiguousarray(cells, dtype=np.int64)
+        kz1 = int(cl[2]) if kz1 is None else int(kz1)
+        nf, nd = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.gtk_set_cartesian_q1_problem(self.h, _ptr(dom), _ptr(cl), int(kz0), kz1, 1 if slab_local else 0,
+                                                       C.byref(nf), C.byref(nd)))
+        self._D = 3
+        self._n_cells = int(cl[0] * cl[1] * (kz1 - kz0))
+        self._n_free, self._n_diri = nf.value, nd.value
+        return nf.value, nd.value
+
+    def copy_device_array(self, which: int, dtype) -> np.ndarray:
+        """host copy of a device array named by gtk_device_pointer's selector (tests / diagnostics)"""
+        _, n = self.device_pointer(which)
+        out = np.empty(n, dtype=dtype)
+        self._ck(self.lib.gtk_copy_device_array(self.h, which, _ptr(out), out.nbytes))
+        return out
 
     def set_manifold_dim(self, d: int):
         """Cells of reference dimension d < D (boundary faces as a mesh of their own); call between set_mesh and set_tabulation."""

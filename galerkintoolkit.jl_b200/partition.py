@@ -64,6 +64,57 @@ def slab_ranges(n3: int, world: int):
     return out
 
 
+@dataclass
+class SlabLayout:
+    """What a rank needs to know about its z-slab WITHOUT any mesh-sized array (the arrays are generated on the device by
+    gtk_set_cartesian_q1_problem): full-boundary Dirichlet Q1 problem, partition as in slab_problem()."""
+    rank: int
+    world: int
+    k0: int                 # owned cell layers [k0, k1)
+    k1: int
+    kc0: int                # first local cell layer (k0 - 1: symbolic halo, except on rank 0)
+    active_cells: tuple     # (first, count) in local cell ids
+    n_free: int             # local free dofs
+    gid0: int               # 0-based global id of local free row 0
+    own_start: np.ndarray   # [world+1]
+    own_lo: int             # owned local rows [own_lo, own_hi)
+    own_hi: int
+
+
+def slab_layout(cells: Sequence[int], rank: int, world: int) -> SlabLayout:
+    n1, n2, n3 = (int(c) for c in cells)
+    assert world >= 1 and 0 <= rank < world and n3 >= world
+    ranges = slab_ranges(n3, world)
+    k0, k1 = ranges[rank]
+    kc0 = k0 - 1 if rank > 0 else k0
+    per_layer = (n1 - 1) * (n2 - 1)
+    nfree_layers = lambda a, b: max(0, min(b, n3 - 1) - max(a, 1) + 1)     # free node layers in [a, b]
+    own_start = np.array([nfree_layers(0, r[0] - 1) * per_layer for r in ranges] + [nfree_layers(0, n3) * per_layer], dtype=np.int64)
+    gid0 = nfree_layers(0, kc0 - 1) * per_layer
+    n_free = nfree_layers(kc0, k1) * per_layer
+    own_lo = int(np.clip(own_start[rank] - gid0, 0, n_free))
+    own_hi = int(np.clip(own_start[rank + 1] - gid0, 0, n_free))
+    return SlabLayout(rank, world, k0, k1, kc0, ((k0 - kc0) * n1 * n2, (k1 - k0) * n1 * n2), n_free, gid0, own_start, own_lo, own_hi)
+
+
+def attach_generated(engine, domain, cells, layout: SlabLayout, tab, dist):
+    """attach_device() with the slab's mesh and space generated in HBM (no mesh-sized host array, no upload): returns the
+    number of nonzeros in the rows this rank owns."""
+    nf, _ = engine.set_cartesian_q1_problem(domain, cells, layout.kc0, layout.k1, slab_local=True)
+    assert nf == layout.n_free
+    engine.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+    engine.set_active_cells(*layout.active_cells)
+    engine.matrix_symbolic()
+    engine.vector_symbolic()
+    uid = [type(engine).comm_unique_id() if layout.rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    engine.comm_init(layout.rank, layout.world, uid[0])
+    engine.comm_build_exchange(layout.gid0, layout.own_start)
+    engine.comm_connect_peer_memory()
+    colptr, _ = engine.matrix_pattern(want_rowval=False)
+    return int(colptr[layout.own_hi]) - int(colptr[layout.own_lo])
+
+
 def slab_problem(domain: Sequence[float], cells: Sequence[int], rank: int, world: int,
                  dirichlet_boundary="boundary") -> SlabPart:
     """Local Q1 problem of `rank` for GT.cartesian_mesh(domain, cells) + lagrange_space(Ω,1;dirichlet_boundary).

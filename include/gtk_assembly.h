@@ -105,6 +105,16 @@ int32_t gtk_set_stream(gtk_ctx* ctx, void* cuda_stream);
  * (cartesian_mesh.jl:213-263; GalerkinToolkitExamples/src/poisson.jl:323-325). */
 int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz,
                      int64_t n_cells, int32_t n_lnodes, const int32_t* cell_nodes);
+/* The synthetic inputs of the benchmark configurations generated in HBM instead of uploaded: GT.cartesian_mesh(domain,
+ * cells) with hexahedra (cartesian_mesh.jl:213-263) restricted to the node layers [kz0, kz1] of the last direction, and
+ * V = lagrange_space(interior(mesh), 1; dirichlet_boundary = boundary(mesh)) (vertex ids topology.jl:1034-1097, dof
+ * numbering space.jl:327-417, 910-920).  Equivalent to gtk_set_mesh + gtk_set_space with the arrays the host would have
+ * produced, bit for bit (coordinates: one multiplication and one addition per component, like the reference).
+ * slab_local_numbering = 0: the reference's numbering of the WHOLE mesh (kz0 = 0, kz1 = cells[2]);
+ * slab_local_numbering = 1: a z-slab of the multi-GPU partition: local node ids, free dofs numbered lexicographically among
+ * the local free nodes (a node is free iff it is interior to the WHOLE box), Dirichlet ids lexicographically among the rest. */
+int32_t gtk_set_cartesian_q1_problem(gtk_ctx* ctx, const double* domain6, const int64_t* cells3, int64_t kz0, int64_t kz1,
+                                     int32_t slab_local_numbering, int64_t* n_free_out, int64_t* n_dirichlet_out);
 /* Cells whose reference space has dimension d < D: boundary faces of a D-dimensional mesh handed over as a mesh of their
  * own (face nodes = face_nodes(mesh, D-1) of the faces of a boundary domain, domain.jl:705-753; `cell_dofs` = the space's
  * dofs on each face; tabulations on the (D-1)-dimensional reference face, gradients with d components).  dV is then
@@ -199,8 +209,11 @@ int32_t gtk_scalar_assemble(gtk_ctx* ctx, int32_t kind, const gtk_form_params* p
 /* ---- device-resident results -------------------------------------------------- */
 /* which: 0 nzval (double[nnz]) 1 b (double[n_rows]) 2 colptr (int64[n_cols+1], 0-based)
  *        3 rowval (int32[nnz], 1-based) 4 field free values (double[n_free]) 5 field Dirichlet values (double[n_dirichlet])
- *        6 / 7 coordinates of the free / Dirichlet dofs (double[n][D], after gtk_space_dof_coordinates) */
+ *        6 / 7 coordinates of the free / Dirichlet dofs (double[n][D], after gtk_space_dof_coordinates)
+ *        8 node coordinates (double[n_nodes][D])  9 cell_nodes (int32[n_cells][n_lnodes])  10 cell_dofs (int32[n_cells][n_ldofs]) */
 int32_t gtk_device_pointer(gtk_ctx* ctx, int32_t which, void** dptr, int64_t* count);
+/* Host copy of the first `bytes` bytes of the array gtk_device_pointer(which) names (diagnostics, tests). */
+int32_t gtk_copy_device_array(gtk_ctx* ctx, int32_t which, void* host, int64_t bytes);
 int32_t gtk_copy_nzval(gtk_ctx* ctx, double* nzval);
 int32_t gtk_copy_vector(gtk_ctx* ctx, double* b);
 

@@ -64,3 +64,22 @@ def test_dmma_active_cells_and_blocks():
         assert eng.info(5) == 3
         assert_values_close(nz, nzval)
     eng.close()
+
+
+def test_config3_full_size_invariants():
+    """BASELINE config 3 at FULL size (Q3 hexahedra, 64^3 cells, 849 278 123 nonzeros) through the DMMA path: nnz of the
+    tensor-product pattern, finite values, positive diagonal, zero column sums away from the boundary, structurally
+    symmetric pattern and symmetric values (off-diagonal 8x8 tiles of an element matrix are mirrored bitwise; inside a
+    diagonal tile both halves are accumulated by the tensor core: equal to rounding) — all checked on the device (tools/bench_highorder.py)."""
+    import os
+    import sys
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a 180 GB B200")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bench_highorder
+    out = bench_highorder.run(64, 3, steps=1, warmup=1, check=True)
+    c = out["checks"]
+    assert out["fast_path"] == 3 and out["nnz"] == 849278123 and out["free_dofs"] == 6967871
+    assert c["nnz_ok"] and c["n_free_ok"] and c["finite"] and c["diag_positive"] and c["zero_colsum_ok"], c
+    assert c["pattern_symmetric"] and c["values_symmetric_relerr"] <= 1e-14, c

@@ -17,6 +17,67 @@ sys.path.insert(0, ROOT)
 DMMA_PEAK_TFLOPS = 37.0   # measured: 16 cycles per DMMA.8x8x4 per SM sub-partition (profiles/r01_dmma_peak.txt)
 
 
+class _DevArr:
+    """device pointer -> torch tensor (zero copy) through __cuda_array_interface__"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def device_invariants(eng, order, n, n_free):
+    """Size-independent properties of the assembled Q_k Laplacian with full Dirichlet boundary, checked ON THE DEVICE at full
+    size (the matrix of config 3 is 6.8 GB of values): nnz of the tensor-product pattern, finite values, positive diagonal,
+    zero column sums away from the boundary (constants are in the kernel of the Laplacian), structural symmetry of the
+    pattern and BITWISE symmetry of the values (the DMMA path mirrors the upper triangle of every element matrix and adds
+    the contributions of a pair (i,j) and (j,i) in the same cell order)."""
+    import torch
+    m = order * n - 1
+    pn, nn = eng.device_pointer(0)
+    pc, nc = eng.device_pointer(2)
+    pr, nr = eng.device_pointer(3)
+    nz = torch.as_tensor(_DevArr(pn, nn, "<f8"), device="cuda")
+    cp = torch.as_tensor(_DevArr(pc, nc, "<i8"), device="cuda")
+    rv = torch.as_tensor(_DevArr(pr, nr, "<i4"), device="cuda")
+    # nnz of the Q_k pattern with full Dirichlet boundary: per direction sum over free nodes of the 1D neighbour count
+    per_dir = 0
+    for i in range(1, order * n):              # free 1D nodes 1 .. kn-1
+        if i % order == 0:                     # vertex node: two cells
+            lo, hi = i - order, i + order
+        else:                                  # cell-interior node: one cell
+            lo, hi = (i // order) * order, (i // order) * order + order
+        per_dir += min(hi, order * n - 1) - max(lo, 1) + 1
+    res = {"n_free_ok": bool(n_free == m ** 3), "nnz": int(nn), "nnz_formula": int(per_dir ** 3), "nnz_ok": bool(nn == per_dir ** 3)}
+    res["finite"] = bool(torch.isfinite(nz).all().item())
+    lens = (cp[1:] - cp[:-1])
+    col = torch.repeat_interleave(torch.arange(n_free, device="cuda", dtype=torch.int32), lens)
+    diag = nz[(rv - 1) == col]
+    res["diag_positive"] = bool(diag.numel() == n_free and (diag > 0).all().item())
+    colsum = torch.segment_reduce(nz, "sum", lengths=lens)
+    scale = float(nz.abs().max().item())
+    nzero = int((colsum.abs() <= 1e-10 * scale).sum().item())
+    res["zero_colsum_columns"] = nzero
+    res["zero_colsum_ok"] = bool(nzero >= (order * (n - 2) - 1) ** 3)
+    del diag, colsum
+    # transpose by sorting the entries by (row, col): position t of the sorted order holds entry (col_t, row_t) of A^T
+    key = (rv.to(torch.int64) - 1) * n_free + col.to(torch.int64)
+    del col
+    perm = torch.argsort(key)
+    del key
+    key_t = cp.new_empty(0)
+    nzt = nz[perm]
+    res["values_bitwise_symmetric"] = bool(torch.equal(nzt.view(torch.int64), nz.view(torch.int64)))
+    res["values_symmetric_relerr"] = float(((nzt - nz).abs().max() / scale).item())
+    del nzt
+    rows_sorted = rv[perm]
+    # structural symmetry: in transposed order the "column" ids (original rows) must reproduce colptr's run lengths
+    cnt = torch.bincount((rows_sorted - 1).to(torch.int64), minlength=n_free)
+    res["pattern_symmetric"] = bool(torch.equal(cnt, lens.to(cnt.dtype)))
+    res["sum_nz"] = float(nz.sum().item())
+    del perm, rows_sorted, cnt, key_t
+    torch.cuda.empty_cache()
+    return res
+
+
 def run(n=64, order=3, steps=5, warmup=2, device=0, check=True):
     import numpy as np
     import gtk_b200
@@ -63,21 +124,7 @@ def run(n=64, order=3, steps=5, warmup=2, device=0, check=True):
         "device_bytes": int(eng.info(2)),
     }
     if check:
-        # size-independent properties: nnz formula for Q_k with full Dirichlet BC, zero row sums in the interior
-        # (constants are in the kernel of the Laplacian), symmetry of the diagonal-block sums
-        nz = eng.copy_nzval()
-        cp, rv = eng.matrix_pattern()
-        m = order * n - 1
-        out["checks"] = {"n_free_ok": bool(V.n_free == m ** 3), "finite": bool(np.isfinite(nz).all()),
-                         "sum_nz": float(nz.sum()), "diag_positive": None}
-        col = np.repeat(np.arange(V.n_free, dtype=np.int64), np.diff(cp.astype(np.int64)))
-        diag = nz[(rv.astype(np.int64) - 1) == col]
-        out["checks"]["diag_positive"] = bool(diag.size == V.n_free and (diag > 0).all())
-        colsum = np.bincount(col, weights=nz, minlength=V.n_free)
-        # a column whose dof shares no cell with a Dirichlet dof sums to zero (constants are in the kernel)
-        nzero = int((np.abs(colsum) <= 1e-10 * np.abs(nz).max()).sum())
-        out["checks"]["zero_colsum_columns"] = nzero
-        out["checks"]["zero_colsum_ok"] = bool(nzero >= (order * (n - 2) - 1) ** 3)
+        out["checks"] = device_invariants(eng, order, n, V.n_free)
     eng.close()
     return out
 
