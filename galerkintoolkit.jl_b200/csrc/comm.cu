@@ -100,6 +100,8 @@ struct GhostPlan {
   cudaStream_t side = nullptr;          // pack + NCCL run here while the rest of the sweep runs on ctx->stream
   cudaEvent_t ev_first = nullptr, ev_xchg = nullptr;
   bool p2p_off = false;                 // the ranks agreed to stay on NCCL (gtk_comm_build_exchange could not map every block)
+  bool assign_untouched = false;        // device-built plan: entries of columns without local contributions are ASSIGNED by the
+                                        // unpack, so the sweep need not write (zero) those columns at all
   bool p2p_ready() const {
     if (peers.empty() || p2p_off || getenv("GTK_DISABLE_P2P")) return false;
     for (auto& p : peers) if (!p.remote_block || !p.ipc_block) return false;
@@ -155,7 +157,10 @@ __global__ void __launch_bounds__(256) k_wait_unpack_add(double* __restrict__ nz
   __syncthreads();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
     const double v = __ldcg(buf + i);   // written by another GPU while this kernel runs: not through L1
-    if (i < n) nzval[idx[i]] += v; else b[rows[i - n]] += v;
+    if (i < n) {
+      const int64_t p = idx[i];
+      if (p >= 0) nzval[p] += v; else nzval[~p] = v;   // ~p: a column no local cell contributes to — the value IS the peer's
+    } else b[rows[i - n]] += v;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -172,7 +177,10 @@ __global__ void k_unpack_add(double* __restrict__ nzval, const int64_t* __restri
                              double* __restrict__ b, const int32_t* __restrict__ rows, int64_t nb,
                              const double* __restrict__ buf) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
-    if (i < n) nzval[idx[i]] += buf[i]; else b[rows[i - n]] += buf[i];
+    if (i < n) {
+      const int64_t p = idx[i];
+      if (p >= 0) nzval[p] += buf[i]; else nzval[~p] = buf[i];
+    } else b[rows[i - n]] += buf[i];
   }
 }
 
@@ -241,6 +249,13 @@ static int32_t install_peer(gtk_ctx* ctx, Peer p) {
       return GTK_ERR_NCCL;                                                                     \
     }                                                                                          \
   } while (0)
+
+// true when the unpack assigns the entries of columns without local contributions (device-built plan): the sweep kernels
+// then restrict themselves to the node layers their active cells touch
+bool gtk_comm_assigns_untouched(const gtk_ctx* ctx) {
+  const GhostPlan* g = (const GhostPlan*)ctx->ghost;
+  return g && g->assign_untouched && !getenv("GTK_SWEEP_HALO");
+}
 
 // The exchange plan indexes nzval / b of ONE pattern: it dies with that pattern (gtk_set_mesh, gtk_set_space,
 // gtk_matrix_symbolic) so that a later gtk_comm_sum_ghost_rows cannot scatter through stale positions.  The NCCL
@@ -358,7 +373,7 @@ static int32_t exchange_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
 }
 
 // add what the peers sent, in increasing peer rank: fixed summation order
-static int32_t unpack_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
+static int32_t unpack_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st, bool alone = true) {
   if (g->p2p_ready()) {
     for (auto& p : g->peers) {
       const int64_t n = p.n_recv_nz + p.n_recv_b;
@@ -366,8 +381,9 @@ static int32_t unpack_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
       const unsigned long long* lhdr = reinterpret_cast<const unsigned long long*>(p.ipc_block);
       unsigned long long* rhdr = reinterpret_cast<unsigned long long*>(p.remote_block);
       { GtkProf pr_(ctx, "k_wait_unpack_add");
-        // at most 2 blocks per SM: a block may spin for the peer's flag while the sweep shares the GPU with it
-        k_wait_unpack_add<<<std::min(grid_for(n), 2 * ctx->sm_count), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b,
+        // sharing the GPU with the sweep: at most 2 blocks per SM (a block may spin for the peer's flag); alone: the
+        // scattered read-modify-writes are latency-bound, so as many threads as there are entries to hide it
+        k_wait_unpack_add<<<alone ? std::min((int)((n + 255) / 256), 16 * ctx->sm_count) : std::min(grid_for(n), 2 * ctx->sm_count), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b,
                                                        p.recv_buf, lhdr + 0, rhdr + 1, p.seq, p.done_ctr + 1); }
       GTK_CK(cudaGetLastError());
       gtk_count_launch(ctx);
@@ -467,7 +483,7 @@ int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t mform, cons
   GTK_CK(cudaStreamWaitEvent(g->side, g->ev_first, 0));
   ctx->launches_last = 0;
   if ((rc = exchange_on(ctx, g, g->side))) return rc;
-  if (early_unpack && (rc = unpack_on(ctx, g, g->side))) return rc;
+  if (early_unpack && (rc = unpack_on(ctx, g, g->side, false))) return rc;
   GTK_CK(cudaEventRecord(g->ev_xchg, g->side));
   if (timing) cudaEventRecord(te[2], g->side);
   launches_acc += ctx->launches_last;
@@ -590,7 +606,8 @@ __global__ void k_ghost_keys(const int64_t* __restrict__ nz_pos, int64_t n, cons
 // 4 row not owned by this rank
 __global__ void k_match_keys(const int64_t* __restrict__ keys, int64_t n, int64_t nb, const int32_t* __restrict__ rowval,
                              const int64_t* __restrict__ colptr, int64_t n_rows, int64_t gid0, int64_t own_lo, int64_t own_hi,
-                             int64_t* __restrict__ recv_nz, int32_t* __restrict__ recv_rows, int* __restrict__ err) {
+                             const uint8_t* __restrict__ touched, int64_t* __restrict__ recv_nz, int32_t* __restrict__ recv_rows,
+                             int* __restrict__ err) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + nb; i += (int64_t)gridDim.x * blockDim.x) {
     if (i >= n) {
       const int64_t g = keys[2 * n + (i - n)];
@@ -606,7 +623,7 @@ __global__ void k_match_keys(const int64_t* __restrict__ keys, int64_t n, int64_
     const int32_t target = (int32_t)(lr + 1);
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < target) lo = mid + 1; else hi = mid; }
     if (lo >= colptr[lc + 1] || rowval[lo] != target) { atomicOr(err, 2); recv_nz[i] = 0; }
-    else recv_nz[i] = lo;
+    else recv_nz[i] = touched[lc] ? lo : ~lo;   // no active cell touches column lc: assign instead of add
   }
 }
 
@@ -692,7 +709,7 @@ extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int
     GTK_CK(cudaStreamSynchronize(st));
     gtk_cuda_free(ctx, cand_nz); gtk_cuda_free(ctx, cand_rows);
   }
-  gtk_cuda_free(ctx, tmp); gtk_cuda_free(ctx, touched); gtk_cuda_free(ctx, d_cnt);
+  gtk_cuda_free(ctx, tmp); gtk_cuda_free(ctx, d_cnt);
   // 3. everybody learns how much it receives from whom
   std::vector<int64_t> row(2 * W, 0), mat((size_t)2 * W * W, 0);
   for (auto& sd : sends) { row[2 * sd.peer] = sd.n_nz; row[2 * sd.peer + 1] = sd.n_b; }
@@ -735,13 +752,13 @@ extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int
     if (rv.n_nz) if ((rc = gtk_dev_alloc(ctx, (void**)&p.recv_nz, sizeof(int64_t) * rv.n_nz))) return rc;
     if (rv.n_b) if ((rc = gtk_dev_alloc(ctx, (void**)&p.recv_rows, sizeof(int32_t) * rv.n_b))) return rc;
     k_match_keys<<<grid_for(rv.n_nz + rv.n_b), 256, 0, st>>>(rv.keys, rv.n_nz, rv.n_b, m.rowval, m.colptr, n, gid0, own_start[me], own_start[me + 1],
-                                                            p.recv_nz, p.recv_rows, d_err);
+                                                            touched, p.recv_nz, p.recv_rows, d_err);
     GTK_CK(cudaGetLastError());
   }
   int h_err = 0;
   GTK_CK(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
   GTK_CK(cudaStreamSynchronize(st));
-  gtk_cuda_free(ctx, d_err);
+  gtk_cuda_free(ctx, d_err); gtk_cuda_free(ctx, touched);
   for (auto& sd : sends) gtk_cuda_free(ctx, sd.keys);
   for (auto& rv : recvs) gtk_cuda_free(ctx, rv.keys);
   if (h_err) {
@@ -752,6 +769,11 @@ extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int
   }
   std::sort(peers.begin(), peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
   for (auto& p : peers) if ((rc = install_peer(ctx, p))) return rc;
+  if (ctx->ghost) {
+    ((GhostPlan*)ctx->ghost)->assign_untouched = true;
+    // columns no active cell touches are not swept any more: they hold what the unpack assigns, or zeros (rows nobody sends)
+    if (ctx->nzval) GTK_CK(cudaMemsetAsync(ctx->nzval, 0, sizeof(double) * ctx->nzval_cap, st));
+  }
   return GTK_OK;   // transport: gtk_comm_connect_peer_memory (collective, also for a rank without peers)
 }
 

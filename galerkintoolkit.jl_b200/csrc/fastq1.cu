@@ -28,10 +28,14 @@
 //
 // gtk_fastq1_symbolic: the symbolic phase of such meshes straight from the node lattice (pattern, slot table, column
 //   records; no COO keys, no sort), and the layer-range launches the multi-GPU exchange overlaps with (comm.cu).
+#include <algorithm>
 #include <utility>
+#include <vector>
 #include <cub/cub.cuh>
 #include "gtk_internal.h"
 #include "q1hex_math.cuh"
+
+bool gtk_comm_assigns_untouched(const gtk_ctx* ctx);   // comm.cu
 
 namespace {
 
@@ -66,6 +70,15 @@ struct FastPlan {
     int key = 0, seg = 0, nseg = 0, z_begin = 0, z_end = 0;
   };
   TilePlan tp_affine[4], tp_sweep[4];   // [launch mode]: all layers / top part of an overlapped step / middle / bottom
+  // work items of the persistent warp-private kernels (launch_affine_w), per launch mode
+  struct ItemPlan {
+    int4* items = nullptr;
+    int n = 0, cap = 0, z_begin = -1, z_end = -1, warps = 0;
+  };
+  ItemPlan ip_affine[4];
+  std::vector<uint8_t> h_act;          // [gx * gyp * (n3+1)] host copy: patch (16 x 2 nodes) holds a matrix column in that node layer
+  unsigned long long* sched = nullptr; // ticket counter (device), grows monotonically across launches
+  unsigned long long sched_next = 0;   // first ticket of the next launch
 };
 
 __global__ void k_verify_structure(const int32_t* __restrict__ cell_nodes, const int32_t* __restrict__ cell_dofs,
@@ -262,6 +275,12 @@ struct SweepArgs {
   int kact0, kact1;   // numeric-active cell layers [kact0, kact1)
   double alpha, fscale;
   int do_matrix, do_vector;
+  // work-item scheduler of the warp-private kernels: items[t] = {i0, j0, kz0, kz1} (patch origin and node layers), handed
+  // out through a 64-bit ticket counter that only ever grows (ticket - sched_base = item index of this launch)
+  const int4* items;
+  int n_items;
+  unsigned long long* sched;
+  unsigned long long sched_base;
 };
 
 template <int BX, int BY>
@@ -593,22 +612,11 @@ struct WCfg {
   static constexpr int WARP_D = CELL_D + 2 * ROWS + 3 * XL;   // doubles of shared memory per warp
 };
 
-template <int WPB, int MAXREG, bool TWOPASS>
-__global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
+// one work item of the warp-private affine sweep: the 16 x 2 patch at (i0, j0), node layers [kz0, kz1)
+template <bool TWOPASS>
+__device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, const int j0, const int kz0, const int kz1,
+                                              double* __restrict__ OutW, double* __restrict__ CellW, double* __restrict__ XW, const int lane) {
   using C = WCfg;
-  extern __shared__ __align__(16) double sm[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int py = blockIdx.y * WPB + w;                 // patch row
-  const int gyp = (a.n2 + 1 + C::BY - 1) / C::BY;      // patch rows in the mesh
-  if (py >= gyp) return;
-  if (a.tile_active && !a.tile_active[blockIdx.x + gridDim.x * (py + (int64_t)gyp * blockIdx.z)]) return;
-  double* OutW = sm + w * C::WARP_D;                   // [2][ROWS]
-  double* CellW = OutW + 2 * C::ROWS;                  // [NC][7]
-  double* XW = CellW + C::CELL_D;                      // [3][PY][PX][3] ring of node-coordinate layers (cp.async, 2 ahead)
-
-  const int i0 = blockIdx.x * C::BX, j0 = py * C::BY;
-  const int kz0 = a.z_begin + blockIdx.z * a.seg_len;
-  const int kz1 = min(kz0 + a.seg_len, a.z_end);
   const int n1 = a.n1, n2 = a.n2;
   const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
   const int li = lane & 15, lj = lane >> 4;
@@ -813,6 +821,31 @@ __global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
   if (bulk_pending) bulk_wait_read();   // shared memory must outlive the bulk store reading it
 }
 
+
+// Persistent launch: every warp draws (patch, z-segment) work items from a ticket counter until none is left.  The host
+// orders the items from long z-segments to short ones (guided self-scheduling): long segments amortise the halo step of a
+// segment start, the short ones at the end level the finishing times of the ~2200 resident warps — the uniform 6-layer
+// segments of the static grid left a tail of up to one whole item (18 % of a warp's work at 128^3).  Which warp computes an
+// item does not change a single bit of the result (every nonzero is produced by exactly one lane in a fixed order).
+template <int WPB, int MAXREG, bool TWOPASS>
+__global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
+  using C = WCfg;
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* OutW = sm + w * C::WARP_D;                   // [2][ROWS]
+  double* CellW = OutW + 2 * C::ROWS;                  // [NC][7]
+  double* XW = CellW + C::CELL_D;                      // [3][PY][PX][3] ring of node-coordinate layers (cp.async, 2 ahead)
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(a.sched, 1ull) - a.sched_base;
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    if (t >= (unsigned long long)a.n_items) break;
+    const int4 it = __ldg(a.items + t);
+    affine_w_item<TWOPASS>(a, it.x, it.y, it.z, it.w, OutW, CellW, XW, lane);
+    __syncwarp();
+  }
+}
+
 // tile_active[x + gx (y + gy z)] = 1 when the tile's footprint x z-segment holds at least one matrix column
 __global__ void k_tile_active(const int32_t* __restrict__ node_dof, int n1, int n2, int z_begin, int z_end, int bx, int by,
                               int seg_len, int gx, int gy, uint8_t* __restrict__ active) {
@@ -842,6 +875,8 @@ void plan_free(gtk_ctx* ctx, FastPlan* p) {
   if (p->d_flag) gtk_cuda_free(ctx, p->d_flag);
   for (auto& tp : p->tp_affine) if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
   for (auto& tp : p->tp_sweep) if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
+  for (auto& ip : p->ip_affine) if (ip.items) gtk_dev_free(ctx, ip.items, sizeof(int4) * (size_t)ip.cap);
+  if (p->sched) gtk_cuda_free(ctx, p->sched);
   delete p;
 }
 
@@ -957,6 +992,17 @@ void layer_range(const gtk_ctx* ctx, int layers, int* z_begin, int* z_end) {
   else if (ctx->seg_mode == 2) { *z_begin = lo; *z_end = split; }
   else if (ctx->seg_mode == 3) { *z_begin = 0; *z_end = lo; }
   else { *z_begin = 0; *z_end = layers; }
+  // multi-GPU slab with a symbolic-only halo cell layer: node layers none of the ACTIVE cells touches hold no local
+  // contribution.  With a device-built exchange plan the unpack assigns their received entries, so they are skipped.
+  if (ctx->act_count >= 0 && gtk_comm_assigns_untouched(ctx)) {
+    const FastPlan* p = (const FastPlan*)ctx->ms.plan;
+    const int64_t per_layer = (int64_t)p->n1 * p->n2;
+    if (ctx->act_first % per_layer == 0 && ctx->act_count % per_layer == 0) {
+      const int k0 = (int)(ctx->act_first / per_layer), k1 = k0 + (int)(ctx->act_count / per_layer);   // active cell layers [k0, k1)
+      if (*z_begin < k0) *z_begin = k0;
+      if (*z_end > k1 + 1) *z_end = k1 + 1;
+    }
+  }
 }
 
 template <int BX, int BY, int MINB>
@@ -983,27 +1029,93 @@ int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   return GTK_OK;
 }
 
+// Work items of a persistent warp-private launch over the node layers [z_begin, z_end): z-segments from long to short
+// (guided self-scheduling for `warps` resident warps), one item per (segment, patch), trimmed to the node layers in which
+// the patch holds a matrix column at all (the Dirichlet planes and the overhang past the mesh produce no item).
+int32_t build_item_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::ItemPlan& ip, int z_begin, int z_end, int warps) {
+  using C = WCfg;
+  if (ip.items && ip.z_begin == z_begin && ip.z_end == z_end && ip.warps == warps) return GTK_OK;
+  const int gx = (p->n1 + 1 + C::BX - 1) / C::BX, gyp = (p->n2 + 1 + C::BY - 1) / C::BY;
+  const int nl = p->n3 + 1;
+  if (p->h_act.empty()) {   // layer-granular activity of every patch, once per plan
+    const size_t n = (size_t)gx * gyp * nl;
+    uint8_t* d = nullptr;
+    GTK_CK(gtk_cuda_malloc(ctx, &d, n));
+    GTK_CK(cudaMemsetAsync(d, 0, n, ctx->stream));
+    k_tile_active<<<grid_for((int64_t)(p->n1 + 1) * (p->n2 + 1) * nl, 256), 256, 0, ctx->stream>>>(p->node_dof, p->n1, p->n2, 0, nl, C::BX, C::BY, 1, gx, gyp, d);
+    GTK_CK(cudaGetLastError());
+    p->h_act.resize(n);
+    GTK_CK(cudaMemcpyAsync(p->h_act.data(), d, n, cudaMemcpyDeviceToHost, ctx->stream));
+    GTK_CK(cudaStreamSynchronize(ctx->stream));
+    gtk_cuda_free(ctx, d);
+  }
+  // guided segment lengths: a segment is about 1/gf of an even share of what is left, within [smin, smax] layers
+  const char* e;
+  const double gf = (e = getenv("GTK_AFFINE_GF")) && atof(e) > 0 ? atof(e) : 2.0;
+  const int smin = (e = getenv("GTK_AFFINE_SMIN")) && atoi(e) > 0 ? atoi(e) : 3;
+  const int smax = (e = getenv("GTK_AFFINE_SMAX")) && atoi(e) > 0 ? atoi(e) : 24;
+  const int fixed = (e = getenv("GTK_AFFINE_SEG")) && atoi(e) > 0 ? atoi(e) : 0;   // uniform segments (the former static grid's choice: 6)
+  std::vector<std::pair<int, int>> segs;
+  for (int z = z_begin; z < z_end;) {
+    const int rem = z_end - z;
+    int len = fixed ? fixed : (int)((double)rem * gx * gyp / (gf * (warps > 0 ? warps : 1)) + 0.999);
+    if (!fixed) len = len < smin ? smin : (len > smax ? smax : len);
+    if (len > rem || rem - len < smin / 2 + 1) len = rem;
+    segs.emplace_back(z, z + len);
+    z += len;
+  }
+  std::vector<int4> items;
+  items.reserve((size_t)gx * gyp * segs.size());
+  for (auto& sg : segs)
+    for (int py = 0; py < gyp; ++py)
+      for (int bx = 0; bx < gx; ++bx) {
+        const uint8_t* act = p->h_act.data() + bx + (size_t)gx * py;
+        int lo = sg.first, hi = sg.second;
+        while (lo < hi && !act[(size_t)gx * gyp * lo]) ++lo;
+        while (hi > lo && !act[(size_t)gx * gyp * (hi - 1)]) --hi;
+        if (hi > lo) items.push_back(make_int4(bx * C::BX, py * C::BY, lo, hi));
+      }
+  if ((int)items.size() > ip.cap) {
+    if (ip.items) gtk_dev_free(ctx, ip.items, sizeof(int4) * (size_t)ip.cap);
+    ip.items = nullptr; ip.cap = 0;
+    int32_t rc = gtk_dev_alloc(ctx, (void**)&ip.items, sizeof(int4) * items.size());
+    if (rc) return rc;
+    ip.cap = (int)items.size();
+  }
+  if (!items.empty()) GTK_CK(cudaMemcpyAsync(ip.items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));   // `items` is a local
+  ip.n = (int)items.size(); ip.z_begin = z_begin; ip.z_end = z_end; ip.warps = warps;
+  return GTK_OK;
+}
+
 template <int WPB, int MAXREG, bool TWOPASS>
 int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   using C = WCfg;
   SweepArgs a = a0;
-  const int gx = (p->n1 + 1 + C::BX - 1) / C::BX, gyp = (p->n2 + 1 + C::BY - 1) / C::BY;
-  const int gy = (gyp + WPB - 1) / WPB;
   const size_t smem = sizeof(double) * (size_t)WPB * C::WARP_D;
-  GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // measured (profiles/): decoupled warps prefer many short z-segments over whole waves of long ones — the tail
-  // shrinks and concurrently written parts of nzval stay close; the halo step of a segment costs about half a step
-  const char* ns = getenv("GTK_AFFINE_SEG");
-  const int seg = ns && atoi(ns) > 0 ? atoi(ns) : 6;
+  static int occ = 0;   // resident CTAs per SM of this instance (same for every context of the process)
+  if (!occ) {
+    GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, WPB * 32, smem));
+    if (occ < 1) occ = 1;
+  }
   layer_range(ctx, p->n3 + 1, &a.z_begin, &a.z_end);
   if (a.z_end <= a.z_begin) return GTK_OK;
-  FastPlan::TilePlan& tp = p->tp_affine[ctx->seg_mode];
-  int32_t rc = build_tile_plan(ctx, p, tp, 1000 + WPB, C::BX, C::BY, gx, gyp, seg, a.z_begin, a.z_end);
+  const int resident = ctx->sm_count * occ;
+  FastPlan::ItemPlan& ip = p->ip_affine[ctx->seg_mode];
+  int32_t rc = build_item_plan(ctx, p, ip, a.z_begin, a.z_end, resident * WPB);
   if (rc) return rc;
-  a.seg_len = tp.seg;
-  a.tile_active = tp.active;
-  dim3 grid(gx, gy, tp.nseg);
-  { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MAXREG, TWOPASS><<<grid, WPB * 32, smem, ctx->stream>>>(a); }
+  if (ip.n == 0) return GTK_OK;
+  if (!p->sched) {
+    GTK_CK(gtk_cuda_malloc(ctx, &p->sched, sizeof(unsigned long long)));
+    GTK_CK(cudaMemsetAsync(p->sched, 0, sizeof(unsigned long long), ctx->stream));
+    p->sched_next = 0;
+  }
+  const int blocks = std::min((ip.n + WPB - 1) / WPB, resident);
+  a.items = ip.items; a.n_items = ip.n; a.sched = p->sched; a.sched_base = p->sched_next;
+  p->sched_next += (unsigned long long)ip.n + (unsigned long long)blocks * WPB;   // every warp ends on exactly one empty draw
+  a.tile_active = nullptr;
+  { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MAXREG, TWOPASS><<<blocks, WPB * 32, smem, ctx->stream>>>(a); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   return GTK_OK;
@@ -1182,6 +1294,8 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
       ctx->nzval = nullptr; ctx->nzval_cap = 0;
       if ((rc = gtk_dev_alloc(ctx, (void**)&ctx->nzval, sizeof(double) * (size_t)ctx->ms.nnz))) return rc;
       ctx->nzval_cap = (size_t)ctx->ms.nnz;
+      // columns outside the swept layers (multi-GPU halo, see layer_range) are never written by the kernels
+      GTK_CK(cudaMemsetAsync(ctx->nzval, 0, sizeof(double) * (size_t)ctx->ms.nnz, ctx->stream));
     }
   }
   if (vform) {
@@ -1190,6 +1304,7 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
       ctx->bvec = nullptr; ctx->bvec_cap = 0;
       if ((rc = gtk_dev_alloc(ctx, (void**)&ctx->bvec, sizeof(double) * (size_t)ctx->vs.n_rows))) return rc;
       ctx->bvec_cap = (size_t)ctx->vs.n_rows;
+      GTK_CK(cudaMemsetAsync(ctx->bvec, 0, sizeof(double) * (size_t)ctx->vs.n_rows, ctx->stream));   // rows of skipped layers
     }
   }
   SweepArgs a;
@@ -1229,7 +1344,16 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
       case 9: rc = launch_affine_w<4, 168, true>(ctx, p, a); break;
       case 10: rc = launch_affine_w<5, 128, true>(ctx, p, a); break;
       case 11: rc = launch_affine_w<4, 168, false>(ctx, p, a); break;
-      default: rc = launch_affine_w<3, 136, true>(ctx, p, a); break;
+      case 12: rc = launch_affine_w<4, 152, false>(ctx, p, a); break;
+      case 13: rc = launch_affine_w<5, 168, false>(ctx, p, a); break;
+      case 14: rc = launch_affine_w<4, 192, false>(ctx, p, a); break;
+      case 15: rc = launch_affine_w<2, 200, false>(ctx, p, a); break;
+      case 16: rc = launch_affine_w<4, 160, true>(ctx, p, a); break;
+      case 17: rc = launch_affine_w<8, 168, false>(ctx, p, a); break;
+      case 1: rc = launch_affine_w<3, 136, true>(ctx, p, a); break;    // round-1 default (static grid: 127 registers, 5 CTAs/SM)
+      // persistent warps no longer need occupancy to hide the tail: the single-pass body with all 45 accumulators live
+      // (168 registers, 3 CTAs x 4 warps per SM) wins — 0.1166 vs 0.1244 ms at 128^3 (profiles/r02_tune_affine.txt)
+      default: rc = launch_affine_w<4, 168, false>(ctx, p, a); break;
     }
     if (rc) return rc;
     ctx->fast_path_last = 2;

@@ -97,21 +97,36 @@ def slab_layout(cells: Sequence[int], rank: int, world: int) -> SlabLayout:
     return SlabLayout(rank, world, k0, k1, kc0, ((k0 - kc0) * n1 * n2, (k1 - k0) * n1 * n2), n_free, gid0, own_start, own_lo, own_hi)
 
 
-def attach_generated(engine, domain, cells, layout: SlabLayout, tab, dist):
+def attach_generated(engine, domain, cells, layout: SlabLayout, tab, dist, timings: Optional[dict] = None):
     """attach_device() with the slab's mesh and space generated in HBM (no mesh-sized host array, no upload): returns the
-    number of nonzeros in the rows this rank owns."""
+    number of nonzeros in the rows this rank owns.  `timings` (optional dict) receives host wall-clock milliseconds of the
+    phases: generate, symbolic (pattern + sweep plan), comm_init (NCCL communicator), exchange_plan, peer_memory."""
+    import time
+    t = [time.perf_counter()]
+
+    def lap(name):
+        engine.lib.gtk_info(engine.h, 0)
+        t.append(time.perf_counter())
+        if timings is not None:
+            timings[name] = 1e3 * (t[-1] - t[-2])
+
     nf, _ = engine.set_cartesian_q1_problem(domain, cells, layout.kc0, layout.k1, slab_local=True)
     assert nf == layout.n_free
     engine.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
     engine.set_active_cells(*layout.active_cells)
+    lap("generate")
     engine.matrix_symbolic()
     engine.vector_symbolic()
+    colptr, _ = engine.matrix_pattern(want_rowval=False)      # synchronises
+    lap("symbolic")
     uid = [type(engine).comm_unique_id() if layout.rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     engine.comm_init(layout.rank, layout.world, uid[0])
+    lap("comm_init")
     engine.comm_build_exchange(layout.gid0, layout.own_start)
+    lap("exchange_plan")
     engine.comm_connect_peer_memory()
-    colptr, _ = engine.matrix_pattern(want_rowval=False)
+    lap("peer_memory")
     return int(colptr[layout.own_hi]) - int(colptr[layout.own_lo])
 
 

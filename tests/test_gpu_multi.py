@@ -86,7 +86,7 @@ def _worker(rank, world, port, cells, dom, q):
         q.put((rank, traceback.format_exc(), -1))
 
 
-@pytest.mark.parametrize("cells,world", [((6, 5, 8), 2), ((20, 12, 17), 2), ((33, 18, 60), 2), ((18, 11, 41), 4)])
+@pytest.mark.parametrize("cells,world", [((6, 5, 8), 2), ((20, 12, 17), 2), ((33, 18, 60), 2), ((18, 11, 41), 4), ((12, 9, 43), 8)])
 def test_multi_gpu_ghost_rows_match_single_domain(cells, world):
     """world = 4 has interior ranks that both send and receive (top, bottom and middle parts of the overlapped sweep)."""
     import torch
