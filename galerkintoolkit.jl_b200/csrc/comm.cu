@@ -19,6 +19,7 @@
 //  * NCCL path (fallback; GTK_DISABLE_P2P=1): pack kernel -> ncclSend / ncclRecv in one group -> add kernels.
 // NCCL is dlopen'ed so that single-GPU users need no NCCL at all.
 #include <dlfcn.h>
+#include <time.h>
 #include <nccl.h>
 #include <cub/cub.cuh>
 #include <algorithm>
@@ -28,6 +29,7 @@
 int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, const int32_t* d_rows, int64_t nb, int* layer,
                              int* max_layer);   // fastq1.cu
 bool gtk_fastq1_plan_ok(const gtk_ctx* ctx);
+int gtk_fastq1_affine_state(gtk_ctx* ctx);   // 1: every active cell is exactly affine (classifies on first use), 0: not, -1: no plan
 
 namespace {
 
@@ -257,6 +259,50 @@ bool gtk_comm_assigns_untouched(const gtk_ctx* ctx) {
   return g && g->assign_untouched && !getenv("GTK_SWEEP_HALO");
 }
 
+// Descriptor of one fused exchange (called by the sweep launcher when ctx->fuse_comm_want): pointers, sequence numbers,
+// layer bounds.  Returns false when the plan does not qualify (no peer memory, more than two peers, layers unknown or
+// overlapping); a true return COMMITS the exchange (sequence numbers advance) — the caller must launch.
+bool gtk_comm_fused_begin(gtk_ctx* ctx, GtkCommDev* d, int n_layers) {
+  GhostPlan* g = (GhostPlan*)ctx->ghost;
+  d->on = 0;
+  if (!g || g->peers.empty() || g->peers.size() > 2 || !g->p2p_ready() || getenv("GTK_DISABLE_FUSED_COMM")) return false;
+  {   // measured on 2 GPUs (profiles/r02_fused_exchange.txt): as PUSH / UNPACK work items the exchange costs what its scattered
+      // 8-byte accesses cost — at 2.4 MB per interface (128^3 slabs) one launch beats three (0.134 vs 0.141 ms), at 39.6 MB
+      // (512 x 512 x 64 slabs) the UNPACK items are a 0.16 ms tail and the multi-launch overlap wins (0.919 vs 1.00 ms)
+    int64_t total = 0;
+    for (auto& p : g->peers) total += p.n_send_nz + p.n_send_b + p.n_recv_nz + p.n_recv_b;
+    const char* e = getenv("GTK_FUSED_COMM_MAX_MB");
+    const double max_mb = e ? atof(e) : 8.0;
+    if (total * 8.0 > max_mb * 1048576.0) return false;
+  }
+  int top = n_layers, bot = 0;
+  for (auto& p : g->peers) {
+    if (p.n_send_nz + p.n_send_b) { if (p.min_send_layer < 0) return false; top = std::min(top, p.min_send_layer); }
+    if (p.n_recv_nz + p.n_recv_b) { if (p.max_recv_layer < 0) return false; bot = std::max(bot, p.max_recv_layer + 1); }
+    if (p.n_send_b && !ctx->bvec) return false;
+  }
+  if (bot > top) return false;
+  d->n_peers = (int)g->peers.size();
+  d->top_layer = top; d->bot_layer = bot;
+  for (int i = 0; i < d->n_peers; ++i) {
+    Peer& p = g->peers[i];
+    ++p.seq;
+    GtkCommPeerDev& q = d->peer[i];
+    q.send_nz = p.send_nz; q.send_rows = p.send_rows; q.n_send_nz = p.n_send_nz; q.n_send_b = p.n_send_b;
+    q.remote_buf = p.remote_block + P2P_HDR;
+    q.remote_ready = reinterpret_cast<unsigned long long*>(p.remote_block) + 0;
+    q.local_ack = reinterpret_cast<const unsigned long long*>(p.ipc_block) + 1;
+    q.recv_nz = p.recv_nz; q.recv_rows = p.recv_rows; q.n_recv_nz = p.n_recv_nz; q.n_recv_b = p.n_recv_b;
+    q.recv_buf = p.recv_buf;
+    q.local_ready = reinterpret_cast<const unsigned long long*>(p.ipc_block) + 0;
+    q.remote_ack = reinterpret_cast<unsigned long long*>(p.remote_block) + 1;
+    q.seq = p.seq;
+    q.push_target = q.unpack_target = 0;   // filled by the launcher (it knows the item counts)
+  }
+  d->on = 1;
+  return true;
+}
+
 // The exchange plan indexes nzval / b of ONE pattern: it dies with that pattern (gtk_set_mesh, gtk_set_space,
 // gtk_matrix_symbolic) so that a later gtk_comm_sum_ghost_rows cannot scatter through stale positions.  The NCCL
 // communicator survives.
@@ -302,6 +348,25 @@ int32_t gtk_comm_init(gtk_ctx* ctx, int32_t rank, int32_t n_ranks, const void* i
   ctx->comm = comm;
   ctx->rank = rank;
   ctx->n_ranks = n_ranks;
+  // NCCL sets its rings and peer-to-peer channels up lazily, on the first collective / first send-recv of a pair (hundreds
+  // of ms each): do that here, as part of creating the communicator, with one tiny all-gather and one exchange with the
+  // two neighbouring ranks — the pairs a slab partition talks to — so that building an exchange plan costs what it costs
+  if (n_ranks > 1 && !getenv("GTK_NO_NCCL_WARMUP")) {
+    int64_t* d = nullptr;
+    GTK_CK(gtk_cuda_malloc(ctx, &d, sizeof(int64_t) * (size_t)(n_ranks + 4)));
+    GTK_CK(cudaMemsetAsync(d, 0, sizeof(int64_t) * (size_t)(n_ranks + 4), ctx->stream));
+    NCCL_CK(nccl().AllGather(d + n_ranks, d, 1, ncclInt64, comm, ctx->stream));
+    NCCL_CK(nccl().GroupStart());
+    for (int dr = -1; dr <= 1; dr += 2) {
+      const int q = rank + dr;
+      if (q < 0 || q >= n_ranks) continue;
+      NCCL_CK(nccl().Send(d + n_ranks, 1, ncclInt64, q, comm, ctx->stream));
+      NCCL_CK(nccl().Recv(d + n_ranks + 2 + (dr > 0), 1, ncclInt64, q, comm, ctx->stream));
+    }
+    NCCL_CK(nccl().GroupEnd());
+    GTK_CK(cudaStreamSynchronize(ctx->stream));
+    gtk_cuda_free(ctx, d);
+  }
   return GTK_OK;
 }
 
@@ -433,6 +498,17 @@ int32_t gtk_assemble_and_sum_ghost_rows_device(gtk_ctx* ctx, int32_t mform, cons
   if (!overlap) {
     if ((rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv))) return rc;
     return gtk_comm_sum_ghost_rows(ctx);
+  }
+  // First choice: ONE persistent kernel that sweeps, pushes the ghost entries over NVLink and adds the received ones
+  // (work items of the same launch, see GtkCommDev) — when the exactly-affine sweep kernel applies and the transport is
+  // peer memory with at most two peers (a slab partition).  Anything else takes the multi-launch overlap below.
+  if (g->p2p_ready() && g->peers.size() <= 2 && !getenv("GTK_DISABLE_FUSED_COMM") && gtk_fastq1_affine_state(ctx) == 1) {
+    ctx->fuse_comm_want = true; ctx->fuse_comm_done = false;
+    rc = gtk_numeric_both_impl(ctx, mform, pm, vform, pv);
+    ctx->fuse_comm_want = false;
+    if (rc) return rc;
+    if (ctx->fuse_comm_done) return GTK_OK;
+    return gtk_comm_sum_ghost_rows(ctx);   // the launcher declined (form / tabulation / layer bounds): serial exchange, same bits
   }
   if (!g->side) {
     // highest priority: the block scheduler otherwise keeps feeding the (much larger) sweep grid launched right after
@@ -646,8 +722,13 @@ struct Iota32 {
 
 }  // namespace
 
+static double wall_ms() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return 1e3 * t.tv_sec + 1e-6 * t.tv_nsec; }
+#define GTK_LAP(label) do { if (timing) { cudaStreamSynchronize(st); const double t_ = wall_ms(); fprintf(stderr, "[gtk rank %d] %s: %.2f ms\n", ctx->rank, label, t_ - t_last); t_last = t_; } } while (0)
+
 extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int64_t* own_start) {
   if (!ctx) return GTK_ERR_INVALID;
+  const bool timing = getenv("GTK_COMM_TIMING") != nullptr;
+  double t_last = wall_ms();
   if (!own_start) GTK_FAIL(GTK_ERR_INVALID, "gtk_comm_build_exchange: own_start is null");
   if (!ctx->comm) GTK_FAIL(GTK_ERR_STATE, "gtk_comm_build_exchange: call gtk_comm_init first");
   MatSym& m = ctx->ms;
@@ -710,6 +791,7 @@ extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int
     gtk_cuda_free(ctx, cand_nz); gtk_cuda_free(ctx, cand_rows);
   }
   gtk_cuda_free(ctx, tmp); gtk_cuda_free(ctx, d_cnt);
+  GTK_LAP("build_exchange: select ghost entries + keys");
   // 3. everybody learns how much it receives from whom
   std::vector<int64_t> row(2 * W, 0), mat((size_t)2 * W * W, 0);
   for (auto& sd : sends) { row[2 * sd.peer] = sd.n_nz; row[2 * sd.peer + 1] = sd.n_b; }
@@ -721,6 +803,7 @@ extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int
   GTK_CK(cudaMemcpyAsync(mat.data(), d_mat, sizeof(int64_t) * 2 * W * W, cudaMemcpyDeviceToHost, st));
   GTK_CK(cudaStreamSynchronize(st));
   gtk_cuda_free(ctx, d_row); gtk_cuda_free(ctx, d_mat);
+  GTK_LAP("build_exchange: all-gather of counts");
   // 4. keys travel to the owners
   struct Recv { int peer; int64_t n_nz, n_b; int64_t* keys = nullptr; };
   std::vector<Recv> recvs;
@@ -736,6 +819,7 @@ extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int
   for (auto& sd : sends) NCCL_CK(nccl().Send(sd.keys, (size_t)(2 * sd.n_nz + sd.n_b), ncclInt64, sd.peer, comm, st));
   for (auto& rv : recvs) NCCL_CK(nccl().Recv(rv.keys, (size_t)(2 * rv.n_nz + rv.n_b), ncclInt64, rv.peer, comm, st));
   NCCL_CK(nccl().GroupEnd());
+  GTK_LAP("build_exchange: send/recv of keys");
   // 5. owners locate the announced entries in their own pattern
   int* d_err = nullptr;
   GTK_CK(gtk_cuda_malloc(ctx, &d_err, sizeof(int)));
@@ -767,8 +851,10 @@ extern "C" int32_t gtk_comm_build_exchange(gtk_ctx* ctx, int64_t gid0, const int
                                   ((h_err & 1) ? "is not a local dof of the owner; " : "") + ((h_err & 2) ? "is missing from the owner's sparsity pattern; " : "") +
                                   ((h_err & 4) ? "lies in a row the receiver does not own; " : ""));
   }
+  GTK_LAP("build_exchange: match keys");
   std::sort(peers.begin(), peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
   for (auto& p : peers) if ((rc = install_peer(ctx, p))) return rc;
+  GTK_LAP("build_exchange: install peers (buffers, min/max layers)");
   if (ctx->ghost) {
     ((GhostPlan*)ctx->ghost)->assign_untouched = true;
     // columns no active cell touches are not swept any more: they hold what the unpack assigns, or zeros (rows nobody sends)
@@ -788,6 +874,8 @@ extern "C" int32_t gtk_comm_connect_peer_memory(gtk_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   ncclComm_t comm = (ncclComm_t)ctx->comm;
   const int W = ctx->n_ranks;
+  const bool timing = getenv("GTK_COMM_TIMING") != nullptr;
+  double t_last = wall_ms();
   int ok = getenv("GTK_DISABLE_P2P") ? 0 : 1;
   const size_t np = g ? g->peers.size() : 0;
   unsigned char* d_h = nullptr;   // [np] mine, [np] theirs, 64 bytes each
@@ -807,6 +895,7 @@ extern "C" int32_t gtk_comm_connect_peer_memory(gtk_ctx* ctx) {
   NCCL_CK(nccl().GroupEnd());
   if (np) GTK_CK(cudaMemcpyAsync(theirs.data(), d_h + 64 * np, 64 * np, cudaMemcpyDeviceToHost, st));
   GTK_CK(cudaStreamSynchronize(st));
+  GTK_LAP("connect_peer_memory: export + swap handles");
   if (ok) for (size_t i = 0; i < np; ++i) {
     Peer& p = g->peers[i];
     if (p.remote_block) { cudaIpcCloseMemHandle(p.remote_block); p.remote_block = nullptr; }
@@ -816,6 +905,7 @@ extern "C" int32_t gtk_comm_connect_peer_memory(gtk_ctx* ctx) {
     if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
     p.remote_block = (double*)ptr;
   }
+  GTK_LAP("connect_peer_memory: cudaIpcOpenMemHandle");
   // agreement: one int per rank
   int *d_ok = nullptr, *d_all = nullptr;
   GTK_CK(gtk_cuda_malloc(ctx, &d_ok, sizeof(int)));
@@ -829,5 +919,6 @@ extern "C" int32_t gtk_comm_connect_peer_memory(gtk_ctx* ctx) {
   bool all_ok = true;
   for (int v : all) all_ok = all_ok && v != 0;
   if (g) g->p2p_off = !all_ok;
+  GTK_LAP("connect_peer_memory: agreement");
   return GTK_OK;
 }

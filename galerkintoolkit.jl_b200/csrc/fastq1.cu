@@ -36,6 +36,7 @@
 #include "q1hex_math.cuh"
 
 bool gtk_comm_assigns_untouched(const gtk_ctx* ctx);   // comm.cu
+bool gtk_comm_fused_begin(gtk_ctx* ctx, GtkCommDev* d, int n_layers);   // comm.cu
 
 namespace {
 
@@ -74,8 +75,13 @@ struct FastPlan {
   struct ItemPlan {
     int4* items = nullptr;
     int n = 0, cap = 0, z_begin = -1, z_end = -1, warps = 0;
+    int top = -1, bot = -1, n_top = 0, n_bot = 0;      // fused exchange: layer bounds and counts of the top / bottom sweep items
+    long long comm_key[4] = {-1, -1, -1, -1};          // entries sent / received per peer slot the PUSH / UNPACK items were cut for
+    int n_push[2] = {0, 0}, n_unpack[2] = {0, 0};
   };
-  ItemPlan ip_affine[4];
+  ItemPlan ip_affine[5];                               // [launch mode]; [4]: fused sweep + exchange
+  unsigned long long* comm_cnt = nullptr;              // [8] counters of the fused exchange (device), monotone
+  unsigned long long comm_base[6] = {0, 0, 0, 0, 0, 0};
   std::vector<uint8_t> h_act;          // [gx * gyp * (n3+1)] host copy: patch (16 x 2 nodes) holds a matrix column in that node layer
   unsigned long long* sched = nullptr; // ticket counter (device), grows monotonically across launches
   unsigned long long sched_next = 0;   // first ticket of the next launch
@@ -281,7 +287,11 @@ struct SweepArgs {
   int n_items;
   unsigned long long* sched;
   unsigned long long sched_base;
+  GtkCommDev comm;      // ghost-row exchange fused into this launch (comm.on)
 };
+
+constexpr int COMM_CHUNK = 512;    // entries of one PUSH / UNPACK work item: ONE round of 16 independent entries per lane (the
+                                   // dependent index -> value loads are latency-bound: a long chunk is a long serial tail)
 
 template <int BX, int BY>
 struct Cfg {
@@ -822,6 +832,103 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
 }
 
 
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// PUSH / UNPACK work item of the fused exchange: item = {peer slot, chunk, kind (-1 push, -2 unpack), 0}.
+// Tickets are handed out in list order and a warp finishes its item before it draws the next, so every item with a lower
+// ticket is running or done when a warp waits here: the waits cannot deadlock.  Waiting on the PEER's flag depends only on
+// the peer's own kernel (its PUSH waits for our ack of the PREVIOUS exchange, issued by the previous launch).
+__device__ __forceinline__ void comm_item(const SweepArgs& a, const int4 it, const int lane) {
+  const GtkCommPeerDev& q = a.comm.peer[it.x];
+  const long long i0 = (long long)it.y * COMM_CHUNK;
+  if (it.z == -1) {
+    const long long n = q.n_send_nz + q.n_send_b, i1 = min(i0 + (long long)COMM_CHUNK, n);
+    if (lane == 0) {
+      const unsigned long long t0 = a.comm.dbg ? gtimer() : 0;
+      while (ld_acquire_gpu_u64(a.comm.cnt + 0) < a.comm.top_target) __nanosleep(100);   // everything a peer waits for is written
+      const unsigned long long t1 = a.comm.dbg ? gtimer() : 0;
+      while (ld_acquire_sys_u64(q.local_ack) + 1 < q.seq) __nanosleep(100);              // the owner consumed the previous exchange
+      if (a.comm.dbg) { const unsigned long long t2 = gtimer(); atomicMax(a.comm.dbg + 0, t1 - t0); atomicMax(a.comm.dbg + 1, t2 - t1); }
+    }
+    __syncwarp();
+    constexpr int U = COMM_CHUNK / 32;   // the whole chunk in ONE round: U independent index -> value chains per lane
+    for (long long ib = i0 + lane; ib < i1; ib += 32 * U) {
+      const double* src[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = ib + 32 * u;
+        src[u] = i >= i1 ? nullptr : (i < q.n_send_nz ? a.nzval + __ldg(q.send_nz + i) : a.b + __ldg(q.send_rows + (i - q.n_send_nz)));
+      }
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = src[u] ? __ldcg(src[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (src[u]) q.remote_buf[ib + 32 * u] = v[u];
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0 && atomicAdd(a.comm.cnt + 2 + it.x, 1ull) + 1 == q.push_target) {   // last chunk: publish
+      __threadfence_system();
+      st_release_sys_u64(q.remote_ready, q.seq);
+    }
+  } else {
+    const long long n = q.n_recv_nz + q.n_recv_b, i1 = min(i0 + (long long)COMM_CHUNK, n);
+    if (lane == 0) {
+      const unsigned long long t0 = a.comm.dbg ? gtimer() : 0;
+      while (ld_acquire_gpu_u64(a.comm.cnt + 1) < a.comm.bot_target) __nanosleep(100);   // our own partial sums are in place
+      const unsigned long long t1 = a.comm.dbg ? gtimer() : 0;
+      while (ld_acquire_sys_u64(q.local_ready) < q.seq) __nanosleep(100);                // the peer's values have landed
+      if (a.comm.dbg) { const unsigned long long t2 = gtimer(); atomicMax(a.comm.dbg + 2, t1 - t0); atomicMax(a.comm.dbg + 3, t2 - t1); }
+    }
+    __syncwarp();
+    constexpr int U = COMM_CHUNK / 32;
+    for (long long ib = i0 + lane; ib < i1; ib += 32 * U) {
+      double* dst[U]; double v[U], old[U]; bool add[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = ib + 32 * u;
+        dst[u] = nullptr; add[u] = true; v[u] = 0.0;
+        if (i < i1) {
+          v[u] = __ldcg(q.recv_buf + i);
+          if (i < q.n_recv_nz) {
+            const long long p = __ldg(q.recv_nz + i);
+            add[u] = p >= 0;                        // ~p: a column no local cell contributes to — the value IS the peer's
+            dst[u] = a.nzval + (p >= 0 ? p : ~p);
+          } else dst[u] = a.b + __ldg(q.recv_rows + (i - q.n_recv_nz));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) old[u] = (dst[u] && add[u]) ? __ldcg(dst[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (dst[u]) *dst[u] = add[u] ? old[u] + v[u] : v[u];
+    }
+    __syncwarp();
+    if (lane == 0 && atomicAdd(a.comm.cnt + 4 + it.x, 1ull) + 1 == q.unpack_target) {   // last chunk: the buffer may be overwritten
+      __threadfence_system();
+      st_release_sys_u64(q.remote_ack, q.seq);
+    }
+  }
+}
+
 // Persistent launch: every warp draws (patch, z-segment) work items from a ticket counter until none is left.  The host
 // orders the items from long z-segments to short ones (guided self-scheduling): long segments amortise the halo step of a
 // segment start, the short ones at the end level the finishing times of the ~2200 resident warps — the uniform 6-layer
@@ -841,7 +948,20 @@ __global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
     t = __shfl_sync(0xFFFFFFFFu, t, 0);
     if (t >= (unsigned long long)a.n_items) break;
     const int4 it = __ldg(a.items + t);
+    if (it.z < 0) { comm_item(a, it, lane); continue; }
     affine_w_item<TWOPASS>(a, it.x, it.y, it.z, it.w, OutW, CellW, XW, lane);
+    if (a.comm.on) {
+      const bool top = it.z >= a.comm.top_layer, bot = it.w <= a.comm.bot_layer;
+      if (top || bot) {   // a PUSH / UNPACK item of this launch reads what this item wrote: complete the bulk stores, publish
+        if (!(a.comm.on & 2)) {
+        bulk_wait_all();
+        fence_proxy_async_all();
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(a.comm.cnt + (top ? 0 : 1), 1ull);
+      }
+    }
     __syncwarp();
   }
 }
@@ -877,6 +997,7 @@ void plan_free(gtk_ctx* ctx, FastPlan* p) {
   for (auto& tp : p->tp_sweep) if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
   for (auto& ip : p->ip_affine) if (ip.items) gtk_dev_free(ctx, ip.items, sizeof(int4) * (size_t)ip.cap);
   if (p->sched) gtk_cuda_free(ctx, p->sched);
+  if (p->comm_cnt) gtk_cuda_free(ctx, p->comm_cnt);
   delete p;
 }
 
@@ -1032,9 +1153,18 @@ int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
 // Work items of a persistent warp-private launch over the node layers [z_begin, z_end): z-segments from long to short
 // (guided self-scheduling for `warps` resident warps), one item per (segment, patch), trimmed to the node layers in which
 // the patch holds a matrix column at all (the Dirichlet planes and the overhang past the mesh produce no item).
-int32_t build_item_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::ItemPlan& ip, int z_begin, int z_end, int warps) {
+int32_t build_item_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::ItemPlan& ip, int z_begin, int z_end, int warps,
+                        const GtkCommDev* comm = nullptr) {
   using C = WCfg;
-  if (ip.items && ip.z_begin == z_begin && ip.z_end == z_end && ip.warps == warps) return GTK_OK;
+  const int top = comm ? comm->top_layer : -1, bot = comm ? comm->bot_layer : -1;
+  long long ckey[4] = {-1, -1, -1, -1};
+  if (comm) for (int i = 0; i < comm->n_peers; ++i) {
+    ckey[2 * i] = comm->peer[i].n_send_nz + comm->peer[i].n_send_b;
+    ckey[2 * i + 1] = comm->peer[i].n_recv_nz + comm->peer[i].n_recv_b;
+  }
+  if (ip.items && ip.z_begin == z_begin && ip.z_end == z_end && ip.warps == warps && ip.top == top && ip.bot == bot &&
+      ckey[0] == ip.comm_key[0] && ckey[1] == ip.comm_key[1] && ckey[2] == ip.comm_key[2] && ckey[3] == ip.comm_key[3])
+    return GTK_OK;
   const int gx = (p->n1 + 1 + C::BX - 1) / C::BX, gyp = (p->n2 + 1 + C::BY - 1) / C::BY;
   const int nl = p->n3 + 1;
   if (p->h_act.empty()) {   // layer-granular activity of every patch, once per plan
@@ -1055,26 +1185,61 @@ int32_t build_item_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::ItemPlan& ip, int z
   const int smin = (e = getenv("GTK_AFFINE_SMIN")) && atoi(e) > 0 ? atoi(e) : 3;
   const int smax = (e = getenv("GTK_AFFINE_SMAX")) && atoi(e) > 0 ? atoi(e) : 24;
   const int fixed = (e = getenv("GTK_AFFINE_SEG")) && atoi(e) > 0 ? atoi(e) : 0;   // uniform segments (the former static grid's choice: 6)
-  std::vector<std::pair<int, int>> segs;
-  for (int z = z_begin; z < z_end;) {
-    const int rem = z_end - z;
-    int len = fixed ? fixed : (int)((double)rem * gx * gyp / (gf * (warps > 0 ? warps : 1)) + 0.999);
-    if (!fixed) len = len < smin ? smin : (len > smax ? smax : len);
-    if (len > rem || rem - len < smin / 2 + 1) len = rem;
-    segs.emplace_back(z, z + len);
-    z += len;
-  }
+  auto guided = [&](int zb, int ze, std::vector<std::pair<int, int>>& segs) {
+    for (int z = zb; z < ze;) {
+      const int rem = ze - z;
+      int len = fixed ? fixed : (int)((double)rem * gx * gyp / (gf * (warps > 0 ? warps : 1)) + 0.999);
+      if (!fixed) len = len < smin ? smin : (len > smax ? smax : len);
+      if (len > rem || rem - len < smin / 2 + 1) len = rem;
+      segs.emplace_back(z, z + len);
+      z += len;
+    }
+  };
   std::vector<int4> items;
-  items.reserve((size_t)gx * gyp * segs.size());
-  for (auto& sg : segs)
-    for (int py = 0; py < gyp; ++py)
-      for (int bx = 0; bx < gx; ++bx) {
-        const uint8_t* act = p->h_act.data() + bx + (size_t)gx * py;
-        int lo = sg.first, hi = sg.second;
-        while (lo < hi && !act[(size_t)gx * gyp * lo]) ++lo;
-        while (hi > lo && !act[(size_t)gx * gyp * (hi - 1)]) --hi;
-        if (hi > lo) items.push_back(make_int4(bx * C::BX, py * C::BY, lo, hi));
-      }
+  auto emit = [&](const std::vector<std::pair<int, int>>& segs) {
+    int n0 = (int)items.size();
+    for (auto& sg : segs)
+      for (int py = 0; py < gyp; ++py)
+        for (int bx = 0; bx < gx; ++bx) {
+          const uint8_t* act = p->h_act.data() + bx + (size_t)gx * py;
+          int lo = sg.first, hi = sg.second;
+          while (lo < hi && !act[(size_t)gx * gyp * lo]) ++lo;
+          while (hi > lo && !act[(size_t)gx * gyp * (hi - 1)]) --hi;
+          if (hi > lo) items.push_back(make_int4(bx * C::BX, py * C::BY, lo, hi));
+        }
+    return (int)items.size() - n0;
+  };
+  ip.n_top = ip.n_bot = 0;
+  ip.n_push[0] = ip.n_push[1] = ip.n_unpack[0] = ip.n_unpack[1] = 0;
+  if (!comm) {
+    std::vector<std::pair<int, int>> segs;
+    guided(z_begin, z_end, segs);
+    emit(segs);
+  } else {
+    // order: what the peers wait for, then what the received values are added to, then the PUSH items (by then the top
+    // items are done or nearly), the bulk of the sweep from long to short segments, and the UNPACK items last
+    const int t0 = std::max(top, z_begin), b1 = std::min(bot, z_end);
+    std::vector<std::pair<int, int>> st, sb, sm;
+    if (z_end > t0) st.emplace_back(t0, z_end);
+    if (b1 > z_begin) sb.emplace_back(z_begin, b1);
+    ip.n_top = emit(st);
+    ip.n_bot = emit(sb);
+    const bool push_last = getenv("GTK_FUSED_PUSH_LAST") != nullptr;
+    if (!push_last) for (int i = 0; i < comm->n_peers; ++i) {
+      ip.n_push[i] = (int)((ckey[2 * i] + COMM_CHUNK - 1) / COMM_CHUNK);
+      for (int c = 0; c < ip.n_push[i]; ++c) items.push_back(make_int4(i, c, -1, 0));
+    }
+    guided(std::max(b1, z_begin), std::min(t0, z_end), sm);
+    emit(sm);
+    if (push_last) for (int i = 0; i < comm->n_peers; ++i) {
+      ip.n_push[i] = (int)((ckey[2 * i] + COMM_CHUNK - 1) / COMM_CHUNK);
+      for (int c = 0; c < ip.n_push[i]; ++c) items.push_back(make_int4(i, c, -1, 0));
+    }
+    for (int i = 0; i < comm->n_peers; ++i) {
+      ip.n_unpack[i] = (int)((ckey[2 * i + 1] + COMM_CHUNK - 1) / COMM_CHUNK);
+      for (int c = 0; c < ip.n_unpack[i]; ++c) items.push_back(make_int4(i, c, -2, 0));
+    }
+  }
   if ((int)items.size() > ip.cap) {
     if (ip.items) gtk_dev_free(ctx, ip.items, sizeof(int4) * (size_t)ip.cap);
     ip.items = nullptr; ip.cap = 0;
@@ -1084,7 +1249,8 @@ int32_t build_item_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::ItemPlan& ip, int z
   }
   if (!items.empty()) GTK_CK(cudaMemcpyAsync(ip.items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice, ctx->stream));
   GTK_CK(cudaStreamSynchronize(ctx->stream));   // `items` is a local
-  ip.n = (int)items.size(); ip.z_begin = z_begin; ip.z_end = z_end; ip.warps = warps;
+  ip.n = (int)items.size(); ip.z_begin = z_begin; ip.z_end = z_end; ip.warps = warps; ip.top = top; ip.bot = bot;
+  for (int i = 0; i < 4; ++i) ip.comm_key[i] = ckey[i];
   return GTK_OK;
 }
 
@@ -1102,9 +1268,39 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   layer_range(ctx, p->n3 + 1, &a.z_begin, &a.z_end);
   if (a.z_end <= a.z_begin) return GTK_OK;
   const int resident = ctx->sm_count * occ;
-  FastPlan::ItemPlan& ip = p->ip_affine[ctx->seg_mode];
-  int32_t rc = build_item_plan(ctx, p, ip, a.z_begin, a.z_end, resident * WPB);
-  if (rc) return rc;
+  int32_t rc;
+  a.comm.on = 0;
+  // the ghost-row exchange rides in this launch when comm.cu asks for it and the plan qualifies
+  const bool fuse = ctx->fuse_comm_want && ctx->seg_mode == 0 && a.do_matrix && gtk_comm_fused_begin(ctx, &a.comm, p->n3 + 1);
+  FastPlan::ItemPlan& ip = p->ip_affine[fuse ? 4 : ctx->seg_mode];
+  if ((rc = build_item_plan(ctx, p, ip, a.z_begin, a.z_end, resident * WPB, fuse ? &a.comm : nullptr))) return rc;
+  if (fuse) {
+    if (!p->comm_cnt) {
+      GTK_CK(gtk_cuda_malloc(ctx, &p->comm_cnt, 16 * sizeof(unsigned long long)));
+      GTK_CK(cudaMemsetAsync(p->comm_cnt, 0, 16 * sizeof(unsigned long long), ctx->stream));
+      for (auto& b : p->comm_base) b = 0;
+    }
+    a.comm.cnt = p->comm_cnt;
+    a.comm.dbg = nullptr;
+    static const bool dbg = getenv("GTK_COMM_TIMING") != nullptr;
+    if (dbg) {
+      unsigned long long h[4];
+      GTK_CK(cudaMemcpyAsync(h, p->comm_cnt + 8, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+      GTK_CK(cudaStreamSynchronize(ctx->stream));
+      fprintf(stderr, "[gtk rank %d] fused exchange, longest waits of the previous step (us): push<-top %.1f  push<-ack %.1f  unpack<-bottom %.1f  unpack<-ready %.1f | items %d (top %d bottom %d push %d/%d unpack %d/%d) layers top>=%d bottom<%d\n",
+              ctx->rank, h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3, h[3] * 1e-3, ip.n, ip.n_top, ip.n_bot, ip.n_push[0], ip.n_push[1], ip.n_unpack[0], ip.n_unpack[1], a.comm.top_layer, a.comm.bot_layer);
+      GTK_CK(cudaMemsetAsync(p->comm_cnt + 8, 0, sizeof(h), ctx->stream));
+      a.comm.dbg = p->comm_cnt + 8;
+    }
+    a.comm.top_target = (p->comm_base[0] += (unsigned long long)ip.n_top);
+    a.comm.bot_target = (p->comm_base[1] += (unsigned long long)ip.n_bot);
+    for (int i = 0; i < a.comm.n_peers; ++i) {
+      a.comm.peer[i].push_target = (p->comm_base[2 + i] += (unsigned long long)ip.n_push[i]);
+      a.comm.peer[i].unpack_target = (p->comm_base[4 + i] += (unsigned long long)ip.n_unpack[i]);
+    }
+    ctx->fuse_comm_done = true;
+    if (getenv("GTK_FUSED_NO_FENCE")) a.comm.on |= 2;
+  }
   if (ip.n == 0) return GTK_OK;
   if (!p->sched) {
     GTK_CK(gtk_cuda_malloc(ctx, &p->sched, sizeof(unsigned long long)));
@@ -1194,6 +1390,21 @@ int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, c
   GTK_CK(cudaStreamSynchronize(ctx->stream));
   if (h != 0x7FFFFFFF) { *layer = h; if (max_layer) *max_layer = h2[1]; }
   return GTK_OK;
+}
+
+int gtk_fastq1_affine_state(gtk_ctx* ctx) {
+  if (!gtk_fastq1_plan_ok(ctx) || getenv("GTK_DISABLE_AFFINE")) return -1;
+  FastPlan* p = (FastPlan*)ctx->ms.plan;
+  if (p->affine_state < 0) {
+    int k0 = 0, k1 = p->n3;
+    if (ctx->act_count >= 0) {
+      const int64_t per_layer = (int64_t)p->n1 * p->n2;
+      if (ctx->act_first % per_layer || ctx->act_count % per_layer) return -1;
+      k0 = (int)(ctx->act_first / per_layer); k1 = k0 + (int)(ctx->act_count / per_layer);
+    }
+    if (classify_affine(ctx, p, ctx->xyz + 3 * p->node_off, k0, k1)) return -1;
+  }
+  return p->affine_state;
 }
 
 bool gtk_fastq1_plan_ok(const gtk_ctx* ctx) {

@@ -79,6 +79,28 @@ struct VecSym {
   int32_t* urow = nullptr;     // [n_urows] 0-based row id
 };
 
+// Ghost-row exchange fused into the persistent sweep kernel (fastq1.cu + comm.cu): the warps that drew all (patch,
+// z-segment) items of the top layers have written what a peer waits for; PUSH items then gather those entries and store
+// them into the owner's buffer over NVLink, UNPACK items add what the peers pushed — work items of the SAME kernel, ordered
+// by device-side counters.  All counters only ever grow; the host passes this launch's targets.
+struct GtkCommPeerDev {
+  const int64_t* send_nz; const int32_t* send_rows; long long n_send_nz, n_send_b;
+  double* remote_buf; unsigned long long* remote_ready; const unsigned long long* local_ack;
+  const int64_t* recv_nz; const int32_t* recv_rows; long long n_recv_nz, n_recv_b;
+  const double* recv_buf; const unsigned long long* local_ready; unsigned long long* remote_ack;
+  unsigned long long seq;                       // exchange number with this peer
+  unsigned long long push_target, unpack_target;   // counter values at which the last PUSH / UNPACK item of this launch finishes
+};
+struct GtkCommDev {
+  int on;                                       // 0: plain sweep
+  int n_peers;
+  int top_layer, bot_layer;                     // sweep items with kz0 >= top_layer feed the PUSH, with kz1 <= bot_layer the UNPACK
+  unsigned long long* cnt;                      // [0] top items done [1] bottom items done [2+p] PUSH items done [4+p] UNPACK items done
+  unsigned long long top_target, bot_target;
+  unsigned long long* dbg;                      // optional [8]: ns spent waiting (GTK_COMM_TIMING), else nullptr
+  GtkCommPeerDev peer[2];
+};
+
 struct gtk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -131,6 +153,8 @@ struct gtk_ctx {
   // sweep kernels: node-layer subset of the next launch (comm.cu overlap): 0 all, 1 layers >= seg_layer (hold what goes to
   // a peer), 3 layers < seg_lo (hold what a peer adds to), 2 the layers in between
   int seg_mode = 0, seg_layer = 0, seg_lo = 0;
+  // fused exchange (comm.cu asks, fastq1.cu answers): want = run the exchange inside the sweep launch if it can; done = it did
+  bool fuse_comm_want = false, fuse_comm_done = false;
 
   // per-kernel profiling (events around each launch of the last numeric call)
   bool profiling = false;
