@@ -30,6 +30,10 @@ int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, c
                              int* max_layer);   // fastq1.cu
 bool gtk_fastq1_plan_ok(const gtk_ctx* ctx);
 int gtk_fastq1_affine_state(gtk_ctx* ctx);   // 1: every active cell is exactly affine (classifies on first use), 0: not, -1: no plan
+int32_t gtk_fastq1_comm_tables(gtk_ctx* ctx, const int64_t* send_nz, int64_t n_send_nz, const int32_t* send_rows, int64_t n_send_b,
+                               const int64_t* recv_nz, int64_t n_recv_nz, const int32_t* recv_rows, int64_t n_recv_b,
+                               int send_layer, int recv_layer, int32_t** tbl_out, bool* ok);
+int64_t gtk_fastq1_plane_nodes(const gtk_ctx* ctx);
 
 namespace {
 
@@ -94,6 +98,10 @@ struct Peer {
   // exchange counter of the peer-memory path WITH THIS PEER: starts at 0 together with the zero-filled flag header of a
   // freshly created ipc_block, so replacing the plan of a pair (both sides re-export / re-import) restarts the protocol
   unsigned long long seq = 0;
+  // exchange fused into the sweep's copy-out (GtkCommDev mode 2): verified per-node buffer offsets, or nullptr
+  int32_t* tbl = nullptr;
+  size_t tbl_bytes = 0;
+  int send_row_layer = -1, recv_row_layer = -1;
 };
 constexpr int P2P_HDR = 32;   // doubles (256 B) in front of the receive buffer
 
@@ -200,6 +208,8 @@ void free_peer(gtk_ctx* ctx, Peer& p) {
   if (p.remote_block) cudaIpcCloseMemHandle(p.remote_block);
   if (p.ipc_block) { cudaFree(p.ipc_block); ctx->bytes_held -= (int64_t)p.ipc_bytes; }
   if (p.done_ctr) cudaFree(p.done_ctr);
+  if (p.tbl) gtk_dev_free(ctx, p.tbl, p.tbl_bytes);
+  p.tbl = nullptr;
   p.remote_block = p.ipc_block = p.recv_buf = nullptr; p.done_ctr = nullptr;
 }
 
@@ -226,8 +236,9 @@ static int32_t install_peer(gtk_ctx* ctx, Peer p) {
   int32_t rc;
   const int64_t n_send = p.n_send_nz + p.n_send_b, n_recv = p.n_recv_nz + p.n_recv_b;
   if (n_send) if ((rc = gtk_dev_alloc(ctx, (void**)&p.send_buf, sizeof(double) * n_send))) return rc;
-  // receive buffer + flag header in ONE raw allocation (not pooled): it is exported to the peer over CUDA IPC
-  p.ipc_bytes = sizeof(double) * (size_t)(P2P_HDR + n_recv);
+  // flag header + TWO receive buffers (exchange k uses buffer k & 1: a sender may run one exchange ahead of the owner's
+  // unpack) in ONE raw allocation (not pooled): it is exported to the peer over CUDA IPC
+  p.ipc_bytes = sizeof(double) * (size_t)(P2P_HDR + 2 * n_recv);
   GTK_CK(cudaMalloc(&p.ipc_block, p.ipc_bytes));
   ctx->bytes_held += (int64_t)p.ipc_bytes;
   GTK_CK(cudaMemsetAsync(p.ipc_block, 0, p.ipc_bytes, ctx->stream));
@@ -235,9 +246,18 @@ static int32_t install_peer(gtk_ctx* ctx, Peer p) {
   GTK_CK(cudaMalloc(&p.done_ctr, 2 * sizeof(unsigned int)));
   GTK_CK(cudaMemsetAsync(p.done_ctr, 0, 2 * sizeof(unsigned int), ctx->stream));
   GTK_CK(cudaStreamSynchronize(ctx->stream));
-  if ((rc = gtk_fastq1_min_layer(ctx, p.send_nz, p.n_send_nz, p.send_rows, p.n_send_b, &p.min_send_layer, nullptr))) return rc;
+  int max_send_layer = -1;
+  if ((rc = gtk_fastq1_min_layer(ctx, p.send_nz, p.n_send_nz, p.send_rows, p.n_send_b, &p.min_send_layer, &max_send_layer))) return rc;
   { int lo_unused = -1;
     if ((rc = gtk_fastq1_min_layer(ctx, p.recv_nz, p.n_recv_nz, p.recv_rows, p.n_recv_b, &lo_unused, &p.max_recv_layer))) return rc; }
+  {   // tables of the copy-out fused exchange: the exchanged rows of a slab interface lie in the highest layer of the columns
+      // that hold them (send: the top node layer, receive: the first owned layer)
+    bool ok = false;
+    if ((rc = gtk_fastq1_comm_tables(ctx, p.send_nz, p.n_send_nz, p.send_rows, p.n_send_b, p.recv_nz, p.n_recv_nz, p.recv_rows, p.n_recv_b,
+                                     max_send_layer, p.max_recv_layer, &p.tbl, &ok))) return rc;
+    p.tbl_bytes = ok ? sizeof(int32_t) * 6 * (size_t)gtk_fastq1_plane_nodes(ctx) : 0;
+    p.send_row_layer = max_send_layer; p.recv_row_layer = p.max_recv_layer;
+  }
   g->peers.push_back(p);
   std::sort(g->peers.begin(), g->peers.end(), [](const Peer& a, const Peer& b) { return a.rank < b.rank; });
   return GTK_OK;
@@ -266,9 +286,12 @@ bool gtk_comm_fused_begin(gtk_ctx* ctx, GtkCommDev* d, int n_layers) {
   GhostPlan* g = (GhostPlan*)ctx->ghost;
   d->on = 0;
   if (!g || g->peers.empty() || g->peers.size() > 2 || !g->p2p_ready() || getenv("GTK_DISABLE_FUSED_COMM")) return false;
-  {   // measured on 2 GPUs (profiles/r02_fused_exchange.txt): as PUSH / UNPACK work items the exchange costs what its scattered
-      // 8-byte accesses cost — at 2.4 MB per interface (128^3 slabs) one launch beats three (0.134 vs 0.141 ms), at 39.6 MB
-      // (512 x 512 x 64 slabs) the UNPACK items are a 0.16 ms tail and the multi-launch overlap wins (0.919 vs 1.00 ms)
+  // mode 2 (the exchange rides in the copy-out of the sweep: ghost entries go from registers to the peer's buffer, received
+  // ones are added in registers) needs the verified per-node tables of every peer; mode 1 (PUSH / UNPACK work items) pays
+  // for scattered 8-byte accesses and only wins for small interfaces (profiles/r02_fused_exchange.txt)
+  bool mode2 = !getenv("GTK_DISABLE_FUSED_COPYOUT");
+  for (auto& p : g->peers) mode2 = mode2 && p.tbl != nullptr;
+  if (!mode2) {
     int64_t total = 0;
     for (auto& p : g->peers) total += p.n_send_nz + p.n_send_b + p.n_recv_nz + p.n_recv_b;
     const char* e = getenv("GTK_FUSED_COMM_MAX_MB");
@@ -288,18 +311,20 @@ bool gtk_comm_fused_begin(gtk_ctx* ctx, GtkCommDev* d, int n_layers) {
     Peer& p = g->peers[i];
     ++p.seq;
     GtkCommPeerDev& q = d->peer[i];
+    const int64_t ns = p.n_send_nz + p.n_send_b, nr = p.n_recv_nz + p.n_recv_b;
     q.send_nz = p.send_nz; q.send_rows = p.send_rows; q.n_send_nz = p.n_send_nz; q.n_send_b = p.n_send_b;
-    q.remote_buf = p.remote_block + P2P_HDR;
+    q.remote_buf = p.remote_block + P2P_HDR + (p.seq & 1) * ns;
     q.remote_ready = reinterpret_cast<unsigned long long*>(p.remote_block) + 0;
     q.local_ack = reinterpret_cast<const unsigned long long*>(p.ipc_block) + 1;
     q.recv_nz = p.recv_nz; q.recv_rows = p.recv_rows; q.n_recv_nz = p.n_recv_nz; q.n_recv_b = p.n_recv_b;
-    q.recv_buf = p.recv_buf;
+    q.recv_buf = p.recv_buf + (p.seq & 1) * nr;
     q.local_ready = reinterpret_cast<const unsigned long long*>(p.ipc_block) + 0;
     q.remote_ack = reinterpret_cast<unsigned long long*>(p.remote_block) + 1;
     q.seq = p.seq;
     q.push_target = q.unpack_target = 0;   // filled by the launcher (it knows the item counts)
+    q.tbl = p.tbl; q.T = p.send_row_layer; q.B = p.recv_row_layer;
   }
-  d->on = 1;
+  d->on = mode2 ? 2 : 1;
   return true;
 }
 
@@ -412,7 +437,7 @@ static int32_t exchange_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st) {
       const unsigned long long* lhdr = reinterpret_cast<const unsigned long long*>(p.ipc_block);
       { GtkProf pr_(ctx, "k_pack_push");
         k_pack_push<<<std::min(grid_for(n), 4 * ctx->sm_count), 256, 0, st>>>(ctx->nzval, p.send_nz, p.n_send_nz, ctx->bvec, p.send_rows, p.n_send_b,
-                                                 p.remote_block + P2P_HDR, rhdr + 0, lhdr + 1, p.seq, p.done_ctr + 0); }
+                                                 p.remote_block + P2P_HDR + (p.seq & 1) * n, rhdr + 0, lhdr + 1, p.seq, p.done_ctr + 0); }
       GTK_CK(cudaGetLastError());
       gtk_count_launch(ctx);
     }
@@ -449,7 +474,7 @@ static int32_t unpack_on(gtk_ctx* ctx, GhostPlan* g, cudaStream_t st, bool alone
         // sharing the GPU with the sweep: at most 2 blocks per SM (a block may spin for the peer's flag); alone: the
         // scattered read-modify-writes are latency-bound, so as many threads as there are entries to hide it
         k_wait_unpack_add<<<alone ? std::min((int)((n + 255) / 256), 16 * ctx->sm_count) : std::min(grid_for(n), 2 * ctx->sm_count), 256, 0, st>>>(ctx->nzval, p.recv_nz, p.n_recv_nz, ctx->bvec, p.recv_rows, p.n_recv_b,
-                                                       p.recv_buf, lhdr + 0, rhdr + 1, p.seq, p.done_ctr + 1); }
+                                                       p.recv_buf + (p.seq & 1) * n, lhdr + 0, rhdr + 1, p.seq, p.done_ctr + 1); }
       GTK_CK(cudaGetLastError());
       gtk_count_launch(ctx);
     }

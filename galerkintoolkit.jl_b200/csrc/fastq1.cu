@@ -76,6 +76,7 @@ struct FastPlan {
     int4* items = nullptr;
     int n = 0, cap = 0, z_begin = -1, z_end = -1, warps = 0;
     int top = -1, bot = -1, n_top = 0, n_bot = 0;      // fused exchange: layer bounds and counts of the top / bottom sweep items
+    int top_eff = -1, bot_eff = -1;                    // first layer of the top items / end layer of the bottom items as cut
     long long comm_key[4] = {-1, -1, -1, -1};          // entries sent / received per peer slot the PUSH / UNPACK items were cut for
     int n_push[2] = {0, 0}, n_unpack[2] = {0, 0};
   };
@@ -622,10 +623,33 @@ struct WCfg {
   static constexpr int WARP_D = CELL_D + 2 * ROWS + 3 * XL;   // doubles of shared memory per warp
 };
 
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
 // one work item of the warp-private affine sweep: the 16 x 2 patch at (i0, j0), node layers [kz0, kz1)
 template <bool TWOPASS>
 __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, const int j0, const int kz0, const int kz1,
-                                              double* __restrict__ OutW, double* __restrict__ CellW, double* __restrict__ XW, const int lane) {
+                                              double* __restrict__ OutW, double* __restrict__ CellW, double* __restrict__ XW, const int lane,
+                                              unsigned& flags_seen) {
   using C = WCfg;
   const int n1 = a.n1, n2 = a.n2;
   const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
@@ -654,6 +678,26 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
 #pragma unroll
   for (int o = 0; o < 18; ++o) pend[o] = 0.0;
   int4 ncn = make_int4(-1, -1, 0, -1);
+  if (a.comm.on == 2) {   // an item that will add received values: pull their lines towards the SM now (flag first: they must have landed)
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (s >= a.comm.n_peers) break;
+      const GtkCommPeerDev& q = a.comm.peer[s];
+      if (q.n_recv_nz + q.n_recv_b > 0 && kz0 <= q.B && q.B < kz1) {
+        if (!(flags_seen & (1u << s))) {
+          if (lane == 0) while (ld_acquire_sys_u64(q.local_ready) < q.seq) __nanosleep(100);
+          __syncwarp();
+          flags_seen |= 1u << s;
+        }
+        if (node_in_mesh) {
+          const int64_t ipn = (i0 + li) + s1 * (j0 + lj);
+          const int ro = __ldg(q.tbl + 4 * s2 + ipn), r0 = __ldg(q.tbl + 3 * s2 + ipn);
+          if (ro >= 0) { prefetch_l1(q.recv_buf + ro); prefetch_l1(q.recv_buf + ro + 8); }
+          if (r0 >= 0) { prefetch_l1(q.recv_buf + r0); prefetch_l1(q.recv_buf + r0 + 8); prefetch_l1(ncp + s2 * (q.B - 1)); }
+        }
+      }
+    }
+  }
   bool bulk_pending = false;
   // node coordinates: every lane copies up to 3 of the 72 nodes of a layer, component by component into a
   // structure-of-arrays slot XW[slot][k][node] (lanes then read consecutive doubles: no bank conflicts)
@@ -754,6 +798,67 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
       GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
 #undef GTK_AFF_CELL
     }
+    int snd_off = -1, snd_o0 = 0, snd_peer = 0;
+    if (emit && a.comm.on == 2) {
+      // ---- exchange fused into the copy-out: ghost rows leave from registers, received partial sums enter them ----
+      const int64_t ip = (i0 + li) + s1 * (j0 + lj);               // in-plane node index
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (s >= a.comm.n_peers) break;
+        const GtkCommPeerDev& q = a.comm.peer[s];
+        if (q.n_recv_nz + q.n_recv_b > 0 && L == q.B && !(a.comm.dbg_skip & 2)) {
+          if (!(flags_seen & (1u << s))) {
+            if (lane == 0) while (ld_acquire_sys_u64(q.local_ready) < q.seq) __nanosleep(100);   // the peer's values have landed
+            __syncwarp();
+            flags_seen |= 1u << s;
+          }
+          if (node_in_mesh) {
+            const int ro = __ldg(q.tbl + 4 * s2 + ip);               // this column: rows of its own layer (dz = 0) are added
+            if (ro >= 0) {
+              const double* src = q.recv_buf + ro;
+              int k = 0;
+#pragma unroll
+              for (int o = 9; o < 18; ++o) if ((mask >> o) & 1u) acc[o] += __ldcg(src + k++);
+            }
+            const int bo = __ldg(q.tbl + 5 * s2 + ip);
+            if (bo >= 0) accb += __ldcg(q.recv_buf + bo);
+            const int r0 = __ldg(q.tbl + 3 * s2 + ip);               // the halo column below: rows of THIS layer (dz = +1) are assigned
+            if (r0 >= 0) {
+              const int4 h = __ldg(reinterpret_cast<const int4*>(ncp + s2 * (L - 1)));
+              const long long cb0 = ((long long)(unsigned)h.y << 32) | (unsigned)h.x;
+              const unsigned m0 = (unsigned)h.z;
+              const double* src = q.recv_buf + r0;
+              int k = 0;
+#pragma unroll
+              for (int o = 18; o < 27; ++o) if ((m0 >> o) & 1u) a.nzval[cb0 + __popc(m0 & ((1u << o) - 1u))] = __ldcg(src + k++);
+            }
+          }
+        }
+        if (q.n_send_nz + q.n_send_b > 0 && (L == q.T || L == q.T - 1)) {
+          if (!(flags_seen & (4u << s))) {   // the owner must be done with this buffer (exchange seq - 2)
+            if (lane == 0) while (ld_acquire_sys_u64(q.local_ack) + 2 < q.seq) __nanosleep(100);
+            __syncwarp();
+            flags_seen |= 4u << s;
+          }
+          const int o0 = L == q.T ? 9 : 18;
+          snd_off = node_in_mesh ? __ldg(q.tbl + (L == q.T ? s2 : 0) + ip) : -1;
+          snd_o0 = o0; snd_peer = s;
+          // columns with all 9 ghost rows leave through the warp's shared-memory row below (coalesced remote stores);
+          // the others (mesh boundary) from registers, entry by entry
+          if (snd_off >= 0 && ((mask >> o0) & 0x1FFu) != 0x1FFu) {
+            double* dst = q.remote_buf + snd_off;
+            int k = 0;
+#pragma unroll
+            for (int o = 9; o < 27; ++o) if (o >= o0 && o < o0 + 9 && ((mask >> o) & 1u)) dst[k++] = acc[o];
+            snd_off = -1;
+          }
+          if (node_in_mesh && L == q.T) {
+            const int bo = __ldg(q.tbl + 2 * s2 + ip);
+            if (bo >= 0) q.remote_buf[bo] = accb;
+          }
+        }
+      }
+    }
     if (emit) {
       if (a.do_vector && col >= 0) a.b[col] = accb;
       if (a.do_matrix) {
@@ -789,6 +894,20 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
         fence_async_smem();
         __syncwarp();
         bulk_pending = false;
+        if (a.comm.on == 2 && __any_sync(0xFFFFFFFFu, snd_off >= 0)) {
+          // ghost rows of the 32 columns: 9 consecutive entries per column in the row just written; lanes walk them as
+          // (column, entry) pairs so that one store instruction covers 32 consecutive doubles of the peer's buffer
+          // whenever neighbouring columns' runs are adjacent (they are, except across mesh boundaries)
+          double* rbuf = a.comm.peer[snd_peer].remote_buf;
+#pragma unroll
+          for (int r = 0; r < 9; ++r) {
+            const int idx = lane + 32 * r;          // 0 .. 287 = 32 columns x 9 entries
+            const int c = idx / 9, k = idx - 9 * c; // column (lane id of its owner), entry
+            const int so = __shfl_sync(0xFFFFFFFFu, snd_off, c);
+            const int phc = __shfl_sync(0xFFFFFFFFu, ph, c);
+            if (so >= 0 && !(a.comm.dbg_skip & 1)) rbuf[so + k] = OutW[(c >> 4) * C::ROWS + phc + (c & 15) * 27 + snd_o0 + k];
+          }
+        }
         if (in_bulk) {
           if (my_ok) {
             const int head = (int)(cb & 1);
@@ -831,27 +950,6 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
   if (bulk_pending) bulk_wait_read();   // shared memory must outlive the bulk store reading it
 }
 
-
-__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long gtimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
 // PUSH / UNPACK work item of the fused exchange: item = {peer slot, chunk, kind (-1 push, -2 unpack), 0}.
 // Tickets are handed out in list order and a warp finishes its item before it draws the next, so every item with a lower
@@ -942,6 +1040,10 @@ __global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
   double* OutW = sm + w * C::WARP_D;                   // [2][ROWS]
   double* CellW = OutW + 2 * C::ROWS;                  // [NC][7]
   double* XW = CellW + C::CELL_D;                      // [3][PY][PX][3] ring of node-coordinate layers (cp.async, 2 ahead)
+  // fused exchange: the peers' flags this warp has already observed (bit s: data of peer s has landed, bit 2+s: peer s
+  // released the send buffer).  A system-scope acquire is expensive (it also invalidates the SM's L1): once per warp
+  // and kernel, not once per item.
+  unsigned flags_seen = 0;
   for (;;) {
     unsigned long long t = 0;
     if (lane == 0) t = atomicAdd(a.sched, 1ull) - a.sched_base;
@@ -949,17 +1051,33 @@ __global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
     if (t >= (unsigned long long)a.n_items) break;
     const int4 it = __ldg(a.items + t);
     if (it.z < 0) { comm_item(a, it, lane); continue; }
-    affine_w_item<TWOPASS>(a, it.x, it.y, it.z, it.w, OutW, CellW, XW, lane);
-    if (a.comm.on) {
+    affine_w_item<TWOPASS>(a, it.x, it.y, it.z, it.w, OutW, CellW, XW, lane, flags_seen);
+    if (a.comm.on == 1) {
       const bool top = it.z >= a.comm.top_layer, bot = it.w <= a.comm.bot_layer;
       if (top || bot) {   // a PUSH / UNPACK item of this launch reads what this item wrote: complete the bulk stores, publish
-        if (!(a.comm.on & 2)) {
         bulk_wait_all();
         fence_proxy_async_all();
-        }
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(a.comm.cnt + (top ? 0 : 1), 1ull);
+      }
+    } else if (a.comm.on == 2) {
+      const bool top = it.z >= a.comm.top_layer, bot = it.w <= a.comm.bot_layer;
+      if (top) {          // this item's ghost entries are in the peers' buffers: the LAST top item raises their `ready` flags
+        if (!(a.comm.dbg_skip & 4)) __threadfence_system();
+        __syncwarp();
+        if (lane == 0 && atomicAdd(a.comm.cnt + 0, 1ull) + 1 == a.comm.top_target) {
+          __threadfence_system();
+          for (int s = 0; s < a.comm.n_peers; ++s)
+            if (a.comm.peer[s].n_send_nz + a.comm.peer[s].n_send_b > 0) st_release_sys_u64(a.comm.peer[s].remote_ready, a.comm.peer[s].seq);
+        }
+      } else if (bot) {   // the received values of this item are consumed: the LAST bottom item acknowledges
+        __syncwarp();
+        if (lane == 0 && atomicAdd(a.comm.cnt + 1, 1ull) + 1 == a.comm.bot_target) {
+          __threadfence_system();
+          for (int s = 0; s < a.comm.n_peers; ++s)
+            if (a.comm.peer[s].n_recv_nz + a.comm.peer[s].n_recv_b > 0) st_release_sys_u64(a.comm.peer[s].remote_ack, a.comm.peer[s].seq);
+        }
       }
     }
     __syncwarp();
@@ -1156,7 +1274,7 @@ int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
 int32_t build_item_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::ItemPlan& ip, int z_begin, int z_end, int warps,
                         const GtkCommDev* comm = nullptr) {
   using C = WCfg;
-  const int top = comm ? comm->top_layer : -1, bot = comm ? comm->bot_layer : -1;
+  const int top = comm ? comm->top_layer : -1, bot = comm ? comm->bot_layer + 100000 * comm->on : -1;   // mode is part of the key
   long long ckey[4] = {-1, -1, -1, -1};
   if (comm) for (int i = 0; i < comm->n_peers; ++i) {
     ckey[2 * i] = comm->peer[i].n_send_nz + comm->peer[i].n_send_b;
@@ -1218,26 +1336,69 @@ int32_t build_item_plan(gtk_ctx* ctx, FastPlan* p, FastPlan::ItemPlan& ip, int z
   } else {
     // order: what the peers wait for, then what the received values are added to, then the PUSH items (by then the top
     // items are done or nearly), the bulk of the sweep from long to short segments, and the UNPACK items last
-    const int t0 = std::max(top, z_begin), b1 = std::min(bot, z_end);
+    const int t0 = std::max(top, z_begin), b1 = std::min(comm->bot_layer, z_end);
     std::vector<std::pair<int, int>> st, sb, sm;
     if (z_end > t0) st.emplace_back(t0, z_end);
     if (b1 > z_begin) sb.emplace_back(z_begin, b1);
-    ip.n_top = emit(st);
-    ip.n_bot = emit(sb);
-    const bool push_last = getenv("GTK_FUSED_PUSH_LAST") != nullptr;
-    if (!push_last) for (int i = 0; i < comm->n_peers; ++i) {
-      ip.n_push[i] = (int)((ckey[2 * i] + COMM_CHUNK - 1) / COMM_CHUNK);
-      for (int c = 0; c < ip.n_push[i]; ++c) items.push_back(make_int4(i, c, -1, 0));
+    int mid_lo = std::max(b1, z_begin), mid_hi = std::min(t0, z_end);
+    if (comm->on == 2) {
+      // exchange inside the copy-out: the exchanged layers ride at the end / start of ordinary-length segments instead of
+      // being 1-2 layer items of their own (each item pays a halo step); the classification in the kernel stays exact
+      // because `top_layer` / `bot_layer` handed to it are widened accordingly (see the launcher)
+      const char* e3 = getenv("GTK_FUSED_EDGE_SEG");
+      const int ext = e3 ? atoi(e3) : 0;   // measured: separate short items win (0.134 vs 0.155 ms at 2 x 128^3): the flags move earlier
+      if (!st.empty()) { st[0].first = std::max(mid_lo, st[0].first - ext); mid_hi = st[0].first; }
+      if (!sb.empty()) { sb[0].second = std::min(mid_hi, sb[0].second + ext); mid_lo = sb[0].second; }
     }
-    guided(std::max(b1, z_begin), std::min(t0, z_end), sm);
-    emit(sm);
-    if (push_last) for (int i = 0; i < comm->n_peers; ++i) {
-      ip.n_push[i] = (int)((ckey[2 * i] + COMM_CHUNK - 1) / COMM_CHUNK);
-      for (int c = 0; c < ip.n_push[i]; ++c) items.push_back(make_int4(i, c, -1, 0));
-    }
-    for (int i = 0; i < comm->n_peers; ++i) {
-      ip.n_unpack[i] = (int)((ckey[2 * i + 1] + COMM_CHUNK - 1) / COMM_CHUNK);
-      for (int c = 0; c < ip.n_unpack[i]; ++c) items.push_back(make_int4(i, c, -2, 0));
+    ip.top_eff = st.empty() ? top : st[0].first;
+    ip.bot_eff = sb.empty() ? comm->bot_layer : sb[0].second;
+    if (comm->on == 2) {
+      // exchange inside the copy-out: the items that feed a peer first (its data is on the way while the bulk of the
+      // sweep runs), the items that consume a peer's data last (it has long arrived)
+      // Neither group runs as a block: a burst of top items would have every warp wait on NVLink stores at once, a block of
+      // bottom items at the end is a latency-bound tail.  Top items are dealt 1 : 3 into the head of the list (the peer
+      // still has its data within the first tenth of the kernel), bottom items 1 : 3 from the middle on (the data has
+      // long arrived; a warp that is early spins on the flag).
+      std::vector<int4> all;
+      std::swap(all, items);
+      ip.n_top = emit(st);
+      std::vector<int4> tops;
+      std::swap(tops, items);
+      ip.n_bot = emit(sb);
+      std::vector<int4> bots;
+      std::swap(bots, items);
+      guided(mid_lo, mid_hi, sm);
+      emit(sm);
+      std::vector<int4> mids;
+      std::swap(mids, items);
+      const char* e2;
+      const int ratio = (e2 = getenv("GTK_FUSED_INTERLEAVE")) && atoi(e2) >= 0 ? atoi(e2) : 8;
+      const double bot_from = (e2 = getenv("GTK_FUSED_BOTTOM_FROM")) ? atof(e2) : 0.5;
+      size_t it = 0, ib = 0, im = 0;
+      const size_t bstart = (size_t)(bot_from * mids.size());
+      items = std::move(all);
+      while (it < tops.size() || im < mids.size() || ib < bots.size()) {
+        if (it < tops.size()) items.push_back(tops[it++]);
+        else if (im >= bstart && ib < bots.size()) items.push_back(bots[ib++]);
+        for (int r = 0; r < ratio && im < mids.size(); ++r) items.push_back(mids[im++]);
+        if (im >= mids.size()) {   // middle exhausted: whatever is left
+          while (it < tops.size()) items.push_back(tops[it++]);
+          while (ib < bots.size()) items.push_back(bots[ib++]);
+        }
+      }
+    } else {
+      ip.n_top = emit(st);
+      ip.n_bot = emit(sb);
+      for (int i = 0; i < comm->n_peers; ++i) {
+        ip.n_push[i] = (int)((ckey[2 * i] + COMM_CHUNK - 1) / COMM_CHUNK);
+        for (int c = 0; c < ip.n_push[i]; ++c) items.push_back(make_int4(i, c, -1, 0));
+      }
+      guided(std::max(b1, z_begin), std::min(t0, z_end), sm);
+      emit(sm);
+      for (int i = 0; i < comm->n_peers; ++i) {
+        ip.n_unpack[i] = (int)((ckey[2 * i + 1] + COMM_CHUNK - 1) / COMM_CHUNK);
+        for (int c = 0; c < ip.n_unpack[i]; ++c) items.push_back(make_int4(i, c, -2, 0));
+      }
     }
   }
   if ((int)items.size() > ip.cap) {
@@ -1281,7 +1442,9 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
       for (auto& b : p->comm_base) b = 0;
     }
     a.comm.cnt = p->comm_cnt;
+    if (a.comm.on == 2) { a.comm.top_layer = ip.top_eff; a.comm.bot_layer = ip.bot_eff; }
     a.comm.dbg = nullptr;
+    { const char* ds = getenv("GTK_FUSED_DBG_SKIP"); a.comm.dbg_skip = ds ? atoi(ds) : 0; }
     static const bool dbg = getenv("GTK_COMM_TIMING") != nullptr;
     if (dbg) {
       unsigned long long h[4];
@@ -1299,7 +1462,6 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
       a.comm.peer[i].unpack_target = (p->comm_base[4 + i] += (unsigned long long)ip.n_unpack[i]);
     }
     ctx->fuse_comm_done = true;
-    if (getenv("GTK_FUSED_NO_FENCE")) a.comm.on |= 2;
   }
   if (ip.n == 0) return GTK_OK;
   if (!p->sched) {
@@ -1390,6 +1552,114 @@ int32_t gtk_fastq1_min_layer(gtk_ctx* ctx, const int64_t* d_nz_pos, int64_t n, c
   GTK_CK(cudaStreamSynchronize(ctx->stream));
   if (h != 0x7FFFFFFF) { *layer = h; if (max_layer) *max_layer = h2[1]; }
   return GTK_OK;
+}
+
+namespace {
+// first buffer index of every column's run of ghost entries (entries are in CSC order: a column's entries are consecutive)
+__global__ void k_comm_run_starts(const int64_t* __restrict__ nz, int64_t n, const int64_t* __restrict__ colptr, int64_t n_cols,
+                                  const int32_t* __restrict__ rowval, const int32_t* __restrict__ dof_node, int64_t s2,
+                                  int row_layer, int32_t* __restrict__ off_lo, int32_t* __restrict__ off_hi, int* __restrict__ bad) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    auto col_of = [&](int64_t q) {
+      const int64_t p = q >= 0 ? q : ~q;
+      int64_t lo = 0, hi = n_cols;
+      while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (colptr[mid] <= p) lo = mid; else hi = mid; }
+      return lo;
+    };
+    const int64_t q = nz[i], p = q >= 0 ? q : ~q;
+    const int64_t col = col_of(q);
+    const int64_t rnode = dof_node[rowval[p] - 1], cnode = dof_node[col];
+    if (rnode / s2 != row_layer) *bad = 1;                      // every exchanged row lies in ONE node layer
+    const int cl = (int)(cnode / s2);
+    if (cl != row_layer && cl != row_layer - 1) *bad = 1;       // ... and its columns in that layer or the one below
+    if (i == 0 || col_of(nz[i - 1]) != col) (cl == row_layer ? off_hi : off_lo)[cnode % s2] = (int32_t)i;
+  }
+}
+__global__ void k_comm_row_starts(const int32_t* __restrict__ rows, int64_t nb, int64_t n_nz, const int32_t* __restrict__ dof_node,
+                                  int64_t s2, int row_layer, int32_t* __restrict__ boff, int* __restrict__ bad) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = dof_node[rows[i]];
+    if (node / s2 != row_layer) *bad = 1;
+    boff[node % s2] = (int32_t)(n_nz + i);
+  }
+}
+// the copy-out of the sweep will address the buffers as run start + rank of the neighbour offset inside the run: check that
+// this reproduces the plan entry by entry (positions, assign flags, monotone slots) and covers it completely
+__global__ void k_comm_verify(const int64_t* __restrict__ nz, int64_t n, const NodeCol* __restrict__ node_col, int64_t s2, int row_layer,
+                              const int32_t* __restrict__ off_lo, const int32_t* __restrict__ off_hi, int expect_assign_lo,
+                              unsigned long long* __restrict__ matched, int* __restrict__ bad) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < 2 * s2; t += (int64_t)gridDim.x * blockDim.x) {
+    const int hi = t >= s2;
+    const int64_t ip = hi ? t - s2 : t;
+    const int32_t off = (hi ? off_hi : off_lo)[ip];
+    if (off < 0) continue;
+    const NodeCol nc = node_col[ip + s2 * (row_layer - 1 + hi)];
+    if (nc.col < 0 || (nc.mask & 0x80000000u)) { *bad = 1; continue; }
+    const int o0 = hi ? 9 : 18;                                  // rows of the same layer (dz = 0) / of the layer above (dz = +1)
+    int k = 0;
+    for (int o = o0; o < o0 + 9; ++o)
+      if ((nc.mask >> o) & 1u) {
+        const int64_t expect = nc.cb + __popc(nc.mask & ((1u << o) - 1u));
+        const int64_t q = off + k < n ? nz[off + k] : -1;
+        const bool assign = q < 0;
+        if ((assign ? ~q : q) != expect) *bad = 1;
+        if (expect_assign_lo >= 0 && assign != (hi ? false : expect_assign_lo != 0)) *bad = 1;
+        ++k;
+      }
+    atomicAdd(matched, (unsigned long long)k);
+  }
+}
+}  // namespace
+
+// Tables for the exchange fused into the copy-out (GtkCommPeerDev::tbl), built and VERIFIED against the plan's index lists;
+// *ok = false (tables not usable) whenever the plan is not the structured one the kernel assumes.
+int32_t gtk_fastq1_comm_tables(gtk_ctx* ctx, const int64_t* send_nz, int64_t n_send_nz, const int32_t* send_rows, int64_t n_send_b,
+                               const int64_t* recv_nz, int64_t n_recv_nz, const int32_t* recv_rows, int64_t n_recv_b,
+                               int send_layer, int recv_layer, int32_t** tbl_out, bool* ok) {
+  *ok = false; *tbl_out = nullptr;
+  if (!gtk_fastq1_plan_ok(ctx)) return GTK_OK;
+  FastPlan* p = (FastPlan*)ctx->ms.plan;
+  const int64_t s2 = (int64_t)(p->n1 + 1) * (p->n2 + 1);
+  if ((n_send_nz && send_layer < 1) || (n_recv_nz && recv_layer < 1)) return GTK_OK;
+  if (n_send_nz + n_send_b >= 0x7FFFFFFFll || n_recv_nz + n_recv_b >= 0x7FFFFFFFll) return GTK_OK;
+  int32_t* tbl = nullptr;
+  int32_t rc = gtk_dev_alloc(ctx, (void**)&tbl, sizeof(int32_t) * 6 * (size_t)s2);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  GTK_CK(cudaMemsetAsync(tbl, 0xFF, sizeof(int32_t) * 6 * (size_t)s2, st));
+  unsigned long long* d_m = nullptr;
+  GTK_CK(gtk_cuda_malloc(ctx, &d_m, 2 * sizeof(unsigned long long) + sizeof(int)));
+  GTK_CK(cudaMemsetAsync(d_m, 0, 2 * sizeof(unsigned long long) + sizeof(int), st));
+  int* d_bad = (int*)(d_m + 2);
+  const MatSym& m = ctx->ms;
+  if (n_send_nz) {
+    k_comm_run_starts<<<grid_for(n_send_nz, 256), 256, 0, st>>>(send_nz, n_send_nz, m.colptr, m.n_cols, m.rowval, p->dof_node, s2, send_layer, tbl, tbl + s2, d_bad);
+    k_comm_verify<<<grid_for(2 * s2, 256), 256, 0, st>>>(send_nz, n_send_nz, p->node_col, s2, send_layer, tbl, tbl + s2, -1, d_m, d_bad);
+  }
+  if (n_send_b) k_comm_row_starts<<<grid_for(n_send_b, 256), 256, 0, st>>>(send_rows, n_send_b, n_send_nz, p->dof_node, s2, send_layer, tbl + 2 * s2, d_bad);
+  if (n_recv_nz) {
+    k_comm_run_starts<<<grid_for(n_recv_nz, 256), 256, 0, st>>>(recv_nz, n_recv_nz, m.colptr, m.n_cols, m.rowval, p->dof_node, s2, recv_layer, tbl + 3 * s2, tbl + 4 * s2, d_bad);
+    // the layer below the received rows must be the untouched halo (entries assigned), the rows' own layer touched (added)
+    k_comm_verify<<<grid_for(2 * s2, 256), 256, 0, st>>>(recv_nz, n_recv_nz, p->node_col, s2, recv_layer, tbl + 3 * s2, tbl + 4 * s2, 1, d_m + 1, d_bad);
+  }
+  if (n_recv_b) k_comm_row_starts<<<grid_for(n_recv_b, 256), 256, 0, st>>>(recv_rows, n_recv_b, n_recv_nz, p->dof_node, s2, recv_layer, tbl + 5 * s2, d_bad);
+  GTK_CK(cudaGetLastError());
+  struct { unsigned long long m[2]; int bad; } h;
+  GTK_CK(cudaMemcpyAsync(&h, d_m, 2 * sizeof(unsigned long long) + sizeof(int), cudaMemcpyDeviceToHost, st));
+  GTK_CK(cudaStreamSynchronize(st));
+  gtk_cuda_free(ctx, d_m);
+  if (h.bad || (int64_t)h.m[0] != n_send_nz || (int64_t)h.m[1] != n_recv_nz) {
+    gtk_dev_free(ctx, tbl, sizeof(int32_t) * 6 * (size_t)s2);
+    return GTK_OK;
+  }
+  *tbl_out = tbl;
+  *ok = true;
+  return GTK_OK;
+}
+
+int64_t gtk_fastq1_plane_nodes(const gtk_ctx* ctx) {
+  const FastPlan* p = (const FastPlan*)ctx->ms.plan;
+  return p ? (int64_t)(p->n1 + 1) * (p->n2 + 1) : 0;
 }
 
 int gtk_fastq1_affine_state(gtk_ctx* ctx) {

@@ -90,14 +90,20 @@ struct GtkCommPeerDev {
   const double* recv_buf; const unsigned long long* local_ready; unsigned long long* remote_ack;
   unsigned long long seq;                       // exchange number with this peer
   unsigned long long push_target, unpack_target;   // counter values at which the last PUSH / UNPACK item of this launch finishes
+  // mode 2 (exchange fused into the sweep's copy-out): per in-plane lattice node, where the ghost entries of its columns
+  // sit in the send / receive buffer (-1: none).  tbl = [snd_off T-1][snd_off T][snd_boff][rcv_off B-1][rcv_off B][rcv_boff],
+  // each s2 = (n1+1)(n2+1) ints; T = node layer of the rows sent to this peer, B = node layer of the rows received from it
+  const int32_t* tbl;
+  int T, B;
 };
 struct GtkCommDev {
-  int on;                                       // 0: plain sweep
+  int on;                                       // 0: plain sweep, 1: PUSH / UNPACK work items, 2: exchange inside the copy-out
   int n_peers;
   int top_layer, bot_layer;                     // sweep items with kz0 >= top_layer feed the PUSH, with kz1 <= bot_layer the UNPACK
   unsigned long long* cnt;                      // [0] top items done [1] bottom items done [2+p] PUSH items done [4+p] UNPACK items done
   unsigned long long top_target, bot_target;
   unsigned long long* dbg;                      // optional [8]: ns spent waiting (GTK_COMM_TIMING), else nullptr
+  int dbg_skip;                                 // experiments only: 1 skip the remote stores, 2 skip the receive-side work, 4 skip the fences
   GtkCommPeerDev peer[2];
 };
 
