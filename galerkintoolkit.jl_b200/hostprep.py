@@ -303,7 +303,8 @@ class Quadrature:
 def quadrature(D: int, simplex: bool, degree: int) -> Quadrature:
     """quadrature.jl:36-52.  n-cube: tensor Gauss-Legendre, n = ceil((d+1)/2)
     per direction, first index fastest, weight = prod (:78-106).  Simplex:
-    Duffy (:124-157) (triangles always; tets when no Strang table applies)."""
+    Duffy (:124-157) for triangles always and for tets of degree > 5; Strang-Fix tables for tets of degree 1-5
+    (:41-48, 500-635)."""
     if not simplex:
         n = int(np.ceil((degree + 1) / 2))
         x1, w1 = gauss_legendre_01(n)
@@ -315,6 +316,8 @@ def quadrature(D: int, simplex: bool, degree: int) -> Quadrature:
             w = w * w1[i]
         return Quadrature(np.ascontiguousarray(x), w)
     from . import _simplex_rules
+    if D == 3 and degree in _simplex_rules.STRANG_TET_DEGREES:      # quadrature.jl:41-48: Strang only in 3D, else Duffy
+        return Quadrature(*_simplex_rules.strang_tet_quadrature(degree))
     return Quadrature(*_simplex_rules.simplex_quadrature(D, degree))
 
 

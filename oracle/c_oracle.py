@@ -28,6 +28,11 @@ def lib():
     return _lib
 
 
+def set_vector_space(n_comp=1, lam=0.0, mu=0.0):
+    """state of the C oracle for vector-valued spaces / isotropic elasticity (form 3); n_comp = 1 restores the scalar path"""
+    lib().gto_set_vector_space(C.c_int(int(n_comp)), C.c_double(float(lam)), C.c_double(float(mu)))
+
+
 def assemble(form, coords, cell_nodes, cell_dofs, n_free, tab, alpha=1.0, f_const=1.0, with_vector=True,
              nthreads=1, nnz_cap=None, K_out=None):
     """→ (colptr, rowval, nzval, b, phase_seconds[count, loop, compress, vector]).  K_out: int64 [N_coo] array that

@@ -39,9 +39,21 @@ static double det3(const double a[3][3]) {
 }
 
 /* element matrix + vector of one cell; be[c*nld + r] column-major like Julia */
-static void cell_kernel(int D, const double* xyz, const int32_t* nodes, int nln, int nld, int nq,
+/* Vector-valued spaces (ncomp > 1): local dof = node*ncomp + comp (space.jl:1267-1271); the tabulations are those of the
+ * nls = nld/ncomp scalar shape functions.  form 3 = isotropic elasticity sigma(eps(u)):eps(v) with Lame parameters
+ * (lam, mu): u = s_a e_i, v = s_b e_j  ->  lam d_i s_a d_j s_b + mu d_j s_a d_i s_b + mu delta_ij grad s_a . grad s_b. */
+static int g_ncomp = 1;
+static double g_lam = 0.0, g_mu = 0.0;
+void gto_set_vector_space(int ncomp, double lam, double mu) { g_ncomp = ncomp < 1 ? 1 : ncomp; g_lam = lam; g_mu = mu; }
+
+static void cell_kernel(int D, const double* xyz, const int32_t* nodes, int nln, int nld_full, int nq,
                         const double* w, const double* N, const double* dN, const double* dM, int form,
                         double alpha, double fconst, double* be, double* bv, double* g /* nld*3 scratch */) {
+  const int ncomp = g_ncomp, nld = nld_full / ncomp;   /* nld: scalar shape functions from here on */
+  if (ncomp > 1) {
+    for (int i = 0; i < nld_full * nld_full; ++i) be[i] = 0.0;
+    if (bv) for (int i = 0; i < nld_full; ++i) bv[i] = 0.0;
+  }
   for (int i = 0; i < nld * nld; ++i) be[i] = 0.0;
   if (bv) for (int i = 0; i < nld; ++i) bv[i] = 0.0;
   for (int q = 0; q < nq; ++q) {
@@ -56,7 +68,7 @@ static void cell_kernel(int D, const double* xyz, const int32_t* nodes, int nln,
       double G[2][2];
       for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) G[i][j] = J[0][i] * J[0][j] + J[1][i] * J[1][j];
       dV = sqrt(det2(G)) * w[q];
-      if (form == 1) {
+      if (form == 1 || form == 3) {
         double a[2][2] = {{J[0][0], J[1][0]}, {J[0][1], J[1][1]}};  /* a = J' */
         double d = det2(a);
         for (int s = 0; s < nld; ++s) {
@@ -76,7 +88,7 @@ static void cell_kernel(int D, const double* xyz, const int32_t* nodes, int nln,
       for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
         G[i][j] = (J[0][i] * J[0][j] + J[1][i] * J[1][j]) + J[2][i] * J[2][j];
       dV = sqrt(det3(G)) * w[q];
-      if (form == 1) {
+      if (form == 1 || form == 3) {
         double a[3][3];
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) a[i][j] = J[j][i];
         double d = det3(a);
@@ -92,6 +104,30 @@ static void cell_kernel(int D, const double* xyz, const int32_t* nodes, int nln,
         }
 #undef A_
       }
+    }
+    if (ncomp > 1) {
+      const int nf = nld_full;
+      for (int c = 0; c < nf; ++c)
+        for (int r = 0; r < nf; ++r) {
+          const int a = r / ncomp, i = r % ncomp, b = c / ncomp, j = c % ncomp;
+          double t;
+          if (form == 3) {
+            t = g_lam * (g[a * 3 + i] * g[b * 3 + j]) + g_mu * (g[a * 3 + j] * g[b * 3 + i]);
+            if (i == j) {
+              double dt = g[a * 3] * g[b * 3];
+              for (int k = 1; k < D; ++k) dt += g[a * 3 + k] * g[b * 3 + k];
+              t = t + g_mu * dt;
+            }
+          } else if (form == 1) {
+            t = 0.0;
+            if (i == j) { t = g[a * 3] * g[b * 3]; for (int k = 1; k < D; ++k) t += g[a * 3 + k] * g[b * 3 + k]; }
+          } else {
+            t = i == j ? N[q * nld + a] * N[q * nld + b] : 0.0;
+          }
+          be[c * nf + r] += (alpha * t) * dV;
+        }
+      if (bv) for (int i = 0; i < nf; ++i) bv[i] += (1.0 * (fconst * N[q * nld + i / ncomp])) * dV;
+      continue;
     }
     for (int c = 0; c < nld; ++c)
       for (int r = 0; r < nld; ++r) {

@@ -236,6 +236,36 @@ def tensor_gauss(D, degree):
     return np.array(pts), np.array(wts)
 
 
+def strang_tet(degree):
+    """quadrature.jl:500-635, literally: strang_quadrature_<degree>(::UnitSimplex{3}) -> (points [n,3], weights [n]).
+    Used by `quadrature(geo, degree)` for tetrahedra of degree 1..5 (quadrature.jl:41-48)."""
+    if degree == 1:
+        a = 1.0 / 4.0; b = 1.0 / 6.0
+        x = [(a, a, a)]; w = [b]
+    elif degree == 2:
+        a = 0.5854101966249685; b = 0.1381966011250105; c = 1.0 / 24.0
+        x = [(b, b, b), (a, b, b), (b, a, b), (b, b, a)]; w = [c, c, c, c]
+    elif degree == 3:
+        a = 1.0 / 4.0; b = 1.0 / 6.0; c = 1.0 / 2.0; d = -2.0 / 15.0; e = 1.5 / 20.0
+        x = [(a, a, a), (b, b, b), (c, b, b), (b, c, b), (b, b, c)]; w = [d, e, e, e, e]
+    elif degree == 4:
+        a = 0.3994035761667992; b = 0.1005964238332008
+        c = (343.0 / 7500.0) / 6.0; d = (56.0 / 375.0) / 6.0
+        e = 1.0 / 4.0; f = 11.0 / 14.0; g = 1.0 / 14.0; h = (-148.0 / 1875.0) / 6.0
+        x = [(e, e, e), (f, g, g), (g, f, g), (g, g, f), (g, g, g), (a, a, b), (a, b, a), (a, b, b), (b, a, a), (b, a, b), (b, b, a)]
+        w = [h, c, c, c, c, d, d, d, d, d, d]
+    elif degree == 5:
+        a = 0.0673422422100983; b = 0.3108859192633005; c = 0.7217942490673264; d = 0.0927352503108912
+        e = 0.4544962958743506; f = 0.0455037041256494
+        p = 0.1126879257180162 / 6.0; q = 0.0734930431163619 / 6.0; r = 0.0425460207770812 / 6.0
+        x = [(a, b, b), (b, a, b), (b, b, a), (b, b, b), (c, d, d), (d, c, d), (d, d, c), (d, d, d),
+             (e, e, f), (e, f, e), (e, f, f), (f, e, e), (f, e, f), (f, f, e)]
+        w = [p, p, p, p, q, q, q, q, r, r, r, r, r, r]
+    else:
+        raise ValueError(degree)
+    return np.array(x, dtype=np.float64), np.array(w, dtype=np.float64)
+
+
 # ---------------------------------------------------------------------------
 # StaticArrays closed forms
 # ---------------------------------------------------------------------------

@@ -163,3 +163,41 @@ def test_oracle_reproduces_the_reference_plaplacian_golden():
         raise AssertionError("Newton did not converge")
     uhl2 = np.sqrt(O.assemble_scalar_field(O.SCALAR_L2SQ, X, CN, CD, td, x, xd))
     assert abs(uhl2 - 0.09133166701839236) < 1.0e-10, uhl2
+
+
+def test_strang_tet_rules_match_the_literal_tables_and_are_exact():
+    """quadrature.jl:41-48, 500-635: tetrahedra of degree 1..5 use the Strang-Fix rules (degree 4 = the 11-point rule of
+    BASELINE config 4, negative centroid weight).  The product builds them from their orbits, the oracle restates the
+    tables literally: equal bit for bit, in the reference's point order, and exact for all monomials up to the degree."""
+    import itertools
+    import math
+    import gtk_b200
+    H = gtk_b200.hostprep
+    for degree in range(1, 6):
+        q = H.quadrature(3, True, degree)
+        xo, wo = O.strang_tet(degree)
+        assert q.coordinates.tobytes() == xo.tobytes() and q.weights.tobytes() == wo.tobytes()
+        for i, j, k in itertools.product(range(degree + 1), repeat=3):
+            if i + j + k <= degree:
+                exact = math.factorial(i) * math.factorial(j) * math.factorial(k) / math.factorial(i + j + k + 3)
+                got = (wo * xo[:, 0] ** i * xo[:, 1] ** j * xo[:, 2] ** k).sum()
+                assert abs(got - exact) < 1e-15
+    assert H.quadrature(3, True, 4).weights.size == 11 and H.quadrature(3, True, 4).weights[0] < 0
+    assert H.quadrature(3, True, 6).weights.size == 64            # beyond the tables: Duffy
+    assert H.quadrature(2, True, 2).weights.size == 4             # triangles: always Duffy
+
+
+def test_c_oracle_elasticity_equals_the_numpy_oracle():
+    """the timed CPU baseline of config 4 (C port, vector-valued P2 tets, isotropic elasticity, Strang degree-4 rule)
+    reproduces the numpy oracle bit for bit"""
+    import c_oracle
+    mesh, V, tab = problem((3, 2, 2), order=2, bc=[1], n_comp=3, simplexify=True, warp=0.1)
+    cp, rv, nz = oracle_matrix(O.ELASTICITY, mesh, V, tab, alpha=1.0, lam=1.3, mu=0.7)
+    c_oracle.set_vector_space(3, 1.3, 0.7)
+    try:
+        out = c_oracle.assemble(3, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, tab_dict(tab), nthreads=3,
+                                nnz_cap=mesh.n_cells * 900)
+    finally:
+        c_oracle.set_vector_space(1)
+    assert tab.w.size == 11
+    assert np.array_equal(out[0], cp) and np.array_equal(out[1], rv) and out[2].tobytes() == nz.tobytes()
