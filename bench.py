@@ -17,6 +17,7 @@ index, assembly.jl:584-588), and both also report the FIRST assembly (symbolic +
   general_path    same mesh with non-affine cells (general sweep kernel)
   unstructured_path   same mesh with the cells in a random order (what a Gmsh mesh hits: element kernel + staged reduction)
   high_order      BASELINE config 3 (Q3 hexahedra 64^3, FP64 tensor cores)
+  elasticity      BASELINE config 4 element (P2 x 3 on tetrahedra, Strang degree-4 rule) at 64^3 x 6 tetrahedra
   config5         BASELINE config 5 at THIS GPU count: 512 x 512 x (512/N) cells per GPU, T_N, T_1 (rank 0 alone, device
                   resident) and the strong-scaling efficiency T_1 / (N T_N)
   cpu_baseline    the C restatement of the reference's CPU path (oracle/, "port") on this box
@@ -376,6 +377,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-high-order", action="store_true", help="skip the BASELINE config 3 (Q3 hex 64^3, DMMA path) entry")
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 (512^3 over the N GPUs) entry")
+    ap.add_argument("--no-elasticity", action="store_true", help="skip the BASELINE config 4 (P2 x 3 elasticity on tetrahedra) entry")
     ap.add_argument("--no-extras", action="store_true", help="headline only: no general/unstructured/high-order/config5/cpu entries")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -383,7 +385,7 @@ def main():
         run_reference(args)
         return
     if args.no_extras:
-        args.no_cpu_baseline = args.no_high_order = args.no_config5 = True
+        args.no_cpu_baseline = args.no_high_order = args.no_config5 = args.no_elasticity = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -681,6 +683,15 @@ def main():
                 line["high_order"]["cpu_baseline"] = cpu_baseline_high_order()
         except Exception as exc:   # reported, never hidden
             line["high_order"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if world == 1 and not args.no_elasticity:
+        # BASELINE config 4 element at the largest size whose host preparation stays within the bench's time budget
+        try:
+            import bench_elasticity
+            line["elasticity"] = bench_elasticity.run(64, steps=3, warmup=1, device=local_rank, check=True)
+            if not args.no_cpu_baseline:
+                line["elasticity"]["cpu_baseline"] = bench_elasticity.cpu_baseline()
+        except Exception as exc:   # reported, never hidden
+            line["elasticity"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_config5:
         try:
             c5 = run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream)

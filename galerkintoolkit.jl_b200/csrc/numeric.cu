@@ -10,6 +10,7 @@
 //       duplicates in reference push order (no atomics; bit-reproducible).
 //
 // The structured Q1 fast path lives in fastq1.cu and is tried first.
+#include <algorithm>
 #include "gtk_internal.h"
 
 int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
@@ -261,6 +262,127 @@ __global__ void __launch_bounds__(128) k_elem_vector(ElemArgs a) {
       acc += (a.alpha * (F[(size_t)(cl * nq + q) * ncomp + ic] * a.N[q * nls + ia])) * dV[cl * nq + q];
     const int64_t cell = cell0 + cl;
     a.out[cell * (int64_t)nld + i] = (cell >= a.act0 && cell < a.act1) ? acc : 0.0;
+  }
+}
+
+// K4: isotropic elasticity on 3D vector-valued elements with up to 10 scalar shape functions (P1 / P2
+// tetrahedra, 3 components: 30 x 30 element matrices) — BASELINE config 4.  One WARP per cell, no block barrier:
+//   A) lanes over (point, shape function): J_q = Σ x⊗∇̂M (local-node order), dV_q = sqrt(det JᵀJ) w_q, ∇s_a = Jᵀ\∇̂s_a
+//      (the closed forms of the generic kernel, so both kernels agree bit for bit) -> the warp's shared memory;
+//   B) lanes over the 55 node pairs a <= b: the 3 x 3 block  Σ_q (α (λ ∂_i s_a ∂_j s_b + μ ∂_j s_a ∂_i s_b + δ_ij μ ∇s_a·∇s_b)) dV_q
+//      in the reference's q order; the block of (b, a) is its transpose BITWISE (products commute), so it is mirrored;
+//   C) the 900 entries leave shared memory as one contiguous, coalesced 7.2 kB store into the staging array.
+// Compute is ~35 kFLOP per cell, the kernel is bound by the staging write (HBM).
+constexpr int K4_MAXS = 10, K4_MAXQ = 14;
+constexpr int K4_WARP_D = K4_MAXQ * K4_MAXS * 3 + K4_MAXQ * 12 + 9 * K4_MAXS * K4_MAXS;   // doubles of shared memory per warp
+__global__ void __launch_bounds__(256) k_elem_elasticity_w(ElemArgs a) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nq = a.nq, nls = a.nls, nld = 3 * nls, nld2 = nld * nld;
+  double* G = smem + (size_t)w * K4_WARP_D;    // [nq][nls][3]
+  double* JQ = G + K4_MAXQ * K4_MAXS * 3;      // [nq][12]: J (9), det Jᵀ, dV
+  double* Ke = JQ + K4_MAXQ * 12;              // [nld][nld] column-major
+  const int npair = nls * (nls + 1) / 2;
+  // this lane's node pairs (ra <= ca), fixed for the whole kernel: pair p = lane and lane + 32
+  int pra[2], pca[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = lane + 32 * h;
+    int ca = 0, off = 0;
+    while (off + ca + 1 <= p) { off += ca + 1; ++ca; }
+    pra[h] = p - off; pca[h] = ca;
+  }
+  for (int64_t cell = (int64_t)blockIdx.x * nwarp + w; cell < a.n_cells; cell += (int64_t)gridDim.x * nwarp) {
+    const bool active = cell >= a.act0 && cell < a.act1;
+    if (active) {
+      if (lane < nq) {   // geometry once per point
+        double J[3][3];
+        jacobian_at<3, 3>(a, cell, lane, J);
+        double JT[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { JT[i][j] = J[j][i]; JQ[lane * 12 + 3 * i + j] = J[i][j]; }
+        JQ[lane * 12 + 9] = 1.0 / det_mat<3>(JT);   // ONE division per point; the gradients multiply by it (1 ulp from the reference's per-component division)
+        JQ[lane * 12 + 10] = change_of_measure<3, 3>(J) * a.w[lane];
+      }
+      __syncwarp();
+      for (int t = lane; t < nq * nls; t += 32) {
+        const int q = t / nls;
+        double J[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) J[i][j] = JQ[q * 12 + 3 * i + j];
+        {
+          const double* b = a.dN + (size_t)t * 3;
+          double* g = G + (size_t)t * 3;
+          const double rd = JQ[q * 12 + 9];
+#define A_(i, j) J[(j)-1][(i)-1]
+          g[0] = ((A_(2, 2) * A_(3, 3) - A_(2, 3) * A_(3, 2)) * b[0] + (A_(1, 3) * A_(3, 2) - A_(1, 2) * A_(3, 3)) * b[1] +
+                  (A_(1, 2) * A_(2, 3) - A_(1, 3) * A_(2, 2)) * b[2]) * rd;
+          g[1] = ((A_(2, 3) * A_(3, 1) - A_(2, 1) * A_(3, 3)) * b[0] + (A_(1, 1) * A_(3, 3) - A_(1, 3) * A_(3, 1)) * b[1] +
+                  (A_(1, 3) * A_(2, 1) - A_(1, 1) * A_(2, 3)) * b[2]) * rd;
+          g[2] = ((A_(2, 1) * A_(3, 2) - A_(2, 2) * A_(3, 1)) * b[0] + (A_(1, 2) * A_(3, 1) - A_(1, 1) * A_(3, 2)) * b[1] +
+                  (A_(1, 1) * A_(2, 2) - A_(1, 2) * A_(2, 1)) * b[2]) * rd;
+#undef A_
+        }
+      }
+    }
+    __syncwarp();
+    if (active) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (lane + 32 * h >= npair) break;
+        const int ra = pra[h], ca = pca[h];
+        double acc[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) acc[i][j] = 0.0;
+        for (int q = 0; q < nq; ++q) {
+          const double* ga = G + ((size_t)q * nls + ra) * 3;
+          const double* gb = G + ((size_t)q * nls + ca) * 3;
+          const double dv = JQ[q * 12 + 10];
+          const double ga0 = ga[0], ga1 = ga[1], ga2 = ga[2], gb0 = gb[0], gb1 = gb[1], gb2 = gb[2];
+          // (α dV) folded into ∇s_a once per point: 33 FP64 instructions per point and pair instead of 55 (the kernel is
+          // FP64-issue bound); rounding differs from the reference's ((α t) dV) order by ~1e-16 relative
+          const double sdv = a.alpha * dv;
+          const double A[3] = {ga0 * sdv, ga1 * sdv, ga2 * sdv};
+          const double lA[3] = {a.lambda * A[0], a.lambda * A[1], a.lambda * A[2]};
+          const double mA[3] = {a.mu * A[0], a.mu * A[1], a.mu * A[2]};
+          const double gbb[3] = {gb0, gb1, gb2};
+          double dtm = mA[0] * gb0;
+          dtm = fma(mA[1], gb1, dtm);
+          dtm = fma(mA[2], gb2, dtm);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              acc[i][j] = fma(lA[i], gbb[j], acc[i][j]);
+              acc[i][j] = fma(mA[j], gbb[i], acc[i][j]);
+              if (i == j) acc[i][j] += dtm;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            Ke[(3 * ca + j) * nld + 3 * ra + i] = acc[i][j];      // row (ra, i), column (ca, j)
+            Ke[(3 * ra + i) * nld + 3 * ca + j] = acc[i][j];      // its mirror: row (ca, j), column (ra, i)
+          }
+      }
+    }
+    __syncwarp();
+    double* out = a.out + cell * (int64_t)nld2;
+    if ((nld2 & 1) == 0) {   // 16-byte stores (cell * nld2 is even whenever nld2 is)
+      double2* o2 = reinterpret_cast<double2*>(out);
+      const double2* k2 = reinterpret_cast<const double2*>(Ke);
+      for (int e = lane; e < nld2 / 2; e += 32) o2[e] = active ? k2[e] : make_double2(0.0, 0.0);
+    } else {
+      for (int e = lane; e < nld2; e += 32) out[e] = active ? Ke[e] : 0.0;
+    }
+    __syncwarp();
   }
 }
 
@@ -557,6 +679,19 @@ int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params
   if (ctx->n_cells == 0 || m.nnz == 0) return GTK_OK;
   a.out = ctx->KE;
   const int D = ctx->D;
+  if (form == GTK_FORM_ELASTICITY_ISO && D == 3 && ctx->dman == 3 && ctx->ncomp == 3 && ctx->nls <= K4_MAXS && ctx->nq <= K4_MAXQ &&
+      !getenv("GTK_DISABLE_K4")) {
+    const size_t smem = 8 * sizeof(double) * K4_WARP_D;
+    GTK_CK(cudaFuncSetAttribute(k_elem_elasticity_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem_elasticity_w, 256, smem));
+    const int64_t blocks = std::min<int64_t>((ctx->n_cells + 7) / 8, (int64_t)ctx->sm_count * (occ < 1 ? 1 : occ));
+    { GtkProf pr_(ctx, "k_elem_elasticity_w"); k_elem_elasticity_w<<<(int)blocks, 256, smem, ctx->stream>>>(a); }
+    GTK_CK(cudaGetLastError());
+    gtk_count_launch(ctx);
+    ctx->fast_path_last = 4;
+    return gtk_reduce_nz_launch(ctx);
+  }
   size_t per_cell = ((size_t)ctx->nq * ctx->nls * D + ctx->nq + (size_t)ctx->nq * (D + 2)) * sizeof(double);
   size_t smem;
   rc = pick_cb(ctx, per_cell, &a.cb, &smem);
