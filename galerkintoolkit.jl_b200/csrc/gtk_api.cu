@@ -1,6 +1,7 @@
 // C ABI of libgtkasm (include/gtk_assembly.h): argument checks, HBM residency of the inputs,
 // dispatch to symbolic.cu / numeric.cu / fastq1.cu / comm.cu.  No CPU compute path exists here:
 // every numeric entry point launches CUDA kernels or returns an error.
+#include <algorithm>
 #include <cstring>
 #include "gtk_internal.h"
 
@@ -273,6 +274,38 @@ int32_t gtk_matrix_pattern(gtk_ctx* ctx, int32_t* colptr, int32_t* rowval) {
   if (rowval && m.nnz) {
     GTK_CK(cudaMemcpyAsync(rowval, m.rowval, sizeof(int32_t) * (size_t)m.nnz, cudaMemcpyDeviceToHost, ctx->stream));
     GTK_CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return GTK_OK;
+}
+
+namespace {
+__global__ void k_widen_rows(const int32_t* __restrict__ src, int64_t n, int64_t* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+int32_t gtk_matrix_pattern_i64(gtk_ctx* ctx, int64_t* colptr, int64_t* rowval) {
+  if (!ctx) return GTK_ERR_INVALID;
+  MatSym& m = ctx->ms;
+  if (!m.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_pattern_i64: no symbolic result");
+  GTK_CK(cudaSetDevice(ctx->device));
+  if (colptr) {
+    GTK_CK(cudaMemcpyAsync(colptr, m.colptr, sizeof(int64_t) * (size_t)(m.n_cols + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    GTK_CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i <= m.n_cols; ++i) colptr[i] += 1;   // 1-based like Julia
+  }
+  if (rowval && m.nnz) {   // widened on the device, chunk by chunk (row ids stay Int32 in HBM)
+    const int64_t chunk = (int64_t)16 << 20;
+    int64_t* tmp = nullptr;
+    GTK_CK(gtk_cuda_malloc(ctx, &tmp, sizeof(int64_t) * (size_t)std::min(chunk, m.nnz)));
+    for (int64_t i0 = 0; i0 < m.nnz; i0 += chunk) {
+      const int64_t n = std::min(chunk, m.nnz - i0);
+      k_widen_rows<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(m.rowval + i0, n, tmp);
+      GTK_CK(cudaGetLastError());
+      GTK_CK(cudaMemcpyAsync(rowval + i0, tmp, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+      GTK_CK(cudaStreamSynchronize(ctx->stream));
+    }
+    gtk_cuda_free(ctx, tmp);
   }
   return GTK_OK;
 }

@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "gtk_comm_ghost_info", "gtk_set_profiling", "gtk_profile_count", "gtk_profile_get",
     "gtk_field_set_values", "gtk_field_set_values_device", "gtk_field_get_values", "gtk_field_axpy_free",
     "gtk_space_dof_coordinates", "gtk_scalar_assemble", "gtk_comm_build_exchange", "gtk_comm_connect_peer_memory",
-    "gtk_set_cartesian_q1_problem", "gtk_copy_device_array",
+    "gtk_set_cartesian_q1_problem", "gtk_copy_device_array", "gtk_matrix_pattern_i64",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library() -> C.CDLL:
         "gtk_comm_build_exchange": (i32, [vp, i64, vp]),
         "gtk_comm_connect_peer_memory": (i32, [vp]),
         "gtk_copy_device_array": (i32, [vp, i32, vp, i64]),
+        "gtk_matrix_pattern_i64": (i32, [vp, vp, vp]),
         "gtk_set_cartesian_q1_problem": (i32, [vp, vp, vp, i64, i64, i32, C.POINTER(i64), C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
@@ -297,6 +298,13 @@ class Engine:
         colptr = np.empty(self.n_cols + 1, dtype=np.int32)
         rowval = np.empty(self.nnz, dtype=np.int32) if want_rowval else None
         self._ck(self.lib.gtk_matrix_pattern(self.h, _ptr(colptr), _ptr(rowval)))
+        return colptr, rowval
+
+    def matrix_pattern_i64(self, want_rowval: bool = True):
+        """colptr / rowval as Int64 (assembly_options index_type = Int64; no 2^31 limit on nnz)"""
+        colptr = np.empty(self.n_cols + 1, dtype=np.int64)
+        rowval = np.empty(self.nnz, dtype=np.int64) if want_rowval else None
+        self._ck(self.lib.gtk_matrix_pattern_i64(self.h, _ptr(colptr), _ptr(rowval)))
         return colptr, rowval
 
     def matrix_numeric(self, form: int, out: Optional[np.ndarray] = None, **params) -> np.ndarray:

@@ -524,7 +524,7 @@ def _upload_field(eng: _eng.Engine, params: dict) -> dict:
 
 
 def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, parameters=(),
-                    free_or_dirichlet=(FREE, FREE), engine: Optional[_eng.Engine] = None):
+                    free_or_dirichlet=(FREE, FREE), engine: Optional[_eng.Engine] = None, assembly_options=None):
     """GT.assemble_matrix(a, T, U, V; reuse, free_or_dirichlet) (problems.jl:319-350).
     Rows enumerate V (test), columns U (trial); only U is V is supported on the GPU path."""
     if T not in (float, np.float64):
@@ -537,9 +537,15 @@ def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, 
     if meas.domain.kind == "boundary" and form != _eng.FORM_MASS:
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "on a boundary measure only ∫_Γ u v dΓ (Robin term) is assembled by the GPU engine")
     params["alpha"] = params.get("alpha", 1.0) * scale
+    # assembly_options (assembly.jl:434-445): index_type Int32 (default) | Int64; eltype / matrix_type other than
+    # Float64 / SparseMatrixCSC are not something this engine produces: explicit error
+    opts = dict(assembly_options or {})
+    index_type = opts.pop("index_type", np.int32)
+    if opts.pop("eltype", np.float64) not in (float, np.float64) or opts:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, f"assembly_options {assembly_options} are not supported by the GPU engine")
     eng = _setup_engine(V, meas, engine)
     eng.matrix_symbolic(*free_or_dirichlet)
-    colptr, rowval = eng.matrix_pattern()
+    colptr, rowval = eng.matrix_pattern_i64() if index_type in (int, np.int64) else eng.matrix_pattern()
     nzval = eng.matrix_numeric(form, **_upload_field(eng, params))
     A = SparseMatrixCSC(eng.n_rows, eng.n_cols, colptr, rowval, nzval)
     if reuse or parameters:

@@ -148,6 +148,11 @@ int32_t gtk_matrix_symbolic(gtk_ctx* ctx, int32_t rows_free_or_dirichlet,
                             int32_t cols_free_or_dirichlet, int64_t* nnz_out);
 /* Copy the pattern out: colptr[n_cols+1], rowval[nnz], 1-based Int32. */
 int32_t gtk_matrix_pattern(gtk_ctx* ctx, int32_t* colptr, int32_t* rowval);
+/* The same pattern with 64-bit indices: `assembly_options = (; index_type = Int64)` of the reference
+ * (assembly.jl:434-445: counter(...; index_type, matrix_type = SparseMatrixCSC{eltype,index_type})), i.e. the colptr / rowval
+ * of a SparseMatrixCSC{Float64,Int64}.  Also the way out for patterns with nnz >= 2^31, which the Int32 variant refuses
+ * (GTK_ERR_TOO_LARGE) — e.g. BASELINE config 5 assembled on one GPU (3.59e9 nonzeros). */
+int32_t gtk_matrix_pattern_i64(gtk_ctx* ctx, int64_t* colptr, int64_t* rowval);
 /* Numeric assembly = generated loop (compiler.jl:1826-1923) + contribute!
  * (assembly.jl:189-208) + compress/compress! (assembly.jl:571-588).  Re-callable:
  * second and later calls are GT.update_matrix! (problems.jl:352-361). */

@@ -98,8 +98,8 @@ function GT.counter(::GPUAssembly, ::Type{T}, dofs_i; index_type = Int32, eltype
 end
 function GT.counter(::GPUAssembly, ::Type{T}, dofs_i, dofs_j; eltype = T, index_type = Int32,
                     matrix_type = SparseMatrixCSC{eltype,index_type}) where T
-    (eltype === Float64 && index_type === Int32 && matrix_type === SparseMatrixCSC{Float64,Int32}) ||
-        error("libgtkasm produces SparseMatrixCSC{Float64,Int32}; assembly_options $((; eltype, index_type, matrix_type)) are not supported")
+    (eltype === Float64 && index_type in (Int32, Int64) && matrix_type === SparseMatrixCSC{Float64,index_type}) ||
+        error("libgtkasm produces SparseMatrixCSC{Float64,Int32 | Int64}; assembly_options $((; eltype, index_type, matrix_type)) are not supported")
     GPUMatrixCounter{eltype,index_type}(length(dofs_i), length(dofs_j))
 end
 
@@ -140,14 +140,18 @@ function GT.compress(a::GPUMatrixAllocation{T,Ti}; reuse = Val(false)) where {T,
     e = a.engine
     e === nothing && error("compress before any integral was assembled")
     (; nrows, ncols) = a.counter
-    colptr = Vector{Int32}(undef, ncols + 1)
-    rowval = Vector{Int32}(undef, a.nnz)
+    colptr = Vector{Ti}(undef, ncols + 1)
+    rowval = Vector{Ti}(undef, a.nnz)
     nzval = Vector{Float64}(undef, a.nnz)
     GC.@preserve colptr rowval nzval begin
-        check(e, ccall((:gtk_matrix_pattern, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), e.handle, colptr, rowval))
+        if Ti === Int32
+            check(e, ccall((:gtk_matrix_pattern, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), e.handle, colptr, rowval))
+        else    # assembly_options = (; index_type = Int64) (assembly.jl:434-445); also lifts the 2^31 limit on nnz
+            check(e, ccall((:gtk_matrix_pattern_i64, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), e.handle, colptr, rowval))
+        end
         check(e, ccall((:gtk_copy_nzval, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.handle, nzval))
     end
-    A = SparseMatrixCSC{Float64,Int32}(nrows, ncols, colptr, rowval, nzval)
+    A = SparseMatrixCSC{Float64,Ti}(nrows, ncols, colptr, rowval, nzval)
     GT.val_parameter(reuse) ? (A, e) : A
 end
 

@@ -95,3 +95,20 @@ def test_assembly_tests_jl_sizes():
     Ad = GT.assemble_matrix(a, np.float64, V, V, free_or_dirichlet=(GT.FREE, GT.DIRICHLET))
     assert (Ad.m, Ad.n) == (V.num_free_dofs(), V.num_dirichlet_dofs())                    # :68
     assert np.isclose(b.sum() + bd.sum(), 1.0, rtol=0, atol=1e-14)
+
+
+def test_assembly_options_index_type_int64():
+    """test/assembly_tests.jl:120-135: `assembly_options = (; matrix = (; index_type = Int))` gives the same matrix with
+    64-bit colptr / rowval; unsupported options raise instead of being ignored."""
+    mesh = GT.cartesian_mesh((0, 1, 0, 1), (5, 4))
+    Ω = GT.interior(mesh)
+    V = GT.lagrange_space(Ω, 2, dirichlet_boundary=GT.boundary(mesh))
+    dΩ = GT.measure(Ω, 4)
+    a = lambda u, v: GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dΩ)
+    A32 = GT.assemble_matrix(a, np.float64, V, V)
+    A64 = GT.assemble_matrix(a, np.float64, V, V, assembly_options=dict(index_type=np.int64))
+    assert A32.colptr.dtype == np.int32 and A64.colptr.dtype == np.int64 and A64.rowval.dtype == np.int64
+    assert np.array_equal(A32.colptr, A64.colptr) and np.array_equal(A32.rowval, A64.rowval)
+    assert A32.nzval.tobytes() == A64.nzval.tobytes()
+    with pytest.raises(GT.UnsupportedFormError):
+        GT.assemble_matrix(a, np.float64, V, V, assembly_options=dict(eltype=np.float32))
