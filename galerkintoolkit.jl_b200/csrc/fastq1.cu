@@ -1657,6 +1657,8 @@ int32_t gtk_fastq1_comm_tables(gtk_ctx* ctx, const int64_t* send_nz, int64_t n_s
   return GTK_OK;
 }
 
+bool gtk_fastq1_tabulation_ok(const gtk_ctx* ctx) { return tabulation_is_q1_gauss2(ctx); }
+
 int64_t gtk_fastq1_plane_nodes(const gtk_ctx* ctx) {
   const FastPlan* p = (const FastPlan*)ctx->ms.plan;
   return p ? (int64_t)(p->n1 + 1) * (p->n2 + 1) : 0;

@@ -12,7 +12,9 @@
 // The structured Q1 fast path lives in fastq1.cu and is tried first.
 #include <algorithm>
 #include "gtk_internal.h"
+#include "q1hex_math.cuh"
 
+bool gtk_fastq1_tabulation_ok(const gtk_ctx* ctx);   // fastq1.cu: the tabulation is the Q1 / 2x2x2 Gauss one
 int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
                        const gtk_form_params* pv, bool* handled);
 int32_t gtk_elemgemm_try(gtk_ctx* ctx, int form, const gtk_form_params* p, bool* handled);   // elemgemm.cu
@@ -262,6 +264,50 @@ __global__ void __launch_bounds__(128) k_elem_vector(ElemArgs a) {
       acc += (a.alpha * (F[(size_t)(cl * nq + q) * ncomp + ic] * a.N[q * nls + ia])) * dV[cl * nq + q];
     const int64_t cell = cell0 + cl;
     a.out[cell * (int64_t)nld + i] = (cell >= a.act0 && cell < a.act1) ? acc : 0.0;
+  }
+}
+
+// Q1 hexahedra on an UNSTRUCTURED mesh (any cell order / node numbering: what a Gmsh mesh gives): one thread per cell
+// computes the sum-factorised element matrix (36 unique entries, q1hex_math.cuh — the arithmetic of the structured sweep
+// kernel) and the element vector and writes them to the staging arrays in one pass: replaces k_cell_metric +
+// k_elem_laplace_dmma<1,2> + k_elem_vector (three kernels that each gather the cell's coordinates again).
+__global__ void __launch_bounds__(128) k_q1hex_cells(const double* __restrict__ xyz, const int32_t* __restrict__ cell_nodes, int64_t n_cells,
+                                                    int64_t act0, int64_t act1, double alpha, double fscale, int do_matrix, int do_vector,
+                                                    double* __restrict__ KE, double* __restrict__ BE) {
+  for (int64_t cell = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cell < n_cells; cell += (int64_t)gridDim.x * blockDim.x) {
+    const bool active = cell >= act0 && cell < act1;
+    double Ke[36], be[8];
+#pragma unroll
+    for (int e = 0; e < 36; ++e) Ke[e] = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) be[e] = 0.0;
+    if (active) {
+      const int4 n0 = __ldg(reinterpret_cast<const int4*>(cell_nodes + cell * 8));
+      const int4 n1 = __ldg(reinterpret_cast<const int4*>(cell_nodes + cell * 8) + 1);
+      const int nd[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+      double X[8][3];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const double* x = xyz + (size_t)(nd[v] - 1) * 3;
+        X[v][0] = __ldg(x); X[v][1] = __ldg(x + 1); X[v][2] = __ldg(x + 2);
+      }
+      q1hex::Cell<double> g;
+      q1hex::geometry<double>(X, g);
+      if (do_matrix) q1hex::laplace_ke<double>(g, alpha, Ke);
+      if (do_vector) q1hex::source_be<double>(g, fscale, be);
+    }
+    if (do_matrix) {
+      double2* out = reinterpret_cast<double2*>(KE + cell * 64);   // e = c * 8 + r, symmetric
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) out[(c * 8 + r) / 2] = make_double2(Ke[q1hex::sym(r, c)], Ke[q1hex::sym(r + 1, c)]);
+    }
+    if (do_vector) {
+      double2* ob = reinterpret_cast<double2*>(BE + cell * 8);
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) ob[i / 2] = make_double2(be[i], be[i + 1]);
+    }
   }
 }
 
@@ -650,8 +696,52 @@ int32_t gtk_reduce_nz_launch(gtk_ctx* ctx) {
   return GTK_OK;
 }
 
+int32_t gtk_reduce_rows_launch(gtk_ctx* ctx, int accumulate);
+
+// Q1 hexahedra / 2x2x2 Gauss / LAPLACE (+ SOURCE_CONST) without lattice structure: the fused cell kernel, then the
+// fixed-order reductions.  mform / vform == 0: that half is not wanted.
+static int32_t q1cells_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform, const gtk_form_params* pv, bool* handled) {
+  *handled = false;
+  if (getenv("GTK_DISABLE_Q1CELLS") || getenv("GTK_DISABLE_FASTPATH") || ctx->D != 3 || ctx->dman != 3 || ctx->nld != 8 || ctx->nln != 8 || ctx->ncomp != 1) return GTK_OK;
+  if (mform && (mform != GTK_FORM_LAPLACE || (pm && (pm->coef_nodal || pm->coef_qp)))) return GTK_OK;
+  if (vform && (vform != GTK_FORM_SOURCE_CONST || (pv && pv->accumulate))) return GTK_OK;
+  if (!mform && !vform) return GTK_OK;
+  if (!gtk_fastq1_tabulation_ok(ctx)) return GTK_OK;
+  MatSym& m = ctx->ms;
+  VecSym& v = ctx->vs;
+  int32_t rc;
+  if (mform) {
+    if (!m.generic_plan && (rc = gtk_symbolic_generic_plan(ctx))) return rc;
+    if ((rc = ensure(ctx, &ctx->KE, &ctx->KE_cap, (size_t)m.n_full))) return rc;
+    if ((rc = ensure(ctx, &ctx->nzval, &ctx->nzval_cap, (size_t)m.nnz))) return rc;
+  }
+  if (vform) {
+    if (!v.generic_plan && (rc = gtk_symbolic_vector_generic_plan(ctx))) return rc;
+    if ((rc = ensure(ctx, &ctx->BE, &ctx->BE_cap, (size_t)v.n_full))) return rc;
+    if ((rc = ensure(ctx, &ctx->bvec, &ctx->bvec_cap, (size_t)v.n_rows))) return rc;
+    GTK_CK(cudaMemsetAsync(ctx->bvec, 0, sizeof(double) * (size_t)(v.n_rows > 0 ? v.n_rows : 1), ctx->stream));
+  }
+  *handled = true;
+  ctx->fast_path_last = 5;
+  if (ctx->n_cells == 0) return GTK_OK;
+  const int64_t a0 = ctx->act_count < 0 ? 0 : ctx->act_first, a1 = ctx->act_count < 0 ? ctx->n_cells : ctx->act_first + ctx->act_count;
+  { GtkProf pr_(ctx, "k_q1hex_cells");
+    k_q1hex_cells<<<grid_for(ctx->n_cells, 128, ctx->sm_count), 128, 0, ctx->stream>>>(ctx->xyz, ctx->cell_nodes, ctx->n_cells, a0, a1, pm ? pm->alpha : 1.0,
+                                                                                  pv ? pv->alpha * pv->f_const[0] : 0.0, mform != 0, vform != 0, ctx->KE, ctx->BE); }
+  GTK_CK(cudaGetLastError());
+  gtk_count_launch(ctx);
+  if (mform && m.nnz && (rc = gtk_reduce_nz_launch(ctx))) return rc;
+  if (vform && v.n_urows && (rc = gtk_reduce_rows_launch(ctx, 0))) return rc;
+  return GTK_OK;
+}
+
 int32_t gtk_numeric_matrix_generic(gtk_ctx* ctx, int form, const gtk_form_params* p) {
   MatSym& m = ctx->ms;
+  {
+    bool handled = false;
+    int32_t rc = q1cells_try(ctx, form, p, 0, nullptr, &handled);
+    if (rc || handled) return rc;
+  }
   if (!m.generic_plan) {   // the structured symbolic phase deferred the sort-based plan
     int32_t rc = gtk_symbolic_generic_plan(ctx);
     if (rc) return rc;
@@ -789,7 +879,12 @@ int32_t gtk_numeric_vector_generic(gtk_ctx* ctx, int form, const gtk_form_params
 #undef LAUNCH_VF
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
-  { GtkProf pr_(ctx, "k_reduce_rows"); k_reduce_rows<<<grid_for(v.n_urows, 256, ctx->sm_count), 256, 0, st>>>(ctx->BE, v.perm, v.rowptr, v.urow,
+  return gtk_reduce_rows_launch(ctx, accumulate);
+}
+
+int32_t gtk_reduce_rows_launch(gtk_ctx* ctx, int accumulate) {
+  VecSym& v = ctx->vs;
+  { GtkProf pr_(ctx, "k_reduce_rows"); k_reduce_rows<<<grid_for(v.n_urows, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->BE, v.perm, v.rowptr, v.urow,
                                                                          v.n_urows, ctx->bvec, accumulate); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
@@ -837,6 +932,8 @@ int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm
   int32_t rc = gtk_fastq1_try(ctx, mform, pm, vform, pv, &handled);
   if (rc) return rc;
   if (handled) return GTK_OK;
+  rc = q1cells_try(ctx, mform, pm, vform, pv, &handled);   // one cell pass for matrix + vector on unstructured Q1 hexahedra
+  if (rc || handled) return rc;
   rc = gtk_numeric_matrix_generic(ctx, mform, pm);
   if (rc) return rc;
   return gtk_numeric_vector_generic(ctx, vform, pv);

@@ -29,6 +29,7 @@ def test_dmma_matches_oracle_and_generic(cells, order, simplexify, bc, warp):
     colptr, rowval, nzval = oracle_matrix(O.LAPLACE, mesh, V, tab, alpha=0.75)
     eng = make_engine(mesh, V, tab)
     os.environ["GTK_DISABLE_FASTPATH"] = "1"      # keep the structured Q1 sweep out of the way
+    os.environ["GTK_DISABLE_Q1CELLS"] = "1"       # ... and the fused Q1 cell kernel of unstructured meshes (tests/test_gpu_unstructured.py)
     try:
         assert eng.matrix_symbolic() == rowval.size
         cp, rv = eng.matrix_pattern()
@@ -50,6 +51,7 @@ def test_dmma_matches_oracle_and_generic(cells, order, simplexify, bc, warp):
         os.environ.pop("GTK_DISABLE_DMMA", None)
         os.environ.pop("GTK_ENABLE_DIRECT_WRITE", None)
         os.environ.pop("GTK_DISABLE_FASTPATH", None)
+        os.environ.pop("GTK_DISABLE_Q1CELLS", None)
         eng.close()
 
 

@@ -129,7 +129,7 @@ def test_fast_path_declines_what_it_does_not_cover():
     cp, rv = eng.matrix_pattern()
     assert np.array_equal(cp, colptr) and np.array_equal(rv, rowval)
     nz = eng.matrix_numeric(E.FORM_LAPLACE)
-    assert eng.info(5) == 3             # not the sweep kernels (1, 2): the element-GEMM path for unstructured meshes
+    assert eng.info(5) == 5             # not the sweep kernels (1, 2): the fused Q1 cell kernel of unstructured meshes
     assert_values_close(nz, nzval)      # other summation order than the oracle's cell order: still within 1e-12
     # mass on the structured mesh: fast path declines (LAPLACE only)
     eng2 = make_engine(mesh, V, tab)
