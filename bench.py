@@ -15,6 +15,7 @@ index, assembly.jl:584-588), and both also report the FIRST assembly (symbolic +
   reassembly / first_assembly   {device_ms, e2e_ms, value, e2e_value} of update_matrix! / of assemble_matrix
   roofline        algorithmic bytes of the step / device time, against MEASURED_PEAKS.json hbm_gbs
   general_path    same mesh with non-affine cells (general sweep kernel)
+  mixed_path      same mesh with ONE displaced node (affine kernel + general kernel on the affected tiles)
   unstructured_path   same mesh with the cells in a random order (what a Gmsh mesh hits: element kernel + staged reduction)
   high_order      BASELINE config 3 (Q3 hexahedra 64^3, FP64 tensor cores)
   elasticity      BASELINE config 4 element (P2 x 3 on tetrahedra, Strang degree-4 rule) at 64^3 x 6 tetrahedra
@@ -582,7 +583,7 @@ def main():
                          "context — mesh/space/tabulation host->device, symbolic, numeric, colptr/rowval/nzval/b device->host"}
 
     # ---- the same step on a NON-affine mesh and on an UNSTRUCTURED (cell-permuted) mesh (N = 1) ----
-    general = unstructured = None
+    general = unstructured = mixed = None
     if world == 1:
         rng = np.random.default_rng(0)
         warped = mesh.node_coordinates.copy()
@@ -596,6 +597,15 @@ def main():
         general = {"mesh": "same topology, interior nodes displaced by 0.2 h U(-1,1) (trilinear, non-affine cells)",
                    "ms_per_step": gms, "value": nnz_total / (gms * 1e-3), "unit": UNIT, "fast_path": eng.info(5),
                    "roofline_frac": alg / (gms * 1e-3) / 1e9 / peak}
+        # ONE displaced node: the affine kernel everywhere + the general kernel on the tiles around the 8 non-affine cells
+        one = mesh.node_coordinates.copy()
+        one[int(np.flatnonzero(inner)[inner.sum() // 2])] += 0.2 / n
+        eng.update_coordinates(one)
+        for _ in range(3):
+            step()
+        mms = timed_loop(torch, stream, step, gsteps)
+        mixed = {"mesh": "config 2 with ONE interior node displaced by 0.2 h (8 non-affine cells)", "ms_per_step": mms,
+                 "value": nnz_total / (mms * 1e-3), "unit": UNIT, "fast_path": eng.info(5), "roofline_frac": alg / (mms * 1e-3) / 1e9 / peak}
         eng.update_coordinates(mesh.node_coordinates)
         if not args.no_extras:
             try:
@@ -666,7 +676,7 @@ def main():
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": alg, "bytes_per_nnz": alg / max(nnz_local, 1), "kernel": dominant,
                          "kernels_ms": kernels, "basis": "whole step device time (all kernels of the step)"},
-            "clocks": clocks, "general_path": general, "unstructured_path": unstructured,
+            "clocks": clocks, "general_path": general, "mixed_path": mixed, "unstructured_path": unstructured,
         }
     eng.close()
     eng = None

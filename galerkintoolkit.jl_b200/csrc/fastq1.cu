@@ -62,7 +62,11 @@ struct FastPlan {
   bool structured = false;           // topology verified (plan_detect)
   bool ok = false;                   // tables built: the sweep kernels may run
   bool tried = false;
-  int affine_state = -1;             // -1 unknown (coordinates changed), 0 some cell is not affine, 1 every cell is exactly affine
+  int affine_state = -1;             // -1 unknown (coordinates changed), 0 general kernel, 1 every cell is exactly affine,
+                                     // 2 mixed: a few non-affine cells — affine kernel everywhere, then the general kernel on the
+                                     // tiles that hold a node of a non-affine cell (they recompute those columns completely)
+  uint8_t* mixed_map = nullptr;      // [gx * gy * nseg] tiles of the general sweep to run in mixed mode
+  size_t mixed_n = 0;
   int* d_flag = nullptr;
   // launch plans (per kernel variant): z-segment length and per-tile skip flags
   struct TilePlan {
@@ -541,25 +545,43 @@ __global__ void __launch_bounds__(Cfg<BX, BY>::NT, MINB) k_q1hex_sweep(SweepArgs
 // ------------------------------------------------------------------------------------------------
 // exactly-affine meshes
 // ------------------------------------------------------------------------------------------------
-__global__ void k_classify_affine(const double* __restrict__ xyz, int n1, int n2, int k0, int k1, int* nonaffine) {
+// mix (optional): tile map of the general sweep kernel (bx x by footprints, z-segments of `seg` node layers from layer 0):
+// every tile that holds one of the 8 nodes of a non-affine cell is marked — the columns of those nodes are the only ones the
+// affine formulas get wrong; nonaffine[1] counts the tiles marked
+__global__ void k_classify_affine(const double* __restrict__ xyz, int n1, int n2, int k0, int k1, int* nonaffine,
+                                  int* __restrict__ mix, int bx, int by, int seg, int gx, int gy) {
   const int64_t nc = (int64_t)n1 * n2 * (k1 - k0);
   const int64_t s1 = n1 + 1, s2 = (int64_t)(n1 + 1) * (n2 + 1);
   bool bad = false;
   for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(c % n1), j = (int)((c / n1) % n2), k = k0 + (int)(c / ((int64_t)n1 * n2));
     const double* x = xyz + 3 * (i + s1 * j + s2 * k);
+    bool cbad = false;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       const double X0 = x[d], X1 = x[3 + d], X2 = x[3 * s1 + d], X3 = x[3 * s1 + 3 + d];
       const double X4 = x[3 * s2 + d], X5 = x[3 * s2 + 3 + d], X6 = x[3 * (s2 + s1) + d], X7 = x[3 * (s2 + s1) + 3 + d];
       const double a = X1 - X0, b = X2 - X0, c2 = X4 - X0;
       // the edge vectors exactly as q1hex::geometry forms them
-      if (!(X3 - X2 == a && X5 - X4 == a && X7 - X6 == a)) bad = true;
-      if (!(X3 - X1 == b && X6 - X4 == b && X7 - X5 == b)) bad = true;
-      if (!(X5 - X1 == c2 && X6 - X2 == c2 && X7 - X3 == c2)) bad = true;
+      if (!(X3 - X2 == a && X5 - X4 == a && X7 - X6 == a)) cbad = true;
+      if (!(X3 - X1 == b && X6 - X4 == b && X7 - X5 == b)) cbad = true;
+      if (!(X5 - X1 == c2 && X6 - X2 == c2 && X7 - X3 == c2)) cbad = true;
+    }
+    if (cbad) {
+      bad = true;
+      if (mix)
+        for (int v = 0; v < 8; ++v) {
+          const int t = (i + (v & 1)) / bx + gx * ((j + ((v >> 1) & 1)) / by + gy * ((k + (v >> 2)) / seg));
+          if (atomicExch(mix + t, 1) == 0) atomicAdd(nonaffine + 1, 1);
+        }
     }
   }
-  if (bad) *nonaffine = 1;
+  if (bad) nonaffine[0] = 1;
+}
+
+__global__ void k_and_tiles(const uint8_t* __restrict__ active, const int* __restrict__ mix, int64_t n, uint8_t* __restrict__ out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    out[t] = active[t] && mix[t];
 }
 
 // Contribution of one affine cell to the entry (row = local node I, column = local node J), added to acc.
@@ -1111,6 +1133,7 @@ void plan_free(gtk_ctx* ctx, FastPlan* p) {
   if (p->col_mask) gtk_dev_free(ctx, p->col_mask, sizeof(uint32_t) * (size_t)(ctx->n_free > 0 ? ctx->n_free : 1));
   if (p->node_col) gtk_dev_free(ctx, p->node_col, sizeof(NodeCol) * (size_t)p->n_nodes);
   if (p->d_flag) gtk_cuda_free(ctx, p->d_flag);
+  if (p->mixed_map) gtk_dev_free(ctx, p->mixed_map, p->mixed_n);
   for (auto& tp : p->tp_affine) if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
   for (auto& tp : p->tp_sweep) if (tp.active) gtk_dev_free(ctx, tp.active, tp.n);
   for (auto& ip : p->ip_affine) if (ip.items) gtk_dev_free(ctx, ip.items, sizeof(int4) * (size_t)ip.cap);
@@ -1245,7 +1268,7 @@ void layer_range(const gtk_ctx* ctx, int layers, int* z_begin, int* z_end) {
 }
 
 template <int BX, int BY, int MINB>
-int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
+int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0, const uint8_t* only_tiles = nullptr) {
   using C = Cfg<BX, BY>;
   SweepArgs a = a0;
   const int gx = (p->n1 + 1 + BX - 1) / BX, gy = (p->n2 + 1 + BY - 1) / BY;
@@ -1259,7 +1282,7 @@ int32_t launch_sweep(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   int32_t rc = build_tile_plan(ctx, p, tp, BX * 100 + BY, BX, BY, gx, gy, seg, a.z_begin, a.z_end);
   if (rc) return rc;
   a.seg_len = tp.seg;
-  a.tile_active = tp.active;
+  a.tile_active = only_tiles ? only_tiles : tp.active;
   GTK_CK(cudaFuncSetAttribute(k_q1hex_sweep<BX, BY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   dim3 grid(gx, gy, tp.nseg);
   { GtkProf pr_(ctx, "k_q1hex_sweep"); k_q1hex_sweep<BX, BY, MINB><<<grid, C::NT, C::SMEM, ctx->stream>>>(a); }
@@ -1481,19 +1504,47 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
 
 // exact per-cell affinity of the numeric-active cell layers; one small kernel + a 4-byte read-back per
 // coordinate upload (cached in the plan until gtk_update_coordinates / gtk_set_mesh)
+constexpr int MIX_BX = 16, MIX_BY = 6;   // footprint of the default general sweep variant (launch_sweep<16, 6, 2>)
+inline int sweep_seg() { const char* ns = getenv("GTK_SWEEP_SEG"); return ns && atoi(ns) > 0 ? atoi(ns) : 12; }
+
 int32_t classify_affine(gtk_ctx* ctx, FastPlan* p, const double* xyz, int k0, int k1) {
   if (!p->d_flag) GTK_CK(gtk_cuda_malloc(ctx, &p->d_flag, 2 * sizeof(int)));
-  GTK_CK(cudaMemsetAsync(p->d_flag, 0, sizeof(int), ctx->stream));
+  GTK_CK(cudaMemsetAsync(p->d_flag, 0, 2 * sizeof(int), ctx->stream));
   const int64_t nc = (int64_t)p->n1 * p->n2 * (k1 - k0);
+  // tile map of the default general sweep over ALL node layers (launch mode 0)
+  const int gx = (p->n1 + 1 + MIX_BX - 1) / MIX_BX, gy = (p->n2 + 1 + MIX_BY - 1) / MIX_BY, seg = sweep_seg();
+  const int nseg = (p->n3 + 1 + seg - 1) / seg;
+  const size_t nt = (size_t)gx * gy * nseg;
+  const char* var = getenv("GTK_SWEEP_VARIANT");
+  const bool mixed_possible = (!var || atoi(var) == 1) && !getenv("GTK_DISABLE_MIXED") && ctx->act_count < 0;
+  int* mix = nullptr;
+  if (mixed_possible) {
+    GTK_CK(gtk_cuda_malloc(ctx, &mix, sizeof(int) * nt));
+    GTK_CK(cudaMemsetAsync(mix, 0, sizeof(int) * nt, ctx->stream));
+  }
   if (nc > 0) {
-    k_classify_affine<<<grid_for(nc, 256), 256, 0, ctx->stream>>>(xyz, p->n1, p->n2, k0, k1, p->d_flag);
+    k_classify_affine<<<grid_for(nc, 256), 256, 0, ctx->stream>>>(xyz, p->n1, p->n2, k0, k1, p->d_flag, mix, MIX_BX, MIX_BY, seg, gx, gy);
     GTK_CK(cudaGetLastError());
     gtk_count_launch(ctx);
   }
-  int flag = 1;
-  GTK_CK(cudaMemcpyAsync(&flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  int flag[2] = {1, 0};
+  GTK_CK(cudaMemcpyAsync(flag, p->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GTK_CK(cudaStreamSynchronize(ctx->stream));
-  p->affine_state = flag ? 0 : 1;
+  p->affine_state = flag[0] ? 0 : 1;
+  // a few distorted cells in an otherwise affine mesh: both kernels, the general one on the marked tiles only.  Worth it
+  // while the general kernel (3x the time per tile) runs on less than ~a quarter of the tiles.
+  if (flag[0] && mixed_possible && (double)flag[1] <= 0.25 * (double)nt) {
+    FastPlan::TilePlan& tp = p->tp_sweep[0];
+    int32_t rc = build_tile_plan(ctx, p, tp, MIX_BX * 100 + MIX_BY, MIX_BX, MIX_BY, gx, gy, seg, 0, p->n3 + 1);
+    if (rc) { gtk_cuda_free(ctx, mix); return rc; }
+    if (p->mixed_map && p->mixed_n != nt) { gtk_dev_free(ctx, p->mixed_map, p->mixed_n); p->mixed_map = nullptr; }
+    if (!p->mixed_map) { if ((rc = gtk_dev_alloc(ctx, (void**)&p->mixed_map, nt))) { gtk_cuda_free(ctx, mix); return rc; } p->mixed_n = nt; }
+    k_and_tiles<<<grid_for((int64_t)nt, 256), 256, 0, ctx->stream>>>(tp.active, mix, (int64_t)nt, p->mixed_map);
+    GTK_CK(cudaGetLastError());
+    GTK_CK(cudaStreamSynchronize(ctx->stream));
+    p->affine_state = 2;
+  }
+  if (mix) gtk_cuda_free(ctx, mix);
   return GTK_OK;
 }
 
@@ -1818,7 +1869,9 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   if (p->affine_state < 0 && !getenv("GTK_DISABLE_AFFINE")) {
     if ((rc = classify_affine(ctx, p, a.xyz, a.kact0, a.kact1))) return rc;
   }
-  if (p->affine_state == 1 && !getenv("GTK_DISABLE_AFFINE")) {
+  // mixed mode only for a plain full launch: layer-range launches (multi-GPU overlap) fall back to the general kernel
+  const bool mixed = p->affine_state == 2 && ctx->seg_mode == 0 && !ctx->fuse_comm_want && ctx->act_count < 0 && !getenv("GTK_DISABLE_AFFINE");
+  if ((p->affine_state == 1 || mixed) && !getenv("GTK_DISABLE_AFFINE")) {
     const char* var = getenv("GTK_AFFINE_VARIANT");
     switch (var ? atoi(var) : 0) {
       case 6: rc = launch_affine_w<3, 168, false>(ctx, p, a); break;
@@ -1840,6 +1893,10 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
     }
     if (rc) return rc;
     ctx->fast_path_last = 2;
+    if (mixed) {   // the columns around the non-affine cells, recomputed completely by the general kernel
+      if ((rc = launch_sweep<MIX_BX, MIX_BY, 2>(ctx, p, a, p->mixed_map))) return rc;
+      ctx->fast_path_last = 6;
+    }
     *handled = true;
     return GTK_OK;
   }
