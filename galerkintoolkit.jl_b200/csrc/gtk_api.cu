@@ -103,6 +103,7 @@ int32_t gtk_destroy(gtk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   gtk_comm_release(ctx);
+  gtk_parts_release(ctx);
   gtk_release_all_matrices(ctx);
   gtk_vecsym_release(ctx);
   for (auto& sl : ctx->slots) { gtk_cuda_free(ctx, sl.nzval); sl.nzval = nullptr; }
@@ -141,6 +142,7 @@ int32_t gtk_set_mesh(gtk_ctx* ctx, int32_t D, int64_t n_nodes, const double* xyz
   if (ctx->cell_dofs) { gtk_dev_free(ctx, ctx->cell_dofs, sz.cell_dofs * sizeof(int32_t)); ctx->cell_dofs = nullptr; sz.cell_dofs = 0; }
   ctx->nld = 0; ctx->nls = 0; ctx->ncomp = 1; ctx->nq = 0;
   gtk_field_release(ctx);
+  gtk_parts_release(ctx);
   int32_t rc = upload(ctx, &ctx->xyz, &sz.xyz, xyz, (size_t)n_nodes * D);
   if (rc) return rc;
   rc = upload(ctx, &ctx->cell_nodes, &sz.cell_nodes, cell_nodes, (size_t)n_cells * n_lnodes);
@@ -154,7 +156,7 @@ int32_t gtk_set_manifold_dim(gtk_ctx* ctx, int32_t d) {
   if (!ctx) return GTK_ERR_INVALID;
   if (!ctx->D) GTK_FAIL(GTK_ERR_STATE, "gtk_set_manifold_dim: set the mesh first");
   if (d < 1 || d > ctx->D) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_manifold_dim: 1 <= d <= D");
-  if (d != ctx->dman) ctx->nq = 0;   // gradients were tabulated with another number of components
+  if (d != ctx->dman) { ctx->nq = 0; gtk_parts_release(ctx); }   // gradients were tabulated with another number of components
   ctx->dman = d;
   return GTK_OK;
 }
@@ -213,6 +215,7 @@ int32_t gtk_set_space(gtk_ctx* ctx, int32_t n_ldofs, int32_t n_comp, const int32
   ctx->nld = n_ldofs; ctx->ncomp = n_comp; ctx->nls = n_ldofs / n_comp;
   ctx->n_free = n_free; ctx->n_diri = n_dirichlet;
   gtk_field_release(ctx);   // the discrete field belongs to the previous space
+  if (ctx->parts) { gtk_parts_release(ctx); ctx->nq = 0; }
   int32_t rc = upload(ctx, &ctx->cell_dofs, &sz.cell_dofs, cell_dofs, (size_t)ctx->n_cells * n_ldofs);
   if (rc) return rc;
   gtk_release_all_matrices(ctx); gtk_vecsym_release(ctx);
@@ -226,6 +229,7 @@ int32_t gtk_set_tabulation(gtk_ctx* ctx, int32_t n_q, const double* w, const dou
   if (n_q < 1 || !w || !N || !dN || !M || !dM) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_tabulation: bad arguments");
   if (!ctx->D || !ctx->nls) GTK_FAIL(GTK_ERR_STATE, "gtk_set_tabulation: set mesh and space first");
   GTK_CK(cudaSetDevice(ctx->device));
+  gtk_parts_release(ctx);   // a plain tabulation replaces the part tables of gtk_set_parts
   auto& sz = ctx->sz;
   ctx->nq = n_q;
   const int D = ctx->dman;   // reference-space dimension of the tabulated gradients

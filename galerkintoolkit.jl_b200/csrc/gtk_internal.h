@@ -182,6 +182,7 @@ struct gtk_ctx {
   void* comm = nullptr;   // ncclComm_t
   int rank = 0, n_ranks = 1;
   void* ghost = nullptr;  // GhostPlan*
+  void* parts = nullptr;  // PartsState* (blocks.cu): parts of a product space / skeleton integral; replaces N / dN
 };
 
 // ---- helpers implemented in gtk_api.cu ----
@@ -244,6 +245,9 @@ int32_t gtk_upload_coefficient(gtk_ctx* ctx, int form, const gtk_form_params* p,
 int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
                               const gtk_form_params* pv);
 int32_t gtk_scalar_impl(gtk_ctx* ctx, int kind, const gtk_form_params* p, double* out);
+
+// ---- blocks.cu ----
+void gtk_parts_release(gtk_ctx* ctx);       // mesh / space / manifold dimension changed: the part tables are void
 
 // ---- field.cu ----
 int32_t gtk_field_ensure(gtk_ctx* ctx);     // allocates (zero-filled) u_free / u_diri for the current space if missing

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include "gtk_internal.h"
 #include "q1hex_math.cuh"
+#include "elem_math.cuh"
 
 bool gtk_fastq1_tabulation_ok(const gtk_ctx* ctx);   // fastq1.cu: the tabulation is the Q1 / 2x2x2 Gauss one
 int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
@@ -57,71 +58,13 @@ __device__ __forceinline__ double field_value(const ElemArgs& a, int dof) {   //
   return dof > 0 ? a.u_free[dof - 1] : a.u_diri[-dof - 1];
 }
 
-template <int D>
-__device__ __forceinline__ double det_mat(const double (&a)[D][D]) {
-  if constexpr (D == 1) return a[0][0];
-  if constexpr (D == 2) return a[0][0] * a[1][1] - a[0][1] * a[1][0];
-  if constexpr (D == 3) {
-    // StaticArrays: x0 . (x1 × x2) over columns
-    double c0 = a[1][1] * a[2][2] - a[2][1] * a[1][2];
-    double c1 = a[2][1] * a[0][2] - a[0][1] * a[2][2];
-    double c2 = a[0][1] * a[1][2] - a[1][1] * a[0][2];
-    return a[0][0] * c0 + a[1][0] * c1 + a[2][0] * c2;
-  }
-}
-
-// sqrt(det(JᵀJ))  (quadrature.jl:4-6); J is D x d (d < D: boundary faces embedded in D dimensions)
-template <int D, int d>
-__device__ __forceinline__ double change_of_measure(const double (&J)[D][d]) {
-  double G[d][d];
-#pragma unroll
-  for (int i = 0; i < d; ++i)
-#pragma unroll
-    for (int j = 0; j < d; ++j) {
-      double s = J[0][i] * J[0][j];
-#pragma unroll
-      for (int k = 1; k < D; ++k) s += J[k][i] * J[k][j];
-      G[i][j] = s;
-    }
-  return sqrt(det_mat<d>(G));
-}
-
-// g = a \ b with a = Jᵀ  (StaticArrays closed forms; accessors.jl:1365-1368)
-template <int D>
-__device__ __forceinline__ void solve_JT(const double (&J)[D][D], double d, const double* b, double* g) {
-  if constexpr (D == 1) { g[0] = b[0] / J[0][0]; }
-  if constexpr (D == 2) {
-    // a[i][j] = J[j][i]
-    g[0] = (J[1][1] * b[0] - J[1][0] * b[1]) / d;
-    g[1] = (J[0][0] * b[1] - J[0][1] * b[0]) / d;
-  }
-  if constexpr (D == 3) {
-#define A_(i, j) J[(j)-1][(i)-1]
-    g[0] = ((A_(2, 2) * A_(3, 3) - A_(2, 3) * A_(3, 2)) * b[0] + (A_(1, 3) * A_(3, 2) - A_(1, 2) * A_(3, 3)) * b[1] +
-            (A_(1, 2) * A_(2, 3) - A_(1, 3) * A_(2, 2)) * b[2]) / d;
-    g[1] = ((A_(2, 3) * A_(3, 1) - A_(2, 1) * A_(3, 3)) * b[0] + (A_(1, 1) * A_(3, 3) - A_(1, 3) * A_(3, 1)) * b[1] +
-            (A_(1, 3) * A_(2, 1) - A_(1, 1) * A_(2, 3)) * b[2]) / d;
-    g[2] = ((A_(2, 1) * A_(3, 2) - A_(2, 2) * A_(3, 1)) * b[0] + (A_(1, 2) * A_(3, 1) - A_(1, 1) * A_(3, 2)) * b[1] +
-            (A_(1, 1) * A_(2, 2) - A_(1, 2) * A_(2, 1)) * b[2]) / d;
-#undef A_
-  }
-}
+using gtkmath::det_mat;
+using gtkmath::change_of_measure;
+using gtkmath::solve_JT;
 
 template <int D, int d>
 __device__ __forceinline__ void jacobian_at(const ElemArgs& a, int64_t cell, int q, double (&J)[D][d]) {
-#pragma unroll
-  for (int i = 0; i < D; ++i)
-#pragma unroll
-    for (int j = 0; j < d; ++j) J[i][j] = 0.0;
-  const int32_t* nodes = a.cell_nodes + cell * a.nln;
-  const double* dMq = a.dM + (size_t)q * a.nln * d;
-  for (int n = 0; n < a.nln; ++n) {   // sequential in local-node order (accessors.jl:941-948)
-    const double* x = a.xyz + (size_t)(nodes[n] - 1) * D;
-#pragma unroll
-    for (int i = 0; i < D; ++i)
-#pragma unroll
-      for (int j = 0; j < d; ++j) J[i][j] += x[i] * dMq[n * d + j];
-  }
+  gtkmath::jacobian_from<D, d>(a.xyz, a.cell_nodes + cell * a.nln, a.nln, a.dM + (size_t)q * a.nln * d, J);
 }
 
 template <int D, int d>
@@ -609,6 +552,8 @@ int32_t ensure(gtk_ctx* ctx, double** p, size_t* cap, size_t n) {
 int32_t fill_args(gtk_ctx* ctx, ElemArgs& a, int form, const gtk_form_params* p) {
   if (!ctx->xyz || !ctx->cell_dofs || !ctx->w || ctx->nq <= 0)
     GTK_FAIL(GTK_ERR_STATE, "mesh, space and tabulation must be set first (in this order; a new mesh or element invalidates the tabulation)");
+  if (ctx->parts)
+    GTK_FAIL(GTK_ERR_STATE, "this context holds the parts of a product space / skeleton integral (gtk_set_parts): use gtk_matrix_numeric_blocks / gtk_vector_assemble_blocks");
   a.xyz = ctx->xyz; a.cell_nodes = ctx->cell_nodes; a.n_cells = ctx->n_cells;
   a.nln = ctx->nln; a.nls = ctx->nls; a.ncomp = ctx->ncomp; a.nld = ctx->nld; a.nq = ctx->nq;
   a.w = ctx->w; a.N = ctx->N; a.dN = ctx->dN; a.M = ctx->M; a.dM = ctx->dM;
@@ -892,6 +837,7 @@ int32_t gtk_reduce_rows_launch(gtk_ctx* ctx, int accumulate) {
 }
 
 int32_t gtk_numeric_matrix_impl(gtk_ctx* ctx, int form, const gtk_form_params* p) {
+  if (ctx->parts) GTK_FAIL(GTK_ERR_STATE, "the context holds the parts of a product space / skeleton integral: use gtk_matrix_numeric_blocks / gtk_vector_assemble_blocks");
   if (!ctx->ms.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_symbolic must be called before gtk_matrix_numeric");
   ctx->launches_last = 0;
   ctx->fast_path_last = 0;
@@ -904,6 +850,7 @@ int32_t gtk_numeric_matrix_impl(gtk_ctx* ctx, int form, const gtk_form_params* p
 }
 
 int32_t gtk_numeric_vector_impl(gtk_ctx* ctx, int form, const gtk_form_params* p) {
+  if (ctx->parts) GTK_FAIL(GTK_ERR_STATE, "the context holds the parts of a product space / skeleton integral: use gtk_matrix_numeric_blocks / gtk_vector_assemble_blocks");
   if (!ctx->vs.ready) {
     int32_t rc = gtk_symbolic_vector_impl(ctx, GTK_FREE);
     if (rc) return rc;
@@ -920,6 +867,7 @@ int32_t gtk_numeric_vector_impl(gtk_ctx* ctx, int form, const gtk_form_params* p
 
 int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
                               const gtk_form_params* pv) {
+  if (ctx->parts) GTK_FAIL(GTK_ERR_STATE, "the context holds the parts of a product space / skeleton integral: use gtk_matrix_numeric_blocks / gtk_vector_assemble_blocks");
   if (!ctx->ms.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_symbolic must be called first");
   if (!ctx->vs.ready) {
     int32_t rc = gtk_symbolic_vector_impl(ctx, ctx->ms.rows_fd);

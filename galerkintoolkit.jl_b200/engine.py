@@ -36,7 +36,11 @@ ABI_SYMBOLS = [
     "gtk_field_set_values", "gtk_field_set_values_device", "gtk_field_get_values", "gtk_field_axpy_free",
     "gtk_space_dof_coordinates", "gtk_scalar_assemble", "gtk_comm_build_exchange", "gtk_comm_connect_peer_memory",
     "gtk_set_cartesian_q1_problem", "gtk_copy_device_array", "gtk_matrix_pattern_i64",
+    "gtk_set_parts", "gtk_matrix_numeric_blocks", "gtk_matrix_numeric_blocks_device",
+    "gtk_vector_assemble_blocks", "gtk_vector_assemble_blocks_device",
 ]
+BLOCK_ZERO, BLOCK_MASS, BLOCK_LAPLACE, BLOCK_VALU_DIVV, BLOCK_DIVU_VALV = 0, 1, 2, 3, 4
+MAX_PARTS = 8
 
 
 class GtkError(RuntimeError):
@@ -54,6 +58,18 @@ class FormParams(C.Structure):
                 ("f_const", C.c_double * 3), ("f_nodal", C.c_void_p), ("f_qp", C.c_void_p),
                 ("coef_nodal", C.c_void_p), ("coef_qp", C.c_void_p), ("accumulate", C.c_int32),
                 ("exponent", C.c_double)]
+
+
+class Part(C.Structure):       # gtk_part
+    _fields_ = [("n_lshape", C.c_int32), ("n_comp", C.c_int32), ("side", C.c_int32), ("N", C.c_void_p), ("dN", C.c_void_p)]
+
+
+class Block(C.Structure):      # gtk_block
+    _fields_ = [("part_u", C.c_int32), ("part_v", C.c_int32), ("form", C.c_int32), ("alpha", C.c_double)]
+
+
+class VBlock(C.Structure):     # gtk_vblock
+    _fields_ = [("part", C.c_int32), ("alpha", C.c_double), ("f_const", C.c_double * 3)]
 
 
 _lib = None
@@ -120,6 +136,11 @@ def load_library() -> C.CDLL:
         "gtk_copy_device_array": (i32, [vp, i32, vp, i64]),
         "gtk_matrix_pattern_i64": (i32, [vp, vp, vp]),
         "gtk_set_cartesian_q1_problem": (i32, [vp, vp, vp, i64, i64, i32, C.POINTER(i64), C.POINTER(i64)]),
+        "gtk_set_parts": (i32, [vp, i32, vp, vp, vp, i32, C.POINTER(Part), i32, i32, vp]),
+        "gtk_matrix_numeric_blocks": (i32, [vp, i32, C.POINTER(Block), vp]),
+        "gtk_matrix_numeric_blocks_device": (i32, [vp, i32, C.POINTER(Block)]),
+        "gtk_vector_assemble_blocks": (i32, [vp, i32, C.POINTER(VBlock), i32, vp]),
+        "gtk_vector_assemble_blocks_device": (i32, [vp, i32, C.POINTER(VBlock), i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -260,6 +281,59 @@ class Engine:
     def set_tabulation(self, w, N, dN, M, dM):
         w, N, dN, M, dM = map(_f64, (w, N, dN, M, dM))
         self._ck(self.lib.gtk_set_tabulation(self.h, w.shape[0], _ptr(w), _ptr(N), _ptr(dN), _ptr(M), _ptr(dM)))
+
+    def set_parts(self, w, M, dM, parts, n_sides: int = 1, face_var=None):
+        """parts: list of dicts(n_comp, side, N [n_var, n_q, n_lshape], dN [n_var, n_q, n_lshape, D] or None) in the order of
+        the super dof table handed to set_space (product spaces / skeleton integrals)"""
+        w, M, dM = map(_f64, (w, M, dM))
+        arr = (Part * len(parts))()
+        keep = []
+        n_var = None
+        for k, pd in enumerate(parts):
+            N = _f64(pd["N"])
+            if N.ndim == 2:
+                N = N[None]
+            dN = None if pd.get("dN") is None else _f64(pd["dN"])
+            if dN is not None and dN.ndim == 3:
+                dN = dN[None]
+            keep += [N, dN]
+            if n_var is None:
+                n_var = N.shape[0]
+            if N.shape[0] != n_var or N.shape[1] != w.shape[0] or (dN is not None and dN.shape[:3] != N.shape):
+                raise ValueError("part tabulations must share n_var and n_q")
+            arr[k].n_lshape, arr[k].n_comp, arr[k].side = N.shape[2], int(pd.get("n_comp", 1)), int(pd.get("side", 0))
+            arr[k].N = N.ctypes.data
+            arr[k].dN = None if dN is None else dN.ctypes.data
+        fv = None if face_var is None else _i32(face_var)
+        self._ck(self.lib.gtk_set_parts(self.h, w.shape[0], _ptr(w), _ptr(M), _ptr(dM), len(parts), arr, int(n_sides), int(n_var), _ptr(fv)))
+        del keep
+
+    def matrix_numeric_blocks(self, blocks, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """blocks: iterable of (part_u, part_v, form, alpha)"""
+        blocks = list(blocks)
+        arr = (Block * max(len(blocks), 1))()
+        for k, (pu, pv, form, alpha) in enumerate(blocks):
+            arr[k].part_u, arr[k].part_v, arr[k].form, arr[k].alpha = int(pu), int(pv), int(form), float(alpha)
+        nz = np.empty(self.nnz, dtype=np.float64) if out is None else out
+        self._ck(self.lib.gtk_matrix_numeric_blocks(self.h, len(blocks), arr, _ptr(nz)))
+        return nz
+
+    def vector_assemble_blocks(self, vblocks, accumulate: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """vblocks: iterable of (part, alpha, f_const)"""
+        if self.n_vec_rows == 0:
+            self.vector_symbolic(FREE)
+        vblocks = list(vblocks)
+        arr = (VBlock * max(len(vblocks), 1))()
+        for k, (part, alpha, f) in enumerate(vblocks):
+            arr[k].part, arr[k].alpha = int(part), float(alpha)
+            fv = np.zeros(3)
+            f = np.atleast_1d(np.asarray(f, dtype=np.float64)).reshape(-1)
+            fv[: f.size] = f
+            for c in range(3):
+                arr[k].f_const[c] = fv[c]
+        b = np.empty(self.n_vec_rows, dtype=np.float64) if out is None else out
+        self._ck(self.lib.gtk_vector_assemble_blocks(self.h, len(vblocks), arr, 1 if accumulate else 0, _ptr(b)))
+        return b
 
     # -- matrix ---------------------------------------------------------------------
     def select_matrix(self, slot: int):

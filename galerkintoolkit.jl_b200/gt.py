@@ -67,6 +67,11 @@ def boundary(mesh, group_names: Optional[Sequence[str]] = None) -> Domain:
     return Domain(mesh, "boundary", sides)
 
 
+def skeleton(mesh) -> Domain:
+    """GT.skeleton(mesh): the interior (D-1)-faces, two cells around each (domain.jl; accessors.jl:394-473)."""
+    return Domain(mesh, "skeleton")
+
+
 @dataclass
 class Measure:
     domain: Domain
@@ -115,8 +120,44 @@ class Space:
         return self._tab[key]
 
 
+    def __mul__(self, other):
+        """V × Q (cartesian_product, space.jl): Python spells × as *"""
+        return cartesian_product(self, other)
+
+
 def lagrange_space(domain, order, dirichlet_boundary=None, tensor_size=None) -> Space:
     return Space(domain, order, dirichlet_boundary, tensor_size)
+
+
+class ProductSpace:
+    """CartesianProductSpace: fields(V × Q) = (V, Q); free / Dirichlet dofs of the fields are numbered block after block
+    (assembly.jl:321-333)."""
+
+    def __init__(self, *spaces):
+        flat = []
+        for sp in spaces:
+            flat += list(sp.fields) if isinstance(sp, ProductSpace) else [sp]
+        if any(sp.domain.mesh is not flat[0].domain.mesh for sp in flat):
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "fields of a product space must share one mesh")
+        self.fields = tuple(flat)
+        self.domain = flat[0].domain
+
+    def __mul__(self, other):
+        return ProductSpace(self, other)
+
+    def num_free_dofs(self):
+        return sum(f.num_free_dofs() for f in self.fields)
+
+    def num_dirichlet_dofs(self):
+        return sum(f.num_dirichlet_dofs() for f in self.fields)
+
+
+def cartesian_product(*spaces) -> ProductSpace:
+    return ProductSpace(*spaces)
+
+
+def fields(space):
+    return space.fields if isinstance(space, ProductSpace) else (space,)
 
 
 # ---------------------------------------------------------------------------
@@ -145,7 +186,9 @@ class Coordinate(Term):        # CoordinateTerm (compiler.jl:60-1028)
 @dataclass
 class FormArg(Term):           # FormArgumentTerm: arg 1 = test, arg 2 = trial (problems.jl:324-327)
     arg: int
-    op: str                    # "value" | "gradient"
+    op: str                    # "value" | "gradient" | "divergence"
+    field: int = 0             # field of a product space (0-based)
+    side: int = 0              # skeleton integrals: u[1] / u[2] = the cell around (1-based; 0 = no restriction)
 
 
 @dataclass
@@ -169,11 +212,17 @@ def _lift(o):
 class FormArgument:
     """form_argument_quantity(space, arg) (compiler.jl:487-531)."""
 
-    def __init__(self, space: Space, arg: int):
-        self.space, self.arg = space, arg
+    def __init__(self, space: Space, arg: int, field: int = 0, side: int = 0):
+        self.space, self.arg, self.field, self.side = space, arg, field, side
 
     def __call__(self, x):
-        return FormArg(self.arg, "value")
+        return FormArg(self.arg, "value", self.field, self.side)
+
+    def __getitem__(self, k: int):
+        """u[1], u[2]: the restriction to the first / second cell around a skeleton face (compiler.jl:507-531, SkeletonTerm)"""
+        if k not in (1, 2):
+            raise IndexError("a skeleton face has two cells around: u[1], u[2]")
+        return FormArgument(self.space, self.arg, self.field, k)
 
 
 def grad(u, x):
@@ -181,7 +230,7 @@ def grad(u, x):
     DiscreteField → Σ_i u_i ∇φ_i (DiscreteFieldTerm, accessors.jl:1549-1556); on an AnalyticalField with a known
     gradient → that gradient sampled by the host."""
     if isinstance(u, FormArgument):
-        return FormArg(u.arg, "gradient")
+        return FormArg(u.arg, "gradient", u.field, u.side)
     if isinstance(u, DiscreteField):
         return FieldTerm(u, "gradient")
     if isinstance(u, AnalyticalField) and u.gradient is not None:
@@ -191,6 +240,13 @@ def grad(u, x):
 
 def dot(a, b):
     return Call("dot", _lift(a), _lift(b))
+
+
+def div(u, x):
+    """div(u,x) = tr(ForwardDiff.jacobian(u,x)) of a vector-valued form argument (docs/src/src_jl/example_stokes.jl)"""
+    if isinstance(u, FormArgument):
+        return FormArg(u.arg, "divergence", u.field, u.side)
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "div of a non form-argument quantity is not supported on the GPU path")
 
 
 @dataclass
@@ -523,6 +579,137 @@ def _upload_field(eng: _eng.Engine, params: dict) -> dict:
     return {k: v for k, v in params.items() if k != "field"}
 
 
+# ---------------------------------------------------------------------------
+# product spaces and skeleton integrals: block recognition
+# ---------------------------------------------------------------------------
+def _expand(t):
+    """term -> list of (scalar, factors, dotted): the integrand as a sum of products of form-argument factors"""
+    if isinstance(t, Const) and np.isscalar(t.value):
+        return [(float(t.value), (), False)]
+    if isinstance(t, FormArg):
+        return [(1.0, (t,), False)]
+    if isinstance(t, Call) and t.fn in ("+", "-") and t.b is not None:
+        sign = 1.0 if t.fn == "+" else -1.0
+        return _expand(t.a) + [(sign * c, f, d) for (c, f, d) in _expand(t.b)]
+    if isinstance(t, Call) and t.fn in ("*", "dot") and t.b is not None:
+        return [(ca * cb, fa + fb, da or db or t.fn == "dot") for (ca, fa, da) in _expand(t.a) for (cb, fb, db) in _expand(t.b)]
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM,
+                               "integrand not recognised by the GPU engine (sums of products of u, v, ∇u, ∇v, div u, div v "
+                               "with constant factors); refusing to fall back to a CPU loop")
+
+
+def _is_blocks_case(space, meas: "Measure") -> bool:
+    return isinstance(space, ProductSpace) or meas.domain.kind == "skeleton"
+
+
+def _block_problem(space, meas: "Measure"):
+    from . import multifield as _mf
+    data = [f.data for f in fields(space)]
+    if meas.domain.kind == "skeleton":
+        return _mf.skeleton_problem(data, meas.degree)
+    if meas.domain.kind == "interior":
+        return _mf.volume_problem(data, meas.degree)
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "product spaces are assembled on interior and skeleton measures only")
+
+
+def _setup_block_engine(space, meas: "Measure", engine: Optional[_eng.Engine] = None):
+    eng = engine or _eng.Engine(_default_device)
+    bp = _block_problem(space, meas)
+    eng.set_mesh(bp.node_coordinates, bp.face_nodes)
+    if bp.manifold_dim != bp.node_coordinates.shape[1]:
+        eng.set_manifold_dim(bp.manifold_dim)
+    eng.set_space(bp.super_dofs, bp.n_free, bp.n_dirichlet, 1)
+    eng.set_parts(bp.w, bp.M, bp.dM, bp.parts, bp.n_sides, bp.face_var)
+    eng._gt_setup = None
+    return eng, bp
+
+
+def _part_of(bp, fa: FormArg, skeleton_measure: bool) -> int:
+    if skeleton_measure:
+        if fa.side not in (1, 2):
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "on a skeleton measure form arguments are restricted to a cell around: u[1](x), u[2](x)")
+        return bp.part_index(fa.field, fa.side - 1)
+    if fa.side:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "u[1] / u[2] are meaningful on skeleton measures only")
+    return bp.part_index(fa.field, 0)
+
+
+def recognise_blocks(term, bp, skeleton_measure: bool):
+    """-> [(part_u, part_v, block form, alpha)]: one recognised term per (part of u, part of v) block."""
+    out = {}
+    for coef, factors, dotted in _expand(term):
+        us = [f for f in factors if f.arg == 2]
+        vs = [f for f in factors if f.arg == 1]
+        if len(us) != 1 or len(vs) != 1 or len(factors) != 2:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "every term of a bilinear integrand must hold exactly one trial and one test factor; no CPU fallback")
+        u, v = us[0], vs[0]
+        ops = (u.op, v.op)
+        if ops == ("value", "value"):
+            form = _eng.BLOCK_MASS
+        elif ops == ("gradient", "gradient") and dotted:
+            form = _eng.BLOCK_LAPLACE
+        elif ops == ("value", "divergence"):
+            form = _eng.BLOCK_VALU_DIVV
+        elif ops == ("divergence", "value"):
+            form = _eng.BLOCK_DIVU_VALV
+        else:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, f"block term ({u.op} of u) x ({v.op} of v) is not recognised by the GPU engine; no CPU fallback")
+        key = (_part_of(bp, u, skeleton_measure), _part_of(bp, v, skeleton_measure))
+        if key in out:
+            if out[key][0] != form:
+                raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "two different terms in one block are not recognised; no CPU fallback")
+            out[key] = (form, out[key][1] + coef)
+        else:
+            out[key] = (form, coef)
+    return [(pu, pv, form, alpha) for (pu, pv), (form, alpha) in out.items()]
+
+
+def recognise_vblocks(term, bp, skeleton_measure: bool, space):
+    """linear forms: Σ constant · v_f[side](x)  ->  [(part, alpha, f_const)]"""
+    out = {}
+    flds = fields(space)
+    for coef, factors, _ in _expand(term):
+        if len(factors) != 1 or factors[0].arg != 1 or factors[0].op != "value":
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "linear block terms are constant multiples of v(x); no CPU fallback")
+        part = _part_of(bp, factors[0], skeleton_measure)
+        out[part] = out.get(part, 0.0) + coef
+    return [(part, alpha, np.ones(flds[bp.parts[part]["field"]].data.n_comp)) for part, alpha in out.items()]
+
+
+def _form_arguments(space, arg: int):
+    if isinstance(space, ProductSpace):
+        return tuple(FormArgument(f, arg, k) for k, f in enumerate(space.fields))
+    return FormArgument(space, arg)
+
+
+def _assemble_matrix_blocks(a, U, V, reuse, free_or_dirichlet, engine, index_type):
+    if U is not V:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
+    term, meas, scale = _single_contribution(a(_form_arguments(U, 2), _form_arguments(V, 1)))
+    eng, bp = _setup_block_engine(V, meas, engine)
+    blocks = [(pu, pv, form, alpha * scale) for (pu, pv, form, alpha) in recognise_blocks(term, bp, meas.domain.kind == "skeleton")]
+    eng.matrix_symbolic(*free_or_dirichlet)
+    colptr, rowval = eng.matrix_pattern_i64() if index_type in (int, np.int64) else eng.matrix_pattern()
+    nzval = eng.matrix_numeric_blocks(blocks)
+    A = SparseMatrixCSC(eng.n_rows, eng.n_cols, colptr, rowval, nzval)
+    if reuse:
+        return A, AssemblyCache(eng, "blocks", dict(blocks=blocks), "matrix")
+    eng.close()
+    return A
+
+
+def _assemble_vector_blocks(l, V, reuse, free_or_dirichlet, engine):
+    term, meas, scale = _single_contribution(l(_form_arguments(V, 1)))
+    eng, bp = _setup_block_engine(V, meas, engine)
+    vblocks = [(part, alpha * scale, f) for (part, alpha, f) in recognise_vblocks(term, bp, meas.domain.kind == "skeleton", V)]
+    eng.vector_symbolic(free_or_dirichlet)
+    b = eng.vector_assemble_blocks(vblocks)
+    if reuse:
+        return b, AssemblyCache(eng, "blocks", dict(vblocks=vblocks), "vector")
+    eng.close()
+    return b
+
+
 def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, parameters=(),
                     free_or_dirichlet=(FREE, FREE), engine: Optional[_eng.Engine] = None, assembly_options=None):
     """GT.assemble_matrix(a, T, U, V; reuse, free_or_dirichlet) (problems.jl:319-350).
@@ -531,8 +718,15 @@ def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, 
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "the engine assembles Float64 only")
     if U is not V:
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
-    u, v = FormArgument(U, 2), FormArgument(V, 1)
-    term, meas, scale = _single_contribution(a(u, v))
+    probe = a(_form_arguments(U, 2), _form_arguments(V, 1))
+    if len(probe.contributions) == 1 and _is_blocks_case(V, probe.contributions[0][1]):
+        # product spaces / skeleton integrals: block kernels on the super element
+        opts = dict(assembly_options or {})
+        index_type = opts.pop("index_type", np.int32)
+        if opts.pop("eltype", np.float64) not in (float, np.float64) or opts or parameters:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "assembly_options / parameters not supported for product spaces on the GPU engine")
+        return _assemble_matrix_blocks(a, U, V, reuse, free_or_dirichlet, engine, index_type)
+    term, meas, scale = _single_contribution(probe)
     form, params = recognise_bilinear(term, V, meas)
     if meas.domain.kind == "boundary" and form != _eng.FORM_MASS:
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "on a boundary measure only ∫_Γ u v dΓ (Robin term) is assembled by the GPU engine")
@@ -557,6 +751,9 @@ def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, 
 def update_matrix(A: SparseMatrixCSC, cache: AssemblyCache, parameters=(), **new_params):
     """GT.update_matrix!(A, cache; parameters) (problems.jl:352-361): numeric re-assembly on the cached pattern; a
     DiscreteField in `parameters` replaces the one the form was recognised with."""
+    if cache.form == "blocks":
+        cache.engine.matrix_numeric_blocks(cache.params["blocks"], out=A.nzval)
+        return A
     cache.params.update(new_params)
     if parameters:
         cache.params["field"] = parameters[0]
@@ -569,8 +766,12 @@ def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, parameters
     """GT.assemble_vector(l, T, V; reuse) (problems.jl:244-274)."""
     if T not in (float, np.float64):
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "the engine assembles Float64 only")
-    v = FormArgument(V, 1)
+    v = _form_arguments(V, 1)
     contributions = l(v).contributions
+    if len(contributions) == 1 and _is_blocks_case(V, contributions[0][1]):
+        if parameters:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "parameters are not supported for product spaces on the GPU engine")
+        return _assemble_vector_blocks(l, V, reuse, free_or_dirichlet, engine)
     if len(contributions) > 1:
         # ∫_Ω f v dΩ + ∫_Γ g v dΓ + …: the reference pushes every integral into ONE COO vector, contribution after
         # contribution (problems.jl:258-266); each integral is one engine pass that continues the sums of the previous
@@ -602,6 +803,9 @@ def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, parameters
 
 def update_vector(b: np.ndarray, cache: AssemblyCache, parameters=(), **new_params):
     """GT.update_vector!(b, cache; parameters) (problems.jl:276-285)."""
+    if cache.form == "blocks":
+        cache.engine.vector_assemble_blocks(cache.params["vblocks"], out=b)
+        return b
     cache.params.update(new_params)
     if parameters:
         cache.params["field"] = parameters[0]

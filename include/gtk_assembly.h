@@ -211,6 +211,59 @@ int32_t gtk_space_dof_coordinates(gtk_ctx* ctx, const double* M_at_nodes, double
  * tree order (bit-reproducible).  kind: GTK_SCALAR_*. */
 int32_t gtk_scalar_assemble(gtk_ctx* ctx, int32_t kind, const gtk_form_params* p, double* out);
 
+/* ---- multi-field spaces and skeleton integrals ---------------------------------------------------- */
+/* The generated loops of the reference run, per integration face, over (field of v, field of u, cell around for v, cell
+ * around for u) and push one element matrix per combination through MonolithicAssemblyAllocation, which adds the field's
+ * block offset to the row / column ids (compiler.jl:1826-1923, assembly.jl:321-333, 386-416; every block is pushed, also
+ * the identically zero ones: block_mask defaults to all true).  Skeleton integrals (`∫(…, measure(skeleton(mesh), degree))`)
+ * have two cells around every face, boundary and volume integrals one (accessors.jl:394-473).
+ *
+ * Engine view: the SUPER element of a face is the concatenation — field-major, then cell-around-major — of its "parts"
+ * (field, side).  The host passes
+ *   gtk_set_mesh          the integration faces (volume cells, or the (D-1)-faces of a skeleton / boundary with
+ *                         gtk_set_manifold_dim(D-1): dV comes from the face's own geometry, accessors.jl:1000-1007),
+ *   gtk_set_space         the super dof table [n_faces][L]: for every part the dofs of that field on that cell around, free ids
+ *                         shifted by the field's free offset, Dirichlet ids by its Dirichlet offset (kept negative),
+ *                         n_free / n_dirichlet = totals over the fields, n_comp = 1,
+ *   gtk_set_parts         the quadrature weights, the geometry tabulation of the faces (as gtk_set_tabulation) and one
+ *                         descriptor per part, in the order of the super dof table.
+ * gtk_matrix_symbolic / gtk_vector_symbolic, patterns, slots, free / Dirichlet selections then work unchanged. */
+#define GTK_MAX_PARTS 8
+typedef struct gtk_part {
+  int32_t n_lshape;   /* scalar shape functions of the field on one cell                                             */
+  int32_t n_comp;     /* components; the part holds n_lshape * n_comp consecutive local dofs, dof = shape * n_comp + c */
+  int32_t side;       /* which cell around the face (0-based; volume integrals: 0)                                   */
+  const double* N;    /* host [n_var][n_q][n_lshape]: the cell's shape functions at the face's quadrature points, one table
+                         per (local face, permutation) variant (accessors.jl:498-522, reference_map :1914-1943); volume: n_var = 1 */
+  const double* dN;   /* host [n_var][n_q][n_lshape][D] reference gradients, or NULL (values only; required NULL on faces) */
+} gtk_part;
+/* face_var: host [n_faces][n_sides], 0-based variant of the tabulation for the cell around on each side (NULL if n_var ==
+ * n_sides == 1).  Replaces gtk_set_tabulation for this mesh / space; a later gtk_set_mesh / gtk_set_space drops the parts. */
+int32_t gtk_set_parts(gtk_ctx* ctx, int32_t n_q, const double* w, const double* M, const double* dM, int32_t n_parts,
+                      const gtk_part* parts, int32_t n_sides, int32_t n_var, const int32_t* face_var);
+/* Block integrands.  Row index = shape function of u (part_u), column = shape function of v (part_v), like the single-field
+ * forms (be[r,c] = Σ_q (alpha · integrand(u = φ_r, v = φ_c)) · dV_q).  alpha carries the integral's scalar, the sign of the
+ * term and the side weights of jump (-1 on side 0, +1 on side 1: v[2](p) - v[1](p)) or mean (1/2) — exact factors. */
+enum {
+  GTK_BLOCK_ZERO = 0,       /* nothing recognised in this block: zeros are pushed (they are stored, as in the reference)   */
+  GTK_BLOCK_MASS = 1,       /* u(x) * v(x)  (component-wise for vector parts; the two parts may be different fields / sides) */
+  GTK_BLOCK_LAPLACE = 2,    /* ∇(v,x) ⋅ ∇(u,x)  (component-wise: the Frobenius product of the Jacobians for vector parts)   */
+  GTK_BLOCK_VALU_DIVV = 3,  /* u(x) * div(v,x): u a scalar part (pressure), v a vector part with n_comp == D                */
+  GTK_BLOCK_DIVU_VALV = 4   /* v(x) * div(u,x): v a scalar part, u a vector part                                           */
+};
+typedef struct gtk_block { int32_t part_u, part_v, form; double alpha; } gtk_block;
+/* Numeric assembly of Σ blocks on the pattern of gtk_matrix_symbolic (blocks not listed are GTK_BLOCK_ZERO); re-callable
+ * like gtk_matrix_numeric (update_matrix!).  E.g. Stokes a((u,p),(v,q)) = ∫ ∇v⋅∇u - div(v) p + q div(u)
+ * (docs/src/src_jl/example_stokes.jl) is {(u,v,LAPLACE,1), (p,v,VALU_DIVV,-1), (u,q,DIVU_VALV,1)}; the reference's test
+ * ∫_Λ jump(u)·jump(v) (test/assembly_tests.jl:397-401) is MASS on the four (side, side) blocks with alpha = ±1. */
+int32_t gtk_matrix_numeric_blocks(gtk_ctx* ctx, int32_t n_blocks, const gtk_block* blocks, double* nzval);
+int32_t gtk_matrix_numeric_blocks_device(gtk_ctx* ctx, int32_t n_blocks, const gtk_block* blocks);
+/* Linear forms: per part ∫ alpha (f · v) with f constant — ∫_Λ jump(v) (test/assembly_tests.jl:420-424) is alpha = -1 / +1
+ * on the two sides, f = 1.  accumulate as in gtk_form_params. */
+typedef struct gtk_vblock { int32_t part; double alpha; double f_const[3]; } gtk_vblock;
+int32_t gtk_vector_assemble_blocks(gtk_ctx* ctx, int32_t n, const gtk_vblock* vblocks, int32_t accumulate, double* b);
+int32_t gtk_vector_assemble_blocks_device(gtk_ctx* ctx, int32_t n, const gtk_vblock* vblocks, int32_t accumulate);
+
 /* ---- device-resident results -------------------------------------------------- */
 /* which: 0 nzval (double[nnz]) 1 b (double[n_rows]) 2 colptr (int64[n_cols+1], 0-based)
  *        3 rowval (int32[nnz], 1-based) 4 field free values (double[n_free]) 5 field Dirichlet values (double[n_dirichlet])

@@ -1059,3 +1059,250 @@ def lagrange_space_literal(domain, cells_per_dir, order, dirichlet_sides=None, n
     out = [[newid[x - 1] for x in row] for row in cell_dofs]
     return dict(coords=coords, cell_nodes=np.array(cell_nodes, dtype=np.int32), cell_dofs=np.array(out, dtype=np.int32),
                 n_free=len(free), n_dirichlet=len(diri), n_dofs=ndofs, face_complex=fc)
+
+
+# ---------------------------------------------------------------------------
+# Multi-field spaces (CartesianProductSpace) and skeleton integrals — SURVEY.md §8 f4
+# Literal restatement, python loops, small meshes only.
+# ---------------------------------------------------------------------------
+def monolithic_offsets(lengths):
+    """assembly.jl:321-333: offsets = blocklasts(dofs) .- map(length, blocks(dofs))"""
+    out, s = [], 0
+    for n in lengths:
+        out.append(s)
+        s += n
+    return out
+
+
+def skeleton_faces(cell_nodes, nnodes, D):
+    """GT.skeleton(mesh) on cartesian_mesh output (quads / hexahedra): the (D-1)-faces with two cells around, in face-id
+    order of the complexified mesh (domain.jl: skeleton = faces with 2 cells in face_incidence(topo, D-1, D)); cells around
+    in increasing cell id (face_incidence(topo, d, D) is the transpose of the cell -> face incidence, filled looping over
+    the cells in order, topology.jl:313-334).  Per face: its nodes in the face's own vertex order, the two (cell, local
+    face id, permutation id) triples (face_permutation_ids, topology.jl:593-634)."""
+    fc = face_complex(cell_nodes, nnodes, D)
+    d = D - 1
+    vertex_node = {v: n + 1 for n, v in enumerate(fc["node_vertex"])}
+    around = {}
+    for cell, row in enumerate(fc["cell_faces"][d]):
+        for lface, face in enumerate(row):
+            around.setdefault(face, []).append((cell + 1, lface + 1))
+    vperms = _vertex_permutations(d)
+    lfaces = _cube_lfaces(D, d)
+    out = []
+    for face in range(1, len(fc["vertices"][d]) + 1):
+        ar = around.get(face, [])
+        if len(ar) != 2:
+            continue
+        fv = fc["vertices"][d][face - 1]
+        sides = []
+        for cell, lface in ar:
+            cv = fc["vertices"][D][cell - 1]
+            cvertices = lfaces[lface - 1]
+            for pi, P in enumerate(vperms):
+                if all(fv[P[c] - 1] == cv[cvertices[c] - 1] for c in range(len(cvertices))):
+                    sides.append((cell, lface, pi + 1))
+                    break
+            else:
+                raise AssertionError("Valid pindex not found")
+        out.append(dict(face=face, nodes=[vertex_node[v] for v in fv], sides=sides))
+    return out
+
+
+def reference_map_tables(D, point_to_x):
+    """accessors.jl:1914-1943 reference_map(refdface, refDface) evaluated at the face quadrature points, for the unit
+    D-cube and its (D-1)-faces: per local face, per node permutation `ids` of the face, φ(x) = Σ_dof coeff[dof]·M_dof(x)
+    with coeff[ids] = node_coordinates(boundary)[lface_nodes]  ->  tables[ldface][perm] = [n_points][D]."""
+    d = D - 1
+    Xref = [[float((v >> m) & 1) for m in range(D)] for v in range(2 ** D)]       # reference cube nodes, first index fastest
+    M, _ = tabulate(d, 1, "Q", point_to_x)                                       # shape functions of the reference face
+    out = []
+    for lnodes in _cube_lfaces(D, d):
+        per_perm = []
+        for ids in _vertex_permutations(d):
+            coeff = [None] * len(lnodes)
+            for k, node in enumerate(lnodes):
+                coeff[ids[k] - 1] = Xref[node - 1]
+            pts = []
+            for p in range(len(point_to_x)):
+                x = [0.0] * D
+                for dof in range(len(coeff)):
+                    for c in range(D):
+                        x[c] += coeff[dof][c] * M[p, dof]
+                pts.append(x)
+            per_perm.append(pts)
+        out.append(per_perm)
+    return out
+
+
+class _LoopPoint:
+    """What the generated integrand sees at one (face, point) for one combination of loop indices: shape functions of the
+    fields masked by `ifelse(face_around == the_face_around && field == the_field, sfun, zero)` (compiler.jl:728-739).
+    v = argument 1 (loop indices field_1 / face_around_1 / dof_1), u = argument 2."""
+
+    def __init__(self, D, field_ncomp):
+        self.D, self.field_ncomp = D, field_ncomp
+
+    def _zero(self, field, gradient):
+        """zero(eltype(shape_functions(f, … the_field …))): the zero of THAT field's shape-function type"""
+        nc = self.field_ncomp[field]
+        if gradient:
+            return np.zeros(self.D) if nc == 1 else np.zeros((nc, self.D))
+        return 0.0 if nc == 1 else np.zeros(nc)
+
+    def _val(self, which, field, side):
+        f, a, val, _ = which
+        return val if (f == field and a == side) else self._zero(field, False)
+
+    def _grad(self, which, field, side):
+        f, a, _, g = which
+        return g if (f == field and a == side) else self._zero(field, True)
+
+    def v(self, field, side=1): return self._val(self.V, field, side)
+    def u(self, field, side=1): return self._val(self.U, field, side)
+    def grad_v(self, field, side=1): return self._grad(self.V, field, side)     # ForwardDiff.gradient / jacobian
+    def grad_u(self, field, side=1): return self._grad(self.U, field, side)
+    def div_v(self, field, side=1): return float(np.trace(self._grad(self.V, field, side)))
+    def div_u(self, field, side=1): return float(np.trace(self._grad(self.U, field, side)))
+
+
+def _shape(N_a, g_a, comp, n_comp, D):
+    """value and gradient of the shape function (node a, component comp): scalar -> (N_a, ∇N_a); vector-valued ->
+    (N_a e_comp, e_comp ⊗ ∇N_a) (space.jl:1267-1271; the Jacobian's row `comp` is ∇N_a)"""
+    if n_comp == 1:
+        return N_a, g_a
+    val = np.zeros(n_comp)
+    val[comp] = N_a
+    if g_a is None:
+        return val, None
+    jac = np.zeros((n_comp, D))
+    jac[comp, :] = g_a
+    return val, jac
+
+
+def frobenius(a, b):
+    """`a ⋅ b` of two SVectors / SMatrices: Σ of the elementwise products in memory (column-major) order"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.ndim == 0:
+        return float(a * b)
+    fa, fb = a.reshape(-1, order="F"), b.reshape(-1, order="F")
+    s = fa[0] * fb[0]
+    for k in range(1, fa.size):
+        s = s + fa[k] * fb[k]
+    return float(s)
+
+
+def assemble_matrix_multifield(D, coords, face_nodes, face_tab, sides, fields, integrand, alpha=1.0,
+                               free_or_dirichlet=(FREE, FREE), cell_geometry=None):
+    """generate_matrix_assembly_template (compiler.jl:1826-1923) + MonolithicAssemblyAllocation (assembly.jl:386-416)
+    + contribute!(::MatrixAllocation) (:189-208) + compress (:571-575), loop for loop.
+
+    coords, face_nodes        geometry of the integration faces (cells of the mesh for volume integrals)
+    face_tab                  dict(w [nq], dM [nq][nlnf][d]): quadrature and geometry tabulation on the reference face
+    sides[face]               list over the cells around of (cell (1-based), tabulation variant (0-based))
+    fields                    list of dict(cell_dofs [n_cells][nld] signed, n_free, n_dirichlet, n_comp,
+                                           N [n_var][nq][nls], dN [n_var][nq][nls][D] or None)
+    integrand(pt)             user integrand on a _LoopPoint (masked shape functions), e.g.
+                              lambda p: frobenius(p.grad_v(0), p.grad_u(0)) - p.div_v(0) * p.u(1) + p.v(1) * p.div_u(0)
+    cell_geometry             (cell_nodes, dM_cell [nq][nln][D]) for physical gradients (volume integrals only)
+    -> colptr, rowval, nzval of the monolithic matrix (rows: u's fields, columns: v's fields — SURVEY A.8b)."""
+    fr, fcn = free_or_dirichlet
+    nf = len(fields)
+    n_rows_f = [f["n_free"] if fr == FREE else f["n_dirichlet"] for f in fields]
+    n_cols_f = [f["n_free"] if fcn == FREE else f["n_dirichlet"] for f in fields]
+    off_i, off_j = monolithic_offsets(n_rows_f), monolithic_offsets(n_cols_f)
+    w, dMf = face_tab["w"], face_tab["dM"]
+    nq = len(w)
+    fn = np.asarray(face_nodes)
+    I, J, V = [], [], []
+    pt = _LoopPoint(D, [f["n_comp"] for f in fields])
+    for face in range(fn.shape[0]):
+        n_around = len(sides[face])
+        nld = [len(f["cell_dofs"][0]) for f in fields]
+        be = {}
+        for f1 in range(nf):
+            for f2 in range(nf):
+                for a1 in range(n_around):
+                    for a2 in range(n_around):
+                        be[a2, a1, f2, f1] = np.zeros((nld[f2], nld[f1]))
+        for q in range(nq):
+            Jf = point_geometry(coords, fn[face:face + 1], np.asarray(dMf[q]))
+            dV = float(change_of_measure(Jf)[0] * w[q])                          # the FACE's own geometry (accessors.jl:1000-1007)
+            # shape functions of every field on every cell around at this point
+            sh = {}
+            for f, fld in enumerate(fields):
+                nc = fld["n_comp"]
+                for a, (cell, var) in enumerate(sides[face]):
+                    g = None
+                    if fld.get("dN") is not None and cell_geometry is not None:
+                        cn, dMc = cell_geometry
+                        Jc = point_geometry(coords, np.asarray(cn)[cell - 1:cell], np.asarray(dMc[q]))
+                        Jt = np.swapaxes(Jc, -1, -2)
+                        g = [_solve(Jt, np.asarray(fld["dN"][var][q][s]).reshape(1, D))[0] for s in range(len(fld["N"][var][q]))]
+                    vals = []
+                    for ld in range(nld[f]):
+                        s, comp = divmod(ld, nc)
+                        vals.append(_shape(fld["N"][var][q][s], None if g is None else g[s], comp, nc, D))
+                    sh[f, a] = vals
+            for f1 in range(nf):
+                for f2 in range(nf):
+                    for a1 in range(n_around):
+                        for a2 in range(n_around):
+                            for j in range(nld[f1]):
+                                pt.V = (f1, a1 + 1) + sh[f1, a1][j]
+                                for i in range(nld[f2]):
+                                    pt.U = (f2, a2 + 1) + sh[f2, a2][i]
+                                    be[a2, a1, f2, f1][i, j] += (alpha * integrand(pt)) * dV
+        for f1 in range(nf):
+            for f2 in range(nf):
+                for a1 in range(n_around):
+                    dofs_j = fields[f1]["cell_dofs"][sides[face][a1][0] - 1]
+                    for a2 in range(n_around):
+                        dofs_i = fields[f2]["cell_dofs"][sides[face][a2][0] - 1]
+                        blk = be[a2, a1, f2, f1]
+                        for j, dj in enumerate(dofs_j):
+                            if _skip(dj, fcn):
+                                continue
+                            for i, di in enumerate(dofs_i):
+                                if _skip(di, fr):
+                                    continue
+                                I.append(off_i[f2] + (di if fr == FREE else -di))
+                                J.append(off_j[f1] + (dj if fcn == FREE else -dj))
+                                V.append(blk[i, j])
+    return sparse_csc(np.array(I, dtype=np.int64), np.array(J, dtype=np.int64), np.array(V), sum(n_rows_f), sum(n_cols_f))
+
+
+def assemble_vector_multifield(D, coords, face_nodes, face_tab, sides, fields, integrand, alpha=1.0, free_or_dirichlet=FREE):
+    """generate_vector_assembly_template (compiler.jl:1933-2000) + monolithic contribute! (assembly.jl:392-399), loop for
+    loop; integrand(pt) sees the masked test function v only."""
+    nf = len(fields)
+    n_rows_f = [f["n_free"] if free_or_dirichlet == FREE else f["n_dirichlet"] for f in fields]
+    off = monolithic_offsets(n_rows_f)
+    w, dMf = face_tab["w"], face_tab["dM"]
+    fn = np.asarray(face_nodes)
+    I, V = [], []
+    pt = _LoopPoint(D, [f["n_comp"] for f in fields])
+    for face in range(fn.shape[0]):
+        n_around = len(sides[face])
+        nld = [len(f["cell_dofs"][0]) for f in fields]
+        be = {(a, f): np.zeros(nld[f]) for f in range(nf) for a in range(n_around)}
+        for q in range(len(w)):
+            Jf = point_geometry(coords, fn[face:face + 1], np.asarray(dMf[q]))
+            dV = float(change_of_measure(Jf)[0] * w[q])
+            for f in range(nf):
+                nc = fields[f]["n_comp"]
+                for a in range(n_around):
+                    var = sides[face][a][1]
+                    for ld in range(nld[f]):
+                        s, comp = divmod(ld, nc)
+                        pt.V = (f, a + 1) + _shape(fields[f]["N"][var][q][s], None, comp, nc, D)
+                        be[a, f][ld] += (alpha * integrand(pt)) * dV
+        for f in range(nf):
+            for a in range(n_around):
+                dofs = fields[f]["cell_dofs"][sides[face][a][0] - 1]
+                for i, di in enumerate(dofs):
+                    if _skip(di, free_or_dirichlet):
+                        continue
+                    I.append(off[f] + (di if free_or_dirichlet == FREE else -di))
+                    V.append(be[a, f][i])
+    return dense_vector(np.array(I, dtype=np.int64), np.array(V), sum(n_rows_f))

@@ -273,6 +273,9 @@ def test_every_entry_point_rejects_a_null_context(built_library):
         "gtk_field_axpy_free": (z, 1.0, z), "gtk_space_dof_coordinates": (z, z, z, z), "gtk_scalar_assemble": (z, 201, z, z),
         "gtk_comm_build_exchange": (z, 0, z), "gtk_comm_connect_peer_memory": (z,),
         "gtk_set_cartesian_q1_problem": (z, z, z, 0, 2, 0, z, z), "gtk_copy_device_array": (z, 0, z, 0), "gtk_matrix_pattern_i64": (z, z, z),
+        "gtk_set_parts": (z, 4, z, z, z, 1, z, 1, 1, z), "gtk_matrix_numeric_blocks": (z, 0, z, z),
+        "gtk_matrix_numeric_blocks_device": (z, 0, z), "gtk_vector_assemble_blocks": (z, 0, z, 0, z),
+        "gtk_vector_assemble_blocks_device": (z, 0, z, 0),
     }
     for name, args in calls.items():
         rc = getattr(lib, name)(*args)

@@ -1,0 +1,377 @@
+"""multi-field spaces (CartesianProductSpace block offsets) and skeleton integrals.
+
+CPU: the oracle's literal restatement of the generated multi-field / skeleton loops (compiler.jl:1826-2000, assembly.jl:
+321-416) against known answers — the reference's own (`sum(b)+1 ≈ 1` for ∫_Λ jump(v), test/assembly_tests.jl:420-427) and
+structural ones (blocks of V × V equal the single-field matrix bitwise, the Stokes coupling blocks are minus each other's
+transpose) — and the package's vectorised input preparation (multifield.py) against the oracle's loops.
+GPU: libgtkasm's block kernels against the oracle on identical inputs, through the C ABI and through the GT mirror."""
+import importlib
+
+import numpy as np
+import pytest
+
+import gt_oracle as O
+import gtk_b200
+from util import assert_values_close
+
+E = gtk_b200.engine
+H = gtk_b200.hostprep
+GT = gtk_b200.gt
+MF = importlib.import_module("galerkintoolkit_jl_b200.multifield")
+
+
+# ---- integrands written the way the reference's tests write them ---------------------------------------------------
+def jump_u(p, f=0): return p.u(f, 2) - p.u(f, 1)          # jump(u,p) = u[2](p) - u[1](p)   (test/assembly_tests.jl:332)
+def jump_v(p, f=0): return p.v(f, 2) - p.v(f, 1)
+
+
+INTEGRANDS = {
+    "jumpjump": lambda p: jump_u(p) * jump_v(p),                                   # test/assembly_tests.jl:397-401
+    "sum_mass": lambda p: (p.v(0) + p.v(1)) * (p.u(0) + p.u(1)),                   # test/assembly_tests.jl:409-412
+    "jump12": lambda p: jump_u(p, 0) * jump_v(p, 1),                               # test/assembly_tests.jl:413-415
+    # docs/src/src_jl/example_stokes.jl: ∇(v,x)⋅∇(u,x) - div(v,x)*p(x) + q(x)*div(u,x)
+    "stokes": lambda p: O.frobenius(p.grad_v(0), p.grad_u(0)) - p.div_v(0) * p.u(1) + p.v(1) * p.div_u(0),
+}
+
+
+def _oracle_fields(bp, spaces, with_gradients):
+    """the oracle's field descriptors from a BlockProblem (one per field; tables of side 0 serve both sides)"""
+    out = []
+    for f, s in enumerate(spaces):
+        part = bp.parts[bp.part_index(f, 0)]
+        out.append(dict(cell_dofs=s.cell_dofs, n_free=s.n_free, n_dirichlet=s.n_dirichlet, n_comp=s.n_comp,
+                        N=part["N"], dN=part["dN"] if with_gradients else None))
+    return out
+
+
+def _oracle_matrix(bp, spaces, mesh, name, alpha=1.0, fd=(O.FREE, O.FREE)):
+    nf = bp.face_nodes.shape[0]
+    if bp.n_sides == 2:
+        sides = [[(int(bp.side_cells[i, a]), int(bp.face_var[i, a])) for a in range(2)] for i in range(nf)]
+        geo = None
+    else:
+        sides = [[(i + 1, 0)] for i in range(nf)]
+        geo = (mesh.cell_nodes, bp.dM)
+    return O.assemble_matrix_multifield(mesh.D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides,
+                                        _oracle_fields(bp, spaces, geo is not None), INTEGRANDS[name], alpha=alpha,
+                                        free_or_dirichlet=fd, cell_geometry=geo)
+
+
+def _warp(mesh, amount=0.15, seed=3):
+    rng = np.random.default_rng(seed)
+    inner = ~H.boundary_node_mask(mesh)
+    h = 1.0 / np.array(mesh.cells_per_dir)
+    mesh.node_coordinates[inner] += amount * h * rng.uniform(-1, 1, size=(int(inner.sum()), mesh.D))
+
+
+def _stokes_spaces(cells, warp=True):
+    D = len(cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells)
+    if warp:
+        _warp(mesh)
+    V = H.lagrange_space(mesh, 2, "boundary", D)
+    Q = H.lagrange_space(mesh, 1, None, 1)
+    return mesh, [V, Q]
+
+
+# ---- CPU: host preparation against the oracle's loops ---------------------------------------------------------------
+@pytest.mark.parametrize("cells", [(3, 2), (4, 4), (2, 3, 2)])
+def test_skeleton_inputs_equal_the_literal_restatement(cells):
+    D = len(cells)
+    dom = tuple([0, 1] * D)
+    mesh = H.cartesian_mesh(dom, cells)
+    V = H.lagrange_space(mesh, 2, [1])
+    bp = MF.skeleton_problem([V], 4)
+    coords, cn = O.cartesian_chain(dom, cells)
+    sf = O.skeleton_faces(cn, coords.shape[0], D)
+    # number of interior faces of a Cartesian mesh
+    assert len(sf) == sum(int(np.prod([c - (1 if k == d else 0) for k, c in enumerate(cells)])) for d in range(D))
+    assert len(sf) == bp.face_nodes.shape[0]
+    q = H.quadrature(D - 1, False, 4)
+    tabs = O.reference_map_tables(D, q.coordinates)
+    for i, f in enumerate(sf):
+        assert list(bp.face_nodes[i]) == f["nodes"]
+        assert [s[0] for s in f["sides"]] == list(bp.side_cells[i])
+        for a, (cell, lface, perm) in enumerate(f["sides"]):
+            No, _ = O.tabulate(D, 2, "Q", np.array(tabs[lface - 1][perm - 1]))
+            assert np.abs(No - bp.parts[a]["N"][bp.face_var[i, a]]).max() < 1e-13
+            # the mapped points are the same physical points on both sides: face geometry == cell geometry there
+            Mf, _ = H.tabulate(D - 1, 1, "Q", q.coordinates)
+            xf = Mf @ mesh.node_coordinates[bp.face_nodes[i] - 1]
+            Mc, _ = H.tabulate(D, 1, "Q", np.array(tabs[lface - 1][perm - 1]))
+            xc = Mc @ mesh.node_coordinates[mesh.cell_nodes[cell - 1] - 1]
+            assert np.abs(xf - xc).max() < 1e-13
+    # super dof table: [side 0 dofs, side 1 dofs]
+    nld = V.cell_dofs.shape[1]
+    assert np.array_equal(bp.super_dofs[:, :nld], V.cell_dofs[bp.side_cells[:, 0] - 1])
+    assert np.array_equal(bp.super_dofs[:, nld:], V.cell_dofs[bp.side_cells[:, 1] - 1])
+
+
+def test_block_offsets_of_a_product_space():
+    mesh, (V, Q) = _stokes_spaces((3, 2), warp=False)
+    dofs, nfree, ndiri, fo, do = MF.offset_dofs([V, Q])
+    assert nfree == V.n_free + Q.n_free and ndiri == V.n_dirichlet + Q.n_dirichlet
+    assert list(fo) == O.monolithic_offsets([V.n_free, Q.n_free]) and list(do) == O.monolithic_offsets([V.n_dirichlet, Q.n_dirichlet])
+    assert np.array_equal(dofs[0], V.cell_dofs)
+    assert np.array_equal(dofs[1], np.where(Q.cell_dofs > 0, Q.cell_dofs + V.n_free, Q.cell_dofs - V.n_dirichlet))
+
+
+# ---- CPU: oracle known answers ---------------------------------------------------------------------------------------
+def test_oracle_jump_of_a_continuous_space_vanishes():
+    """test/assembly_tests.jl:420-427: b = assemble_vector(∫_Λ jump(v)); @test sum(b)+1 ≈ 1 — and, entry by entry, the jump of a
+    continuous basis function is zero, so b ≈ 0 and the jump-jump matrix holds (explicitly stored) zeros only"""
+    mesh = H.cartesian_mesh((0, 1, 0, 1), (4, 4))
+    _warp(mesh)
+    V = H.lagrange_space(mesh, 1, [1, 3])
+    bp = MF.skeleton_problem([V], 2)
+    sides = [[(int(bp.side_cells[i, a]), int(bp.face_var[i, a])) for a in range(2)] for i in range(bp.face_nodes.shape[0])]
+    b = O.assemble_vector_multifield(2, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides,
+                                     _oracle_fields(bp, [V], False), lambda p: jump_v(p))
+    assert b.shape == (V.n_free,) and sum(b) + 1 == pytest.approx(1.0, abs=1e-14) and np.abs(b).max() < 1e-15
+    cp, rv, nz = _oracle_matrix(bp, [V], mesh, "jumpjump")
+    assert cp.shape == (V.n_free + 1,) and np.abs(nz).max() < 1e-15
+    # pattern: two free dofs are coupled iff they belong to two cells (possibly the same) that share an interior face
+    pairs = set()
+    for c0, c1 in bp.side_cells:
+        d = [x for x in list(V.cell_dofs[c0 - 1]) + list(V.cell_dofs[c1 - 1]) if x > 0]
+        pairs |= {(r, c) for r in d for c in d}
+    got = {(int(rv[k]), c + 1) for c in range(V.n_free) for k in range(cp[c] - 1, cp[c + 1] - 1)}
+    assert got == pairs
+
+
+def test_oracle_product_space_blocks_equal_the_single_field_matrix():
+    """a((u1,u2),(v1,v2)) = ∫ (v1+v2)*(u1+u2) over V × V: every block of the monolithic matrix is the mass matrix of V, bit for bit"""
+    mesh = H.cartesian_mesh((0, 1, 0, 1), (3, 3))
+    _warp(mesh)
+    V = H.lagrange_space(mesh, 1, [2])
+    bp = MF.volume_problem([V, V], 2)
+    cp, rv, nz = _oracle_matrix(bp, [V, V], mesh, "sum_mass")
+    tab = H.measure_tabulation(V, 2)
+    cp1, rv1, nz1 = O.assemble_matrix(O.MASS, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, V.n_dirichlet,
+                                      dict(w=tab.w, N=tab.N, dN=tab.dN, M=tab.M, dM=tab.dM))
+    n = V.n_free
+    assert cp.shape == (2 * n + 1,)
+    for cb in range(2):
+        for c in range(n):
+            lo, hi = cp[cb * n + c] - 1, cp[cb * n + c + 1] - 1
+            lo1, hi1 = cp1[c] - 1, cp1[c + 1] - 1
+            assert np.array_equal(rv[lo:hi], np.concatenate([rv1[lo1:hi1], rv1[lo1:hi1] + n]))
+            assert np.array_equal(nz[lo:hi], np.concatenate([nz1[lo1:hi1], nz1[lo1:hi1]]))
+
+
+def test_oracle_stokes_blocks():
+    """K = vector Laplacian of V (bitwise the single-field assembly), the (p, v) block is minus the transpose of the (u, q)
+    block, the (p, q) block is stored and zero (block_mask all true, assembly.jl:321-333)"""
+    import scipy.sparse as sp
+    mesh, (V, Q) = _stokes_spaces((2, 2))
+    bp = MF.volume_problem([V, Q], 4)
+    cp, rv, nz = _oracle_matrix(bp, [V, Q], mesh, "stokes")
+    n, m = V.n_free, Q.n_free
+    A = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(n + m, n + m))
+    tab = H.measure_tabulation(V, 4)
+    cp1, rv1, nz1 = O.assemble_matrix(O.LAPLACE, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, V.n_dirichlet,
+                                      dict(w=tab.w, N=tab.N, dN=tab.dN, M=tab.M, dM=tab.dM), n_comp=2)
+    K1 = sp.csc_matrix((nz1, rv1 - 1, cp1 - 1), shape=(n, n))
+    assert abs(A[:n, :n] - K1).max() == 0.0
+    B_uq = A[:n, n:].toarray()          # rows u, columns q:  ∫ q div(u)
+    B_pv = A[n:, :n].toarray()          # rows p, columns v: -∫ div(v) p
+    assert np.abs(B_uq).max() > 1e-3 and np.abs(B_pv + B_uq.T).max() < 1e-15
+    assert abs(A[n:, n:]).max() == 0.0 and A[n:, n:].nnz > 0      # explicit zeros are part of the pattern
+    # div of the constant-pressure mode integrates the velocity flux through the boundary: zero for interior (free) velocities
+    assert np.abs(B_uq @ np.ones(m)).max() < 1e-13
+
+
+def test_recognition_of_block_forms_without_a_gpu():
+    mesh = GT.cartesian_mesh((0, 1, 0, 1), (3, 3))
+    Om = GT.interior(mesh)
+    V = GT.lagrange_space(Om, 2, dirichlet_boundary=GT.boundary(mesh), tensor_size=(2,))
+    Q = GT.lagrange_space(Om, 1)
+    X = V * Q
+    assert X.num_free_dofs() == V.num_free_dofs() + Q.num_free_dofs()
+    dO = GT.measure(Om, 4)
+    a = lambda up, vq: GT.integrate(lambda x: GT.dot(GT.grad(vq[0], x), GT.grad(up[0], x)) - GT.div(vq[0], x) * up[1](x)
+                                    + vq[1](x) * GT.div(up[0], x), dO)
+    term, meas, _ = a(GT._form_arguments(X, 2), GT._form_arguments(X, 1)).contributions[0]
+    bp = GT._block_problem(X, meas)
+    assert sorted(GT.recognise_blocks(term, bp, False)) == [(0, 0, E.BLOCK_LAPLACE, 1.0), (0, 1, E.BLOCK_DIVU_VALV, 1.0),
+                                                            (1, 0, E.BLOCK_VALU_DIVV, -1.0)]
+    dL = GT.measure(GT.skeleton(mesh), 2)
+    W = GT.lagrange_space(Om, 1)
+    jump = lambda u, p: u[2](p) - u[1](p)
+    aj = lambda u, v: GT.integrate(lambda p: jump(u, p) * jump(v, p), dL)
+    term, meas, _ = aj(GT._form_arguments(W, 2), GT._form_arguments(W, 1)).contributions[0]
+    bs = GT._block_problem(W, meas)
+    assert sorted(GT.recognise_blocks(term, bs, True)) == [(0, 0, E.BLOCK_MASS, 1.0), (0, 1, E.BLOCK_MASS, -1.0),
+                                                           (1, 0, E.BLOCK_MASS, -1.0), (1, 1, E.BLOCK_MASS, 1.0)]
+    with pytest.raises(GT.UnsupportedFormError):     # an unrestricted argument on a skeleton measure
+        t, m, _ = GT.integrate(lambda p: GT.FormArgument(W, 2)(p) * GT.FormArgument(W, 1)(p), dL).contributions[0]
+        GT.recognise_blocks(t, bs, True)
+    with pytest.raises(GT.UnsupportedFormError):     # gradient of u times value of v: no such block kernel
+        t, m, _ = GT.integrate(lambda p: GT.dot(GT.grad(GT.FormArgument(V, 2, 0), p), GT.FormArgument(V, 1, 0)(p)), dO).contributions[0]
+        GT.recognise_blocks(t, bp, False)
+
+
+# ---- GPU: block kernels against the oracle -----------------------------------------------------------------------------
+def _engine(bp):
+    eng = E.Engine(0)
+    eng.set_mesh(bp.node_coordinates, bp.face_nodes)
+    if bp.manifold_dim != bp.node_coordinates.shape[1]:
+        eng.set_manifold_dim(bp.manifold_dim)
+    eng.set_space(bp.super_dofs, bp.n_free, bp.n_dirichlet, 1)
+    eng.set_parts(bp.w, bp.M, bp.dM, bp.parts, bp.n_sides, bp.face_var)
+    return eng
+
+
+def _check(eng, blocks, expect, fd=(E.FREE, E.FREE)):
+    cp, rv, nz = expect
+    eng.matrix_symbolic(*fd)
+    gcp, grv = eng.matrix_pattern()
+    assert np.array_equal(gcp, cp) and np.array_equal(grv, rv)          # bit-exact pattern, explicit zeros included
+    gnz = eng.matrix_numeric_blocks(blocks)
+    assert_values_close(gnz, nz)
+    assert np.array_equal(eng.matrix_numeric_blocks(blocks), gnz)       # re-assembly: byte-identical
+    return gnz
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells", [(3, 2), (2, 2, 2)])
+def test_gpu_stokes_blocks_parity(cells):
+    mesh, spaces = _stokes_spaces(cells)
+    bp = MF.volume_problem(spaces, 4)
+    blocks = [(0, 0, E.BLOCK_LAPLACE, 1.0), (1, 0, E.BLOCK_VALU_DIVV, -1.0), (0, 1, E.BLOCK_DIVU_VALV, 1.0)]
+    eng = _engine(bp)
+    _check(eng, blocks, _oracle_matrix(bp, spaces, mesh, "stokes"))
+    # free x Dirichlet columns of the same form (Ad of a linear problem, problems.jl:363-380)
+    _check(eng, blocks, _oracle_matrix(bp, spaces, mesh, "stokes", fd=(O.FREE, O.DIRICHLET)), fd=(E.FREE, E.DIRICHLET))
+    assert eng.lib.gtk_info(eng.h, 5) == 7
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_product_space_mass_parity():
+    mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (3, 2, 2), simplexify=True)
+    V = H.lagrange_space(mesh, 2, [1])
+    W = H.lagrange_space(mesh, 1, [2, 3])
+    bp = MF.volume_problem([V, W], 4)
+    eng = _engine(bp)
+    _check(eng, [(pu, pv, E.BLOCK_MASS, 0.5) for pu in range(2) for pv in range(2)],
+           _oracle_matrix(bp, [V, W], mesh, "sum_mass", alpha=0.5))
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,order", [((4, 4), 1), ((3, 2), 2), ((3, 2, 2), 1), ((2, 2, 2), 2)])
+def test_gpu_skeleton_jump_parity(cells, order):
+    D = len(cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells)
+    _warp(mesh)
+    V = H.lagrange_space(mesh, order, [1, 3])
+    bp = MF.skeleton_problem([V], 2 * order)
+    eng = _engine(bp)
+    blocks = [(0, 0, E.BLOCK_MASS, 1.0), (0, 1, E.BLOCK_MASS, -1.0), (1, 0, E.BLOCK_MASS, -1.0), (1, 1, E.BLOCK_MASS, 1.0)]
+    cp, rv, nz = _oracle_matrix(bp, [V], mesh, "jumpjump")
+    eng.matrix_symbolic()
+    gcp, grv = eng.matrix_pattern()
+    assert np.array_equal(gcp, cp) and np.array_equal(grv, rv)
+    gnz = eng.matrix_numeric_blocks(blocks)
+    # a continuous space has no jumps: the values are rounding-level zeros on both sides; compare against the entry scale h^(D-1)
+    scale = (1.0 / max(cells)) ** (D - 1)
+    assert np.abs(gnz - nz).max() < 1e-12 * scale and np.abs(gnz).max() < 1e-12 * scale
+    # one side only: a non-trivial matrix (∫_Λ u[1] v[1]), values to 1e-12
+    one = eng.matrix_numeric_blocks([(0, 0, E.BLOCK_MASS, 1.0)])
+    sides = [[(int(bp.side_cells[i, a]), int(bp.face_var[i, a])) for a in range(2)] for i in range(bp.face_nodes.shape[0])]
+    ref = O.assemble_matrix_multifield(D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides,
+                                       _oracle_fields(bp, [V], False), lambda p: p.u(0, 1) * p.v(0, 1))
+    assert np.array_equal(ref[0], gcp) and np.array_equal(ref[1], grv)
+    assert_values_close(one, ref[2])
+    # ∫_Λ jump(v): zero vector; ∫_Λ v[2]: against the oracle
+    b = eng.vector_assemble_blocks([(0, -1.0, 1.0), (1, 1.0, 1.0)])
+    assert b.shape == (V.n_free,) and np.abs(b).max() < 1e-12 * scale
+    b2 = eng.vector_assemble_blocks([(1, 1.0, 1.0)])
+    rb = O.assemble_vector_multifield(D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides,
+                                      _oracle_fields(bp, [V], False), lambda p: p.v(0, 2))
+    assert_values_close(b2, rb)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_skeleton_two_fields_parity():
+    """test/assembly_tests.jl:407-416: V² = V × V, ∫_Λ jump(u1) jump(v2): one non-zero field block, all of them stored"""
+    mesh = H.cartesian_mesh((0, 1, 0, 1), (4, 3))
+    _warp(mesh)
+    V = H.lagrange_space(mesh, 1, [1, 3])
+    bp = MF.skeleton_problem([V, V], 2)
+    eng = _engine(bp)
+    pu = [bp.part_index(0, 0), bp.part_index(0, 1)]
+    pv = [bp.part_index(1, 0), bp.part_index(1, 1)]
+    blocks = [(pu[a], pv[b], E.BLOCK_MASS, (-1.0 if a == 0 else 1.0) * (-1.0 if b == 0 else 1.0)) for a in range(2) for b in range(2)]
+    cp, rv, nz = _oracle_matrix(bp, [V, V], mesh, "jump12")
+    eng.matrix_symbolic()
+    gcp, grv = eng.matrix_pattern()
+    assert np.array_equal(gcp, cp) and np.array_equal(grv, rv) and gcp.shape == (2 * V.n_free + 1,)
+    gnz = eng.matrix_numeric_blocks(blocks)
+    assert np.abs(gnz - nz).max() < 1e-13
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reference_tests_through_the_gt_mirror():
+    """test/assembly_tests.jl:366-427 transcribed: jump-jump matrix, V² = V × V products, ∫_Λ jump(v)"""
+    mesh = GT.cartesian_mesh((0, 1, 0, 1), (4, 4))
+    Om, Lam = GT.interior(mesh), GT.skeleton(mesh)
+    Gdiri = GT.boundary(mesh, group_names=["1-face-1", "1-face-3"])
+    V = GT.lagrange_space(Om, 1, dirichlet_boundary=Gdiri)
+    dO, dL = GT.measure(Om, 2), GT.measure(Lam, 2)
+    jump = lambda u, p: u[2](p) - u[1](p)
+    A = GT.assemble_matrix(lambda u, v: GT.integrate(lambda p: jump(u, p) * jump(v, p), dL), float, V, V)
+    assert A.m == V.num_free_dofs() and A.n == V.num_free_dofs() and np.abs(A.nzval).max() < 1e-14
+    V2 = V * V
+    a2 = lambda u, v: GT.integrate(lambda q: (v[0](q) + v[1](q)) * (u[0](q) + u[1](q)), dO)
+    A2, cache = GT.assemble_matrix(a2, float, V2, V2, reuse=True)
+    assert A2.m == 2 * V.num_free_dofs()
+    M = GT.assemble_matrix(lambda u, v: GT.integrate(lambda q: u(q) * v(q), dO), float, V, V)
+    S = A2.to_scipy()
+    n = V.num_free_dofs()
+    for i in range(2):
+        for j in range(2):
+            assert abs(S[i * n:(i + 1) * n, j * n:(j + 1) * n] - M.to_scipy()).max() < 1e-15
+    before = A2.nzval.copy()
+    GT.update_matrix(A2, cache)
+    assert np.array_equal(before, A2.nzval)
+    cache.engine.close()
+    b = GT.assemble_vector(lambda v: GT.integrate(lambda p: jump(v, p), dL), float, V)
+    assert b.shape == (n,) and sum(b) + 1 == pytest.approx(1.0, abs=1e-13)
+    with pytest.raises(GT.UnsupportedFormError):      # no CPU fallback for what the block kernels do not cover
+        GT.assemble_matrix(lambda u, v: GT.integrate(lambda p: GT.dot(GT.grad(u[1], p), GT.grad(v[2], p)), dL), float, V, V)
+
+
+@pytest.mark.gpu
+def test_gpu_stokes_lid_driven_cavity_solves():
+    """docs/src/src_jl/example_stokes.jl at 6 x 6: the assembled saddle-point system is solvable (one pressure dof pinned) and the
+    discrete velocity is divergence-free against every pressure test function"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    mesh = GT.cartesian_mesh((0, 1, 0, 1), (6, 6))
+    Om = GT.interior(mesh)
+    V = GT.lagrange_space(Om, 2, dirichlet_boundary=GT.boundary(mesh), tensor_size=(2,))
+    Q = GT.lagrange_space(Om, 1)
+    X = V * Q
+    dO = GT.measure(Om, 4)
+    a = lambda up, vq: GT.integrate(lambda x: GT.dot(GT.grad(vq[0], x), GT.grad(up[0], x)) - GT.div(vq[0], x) * up[1](x)
+                                    + vq[1](x) * GT.div(up[0], x), dO)
+    A = GT.assemble_matrix(a, float, X, X)
+    Ad = GT.assemble_matrix(a, float, X, X, free_or_dirichlet=(GT.FREE, GT.DIRICHLET))
+    n, m = V.num_free_dofs(), Q.num_free_dofs()
+    assert A.m == n + m and Ad.n == V.num_dirichlet_dofs()
+    # lid velocity (1, 0) on the side y = 1
+    xd = np.zeros(V.num_dirichlet_dofs())
+    Xd = V.data.dirichlet_dof_nodes
+    comp = GT._dof_component(V, False)
+    xd[(np.abs(Xd[:, 1] - 1.0) < 1e-12) & (comp == 0)] = 1.0
+    S = A.to_scipy().tolil()
+    rhs = -(Ad.to_scipy() @ xd)
+    S[n, :] = 0.0; S[:, n] = 0.0; S[n, n] = 1.0; rhs[n] = 0.0          # pin one pressure dof (GT.last_dof() in the example)
+    x = spla.spsolve(sp.csc_matrix(S), rhs)
+    assert np.isfinite(x).all() and np.abs(x[:n]).max() > 1e-2
+    full = A.to_scipy() @ x + Ad.to_scipy() @ xd
+    assert np.abs(np.delete(full, n)).max() < 1e-10
