@@ -19,6 +19,7 @@ index, assembly.jl:584-588), and both also report the FIRST assembly (symbolic +
   unstructured_path   same mesh with the cells in a random order (what a Gmsh mesh hits: element kernel + staged reduction)
   high_order      BASELINE config 3 (Q3 hexahedra 64^3, FP64 tensor cores)
   elasticity      BASELINE config 4 element (P2 x 3 on tetrahedra, Strang degree-4 rule) at 64^3 x 6 tetrahedra
+  multifield      SURVEY §8 f4: Stokes (Q2 x 3 x Q1 product space, 24^3 hexahedra) and ∫_Λ jump(u) jump(v) over the interior faces of 48^3 cells
   config5         BASELINE config 5 at THIS GPU count: 512 x 512 x (512/N) cells per GPU, T_N, T_1 (rank 0 alone, device
                   resident) and the strong-scaling efficiency T_1 / (N T_N)
   cpu_baseline    the C restatement of the reference's CPU path (oracle/, "port") on this box
@@ -379,6 +380,7 @@ def main():
     ap.add_argument("--no-high-order", action="store_true", help="skip the BASELINE config 3 (Q3 hex 64^3, DMMA path) entry")
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 (512^3 over the N GPUs) entry")
     ap.add_argument("--no-elasticity", action="store_true", help="skip the BASELINE config 4 (P2 x 3 elasticity on tetrahedra) entry")
+    ap.add_argument("--no-multifield", action="store_true", help="skip the Stokes (product space) and skeleton-integral entries (SURVEY §8 f4)")
     ap.add_argument("--no-extras", action="store_true", help="headline only: no general/unstructured/high-order/config5/cpu entries")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -386,7 +388,7 @@ def main():
         run_reference(args)
         return
     if args.no_extras:
-        args.no_cpu_baseline = args.no_high_order = args.no_config5 = args.no_elasticity = True
+        args.no_cpu_baseline = args.no_high_order = args.no_config5 = args.no_elasticity = args.no_multifield = True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -702,6 +704,13 @@ def main():
                 line["elasticity"]["cpu_baseline"] = bench_elasticity.cpu_baseline()
         except Exception as exc:   # reported, never hidden
             line["elasticity"] = {"error": f"{type(exc).__name__}: {exc}"}
+    if world == 1 and not args.no_multifield:
+        # a product space (Stokes, Q2 x 3 x Q1) and a skeleton integral through the block kernels
+        try:
+            import bench_multifield
+            line["multifield"] = bench_multifield.run(24, 48, steps=3, warmup=1, device=local_rank)
+        except Exception as exc:   # reported, never hidden
+            line["multifield"] = {"error": f"{type(exc).__name__}: {exc}"}
     if not args.no_config5:
         try:
             c5 = run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream)

@@ -318,6 +318,13 @@ class Engine:
         self._ck(self.lib.gtk_matrix_numeric_blocks(self.h, len(blocks), arr, _ptr(nz)))
         return nz
 
+    def matrix_numeric_blocks_device(self, blocks):
+        blocks = list(blocks)
+        arr = (Block * max(len(blocks), 1))()
+        for k, (pu, pv, form, alpha) in enumerate(blocks):
+            arr[k].part_u, arr[k].part_v, arr[k].form, arr[k].alpha = int(pu), int(pv), int(form), float(alpha)
+        self._ck(self.lib.gtk_matrix_numeric_blocks_device(self.h, len(blocks), arr))
+
     def vector_assemble_blocks(self, vblocks, accumulate: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
         """vblocks: iterable of (part, alpha, f_const)"""
         if self.n_vec_rows == 0:

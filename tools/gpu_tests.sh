@@ -1,4 +1,4 @@
 #!/bin/bash
 # usage: gpu_tests.sh [pytest args]   (default: the whole GPU suite)
 mkdir -p gpurun_out
-timeout 900 python -m pytest ${@:-tests} -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest ${@:-tests} -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/pytest_gpu.log
