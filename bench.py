@@ -270,10 +270,23 @@ def cpu_baseline_high_order(order=3, n=16):
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
-def timed_loop(torch, stream, fn, steps, barrier=None):
+SPIN_MS = float(os.environ.get("GTK_BENCH_SPIN_MS", "60"))   # untimed device work right before every timed region (0 = off)
+
+
+def spin_count(est_ms_per_step):
+    """steps that keep the GPU busy for ~SPIN_MS: the SM clock and the memory system are in their sustained state when the
+    timed region starts (a 20-step region of a 0.12 ms kernel is 2.5 ms long — shorter than the clock ramp after an idle gap)"""
+    return 0 if SPIN_MS <= 0 else max(1, int(SPIN_MS / max(est_ms_per_step, 1e-3)))
+
+
+def timed_loop(torch, stream, fn, steps, barrier=None, spin=0):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(spin):          # untimed; same count on every rank (the fused exchange runs in lockstep)
+        fn()
     if barrier:
         barrier()
+    else:
+        torch.cuda.synchronize()
     ev0.record(stream)
     for _ in range(steps):
         fn()
@@ -325,7 +338,7 @@ def run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, steps=1
         sym_ms = tm["symbolic"] + tm["exchange_plan"] + tm["peer_memory"]
     for _ in range(3):
         step()
-    ms = timed_loop(torch, stream, step, steps, barrier)
+    ms = timed_loop(torch, stream, step, steps, barrier, spin=spin_count(8.0 / world))
     tot = torch.tensor([float(nnz_owned), ms, sym_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         mx = tot.clone()
@@ -356,7 +369,7 @@ def run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, steps=1
             s1 = lambda: e1.assemble_matrix_and_vector_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
             for _ in range(3):
                 s1()
-            t1_ms = timed_loop(torch, stream, s1, steps)
+            t1_ms = timed_loop(torch, stream, s1, steps, spin=spin_count(8.0))
             e1.close()
         t = torch.tensor([t1_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -485,7 +498,7 @@ def main():
         sampler.start()
     barrier()
     sampler.mark_begin()
-    ms_per_step = timed_loop(torch, stream, step, args.steps, barrier)
+    ms_per_step = timed_loop(torch, stream, step, args.steps, barrier, spin=spin_count(0.15))
     sampler.mark_end()
     if rank == 0 and sampler.nv is not None:
         inside = sum(1 for smp in sampler.samples if sampler.t_begin <= smp[0] <= sampler.t_end)
@@ -595,7 +608,7 @@ def main():
         for _ in range(3):
             step()
         gsteps = max(5, min(args.steps, 20))
-        gms = timed_loop(torch, stream, step, gsteps)
+        gms = timed_loop(torch, stream, step, gsteps, spin=spin_count(0.4))
         general = {"mesh": "same topology, interior nodes displaced by 0.2 h U(-1,1) (trilinear, non-affine cells)",
                    "ms_per_step": gms, "value": nnz_total / (gms * 1e-3), "unit": UNIT, "fast_path": eng.info(5),
                    "roofline_frac": alg / (gms * 1e-3) / 1e9 / peak}
@@ -605,7 +618,7 @@ def main():
         eng.update_coordinates(one)
         for _ in range(3):
             step()
-        mms = timed_loop(torch, stream, step, gsteps)
+        mms = timed_loop(torch, stream, step, gsteps, spin=spin_count(0.2))
         mixed = {"mesh": "config 2 with ONE interior node displaced by 0.2 h (8 non-affine cells)", "ms_per_step": mms,
                  "value": nnz_total / (mms * 1e-3), "unit": UNIT, "fast_path": eng.info(5), "roofline_frac": alg / (mms * 1e-3) / 1e9 / peak}
         eng.update_coordinates(mesh.node_coordinates)
@@ -627,7 +640,7 @@ def main():
                 usym_ms = 1e3 * (time.perf_counter() - t0)
                 for _ in range(2):
                     ustep()
-                ums = timed_loop(torch, stream, ustep, 5)
+                ums = timed_loop(torch, stream, ustep, 5, spin=spin_count(1.3))
                 eu.set_profiling(True)
                 ustep()
                 torch.cuda.synchronize()
@@ -659,6 +672,10 @@ def main():
             traffic = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "spin_up": {"ms": SPIN_MS, "untimed_steps": spin_count(0.15),
+                        "what": "untimed repetitions of the same step right before the barrier + synchronize that opens every timed region "
+                                "(after the W warm-up steps), so a region a few ms long is not measured on the clock ramp that follows an "
+                                "idle gap; GTK_BENCH_SPIN_MS=0 switches it off"},
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "partition": "none" if world == 1 else (f"{world} z-slabs of {n}^3 cells generated in HBM, ghost-row sum over " +

@@ -18,16 +18,11 @@ run1() {
 run1 "1gpu default" X=1
 run1 "1gpu smax32" GTK_AFFINE_SMAX=32
 run1 "1gpu smax16" GTK_AFFINE_SMAX=16
-run1 "1gpu gf3" GTK_AFFINE_GF=3
 run "default" X=1
 run "edge6" GTK_FUSED_EDGE_SEG=6
 run "edge12" GTK_FUSED_EDGE_SEG=12
 run "edge22" GTK_FUSED_EDGE_SEG=22
-run "edge12 il4" GTK_FUSED_EDGE_SEG=12 GTK_FUSED_INTERLEAVE=4
 run "edge12 il16" GTK_FUSED_EDGE_SEG=12 GTK_FUSED_INTERLEAVE=16
 run "edge12 bf0.7" GTK_FUSED_EDGE_SEG=12 GTK_FUSED_BOTTOM_FROM=0.7
-run "edge12 bf0.2" GTK_FUSED_EDGE_SEG=12 GTK_FUSED_BOTTOM_FROM=0.2
 run "il16" GTK_FUSED_INTERLEAVE=16
-run "il2" GTK_FUSED_INTERLEAVE=2
-run "bf0.8" GTK_FUSED_BOTTOM_FROM=0.8
 run "skipall(timing only)" GTK_FUSED_DBG_SKIP=7
