@@ -668,7 +668,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
 // one work item of the warp-private affine sweep: the 16 x 2 patch at (i0, j0), node layers [kz0, kz1)
-template <bool TWOPASS>
+template <bool TWOPASS, bool COMM>
 __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, const int j0, const int kz0, const int kz1,
                                               double* __restrict__ OutW, double* __restrict__ CellW, double* __restrict__ XW, const int lane,
                                               unsigned& flags_seen) {
@@ -700,7 +700,7 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
 #pragma unroll
   for (int o = 0; o < 18; ++o) pend[o] = 0.0;
   int4 ncn = make_int4(-1, -1, 0, -1);
-  if (a.comm.on == 2) {   // an item that will add received values: pull their lines towards the SM now (flag first: they must have landed)
+  if constexpr (COMM) if (a.comm.on == 2) {   // an item that will add received values: pull their lines towards the SM now (flag first: they must have landed)
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       if (s >= a.comm.n_peers) break;
@@ -821,7 +821,7 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
 #undef GTK_AFF_CELL
     }
     int snd_off = -1, snd_o0 = 0, snd_peer = 0;
-    if (emit && a.comm.on == 2) {
+    if constexpr (COMM) if (emit && a.comm.on == 2) {
       // ---- exchange fused into the copy-out: ghost rows leave from registers, received partial sums enter them ----
       const int64_t ip = (i0 + li) + s1 * (j0 + lj);               // in-plane node index
 #pragma unroll
@@ -916,7 +916,7 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
         fence_async_smem();
         __syncwarp();
         bulk_pending = false;
-        if (a.comm.on == 2 && __any_sync(0xFFFFFFFFu, snd_off >= 0)) {
+        if constexpr (COMM) if (a.comm.on == 2 && __any_sync(0xFFFFFFFFu, snd_off >= 0)) {
           // ghost rows of the 32 columns: 9 consecutive entries per column in the row just written; lanes walk them as
           // (column, entry) pairs so that one store instruction covers 32 consecutive doubles of the peer's buffer
           // whenever neighbouring columns' runs are adjacent (they are, except across mesh boundaries)
@@ -1054,7 +1054,9 @@ __device__ __forceinline__ void comm_item(const SweepArgs& a, const int4 it, con
 // segment start, the short ones at the end level the finishing times of the ~2200 resident warps — the uniform 6-layer
 // segments of the static grid left a tail of up to one whole item (18 % of a warp's work at 128^3).  Which warp computes an
 // item does not change a single bit of the result (every nonzero is produced by exactly one lane in a fixed order).
-template <int WPB, int MAXREG, bool TWOPASS>
+// COMM = false: the single-GPU instantiation carries none of the exchange code (it costs the layer loop 6 % otherwise:
+// 0.1166 vs 0.124 ms at 128^3)
+template <int WPB, int MAXREG, bool TWOPASS, bool COMM>
 __global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
   using C = WCfg;
   extern __shared__ __align__(16) double sm[];
@@ -1072,9 +1074,21 @@ __global__ void __maxnreg__(MAXREG) k_q1hex_affine_w(SweepArgs a) {
     t = __shfl_sync(0xFFFFFFFFu, t, 0);
     if (t >= (unsigned long long)a.n_items) break;
     const int4 it = __ldg(a.items + t);
-    if (it.z < 0) { comm_item(a, it, lane); continue; }
-    affine_w_item<TWOPASS>(a, it.x, it.y, it.z, it.w, OutW, CellW, XW, lane, flags_seen);
-    if (a.comm.on == 1) {
+    if constexpr (COMM) if (it.z < 0) { comm_item(a, it, lane); continue; }
+    // only the items that hold an exchanged node layer run the body with the exchange code; the bulk of the sweep runs the
+    // same lean body as the single-GPU kernel
+    bool edge = false;
+    if constexpr (COMM) if (a.comm.on == 2) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (s >= a.comm.n_peers) break;
+        const GtkCommPeerDev& q = a.comm.peer[s];
+        edge |= (q.n_recv_nz + q.n_recv_b > 0 && it.z <= q.B && q.B < it.w) || (q.n_send_nz + q.n_send_b > 0 && it.z <= q.T && q.T - 1 < it.w);
+      }
+    }
+    if (COMM && edge) affine_w_item<TWOPASS, COMM>(a, it.x, it.y, it.z, it.w, OutW, CellW, XW, lane, flags_seen);
+    else affine_w_item<TWOPASS, false>(a, it.x, it.y, it.z, it.w, OutW, CellW, XW, lane, flags_seen);
+    if constexpr (COMM) if (a.comm.on == 1) {
       const bool top = it.z >= a.comm.top_layer, bot = it.w <= a.comm.bot_layer;
       if (top || bot) {   // a PUSH / UNPACK item of this launch reads what this item wrote: complete the bulk stores, publish
         bulk_wait_all();
@@ -1443,11 +1457,14 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   using C = WCfg;
   SweepArgs a = a0;
   const size_t smem = sizeof(double) * (size_t)WPB * C::WARP_D;
-  static int occ = 0;   // resident CTAs per SM of this instance (same for every context of the process)
+  static int occ = 0;   // resident CTAs per SM of this instance (same for every context of the process; the smaller of the two bodies)
   if (!occ) {
-    GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_q1hex_affine_w<WPB, MAXREG, TWOPASS>, WPB * 32, smem));
-    if (occ < 1) occ = 1;
+    int o0 = 1, o1 = 1;
+    GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MAXREG, TWOPASS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GTK_CK(cudaFuncSetAttribute(k_q1hex_affine_w<WPB, MAXREG, TWOPASS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_q1hex_affine_w<WPB, MAXREG, TWOPASS, false>, WPB * 32, smem));
+    GTK_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_q1hex_affine_w<WPB, MAXREG, TWOPASS, true>, WPB * 32, smem));
+    occ = std::max(1, std::min(o0, o1));
   }
   layer_range(ctx, p->n3 + 1, &a.z_begin, &a.z_end);
   if (a.z_end <= a.z_begin) return GTK_OK;
@@ -1496,7 +1513,9 @@ int32_t launch_affine_w(gtk_ctx* ctx, FastPlan* p, const SweepArgs& a0) {
   a.items = ip.items; a.n_items = ip.n; a.sched = p->sched; a.sched_base = p->sched_next;
   p->sched_next += (unsigned long long)ip.n + (unsigned long long)blocks * WPB;   // every warp ends on exactly one empty draw
   a.tile_active = nullptr;
-  { GtkProf pr_(ctx, "k_q1hex_affine_w"); k_q1hex_affine_w<WPB, MAXREG, TWOPASS><<<blocks, WPB * 32, smem, ctx->stream>>>(a); }
+  { GtkProf pr_(ctx, "k_q1hex_affine_w");
+    if (fuse) k_q1hex_affine_w<WPB, MAXREG, TWOPASS, true><<<blocks, WPB * 32, smem, ctx->stream>>>(a);
+    else k_q1hex_affine_w<WPB, MAXREG, TWOPASS, false><<<blocks, WPB * 32, smem, ctx->stream>>>(a); }
   GTK_CK(cudaGetLastError());
   gtk_count_launch(ctx);
   return GTK_OK;
@@ -1874,18 +1893,12 @@ int32_t gtk_fastq1_try(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int v
   if ((p->affine_state == 1 || mixed) && !getenv("GTK_DISABLE_AFFINE")) {
     const char* var = getenv("GTK_AFFINE_VARIANT");
     switch (var ? atoi(var) : 0) {
+      // (variants 7, 8, 12-17 of profiles/r02_tune_affine.txt — other warp counts / register caps, all measured slower or equal —
+      //  were removed after the tuning round to keep the build short)
       case 6: rc = launch_affine_w<3, 168, false>(ctx, p, a); break;
-      case 7: rc = launch_affine_w<6, 168, false>(ctx, p, a); break;
-      case 8: rc = launch_affine_w<2, 168, false>(ctx, p, a); break;
       case 9: rc = launch_affine_w<4, 168, true>(ctx, p, a); break;
       case 10: rc = launch_affine_w<5, 128, true>(ctx, p, a); break;
       case 11: rc = launch_affine_w<4, 168, false>(ctx, p, a); break;
-      case 12: rc = launch_affine_w<4, 152, false>(ctx, p, a); break;
-      case 13: rc = launch_affine_w<5, 168, false>(ctx, p, a); break;
-      case 14: rc = launch_affine_w<4, 192, false>(ctx, p, a); break;
-      case 15: rc = launch_affine_w<2, 200, false>(ctx, p, a); break;
-      case 16: rc = launch_affine_w<4, 160, true>(ctx, p, a); break;
-      case 17: rc = launch_affine_w<8, 168, false>(ctx, p, a); break;
       case 1: rc = launch_affine_w<3, 136, true>(ctx, p, a); break;    // round-1 default (static grid: 127 registers, 5 CTAs/SM)
       // persistent warps no longer need occupancy to hide the tail: the single-pass body with all 45 accumulators live
       // (168 registers, 3 CTAs x 4 warps per SM) wins — 0.1166 vs 0.1244 ms at 128^3 (profiles/r02_tune_affine.txt)
