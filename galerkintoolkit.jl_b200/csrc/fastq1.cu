@@ -589,7 +589,9 @@ __global__ void k_and_tiles(const uint8_t* __restrict__ active, const int* __res
 //   Ke[I][J] = sum_a  s_a 2^(eq_u+eq_v) A_a  +  sum_{a<b, eq_a == eq_b}  t_ab 2^(eq_c) B_ab
 //   eq_d = (I_d == J_d),  s_a = +1 if eq_a else -1,  t_ab = (eq_a ? +1 : -1) sgn(J_a) sgn(J_b),  sgn(bit) = bit ? +1 : -1
 // (exact integrals of the products of reference gradients over the 2x2x2 Gauss rule: 2/3 and 1/3 per direction)
-template <int J, int I>
+// ORTHO: the cell's edge vectors are mutually orthogonal (B01 = B02 = B12 = 0 exactly — every cell of GT.cartesian_mesh):
+// the three mixed terms are skipped, which adds exactly nothing.
+template <int J, int I, bool ORTHO = false>
 __device__ __forceinline__ void affine_entry(const double (&c)[6], double& acc) {
   constexpr int x = I ^ J;
   constexpr bool e0 = !(x & 1), e1 = !(x & 2), e2 = !(x & 4);
@@ -600,9 +602,11 @@ __device__ __forceinline__ void affine_entry(const double (&c)[6], double& acc) 
   acc = fma(k0, c[0], acc);
   acc = fma(k1, c[1], acc);
   acc = fma(k2, c[2], acc);
-  if constexpr (e0 == e1) acc = fma((e0 ? 1.0 : -1.0) * j0 * j1 * double(1 << int(e2)), c[3], acc);
-  if constexpr (e0 == e2) acc = fma((e0 ? 1.0 : -1.0) * j0 * j2 * double(1 << int(e1)), c[4], acc);
-  if constexpr (e1 == e2) acc = fma((e1 ? 1.0 : -1.0) * j1 * j2 * double(1 << int(e0)), c[5], acc);
+  if constexpr (!ORTHO) {
+    if constexpr (e0 == e1) acc = fma((e0 ? 1.0 : -1.0) * j0 * j1 * double(1 << int(e2)), c[3], acc);
+    if constexpr (e0 == e2) acc = fma((e0 ? 1.0 : -1.0) * j0 * j2 * double(1 << int(e1)), c[4], acc);
+    if constexpr (e1 == e2) acc = fma((e1 ? 1.0 : -1.0) * j1 * j2 * double(1 << int(e0)), c[5], acc);
+  }
 }
 
 // neighbour-offset index of row node I seen from column node J (both local to one cell)
@@ -612,9 +616,9 @@ __host__ __device__ constexpr int off_index() {
 }
 
 // all 8 rows of column node J of one cell; dst is indexed by the neighbour offset
-template <int J, int... I>
+template <int J, bool ORTHO = false, int... I>
 __device__ __forceinline__ void affine_column(const double (&c)[6], double* dst, std::integer_sequence<int, I...>) {
-  (affine_entry<J, I>(c, dst[off_index<J, I>()]), ...);
+  (affine_entry<J, I, ORTHO>(c, dst[off_index<J, I>()]), ...);
 }
 
 template <int O>
@@ -761,6 +765,7 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
     // ---- A) cells of layer L ----
     __syncwarp();                                      // node phase of the previous step has read CellW; node layers L, L+1 visible
     prefetch_nodes(L + 2, s2r);                        // lands during this step; its slot held layer L-1
+    bool my_ortho = true;
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       if (cok[p]) {
@@ -789,13 +794,14 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
           cs[4] = so * (r0[0] * r2[0] + r0[1] * r2[1] + r0[2] * r2[2]);
           cs[5] = so * (r1[0] * r2[0] + r1[1] * r2[1] + r1[2] * r2[2]);
           cs[6] = a.fscale * (q1hex::W8 * ad);
+          my_ortho = my_ortho && cs[3] == 0.0 && cs[4] == 0.0 && cs[5] == 0.0;
         } else {
 #pragma unroll
           for (int e = 0; e < C::CSTR; ++e) cs[e] = 0.0;
         }
       }
     }
-    __syncwarp();
+    const bool ortho = __all_sync(0xFFFFFFFFu, my_ortho);   // (also the barrier between the cell and the node phase)
     // ---- B) this lane's node: two passes over its 4 cells keep the live registers low (27 accumulators at a time) ----
     using Rows = std::make_integer_sequence<int, 8>;
     double acc[27], accb = pendb;
@@ -809,15 +815,16 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
       pendb = 0.0;
     }
     if (emit || !TWOPASS) {   // bottom role: finishes node layer L (cells in increasing cell id: v outer, u inner)
-#define GTK_AFF_CELL(U, V)                                                               \
+#define GTK_AFF_CELL(U, V, ORT)                                                          \
       {                                                                                    \
         const double* cc = cl + ((U) + C::CX * (V)) * C::CSTR;                             \
-        const double c6[6] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5]};                   \
+        const double c6[6] = {cc[0], cc[1], cc[2], (ORT) ? 0.0 : cc[3], (ORT) ? 0.0 : cc[4], (ORT) ? 0.0 : cc[5]}; \
         constexpr int JB = (1 - (U)) + 2 * (1 - (V));                                      \
-        if (emit) { affine_column<JB>(c6, acc, Rows{}); accb += cc[6]; }                   \
-        if constexpr (!TWOPASS) { affine_column<JB + 4>(c6, pend, Rows{}); pendb += cc[6]; }   /* top role in the same pass */ \
+        if (emit) { affine_column<JB, ORT>(c6, acc, Rows{}); accb += cc[6]; }              \
+        if constexpr (!TWOPASS) { affine_column<JB + 4, ORT>(c6, pend, Rows{}); pendb += cc[6]; }   /* top role in the same pass */ \
       }
-      GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
+      if (ortho) { GTK_AFF_CELL(0, 0, true) GTK_AFF_CELL(1, 0, true) GTK_AFF_CELL(0, 1, true) GTK_AFF_CELL(1, 1, true) }
+      else { GTK_AFF_CELL(0, 0, false) GTK_AFF_CELL(1, 0, false) GTK_AFF_CELL(0, 1, false) GTK_AFF_CELL(1, 1, false) }
 #undef GTK_AFF_CELL
     }
     int snd_off = -1, snd_o0 = 0, snd_peer = 0;
@@ -956,14 +963,15 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
 #pragma unroll
       for (int o = 0; o < 18; ++o) pend[o] = 0.0;
       pendb = 0.0;
-#define GTK_AFF_CELL(U, V)                                                               \
+#define GTK_AFF_CELL(U, V, ORT)                                                          \
       {                                                                                    \
         const double* cc = cl + ((U) + C::CX * (V)) * C::CSTR;                             \
-        const double c6[6] = {cc[0], cc[1], cc[2], cc[3], cc[4], cc[5]};                   \
-        affine_column<(1 - (U)) + 2 * (1 - (V)) + 4>(c6, pend, Rows{});                    \
+        const double c6[6] = {cc[0], cc[1], cc[2], (ORT) ? 0.0 : cc[3], (ORT) ? 0.0 : cc[4], (ORT) ? 0.0 : cc[5]}; \
+        affine_column<(1 - (U)) + 2 * (1 - (V)) + 4, ORT>(c6, pend, Rows{});               \
         pendb += cc[6];                                                                    \
       }
-      GTK_AFF_CELL(0, 0) GTK_AFF_CELL(1, 0) GTK_AFF_CELL(0, 1) GTK_AFF_CELL(1, 1)
+      if (ortho) { GTK_AFF_CELL(0, 0, true) GTK_AFF_CELL(1, 0, true) GTK_AFF_CELL(0, 1, true) GTK_AFF_CELL(1, 1, true) }
+      else { GTK_AFF_CELL(0, 0, false) GTK_AFF_CELL(1, 0, false) GTK_AFF_CELL(0, 1, false) GTK_AFF_CELL(1, 1, false) }
 #undef GTK_AFF_CELL
     }
     cp_async_wait_all();       // node layer L+2 has landed (this lane's part; the __syncwarp of the next step publishes it)

@@ -86,6 +86,37 @@ def _graded(mesh, cells):
     return mesh
 
 
+@pytest.mark.parametrize("cells,bc", [((16, 8, 8), "boundary"), ((8, 8, 4), [1, 6])])
+def test_affine_kernel_on_sheared_meshes(cells, bc):
+    """A global shear with dyadic factors keeps every cell an exact parallelepiped with NON-orthogonal edges: the affine kernel
+    must take its full six-coefficient branch (the three mixed terms B01, B02, B12 are non-zero), not the orthogonal-cell
+    shortcut a Cartesian mesh takes."""
+    mesh, V, tab = problem(cells, bc=bc)
+    X = mesh.node_coordinates
+    X[:, 0] += 0.5 * X[:, 1] + 0.25 * X[:, 2]
+    X[:, 1] += 0.5 * X[:, 2]
+    colptr, rowval, nzval = oracle_matrix(O.LAPLACE, mesh, V, tab, alpha=1.25)
+    b_ref = oracle_vector(O.SOURCE_CONST, mesh, V, tab, f_const=[2.0])
+    eng = make_engine(mesh, V, tab)
+    eng.matrix_symbolic()
+    nz, b = eng.assemble_matrix_and_vector(E.FORM_LAPLACE, dict(alpha=1.25), E.FORM_SOURCE_CONST, dict(f_const=[2.0]))
+    assert eng.info(5) == 2, "a dyadic shear keeps the cells exactly affine"
+    assert_values_close(nz, nzval)
+    assert_values_close(b, b_ref)
+    # half of the mesh sheared, the other half Cartesian: warps see orthogonal and non-orthogonal layers / patches side by side
+    mesh2, V2, tab2 = problem(cells, bc=bc)
+    Y = mesh2.node_coordinates
+    upper = Y[:, 2] >= 0.5
+    Y[upper, 0] += 0.5 * (Y[upper, 2] - 0.5)
+    ref2 = oracle_matrix(O.LAPLACE, mesh2, V2, tab2, alpha=1.25)
+    eng2 = make_engine(mesh2, V2, tab2)
+    eng2.matrix_symbolic()
+    nz2 = eng2.matrix_numeric(E.FORM_LAPLACE, alpha=1.25)
+    assert eng2.info(5) == 2
+    assert_values_close(nz2, ref2[2])
+    eng.close(); eng2.close()
+
+
 @pytest.mark.parametrize("cells,bc", [((18, 9, 11), "boundary"), ((7, 5, 6), None), ((33, 17, 20), [2, 3])])
 def test_affine_kernel_on_graded_and_mixed_meshes(cells, bc):
     mesh, V, tab = problem(cells, bc=bc)
