@@ -109,35 +109,37 @@ __global__ void __launch_bounds__(128) k_elem_blocks(BlockArgs a) {
     const int form = a.b_form[pu][pv];
     const int64_t cell = cell0 + cl;
     double acc = 0.0;
-    if (form != GTK_BLOCK_ZERO && cell >= a.act0 && cell < a.act1) {
+    const int ru = r - a.p_off[pu], cv = c - a.p_off[pv];
+    const int ncu = a.p_ncomp[pu], ncv = a.p_ncomp[pv];
+    const int ra = ru / ncu, ri = ru - ra * ncu;
+    const int ca = cv / ncv, cj = cv - ca * ncv;
+    // component-wise forms couple equal components only: the other entries of the block are (stored) zeros
+    const bool off_component = (form == GTK_BLOCK_MASS || form == GTK_BLOCK_LAPLACE) && ri != cj;
+    if (form != GTK_BLOCK_ZERO && !off_component && cell >= a.act0 && cell < a.act1) {
       const double alpha = a.b_alpha[pu][pv];
-      const int ru = r - a.p_off[pu], cv = c - a.p_off[pv];
-      const int ncu = a.p_ncomp[pu], ncv = a.p_ncomp[pv];
-      const int ra = ru / ncu, ri = ru - ra * ncu;
-      const int ca = cv / ncv, cj = cv - ca * ncv;
       const int nlu = a.p_nls[pu], nlv = a.p_nls[pv];
       const double* Nu = a.p_N[pu] + (size_t)variant_of(a, cell, pu) * nq * nlu + ra;
       const double* Nv = a.p_N[pv] + (size_t)variant_of(a, cell, pv) * nq * nlv + ca;
-      for (int q = 0; q < nq; ++q) {
-        const double* gq = G + ((size_t)(cl * nq + q) * a.nls_total) * D;
-        const double* gu = gq + (size_t)(a.p_goff[pu] + ra) * D;
-        const double* gv = gq + (size_t)(a.p_goff[pv] + ca) * D;
-        double v = 0.0;
-        if (form == GTK_BLOCK_MASS) {
-          if (ri == cj) v = alpha * (Nu[q * nlu] * Nv[q * nlv]);
-        } else if (form == GTK_BLOCK_LAPLACE) {
-          if constexpr (D == d) if (ri == cj) {
+      // one loop per form (the form is fixed per entry): Σ_q (alpha * integrand) * dV in the reference's order
+      const double* dv = dV + cl * nq;
+      const size_t gstride = (size_t)a.nls_total * D;
+      const double* gu = G + (size_t)cl * nq * gstride + (size_t)(a.p_goff[pu] + ra) * D;
+      const double* gv = G + (size_t)cl * nq * gstride + (size_t)(a.p_goff[pv] + ca) * D;
+      if (form == GTK_BLOCK_MASS) {
+        for (int q = 0; q < nq; ++q) acc += (alpha * (Nu[q * nlu] * Nv[q * nlv])) * dv[q];
+      } else if constexpr (D == d) {
+        if (form == GTK_BLOCK_LAPLACE) {
+          for (int q = 0; q < nq; ++q, gu += gstride, gv += gstride) {
             double dt = gv[0] * gu[0];
 #pragma unroll
             for (int k = 1; k < D; ++k) dt += gv[k] * gu[k];
-            v = alpha * dt;
+            acc += (alpha * dt) * dv[q];
           }
         } else if (form == GTK_BLOCK_VALU_DIVV) {       // u(x) * div(v)(x): u scalar part, v vector part
-          if constexpr (D == d) v = alpha * (gv[cj] * Nu[q * nlu]);
+          for (int q = 0; q < nq; ++q, gv += gstride) acc += (alpha * (gv[cj] * Nu[q * nlu])) * dv[q];
         } else if (form == GTK_BLOCK_DIVU_VALV) {       // v(x) * div(u)(x): v scalar part, u vector part
-          if constexpr (D == d) v = alpha * (Nv[q * nlv] * gu[ri]);
+          for (int q = 0; q < nq; ++q, gu += gstride) acc += (alpha * (Nv[q * nlv] * gu[ri])) * dv[q];
         }
-        acc += v * dV[cl * nq + q];
       }
     }
     a.out[cell * (int64_t)L2 + rem] = acc;
