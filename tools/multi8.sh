@@ -1,10 +1,14 @@
 #!/bin/bash
-# 8 GPUs: weak-scaling bench line (8 x 128^3) and BASELINE config 5 itself (512^3 cells = 8 z-slabs of 512x512x64)
+# 8 GPUs: the multi-rank parity tests, then the bench line the driver's scaling run produces at N = 8 (weak 8 x 128^3 headline
+# + the config5 object: 512^3 cells as 8 z-slabs with T_1 measured in the same job)
 mkdir -p gpurun_out
-nvidia-smi -L | head -8
-free -g | head -2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 50 --warmup 5 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; echo "bench n8 rc=$?"
-tail -c 1800 gpurun_out/bench_n8.json
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --steps 20 --warmup 3 --cells 512,512,64 > gpurun_out/bench_config5_n8.json 2> gpurun_out/bench_config5_n8.err; echo "config5 rc=$?"
-tail -c 1800 gpurun_out/bench_config5_n8.json
-tail -3 gpurun_out/bench_config5_n8.err
+N=${1:-8}
+timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/pytest_multi$N.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_multi$N.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench n$N rc=$?"
+python - <<PY
+import json
+d=json.loads([l for l in open("gpurun_out/bench_n$N.json") if l.startswith("{")][-1])
+print({k:d.get(k) for k in ("value","ms_per_step","symbolic_ms","e2e","partition")})
+print(json.dumps(d.get("config5"))[:1500])
+PY
+tail -3 gpurun_out/bench_n$N.err
