@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgtkasm.so")
-SOURCES = ["gtk_api.cu", "symbolic.cu", "numeric.cu", "fastq1.cu", "elemgemm.cu", "matvec.cu", "comm.cu", "field.cu", "cartesian.cu", "blocks.cu"]
+SOURCES = ["gtk_api.cu", "symbolic.cu", "numeric.cu", "fastq1.cu", "elemgemm.cu", "matvec.cu", "comm.cu", "field.cu", "cartesian.cu", "blocks.cu", "matsum.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-deprecated-declarations", "-Wno-deprecated-declarations",
               "--expt-relaxed-constexpr"]

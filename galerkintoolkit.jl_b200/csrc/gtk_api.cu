@@ -104,6 +104,7 @@ int32_t gtk_destroy(gtk_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   gtk_comm_release(ctx);
   gtk_parts_release(ctx);
+  gtk_sumplan_release(ctx);
   gtk_release_all_matrices(ctx);
   gtk_vecsym_release(ctx);
   for (auto& sl : ctx->slots) { gtk_cuda_free(ctx, sl.nzval); sl.nzval = nullptr; }
@@ -257,6 +258,7 @@ int32_t gtk_matrix_symbolic(gtk_ctx* ctx, int32_t rfd, int32_t cfd, int64_t* nnz
   if (!ctx->cell_dofs) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_symbolic: set mesh and space first");
   GTK_CK(cudaSetDevice(ctx->device));
   gtk_fastq1_release(ctx);
+  gtk_sumplan_release(ctx);
   int32_t rc = gtk_symbolic_matrix_impl(ctx, rfd, cfd);
   if (rc) return rc;
   if (nnz_out) *nnz_out = ctx->ms.nnz;

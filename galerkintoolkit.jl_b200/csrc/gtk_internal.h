@@ -182,6 +182,7 @@ struct gtk_ctx {
   void* comm = nullptr;   // ncclComm_t
   int rank = 0, n_ranks = 1;
   void* ghost = nullptr;  // GhostPlan*
+  void* sumplan = nullptr;   // SumPlan* (matsum.cu): this context holds the merged matrix of a sum of integrals
   void* parts = nullptr;  // PartsState* (blocks.cu): parts of a product space / skeleton integral; replaces N / dN
 };
 
@@ -245,6 +246,9 @@ int32_t gtk_upload_coefficient(gtk_ctx* ctx, int form, const gtk_form_params* p,
 int32_t gtk_numeric_both_impl(gtk_ctx* ctx, int mform, const gtk_form_params* pm, int vform,
                               const gtk_form_params* pv);
 int32_t gtk_scalar_impl(gtk_ctx* ctx, int kind, const gtk_form_params* p, double* out);
+
+// ---- matsum.cu ----
+void gtk_sumplan_release(gtk_ctx* ctx);
 
 // ---- blocks.cu ----
 void gtk_parts_release(gtk_ctx* ctx);       // mesh / space / manifold dimension changed: the part tables are void

@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "gtk_set_cartesian_q1_problem", "gtk_copy_device_array", "gtk_matrix_pattern_i64",
     "gtk_set_parts", "gtk_matrix_numeric_blocks", "gtk_matrix_numeric_blocks_device",
     "gtk_vector_assemble_blocks", "gtk_vector_assemble_blocks_device",
+    "gtk_matrix_sum_symbolic", "gtk_matrix_sum_numeric", "gtk_matrix_sum_numeric_device",
 ]
 BLOCK_ZERO, BLOCK_MASS, BLOCK_LAPLACE, BLOCK_VALU_DIVV, BLOCK_DIVU_VALV = 0, 1, 2, 3, 4
 MAX_PARTS = 8
@@ -141,6 +142,9 @@ def load_library() -> C.CDLL:
         "gtk_matrix_numeric_blocks_device": (i32, [vp, i32, C.POINTER(Block)]),
         "gtk_vector_assemble_blocks": (i32, [vp, i32, C.POINTER(VBlock), i32, vp]),
         "gtk_vector_assemble_blocks_device": (i32, [vp, i32, C.POINTER(VBlock), i32]),
+        "gtk_matrix_sum_symbolic": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
+        "gtk_matrix_sum_numeric": (i32, [vp, i32, C.POINTER(vp), vp]),
+        "gtk_matrix_sum_numeric_device": (i32, [vp, i32, C.POINTER(vp)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -324,6 +328,22 @@ class Engine:
         for k, (pu, pv, form, alpha) in enumerate(blocks):
             arr[k].part_u, arr[k].part_v, arr[k].form, arr[k].alpha = int(pu), int(pv), int(form), float(alpha)
         self._ck(self.lib.gtk_matrix_numeric_blocks_device(self.h, len(blocks), arr))
+
+    # -- sums of integrals over different domains: this context holds the merged matrix ------------
+    def matrix_sum_symbolic(self, sources) -> int:
+        """union pattern of the matrices assembled by the `sources` engines (same row / column selection)"""
+        arr = (C.c_void_p * len(sources))(*[e.h.value for e in sources])
+        nnz = C.c_int64(0)
+        self._ck(self.lib.gtk_matrix_sum_symbolic(self.h, len(sources), arr, C.byref(nnz)))
+        self.nnz, self.n_rows, self.n_cols = nnz.value, sources[0].n_rows, sources[0].n_cols
+        self._n_free, self._n_diri = sources[0]._n_free, sources[0]._n_diri
+        return self.nnz
+
+    def matrix_sum_numeric(self, sources, out: Optional[np.ndarray] = None) -> np.ndarray:
+        arr = (C.c_void_p * len(sources))(*[e.h.value for e in sources])
+        nz = np.empty(self.nnz, dtype=np.float64) if out is None else out
+        self._ck(self.lib.gtk_matrix_sum_numeric(self.h, len(sources), arr, _ptr(nz)))
+        return nz
 
     def vector_assemble_blocks(self, vblocks, accumulate: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
         """vblocks: iterable of (part, alpha, f_const)"""

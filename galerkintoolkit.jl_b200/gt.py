@@ -710,6 +710,47 @@ def _assemble_vector_blocks(l, V, reuse, free_or_dirichlet, engine):
     return b
 
 
+def _assemble_matrix_sum(contributions, U, V, reuse, free_or_dirichlet, index_type):
+    """a(u,v) = ∫_Ω … + ∫_Γ … + ∫_Λ …: the reference pushes every contribution into one COO allocation and compresses once
+    (problems.jl:319-350).  One engine context per integral (its own integration faces), merged on the device
+    (gtk_matrix_sum_*): union pattern, values summed in the order of the contributions."""
+    parts = []
+    try:
+        for term, meas, scale in contributions:
+            if _is_blocks_case(V, meas):
+                eng, bp = _setup_block_engine(V, meas)
+                blocks = [(pu, pv, form, alpha * scale) for (pu, pv, form, alpha) in recognise_blocks(term, bp, meas.domain.kind == "skeleton")]
+                run = (lambda e=eng, b=blocks: e.matrix_numeric_blocks_device(b))
+            else:
+                form, params = recognise_bilinear(term, V, meas)
+                if meas.domain.kind == "boundary" and form != _eng.FORM_MASS:
+                    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "on a boundary measure only ∫_Γ u v dΓ (Robin term) is assembled by the GPU engine")
+                if "field" in params:
+                    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "forms with parameters are assembled one integral at a time on the GPU path")
+                params["alpha"] = params.get("alpha", 1.0) * scale
+                eng = _setup_engine(V, meas)
+                run = (lambda e=eng, f=form, p=params: e.matrix_numeric_device(f, **p))
+            parts.append((eng, run))
+            eng.matrix_symbolic(*free_or_dirichlet)
+            run()
+        total = _eng.Engine(_default_device)
+        sources = [e for e, _ in parts]
+        total.matrix_sum_symbolic(sources)
+        colptr, rowval = total.matrix_pattern_i64() if index_type in (int, np.int64) else total.matrix_pattern()
+        nzval = total.matrix_sum_numeric(sources)
+    except Exception:
+        for e, _ in parts:
+            e.close()
+        raise
+    A = SparseMatrixCSC(total.n_rows, total.n_cols, colptr, rowval, nzval)
+    if reuse:
+        return A, AssemblyCache(total, "sum", dict(parts=parts), "matrix")
+    for e, _ in parts:
+        e.close()
+    total.close()
+    return A
+
+
 def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, parameters=(),
                     free_or_dirichlet=(FREE, FREE), engine: Optional[_eng.Engine] = None, assembly_options=None):
     """GT.assemble_matrix(a, T, U, V; reuse, free_or_dirichlet) (problems.jl:319-350).
@@ -726,6 +767,13 @@ def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, 
         if opts.pop("eltype", np.float64) not in (float, np.float64) or opts or parameters:
             raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "assembly_options / parameters not supported for product spaces on the GPU engine")
         return _assemble_matrix_blocks(a, U, V, reuse, free_or_dirichlet, engine, index_type)
+    if len(probe.contributions) > 1:
+        # a sum of integrals, possibly over different domains: one context per integral, merged on the device
+        opts = dict(assembly_options or {})
+        index_type = opts.pop("index_type", np.int32)
+        if opts.pop("eltype", np.float64) not in (float, np.float64) or opts or parameters or engine is not None:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "assembly_options / parameters / engine are not supported for sums of integrals on the GPU engine")
+        return _assemble_matrix_sum(probe.contributions, U, V, reuse, free_or_dirichlet, index_type)
     term, meas, scale = _single_contribution(probe)
     form, params = recognise_bilinear(term, V, meas)
     if meas.domain.kind == "boundary" and form != _eng.FORM_MASS:
@@ -753,6 +801,11 @@ def update_matrix(A: SparseMatrixCSC, cache: AssemblyCache, parameters=(), **new
     DiscreteField in `parameters` replaces the one the form was recognised with."""
     if cache.form == "blocks":
         cache.engine.matrix_numeric_blocks(cache.params["blocks"], out=A.nzval)
+        return A
+    if cache.form == "sum":
+        for _, run in cache.params["parts"]:
+            run()
+        cache.engine.matrix_sum_numeric([e for e, _ in cache.params["parts"]], out=A.nzval)
         return A
     cache.params.update(new_params)
     if parameters:

@@ -264,6 +264,21 @@ typedef struct gtk_vblock { int32_t part; double alpha; double f_const[3]; } gtk
 int32_t gtk_vector_assemble_blocks(gtk_ctx* ctx, int32_t n, const gtk_vblock* vblocks, int32_t accumulate, double* b);
 int32_t gtk_vector_assemble_blocks_device(gtk_ctx* ctx, int32_t n, const gtk_vblock* vblocks, int32_t accumulate);
 
+/* ---- sums of integrals over different domains in ONE matrix --------------------------------------------------------- */
+/* a(u,v) = ∫_Ω … dΩ + ∫_Γ … dΓ + ∫_Λ … dΛ: the reference lets every contribution of the form push into the same COO
+ * allocation and compresses once (problems.jl:319-350), so the matrix has the UNION pattern and, per stored entry, the sum of
+ * all triplets.  The engine assembles one integral per context (each has its own integration faces: cells, boundary faces,
+ * interior faces); `ctx` (a context of its own, on the same GPU, no mesh needed) then holds the merged matrix:
+ *   gtk_matrix_sum_symbolic  union colptr / rowval of the sources' patterns (same row / column selection and sizes) and, per
+ *                            source, the position of each of its nonzeros in the union; afterwards gtk_matrix_pattern[_i64],
+ *                            gtk_copy_nzval, gtk_device_pointer, gtk_select_matrix / gtk_matvec_add work on `ctx` as usual;
+ *   gtk_matrix_sum_numeric   nzval = Σ_k nzval_k in the order of `src` (call after the sources' numeric assemblies; re-callable:
+ *                            update_matrix!).  No float atomics; per entry the sum is (Σ integral 1) + (Σ integral 2) + …,
+ *                            the reference adds the later integrals' triplets one by one instead (O(1e-16) relative apart). */
+int32_t gtk_matrix_sum_symbolic(gtk_ctx* ctx, int32_t n, gtk_ctx** src, int64_t* nnz_out);
+int32_t gtk_matrix_sum_numeric(gtk_ctx* ctx, int32_t n, gtk_ctx** src, double* nzval);
+int32_t gtk_matrix_sum_numeric_device(gtk_ctx* ctx, int32_t n, gtk_ctx** src);
+
 /* ---- device-resident results -------------------------------------------------- */
 /* which: 0 nzval (double[nnz]) 1 b (double[n_rows]) 2 colptr (int64[n_cols+1], 0-based)
  *        3 rowval (int32[nnz], 1-based) 4 field free values (double[n_free]) 5 field Dirichlet values (double[n_dirichlet])

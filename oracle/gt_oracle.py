@@ -1193,7 +1193,7 @@ def frobenius(a, b):
 
 
 def assemble_matrix_multifield(D, coords, face_nodes, face_tab, sides, fields, integrand, alpha=1.0,
-                               free_or_dirichlet=(FREE, FREE), cell_geometry=None):
+                               free_or_dirichlet=(FREE, FREE), cell_geometry=None, return_coo=False):
     """generate_matrix_assembly_template (compiler.jl:1826-1923) + MonolithicAssemblyAllocation (assembly.jl:386-416)
     + contribute!(::MatrixAllocation) (:189-208) + compress (:571-575), loop for loop.
 
@@ -1269,7 +1269,18 @@ def assemble_matrix_multifield(D, coords, face_nodes, face_tab, sides, fields, i
                                 I.append(off_i[f2] + (di if fr == FREE else -di))
                                 J.append(off_j[f1] + (dj if fcn == FREE else -dj))
                                 V.append(blk[i, j])
+    if return_coo:      # the triplets as pushed: a sum of integrals concatenates them before ONE compress (problems.jl:319-350)
+        return np.array(I, dtype=np.int64), np.array(J, dtype=np.int64), np.array(V)
     return sparse_csc(np.array(I, dtype=np.int64), np.array(J, dtype=np.int64), np.array(V), sum(n_rows_f), sum(n_cols_f))
+
+
+def assemble_matrix_sum(coo_list, m, n):
+    """assemble_matrix over a sum of integrals (problems.jl:319-350): every contribution pushes its triplets into the same COO
+    allocation, in the order of the sum; one compress."""
+    I = np.concatenate([np.asarray(c[0], dtype=np.int64) for c in coo_list])
+    J = np.concatenate([np.asarray(c[1], dtype=np.int64) for c in coo_list])
+    V = np.concatenate([np.asarray(c[2], dtype=np.float64) for c in coo_list])
+    return sparse_csc(I, J, V, m, n)
 
 
 def assemble_vector_multifield(D, coords, face_nodes, face_tab, sides, fields, integrand, alpha=1.0, free_or_dirichlet=FREE):

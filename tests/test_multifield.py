@@ -375,3 +375,74 @@ def test_gpu_stokes_lid_driven_cavity_solves():
     assert np.isfinite(x).all() and np.abs(x[:n]).max() > 1e-2
     full = A.to_scipy() @ x + Ad.to_scipy() @ xd
     assert np.abs(np.delete(full, n)).max() < 1e-10
+
+
+# ---- sums of integrals over different domains in ONE matrix (gtk_matrix_sum_*) ------------------------------------------
+def _volume_coo(form, mesh, V, degree, alpha=1.0):
+    tab = H.measure_tabulation(V, degree)
+    be = O.element_matrices(form, mesh.node_coordinates, mesh.cell_nodes, dict(w=tab.w, N=tab.N, dN=tab.dN, M=tab.M, dM=tab.dM),
+                            n_comp=V.n_comp, alpha=alpha)
+    return O.coo_matrix(be, V.cell_dofs, V.cell_dofs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells", [(4, 4), (3, 2, 2)])
+def test_gpu_sum_of_integrals_over_three_domains(cells):
+    """test/assembly_tests.jl:366-403: a(u,v) = ∫_Ω u v + ∫_Γ u v + ∫_Λ jump(u) jump(v) assembled as ONE matrix: the union
+    pattern (the skeleton term couples all dofs of two neighbouring cells) and the sum of all triplets"""
+    D = len(cells)
+    mesh = GT.cartesian_mesh(tuple([0, 1] * D), cells)
+    _warp(mesh)
+    Om, Lam = GT.interior(mesh), GT.skeleton(mesh)
+    names = ["1-face-1", "1-face-3"] if D == 2 else ["2-face-1", "2-face-3"]
+    Gam = GT.boundary(mesh, group_names=["1-face-2", "1-face-4"] if D == 2 else ["2-face-2", "2-face-6"])
+    V = GT.lagrange_space(Om, 1, dirichlet_boundary=GT.boundary(mesh, group_names=names))
+    dO, dG, dL = GT.measure(Om, 2), GT.measure(Gam, 2), GT.measure(Lam, 2)
+    jump = lambda u, p: u[2](p) - u[1](p)
+    a = lambda u, v: (GT.integrate(lambda q: u(q) * v(q), dO) + 0.5 * GT.integrate(lambda q: u(q) * v(q), dG)
+                      + GT.integrate(lambda p: jump(u, p) * jump(v, p), dL))
+    A, cache = GT.assemble_matrix(a, float, V, V, reuse=True)
+    # the oracle: triplets of the three contributions, concatenated, one compress
+    Vd = V.data
+    coo = [_volume_coo(O.MASS, mesh, Vd, 2)]
+    fp = H.face_problem(Vd, [2, 4] if D == 2 else [2, 6], 2)
+    bef = O.element_matrices(O.MASS, mesh.node_coordinates, fp.face_nodes, dict(w=fp.tab.w, N=fp.tab.N, dN=fp.tab.dN, M=fp.tab.M, dM=fp.tab.dM), alpha=0.5)
+    coo.append(O.coo_matrix(bef, fp.face_dofs, fp.face_dofs))
+    bp = MF.skeleton_problem([Vd], 2)
+    sides = [[(int(bp.side_cells[i, s]), int(bp.face_var[i, s])) for s in range(2)] for i in range(bp.face_nodes.shape[0])]
+    coo.append(O.assemble_matrix_multifield(D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides,
+                                            _oracle_fields(bp, [Vd], False), INTEGRANDS["jumpjump"], return_coo=True))
+    cp, rv, nz = O.assemble_matrix_sum(coo, Vd.n_free, Vd.n_free)
+    assert np.array_equal(A.colptr, cp) and np.array_equal(A.rowval, rv)
+    assert_values_close(A.nzval, nz)
+    # wider than the volume pattern alone
+    M = GT.assemble_matrix(lambda u, v: GT.integrate(lambda q: u(q) * v(q), dO), float, V, V)
+    assert A.nzval.size > M.nzval.size
+    before = A.nzval.copy()
+    A.nzval[:] = 0.0
+    GT.update_matrix(A, cache)                    # update_matrix!: every integral re-assembled, merged again
+    assert np.array_equal(before, A.nzval)
+    for e, _ in cache.params["parts"]:
+        e.close()
+    cache.engine.close()
+
+
+@pytest.mark.gpu
+def test_gpu_poisson_with_robin_term_as_one_matrix():
+    """a(u,v) = ∫_Ω ∇u⋅∇v + ∫_Γ u v on 3D Q1 hexahedra: the volume part runs the structured sweep kernel, the Robin part the
+    boundary-face kernel, merged on the device; pattern = the volume pattern"""
+    mesh = GT.cartesian_mesh((0, 1, 0, 1, 0, 1), (6, 5, 4))
+    Om = GT.interior(mesh)
+    Gam = GT.boundary(mesh, group_names=["2-face-2", "2-face-4"])
+    V = GT.lagrange_space(Om, 1, dirichlet_boundary=GT.boundary(mesh, group_names=["2-face-1"]))
+    dO, dG = GT.measure(Om, 2), GT.measure(Gam, 2)
+    a = lambda u, v: GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dO) + 3.0 * GT.integrate(lambda x: u(x) * v(x), dG)
+    A = GT.assemble_matrix(a, float, V, V)
+    Vd = V.data
+    fp = H.face_problem(Vd, [2, 4], 2)
+    bef = O.element_matrices(O.MASS, mesh.node_coordinates, fp.face_nodes, dict(w=fp.tab.w, N=fp.tab.N, dN=fp.tab.dN, M=fp.tab.M, dM=fp.tab.dM), alpha=3.0)
+    cp, rv, nz = O.assemble_matrix_sum([_volume_coo(O.LAPLACE, mesh, Vd, 2), O.coo_matrix(bef, fp.face_dofs, fp.face_dofs)], Vd.n_free, Vd.n_free)
+    assert np.array_equal(A.colptr, cp) and np.array_equal(A.rowval, rv)
+    assert_values_close(A.nzval, nz)
+    K = GT.assemble_matrix(lambda u, v: GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dO), float, V, V)
+    assert np.array_equal(K.colptr, A.colptr) and np.array_equal(K.rowval, A.rowval)
