@@ -48,6 +48,13 @@ struct BlockArgs {
   int b_form[BP_MAX][BP_MAX];            // [part of u = row][part of v = column]
   double b_alpha[BP_MAX][BP_MAX];
   double v_alpha[BP_MAX], v_f[BP_MAX][3];   // linear forms: per part
+  // skeleton faces with gradient / normal terms (GTK_BLOCK_IP): geometry of the cells around
+  const int32_t* cellD_nodes;            // [n_Dcells][nlnD] 1-based
+  const int32_t* side_cells;             // [n_faces][n_sides] 1-based cell around
+  const double* dMc;                     // [n_var][nq][nlnD][D] geometry gradients of the cell at the mapped face points
+  const double* nref;                    // [n_var][D] reference normal of the variant's local face
+  int nlnD, skel;
+  double b_c[BP_MAX][BP_MAX][3];         // GTK_BLOCK_IP coefficients
   double* out;
   int cb;
   int64_t act0, act1;
@@ -65,14 +72,62 @@ __device__ __forceinline__ int variant_of(const BlockArgs& a, int64_t cell, int 
 
 // phase A shared by both kernels
 template <int D, int d>
-__device__ __forceinline__ void blocks_phase_a(const BlockArgs& a, int64_t cell0, int ncb, double* G, double* dV) {
+__device__ __forceinline__ void blocks_phase_a(const BlockArgs& a, int64_t cell0, int ncb, double* G, double* dV, double* Nrm = nullptr,
+                                               double* hF = nullptr) {
   const int nq = a.nq;
+  if constexpr (D != d) if (a.skel && hF) {
+    // diameter(::MeshFace) (accessors.jl:907-921): the largest distance between two nodes of the face
+    for (int cl = threadIdx.x; cl < ncb; cl += blockDim.x) {
+      const int32_t* nd = a.cell_nodes + (cell0 + cl) * a.nln;
+      double diam = 0.0;
+      for (int i = 0; i < a.nln; ++i)
+        for (int j = 0; j < a.nln; ++j) {
+          double s2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) { const double dx = a.xyz[(size_t)(nd[i] - 1) * D + k] - a.xyz[(size_t)(nd[j] - 1) * D + k]; s2 += dx * dx; }
+          diam = fmax(diam, sqrt(s2));
+        }
+      hF[cl] = diam;
+    }
+  }
   for (int t = threadIdx.x; t < ncb * nq; t += blockDim.x) {
     const int cl = t / nq, q = t - cl * nq;
     const int64_t cell = cell0 + cl;
     double J[D][d];
     gtkmath::jacobian_from<D, d>(a.xyz, a.cell_nodes + cell * a.nln, a.nln, a.dM + (size_t)q * a.nln * d, J);
     dV[t] = gtkmath::change_of_measure<D, d>(J) * a.w[q];
+    if constexpr (D != d) if (a.skel && Nrm) {
+      // the cells around: Jacobian of the CELL's geometry at the mapped face point (unit_normal, accessors.jl:1009-1035;
+      // shape_functions(gradient, …) :1312-1333), physical gradients of the side's parts, unit normal J^-T n_ref / |…|
+      for (int side = 0; side < a.n_sides; ++side) {
+        const int64_t c = a.side_cells[cell * a.n_sides + side] - 1;
+        const int var = a.face_var[cell * a.n_sides + side];
+        double Jc[D][D];
+        gtkmath::jacobian_from<D, D>(a.xyz, a.cellD_nodes + c * a.nlnD, a.nlnD, a.dMc + ((size_t)var * nq + q) * a.nlnD * D, Jc);
+        double JT[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) JT[i][j] = Jc[j][i];
+        const double dt = gtkmath::det_mat<D>(JT);
+        for (int p = 0; p < a.n_parts; ++p) {
+          if (a.p_side[p] != side || !a.p_dN[p]) continue;
+          const int nls = a.p_nls[p];
+          const double* dNq = a.p_dN[p] + ((size_t)var * nq + q) * nls * D;
+          double* g = G + ((size_t)t * a.nls_total + a.p_goff[p]) * D;
+          for (int s = 0; s < nls; ++s) gtkmath::solve_JT<D>(Jc, dt, dNq + s * D, g + s * D);
+        }
+        double v[D];
+        gtkmath::solve_JT<D>(Jc, dt, a.nref + (size_t)var * D, v);
+        double m2 = v[0] * v[0];
+#pragma unroll
+        for (int k = 1; k < D; ++k) m2 += v[k] * v[k];
+        const double m = sqrt(m2);
+        double* nr = Nrm + ((size_t)t * a.n_sides + side) * D;
+#pragma unroll
+        for (int k = 0; k < D; ++k) nr[k] = m < 2.220446049250313e-16 ? 0.0 : v[k] / m;      // map_unit_normal (accessors.jl:1026-1035)
+      }
+    }
     if constexpr (D == d) if (a.need_grad) {
       double JT[D][D];
 #pragma unroll
@@ -96,10 +151,12 @@ __global__ void __launch_bounds__(128) k_elem_blocks(BlockArgs a) {
   extern __shared__ double smem[];
   const int nq = a.nq, L = a.L;
   double* dV = smem;                                   // [cb][nq]
-  double* G = dV + (size_t)a.cb * nq;                  // [cb][nq][nls_total][D]   (volume cells with gradient blocks only)
+  double* G = dV + (size_t)a.cb * nq;                  // [cb][nq][nls_total][D]   (blocks with gradients only)
+  double* Nrm = G + (a.need_grad ? (size_t)a.cb * nq * a.nls_total * D : 0);   // [cb][nq][n_sides][D] unit normals (skeleton, IP blocks)
+  double* hF = Nrm + (a.skel ? (size_t)a.cb * nq * a.n_sides * D : 0);         // [cb] face diameters
   const int64_t cell0 = (int64_t)blockIdx.x * a.cb;
   const int ncb = (int)min((int64_t)a.cb, a.n_cells - cell0);
-  blocks_phase_a<D, d>(a, cell0, ncb, G, dV);
+  blocks_phase_a<D, d>(a, cell0, ncb, G, dV, Nrm, hF);
   __syncthreads();
   const int L2 = L * L;
   for (int t = threadIdx.x; t < ncb * L2; t += blockDim.x) {
@@ -127,6 +184,26 @@ __global__ void __launch_bounds__(128) k_elem_blocks(BlockArgs a) {
       const double* gv = G + (size_t)cl * nq * gstride + (size_t)(a.p_goff[pv] + ca) * D;
       if (form == GTK_BLOCK_MASS) {
         for (int q = 0; q < nq; ++q) acc += (alpha * (Nu[q * nlu] * Nv[q * nlv])) * dv[q];
+      } else if (form == GTK_BLOCK_IP) {
+        // interior-penalty terms on a skeleton face, u on side su, v on side sv (test/assembly_tests.jl:329-340):
+        //   c0 ((1/h) v n_sv)⋅(u n_su) + c1 (v n_sv)⋅∇u + c2 ∇v⋅(u n_su)
+        if constexpr (D != d) {
+          const int su = a.p_side[pu], sv = a.p_side[pv];
+          const double c0 = a.b_c[pu][pv][0] / hF[cl], c1 = a.b_c[pu][pv][1], c2 = a.b_c[pu][pv][2];
+          for (int q = 0; q < nq; ++q, gu += gstride, gv += gstride) {
+            const double* nu = Nrm + ((size_t)(cl * nq + q) * a.n_sides + su) * D;
+            const double* nv = Nrm + ((size_t)(cl * nq + q) * a.n_sides + sv) * D;
+            const double fu = Nu[q * nlu], fv = Nv[q * nlv];
+            double t0 = (c0 * (fv * nv[0])) * (fu * nu[0]), t1 = (fv * nv[0]) * gu[0], t2 = gv[0] * (fu * nu[0]);
+#pragma unroll
+            for (int k = 1; k < D; ++k) {
+              t0 += (c0 * (fv * nv[k])) * (fu * nu[k]);
+              t1 += (fv * nv[k]) * gu[k];
+              t2 += gv[k] * (fu * nu[k]);
+            }
+            acc += (alpha * ((t0 + c1 * t1) + c2 * t2)) * dv[q];
+          }
+        }
       } else if constexpr (D == d) {
         if (form == GTK_BLOCK_LAPLACE) {
           for (int q = 0; q < nq; ++q, gu += gstride, gv += gstride) {
@@ -179,6 +256,15 @@ struct PartsState {
   size_t N_at[BP_MAX], dN_at[BP_MAX];
   int32_t* face_var = nullptr; size_t face_var_n = 0;
   int64_t n_cells = 0;
+  int nq = 0;
+  // cells around skeleton faces (gtk_set_skeleton_cells)
+  bool skel = false;
+  int nlnD = 0;
+  int64_t n_Dcells = 0;
+  int32_t* cellD_nodes = nullptr; size_t cellD_n = 0;
+  int32_t* side_cells = nullptr;  size_t side_n = 0;
+  double* skel_tab = nullptr;     size_t skel_tab_n = 0;   // dMc then nref
+  size_t nref_at = 0;
 };
 
 inline PartsState* parts(gtk_ctx* ctx) { return static_cast<PartsState*>(ctx->parts); }
@@ -213,6 +299,10 @@ int32_t fill(gtk_ctx* ctx, BlockArgs& a) {
     for (int q = 0; q < BP_MAX; ++q) { a.b_form[p][q] = GTK_BLOCK_ZERO; a.b_alpha[p][q] = 0.0; }
   }
   a.face_var = ps->face_var;
+  a.skel = ps->skel ? 1 : 0;
+  a.cellD_nodes = ps->cellD_nodes; a.side_cells = ps->side_cells; a.nlnD = ps->nlnD;
+  a.dMc = ps->skel_tab; a.nref = ps->skel_tab ? ps->skel_tab + ps->nref_at : nullptr;
+  for (int p = 0; p < BP_MAX; ++p) for (int q = 0; q < BP_MAX; ++q) for (int k = 0; k < 3; ++k) a.b_c[p][q][k] = 0.0;
   a.act0 = ctx->act_count < 0 ? 0 : ctx->act_first;
   a.act1 = ctx->act_count < 0 ? ctx->n_cells : ctx->act_first + ctx->act_count;
   return GTK_OK;
@@ -235,6 +325,9 @@ void gtk_parts_release(gtk_ctx* ctx) {
   if (!ps) return;
   if (ps->tab) gtk_dev_free(ctx, ps->tab, ps->tab_n * sizeof(double));
   if (ps->face_var) gtk_dev_free(ctx, ps->face_var, ps->face_var_n * sizeof(int32_t));
+  if (ps->cellD_nodes) gtk_dev_free(ctx, ps->cellD_nodes, ps->cellD_n * sizeof(int32_t));
+  if (ps->side_cells) gtk_dev_free(ctx, ps->side_cells, ps->side_n * sizeof(int32_t));
+  if (ps->skel_tab) gtk_dev_free(ctx, ps->skel_tab, ps->skel_tab_n * sizeof(double));
   delete ps;
   ctx->parts = nullptr;
 }
@@ -251,14 +344,12 @@ extern "C" int32_t gtk_set_parts(gtk_ctx* ctx, int32_t n_q, const double* w, con
   PartsState* ps = new PartsState();
   ctx->parts = ps;
   const int D = ctx->D, dm = ctx->dman;
-  ps->n_parts = n_parts; ps->n_sides = n_sides; ps->n_var = n_var; ps->n_cells = ctx->n_cells;
+  ps->n_parts = n_parts; ps->n_sides = n_sides; ps->n_var = n_var; ps->n_cells = ctx->n_cells; ps->nq = n_q;
   size_t at = 0;
   int off = 0, goff = 0;
   for (int p = 0; p < n_parts; ++p) {
     if (pd[p].n_lshape < 1 || pd[p].n_comp < 1 || pd[p].n_comp > 3 || pd[p].side < 0 || pd[p].side >= n_sides || !pd[p].N)
       GTK_FAIL(GTK_ERR_INVALID, "gtk_set_parts: bad part descriptor " + std::to_string(p));
-    if (pd[p].dN && dm != D)
-      GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "gradient tables on faces of lower dimension than the space are not supported (values only); no CPU fallback");
     ps->nls[p] = pd[p].n_lshape; ps->ncomp[p] = pd[p].n_comp; ps->side[p] = pd[p].side;
     ps->off[p] = off; ps->goff[p] = goff; ps->has_dN[p] = pd[p].dN != nullptr;
     off += pd[p].n_lshape * pd[p].n_comp; goff += pd[p].n_lshape;
@@ -303,10 +394,45 @@ extern "C" int32_t gtk_set_parts(gtk_ctx* ctx, int32_t n_q, const double* w, con
   return GTK_OK;
 }
 
+extern "C" int32_t gtk_set_skeleton_cells(gtk_ctx* ctx, int64_t n_cells, int32_t n_lnodes, const int32_t* cell_nodes, const int32_t* side_cells,
+                                          const double* dM_cell, const double* ref_normals) {
+  if (!ctx) return GTK_ERR_INVALID;
+  PartsState* ps = parts(ctx);
+  if (!ps) GTK_FAIL(GTK_ERR_STATE, "gtk_set_skeleton_cells: call gtk_set_parts first");
+  if (ctx->dman != ctx->D - 1 || ps->n_sides != 2) GTK_FAIL(GTK_ERR_STATE, "gtk_set_skeleton_cells: the integration faces must be (D-1)-faces with two cells around");
+  if (n_cells < 1 || n_lnodes < 2 || !cell_nodes || !side_cells || !dM_cell || !ref_normals) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_skeleton_cells: bad arguments");
+  GTK_CK(cudaSetDevice(ctx->device));
+  const int D = ctx->D;
+  const size_t nf2 = (size_t)ctx->n_cells * 2;
+  for (size_t i = 0; i < nf2; ++i)
+    if (side_cells[i] < 1 || side_cells[i] > n_cells) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_skeleton_cells: side_cells out of range");
+  for (size_t i = 0; i < (size_t)n_cells * n_lnodes; ++i)
+    if (cell_nodes[i] < 1 || cell_nodes[i] > ctx->n_nodes) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_skeleton_cells: cell_nodes out of range");
+  if (ps->cellD_nodes) { gtk_dev_free(ctx, ps->cellD_nodes, ps->cellD_n * sizeof(int32_t)); ps->cellD_nodes = nullptr; }
+  if (ps->side_cells) { gtk_dev_free(ctx, ps->side_cells, ps->side_n * sizeof(int32_t)); ps->side_cells = nullptr; }
+  if (ps->skel_tab) { gtk_dev_free(ctx, ps->skel_tab, ps->skel_tab_n * sizeof(double)); ps->skel_tab = nullptr; }
+  ps->skel = false;
+  int32_t rc;
+  ps->cellD_n = (size_t)n_cells * n_lnodes; ps->side_n = nf2 > 0 ? nf2 : 1;
+  const size_t ndm = (size_t)ps->n_var * ps->nq * n_lnodes * D, nnr = (size_t)ps->n_var * D;
+  ps->skel_tab_n = ndm + nnr; ps->nref_at = ndm;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&ps->cellD_nodes, ps->cellD_n * sizeof(int32_t)))) return rc;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&ps->side_cells, ps->side_n * sizeof(int32_t)))) return rc;
+  if ((rc = gtk_dev_alloc(ctx, (void**)&ps->skel_tab, ps->skel_tab_n * sizeof(double)))) return rc;
+  GTK_CK(cudaMemcpyAsync(ps->cellD_nodes, cell_nodes, ps->cellD_n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (nf2) GTK_CK(cudaMemcpyAsync(ps->side_cells, side_cells, nf2 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  GTK_CK(cudaMemcpyAsync(ps->skel_tab, dM_cell, ndm * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GTK_CK(cudaMemcpyAsync(ps->skel_tab + ndm, ref_normals, nnr * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  ps->nlnD = n_lnodes; ps->n_Dcells = n_cells; ps->skel = true;
+  return GTK_OK;
+}
+
 static int32_t launch_blocks(gtk_ctx* ctx, BlockArgs& a, bool matrix) {
   const int D = ctx->D, dm = ctx->dman;
   size_t per_cell = (size_t)ctx->nq * sizeof(double);
   if (matrix && a.need_grad) per_cell += (size_t)ctx->nq * a.nls_total * D * sizeof(double);
+  if (matrix && a.skel) per_cell += ((size_t)ctx->nq * a.n_sides * D + 1) * sizeof(double);
   size_t smem;
   int32_t rc = pick(ctx, per_cell, &a.cb, &smem);
   if (rc) return rc;
@@ -348,6 +474,11 @@ extern "C" int32_t gtk_matrix_numeric_blocks_device(gtk_ctx* ctx, int32_t n_bloc
     const bool grad = k.form == GTK_BLOCK_LAPLACE || k.form == GTK_BLOCK_VALU_DIVV || k.form == GTK_BLOCK_DIVU_VALV;
     bool ok = false;
     if (k.form == GTK_BLOCK_ZERO) ok = true;
+    else if (k.form == GTK_BLOCK_IP) {
+      if (!ps->skel || ctx->dman == ctx->D)
+        GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "interior-penalty blocks need a skeleton measure and gtk_set_skeleton_cells; no CPU fallback");
+      ok = cu == 1 && cv == 1 && ps->has_dN[k.part_u] && ps->has_dN[k.part_v];
+    }
     else if (k.form == GTK_BLOCK_MASS) ok = cu == cv;
     else if (k.form == GTK_BLOCK_LAPLACE) ok = cu == cv && ps->has_dN[k.part_u] && ps->has_dN[k.part_v];
     else if (k.form == GTK_BLOCK_VALU_DIVV) ok = cu == 1 && cv == ctx->D && ps->has_dN[k.part_v];
@@ -361,7 +492,13 @@ extern "C" int32_t gtk_matrix_numeric_blocks_device(gtk_ctx* ctx, int32_t n_bloc
       GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "one term per (part_u, part_v) block; sums inside a block are not recognised; no CPU fallback");
     a.b_form[k.part_u][k.part_v] = k.form;
     a.b_alpha[k.part_u][k.part_v] = k.alpha;
-    if (grad) a.need_grad = 1;
+    for (int c = 0; c < 3; ++c) a.b_c[k.part_u][k.part_v][c] = k.c[c];
+    if (grad || k.form == GTK_BLOCK_IP) a.need_grad = 1;
+  }
+  {
+    bool any_ip = false;
+    for (int b = 0; b < n_blocks; ++b) any_ip |= blocks[b].form == GTK_BLOCK_IP;
+    if (!any_ip) a.skel = 0;
   }
   ctx->launches_last = 0;
   ctx->fast_path_last = 7;

@@ -38,9 +38,9 @@ ABI_SYMBOLS = [
     "gtk_set_cartesian_q1_problem", "gtk_copy_device_array", "gtk_matrix_pattern_i64",
     "gtk_set_parts", "gtk_matrix_numeric_blocks", "gtk_matrix_numeric_blocks_device",
     "gtk_vector_assemble_blocks", "gtk_vector_assemble_blocks_device",
-    "gtk_matrix_sum_symbolic", "gtk_matrix_sum_numeric", "gtk_matrix_sum_numeric_device",
+    "gtk_matrix_sum_symbolic", "gtk_matrix_sum_numeric", "gtk_matrix_sum_numeric_device", "gtk_set_skeleton_cells",
 ]
-BLOCK_ZERO, BLOCK_MASS, BLOCK_LAPLACE, BLOCK_VALU_DIVV, BLOCK_DIVU_VALV = 0, 1, 2, 3, 4
+BLOCK_ZERO, BLOCK_MASS, BLOCK_LAPLACE, BLOCK_VALU_DIVV, BLOCK_DIVU_VALV, BLOCK_IP = 0, 1, 2, 3, 4, 5
 MAX_PARTS = 8
 
 
@@ -66,7 +66,7 @@ class Part(C.Structure):       # gtk_part
 
 
 class Block(C.Structure):      # gtk_block
-    _fields_ = [("part_u", C.c_int32), ("part_v", C.c_int32), ("form", C.c_int32), ("alpha", C.c_double)]
+    _fields_ = [("part_u", C.c_int32), ("part_v", C.c_int32), ("form", C.c_int32), ("alpha", C.c_double), ("c", C.c_double * 3)]
 
 
 class VBlock(C.Structure):     # gtk_vblock
@@ -142,6 +142,7 @@ def load_library() -> C.CDLL:
         "gtk_matrix_numeric_blocks_device": (i32, [vp, i32, C.POINTER(Block)]),
         "gtk_vector_assemble_blocks": (i32, [vp, i32, C.POINTER(VBlock), i32, vp]),
         "gtk_vector_assemble_blocks_device": (i32, [vp, i32, C.POINTER(VBlock), i32]),
+        "gtk_set_skeleton_cells": (i32, [vp, i64, i32, vp, vp, vp, vp]),
         "gtk_matrix_sum_symbolic": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
         "gtk_matrix_sum_numeric": (i32, [vp, i32, C.POINTER(vp), vp]),
         "gtk_matrix_sum_numeric_device": (i32, [vp, i32, C.POINTER(vp)]),
@@ -312,22 +313,34 @@ class Engine:
         self._ck(self.lib.gtk_set_parts(self.h, w.shape[0], _ptr(w), _ptr(M), _ptr(dM), len(parts), arr, int(n_sides), int(n_var), _ptr(fv)))
         del keep
 
-    def matrix_numeric_blocks(self, blocks, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """blocks: iterable of (part_u, part_v, form, alpha)"""
+    @staticmethod
+    def _block_array(blocks):
         blocks = list(blocks)
         arr = (Block * max(len(blocks), 1))()
-        for k, (pu, pv, form, alpha) in enumerate(blocks):
+        for k, blk in enumerate(blocks):
+            pu, pv, form, alpha = blk[:4]
             arr[k].part_u, arr[k].part_v, arr[k].form, arr[k].alpha = int(pu), int(pv), int(form), float(alpha)
+            c = blk[4] if len(blk) > 4 else (0.0, 0.0, 0.0)
+            for i in range(3):
+                arr[k].c[i] = float(c[i])
+        return arr, len(blocks)
+
+    def set_skeleton_cells(self, cell_nodes, side_cells, dM_cell, ref_normals):
+        """cells around the faces of a skeleton measure (gradients / normals on the faces: BLOCK_IP); after set_parts"""
+        cn, sc = _i32(cell_nodes), _i32(side_cells)
+        dm, nr = _f64(dM_cell), _f64(ref_normals)
+        self._ck(self.lib.gtk_set_skeleton_cells(self.h, cn.shape[0], cn.shape[1], _ptr(cn), _ptr(sc), _ptr(dm), _ptr(nr)))
+
+    def matrix_numeric_blocks(self, blocks, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """blocks: iterable of (part_u, part_v, form, alpha[, (c0, c1, c2)])"""
+        arr, n = self._block_array(blocks)
         nz = np.empty(self.nnz, dtype=np.float64) if out is None else out
-        self._ck(self.lib.gtk_matrix_numeric_blocks(self.h, len(blocks), arr, _ptr(nz)))
+        self._ck(self.lib.gtk_matrix_numeric_blocks(self.h, n, arr, _ptr(nz)))
         return nz
 
     def matrix_numeric_blocks_device(self, blocks):
-        blocks = list(blocks)
-        arr = (Block * max(len(blocks), 1))()
-        for k, (pu, pv, form, alpha) in enumerate(blocks):
-            arr[k].part_u, arr[k].part_v, arr[k].form, arr[k].alpha = int(pu), int(pv), int(form), float(alpha)
-        self._ck(self.lib.gtk_matrix_numeric_blocks_device(self.h, len(blocks), arr))
+        arr, n = self._block_array(blocks)
+        self._ck(self.lib.gtk_matrix_numeric_blocks_device(self.h, n, arr))
 
     # -- sums of integrals over different domains: this context holds the merged matrix ------------
     def matrix_sum_symbolic(self, sources) -> int:

@@ -171,6 +171,8 @@ class Term:
     def __sub__(self, o): return Call("-", self, _lift(o))
     def __rsub__(self, o): return Call("-", _lift(o), self)
     def __matmul__(self, o): return Call("dot", self, _lift(o))
+    def __truediv__(self, o): return Call("/", self, _lift(o))
+    def __rtruediv__(self, o): return Call("/", _lift(o), self)
 
 
 @dataclass
@@ -205,8 +207,44 @@ class Named(Term):             # named integrand whose identity is matched (SURV
     args: tuple
 
 
+@dataclass
+class Normal(Term):            # unit_normal(mesh, D-1)[side](x) on a skeleton face (accessors.jl:1009-1035)
+    side: int
+
+
+@dataclass
+class FaceDiameter(Term):      # face_diameter_field(Λ)(x) (field.jl:488-492)
+    inverse: bool = False
+
+
 def _lift(o):
     return o if isinstance(o, Term) else Const(o)
+
+
+class _UnitNormal:
+    """n = GT.unit_normal(mesh, D-1): n[1](x), n[2](x) = the outward unit normals of the two cells around a skeleton face"""
+
+    def __getitem__(self, k: int):
+        if k not in (1, 2):
+            raise IndexError("a skeleton face has two cells around: n[1], n[2]")
+        return lambda x: Normal(k)
+
+
+def unit_normal(mesh, d: int) -> _UnitNormal:
+    if d != mesh.D - 1:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "unit normals are defined on (D-1)-faces")
+    return _UnitNormal()
+
+
+def face_diameter_field(domain: Domain):
+    """h_Λ = GT.face_diameter_field(Λ): h_Λ(x) is the diameter of the face x lies on (field.jl:488-492)"""
+    if domain.kind != "skeleton":
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "face diameters are supported on skeleton domains on the GPU path")
+    return lambda x: FaceDiameter()
+
+
+def uniform_quantity(v):
+    return v
 
 
 class FormArgument:
@@ -586,8 +624,15 @@ def _expand(t):
     """term -> list of (scalar, factors, dotted): the integrand as a sum of products of form-argument factors"""
     if isinstance(t, Const) and np.isscalar(t.value):
         return [(float(t.value), (), False)]
-    if isinstance(t, FormArg):
+    if isinstance(t, (FormArg, Normal, FaceDiameter)):
         return [(1.0, (t,), False)]
+    if isinstance(t, Call) and t.fn == "/" and t.b is not None:
+        den = _expand(t.b)
+        if len(den) == 1 and den[0][1] == ():                                   # a / scalar
+            return [(c / den[0][0], f, d) for (c, f, d) in _expand(t.a)]
+        if len(den) == 1 and len(den[0][1]) == 1 and isinstance(den[0][1][0], FaceDiameter) and not den[0][1][0].inverse:
+            return [(c / den[0][0], f + (FaceDiameter(True),), d) for (c, f, d) in _expand(t.a)]   # a / h(x)
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "division by anything but a constant or the face diameter is not recognised; no CPU fallback")
     if isinstance(t, Call) and t.fn in ("+", "-") and t.b is not None:
         sign = 1.0 if t.fn == "+" else -1.0
         return _expand(t.a) + [(sign * c, f, d) for (c, f, d) in _expand(t.b)]
@@ -606,7 +651,7 @@ def _block_problem(space, meas: "Measure"):
     from . import multifield as _mf
     data = [f.data for f in fields(space)]
     if meas.domain.kind == "skeleton":
-        return _mf.skeleton_problem(data, meas.degree)
+        return _mf.skeleton_problem(data, meas.degree, gradients=True)
     if meas.domain.kind == "interior":
         return _mf.volume_problem(data, meas.degree)
     raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "product spaces are assembled on interior and skeleton measures only")
@@ -620,6 +665,8 @@ def _setup_block_engine(space, meas: "Measure", engine: Optional[_eng.Engine] = 
         eng.set_manifold_dim(bp.manifold_dim)
     eng.set_space(bp.super_dofs, bp.n_free, bp.n_dirichlet, 1)
     eng.set_parts(bp.w, bp.M, bp.dM, bp.parts, bp.n_sides, bp.face_var)
+    if bp.dM_cell is not None:
+        eng.set_skeleton_cells(bp.cell_nodes, bp.side_cells, bp.dM_cell, bp.ref_normals)
     eng._gt_setup = None
     return eng, bp
 
@@ -637,13 +684,32 @@ def _part_of(bp, fa: FormArg, skeleton_measure: bool) -> int:
 def recognise_blocks(term, bp, skeleton_measure: bool):
     """-> [(part_u, part_v, block form, alpha)]: one recognised term per (part of u, part of v) block."""
     out = {}
+    ip = {}                                  # interior-penalty blocks: key -> [c0, c1, c2]
     for coef, factors, dotted in _expand(term):
-        us = [f for f in factors if f.arg == 2]
-        vs = [f for f in factors if f.arg == 1]
-        if len(us) != 1 or len(vs) != 1 or len(factors) != 2:
+        us = [f for f in factors if isinstance(f, FormArg) and f.arg == 2]
+        vs = [f for f in factors if isinstance(f, FormArg) and f.arg == 1]
+        others = [f for f in factors if not isinstance(f, FormArg)]
+        if len(us) != 1 or len(vs) != 1 or len(factors) != 2 + len(others):
             raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "every term of a bilinear integrand must hold exactly one trial and one test factor; no CPU fallback")
         u, v = us[0], vs[0]
         ops = (u.op, v.op)
+        if others:
+            # terms with unit normals / the face diameter: (1/h)(v n_sv)⋅(u n_su), (v n_sv)⋅∇u, ∇v⋅(u n_su)
+            normals = sorted(f.side for f in others if isinstance(f, Normal))
+            invh = [f for f in others if isinstance(f, FaceDiameter)]
+            if not skeleton_measure or len(normals) + len(invh) != len(others) or any(not f.inverse for f in invh) or not dotted:
+                raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "normal / face-diameter term not recognised by the GPU engine; no CPU fallback")
+            if ops == ("value", "value") and len(invh) == 1 and normals == sorted([u.side, v.side]):
+                kind = 0
+            elif ops == ("gradient", "value") and not invh and normals == [v.side]:
+                kind = 1
+            elif ops == ("value", "gradient") and not invh and normals == [u.side]:
+                kind = 2
+            else:
+                raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "normal / face-diameter term not recognised by the GPU engine; no CPU fallback")
+            key = (_part_of(bp, u, True), _part_of(bp, v, True))
+            ip.setdefault(key, [0.0, 0.0, 0.0])[kind] += coef
+            continue
         if ops == ("value", "value"):
             form = _eng.BLOCK_MASS
         elif ops == ("gradient", "gradient") and dotted:
@@ -661,7 +727,10 @@ def recognise_blocks(term, bp, skeleton_measure: bool):
             out[key] = (form, out[key][1] + coef)
         else:
             out[key] = (form, coef)
-    return [(pu, pv, form, alpha) for (pu, pv), (form, alpha) in out.items()]
+    if set(ip) & set(out):
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "two different terms in one block are not recognised; no CPU fallback")
+    return [(pu, pv, form, alpha) for (pu, pv), (form, alpha) in out.items()] + \
+           [(pu, pv, _eng.BLOCK_IP, 1.0, tuple(c)) for (pu, pv), c in ip.items()]
 
 
 def recognise_vblocks(term, bp, skeleton_measure: bool, space):
@@ -687,7 +756,7 @@ def _assemble_matrix_blocks(a, U, V, reuse, free_or_dirichlet, engine, index_typ
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
     term, meas, scale = _single_contribution(a(_form_arguments(U, 2), _form_arguments(V, 1)))
     eng, bp = _setup_block_engine(V, meas, engine)
-    blocks = [(pu, pv, form, alpha * scale) for (pu, pv, form, alpha) in recognise_blocks(term, bp, meas.domain.kind == "skeleton")]
+    blocks = [(b[0], b[1], b[2], b[3] * scale) + tuple(b[4:]) for b in recognise_blocks(term, bp, meas.domain.kind == "skeleton")]
     eng.matrix_symbolic(*free_or_dirichlet)
     colptr, rowval = eng.matrix_pattern_i64() if index_type in (int, np.int64) else eng.matrix_pattern()
     nzval = eng.matrix_numeric_blocks(blocks)
@@ -719,7 +788,7 @@ def _assemble_matrix_sum(contributions, U, V, reuse, free_or_dirichlet, index_ty
         for term, meas, scale in contributions:
             if _is_blocks_case(V, meas):
                 eng, bp = _setup_block_engine(V, meas)
-                blocks = [(pu, pv, form, alpha * scale) for (pu, pv, form, alpha) in recognise_blocks(term, bp, meas.domain.kind == "skeleton")]
+                blocks = [(b[0], b[1], b[2], b[3] * scale) + tuple(b[4:]) for b in recognise_blocks(term, bp, meas.domain.kind == "skeleton")]
                 run = (lambda e=eng, b=blocks: e.matrix_numeric_blocks_device(b))
             else:
                 form, params = recognise_bilinear(term, V, meas)

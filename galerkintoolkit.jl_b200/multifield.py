@@ -49,6 +49,9 @@ class BlockProblem:
     n_sides: int
     face_var: np.ndarray | None  # [n_faces, n_sides] 0-based tabulation variant
     side_cells: np.ndarray | None = None   # [n_faces, n_sides] 1-based cells around (skeleton)
+    cell_nodes: np.ndarray | None = None   # skeleton with gradients: nodes of the D-cells,
+    dM_cell: np.ndarray | None = None      #   their geometry gradients at the mapped face points [n_var, nq, nln, D],
+    ref_normals: np.ndarray | None = None  #   the reference normal of every variant's local face [n_var, D]
 
     def part_index(self, field: int, side: int = 0) -> int:
         for k, p in enumerate(self.parts):
@@ -96,7 +99,21 @@ def interior_faces(mesh: _hp.Mesh):
     return np.ascontiguousarray(face_nodes, dtype=np.int32), side_cells
 
 
-def skeleton_problem(spaces: Sequence[_hp.LagrangeSpace], degree: int) -> BlockProblem:
+def _reference_normal(Xface: np.ndarray, simplex: bool) -> np.ndarray:
+    """normals(mesh(domain(refface)))[ldface] (domain.jl:226, 258 cubes; :428, 460 simplices) of the local face whose reference
+    nodes are Xface: the outward unit normal of that face of the reference cell"""
+    D = Xface.shape[1]
+    for k in range(D):
+        if np.all(Xface[:, k] == Xface[0, k]) and (not simplex or Xface[0, k] == 0.0):
+            n = np.zeros(D)
+            n[k] = 1.0 if Xface[0, k] == 1.0 else -1.0
+            return n
+    if simplex:                                         # the face opposite the origin
+        return np.full(D, 1.0 / np.sqrt(D))
+    raise AssertionError("not a face of the reference cell")
+
+
+def skeleton_problem(spaces: Sequence[_hp.LagrangeSpace], degree: int, gradients: bool = False) -> BlockProblem:
     """∫(…, measure(skeleton(mesh), degree)): per field two parts (the cells around), values only.
     The tabulation variant of (face, side) is named by where the face's nodes sit in the cell: the face point ξ maps to
     Σ_k X̂[loc_k] M_k(ξ) in the cell's reference coordinates (reference_map: the coefficient of the face's k-th shape function
@@ -123,9 +140,16 @@ def skeleton_problem(spaces: Sequence[_hp.LagrangeSpace], degree: int) -> BlockP
     dofs, nfree, ndiri, _, _ = offset_dofs(spaces)
     parts, cols = [], []
     for f, s in enumerate(spaces):
-        N = np.stack([_hp.tabulate(D, s.order, s.kind, cell_pts[v])[0] for v in range(variants.shape[0])])
+        tabs = [_hp.tabulate(D, s.order, s.kind, cell_pts[v]) for v in range(variants.shape[0])]
+        N = np.stack([t[0] for t in tabs])
+        dN = np.stack([t[1] for t in tabs]) if gradients else None
         for a in range(2):
-            parts.append(dict(field=f, side=a, n_comp=s.n_comp, N=N, dN=None))
+            parts.append(dict(field=f, side=a, n_comp=s.n_comp, N=N, dN=dN))
             cols.append(dofs[f][sc[:, a] - 1])
-    return BlockProblem(mesh.node_coordinates, fn, D - 1, np.ascontiguousarray(np.concatenate(cols, axis=1)), nfree, ndiri,
-                        np.ascontiguousarray(q.weights), M, dM, parts, 2, face_var, sc)
+    bp = BlockProblem(mesh.node_coordinates, fn, D - 1, np.ascontiguousarray(np.concatenate(cols, axis=1)), nfree, ndiri,
+                      np.ascontiguousarray(q.weights), M, dM, parts, 2, face_var, sc)
+    if gradients:       # geometry of the cells around at the mapped points + reference normals (unit_normal, accessors.jl:1009-1035)
+        bp.cell_nodes = mesh.cell_nodes
+        bp.dM_cell = np.stack([_hp.tabulate(D, 1, kind, cell_pts[v])[1] for v in range(variants.shape[0])])
+        bp.ref_normals = np.stack([_reference_normal(Xref[variants[v]], mesh.simplex) for v in range(variants.shape[0])])
+    return bp

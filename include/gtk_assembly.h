@@ -235,7 +235,8 @@ typedef struct gtk_part {
   int32_t side;       /* which cell around the face (0-based; volume integrals: 0)                                   */
   const double* N;    /* host [n_var][n_q][n_lshape]: the cell's shape functions at the face's quadrature points, one table
                          per (local face, permutation) variant (accessors.jl:498-522, reference_map :1914-1943); volume: n_var = 1 */
-  const double* dN;   /* host [n_var][n_q][n_lshape][D] reference gradients, or NULL (values only; required NULL on faces) */
+  const double* dN;   /* host [n_var][n_q][n_lshape][D] reference gradients, or NULL (values only); on skeleton faces they are used
+                         by GTK_BLOCK_IP together with gtk_set_skeleton_cells */
 } gtk_part;
 /* face_var: host [n_faces][n_sides], 0-based variant of the tabulation for the cell around on each side (NULL if n_var ==
  * n_sides == 1).  Replaces gtk_set_tabulation for this mesh / space; a later gtk_set_mesh / gtk_set_space drops the parts. */
@@ -249,9 +250,21 @@ enum {
   GTK_BLOCK_MASS = 1,       /* u(x) * v(x)  (component-wise for vector parts; the two parts may be different fields / sides) */
   GTK_BLOCK_LAPLACE = 2,    /* ∇(v,x) ⋅ ∇(u,x)  (component-wise: the Frobenius product of the Jacobians for vector parts)   */
   GTK_BLOCK_VALU_DIVV = 3,  /* u(x) * div(v,x): u a scalar part (pressure), v a vector part with n_comp == D                */
-  GTK_BLOCK_DIVU_VALV = 4   /* v(x) * div(u,x): v a scalar part, u a vector part                                           */
+  GTK_BLOCK_DIVU_VALV = 4,  /* v(x) * div(u,x): v a scalar part, u a vector part                                           */
+  GTK_BLOCK_IP = 5          /* skeleton faces, scalar parts, u on the cell around s_u, v on s_v (needs gtk_set_skeleton_cells):
+                               c[0] ((1/h) v n_sv)⋅(u n_su) + c[1] (v n_sv)⋅∇u + c[2] ∇v⋅(u n_su), n = unit normals of the two cells
+                               (accessors.jl:1009-1035), h = diameter of the face (field.jl:488-492, accessors.jl:907-921): the
+                               interior-penalty terms (γ/h) jump(v,n)⋅jump(u,n) - jump(v,n)⋅mean(∇u) - mean(∇v)⋅jump(u,n) of
+                               test/assembly_tests.jl:329-340 are c = (γ, -1/2, -1/2) on all four (side, side) blocks            */
 };
-typedef struct gtk_block { int32_t part_u, part_v, form; double alpha; } gtk_block;
+typedef struct gtk_block { int32_t part_u, part_v, form; double alpha; double c[3]; } gtk_block;
+/* Cells around the faces of a skeleton measure, for blocks with gradients / normals there (call after gtk_set_parts):
+ * cell_nodes [n_cells][n_lnodes] = face_nodes(mesh, D).data, side_cells [n_faces][2] (1-based), dM_cell [n_var][n_q][n_lnodes][D]
+ * = the cell's geometry gradients at the face points mapped into the cell per (local face, permutation) variant, ref_normals
+ * [n_var][D] = normals(mesh(domain(refface)))[ldface] of the variant's local face (domain.jl:226, 258).  The parts' dN tables are
+ * then [n_var][n_q][n_lshape][D] at the same mapped points. */
+int32_t gtk_set_skeleton_cells(gtk_ctx* ctx, int64_t n_cells, int32_t n_lnodes, const int32_t* cell_nodes, const int32_t* side_cells,
+                               const double* dM_cell, const double* ref_normals);
 /* Numeric assembly of Σ blocks on the pattern of gtk_matrix_symbolic (blocks not listed are GTK_BLOCK_ZERO); re-callable
  * like gtk_matrix_numeric (update_matrix!).  E.g. Stokes a((u,p),(v,q)) = ∫ ∇v⋅∇u - div(v) p + q div(u)
  * (docs/src/src_jl/example_stokes.jl) is {(u,v,LAPLACE,1), (p,v,VALU_DIVV,-1), (u,q,DIVU_VALV,1)}; the reference's test

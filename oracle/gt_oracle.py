@@ -1158,6 +1158,8 @@ class _LoopPoint:
         f, a, _, g = which
         return g if (f == field and a == side) else self._zero(field, True)
 
+    def n(self, side): return self.normals[side - 1]       # unit_normal(mesh, D-1)[side](x)  (accessors.jl:1009-1035)
+
     def v(self, field, side=1): return self._val(self.V, field, side)
     def u(self, field, side=1): return self._val(self.U, field, side)
     def grad_v(self, field, side=1): return self._grad(self.V, field, side)     # ForwardDiff.gradient / jacobian
@@ -1180,6 +1182,28 @@ def _shape(N_a, g_a, comp, n_comp, D):
     return val, jac
 
 
+def map_unit_normal(J, n):
+    """accessors.jl:1026-1035, literally: pinvJt = transpose(inv(Jt*J)*Jt); v = pinvJt*n; v / sqrt(v⋅v) (zero below eps)"""
+    J = np.asarray(J, dtype=np.float64)
+    Jt = J.T
+    pinvJt = (np.linalg.inv(Jt @ J) @ Jt).T
+    v = pinvJt @ np.asarray(n, dtype=np.float64)
+    m = np.sqrt(frobenius(v, v))
+    if m < np.finfo(np.float64).eps:
+        return np.zeros_like(v)
+    return v / m
+
+
+def face_diameter(coords, nodes):
+    """diameter(::MeshFace) (accessors.jl:907-921): the largest distance between two nodes of the face"""
+    diam = 0.0
+    for i in nodes:
+        for j in nodes:
+            dx = np.asarray(coords[i - 1]) - np.asarray(coords[j - 1])
+            diam = max(diam, float(np.sqrt(frobenius(dx, dx))))
+    return diam
+
+
 def frobenius(a, b):
     """`a ⋅ b` of two SVectors / SMatrices: Σ of the elementwise products in memory (column-major) order"""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
@@ -1193,7 +1217,7 @@ def frobenius(a, b):
 
 
 def assemble_matrix_multifield(D, coords, face_nodes, face_tab, sides, fields, integrand, alpha=1.0,
-                               free_or_dirichlet=(FREE, FREE), cell_geometry=None, return_coo=False):
+                               free_or_dirichlet=(FREE, FREE), cell_geometry=None, return_coo=False, skeleton_geometry=None):
     """generate_matrix_assembly_template (compiler.jl:1826-1923) + MonolithicAssemblyAllocation (assembly.jl:386-416)
     + contribute!(::MatrixAllocation) (:189-208) + compress (:571-575), loop for loop.
 
@@ -1205,6 +1229,8 @@ def assemble_matrix_multifield(D, coords, face_nodes, face_tab, sides, fields, i
     integrand(pt)             user integrand on a _LoopPoint (masked shape functions), e.g.
                               lambda p: frobenius(p.grad_v(0), p.grad_u(0)) - p.div_v(0) * p.u(1) + p.v(1) * p.div_u(0)
     cell_geometry             (cell_nodes, dM_cell [nq][nln][D]) for physical gradients (volume integrals only)
+    skeleton_geometry         (cell_nodes, dM_cell [n_var][nq][nln][D], ref_normals [n_var][D]): gradients and unit normals of
+                              the cells around a skeleton face (pt.grad_u(f, side), pt.n(side)); pt.h = diameter of the face
     -> colptr, rowval, nzval of the monolithic matrix (rows: u's fields, columns: v's fields — SURVEY A.8b)."""
     fr, fcn = free_or_dirichlet
     nf = len(fields)
@@ -1230,11 +1256,22 @@ def assemble_matrix_multifield(D, coords, face_nodes, face_tab, sides, fields, i
             dV = float(change_of_measure(Jf)[0] * w[q])                          # the FACE's own geometry (accessors.jl:1000-1007)
             # shape functions of every field on every cell around at this point
             sh = {}
+            if skeleton_geometry is not None:
+                cnS, dMS, nrefS = skeleton_geometry
+                pt.h = face_diameter(coords, fn[face])
+                pt.normals, JS = [], []
+                for (cell, var) in sides[face]:
+                    Jc = point_geometry(coords, np.asarray(cnS)[cell - 1:cell], np.asarray(dMS[var][q]))
+                    JS.append(Jc)
+                    pt.normals.append(map_unit_normal(Jc[0], nrefS[var]))
             for f, fld in enumerate(fields):
                 nc = fld["n_comp"]
                 for a, (cell, var) in enumerate(sides[face]):
                     g = None
-                    if fld.get("dN") is not None and cell_geometry is not None:
+                    if fld.get("dN") is not None and skeleton_geometry is not None:
+                        Jt = np.swapaxes(JS[a], -1, -2)
+                        g = [_solve(Jt, np.asarray(fld["dN"][var][q][s]).reshape(1, D))[0] for s in range(len(fld["N"][var][q]))]
+                    elif fld.get("dN") is not None and cell_geometry is not None:
                         cn, dMc = cell_geometry
                         Jc = point_geometry(coords, np.asarray(cn)[cell - 1:cell], np.asarray(dMc[q]))
                         Jt = np.swapaxes(Jc, -1, -2)

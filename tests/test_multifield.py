@@ -446,3 +446,109 @@ def test_gpu_poisson_with_robin_term_as_one_matrix():
     assert_values_close(A.nzval, nz)
     K = GT.assemble_matrix(lambda u, v: GT.integrate(lambda x: GT.dot(GT.grad(u, x), GT.grad(v, x)), dO), float, V, V)
     assert np.array_equal(K.colptr, A.colptr) and np.array_equal(K.rowval, A.rowval)
+
+
+# ---- gradients and unit normals on skeleton faces: interior-penalty terms (GTK_BLOCK_IP) ---------------------------------
+def _ip(p, su, sv, c):
+    """c0 ((1/h) v n_sv)⋅(u n_su) + c1 (v n_sv)⋅∇u + c2 ∇v⋅(u n_su) with u on the cell around su, v on sv (masked elsewhere)"""
+    fv, fu = p.v(0, sv), p.u(0, su)
+    return (O.frobenius((c[0] / p.h) * (fv * p.n(sv)), fu * p.n(su)) + c[1] * O.frobenius(fv * p.n(sv), p.grad_u(0, su))
+            + c[2] * O.frobenius(p.grad_v(0, sv), fu * p.n(su)))
+
+
+def _skeleton_oracle(bp, V, mesh, integrand, **kw):
+    sides = [[(int(bp.side_cells[i, a]), int(bp.face_var[i, a])) for a in range(2)] for i in range(bp.face_nodes.shape[0])]
+    return O.assemble_matrix_multifield(mesh.D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides,
+                                        _oracle_fields(bp, [V], True), integrand,
+                                        skeleton_geometry=(bp.cell_nodes, bp.dM_cell, bp.ref_normals), **kw)
+
+
+@pytest.mark.parametrize("cells", [(3, 3), (2, 2, 2)])
+def test_unit_normals_of_the_two_cells_around_a_face_are_opposite(cells):
+    """map_unit_normal (accessors.jl:1026-1035) at the mapped face points: unit length, n[1] = -n[2], n[1] points from the first
+    cell around into the second — on a warped mesh, through the tables multifield.py hands to the engine"""
+    D = len(cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells)
+    _warp(mesh)
+    V = H.lagrange_space(mesh, 1, None)
+    bp = MF.skeleton_problem([V], 2, gradients=True)
+    X = mesh.node_coordinates
+    for i in range(bp.face_nodes.shape[0]):
+        c = [X[mesh.cell_nodes[bp.side_cells[i, a] - 1] - 1].mean(axis=0) for a in range(2)]
+        for q in range(bp.w.size):
+            n = []
+            for a in range(2):
+                var = bp.face_var[i, a]
+                J = O.point_geometry(X, mesh.cell_nodes[bp.side_cells[i, a] - 1][None, :], bp.dM_cell[var][q])[0]
+                n.append(O.map_unit_normal(J, bp.ref_normals[var]))
+            assert abs(np.linalg.norm(n[0]) - 1.0) < 1e-14 and np.abs(n[0] + n[1]).max() < 1e-13
+            assert np.dot(n[0], c[1] - c[0]) > 0.0
+
+
+def test_oracle_interior_penalty_terms_cancel_on_a_continuous_space():
+    """test/assembly_tests.jl:329-340: 'The skeleton terms are not needed. They are added just to make sure that they are computed
+    correctly' — on a continuous space jump(u, n) of every basis function vanishes, so the assembled term is zero to rounding"""
+    mesh = H.cartesian_mesh((0, 1, 0, 1), (3, 3))
+    _warp(mesh)
+    V = H.lagrange_space(mesh, 1, "boundary")
+    bp = MF.skeleton_problem([V], 2, gradients=True)
+    full = lambda p: sum(_ip(p, su, sv, (1.0, -0.5, -0.5)) for su in (1, 2) for sv in (1, 2))
+    cp, rv, nz = _skeleton_oracle(bp, V, mesh, full)
+    one = _skeleton_oracle(bp, V, mesh, lambda p: _ip(p, 1, 1, (1.0, -0.5, -0.5)))
+    assert np.abs(one[2]).max() > 0.1 and np.abs(nz).max() < 1e-14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,order", [((4, 3), 1), ((3, 2), 2), ((2, 2, 2), 1)])
+def test_gpu_interior_penalty_blocks_parity(cells, order):
+    D = len(cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells)
+    _warp(mesh)
+    V = H.lagrange_space(mesh, order, [1])
+    bp = MF.skeleton_problem([V], 2 * order, gradients=True)
+    eng = _engine(bp)
+    eng.set_skeleton_cells(bp.cell_nodes, bp.side_cells, bp.dM_cell, bp.ref_normals)
+    eng.matrix_symbolic()
+    gcp, grv = eng.matrix_pattern()
+    # two one-sided blocks with different coefficients: nothing cancels, every term is exercised
+    ca, cb = (2.0, -0.5, 0.25), (1.0, 0.3, -0.5)
+    ref = _skeleton_oracle(bp, V, mesh, lambda p: 1.0 * _ip(p, 1, 1, ca) + 0.7 * _ip(p, 2, 1, cb))
+    assert np.array_equal(ref[0], gcp) and np.array_equal(ref[1], grv)
+    got = eng.matrix_numeric_blocks([(0, 0, E.BLOCK_IP, 1.0, ca), (1, 0, E.BLOCK_IP, 0.7, cb)])
+    assert_values_close(got, ref[2])
+    assert np.array_equal(eng.matrix_numeric_blocks([(0, 0, E.BLOCK_IP, 1.0, ca), (1, 0, E.BLOCK_IP, 0.7, cb)]), got)
+    # the full interior-penalty term on this continuous space: zero to rounding
+    full = eng.matrix_numeric_blocks([(pu, pv, E.BLOCK_IP, 1.0, (1.0, -0.5, -0.5)) for pu in range(2) for pv in range(2)])
+    assert np.abs(full).max() < 1e-12 * np.abs(got).max()
+    with pytest.raises(E.UnsupportedFormError):          # IP needs scalar parts with gradient tables
+        eng2 = _engine(MF.skeleton_problem([V], 2 * order))
+        eng2.matrix_symbolic()
+        eng2.matrix_numeric_blocks([(0, 0, E.BLOCK_IP, 1.0, ca)])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reference_poisson_with_skeleton_terms():
+    """test/assembly_tests.jl:311-360 transcribed: Poisson with Dirichlet data u = x + y, the interior-penalty skeleton terms added
+    to the form 'just to make sure that they are computed correctly'; the discrete solution is the exact one (tol 1e-10)"""
+    import scipy.sparse.linalg as spla
+    mesh = GT.cartesian_mesh((0, 1, 0, 1), (4, 4))
+    Om, Lam, Gd = GT.interior(mesh), GT.skeleton(mesh), GT.boundary(mesh)
+    V = GT.lagrange_space(Om, 1, dirichlet_boundary=Gd)
+    dO, dL = GT.measure(Om, 2), GT.measure(Lam, 2)
+    n = GT.unit_normal(mesh, 1)
+    h = GT.face_diameter_field(Lam)
+    gamma = GT.uniform_quantity(1.0)
+    jump = lambda u, n_, x: u[2](x) * n_[2](x) + u[1](x) * n_[1](x)
+    mean = lambda f, u, x: 0.5 * (f(u[1], x) + f(u[2], x))
+    a = lambda u, v: (GT.integrate(lambda q: GT.dot(GT.grad(u, q), GT.grad(v, q)), dO)
+                      + GT.integrate(lambda x: GT.dot((gamma / h(x)) * jump(v, n, x), jump(u, n, x)) - GT.dot(jump(v, n, x), mean(GT.grad, u, x))
+                                     - GT.dot(mean(GT.grad, v, x), jump(u, n, x)), dL))
+    A = GT.assemble_matrix(a, float, V, V)
+    Ad = GT.assemble_matrix(a, float, V, V, free_or_dirichlet=(GT.FREE, GT.DIRICHLET))
+    xd = V.data.dirichlet_dof_nodes.sum(axis=1)                     # interpolate_dirichlet!(u, uhd), u = sum
+    x = spla.spsolve(A.to_scipy().tocsc(), -(Ad.to_scipy() @ xd))   # l(v) = 0
+    assert np.abs(x - V.data.free_dof_nodes.sum(axis=1)).max() < 1e-10
+    # the skeleton term alone widens the pattern and contributes nothing
+    K = GT.assemble_matrix(lambda u, v: GT.integrate(lambda q: GT.dot(GT.grad(u, q), GT.grad(v, q)), dO), float, V, V)
+    assert A.nzval.size > K.nzval.size and abs(A.to_scipy() - K.to_scipy()).max() < 1e-12
