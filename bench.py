@@ -299,7 +299,16 @@ def timed_loop(torch, stream, fn, steps, barrier=None, spin=0):
     return ev0.elapsed_time(ev1) / steps
 
 
-def run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, steps=10):
+PARTITION_MODE = os.environ.get("GTK_PARTITION_MODE", "recompute")   # "recompute" (communication-avoiding) | "exchange" (ghost-row sum)
+MODE_TEXT = {
+    "recompute": "every rank also assembles the lower neighbour's top cell layer (it holds those cells and their node coordinates anyway), so "
+                 "all cells that touch its own rows are local: NO data-path exchange; own rows bitwise equal to the single-GPU matrix",
+    "exchange": "every cell assembled once; ghost-row partial sums summed into their owner over NVLink peer memory (NCCL fallback) inside the "
+                "sweep kernel's copy-out; exchange plan built on the device",
+}
+
+
+def run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, steps=10, mode=None, t1_known=None):
     """BASELINE config 5 at this GPU count: 512^3 cells as `world` z-slabs, all inputs generated in HBM.  T_1 is measured
     in the same job by rank 0 alone on the whole mesh (device resident: nnz exceeds the Int32 colptr of the ABI's copy-out)."""
     cells = (512, 512, 512)
@@ -330,13 +339,19 @@ def run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, steps=1
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         tm = {}
-        nnz_owned = P.attach_generated(eng, dom, cells, lay, tab, dist, tm)
+        mode = mode or PARTITION_MODE
+        nnz_owned = P.attach_generated(eng, dom, cells, lay, tab, dist, tm, mode=mode)
         out["setup_phases_ms_rank0"] = {k: round(v, 3) for k, v in tm.items()}
-        step = lambda: eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
+        out["partition_mode"] = mode
+        out["partition"] = MODE_TEXT[mode]
+        if mode == "exchange":
+            step = lambda: eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
+        else:
+            step = lambda: eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
     torch.cuda.synchronize()
     sym_ms = 1e3 * (time.perf_counter() - t1)
     if world > 1:   # the NCCL communicator is created once per process in an application: not part of the symbolic phase
-        sym_ms = tm["symbolic"] + tm["exchange_plan"] + tm["peer_memory"]
+        sym_ms = tm["symbolic"] + tm.get("exchange_plan", 0.0) + tm.get("peer_memory", 0.0)
     for _ in range(3):
         step()
     ms = timed_loop(torch, stream, step, steps, barrier, spin=spin_count(8.0 / world))
@@ -346,8 +361,9 @@ def run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, steps=1
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
         nnz_total, ms, sym_ms = int(tot[0].item()), float(mx[1].item()), float(mx[2].item())
-        transport = "peer memory (NVLink stores + flags)" if eng.comm_ghost_info(3) == 1 else "NCCL send/recv"
-        out["exchange"] = {"transport": transport, "bytes_per_step_rank0": eng.comm_ghost_info(2), "plan": "built on the device"}
+        if mode == "exchange":
+            transport = "peer memory (NVLink stores + flags)" if eng.comm_ghost_info(3) == 1 else "NCCL send/recv"
+            out["exchange"] = {"transport": transport, "bytes_per_step_rank0": eng.comm_ghost_info(2), "plan": "built on the device"}
     else:
         nnz_total = int(nnz_owned)
     out.update({"nnz": nnz_total, "ms_per_step": ms, "value": nnz_total / (ms * 1e-3), "unit": UNIT,
@@ -358,7 +374,9 @@ def run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, steps=1
     torch.cuda.synchronize()
     # T_1 on rank 0 (the same measurement when world == 1)
     t1_ms = ms
-    if world > 1:
+    if world > 1 and t1_known is not None:
+        t1_ms = t1_known
+    elif world > 1:
         t1_ms = 0.0
         if rank == 0:
             e1 = E.Engine(local_rank)
@@ -460,17 +478,17 @@ def main():
         host_prep_s, upload_ms = time.perf_counter() - t0, 0.0
         t0 = time.perf_counter()
         setup_tm = {}
-        nnz_owned = P.attach_generated(eng, dom, cells_total, lay, tab, dist, setup_tm)
+        nnz_owned = P.attach_generated(eng, dom, cells_total, lay, tab, dist, setup_tm, mode=PARTITION_MODE)
         nnz_local, n_free_local, n_owned_rows = eng.nnz, lay.n_free, lay.own_hi - lay.own_lo
         n_nodes_local, n_cells_local = (n + 1) ** 2 * (lay.k1 - lay.kc0 + 1), n * n * (lay.k1 - lay.kc0)
     torch.cuda.synchronize()
     symbolic_first_ms = 1e3 * (time.perf_counter() - t0)   # includes lazy CUDA module load + first allocations (+ NCCL init for N > 1)
     symbolic_ms = symbolic_first_ms
     if world > 1:
-        symbolic_ms = setup_tm["symbolic"] + setup_tm["exchange_plan"] + setup_tm["peer_memory"]
+        symbolic_ms = setup_tm["symbolic"] + setup_tm.get("exchange_plan", 0.0) + setup_tm.get("peer_memory", 0.0)
 
     def step():
-        if world > 1:   # one call: sweep + ghost-row summation, the exchange overlapped with the sweep
+        if world > 1 and PARTITION_MODE == "exchange":   # one call: sweep + ghost-row summation, the exchange inside the sweep
             eng.assemble_and_sum_ghost_rows_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
         else:
             eng.assemble_matrix_and_vector_device(E.FORM_LAPLACE, mp, E.FORM_SOURCE_CONST, vp)
@@ -675,9 +693,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": cfg,
-            "partition": "none" if world == 1 else (f"{world} z-slabs of {n}^3 cells generated in HBM, ghost-row sum over " +
-                                                    ("peer memory (NVLink stores + flags)" if eng.comm_ghost_info(3) == 1 else "NCCL send/recv") +
-                                                    f", overlapped with the sweep ({eng.comm_ghost_info(2)} B/step on rank 0); exchange plan built on the device"),
+            "partition": "none" if world == 1 else (f"{world} z-slabs of {n}^3 cells generated in HBM; mode '{PARTITION_MODE}': " + MODE_TEXT[PARTITION_MODE] +
+                                                    (f" ({eng.comm_ghost_info(2)} B/step on rank 0, " + ("peer memory" if eng.comm_ghost_info(3) == 1 else "NCCL") + ")"
+                                                     if PARTITION_MODE == "exchange" else "") +
+                                                    "; the other mode: GTK_PARTITION_MODE=exchange|recompute; config5 reports both"),
             "fast_path": eng.info(5), "cpu_affinity": affinity,
             "setup_phases_ms_rank0": None if world == 1 else {k: round(v, 3) for k, v in setup_tm.items()},
             "symbolic_ms": symbolic_ms, "symbolic_first_ms": symbolic_first_ms, "input_upload_ms": upload_ms, "host_prep_s": host_prep_s,
@@ -728,6 +747,11 @@ def main():
     if not args.no_config5:
         try:
             c5 = run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream)
+            if world > 1:      # the other way of completing the own rows, same job, same T_1
+                other = "exchange" if PARTITION_MODE == "recompute" else "recompute"
+                c5o = run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, mode=other, t1_known=c5.get("t1_ms"))
+                c5["other_mode"] = {k: c5o.get(k) for k in ("partition_mode", "partition", "ms_per_step", "value", "strong_efficiency", "symbolic_ms",
+                                                           "exchange", "setup_phases_ms_rank0")}
         except Exception as exc:   # reported, never hidden
             c5 = {"error": f"{type(exc).__name__}: {exc}"}
         if rank == 0:

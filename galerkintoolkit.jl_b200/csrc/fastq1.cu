@@ -801,7 +801,8 @@ __device__ __forceinline__ void affine_w_item(const SweepArgs& a, const int i0, 
         }
       }
     }
-    const bool ortho = __all_sync(0xFFFFFFFFu, my_ortho);   // (also the barrier between the cell and the node phase)
+    const bool ortho = __all_sync(0xFFFFFFFFu, my_ortho);
+    __syncwarp();                                          // the vote does not order shared memory: CellW written above is read below
     // ---- B) this lane's node: two passes over its 4 cells keep the live registers low (27 accumulators at a time) ----
     using Rows = std::make_integer_sequence<int, 8>;
     double acc[27], accb = pendb;

@@ -15,6 +15,15 @@ Rank r's local problem:
   ghost rows dofs of node layer k1 (owner r+1): their partial sums are sent up and added there.
 After the exchange every rank holds its own rows fully summed = the row-partitioned matrix
 PartitionedArrays.assemble! would produce.  Same GPU count ⇒ bitwise-identical results.
+
+Two ways to complete the own rows (``mode``):
+  "exchange"   as above: every cell is assembled once, ghost-row partial sums travel to their owner (NVLink / NCCL);
+  "recompute"  communication-avoiding: the halo cell layer k0-1 is ALSO assembled numerically (it is in the local mesh anyway,
+               with its node coordinates), so every cell that touches an own row is local and the own rows are complete without
+               any data-path exchange.  Costs one redundant cell layer per rank (1/64 of a config-5 slab) instead of 2 x 38 MB
+               of ghost entries, a flag handshake and two rounds of short work items; the ghost rows (layer k1, and the halo's
+               bottom layer k0-1) hold partial sums nobody reads.  Own rows are BITWISE those of the single-GPU matrix for any
+               GPU count (same cells, same order, same coordinates), which the exchange cannot offer.
 """
 from __future__ import annotations
 
@@ -97,7 +106,7 @@ def slab_layout(cells: Sequence[int], rank: int, world: int) -> SlabLayout:
     return SlabLayout(rank, world, k0, k1, kc0, ((k0 - kc0) * n1 * n2, (k1 - k0) * n1 * n2), n_free, gid0, own_start, own_lo, own_hi)
 
 
-def attach_generated(engine, domain, cells, layout: SlabLayout, tab, dist, timings: Optional[dict] = None):
+def attach_generated(engine, domain, cells, layout: SlabLayout, tab, dist, timings: Optional[dict] = None, mode: str = "exchange"):
     """attach_device() with the slab's mesh and space generated in HBM (no mesh-sized host array, no upload): returns the
     number of nonzeros in the rows this rank owns.  `timings` (optional dict) receives host wall-clock milliseconds of the
     phases: generate, symbolic (pattern + sweep plan), comm_init (NCCL communicator), exchange_plan, peer_memory."""
@@ -113,12 +122,17 @@ def attach_generated(engine, domain, cells, layout: SlabLayout, tab, dist, timin
     nf, _ = engine.set_cartesian_q1_problem(domain, cells, layout.kc0, layout.k1, slab_local=True)
     assert nf == layout.n_free
     engine.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
-    engine.set_active_cells(*layout.active_cells)
+    if mode == "exchange":
+        engine.set_active_cells(*layout.active_cells)
+    elif mode != "recompute":
+        raise ValueError(f"unknown partition mode {mode!r}")
     lap("generate")
     engine.matrix_symbolic()
     engine.vector_symbolic()
     colptr, _ = engine.matrix_pattern(want_rowval=False)      # synchronises
     lap("symbolic")
+    if mode == "recompute":       # every cell that touches an own row is assembled locally: nothing to exchange
+        return int(colptr[layout.own_hi]) - int(colptr[layout.own_lo])
     uid = [type(engine).comm_unique_id() if layout.rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     engine.comm_init(layout.rank, layout.world, uid[0])
@@ -336,6 +350,21 @@ def attach(engine, part: SlabPart, tab, dist):
     owned = owned_rows_mask(part)
     n_owned_nnz = int(owned[rowval.astype(np.int64) - 1].sum())
     return colptr, rowval, n_owned_nnz
+
+
+def attach_recompute(engine, part: SlabPart, tab):
+    """mode "recompute" for a host-built SlabPart: all local cells (own + halo layer) are numerically active, no communicator,
+    no exchange plan.  After any numeric call the rows this rank owns are complete.  Returns (colptr, rowval, n_owned_nnz)."""
+    m, V = part.mesh, part.space
+    engine.set_mesh(m.node_coordinates, m.cell_nodes)
+    engine.set_space(V.cell_dofs, V.n_free, V.n_dirichlet)
+    engine.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+    engine.matrix_symbolic()
+    engine.vector_symbolic()
+    colptr, rowval = engine.matrix_pattern()
+    lo = int(np.clip(part.own_start[part.rank] - part.gid0, 0, V.n_free))
+    hi = int(np.clip(part.own_start[part.rank + 1] - part.gid0, 0, V.n_free))
+    return colptr, rowval, int(colptr[hi]) - int(colptr[lo])
 
 
 def attach_device(engine, part: SlabPart, tab, dist, want_pattern: bool = True):

@@ -71,6 +71,34 @@ def _worker(rank, world, port, cells, dom, q):
         eng2.comm_sum_ghost_rows()
         results.append((eng2.copy_nzval(), eng2.copy_vector()))
         eng2.close()
+        # communication-avoiding mode: the halo cell layer is assembled too, nothing is exchanged; the own rows are BITWISE
+        # those of the single-GPU assembly of the whole mesh (computed here on this rank's GPU), for any number of ranks
+        eng3 = E.Engine(rank)
+        cp3, rv3, n_owned3 = P.attach_recompute(eng3, part, tab)
+        assert np.array_equal(cp3, colptr) and np.array_equal(rv3, rowval) and n_owned3 == n_owned
+        eng3.assemble_matrix_and_vector_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+        nz3, b3 = eng3.copy_nzval(), eng3.copy_vector()
+        eng3.close()
+        check_owned_rows(part, colptr, rowval, nz3, b3, A_glob, bg)
+        eng1 = E.Engine(rank)
+        eng1.set_mesh(mesh.node_coordinates, mesh.cell_nodes)
+        eng1.set_space(V.cell_dofs, V.n_free, V.n_dirichlet)
+        eng1.set_tabulation(tab.w, tab.N, tab.dN, tab.M, tab.dM)
+        eng1.matrix_symbolic(); eng1.vector_symbolic()
+        cp1, rv1 = eng1.matrix_pattern()
+        eng1.assemble_matrix_and_vector_device(E.FORM_LAPLACE, dict(alpha=1.0), E.FORM_SOURCE_CONST, dict(f_const=[1.0]))
+        A1 = sp.csc_matrix((eng1.copy_nzval(), rv1.astype(np.int64) - 1, cp1.astype(np.int64) - 1), shape=(V.n_free, V.n_free)).tocsr()
+        b1 = eng1.copy_vector()
+        eng1.close()
+        A3 = sp.csc_matrix((nz3, rv3.astype(np.int64) - 1, cp3.astype(np.int64) - 1), shape=(part.space.n_free, part.space.n_free)).tocsr()
+        own_rows = np.flatnonzero(part.row_owner == part.rank)
+        g = part.row_gid - 1                                   # local row / column -> global (0-based)
+        for r in own_rows[:: max(1, own_rows.size // 400)]:
+            lo, hi = A3.indptr[r], A3.indptr[r + 1]
+            ref_row = A1.getrow(g[r])
+            assert np.array_equal(g[A3.indices[lo:hi]], ref_row.indices)
+            assert A3.data[lo:hi].tobytes() == ref_row.data.tobytes(), "own rows must be bitwise the single-GPU rows"
+        assert b3[own_rows].tobytes() == b1[g[own_rows]].tobytes()
         nzval, b = results[0]
         check_owned_rows(part, colptr, rowval, nzval, b, A_glob, bg)
         own = part.row_owner == part.rank
