@@ -25,8 +25,9 @@ index, assembly.jl:584-588), and both also report the FIRST assembly (symbolic +
   cpu_baseline    the C restatement of the reference's CPU path (oracle/, "port") on this box
 
 N > 1: one process per GPU (torchrun); the headline mesh is a stack of N z-slabs of 128^3 cells (weak scaling), generated
-in HBM (gtk_set_cartesian_q1_problem); ghost-row contributions of the slab interfaces are summed into their owner over
-NVLink peer memory (NCCL fallback) inside the timed step; the exchange plan is built on the device.
+in HBM (gtk_set_cartesian_q1_problem).  A rank's own rows are completed either by also assembling the lower neighbour's top
+cell layer (GTK_PARTITION_MODE=recompute, default: no data-path exchange, own rows bitwise the single-GPU rows) or by summing
+ghost-row contributions into their owner over NVLink peer memory / NCCL inside the timed step (=exchange).  config5 reports both.
 """
 import argparse
 import json
