@@ -369,7 +369,7 @@ def run_config5(torch, dist, E, P, tab, rank, world, local_rank, stream, steps=1
         nnz_total = int(nnz_owned)
     out.update({"nnz": nnz_total, "ms_per_step": ms, "value": nnz_total / (ms * 1e-3), "unit": UNIT,
                 "symbolic_ms": sym_ms, "symbolic_includes": "pattern + sweep plan" +
-                ("" if world == 1 else " + exchange plan (device) + peer-memory handles; NCCL communicator creation and input generation listed in setup_phases_ms_rank0")})
+                ("" if world == 1 or mode != "exchange" else " + exchange plan (device) + peer-memory handles; NCCL communicator creation and input generation listed in setup_phases_ms_rank0")})
     eng.close()
     del eng
     torch.cuda.synchronize()

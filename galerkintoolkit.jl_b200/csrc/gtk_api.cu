@@ -265,6 +265,20 @@ int32_t gtk_matrix_symbolic(gtk_ctx* ctx, int32_t rfd, int32_t cfd, int64_t* nnz
   return GTK_OK;
 }
 
+int32_t gtk_matrix_colptr_at(gtk_ctx* ctx, int32_t n, const int64_t* cols, int64_t* out) {
+  if (!ctx) return GTK_ERR_INVALID;
+  MatSym& m = ctx->ms;
+  if (!m.ready) GTK_FAIL(GTK_ERR_STATE, "gtk_matrix_colptr_at: no symbolic result");
+  if (n < 0 || (n && (!cols || !out))) GTK_FAIL(GTK_ERR_INVALID, "gtk_matrix_colptr_at: bad arguments");
+  GTK_CK(cudaSetDevice(ctx->device));
+  for (int i = 0; i < n; ++i) {
+    if (cols[i] < 0 || cols[i] > m.n_cols) GTK_FAIL(GTK_ERR_INVALID, "gtk_matrix_colptr_at: column out of range");
+    GTK_CK(cudaMemcpyAsync(out + i, m.colptr + cols[i], sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  GTK_CK(cudaStreamSynchronize(ctx->stream));
+  return GTK_OK;
+}
+
 int32_t gtk_matrix_pattern(gtk_ctx* ctx, int32_t* colptr, int32_t* rowval) {
   if (!ctx) return GTK_ERR_INVALID;
   MatSym& m = ctx->ms;

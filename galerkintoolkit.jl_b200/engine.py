@@ -39,6 +39,7 @@ ABI_SYMBOLS = [
     "gtk_set_parts", "gtk_matrix_numeric_blocks", "gtk_matrix_numeric_blocks_device",
     "gtk_vector_assemble_blocks", "gtk_vector_assemble_blocks_device",
     "gtk_matrix_sum_symbolic", "gtk_matrix_sum_numeric", "gtk_matrix_sum_numeric_device", "gtk_set_skeleton_cells",
+    "gtk_matrix_colptr_at",
 ]
 BLOCK_ZERO, BLOCK_MASS, BLOCK_LAPLACE, BLOCK_VALU_DIVV, BLOCK_DIVU_VALV, BLOCK_IP = 0, 1, 2, 3, 4, 5
 MAX_PARTS = 8
@@ -143,6 +144,7 @@ def load_library() -> C.CDLL:
         "gtk_vector_assemble_blocks": (i32, [vp, i32, C.POINTER(VBlock), i32, vp]),
         "gtk_vector_assemble_blocks_device": (i32, [vp, i32, C.POINTER(VBlock), i32]),
         "gtk_set_skeleton_cells": (i32, [vp, i64, i32, vp, vp, vp, vp]),
+        "gtk_matrix_colptr_at": (i32, [vp, i32, vp, vp]),
         "gtk_matrix_sum_symbolic": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
         "gtk_matrix_sum_numeric": (i32, [vp, i32, C.POINTER(vp), vp]),
         "gtk_matrix_sum_numeric_device": (i32, [vp, i32, C.POINTER(vp)]),
@@ -413,6 +415,13 @@ class Engine:
         rowval = np.empty(self.nnz, dtype=np.int32) if want_rowval else None
         self._ck(self.lib.gtk_matrix_pattern(self.h, _ptr(colptr), _ptr(rowval)))
         return colptr, rowval
+
+    def matrix_colptr_at(self, cols) -> np.ndarray:
+        """0-based colptr entries of a few (0-based) columns, straight from the device"""
+        c = np.ascontiguousarray(cols, dtype=np.int64)
+        out = np.empty(c.size, dtype=np.int64)
+        self._ck(self.lib.gtk_matrix_colptr_at(self.h, c.size, _ptr(c), _ptr(out)))
+        return out
 
     def matrix_pattern_i64(self, want_rowval: bool = True):
         """colptr / rowval as Int64 (assembly_options index_type = Int64; no 2^31 limit on nnz)"""

@@ -129,10 +129,10 @@ def attach_generated(engine, domain, cells, layout: SlabLayout, tab, dist, timin
     lap("generate")
     engine.matrix_symbolic()
     engine.vector_symbolic()
-    colptr, _ = engine.matrix_pattern(want_rowval=False)      # synchronises
+    own = engine.matrix_colptr_at([layout.own_lo, layout.own_hi])      # synchronises; two entries instead of the whole colptr
     lap("symbolic")
     if mode == "recompute":       # every cell that touches an own row is assembled locally: nothing to exchange
-        return int(colptr[layout.own_hi]) - int(colptr[layout.own_lo])
+        return int(own[1] - own[0])
     uid = [type(engine).comm_unique_id() if layout.rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     engine.comm_init(layout.rank, layout.world, uid[0])
@@ -141,7 +141,7 @@ def attach_generated(engine, domain, cells, layout: SlabLayout, tab, dist, timin
     lap("exchange_plan")
     engine.comm_connect_peer_memory()
     lap("peer_memory")
-    return int(colptr[layout.own_hi]) - int(colptr[layout.own_lo])
+    return int(own[1] - own[0])
 
 
 def slab_problem(domain: Sequence[float], cells: Sequence[int], rank: int, world: int,

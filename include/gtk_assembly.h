@@ -153,6 +153,10 @@ int32_t gtk_matrix_pattern(gtk_ctx* ctx, int32_t* colptr, int32_t* rowval);
  * of a SparseMatrixCSC{Float64,Int64}.  Also the way out for patterns with nnz >= 2^31, which the Int32 variant refuses
  * (GTK_ERR_TOO_LARGE) — e.g. BASELINE config 5 assembled on one GPU (3.59e9 nonzeros). */
 int32_t gtk_matrix_pattern_i64(gtk_ctx* ctx, int64_t* colptr, int64_t* rowval);
+/* colptr entries of the selected matrix for a few columns (0-based columns, n_cols allowed; values 0-based positions in nzval):
+ * what a host needs to count the stored entries of a column range — e.g. the rows a rank owns in a partitioned assembly —
+ * without copying the whole colptr out. */
+int32_t gtk_matrix_colptr_at(gtk_ctx* ctx, int32_t n, const int64_t* cols, int64_t* out);
 /* Numeric assembly = generated loop (compiler.jl:1826-1923) + contribute!
  * (assembly.jl:189-208) + compress/compress! (assembly.jl:571-588).  Re-callable:
  * second and later calls are GT.update_matrix! (problems.jl:352-361). */
