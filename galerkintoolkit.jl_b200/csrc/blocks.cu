@@ -48,6 +48,8 @@ struct BlockArgs {
   int b_form[BP_MAX][BP_MAX];            // [part of u = row][part of v = column]
   double b_alpha[BP_MAX][BP_MAX];
   double v_alpha[BP_MAX], v_f[BP_MAX][3];   // linear forms: per part
+  double v_c[BP_MAX][3];                 // linear forms with data g(x_q): k0 v g + (k1/h) v g + k2 (n⋅∇v) g
+  const double* v_g;                     // [n_faces][nq] data sampled at the faces' quadrature points, or null
   // skeleton faces with gradient / normal terms (GTK_BLOCK_IP): geometry of the cells around
   const int32_t* cellD_nodes;            // [n_Dcells][nlnD] 1-based
   const int32_t* side_cells;             // [n_faces][n_sides] 1-based cell around
@@ -227,10 +229,13 @@ template <int D, int d>
 __global__ void __launch_bounds__(128) k_elem_vblocks(BlockArgs a) {
   extern __shared__ double smem[];
   const int nq = a.nq, L = a.L;
-  double* dV = smem;
+  double* dV = smem;                                   // [cb][nq]
+  double* G = dV + (size_t)a.cb * nq;                  // [cb][nq][nls_total][D]   (faces with gradient / normal terms only)
+  double* Nrm = G + (a.need_grad ? (size_t)a.cb * nq * a.nls_total * D : 0);
+  double* hF = Nrm + (a.skel ? (size_t)a.cb * nq * a.n_sides * D : 0);
   const int64_t cell0 = (int64_t)blockIdx.x * a.cb;
   const int ncb = (int)min((int64_t)a.cb, a.n_cells - cell0);
-  blocks_phase_a<D, d>(a, cell0, ncb, nullptr, dV);
+  blocks_phase_a<D, d>(a, cell0, ncb, a.skel ? G : nullptr, dV, a.skel ? Nrm : nullptr, a.skel ? hF : nullptr);
   __syncthreads();
   for (int t = threadIdx.x; t < ncb * L; t += blockDim.x) {
     const int cl = t / L, i = t - cl * L;
@@ -241,8 +246,28 @@ __global__ void __launch_bounds__(128) k_elem_vblocks(BlockArgs a) {
       const int il = i - a.p_off[p], nc = a.p_ncomp[p], nls = a.p_nls[p];
       const int ia = il / nc, ic = il - ia * nc;
       const double* Np = a.p_N[p] + (size_t)variant_of(a, cell, p) * nq * nls + ia;
-      const double f = a.v_f[p][ic], alpha = a.v_alpha[p];
-      for (int q = 0; q < nq; ++q) acc += (alpha * (f * Np[q * nls])) * dV[cl * nq + q];
+      const double alpha = a.v_alpha[p];
+      if (!a.v_g) {
+        const double f = a.v_f[p][ic];
+        for (int q = 0; q < nq; ++q) acc += (alpha * (f * Np[q * nls])) * dV[cl * nq + q];
+      } else {
+        // data terms (Nitsche right-hand side, docs/src/src_jl/example_hello_world_dg.jl:83-87): g sampled at the face points
+        const double k0 = a.v_c[p][0], k1 = a.skel ? a.v_c[p][1] / hF[cl] : 0.0, k2 = a.v_c[p][2];
+        const double* gq = a.v_g + cell * nq;
+        for (int q = 0; q < nq; ++q) {
+          const double fv = Np[q * nls];
+          double t = (k0 * fv) * gq[q] + (k1 * fv) * gq[q];
+          if constexpr (D != d) if (a.skel && k2 != 0.0) {
+            const double* gv = G + ((size_t)(cl * nq + q) * a.nls_total + a.p_goff[p] + ia) * D;
+            const double* nv = Nrm + ((size_t)(cl * nq + q) * a.n_sides + a.p_side[p]) * D;
+            double dn = nv[0] * gv[0];
+#pragma unroll
+            for (int k = 1; k < D; ++k) dn += nv[k] * gv[k];
+            t += k2 * (dn * gq[q]);
+          }
+          acc += (alpha * t) * dV[cl * nq + q];
+        }
+      }
     }
     a.out[cell * (int64_t)L + i] = acc;
   }
@@ -295,10 +320,12 @@ int32_t fill(gtk_ctx* ctx, BlockArgs& a) {
     a.p_N[p] = on ? ps->tab + ps->N_at[p] : nullptr;
     a.p_dN[p] = on && ps->has_dN[p] ? ps->tab + ps->dN_at[p] : nullptr;
     a.v_alpha[p] = 0.0;
+    for (int k = 0; k < 3; ++k) a.v_c[p][k] = 0.0;
     for (int k = 0; k < 3; ++k) a.v_f[p][k] = 0.0;
     for (int q = 0; q < BP_MAX; ++q) { a.b_form[p][q] = GTK_BLOCK_ZERO; a.b_alpha[p][q] = 0.0; }
   }
   a.face_var = ps->face_var;
+  a.v_g = nullptr;
   a.skel = ps->skel ? 1 : 0;
   a.cellD_nodes = ps->cellD_nodes; a.side_cells = ps->side_cells; a.nlnD = ps->nlnD;
   a.dMc = ps->skel_tab; a.nref = ps->skel_tab ? ps->skel_tab + ps->nref_at : nullptr;
@@ -399,11 +426,11 @@ extern "C" int32_t gtk_set_skeleton_cells(gtk_ctx* ctx, int64_t n_cells, int32_t
   if (!ctx) return GTK_ERR_INVALID;
   PartsState* ps = parts(ctx);
   if (!ps) GTK_FAIL(GTK_ERR_STATE, "gtk_set_skeleton_cells: call gtk_set_parts first");
-  if (ctx->dman != ctx->D - 1 || ps->n_sides != 2) GTK_FAIL(GTK_ERR_STATE, "gtk_set_skeleton_cells: the integration faces must be (D-1)-faces with two cells around");
+  if (ctx->dman != ctx->D - 1) GTK_FAIL(GTK_ERR_STATE, "gtk_set_skeleton_cells: the integration faces must be (D-1)-faces (skeleton: two cells around, boundary: one)");
   if (n_cells < 1 || n_lnodes < 2 || !cell_nodes || !side_cells || !dM_cell || !ref_normals) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_skeleton_cells: bad arguments");
   GTK_CK(cudaSetDevice(ctx->device));
   const int D = ctx->D;
-  const size_t nf2 = (size_t)ctx->n_cells * 2;
+  const size_t nf2 = (size_t)ctx->n_cells * ps->n_sides;
   for (size_t i = 0; i < nf2; ++i)
     if (side_cells[i] < 1 || side_cells[i] > n_cells) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_skeleton_cells: side_cells out of range");
   for (size_t i = 0; i < (size_t)n_cells * n_lnodes; ++i)
@@ -432,7 +459,8 @@ static int32_t launch_blocks(gtk_ctx* ctx, BlockArgs& a, bool matrix) {
   const int D = ctx->D, dm = ctx->dman;
   size_t per_cell = (size_t)ctx->nq * sizeof(double);
   if (matrix && a.need_grad) per_cell += (size_t)ctx->nq * a.nls_total * D * sizeof(double);
-  if (matrix && a.skel) per_cell += ((size_t)ctx->nq * a.n_sides * D + 1) * sizeof(double);
+  if (!matrix && a.skel) per_cell += (size_t)ctx->nq * a.nls_total * D * sizeof(double);
+  if (a.skel) per_cell += ((size_t)ctx->nq * a.n_sides * D + 1) * sizeof(double);
   size_t smem;
   int32_t rc = pick(ctx, per_cell, &a.cb, &smem);
   if (rc) return rc;
@@ -520,7 +548,7 @@ extern "C" int32_t gtk_matrix_numeric_blocks(gtk_ctx* ctx, int32_t n_blocks, con
   return gtk_copy_nzval(ctx, nzval);
 }
 
-extern "C" int32_t gtk_vector_assemble_blocks_device(gtk_ctx* ctx, int32_t n, const gtk_vblock* vb, int32_t accumulate) {
+extern "C" int32_t gtk_vector_assemble_blocks_data_device(gtk_ctx* ctx, int32_t n, const gtk_vblock* vb, const double* g_qp, int32_t accumulate) {
   if (!ctx) return GTK_ERR_INVALID;
   if (n < 0 || (n && !vb)) GTK_FAIL(GTK_ERR_INVALID, "gtk_vector_assemble_blocks: bad arguments");
   GTK_CK(cudaSetDevice(ctx->device));
@@ -532,7 +560,20 @@ extern "C" int32_t gtk_vector_assemble_blocks_device(gtk_ctx* ctx, int32_t n, co
     if (vb[b].part < 0 || vb[b].part >= ps->n_parts) GTK_FAIL(GTK_ERR_INVALID, "gtk_vector_assemble_blocks: part index out of range");
     if (a.v_alpha[vb[b].part] != 0.0) GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "one term per part; no CPU fallback");
     a.v_alpha[vb[b].part] = vb[b].alpha;
-    for (int k = 0; k < 3; ++k) a.v_f[vb[b].part][k] = vb[b].f_const[k];
+    for (int k = 0; k < 3; ++k) { a.v_f[vb[b].part][k] = vb[b].f_const[k]; a.v_c[vb[b].part][k] = vb[b].c[k]; }
+    if (g_qp && ps->ncomp[vb[b].part] != 1) GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "data terms need scalar parts; no CPU fallback");
+    if (g_qp && (vb[b].c[1] != 0.0 || vb[b].c[2] != 0.0) && (!ps->skel || !ps->has_dN[vb[b].part]))
+      GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "face-diameter / normal-derivative data terms need gtk_set_skeleton_cells and gradient tables; no CPU fallback");
+  }
+  if (g_qp) {
+    const size_t ng = (size_t)ctx->n_cells * ctx->nq;
+    if ((rc = ensure_d(ctx, &ctx->f_dev, &ctx->f_cap, ng))) return rc;
+    GTK_CK(cudaMemcpyAsync(ctx->f_dev, g_qp, ng * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    GTK_CK(cudaStreamSynchronize(ctx->stream));   // borrowed host buffer
+    a.v_g = ctx->f_dev;
+    a.need_grad = a.skel;
+  } else {
+    a.skel = 0;
   }
   if (!ctx->vs.ready && (rc = gtk_symbolic_vector_impl(ctx, GTK_FREE))) return rc;
   VecSym& v = ctx->vs;
@@ -547,6 +588,17 @@ extern "C" int32_t gtk_vector_assemble_blocks_device(gtk_ctx* ctx, int32_t n, co
   a.out = ctx->BE;
   if ((rc = launch_blocks(ctx, a, false))) return rc;
   return gtk_reduce_rows_launch(ctx, accumulate ? 1 : 0);
+}
+
+extern "C" int32_t gtk_vector_assemble_blocks_device(gtk_ctx* ctx, int32_t n, const gtk_vblock* vb, int32_t accumulate) {
+  return gtk_vector_assemble_blocks_data_device(ctx, n, vb, nullptr, accumulate);
+}
+
+extern "C" int32_t gtk_vector_assemble_blocks_data(gtk_ctx* ctx, int32_t n, const gtk_vblock* vb, const double* g_qp, int32_t accumulate, double* b) {
+  int32_t rc = gtk_vector_assemble_blocks_data_device(ctx, n, vb, g_qp, accumulate);
+  if (rc) return rc;
+  if (!b) GTK_FAIL(GTK_ERR_INVALID, "gtk_vector_assemble_blocks_data: b is null");
+  return gtk_copy_vector(ctx, b);
 }
 
 extern "C" int32_t gtk_vector_assemble_blocks(gtk_ctx* ctx, int32_t n, const gtk_vblock* vb, int32_t accumulate, double* b) {

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "gtk_set_parts", "gtk_matrix_numeric_blocks", "gtk_matrix_numeric_blocks_device",
     "gtk_vector_assemble_blocks", "gtk_vector_assemble_blocks_device",
     "gtk_matrix_sum_symbolic", "gtk_matrix_sum_numeric", "gtk_matrix_sum_numeric_device", "gtk_set_skeleton_cells",
-    "gtk_matrix_colptr_at",
+    "gtk_matrix_colptr_at", "gtk_vector_assemble_blocks_data", "gtk_vector_assemble_blocks_data_device",
 ]
 BLOCK_ZERO, BLOCK_MASS, BLOCK_LAPLACE, BLOCK_VALU_DIVV, BLOCK_DIVU_VALV, BLOCK_IP = 0, 1, 2, 3, 4, 5
 MAX_PARTS = 8
@@ -71,7 +71,7 @@ class Block(C.Structure):      # gtk_block
 
 
 class VBlock(C.Structure):     # gtk_vblock
-    _fields_ = [("part", C.c_int32), ("alpha", C.c_double), ("f_const", C.c_double * 3)]
+    _fields_ = [("part", C.c_int32), ("alpha", C.c_double), ("f_const", C.c_double * 3), ("c", C.c_double * 3)]
 
 
 _lib = None
@@ -145,6 +145,8 @@ def load_library() -> C.CDLL:
         "gtk_vector_assemble_blocks_device": (i32, [vp, i32, C.POINTER(VBlock), i32]),
         "gtk_set_skeleton_cells": (i32, [vp, i64, i32, vp, vp, vp, vp]),
         "gtk_matrix_colptr_at": (i32, [vp, i32, vp, vp]),
+        "gtk_vector_assemble_blocks_data": (i32, [vp, i32, C.POINTER(VBlock), vp, i32, vp]),
+        "gtk_vector_assemble_blocks_data_device": (i32, [vp, i32, C.POINTER(VBlock), vp, i32]),
         "gtk_matrix_sum_symbolic": (i32, [vp, i32, C.POINTER(vp), C.POINTER(i64)]),
         "gtk_matrix_sum_numeric": (i32, [vp, i32, C.POINTER(vp), vp]),
         "gtk_matrix_sum_numeric_device": (i32, [vp, i32, C.POINTER(vp)]),
@@ -360,8 +362,9 @@ class Engine:
         self._ck(self.lib.gtk_matrix_sum_numeric(self.h, len(sources), arr, _ptr(nz)))
         return nz
 
-    def vector_assemble_blocks(self, vblocks, accumulate: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """vblocks: iterable of (part, alpha, f_const)"""
+    def vector_assemble_blocks(self, vblocks, accumulate: bool = False, out: Optional[np.ndarray] = None, g_qp=None) -> np.ndarray:
+        """vblocks: iterable of (part, alpha, f_const) — or, with data g_qp [n_faces, n_q], (part, alpha, (c0, c1, c2)):
+        ∫ alpha g (c0 v + (c1/h) v + c2 n⋅∇v)"""
         if self.n_vec_rows == 0:
             self.vector_symbolic(FREE)
         vblocks = list(vblocks)
@@ -372,9 +375,14 @@ class Engine:
             f = np.atleast_1d(np.asarray(f, dtype=np.float64)).reshape(-1)
             fv[: f.size] = f
             for c in range(3):
-                arr[k].f_const[c] = fv[c]
+                arr[k].f_const[c] = 0.0 if g_qp is not None else fv[c]
+                arr[k].c[c] = fv[c] if g_qp is not None else 0.0
         b = np.empty(self.n_vec_rows, dtype=np.float64) if out is None else out
-        self._ck(self.lib.gtk_vector_assemble_blocks(self.h, len(vblocks), arr, 1 if accumulate else 0, _ptr(b)))
+        if g_qp is None:
+            self._ck(self.lib.gtk_vector_assemble_blocks(self.h, len(vblocks), arr, 1 if accumulate else 0, _ptr(b)))
+        else:
+            g = _f64(g_qp)
+            self._ck(self.lib.gtk_vector_assemble_blocks_data(self.h, len(vblocks), arr, _ptr(g), 1 if accumulate else 0, _ptr(b)))
         return b
 
     # -- matrix ---------------------------------------------------------------------

@@ -86,7 +86,7 @@ def measure(domain: Domain, degree: int) -> Measure:
 class Space:
     """lagrange_space(Ω, order; dirichlet_boundary, tensor_size) (space.jl:1702-1735)."""
 
-    def __init__(self, domain: Domain, order: int, dirichlet_boundary: Optional[Domain] = None, tensor_size=None):
+    def __init__(self, domain: Domain, order: int, dirichlet_boundary: Optional[Domain] = None, tensor_size=None, continuous: bool = True):
         if domain.kind != "interior":
             raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "spaces on boundary domains are out of scope")
         n_comp = 1 if tensor_size is None else int(np.prod(tensor_size))
@@ -94,7 +94,13 @@ class Space:
         if dirichlet_boundary is not None:
             bc = "boundary" if dirichlet_boundary.sides is None else list(dirichlet_boundary.sides)
         self.domain = domain
-        self.data = _hp.lagrange_space(domain.mesh, order, bc, n_comp)
+        self.continuous = bool(continuous)
+        if not continuous:
+            if bc is not None:
+                raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "discontinuous spaces take their boundary conditions weakly (no dirichlet_boundary)")
+            self.data = _hp.discontinuous_lagrange_space(domain.mesh, order, n_comp)
+        else:
+            self.data = _hp.lagrange_space(domain.mesh, order, bc, n_comp)
         self._tab = {}
 
     # -- reference accessors ---------------------------------------------------
@@ -125,8 +131,8 @@ class Space:
         return cartesian_product(self, other)
 
 
-def lagrange_space(domain, order, dirichlet_boundary=None, tensor_size=None) -> Space:
-    return Space(domain, order, dirichlet_boundary, tensor_size)
+def lagrange_space(domain, order, dirichlet_boundary=None, tensor_size=None, continuous: bool = True) -> Space:
+    return Space(domain, order, dirichlet_boundary, tensor_size, continuous)
 
 
 class ProductSpace:
@@ -229,6 +235,10 @@ class _UnitNormal:
             raise IndexError("a skeleton face has two cells around: n[1], n[2]")
         return lambda x: Normal(k)
 
+    def __call__(self, x):
+        """on a boundary face: the outward unit normal of the one cell around"""
+        return Normal(0)
+
 
 def unit_normal(mesh, d: int) -> _UnitNormal:
     if d != mesh.D - 1:
@@ -238,8 +248,8 @@ def unit_normal(mesh, d: int) -> _UnitNormal:
 
 def face_diameter_field(domain: Domain):
     """h_Λ = GT.face_diameter_field(Λ): h_Λ(x) is the diameter of the face x lies on (field.jl:488-492)"""
-    if domain.kind != "skeleton":
-        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "face diameters are supported on skeleton domains on the GPU path")
+    if domain.kind not in ("skeleton", "boundary"):
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "face diameters are supported on skeleton and boundary domains on the GPU path")
     return lambda x: FaceDiameter()
 
 
@@ -643,8 +653,25 @@ def _expand(t):
                                "with constant factors); refusing to fall back to a CPU loop")
 
 
-def _is_blocks_case(space, meas: "Measure") -> bool:
-    return isinstance(space, ProductSpace) or meas.domain.kind == "skeleton"
+def _has_face_terms(term) -> bool:
+    """unit normals, face diameters or gradients of form arguments somewhere in the term"""
+    if isinstance(term, (Normal, FaceDiameter)):
+        return True
+    if isinstance(term, FormArg):
+        return term.op != "value"
+    if isinstance(term, Call):
+        return _has_face_terms(term.a) or (term.b is not None and _has_face_terms(term.b))
+    return False
+
+
+def _is_blocks_case(space, meas: "Measure", term=None) -> bool:
+    """product spaces, skeleton integrals, and boundary integrals that need the cell around the face (Nitsche terms: normals,
+    gradients, face diameters) or live on a discontinuous space go to the block kernels"""
+    if isinstance(space, ProductSpace) or meas.domain.kind == "skeleton":
+        return True
+    if meas.domain.kind == "boundary":
+        return any(not f.continuous for f in fields(space)) or (term is not None and _has_face_terms(term))
+    return False
 
 
 def _block_problem(space, meas: "Measure"):
@@ -654,12 +681,14 @@ def _block_problem(space, meas: "Measure"):
         return _mf.skeleton_problem(data, meas.degree, gradients=True)
     if meas.domain.kind == "interior":
         return _mf.volume_problem(data, meas.degree)
-    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "product spaces are assembled on interior and skeleton measures only")
+    if meas.domain.kind == "boundary" and not data[0].mesh.simplex:
+        return _mf.boundary_problem(data, meas.domain.sides, meas.degree)
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "block kernels run on interior, skeleton and (cube-mesh) boundary measures")
 
 
-def _setup_block_engine(space, meas: "Measure", engine: Optional[_eng.Engine] = None):
+def _setup_block_engine(space, meas: "Measure", engine: Optional[_eng.Engine] = None, bp=None):
+    bp = bp if bp is not None else _block_problem(space, meas)
     eng = engine or _eng.Engine(_default_device)
-    bp = _block_problem(space, meas)
     eng.set_mesh(bp.node_coordinates, bp.face_nodes)
     if bp.manifold_dim != bp.node_coordinates.shape[1]:
         eng.set_manifold_dim(bp.manifold_dim)
@@ -671,8 +700,16 @@ def _setup_block_engine(space, meas: "Measure", engine: Optional[_eng.Engine] = 
     return eng, bp
 
 
-def _part_of(bp, fa: FormArg, skeleton_measure: bool) -> int:
-    if skeleton_measure:
+def _kind(skeleton_measure) -> str:
+    """measure kind of a block problem: "skeleton" (two cells around), "boundary" (one) or "interior"; True / False are the
+    skeleton / interior shorthands"""
+    if isinstance(skeleton_measure, str):
+        return skeleton_measure
+    return "skeleton" if skeleton_measure else "interior"
+
+
+def _part_of(bp, fa: FormArg, skeleton_measure) -> int:
+    if _kind(skeleton_measure) == "skeleton":
         if fa.side not in (1, 2):
             raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "on a skeleton measure form arguments are restricted to a cell around: u[1](x), u[2](x)")
         return bp.part_index(fa.field, fa.side - 1)
@@ -681,7 +718,7 @@ def _part_of(bp, fa: FormArg, skeleton_measure: bool) -> int:
     return bp.part_index(fa.field, 0)
 
 
-def recognise_blocks(term, bp, skeleton_measure: bool):
+def recognise_blocks(term, bp, skeleton_measure):
     """-> [(part_u, part_v, block form, alpha)]: one recognised term per (part of u, part of v) block."""
     out = {}
     ip = {}                                  # interior-penalty blocks: key -> [c0, c1, c2]
@@ -697,17 +734,18 @@ def recognise_blocks(term, bp, skeleton_measure: bool):
             # terms with unit normals / the face diameter: (1/h)(v n_sv)⋅(u n_su), (v n_sv)⋅∇u, ∇v⋅(u n_su)
             normals = sorted(f.side for f in others if isinstance(f, Normal))
             invh = [f for f in others if isinstance(f, FaceDiameter)]
-            if not skeleton_measure or len(normals) + len(invh) != len(others) or any(not f.inverse for f in invh) or not dotted:
+            mk = _kind(skeleton_measure)
+            if mk == "interior" or len(normals) + len(invh) != len(others) or any(not f.inverse for f in invh) or (normals and not dotted):
                 raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "normal / face-diameter term not recognised by the GPU engine; no CPU fallback")
-            if ops == ("value", "value") and len(invh) == 1 and normals == sorted([u.side, v.side]):
-                kind = 0
+            if ops == ("value", "value") and len(invh) == 1 and (normals == sorted([u.side, v.side]) or (mk == "boundary" and not normals)):
+                kind = 0          # boundary: (γ/h) v u = (γ/h)(v n)⋅(u n) with the one normal
             elif ops == ("gradient", "value") and not invh and normals == [v.side]:
                 kind = 1
             elif ops == ("value", "gradient") and not invh and normals == [u.side]:
                 kind = 2
             else:
                 raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "normal / face-diameter term not recognised by the GPU engine; no CPU fallback")
-            key = (_part_of(bp, u, True), _part_of(bp, v, True))
+            key = (_part_of(bp, u, mk), _part_of(bp, v, mk))
             ip.setdefault(key, [0.0, 0.0, 0.0])[kind] += coef
             continue
         if ops == ("value", "value"):
@@ -720,6 +758,8 @@ def recognise_blocks(term, bp, skeleton_measure: bool):
             form = _eng.BLOCK_DIVU_VALV
         else:
             raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, f"block term ({u.op} of u) x ({v.op} of v) is not recognised by the GPU engine; no CPU fallback")
+        if form != _eng.BLOCK_MASS and _kind(skeleton_measure) != "interior":
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "on faces, gradients enter through normal terms only ((v n)⋅∇u, ∇v⋅(u n)); no CPU fallback")
         key = (_part_of(bp, u, skeleton_measure), _part_of(bp, v, skeleton_measure))
         if key in out:
             if out[key][0] != form:
@@ -733,16 +773,67 @@ def recognise_blocks(term, bp, skeleton_measure: bool):
            [(pu, pv, _eng.BLOCK_IP, 1.0, tuple(c)) for (pu, pv), c in ip.items()]
 
 
-def recognise_vblocks(term, bp, skeleton_measure: bool, space):
-    """linear forms: Σ constant · v_f[side](x)  ->  [(part, alpha, f_const)]"""
-    out = {}
+def recognise_vblocks(term, bp, skeleton_measure, space):
+    """linear forms -> ([(part, alpha, f_const or (c0, c1, c2))], g_qp or None):
+    constant multiples of v(x) (f_const), or — with an analytical field g sampled at the face points —
+    g (c0 v + (c1/h) v + c2 n⋅∇v): volume sources v f and the Nitsche right-hand side (γ/h) v g - n⋅∇v g"""
+    mk = _kind(skeleton_measure)
     flds = fields(space)
-    for coef, factors, _ in _expand(term):
-        if len(factors) != 1 or factors[0].arg != 1 or factors[0].op != "value":
-            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "linear block terms are constant multiples of v(x); no CPU fallback")
-        part = _part_of(bp, factors[0], skeleton_measure)
-        out[part] = out.get(part, 0.0) + coef
-    return [(part, alpha, np.ones(flds[bp.parts[part]["field"]].data.n_comp)) for part, alpha in out.items()]
+    const, data, fn = {}, {}, None
+    for coef, factors, dotted in _expand_with_data(term):
+        vs = [f for f in factors if isinstance(f, FormArg)]
+        normals = [f for f in factors if isinstance(f, Normal)]
+        invh = [f for f in factors if isinstance(f, FaceDiameter)]
+        datas = [f for f in factors if isinstance(f, Call)]
+        if len(vs) != 1 or vs[0].arg != 1 or len(vs) + len(normals) + len(invh) + len(datas) != len(factors) or len(datas) > 1:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "linear block term not recognised by the GPU engine; no CPU fallback")
+        v = vs[0]
+        part = _part_of(bp, v, mk)
+        if not datas:
+            if v.op != "value" or normals or invh:
+                raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "linear block terms without data are constant multiples of v(x); no CPU fallback")
+            const[part] = const.get(part, 0.0) + coef
+            continue
+        if fn is not None and datas[0].fn is not fn:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "one analytical field per linear block integral; no CPU fallback")
+        fn = datas[0].fn
+        if v.op == "value" and not normals and not invh:
+            kind = 0
+        elif v.op == "value" and not normals and len(invh) == 1 and invh[0].inverse and mk != "interior":
+            kind = 1
+        elif v.op == "gradient" and len(normals) == 1 and normals[0].side == v.side and not invh and dotted and mk != "interior":
+            kind = 2
+        else:
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "linear block term not recognised by the GPU engine; no CPU fallback")
+        data.setdefault(part, [0.0, 0.0, 0.0])[kind] += coef
+    if const and data:
+        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "constant and data terms in one linear block integral are not recognised; no CPU fallback")
+    if data:
+        from . import multifield as _mf
+        xq = _mf.face_point_coordinates(bp)                                     # [n_faces, nq, D]
+        g = np.asarray(fn(np.moveaxis(xq, -1, 0)), dtype=np.float64)
+        g = np.ascontiguousarray(np.broadcast_to(g, xq.shape[:2]))
+        return [(part, 1.0, tuple(c)) for part, c in data.items()], g
+    return [(part, alpha, np.ones(flds[bp.parts[part]["field"]].data.n_comp)) for part, alpha in const.items()], None
+
+
+def _expand_with_data(t):
+    """_expand that also accepts analytical-field factors f(x) (Call(fn, Coordinate)) as opaque data factors"""
+    if isinstance(t, Call) and callable(t.fn) and isinstance(t.a, Coordinate):
+        return [(1.0, (t,), False)]
+    if isinstance(t, Call) and t.fn in ("+", "-") and t.b is not None:
+        sign = 1.0 if t.fn == "+" else -1.0
+        return _expand_with_data(t.a) + [(sign * c, f, d) for (c, f, d) in _expand_with_data(t.b)]
+    if isinstance(t, Call) and t.fn in ("*", "dot") and t.b is not None:
+        return [(ca * cb, fa + fb, da or db or t.fn == "dot") for (ca, fa, da) in _expand_with_data(t.a) for (cb, fb, db) in _expand_with_data(t.b)]
+    if isinstance(t, Call) and t.fn == "/" and t.b is not None:
+        den = _expand(t.b)
+        num = _expand_with_data(t.a)
+        if len(den) == 1 and den[0][1] == ():
+            return [(c / den[0][0], f, d) for (c, f, d) in num]
+        if len(den) == 1 and len(den[0][1]) == 1 and isinstance(den[0][1][0], FaceDiameter) and not den[0][1][0].inverse:
+            return [(c / den[0][0], f + (FaceDiameter(True),), d) for (c, f, d) in num]
+    return _expand(t)
 
 
 def _form_arguments(space, arg: int):
@@ -755,8 +846,9 @@ def _assemble_matrix_blocks(a, U, V, reuse, free_or_dirichlet, engine, index_typ
     if U is not V:
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
     term, meas, scale = _single_contribution(a(_form_arguments(U, 2), _form_arguments(V, 1)))
-    eng, bp = _setup_block_engine(V, meas, engine)
-    blocks = [(b[0], b[1], b[2], b[3] * scale) + tuple(b[4:]) for b in recognise_blocks(term, bp, meas.domain.kind == "skeleton")]
+    bp = _block_problem(V, meas)
+    blocks = [(b[0], b[1], b[2], b[3] * scale) + tuple(b[4:]) for b in recognise_blocks(term, bp, meas.domain.kind)]   # raises before any engine exists
+    eng, bp = _setup_block_engine(V, meas, engine, bp)
     eng.matrix_symbolic(*free_or_dirichlet)
     colptr, rowval = eng.matrix_pattern_i64() if index_type in (int, np.int64) else eng.matrix_pattern()
     nzval = eng.matrix_numeric_blocks(blocks)
@@ -769,12 +861,14 @@ def _assemble_matrix_blocks(a, U, V, reuse, free_or_dirichlet, engine, index_typ
 
 def _assemble_vector_blocks(l, V, reuse, free_or_dirichlet, engine):
     term, meas, scale = _single_contribution(l(_form_arguments(V, 1)))
-    eng, bp = _setup_block_engine(V, meas, engine)
-    vblocks = [(part, alpha * scale, f) for (part, alpha, f) in recognise_vblocks(term, bp, meas.domain.kind == "skeleton", V)]
+    bp = _block_problem(V, meas)
+    vb, g_qp = recognise_vblocks(term, bp, meas.domain.kind, V)
+    eng, bp = _setup_block_engine(V, meas, engine, bp)
+    vblocks = [(part, alpha * scale, f) for (part, alpha, f) in vb]
     eng.vector_symbolic(free_or_dirichlet)
-    b = eng.vector_assemble_blocks(vblocks)
+    b = eng.vector_assemble_blocks(vblocks, g_qp=g_qp)
     if reuse:
-        return b, AssemblyCache(eng, "blocks", dict(vblocks=vblocks), "vector")
+        return b, AssemblyCache(eng, "blocks", dict(vblocks=vblocks, g_qp=g_qp), "vector")
     eng.close()
     return b
 
@@ -786,9 +880,10 @@ def _assemble_matrix_sum(contributions, U, V, reuse, free_or_dirichlet, index_ty
     parts = []
     try:
         for term, meas, scale in contributions:
-            if _is_blocks_case(V, meas):
-                eng, bp = _setup_block_engine(V, meas)
-                blocks = [(b[0], b[1], b[2], b[3] * scale) + tuple(b[4:]) for b in recognise_blocks(term, bp, meas.domain.kind == "skeleton")]
+            if _is_blocks_case(V, meas, term):
+                bp = _block_problem(V, meas)
+                blocks = [(b[0], b[1], b[2], b[3] * scale) + tuple(b[4:]) for b in recognise_blocks(term, bp, meas.domain.kind)]
+                eng, bp = _setup_block_engine(V, meas, None, bp)
                 run = (lambda e=eng, b=blocks: e.matrix_numeric_blocks_device(b))
             else:
                 form, params = recognise_bilinear(term, V, meas)
@@ -829,7 +924,7 @@ def assemble_matrix(a: Callable, T, U: Space, V: Space, *, reuse: bool = False, 
     if U is not V:
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "trial and test spaces must be the same object on the GPU path")
     probe = a(_form_arguments(U, 2), _form_arguments(V, 1))
-    if len(probe.contributions) == 1 and _is_blocks_case(V, probe.contributions[0][1]):
+    if len(probe.contributions) == 1 and _is_blocks_case(V, probe.contributions[0][1], probe.contributions[0][0]):
         # product spaces / skeleton integrals: block kernels on the super element
         opts = dict(assembly_options or {})
         index_type = opts.pop("index_type", np.int32)
@@ -890,7 +985,7 @@ def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, parameters
         raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "the engine assembles Float64 only")
     v = _form_arguments(V, 1)
     contributions = l(v).contributions
-    if len(contributions) == 1 and _is_blocks_case(V, contributions[0][1]):
+    if len(contributions) == 1 and _is_blocks_case(V, contributions[0][1], contributions[0][0]):
         if parameters:
             raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "parameters are not supported for product spaces on the GPU engine")
         return _assemble_vector_blocks(l, V, reuse, free_or_dirichlet, engine)
@@ -901,6 +996,16 @@ def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, parameters
             raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "reuse is available for single-integral linear forms")
         b = None
         for term, meas, scale in contributions:
+            if _is_blocks_case(V, meas, term):          # skeleton / Nitsche / product-space integral: block kernels, same COO vector
+                bp = _block_problem(V, meas)
+                vb, g_qp = recognise_vblocks(term, bp, meas.domain.kind, V)
+                eng, bp = _setup_block_engine(V, meas, None, bp)
+                eng.vector_symbolic(free_or_dirichlet)
+                if b is not None:
+                    eng.set_vector(b)
+                b = eng.vector_assemble_blocks([(part, alpha * scale, f) for (part, alpha, f) in vb], accumulate=b is not None, g_qp=g_qp)
+                eng.close()
+                continue
             form, params = recognise_linear(term, V, meas)
             params["alpha"] = params.get("alpha", 1.0) * scale
             eng = _setup_engine(V, meas)
@@ -926,7 +1031,7 @@ def assemble_vector(l: Callable, T, V: Space, *, reuse: bool = False, parameters
 def update_vector(b: np.ndarray, cache: AssemblyCache, parameters=(), **new_params):
     """GT.update_vector!(b, cache; parameters) (problems.jl:276-285)."""
     if cache.form == "blocks":
-        cache.engine.vector_assemble_blocks(cache.params["vblocks"], out=b)
+        cache.engine.vector_assemble_blocks(cache.params["vblocks"], out=b, g_qp=cache.params.get("g_qp"))
         return b
     cache.params.update(new_params)
     if parameters:

@@ -353,6 +353,22 @@ def _apply_dirichlet(cell_dofs_all: np.ndarray, ndofs: int, tag: np.ndarray):
     return perm[cell_dofs_all - 1].astype(np.int32), int(free.size), int(diri.size), free, diri
 
 
+def discontinuous_lagrange_space(mesh: Mesh, order: int = 1, n_comp: int = 1) -> LagrangeSpace:
+    """GT.lagrange_space(Ω, order; continuous=false): every dof is an own dof of its cell (reference_face_own_dofs,
+    space.jl:860-882: all local dofs belong to the D-face), so dof = (cell-1) * n_ldofs + local dof; no Dirichlet dofs
+    (boundary conditions are imposed weakly, docs/src/src_jl/example_hello_world_dg.jl)."""
+    kind = "P" if mesh.simplex else "Q"
+    lat = reference_nodes(mesh.D, order, kind)                                  # [nls, D] reference nodes
+    nls = lat.shape[0]
+    nld = nls * n_comp
+    cell_dofs = (np.arange(mesh.n_cells * nld, dtype=np.int64).reshape(mesh.n_cells, nld) + 1).astype(np.int32)
+    M, _ = tabulate(mesh.D, 1, kind, lat)                                       # geometry functions at the dof nodes
+    X = np.einsum("sk,ckd->csd", M, mesh.node_coordinates[mesh.cell_nodes.astype(np.int64) - 1])   # [nc, nls, D]
+    xyz = np.repeat(X.reshape(-1, mesh.D), n_comp, axis=0)
+    return LagrangeSpace(mesh, order, n_comp, kind, np.ascontiguousarray(cell_dofs), int(mesh.n_cells * nld), 0,
+                         free_dof_nodes=xyz, dirichlet_dof_nodes=np.zeros((0, mesh.D)))
+
+
 def lagrange_space(mesh: Mesh, order: int = 1, dirichlet_boundary=None,
                    n_comp: int = 1, node_dof_override=None) -> LagrangeSpace:
     """GT.lagrange_space(Ω, order; dirichlet_boundary, tensor_size=Val((n_comp,))).

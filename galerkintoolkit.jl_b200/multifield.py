@@ -153,3 +153,43 @@ def skeleton_problem(spaces: Sequence[_hp.LagrangeSpace], degree: int, gradients
         bp.dM_cell = np.stack([_hp.tabulate(D, 1, kind, cell_pts[v])[1] for v in range(variants.shape[0])])
         bp.ref_normals = np.stack([_reference_normal(Xref[variants[v]], mesh.simplex) for v in range(variants.shape[0])])
     return bp
+
+
+def boundary_problem(spaces: Sequence[_hp.LagrangeSpace], sides, degree: int) -> BlockProblem:
+    """∫(…, measure(boundary(mesh; group_names), degree)) with the cell around every face (`faces_around = Fill(1)`, mesh.jl:
+    249-271): ALL dofs of that cell are pushed, its shape functions, gradients and unit normal are evaluated at the face points
+    mapped into the cell — what Nitsche terms need (docs/src/src_jl/example_hello_world_dg.jl:70-76)."""
+    mesh = spaces[0].mesh
+    D = mesh.D
+    kind = spaces[0].kind
+    fn, fc, _ = _hp.boundary_faces(mesh, sides)
+    fn = np.ascontiguousarray(fn, dtype=np.int32)
+    sc = (np.asarray(fc, dtype=np.int64) + 1)[:, None]                          # the one cell around, 1-based
+    cn = mesh.cell_nodes.astype(np.int64)
+    eq = cn[sc[:, 0] - 1][:, None, :] == fn.astype(np.int64)[:, :, None]
+    if not eq.any(axis=2).all():
+        raise AssertionError("a boundary-face node is missing from the cell around the face")
+    loc = eq.argmax(axis=2)
+    variants, inv = np.unique(loc, axis=0, return_inverse=True)
+    face_var = inv.reshape(-1, 1).astype(np.int32)
+    q = _hp.quadrature(D - 1, mesh.simplex, degree)
+    M, dM = _hp.tabulate(D - 1, 1, kind, q.coordinates)
+    Xref = _hp.reference_nodes(D, 1, kind)
+    cell_pts = np.einsum("qk,vkd->vqd", M, Xref[variants])
+    dofs, nfree, ndiri, _, _ = offset_dofs(spaces)
+    parts, cols = [], []
+    for f, s in enumerate(spaces):
+        tabs = [_hp.tabulate(D, s.order, s.kind, cell_pts[v]) for v in range(variants.shape[0])]
+        parts.append(dict(field=f, side=0, n_comp=s.n_comp, N=np.stack([t[0] for t in tabs]), dN=np.stack([t[1] for t in tabs])))
+        cols.append(dofs[f][sc[:, 0] - 1])
+    bp = BlockProblem(mesh.node_coordinates, fn, D - 1, np.ascontiguousarray(np.concatenate(cols, axis=1)), nfree, ndiri,
+                      np.ascontiguousarray(q.weights), M, dM, parts, 1, face_var, sc)
+    bp.cell_nodes = mesh.cell_nodes
+    bp.dM_cell = np.stack([_hp.tabulate(D, 1, kind, cell_pts[v])[1] for v in range(variants.shape[0])])
+    bp.ref_normals = np.stack([_reference_normal(Xref[variants[v]], mesh.simplex) for v in range(variants.shape[0])])
+    return bp
+
+
+def face_point_coordinates(bp: BlockProblem) -> np.ndarray:
+    """physical coordinates of the quadrature points of every integration face: [n_faces, n_q, D]"""
+    return np.einsum("qk,fkd->fqd", bp.M, bp.node_coordinates[bp.face_nodes.astype(np.int64) - 1])

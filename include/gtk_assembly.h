@@ -263,7 +263,7 @@ enum {
 };
 typedef struct gtk_block { int32_t part_u, part_v, form; double alpha; double c[3]; } gtk_block;
 /* Cells around the faces of a skeleton measure, for blocks with gradients / normals there (call after gtk_set_parts):
- * cell_nodes [n_cells][n_lnodes] = face_nodes(mesh, D).data, side_cells [n_faces][2] (1-based), dM_cell [n_var][n_q][n_lnodes][D]
+ * cell_nodes [n_cells][n_lnodes] = face_nodes(mesh, D).data, side_cells [n_faces][n_sides] (1-based; boundary faces have one cell around), dM_cell [n_var][n_q][n_lnodes][D]
  * = the cell's geometry gradients at the face points mapped into the cell per (local face, permutation) variant, ref_normals
  * [n_var][D] = normals(mesh(domain(refface)))[ldface] of the variant's local face (domain.jl:226, 258).  The parts' dN tables are
  * then [n_var][n_q][n_lshape][D] at the same mapped points. */
@@ -277,9 +277,15 @@ int32_t gtk_matrix_numeric_blocks(gtk_ctx* ctx, int32_t n_blocks, const gtk_bloc
 int32_t gtk_matrix_numeric_blocks_device(gtk_ctx* ctx, int32_t n_blocks, const gtk_block* blocks);
 /* Linear forms: per part ∫ alpha (f · v) with f constant — ∫_Λ jump(v) (test/assembly_tests.jl:420-424) is alpha = -1 / +1
  * on the two sides, f = 1.  accumulate as in gtk_form_params. */
-typedef struct gtk_vblock { int32_t part; double alpha; double f_const[3]; } gtk_vblock;
+typedef struct gtk_vblock { int32_t part; double alpha; double f_const[3]; double c[3]; } gtk_vblock;
 int32_t gtk_vector_assemble_blocks(gtk_ctx* ctx, int32_t n, const gtk_vblock* vblocks, int32_t accumulate, double* b);
 int32_t gtk_vector_assemble_blocks_device(gtk_ctx* ctx, int32_t n, const gtk_vblock* vblocks, int32_t accumulate);
+/* Linear forms with data g sampled by the host at the faces' quadrature points (g_qp: host [n_faces][n_q]; scalar parts):
+ *   per part  ∫ alpha g (c[0] v + (c[1]/h) v + c[2] n⋅∇v)     (f_const unused)
+ * — the Nitsche right-hand side (γ/h) v g - n⋅∇v g of docs/src/src_jl/example_hello_world_dg.jl:83-87 is c = (0, γ, -1) on the
+ * faces of the Dirichlet boundary (one cell around: gtk_set_skeleton_cells with n_sides = 1), a volume source v f is c = (1, 0, 0). */
+int32_t gtk_vector_assemble_blocks_data(gtk_ctx* ctx, int32_t n, const gtk_vblock* vblocks, const double* g_qp, int32_t accumulate, double* b);
+int32_t gtk_vector_assemble_blocks_data_device(gtk_ctx* ctx, int32_t n, const gtk_vblock* vblocks, const double* g_qp, int32_t accumulate);
 
 /* ---- sums of integrals over different domains in ONE matrix --------------------------------------------------------- */
 /* a(u,v) = ∫_Ω … dΩ + ∫_Γ … dΓ + ∫_Λ … dΛ: the reference lets every contribution of the form push into the same COO

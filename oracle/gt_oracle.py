@@ -1320,9 +1320,11 @@ def assemble_matrix_sum(coo_list, m, n):
     return sparse_csc(I, J, V, m, n)
 
 
-def assemble_vector_multifield(D, coords, face_nodes, face_tab, sides, fields, integrand, alpha=1.0, free_or_dirichlet=FREE):
+def assemble_vector_multifield(D, coords, face_nodes, face_tab, sides, fields, integrand, alpha=1.0, free_or_dirichlet=FREE,
+                               skeleton_geometry=None, point_data=None):
     """generate_vector_assembly_template (compiler.jl:1933-2000) + monolithic contribute! (assembly.jl:392-399), loop for
-    loop; integrand(pt) sees the masked test function v only."""
+    loop; integrand(pt) sees the masked test function v only.  skeleton_geometry as in assemble_matrix_multifield (gradients of
+    v, pt.n(side), pt.h); point_data [n_faces][nq]: an analytical field sampled at the face points (pt.g)."""
     nf = len(fields)
     n_rows_f = [f["n_free"] if free_or_dirichlet == FREE else f["n_dirichlet"] for f in fields]
     off = monolithic_offsets(n_rows_f)
@@ -1337,13 +1339,28 @@ def assemble_vector_multifield(D, coords, face_nodes, face_tab, sides, fields, i
         for q in range(len(w)):
             Jf = point_geometry(coords, fn[face:face + 1], np.asarray(dMf[q]))
             dV = float(change_of_measure(Jf)[0] * w[q])
+            if point_data is not None:
+                pt.g = float(point_data[face][q])
+            JS = None
+            if skeleton_geometry is not None:
+                cnS, dMS, nrefS = skeleton_geometry
+                pt.h = face_diameter(coords, fn[face])
+                pt.normals, JS = [], []
+                for (cell, var) in sides[face]:
+                    Jc = point_geometry(coords, np.asarray(cnS)[cell - 1:cell], np.asarray(dMS[var][q]))
+                    JS.append(Jc)
+                    pt.normals.append(map_unit_normal(Jc[0], nrefS[var]))
             for f in range(nf):
                 nc = fields[f]["n_comp"]
                 for a in range(n_around):
                     var = sides[face][a][1]
+                    g = None
+                    if JS is not None and fields[f].get("dN") is not None:
+                        Jt = np.swapaxes(JS[a], -1, -2)
+                        g = [_solve(Jt, np.asarray(fields[f]["dN"][var][q][s]).reshape(1, D))[0] for s in range(len(fields[f]["N"][var][q]))]
                     for ld in range(nld[f]):
                         s, comp = divmod(ld, nc)
-                        pt.V = (f, a + 1) + _shape(fields[f]["N"][var][q][s], None, comp, nc, D)
+                        pt.V = (f, a + 1) + _shape(fields[f]["N"][var][q][s], None if g is None else g[s], comp, nc, D)
                         be[a, f][ld] += (alpha * integrand(pt)) * dV
         for f in range(nf):
             for a in range(n_around):

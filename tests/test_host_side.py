@@ -278,6 +278,7 @@ def test_every_entry_point_rejects_a_null_context(built_library):
         "gtk_vector_assemble_blocks_device": (z, 0, z, 0),
         "gtk_matrix_sum_symbolic": (z, 1, z, z), "gtk_matrix_sum_numeric": (z, 1, z, z), "gtk_matrix_sum_numeric_device": (z, 1, z),
         "gtk_set_skeleton_cells": (z, 1, 4, z, z, z, z), "gtk_matrix_colptr_at": (z, 0, z, z),
+        "gtk_vector_assemble_blocks_data": (z, 0, z, z, 0, z), "gtk_vector_assemble_blocks_data_device": (z, 0, z, z, 0),
     }
     for name, args in calls.items():
         rc = getattr(lib, name)(*args)

@@ -552,3 +552,104 @@ def test_gpu_reference_poisson_with_skeleton_terms():
     # the skeleton term alone widens the pattern and contributes nothing
     K = GT.assemble_matrix(lambda u, v: GT.integrate(lambda q: GT.dot(GT.grad(u, q), GT.grad(v, q)), dO), float, V, V)
     assert A.nzval.size > K.nzval.size and abs(A.to_scipy() - K.to_scipy()).max() < 1e-12
+
+
+# ---- discontinuous spaces, Nitsche terms on boundary faces: the reference's interior-penalty example -------------------
+def _boundary_oracle_sides(bp):
+    return [[(int(bp.side_cells[i, 0]), int(bp.face_var[i, 0]))] for i in range(bp.face_nodes.shape[0])]
+
+
+def test_discontinuous_space_numbering_and_boundary_inputs():
+    """lagrange_space(Ω, k; continuous=false): dof = (cell-1) n_ldofs + local dof (space.jl:860-882); boundary faces carry the one
+    cell around with an outward normal"""
+    mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (3, 2, 2))
+    _warp(mesh)
+    V = H.discontinuous_lagrange_space(mesh, 1)
+    assert V.n_free == mesh.n_cells * 8 and V.n_dirichlet == 0
+    assert np.array_equal(V.cell_dofs, np.arange(1, mesh.n_cells * 8 + 1).reshape(-1, 8))
+    assert np.allclose(V.free_dof_nodes, mesh.node_coordinates[mesh.cell_nodes.astype(np.int64) - 1].reshape(-1, 3))
+    bp = MF.boundary_problem([V], None, 2)
+    assert bp.face_nodes.shape[0] == 2 * (3 * 2 + 3 * 2 + 2 * 2) and bp.n_sides == 1
+    X = mesh.node_coordinates
+    centre = X.mean(axis=0)
+    for i in range(bp.face_nodes.shape[0]):
+        cell, var = int(bp.side_cells[i, 0]), int(bp.face_var[i, 0])
+        J = O.point_geometry(X, mesh.cell_nodes[cell - 1][None, :], bp.dM_cell[var][0])[0]
+        n = O.map_unit_normal(J, bp.ref_normals[var])
+        fc = X[bp.face_nodes[i] - 1].mean(axis=0)
+        assert abs(np.linalg.norm(n) - 1) < 1e-14 and np.dot(n, fc - centre) > 0.0      # outward
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells", [(3, 3), (2, 2, 2)])
+def test_gpu_nitsche_terms_parity(cells):
+    """(γ/h) v u - v n⋅∇u - n⋅∇v u on boundary faces and the right-hand side (γ/h) v g - n⋅∇v g, on a discontinuous space"""
+    D = len(cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells)
+    _warp(mesh)
+    V = H.discontinuous_lagrange_space(mesh, 1)
+    sides_sel = [1, 4] if D == 2 else [2, 5]
+    bp = MF.boundary_problem([V], sides_sel, 2)
+    eng = _engine(bp)
+    eng.set_skeleton_cells(bp.cell_nodes, bp.side_cells, bp.dM_cell, bp.ref_normals)
+    fields_o = _oracle_fields(bp, [V], True)
+    geo = (bp.cell_nodes, bp.dM_cell, bp.ref_normals)
+    sides = _boundary_oracle_sides(bp)
+    gamma = 0.7
+    mat = lambda p: (gamma / p.h) * p.v(0) * p.u(0) - O.frobenius(p.v(0) * p.n(1), p.grad_u(0)) - O.frobenius(p.n(1), p.grad_v(0)) * p.u(0)
+    ref = O.assemble_matrix_multifield(D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides, fields_o, mat,
+                                       skeleton_geometry=geo)
+    eng.matrix_symbolic()
+    gcp, grv = eng.matrix_pattern()
+    assert np.array_equal(ref[0], gcp) and np.array_equal(ref[1], grv)
+    got = eng.matrix_numeric_blocks([(0, 0, E.BLOCK_IP, 1.0, (gamma, -1.0, -1.0))])
+    assert_values_close(got, ref[2])
+    xq = MF.face_point_coordinates(bp)
+    g = np.sin(xq[..., 0]) + 2.0 * xq[..., 1]
+    vec = lambda p: (gamma / p.h) * p.v(0) * p.g - O.frobenius(p.n(1), p.grad_v(0)) * p.g
+    rb = O.assemble_vector_multifield(D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides, fields_o, vec,
+                                      skeleton_geometry=geo, point_data=g)
+    b = eng.vector_assemble_blocks([(0, 1.0, (0.0, gamma, -1.0))], g_qp=g)
+    assert_values_close(b, rb)
+    b2 = eng.vector_assemble_blocks([(0, 1.0, (0.0, gamma, -1.0))], g_qp=g, accumulate=True)     # continues the same COO vector
+    assert_values_close(b2, 2.0 * rb)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reference_interior_penalty_example():
+    """docs/src/src_jl/example_hello_world_dg.jl transcribed: symmetric interior penalty on a DISCONTINUOUS Q1 space, 4 x 4 x 4
+    hexahedra — Laplace operator on Ω + interior penalty on Λ + Nitsche terms on Γ in ONE matrix, right-hand side with the
+    Nitsche data terms; the example's own check: the L2 error against g = sum(x) is below 1e-9"""
+    import scipy.sparse.linalg as spla
+    mesh = GT.cartesian_mesh((0, 1, 0, 1, 0, 1), (4, 4, 4))
+    D = 3
+    n = GT.unit_normal(mesh, D - 1)
+    Om, Gd, Lam = GT.interior(mesh), GT.boundary(mesh), GT.skeleton(mesh)
+    h_L, h_G = GT.face_diameter_field(Lam), GT.face_diameter_field(Gd)
+    g = GT.AnalyticalField(lambda x: x[0] + x[1] + x[2], Om)
+    f = GT.AnalyticalField(lambda x: 0.0 * x[0], Om)
+    mean = lambda fn, u, x: 0.5 * (fn(u[1], x) + fn(u[2], x))
+    jump = lambda u, n_, x: u[2](x) * n_[2](x) + u[1](x) * n_[1](x)
+    k = 1
+    gamma = GT.uniform_quantity(k * (k + 1) / 10)
+    V = GT.lagrange_space(Om, k, continuous=False)
+    dO, dL, dG = GT.measure(Om, 2 * k), GT.measure(Lam, 2 * k), GT.measure(Gd, 2 * k)
+    grad, dot = GT.grad, GT.dot
+    a = lambda u, v: (GT.integrate(lambda x: dot(grad(u, x), grad(v, x)), dO)
+                      + GT.integrate(lambda x: dot((gamma / h_L(x)) * jump(v, n, x), jump(u, n, x)) - dot(jump(v, n, x), mean(grad, u, x))
+                                     - dot(mean(grad, v, x), jump(u, n, x)), dL)
+                      + GT.integrate(lambda x: (gamma / h_G(x)) * v(x) * u(x) - dot(v(x) * n(x), grad(u, x)) - dot(n(x), grad(v, x)) * u(x), dG))
+    l = lambda v: (GT.integrate(lambda x: v(x) * f(x), dO)
+                   + GT.integrate(lambda x: (gamma / h_G(x)) * v(x) * g(x) - dot(n(x), grad(v, x)) * g(x), dG))
+    A = GT.assemble_matrix(a, float, V, V)
+    b = GT.assemble_vector(l, float, V)
+    assert A.m == A.n == 64 * 8 == b.size
+    S = A.to_scipy().tocsc()
+    assert abs(S - S.T).max() < 1e-12 * abs(S).max()                 # the symmetric interior penalty method
+    x = spla.spsolve(S, b)
+    Xdof = V.data.free_dof_nodes
+    assert np.abs(x - Xdof.sum(axis=1)).max() < 1e-9                 # nodal error of the exact (linear) solution
+    uh = GT.solution_field(V, x)
+    el2 = np.sqrt(GT.integrate(lambda y: GT.abs2(uh(y) - g(y)), dO).sum())
+    assert el2 < 1.0e-9                                              # the example's own assertion
