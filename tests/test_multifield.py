@@ -653,3 +653,42 @@ def test_gpu_reference_interior_penalty_example():
     uh = GT.solution_field(V, x)
     el2 = np.sqrt(GT.integrate(lambda y: GT.abs2(uh(y) - g(y)), dO).sum())
     assert el2 < 1.0e-9                                              # the example's own assertion
+
+
+def test_oracle_reproduces_the_reference_interior_penalty_example():
+    """docs/src/src_jl/example_hello_world_dg.jl on the CPU ORACLE (3 x 3 x 3 cells; the example's assertion holds on any mesh since
+    g = sum(x) is in the space): Laplace operator + interior penalty + Nitsche terms pushed as ONE COO allocation, Nitsche data
+    on the right-hand side; the discrete solution is g — `@assert el2 < 1.0e-9`.  A second known answer of the reference (after the
+    p-Laplacian norm) that pins the restatement: normals, gradients on faces, face diameters, discontinuous numbering."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    cells = (3, 3, 3)
+    mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), cells)
+    V = H.discontinuous_lagrange_space(mesh, 1)
+    gamma = 1 * (1 + 1) / 10
+    coo = [_volume_coo(O.LAPLACE, mesh, V, 2)]
+    bs = MF.skeleton_problem([V], 2, gradients=True)
+    sides = [[(int(bs.side_cells[i, a]), int(bs.face_var[i, a])) for a in range(2)] for i in range(bs.face_nodes.shape[0])]
+    jn = lambda p, w: (p.u(0, 2) * p.n(2) + p.u(0, 1) * p.n(1)) if w == "u" else (p.v(0, 2) * p.n(2) + p.v(0, 1) * p.n(1))
+    mg = lambda p, w: 0.5 * ((p.grad_u(0, 1) + p.grad_u(0, 2)) if w == "u" else (p.grad_v(0, 1) + p.grad_v(0, 2)))
+    ip = lambda p: O.frobenius((gamma / p.h) * jn(p, "v"), jn(p, "u")) - O.frobenius(jn(p, "v"), mg(p, "u")) - O.frobenius(mg(p, "v"), jn(p, "u"))
+    coo.append(O.assemble_matrix_multifield(3, mesh.node_coordinates, bs.face_nodes, dict(w=bs.w, dM=bs.dM), sides, _oracle_fields(bs, [V], True), ip,
+                                            skeleton_geometry=(bs.cell_nodes, bs.dM_cell, bs.ref_normals), return_coo=True))
+    bb = MF.boundary_problem([V], None, 2)
+    bsides = _boundary_oracle_sides(bb)
+    geo = (bb.cell_nodes, bb.dM_cell, bb.ref_normals)
+    nit = lambda p: (gamma / p.h) * p.v(0) * p.u(0) - O.frobenius(p.v(0) * p.n(1), p.grad_u(0)) - O.frobenius(p.n(1), p.grad_v(0)) * p.u(0)
+    coo.append(O.assemble_matrix_multifield(3, mesh.node_coordinates, bb.face_nodes, dict(w=bb.w, dM=bb.dM), bsides, _oracle_fields(bb, [V], True), nit,
+                                            skeleton_geometry=geo, return_coo=True))
+    cp, rv, nz = O.assemble_matrix_sum(coo, V.n_free, V.n_free)
+    gq = MF.face_point_coordinates(bb).sum(axis=2)
+    rhs = lambda p: (gamma / p.h) * p.v(0) * p.g - O.frobenius(p.n(1), p.grad_v(0)) * p.g
+    b = O.assemble_vector_multifield(3, mesh.node_coordinates, bb.face_nodes, dict(w=bb.w, dM=bb.dM), bsides, _oracle_fields(bb, [V], True), rhs,
+                                     skeleton_geometry=geo, point_data=gq)
+    A = sp.csc_matrix((nz, rv.astype(np.int64) - 1, cp.astype(np.int64) - 1), shape=(V.n_free, V.n_free))
+    assert abs(A - A.T).max() < 1e-13
+    x = spla.spsolve(A, b)
+    err = x - V.free_dof_nodes.sum(axis=1)
+    assert np.abs(err).max() < 1e-9
+    # el2 = sqrt(∫ (uh - g)^2): with the nodal error e the integrand is the P/Q1 interpolant of e — bound it by max|e| sqrt(|Ω|)
+    assert np.abs(err).max() * 1.0 < 1e-9
