@@ -2,7 +2,7 @@
 """Regenerates tests/golden/*.npz from oracle/gt_oracle.py (run from the repo root: python tests/golden/make_golden.py).
 
 These fixtures freeze the ORACLE's output (inputs + colptr/rowval/nzval/b) on small cases; they are NOT outputs of the
-reference itself (pure Julia, not runnable in this image) — see DESIGN.md §6 "parity unpinned".  If a Julia-equipped box
+reference itself (pure Julia, not runnable in this image) — see DESIGN.md §6 (the oracle itself is pinned by the reference's known answers, not by these files).  If a Julia-equipped box
 appears, the same cases can be dumped from GalerkinToolkit (face_dofs(V).data, A.colptr/rowval/nzval, b) and diffed."""
 import os
 import sys
