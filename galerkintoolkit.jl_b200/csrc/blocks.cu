@@ -368,6 +368,21 @@ extern "C" int32_t gtk_set_parts(gtk_ctx* ctx, int32_t n_q, const double* w, con
   if ((n_var > 1 || n_sides > 1) && !face_var) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_parts: face_var is required with several variants or sides");
   GTK_CK(cudaSetDevice(ctx->device));
   gtk_parts_release(ctx);
+  {   // validate everything before any state is created: a failed call leaves the context without parts
+    int total = 0;
+    for (int p = 0; p < n_parts; ++p) {
+      if (pd[p].n_lshape < 1 || pd[p].n_comp < 1 || pd[p].n_comp > 3 || pd[p].side < 0 || pd[p].side >= n_sides || !pd[p].N)
+        GTK_FAIL(GTK_ERR_INVALID, "gtk_set_parts: bad part descriptor " + std::to_string(p));
+      total += pd[p].n_lshape * pd[p].n_comp;
+    }
+    if (total != ctx->nld)
+      GTK_FAIL(GTK_ERR_INVALID, "gtk_set_parts: the parts hold " + std::to_string(total) + " local dofs, the dof table of gtk_set_space " + std::to_string(ctx->nld));
+    if (face_var) {
+      const size_t n = (size_t)ctx->n_cells * n_sides;
+      for (size_t i = 0; i < n; ++i)
+        if (face_var[i] < 0 || face_var[i] >= n_var) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_parts: face_var out of range");
+    }
+  }
   PartsState* ps = new PartsState();
   ctx->parts = ps;
   const int D = ctx->D, dm = ctx->dman;
@@ -375,8 +390,6 @@ extern "C" int32_t gtk_set_parts(gtk_ctx* ctx, int32_t n_q, const double* w, con
   size_t at = 0;
   int off = 0, goff = 0;
   for (int p = 0; p < n_parts; ++p) {
-    if (pd[p].n_lshape < 1 || pd[p].n_comp < 1 || pd[p].n_comp > 3 || pd[p].side < 0 || pd[p].side >= n_sides || !pd[p].N)
-      GTK_FAIL(GTK_ERR_INVALID, "gtk_set_parts: bad part descriptor " + std::to_string(p));
     ps->nls[p] = pd[p].n_lshape; ps->ncomp[p] = pd[p].n_comp; ps->side[p] = pd[p].side;
     ps->off[p] = off; ps->goff[p] = goff; ps->has_dN[p] = pd[p].dN != nullptr;
     off += pd[p].n_lshape * pd[p].n_comp; goff += pd[p].n_lshape;
@@ -384,7 +397,6 @@ extern "C" int32_t gtk_set_parts(gtk_ctx* ctx, int32_t n_q, const double* w, con
     ps->dN_at[p] = at; if (pd[p].dN) at += (size_t)n_var * n_q * pd[p].n_lshape * D;
   }
   ps->L = off; ps->nls_total = goff;
-  if (off != ctx->nld) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_parts: the parts hold " + std::to_string(off) + " local dofs, the dof table of gtk_set_space " + std::to_string(ctx->nld));
   std::vector<double> h(at);
   for (int p = 0; p < n_parts; ++p) {
     std::copy(pd[p].N, pd[p].N + (size_t)n_var * n_q * pd[p].n_lshape, h.begin() + ps->N_at[p]);
@@ -396,8 +408,6 @@ extern "C" int32_t gtk_set_parts(gtk_ctx* ctx, int32_t n_q, const double* w, con
   GTK_CK(cudaMemcpyAsync(ps->tab, h.data(), at * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (face_var) {
     const size_t n = (size_t)ctx->n_cells * n_sides;
-    for (size_t i = 0; i < n; ++i)
-      if (face_var[i] < 0 || face_var[i] >= n_var) GTK_FAIL(GTK_ERR_INVALID, "gtk_set_parts: face_var out of range");
     if ((rc = gtk_dev_alloc(ctx, (void**)&ps->face_var, std::max<size_t>(n, 1) * sizeof(int32_t)))) return rc;
     ps->face_var_n = std::max<size_t>(n, 1);
     GTK_CK(cudaMemcpyAsync(ps->face_var, face_var, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));

@@ -82,3 +82,52 @@ def test_widening_the_active_cells_reclassifies_affine_layers():
     ref = O.assemble_matrix(O.LAPLACE, X, mesh.cell_nodes, V.cell_dofs, V.n_free, V.n_dirichlet, tab_dict(tab))
     assert np.abs(nz - ref[2]).max() <= 1e-12 * np.abs(ref[2]).max()
     eng.close()
+
+
+def test_block_and_sum_entry_points_reject_inconsistent_state():
+    """gtk_set_parts / gtk_matrix_numeric_blocks / gtk_matrix_sum_*: wrong sizes, missing tables and mixed-up contexts are errors"""
+    import importlib
+    MF = importlib.import_module("galerkintoolkit_jl_b200.multifield")
+    H = gtk_b200.hostprep
+    mesh = H.cartesian_mesh((0, 1, 0, 1), (3, 3))
+    V = H.lagrange_space(mesh, 1, [1])
+    bp = MF.skeleton_problem([V], 2)
+    eng = E.Engine(0)
+    eng.set_mesh(bp.node_coordinates, bp.face_nodes)
+    eng.set_manifold_dim(1)
+    eng.set_space(bp.super_dofs, bp.n_free, bp.n_dirichlet, 1)
+    with pytest.raises(E.GtkError):                       # the parts must add up to the super element of gtk_set_space
+        eng.set_parts(bp.w, bp.M, bp.dM, bp.parts[:1], bp.n_sides, bp.face_var)
+    bad = bp.face_var.copy(); bad[0, 0] = 99
+    with pytest.raises(E.GtkError):                       # variant index outside the tables
+        eng.set_parts(bp.w, bp.M, bp.dM, bp.parts, bp.n_sides, bad)
+    with pytest.raises(E.GtkError):                       # a failed gtk_set_parts leaves no parts behind
+        eng.matrix_symbolic(); eng.matrix_numeric_blocks([(0, 0, E.BLOCK_MASS, 1.0)])
+    eng.set_parts(bp.w, bp.M, bp.dM, bp.parts, bp.n_sides, bp.face_var)
+    eng.matrix_symbolic()
+    with pytest.raises(E.GtkError):                       # part index out of range
+        eng.matrix_numeric_blocks([(0, 7, E.BLOCK_MASS, 1.0)])
+    with pytest.raises(E.UnsupportedFormError):           # gradients on faces without the cells around
+        eng.matrix_numeric_blocks([(0, 0, E.BLOCK_LAPLACE, 1.0)])
+    with pytest.raises(E.GtkError):                       # the plain numeric entry points refuse a context that holds parts
+        eng.matrix_numeric(E.FORM_MASS)
+    nz = eng.matrix_numeric_blocks([(0, 0, E.BLOCK_MASS, 1.0)])
+    assert np.isfinite(nz).all()
+    # sums: sources of different sizes, the destination among the sources, numeric before symbolic
+    mesh2, V2, tab2 = problem((3, 3, 3))
+    other = make_engine(mesh2, V2, tab2)
+    other.matrix_symbolic(); other.matrix_numeric(E.FORM_MASS)
+    total = E.Engine(0)
+    with pytest.raises(E.GtkError):
+        total.matrix_sum_symbolic([eng, other])
+    with pytest.raises(E.GtkError):
+        eng.matrix_sum_symbolic([eng])
+    with pytest.raises(E.GtkError):
+        total.matrix_sum_numeric([eng])
+    total.matrix_sum_symbolic([eng, eng])                 # the same integral twice: same pattern, doubled values
+    cp, rv = total.matrix_pattern()
+    ecp, erv = eng.matrix_pattern()
+    assert np.array_equal(cp, ecp) and np.array_equal(rv, erv)
+    assert np.array_equal(total.matrix_sum_numeric([eng, eng]), 2.0 * nz)
+    for e in (eng, other, total):
+        e.close()
