@@ -368,4 +368,107 @@ function GT.generate_assemble_vector(c::GT.DomainContribution{A,<:GPUQuadrature}
     params_loop
 end
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Product spaces (V × Q): explicit-block entry point (SURVEY §8 f4).
+#
+# The engine assembles a CartesianProductSpace as ONE super element per cell (all fields' dofs, shifted by the field's block
+# offset — exactly what MonolithicAssemblyAllocation does per push, assembly.jl:321-333, 386-416).  Transparent dispatch from
+# `GT.assemble_matrix(a, T, VxQ, VxQ)` would need block recognition on the multi-field term IR (the `field == the_field`
+# masks of compiler.jl:728-739); that recogniser exists in this repository only in its Python mirror (gt.py: recognise_blocks),
+# so the Julia side offers the explicit form: the caller names the blocks.
+#
+#     VxQ = V × Q;  dΩ = GPU.gpu_measure(Ω, 4)
+#     blocks = [GPU.block(1, 1, GPU.BLOCK_LAPLACE, 1.0),        # ∇v⋅∇u        (u field 1, v field 1)
+#               GPU.block(2, 1, GPU.BLOCK_VALU_DIVV, -1.0),     # -div(v) p    (u field 2, v field 1)
+#               GPU.block(1, 2, GPU.BLOCK_DIVU_VALV, 1.0)]      # q div(u)     (u field 1, v field 2)
+#     A = GPU.assemble_product_matrix(VxQ, dΩ, blocks)          # SparseMatrixCSC{Float64,Int32}, all field blocks stored
+# ---------------------------------------------------------------------------------------------------------------------
+const BLOCK_MASS = Cint(1)
+const BLOCK_LAPLACE = Cint(2)
+const BLOCK_VALU_DIVV = Cint(3)
+const BLOCK_DIVU_VALV = Cint(4)
+
+# mirrors of the C structs (isbits, field for field)
+struct gtk_part
+    n_lshape::Cint
+    n_comp::Cint
+    side::Cint
+    N::Ptr{Cdouble}
+    dN::Ptr{Cdouble}
+end
+struct gtk_block
+    part_u::Cint
+    part_v::Cint
+    form::Cint
+    alpha::Cdouble
+    c::NTuple{3,Cdouble}
+end
+block(field_u, field_v, form, alpha) = gtk_block(Cint(field_u - 1), Cint(field_v - 1), form, Float64(alpha), (0.0, 0.0, 0.0))
+
+function assemble_product_matrix(VxQ::GT.AbstractSpace, q::GPUQuadrature, blocks::Vector{gtk_block})
+    flds = GT.fields(VxQ)
+    Ω = GT.domain(q)
+    mesh = GT.mesh(Ω)
+    D = GT.num_dims(mesh)
+    GT.num_dims(Ω) == D || error("libgtkasm: assemble_product_matrix integrates over the interior of the mesh")
+    xyz = GT.node_coordinates(mesh)
+    cell_nodes = GT.face_nodes(mesh, D)
+    n_cells = length(cell_nodes)
+    # block offsets (assembly.jl:321-333) and the super dof table: field-major, free ids + free offset, Dirichlet ids - Dirichlet offset
+    nfree = [length(GT.free_dofs(f)) for f in flds]
+    ndiri = [length(GT.dirichlet_dofs(f)) for f in flds]
+    off_f = cumsum(vcat(0, nfree))[1:end-1]
+    off_d = cumsum(vcat(0, ndiri))[1:end-1]
+    nld = [length(GT.face_dofs(f)[1]) for f in flds]
+    L = sum(nld)
+    super = Vector{Int32}(undef, n_cells * L)
+    for cell in 1:n_cells
+        k = (cell - 1) * L
+        for (i, f) in enumerate(flds)
+            for d in GT.face_dofs(f)[cell]
+                k += 1
+                super[k] = d > 0 ? Int32(d + off_f[i]) : Int32(d - off_d[i])
+            end
+        end
+    end
+    points = GT.coordinates(GT.reference_quadratures(q)[1])
+    w = collect(Float64, GT.weights(GT.reference_quadratures(q)[1]))
+    refcell = GT.reference_spaces(mesh, Val(D))[1]
+    ∇ = ForwardDiff.gradient
+    M = collect(permutedims(GT.tabulator(refcell)(GT.value, points)))
+    dM = collect(permutedims(GT.tabulator(refcell)(∇, points)))
+    # per field: SCALAR shape functions of its reference element (vector-valued fields: n_comp components per node)
+    tabs = map(flds) do f
+        reffe = GT.reference_spaces(f)[1]
+        ts = GT.tensor_size(reffe)                      # :scalar or a tuple such as (D,)  (space.jl:1061, 1185-1187)
+        ncomp = ts === :scalar ? 1 : prod(ts)
+        scalar = ncomp == 1 ? reffe : GT.lagrange_space(GT.domain(reffe), GT.order(reffe))
+        N = collect(permutedims(GT.tabulator(scalar)(GT.value, points)))
+        dN = collect(permutedims(GT.tabulator(scalar)(∇, points)))
+        (; ncomp, N, dN)
+    end
+    e = Engine()
+    nd = cell_nodes.data
+    GC.@preserve xyz nd super w M dM tabs begin
+        check(e, ccall((:gtk_set_mesh, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Cdouble}, Int64, Cint, Ptr{Int32}),
+                       e.handle, D, length(xyz), pointer(reinterpret(Float64, xyz)), n_cells, length(cell_nodes[1]), nd))
+        check(e, ccall((:gtk_set_space, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int32}, Int64, Int64),
+                       e.handle, L, 1, super, sum(nfree), sum(ndiri)))
+        parts = [gtk_part(Cint(size(t.N, 1)), Cint(t.ncomp), Cint(0), pointer(t.N), pointer(reinterpret(Float64, t.dN))) for t in tabs]
+        check(e, ccall((:gtk_set_parts, LIB), Cint,
+                       (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{gtk_part}, Cint, Cint, Ptr{Int32}),
+                       e.handle, length(w), w, M, pointer(reinterpret(Float64, dM)), length(parts), parts, 1, 1, C_NULL))
+    end
+    nnz = Ref{Int64}(0)
+    check(e, ccall((:gtk_matrix_symbolic, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}), e.handle, GTK_FREE, GTK_FREE, nnz))
+    check(e, ccall((:gtk_matrix_numeric_blocks_device, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{gtk_block}), e.handle, length(blocks), blocks))
+    n = sum(nfree)
+    colptr = Vector{Int32}(undef, n + 1)
+    rowval = Vector{Int32}(undef, nnz[])
+    nzval = Vector{Float64}(undef, nnz[])
+    check(e, ccall((:gtk_matrix_pattern, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), e.handle, colptr, rowval))
+    check(e, ccall((:gtk_copy_nzval, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.handle, nzval))
+    SparseArrays.SparseMatrixCSC(n, n, colptr, rowval, nzval)
+end
+
 end # module

@@ -123,3 +123,23 @@ def test_form_params_mirror_has_the_header_layout():
     jbody = re.search(r"struct FormParams\n(.*?)\nend", shim, flags=re.S).group(1)
     jfields = [ln.split("::")[0].strip() for ln in jbody.splitlines() if "::" in ln]
     assert jfields == cfields, (jfields, cfields)
+
+
+def test_block_struct_mirrors_have_the_header_layout():
+    """gtk_part / gtk_block in the Julia file mirror the C structs field for field (product-space entry point)"""
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER, encoding="utf-8").read(), flags=re.S)
+    shim = open(SHIM, encoding="utf-8").read()
+    for name in ("gtk_part", "gtk_block"):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
+        cfields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = re.sub(r"^(const\s+)?\w+\s*\*?", "", decl)
+            cfields += [re.sub(r"\[\d+\]", "", n).strip(" *") for n in names.split(",")]
+        jbody = re.search(r"struct %s\n(.*?)\nend" % name, shim, flags=re.S).group(1)
+        jfields = [ln.split("::")[0].strip() for ln in jbody.splitlines() if "::" in ln]
+        assert jfields == cfields, (name, jfields, cfields)
+    calls = {c for c in re.findall(r"ccall\(\(:(gtk_\w+), LIB\)", _code(SHIM))}
+    assert {"gtk_set_parts", "gtk_matrix_numeric_blocks_device"} <= calls
