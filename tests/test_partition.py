@@ -96,6 +96,33 @@ def test_slab_partition_and_exchange_in_process(cells, world, bc):
         check_owned_rows(p, local[r][0], local[r][1], vals[r][0], vals[r][1], A_glob, bg)
 
 
+@pytest.mark.parametrize("cells,world", [((4, 3, 6), 2), ((5, 4, 9), 3), ((3, 3, 8), 4)])
+def test_recompute_mode_completes_the_own_rows_bitwise(cells, world):
+    """Partition mode "recompute" (no exchange): a rank that ALSO assembles its halo cell layer holds, in the rows it owns, bitwise
+    the rows of the single-domain matrix — every contributing cell is local and is visited in the same (increasing cell id) order"""
+    dom = (0, 1, 0, 2, 0, 3)
+    mesh, V, tab = problem(cells, bc="boundary", domain=dom)
+    tabd = tab_dict(tab)
+    cp, rv, nz = O.assemble_matrix(O.LAPLACE, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, V.n_dirichlet, tabd)
+    bg = O.assemble_vector(O.SOURCE_CONST, mesh.node_coordinates, mesh.cell_nodes, V.cell_dofs, V.n_free, V.n_dirichlet, tabd, f_const=[1.0])
+    A_glob = sp.csc_matrix((nz, rv.astype(np.int64) - 1, cp.astype(np.int64) - 1), shape=(V.n_free, V.n_free)).tocsr()
+    for r in range(world):
+        p = P.slab_problem(dom, cells, r, world)
+        m, W = p.mesh, p.space
+        lcp, lrv, lnz = O.assemble_matrix(O.LAPLACE, m.node_coordinates, m.cell_nodes, W.cell_dofs, W.n_free, W.n_dirichlet, tabd)   # ALL local cells
+        lb = O.assemble_vector(O.SOURCE_CONST, m.node_coordinates, m.cell_nodes, W.cell_dofs, W.n_free, W.n_dirichlet, tabd, f_const=[1.0])
+        A_loc = sp.csc_matrix((lnz, lrv.astype(np.int64) - 1, lcp.astype(np.int64) - 1), shape=(W.n_free, W.n_free)).tocsr()
+        g = p.row_gid - 1
+        own = np.flatnonzero(p.row_owner == p.rank)
+        assert own.size > 0
+        for i in own:
+            lo, hi = A_loc.indptr[i], A_loc.indptr[i + 1]
+            ref = A_glob.getrow(g[i])
+            assert np.array_equal(g[A_loc.indices[lo:hi]], ref.indices)
+            assert A_loc.data[lo:hi].tobytes() == ref.data.tobytes()
+        assert lb[own].tobytes() == bg[g[own]].tobytes()
+
+
 def _gloo_worker(rank, world, port, cells, dom, q):
     try:
         import torch.distributed as dist
