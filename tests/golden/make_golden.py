@@ -68,7 +68,53 @@ def build_linear_problem():
     return out
 
 
+def build_f4():
+    """SURVEY §8 f4 fixtures (golden/extra/, own schema): Stokes Q2 x Q1 on a warped 3 x 2 quad mesh (monolithic matrix with all
+    four field blocks) and the interior-penalty operator of docs/src/src_jl/example_hello_world_dg.jl on a warped 3 x 3 mesh
+    (discontinuous Q1: Laplace + skeleton + Nitsche triplets compressed once, Nitsche right-hand side for g = x + 2y)."""
+    import importlib
+    import gtk_b200
+    import test_multifield as T
+    H = gtk_b200.hostprep
+    MF = importlib.import_module("galerkintoolkit_jl_b200.multifield")
+    out = {}
+    mesh, spaces = T._stokes_spaces((3, 2))
+    bp = MF.volume_problem(spaces, 4)
+    cp, rv, nz = T._oracle_matrix(bp, spaces, mesh, "stokes")
+    out["f4_stokes_q2q1_2d_3x2"] = dict(xyz=mesh.node_coordinates, cell_nodes=mesh.cell_nodes, super_dofs=bp.super_dofs, n_free=bp.n_free,
+                                        n_dirichlet=bp.n_dirichlet, colptr=cp, rowval=rv, nzval=nz)
+    mesh = H.cartesian_mesh((0, 1, 0, 1), (3, 3))
+    T._warp(mesh)
+    V = H.discontinuous_lagrange_space(mesh, 1)
+    gamma = 0.2
+    coo = [T._volume_coo(O.LAPLACE, mesh, V, 2)]
+    bs = MF.skeleton_problem([V], 2, gradients=True)
+    sides = [[(int(bs.side_cells[i, a]), int(bs.face_var[i, a])) for a in range(2)] for i in range(bs.face_nodes.shape[0])]
+    full = lambda p: sum(T._ip(p, su, sv, (gamma, -0.5, -0.5)) for su in (1, 2) for sv in (1, 2))
+    coo.append(O.assemble_matrix_multifield(2, mesh.node_coordinates, bs.face_nodes, dict(w=bs.w, dM=bs.dM), sides, T._oracle_fields(bs, [V], True), full,
+                                            skeleton_geometry=(bs.cell_nodes, bs.dM_cell, bs.ref_normals), return_coo=True))
+    bb = MF.boundary_problem([V], None, 2)
+    bsides = T._boundary_oracle_sides(bb)
+    geo = (bb.cell_nodes, bb.dM_cell, bb.ref_normals)
+    nit = lambda p: (gamma / p.h) * p.v(0) * p.u(0) - O.frobenius(p.v(0) * p.n(1), p.grad_u(0)) - O.frobenius(p.n(1), p.grad_v(0)) * p.u(0)
+    coo.append(O.assemble_matrix_multifield(2, mesh.node_coordinates, bb.face_nodes, dict(w=bb.w, dM=bb.dM), bsides, T._oracle_fields(bb, [V], True), nit,
+                                            skeleton_geometry=geo, return_coo=True))
+    cp, rv, nz = O.assemble_matrix_sum(coo, V.n_free, V.n_free)
+    xq = MF.face_point_coordinates(bb)
+    g = xq[..., 0] + 2.0 * xq[..., 1]
+    rhs = lambda p: (gamma / p.h) * p.v(0) * p.g - O.frobenius(p.n(1), p.grad_v(0)) * p.g
+    b = O.assemble_vector_multifield(2, mesh.node_coordinates, bb.face_nodes, dict(w=bb.w, dM=bb.dM), bsides, T._oracle_fields(bb, [V], True), rhs,
+                                     skeleton_geometry=geo, point_data=g)
+    out["f4_interior_penalty_dg_2d_3x3"] = dict(xyz=mesh.node_coordinates, cell_nodes=mesh.cell_nodes, cell_dofs=V.cell_dofs, gamma=gamma,
+                                                colptr=cp, rowval=rv, nzval=nz, b=b)
+    return out
+
+
 if __name__ == "__main__":
+    os.makedirs(os.path.join(HERE, "extra"), exist_ok=True)
+    for name, data in build_f4().items():
+        np.savez_compressed(os.path.join(HERE, "extra", name + ".npz"), **data)
+        print("wrote extra/" + name)
     for name in CASES:
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **build(name))
         print("wrote", name)
