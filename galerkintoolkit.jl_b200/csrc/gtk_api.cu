@@ -80,7 +80,7 @@ int32_t upload(gtk_ctx* ctx, T** dst, size_t* old_n, const T* src, size_t n) {
 
 extern "C" {
 
-int32_t gtk_version(void) { return 103; }
+int32_t gtk_version(void) { return 200; }   // round 2: gtk_part / gtk_block / gtk_vblock layouts, block, sum and field entry points
 
 int32_t gtk_create(int32_t device, gtk_ctx** out) {
   if (!out) return GTK_ERR_INVALID;
