@@ -1082,21 +1082,23 @@ def monolithic_offsets(lengths):
     return out
 
 
-def skeleton_faces(cell_nodes, nnodes, D):
-    """GT.skeleton(mesh) on cartesian_mesh output (quads / hexahedra): the (D-1)-faces with two cells around, in face-id
-    order of the complexified mesh (domain.jl: skeleton = faces with 2 cells in face_incidence(topo, D-1, D)); cells around
-    in increasing cell id (face_incidence(topo, d, D) is the transpose of the cell -> face incidence, filled looping over
-    the cells in order, topology.jl:313-334).  Per face: its nodes in the face's own vertex order, the two (cell, local
-    face id, permutation id) triples (face_permutation_ids, topology.jl:593-634)."""
-    fc = face_complex(cell_nodes, nnodes, D)
+def skeleton_faces(cell_nodes, nnodes, D, fc=None, simplex=False):
+    """GT.skeleton(mesh) on cartesian_mesh output (quads / hexahedra; simplexified meshes with `fc` = the face complex of
+    simplex_face_complex and simplex=True): the (D-1)-faces with two cells around, in face-id order of the complexified mesh
+    (domain.jl: skeleton = faces with 2 cells in face_incidence(topo, D-1, D)); cells around in increasing cell id
+    (face_incidence(topo, d, D) is the transpose of the cell -> face incidence, filled looping over the cells in order,
+    topology.jl:313-334).  Per face: its nodes in the face's own vertex order, the two (cell, local face id, permutation id)
+    triples (face_permutation_ids, topology.jl:593-634)."""
+    if fc is None:
+        fc = face_complex(cell_nodes, nnodes, D)
     d = D - 1
     vertex_node = {v: n + 1 for n, v in enumerate(fc["node_vertex"])}
     around = {}
     for cell, row in enumerate(fc["cell_faces"][d]):
         for lface, face in enumerate(row):
             around.setdefault(face, []).append((cell + 1, lface + 1))
-    vperms = _vertex_permutations(d)
-    lfaces = _cube_lfaces(D, d)
+    vperms = _simplex_vertex_permutations(d) if simplex else _vertex_permutations(d)
+    lfaces = _simplex_lfaces(D, d) if simplex else _cube_lfaces(D, d)
     out = []
     for face in range(1, len(fc["vertices"][d]) + 1):
         ar = around.get(face, [])
@@ -1117,17 +1119,22 @@ def skeleton_faces(cell_nodes, nnodes, D):
     return out
 
 
-def reference_map_tables(D, point_to_x):
+def reference_map_tables(D, point_to_x, simplex=False):
     """accessors.jl:1914-1943 reference_map(refdface, refDface) evaluated at the face quadrature points, for the unit
-    D-cube and its (D-1)-faces: per local face, per node permutation `ids` of the face, φ(x) = Σ_dof coeff[dof]·M_dof(x)
-    with coeff[ids] = node_coordinates(boundary)[lface_nodes]  ->  tables[ldface][perm] = [n_points][D]."""
+    D-cube (or D-simplex) and its (D-1)-faces: per local face, per node permutation `ids` of the face,
+    φ(x) = Σ_dof coeff[dof]·M_dof(x) with coeff[ids] = node_coordinates(boundary)[lface_nodes]  ->  tables[ldface][perm] = [n_points][D]."""
     d = D - 1
-    Xref = [[float((v >> m) & 1) for m in range(D)] for v in range(2 ** D)]       # reference cube nodes, first index fastest
-    M, _ = tabulate(d, 1, "Q", point_to_x)                                       # shape functions of the reference face
+    if simplex:
+        Xref = [[0.0] * D] + [[1.0 if m == k else 0.0 for m in range(D)] for k in range(D)]      # v1 = 0, v_{k+2} = e_k
+        lfaces, vperms = _simplex_lfaces(D, d), _simplex_vertex_permutations(d)
+    else:
+        Xref = [[float((v >> m) & 1) for m in range(D)] for v in range(2 ** D)]                 # first index fastest
+        lfaces, vperms = _cube_lfaces(D, d), _vertex_permutations(d)
+    M, _ = tabulate(d, 1, "P" if simplex else "Q", point_to_x)                                   # shape functions of the reference face
     out = []
-    for lnodes in _cube_lfaces(D, d):
+    for lnodes in lfaces:
         per_perm = []
-        for ids in _vertex_permutations(d):
+        for ids in vperms:
             coeff = [None] * len(lnodes)
             for k, node in enumerate(lnodes):
                 coeff[ids[k] - 1] = Xref[node - 1]

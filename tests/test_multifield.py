@@ -692,3 +692,55 @@ def test_oracle_reproduces_the_reference_interior_penalty_example():
     assert np.abs(err).max() < 1e-9
     # el2 = sqrt(∫ (uh - g)^2): with the nodal error e the integrand is the P/Q1 interpolant of e — bound it by max|e| sqrt(|Ω|)
     assert np.abs(err).max() * 1.0 < 1e-9
+
+
+# ---- simplexified meshes: skeleton inputs and face terms on triangles / tetrahedra -------------------------------------------
+@pytest.mark.parametrize("cells", [(3, 2), (2, 2, 2)])
+def test_skeleton_inputs_on_simplices_equal_the_literal_restatement(cells):
+    D = len(cells)
+    dom = tuple([0, 1] * D)
+    mesh = H.cartesian_mesh(dom, cells, simplexify=True)
+    V = H.lagrange_space(mesh, 2, [1])
+    bp = MF.skeleton_problem([V], 4, gradients=True)
+    coords, cn, fc = O.simplex_face_complex(dom, cells)
+    sf = O.skeleton_faces(cn, coords.shape[0], D, fc=fc, simplex=True)
+    assert len(sf) == bp.face_nodes.shape[0] > 0
+    q = H.quadrature(D - 1, True, 4)
+    tabs = O.reference_map_tables(D, q.coordinates, simplex=True)
+    refn = {2: [(0.0, -1.0), (-1.0, 0.0), (2 ** -0.5, 2 ** -0.5)],
+            3: [(0.0, 0.0, -1.0), (0.0, -1.0, 0.0), (-1.0, 0.0, 0.0), (3 ** -0.5, 3 ** -0.5, 3 ** -0.5)]}[D]      # domain.jl:428, 460
+    for i, f in enumerate(sf):
+        assert list(bp.face_nodes[i]) == f["nodes"] and [s[0] for s in f["sides"]] == list(bp.side_cells[i])
+        for a, (cell, lface, perm) in enumerate(f["sides"]):
+            var = bp.face_var[i, a]
+            No, _ = O.tabulate(D, 2, "P", np.array(tabs[lface - 1][perm - 1]))
+            assert np.abs(No - bp.parts[a]["N"][var]).max() < 1e-13
+            assert np.allclose(bp.ref_normals[var], refn[lface - 1], atol=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,order", [((3, 3), 1), ((2, 2, 2), 2)])
+def test_gpu_face_terms_on_simplices_parity(cells, order):
+    """jump products and interior-penalty blocks on triangles / tetrahedra (P1 / P2): same kernels, simplex tables"""
+    D = len(cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells, simplexify=True)
+    _warp(mesh)
+    V = H.lagrange_space(mesh, order, [1])
+    bp = MF.skeleton_problem([V], 2 * order, gradients=True)
+    eng = _engine(bp)
+    eng.set_skeleton_cells(bp.cell_nodes, bp.side_cells, bp.dM_cell, bp.ref_normals)
+    eng.matrix_symbolic()
+    gcp, grv = eng.matrix_pattern()
+    ca, cb = (2.0, -0.5, 0.25), (1.0, 0.3, -0.5)
+    ref = _skeleton_oracle(bp, V, mesh, lambda p: 1.0 * _ip(p, 1, 1, ca) + 0.7 * _ip(p, 2, 1, cb))
+    assert np.array_equal(ref[0], gcp) and np.array_equal(ref[1], grv)
+    got = eng.matrix_numeric_blocks([(0, 0, E.BLOCK_IP, 1.0, ca), (1, 0, E.BLOCK_IP, 0.7, cb)])
+    assert_values_close(got, ref[2])
+    full = eng.matrix_numeric_blocks([(pu, pv, E.BLOCK_IP, 1.0, (1.0, -0.5, -0.5)) for pu in range(2) for pv in range(2)])
+    assert np.abs(full).max() < 1e-12 * np.abs(got).max()             # continuous space: the four blocks cancel
+    one = eng.matrix_numeric_blocks([(0, 1, E.BLOCK_MASS, 1.0)])      # ∫_Λ u[1] v[2]
+    sides = [[(int(bp.side_cells[i, a]), int(bp.face_var[i, a])) for a in range(2)] for i in range(bp.face_nodes.shape[0])]
+    r1 = O.assemble_matrix_multifield(D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), sides,
+                                      _oracle_fields(bp, [V], False), lambda p: p.u(0, 1) * p.v(0, 2))
+    assert_values_close(one, r1[2])
+    eng.close()
