@@ -681,9 +681,9 @@ def _block_problem(space, meas: "Measure"):
         return _mf.skeleton_problem(data, meas.degree, gradients=True)
     if meas.domain.kind == "interior":
         return _mf.volume_problem(data, meas.degree)
-    if meas.domain.kind == "boundary" and not data[0].mesh.simplex:
+    if meas.domain.kind == "boundary":
         return _mf.boundary_problem(data, meas.domain.sides, meas.degree)
-    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "block kernels run on interior, skeleton and (cube-mesh) boundary measures")
+    raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "block kernels run on interior, skeleton and boundary measures")
 
 
 def _setup_block_engine(space, meas: "Measure", engine: Optional[_eng.Engine] = None, bp=None):

@@ -164,7 +164,24 @@ def boundary_problem(spaces: Sequence[_hp.LagrangeSpace], sides, degree: int) ->
     kind = spaces[0].kind
     fn, fc, _ = _hp.boundary_faces(mesh, sides)
     fn = np.ascontiguousarray(fn, dtype=np.int32)
-    sc = (np.asarray(fc, dtype=np.int64) + 1)[:, None]                          # the one cell around, 1-based
+    if mesh.simplex:
+        # boundary_faces names the parent HEXAHEDRON; the simplex around a boundary face is the one cell of the face complex that
+        # holds it (the pre-existing boundary faces keep the ids 1..n_parent in the order boundary_faces lists them)
+        from . import refnumbering as _rn
+        cplx = _rn.face_complex(mesh)
+        cf = cplx["cell_faces"][D - 1]
+        n_parent = cplx["n_parent"][D - 1]
+        owner = np.zeros(n_parent + 1, dtype=np.int64)
+        cell_of = np.repeat(np.arange(1, cf.shape[0] + 1), cf.shape[1])
+        is_b = cf.reshape(-1) <= n_parent
+        owner[cf.reshape(-1)[is_b]] = cell_of[is_b]
+        all_nodes, all_group, _ = _rn.boundary_face_nodes(mesh, D - 1)
+        keep = np.ones(all_group.shape[0], dtype=bool) if sides is None else np.isin(all_group, np.asarray(list(sides), dtype=np.int64))
+        sc = owner[1:][keep][:, None]
+        if (sc == 0).any() or sc.shape[0] != fn.shape[0]:
+            raise AssertionError("a boundary face has no cell around in the face complex")
+    else:
+        sc = (np.asarray(fc, dtype=np.int64) + 1)[:, None]                      # the one cell around, 1-based
     cn = mesh.cell_nodes.astype(np.int64)
     eq = cn[sc[:, 0] - 1][:, None, :] == fn.astype(np.int64)[:, :, None]
     if not eq.any(axis=2).all():

@@ -580,12 +580,33 @@ def test_discontinuous_space_numbering_and_boundary_inputs():
         assert abs(np.linalg.norm(n) - 1) < 1e-14 and np.dot(n, fc - centre) > 0.0      # outward
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("cells", [(3, 3), (2, 2, 2)])
-def test_gpu_nitsche_terms_parity(cells):
-    """(γ/h) v u - v n⋅∇u - n⋅∇v u on boundary faces and the right-hand side (γ/h) v g - n⋅∇v g, on a discontinuous space"""
+@pytest.mark.parametrize("cells", [(3, 2), (2, 2, 2)])
+def test_boundary_inputs_on_simplices(cells):
+    """the simplex around a boundary face comes from the face complex (boundary_faces names the parent hexahedron); its unit
+    normal points out of the domain"""
     D = len(cells)
-    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells, simplexify=True)
+    _warp(mesh)
+    V = H.discontinuous_lagrange_space(mesh, 1)
+    bp = MF.boundary_problem([V], None, 2)
+    X = mesh.node_coordinates
+    centre = X.mean(axis=0)
+    assert bp.face_nodes.shape[0] == H.boundary_faces(mesh, None)[0].shape[0]
+    for i in range(bp.face_nodes.shape[0]):
+        cell, var = int(bp.side_cells[i, 0]), int(bp.face_var[i, 0])
+        assert set(bp.face_nodes[i]) <= set(mesh.cell_nodes[cell - 1])
+        J = O.point_geometry(X, mesh.cell_nodes[cell - 1][None, :], bp.dM_cell[var][0])[0]
+        n = O.map_unit_normal(J, bp.ref_normals[var])
+        assert abs(np.linalg.norm(n) - 1) < 1e-14 and np.dot(n, X[bp.face_nodes[i] - 1].mean(axis=0) - centre) > 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,simplexify", [((3, 3), False), ((2, 2, 2), False), ((3, 2), True), ((2, 2, 2), True)])
+def test_gpu_nitsche_terms_parity(cells, simplexify):
+    """(γ/h) v u - v n⋅∇u - n⋅∇v u on boundary faces and the right-hand side (γ/h) v g - n⋅∇v g, on a discontinuous space
+    (quadrilaterals / hexahedra and triangles / tetrahedra)"""
+    D = len(cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells, simplexify=simplexify)
     _warp(mesh)
     V = H.discontinuous_lagrange_space(mesh, 1)
     sides_sel = [1, 4] if D == 2 else [2, 5]
