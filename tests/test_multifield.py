@@ -765,3 +765,41 @@ def test_gpu_face_terms_on_simplices_parity(cells, order):
                                       _oracle_fields(bp, [V], False), lambda p: p.u(0, 1) * p.v(0, 2))
     assert_values_close(one, r1[2])
     eng.close()
+
+
+def test_recognition_of_the_interior_penalty_example_without_a_gpu():
+    """docs/src/src_jl/example_hello_world_dg.jl: what the three integrals of `a` and the Nitsche integral of `l` are recognised as"""
+    mesh = GT.cartesian_mesh((0, 1, 0, 1, 0, 1), (2, 2, 2))
+    n = GT.unit_normal(mesh, 2)
+    Om, Gd, Lam = GT.interior(mesh), GT.boundary(mesh), GT.skeleton(mesh)
+    h_L, h_G = GT.face_diameter_field(Lam), GT.face_diameter_field(Gd)
+    g = GT.AnalyticalField(lambda x: x[0] + x[1] + x[2], Om)
+    mean = lambda fn, u, x: 0.5 * (fn(u[1], x) + fn(u[2], x))
+    jump = lambda u, n_, x: u[2](x) * n_[2](x) + u[1](x) * n_[1](x)
+    gamma = GT.uniform_quantity(0.2)
+    V = GT.lagrange_space(Om, 1, continuous=False)
+    assert V.num_free_dofs() == 64 and V.num_dirichlet_dofs() == 0
+    dL, dG = GT.measure(Lam, 2), GT.measure(Gd, 2)
+    grad, dot = GT.grad, GT.dot
+    u, v = GT._form_arguments(V, 2), GT._form_arguments(V, 1)
+    ip = GT.integrate(lambda x: dot((gamma / h_L(x)) * jump(v, n, x), jump(u, n, x)) - dot(jump(v, n, x), mean(grad, u, x))
+                      - dot(mean(grad, v, x), jump(u, n, x)), dL).contributions[0][0]
+    bs = GT._block_problem(V, dL)
+    blocks = sorted(GT.recognise_blocks(ip, bs, "skeleton"))
+    assert [b[:3] for b in blocks] == [(pu, pv, E.BLOCK_IP) for pu in range(2) for pv in range(2)]
+    assert all(b[4] == (0.2, -0.5, -0.5) for b in blocks)
+    nit = GT.integrate(lambda x: (gamma / h_G(x)) * v(x) * u(x) - dot(v(x) * n(x), grad(u, x)) - dot(n(x), grad(v, x)) * u(x), dG).contributions[0][0]
+    assert GT._is_blocks_case(V, dG, nit)
+    bb = GT._block_problem(V, dG)
+    assert GT.recognise_blocks(nit, bb, "boundary") == [(0, 0, E.BLOCK_IP, 1.0, (0.2, -1.0, -1.0))]
+    rhs = GT.integrate(lambda x: (gamma / h_G(x)) * v(x) * g(x) - dot(n(x), grad(v, x)) * g(x), dG).contributions[0][0]
+    vb, gq = GT.recognise_vblocks(rhs, bb, "boundary", V)
+    assert vb == [(0, 1.0, (0.0, 0.2, -1.0))] and gq.shape == (bb.face_nodes.shape[0], bb.w.size)
+    assert np.allclose(gq, MF.face_point_coordinates(bb).sum(axis=2))
+    # a continuous space with a plain Robin term keeps the trace-space path; with normals it goes to the block kernels
+    W = GT.lagrange_space(Om, 1)
+    w2, w1 = GT._form_arguments(W, 2), GT._form_arguments(W, 1)
+    robin = GT.integrate(lambda x: w2(x) * w1(x), dG).contributions[0][0]
+    assert not GT._is_blocks_case(W, dG, robin) and GT._is_blocks_case(W, dG, nit)
+    with pytest.raises(GT.UnsupportedFormError):          # a gradient-gradient product on faces is not a recognised face term
+        GT.recognise_blocks(GT.integrate(lambda x: dot(grad(u, x), grad(v, x)), dG).contributions[0][0], bb, "boundary")
