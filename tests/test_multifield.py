@@ -803,3 +803,31 @@ def test_recognition_of_the_interior_penalty_example_without_a_gpu():
     assert not GT._is_blocks_case(W, dG, robin) and GT._is_blocks_case(W, dG, nit)
     with pytest.raises(GT.UnsupportedFormError):          # a gradient-gradient product on faces is not a recognised face term
         GT.recognise_blocks(GT.integrate(lambda x: dot(grad(u, x), grad(v, x)), dG).contributions[0][0], bb, "boundary")
+
+
+def test_reference_integration_tests_with_unit_normals():
+    """test/integration_tests.jl:86-106, 158-160 on the ORACLE's face machinery (domain (0,2)^2, 8 x 8 cells, degree 2):
+    `∫(x->norm(n(x)),dΓ) ≈ 4` over the sides "1-face-2", "1-face-4" and `∫(x->norm(n[1](x)+n[2](x)),dΛ) + 1 ≈ 1`"""
+    mesh = H.cartesian_mesh((0, 2, 0, 2), (8, 8))
+    V = H.lagrange_space(mesh, 1, None)
+    X = mesh.node_coordinates
+
+    def integrate(bp, f):
+        total = 0.0
+        for i in range(bp.face_nodes.shape[0]):
+            for q in range(bp.w.size):
+                Jf = O.point_geometry(X, bp.face_nodes[i:i + 1], bp.dM[q])
+                dV = float(O.change_of_measure(Jf)[0] * bp.w[q])                      # weight(::MeshFace), accessors.jl:1000-1007
+                normals = []
+                for a in range(bp.n_sides):
+                    cell, var = int(bp.side_cells[i, a]), int(bp.face_var[i, a])
+                    Jc = O.point_geometry(X, mesh.cell_nodes[cell - 1][None, :], bp.dM_cell[var][q])[0]
+                    normals.append(O.map_unit_normal(Jc, bp.ref_normals[var]))
+                total += f(normals) * dV
+        return total
+
+    bb = MF.boundary_problem([V], [2, 4], 2)
+    assert integrate(bb, lambda n: np.linalg.norm(n[0])) == pytest.approx(4.0, rel=1e-13)
+    bs = MF.skeleton_problem([V], 2, gradients=True)
+    assert integrate(bs, lambda n: np.linalg.norm(n[0] + n[1])) + 1.0 == pytest.approx(1.0, abs=1e-13)
+    assert integrate(bs, lambda n: 1.0) == pytest.approx(2 * 7 * 2.0, rel=1e-13)       # total length of the interior faces
