@@ -186,12 +186,12 @@ __global__ void __launch_bounds__(128) k_elem_blocks(BlockArgs a) {
       const double* gv = G + (size_t)cl * nq * gstride + (size_t)(a.p_goff[pv] + ca) * D;
       if (form == GTK_BLOCK_MASS) {
         for (int q = 0; q < nq; ++q) acc += (alpha * (Nu[q * nlu] * Nv[q * nlv])) * dv[q];
-      } else if (form == GTK_BLOCK_IP) {
+      } else if (form == GTK_BLOCK_IP || form == GTK_BLOCK_IP_NOH) {
         // interior-penalty terms on a skeleton face, u on side su, v on side sv (test/assembly_tests.jl:329-340):
         //   c0 ((1/h) v n_sv)⋅(u n_su) + c1 (v n_sv)⋅∇u + c2 ∇v⋅(u n_su)
         if constexpr (D != d) {
           const int su = a.p_side[pu], sv = a.p_side[pv];
-          const double c0 = a.b_c[pu][pv][0] / hF[cl], c1 = a.b_c[pu][pv][1], c2 = a.b_c[pu][pv][2];
+          const double c0 = form == GTK_BLOCK_IP ? a.b_c[pu][pv][0] / hF[cl] : a.b_c[pu][pv][0], c1 = a.b_c[pu][pv][1], c2 = a.b_c[pu][pv][2];
           for (int q = 0; q < nq; ++q, gu += gstride, gv += gstride) {
             const double* nu = Nrm + ((size_t)(cl * nq + q) * a.n_sides + su) * D;
             const double* nv = Nrm + ((size_t)(cl * nq + q) * a.n_sides + sv) * D;
@@ -512,7 +512,7 @@ extern "C" int32_t gtk_matrix_numeric_blocks_device(gtk_ctx* ctx, int32_t n_bloc
     const bool grad = k.form == GTK_BLOCK_LAPLACE || k.form == GTK_BLOCK_VALU_DIVV || k.form == GTK_BLOCK_DIVU_VALV;
     bool ok = false;
     if (k.form == GTK_BLOCK_ZERO) ok = true;
-    else if (k.form == GTK_BLOCK_IP) {
+    else if (k.form == GTK_BLOCK_IP || k.form == GTK_BLOCK_IP_NOH) {
       if (!ps->skel || ctx->dman == ctx->D)
         GTK_FAIL(GTK_ERR_UNSUPPORTED_FORM, "interior-penalty blocks need a skeleton measure and gtk_set_skeleton_cells; no CPU fallback");
       ok = cu == 1 && cv == 1 && ps->has_dN[k.part_u] && ps->has_dN[k.part_v];
@@ -531,11 +531,11 @@ extern "C" int32_t gtk_matrix_numeric_blocks_device(gtk_ctx* ctx, int32_t n_bloc
     a.b_form[k.part_u][k.part_v] = k.form;
     a.b_alpha[k.part_u][k.part_v] = k.alpha;
     for (int c = 0; c < 3; ++c) a.b_c[k.part_u][k.part_v][c] = k.c[c];
-    if (grad || k.form == GTK_BLOCK_IP) a.need_grad = 1;
+    if (grad || k.form == GTK_BLOCK_IP || k.form == GTK_BLOCK_IP_NOH) a.need_grad = 1;
   }
   {
     bool any_ip = false;
-    for (int b = 0; b < n_blocks; ++b) any_ip |= blocks[b].form == GTK_BLOCK_IP;
+    for (int b = 0; b < n_blocks; ++b) any_ip |= blocks[b].form == GTK_BLOCK_IP || blocks[b].form == GTK_BLOCK_IP_NOH;
     if (!any_ip) a.skel = 0;
   }
   ctx->launches_last = 0;

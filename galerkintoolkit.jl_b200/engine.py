@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "gtk_matrix_sum_symbolic", "gtk_matrix_sum_numeric", "gtk_matrix_sum_numeric_device", "gtk_set_skeleton_cells",
     "gtk_matrix_colptr_at", "gtk_vector_assemble_blocks_data", "gtk_vector_assemble_blocks_data_device",
 ]
-BLOCK_ZERO, BLOCK_MASS, BLOCK_LAPLACE, BLOCK_VALU_DIVV, BLOCK_DIVU_VALV, BLOCK_IP = 0, 1, 2, 3, 4, 5
+BLOCK_ZERO, BLOCK_MASS, BLOCK_LAPLACE, BLOCK_VALU_DIVV, BLOCK_DIVU_VALV, BLOCK_IP, BLOCK_IP_NOH = 0, 1, 2, 3, 4, 5, 6
 MAX_PARTS = 8
 
 

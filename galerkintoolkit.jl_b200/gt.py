@@ -767,10 +767,17 @@ def recognise_blocks(term, bp, skeleton_measure):
             out[key] = (form, out[key][1] + coef)
         else:
             out[key] = (form, coef)
-    if set(ip) & set(out):
-        raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "two different terms in one block are not recognised; no CPU fallback")
+    merged = []
+    for key in sorted(set(ip) & set(out)):
+        # v u next to normal terms in one block (Nitsche without the 1/h scaling, test/issue_224.jl:73-76): on a boundary face
+        # v u = (v n)⋅(u n), so it is the c0 term of the interior-penalty form WITHOUT the division by h
+        form, alpha = out[key]
+        if form != _eng.BLOCK_MASS or ip[key][0] != 0.0 or _kind(skeleton_measure) != "boundary":
+            raise UnsupportedFormError(_eng.GTK_ERR_UNSUPPORTED_FORM, "two different terms in one block are not recognised; no CPU fallback")
+        merged.append((key[0], key[1], _eng.BLOCK_IP_NOH, 1.0, (alpha, ip[key][1], ip[key][2])))
+        del out[key], ip[key]
     return [(pu, pv, form, alpha) for (pu, pv), (form, alpha) in out.items()] + \
-           [(pu, pv, _eng.BLOCK_IP, 1.0, tuple(c)) for (pu, pv), c in ip.items()]
+           [(pu, pv, _eng.BLOCK_IP, 1.0, tuple(c)) for (pu, pv), c in ip.items()] + merged
 
 
 def recognise_vblocks(term, bp, skeleton_measure, space):

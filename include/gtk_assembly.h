@@ -255,11 +255,13 @@ enum {
   GTK_BLOCK_LAPLACE = 2,    /* ∇(v,x) ⋅ ∇(u,x)  (component-wise: the Frobenius product of the Jacobians for vector parts)   */
   GTK_BLOCK_VALU_DIVV = 3,  /* u(x) * div(v,x): u a scalar part (pressure), v a vector part with n_comp == D                */
   GTK_BLOCK_DIVU_VALV = 4,  /* v(x) * div(u,x): v a scalar part, u a vector part                                           */
-  GTK_BLOCK_IP = 5          /* skeleton faces, scalar parts, u on the cell around s_u, v on s_v (needs gtk_set_skeleton_cells):
+  GTK_BLOCK_IP = 5,         /* skeleton faces, scalar parts, u on the cell around s_u, v on s_v (needs gtk_set_skeleton_cells):
                                c[0] ((1/h) v n_sv)⋅(u n_su) + c[1] (v n_sv)⋅∇u + c[2] ∇v⋅(u n_su), n = unit normals of the two cells
                                (accessors.jl:1009-1035), h = diameter of the face (field.jl:488-492, accessors.jl:907-921): the
                                interior-penalty terms (γ/h) jump(v,n)⋅jump(u,n) - jump(v,n)⋅mean(∇u) - mean(∇v)⋅jump(u,n) of
                                test/assembly_tests.jl:329-340 are c = (γ, -1/2, -1/2) on all four (side, side) blocks            */
+  GTK_BLOCK_IP_NOH = 6      /* the same with c[0] NOT divided by h: c[0] (v n_sv)⋅(u n_su) + c[1] (v n_sv)⋅∇u + c[2] ∇v⋅(u n_su) — on a boundary
+                               face (n⋅n = 1) the Nitsche terms v u - v n⋅∇u - n⋅∇v u of test/issue_224.jl:73-76 are c = (1, -1, -1)      */
 };
 typedef struct gtk_block { int32_t part_u, part_v, form; double alpha; double c[3]; } gtk_block;
 /* Cells around the faces of a skeleton measure, for blocks with gradients / normals there (call after gtk_set_parts):

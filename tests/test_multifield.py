@@ -831,3 +831,88 @@ def test_reference_integration_tests_with_unit_normals():
     bs = MF.skeleton_problem([V], 2, gradients=True)
     assert integrate(bs, lambda n: np.linalg.norm(n[0] + n[1])) + 1.0 == pytest.approx(1.0, abs=1e-13)
     assert integrate(bs, lambda n: 1.0) == pytest.approx(2 * 7 * 2.0, rel=1e-13)       # total length of the interior faces
+
+
+# ---- Nitsche terms without the 1/h scaling (test/issue_224.jl) -------------------------------------------------------------------
+def _issue_224_forms(mesh, V):
+    Om, Gam = GT.interior(mesh), GT.boundary(mesh)
+    dO, dG = GT.measure(Om, 2), GT.measure(Gam, 2)
+    n = GT.unit_normal(mesh, mesh.D - 1)
+    g = GT.AnalyticalField(lambda x: sum(x[k] for k in range(mesh.D)), Om)
+    grad, dot = GT.grad, GT.dot
+    a = lambda u, v: (GT.integrate(lambda x: v(x) * u(x) - dot(v(x) * n(x), grad(u, x)) - dot(n(x), grad(v, x)) * u(x), dG)
+                      + GT.integrate(lambda x: dot(grad(u, x), grad(v, x)), dO))
+    l = lambda v: (GT.integrate(lambda x: v(x) * g(x) - dot(n(x), grad(v, x)) * g(x), dG) + GT.integrate(lambda x: v(x) * 0, dO))
+    return a, l, g, dO, dG
+
+
+def test_recognition_of_nitsche_terms_without_the_penalty_scaling():
+    mesh = GT.cartesian_mesh((0, 1, 0, 1, 0, 1), (2, 2, 2), simplexify=True)
+    V = GT.lagrange_space(GT.interior(mesh), 1)
+    a, l, g, dO, dG = _issue_224_forms(mesh, V)
+    term = a(GT._form_arguments(V, 2), GT._form_arguments(V, 1)).contributions[0][0]
+    assert GT._is_blocks_case(V, dG, term)
+    bb = GT._block_problem(V, dG)
+    assert GT.recognise_blocks(term, bb, "boundary") == [(0, 0, E.BLOCK_IP_NOH, 1.0, (1.0, -1.0, -1.0))]
+    lt = l(GT._form_arguments(V, 1)).contributions[0][0]
+    vb, gq = GT.recognise_vblocks(lt, bb, "boundary", V)
+    assert vb == [(0, 1.0, (1.0, 0.0, -1.0))] and gq.shape[0] == bb.face_nodes.shape[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,simplexify", [((3, 3), False), ((2, 2, 2), True)])
+def test_gpu_nitsche_without_scaling_parity(cells, simplexify):
+    D = len(cells)
+    mesh = H.cartesian_mesh(tuple([0, 1] * D), cells, simplexify=simplexify)
+    _warp(mesh)
+    V = H.lagrange_space(mesh, 1, None)
+    bp = MF.boundary_problem([V], None, 2)
+    eng = _engine(bp)
+    eng.set_skeleton_cells(bp.cell_nodes, bp.side_cells, bp.dM_cell, bp.ref_normals)
+    mat = lambda p: p.v(0) * p.u(0) - O.frobenius(p.v(0) * p.n(1), p.grad_u(0)) - O.frobenius(p.n(1), p.grad_v(0)) * p.u(0)
+    ref = O.assemble_matrix_multifield(D, mesh.node_coordinates, bp.face_nodes, dict(w=bp.w, dM=bp.dM), _boundary_oracle_sides(bp),
+                                       _oracle_fields(bp, [V], True), mat, skeleton_geometry=(bp.cell_nodes, bp.dM_cell, bp.ref_normals))
+    eng.matrix_symbolic()
+    gcp, grv = eng.matrix_pattern()
+    assert np.array_equal(ref[0], gcp) and np.array_equal(ref[1], grv)
+    assert_values_close(eng.matrix_numeric_blocks([(0, 0, E.BLOCK_IP_NOH, 1.0, (1.0, -1.0, -1.0))]), ref[2])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reference_issue_224_nitsche_on_tetrahedra():
+    """test/issue_224.jl transcribed (on the simplexified 2 x 2 x 2 mesh instead of its single hand-made tetrahedron): weak Dirichlet
+    conditions through v u - v n⋅∇u - n⋅∇v u on Γ, continuous P1, exact solution sum(x): `@test sqrt(sum(int)) < 1.0e-10`"""
+    import scipy.sparse.linalg as spla
+    mesh = GT.cartesian_mesh((0, 1, 0, 1, 0, 1), (2, 2, 2), simplexify=True)
+    V = GT.lagrange_space(GT.interior(mesh), 1)
+    a, l, g, dO, dG = _issue_224_forms(mesh, V)
+    A = GT.assemble_matrix(a, float, V, V)
+    b = GT.assemble_vector(l, float, V)
+    x = spla.spsolve(A.to_scipy().tocsc(), b)
+    assert np.abs(x - V.data.free_dof_nodes.sum(axis=1)).max() < 1e-10
+    uh = GT.solution_field(V, x)
+    assert np.sqrt(GT.integrate(lambda y: GT.abs2(uh(y) - g(y)), dO).sum()) < 1.0e-10
+
+
+def test_oracle_reproduces_the_reference_issue_224_known_answer():
+    """test/issue_224.jl on the CPU ORACLE (simplexified 2 x 2 x 2 mesh): Nitsche terms without penalty scaling on Γ + Laplace operator,
+    data right-hand side; the discrete solution is sum(x): `@test sqrt(sum(int)) < 1.0e-10`"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (2, 2, 2), simplexify=True)
+    V = H.lagrange_space(mesh, 1, None)
+    bb = MF.boundary_problem([V], None, 2)
+    geo = (bb.cell_nodes, bb.dM_cell, bb.ref_normals)
+    sides, flds = _boundary_oracle_sides(bb), _oracle_fields(bb, [V], True)
+    nit = lambda p: p.v(0) * p.u(0) - O.frobenius(p.v(0) * p.n(1), p.grad_u(0)) - O.frobenius(p.n(1), p.grad_v(0)) * p.u(0)
+    coo = [O.assemble_matrix_multifield(3, mesh.node_coordinates, bb.face_nodes, dict(w=bb.w, dM=bb.dM), sides, flds, nit,
+                                        skeleton_geometry=geo, return_coo=True), _volume_coo(O.LAPLACE, mesh, V, 2)]
+    cp, rv, nz = O.assemble_matrix_sum(coo, V.n_free, V.n_free)
+    gq = MF.face_point_coordinates(bb).sum(axis=2)
+    rhs = lambda p: p.v(0) * p.g - O.frobenius(p.n(1), p.grad_v(0)) * p.g
+    b = O.assemble_vector_multifield(3, mesh.node_coordinates, bb.face_nodes, dict(w=bb.w, dM=bb.dM), sides, flds, rhs,
+                                     skeleton_geometry=geo, point_data=gq)
+    A = sp.csc_matrix((nz, rv.astype(np.int64) - 1, cp.astype(np.int64) - 1), shape=(V.n_free, V.n_free))
+    x = spla.spsolve(A, b)
+    assert np.abs(x - V.free_dof_nodes.sum(axis=1)).max() < 1e-10
