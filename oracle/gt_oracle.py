@@ -8,7 +8,7 @@ The product (``galerkintoolkit.jl_b200``) never does.
 Pinning status: the reference is pure Julia and cannot run in this container
 (no ``julia``, no depot, no network), and its test-suite holds **no golden
 matrices** for assembly.  What it does hold on this path are
-two numeric known answers, and this oracle reproduces both:
+numeric known answers, and this oracle reproduces them:
   * the discrete p-Laplacian L2 norm 0.09133166701839236
     (test/problems_ext_tests.jl:148-172, tolerance 1e-10) —
     tests/test_oracle_invariants.py::test_oracle_reproduces_the_reference_plaplacian_golden;
@@ -16,6 +16,8 @@ two numeric known answers, and this oracle reproduces both:
     (docs/src/src_jl/example_hello_world_dg.jl: discontinuous space, skeleton +
     Nitsche terms, unit normals, face diameters) —
     tests/test_multifield.py::test_oracle_reproduces_the_reference_interior_penalty_example;
+  * test/issue_224.jl's ``@test sqrt(sum(int)) < 1.0e-10`` (Nitsche terms on tetrahedra) —
+    tests/test_multifield.py::test_oracle_reproduces_the_reference_issue_224_known_answer;
 plus the reference's invariants checked in ``tests/test_oracle_invariants.py``:
 sum(M)=|Ω|, sum(b)=∫f (test/problems_tests.jl:53-57), tabulator(nodes)=I
 (test/space_tests.jl:218-220), quadrature weights sum (test/integration_tests.jl:28-34),
