@@ -895,12 +895,14 @@ def test_gpu_reference_issue_224_nitsche_on_tetrahedra():
     assert np.sqrt(GT.integrate(lambda y: GT.abs2(uh(y) - g(y)), dO).sum()) < 1.0e-10
 
 
-def test_oracle_reproduces_the_reference_issue_224_known_answer():
-    """test/issue_224.jl on the CPU ORACLE (simplexified 2 x 2 x 2 mesh): Nitsche terms without penalty scaling on Γ + Laplace operator,
-    data right-hand side; the discrete solution is sum(x): `@test sqrt(sum(int)) < 1.0e-10`"""
+@pytest.mark.parametrize("simplexify", [True, False])
+def test_oracle_reproduces_the_reference_issue_224_known_answer(simplexify):
+    """test/issue_224.jl (tetrahedra) and test/issue_230.jl (hexahedra, there from Gmsh) on the CPU ORACLE (2 x 2 x 2 Cartesian mesh,
+    simplexified or not): Nitsche terms without penalty scaling on Γ + Laplace operator, data right-hand side; the discrete solution
+    is sum(x): `@test sqrt(sum(int)) < 1.0e-10` / `@assert sqrt(sum(int)) < 1.0e-9`"""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
-    mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (2, 2, 2), simplexify=True)
+    mesh = H.cartesian_mesh((0, 1, 0, 1, 0, 1), (2, 2, 2), simplexify=simplexify)
     V = H.lagrange_space(mesh, 1, None)
     bb = MF.boundary_problem([V], None, 2)
     geo = (bb.cell_nodes, bb.dM_cell, bb.ref_normals)
